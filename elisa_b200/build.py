@@ -1,0 +1,57 @@
+"""In-tree build of the CUDA library (sm_100a only).  `python -m elisa_b200.build`."""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'csrc', 'elisa_b200.cu')
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('elisa_b200.cu', 'components.cuh', 'dual.cuh', 'gemm_f64.cuh', 'stats.cuh')]
+DEPS.append(os.path.join(os.path.dirname(HERE), 'include', 'elisa_b200.h'))
+LIB = os.path.join(HERE, 'lib', 'libelisa_b200.so')
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a',
+    '-O3', '-lineinfo', '-std=c++17',
+    '-Xcompiler', '-fPIC', '-shared',
+]
+
+
+def find_nvcc() -> str:
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: elisa_b200 needs the CUDA toolkit to build its sm_100a library')
+    return nvcc
+
+
+def is_fresh() -> bool:
+    if not os.path.exists(LIB):
+        return False
+    t = os.path.getmtime(LIB)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/elisa_b200.cu -> lib/libelisa_b200.so (skipped when up to date)."""
+    if not force and is_fresh():
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [find_nvcc(), *NVCC_FLAGS, '-o', LIB, SRC]
+    if verbose:
+        cmd.insert(1, '-Xptxas')
+        cmd.insert(2, '-v')
+        print(' '.join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed building libelisa_b200.so')
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,1203 @@
+// elisa_b200 -- plan, kernels and C ABI of the B200-native forward-folding likelihood path.
+//
+// Per chunk of parameter vectors and per spectrum the path is four launches:
+//   1. unfold_kernel      component photon-flux integrals + model composition -> U [n, E]
+//                         (and, with gradients, dU/dtheta_j [j, n, E] by forward duals)
+//   2. gemm_f64_kernel<EpilogueStat>   fold U . R with DMMA; the epilogue scales by
+//                         area * exposure, evaluates the fit statistic per channel, reduces
+//                         it over the tile's channels and emits W = d loglike / d(R u)
+//   3. gemm_f64_kernel<EpilogueGrad>   transposed fold W . R^T with DMMA; the epilogue
+//                         contracts G[n, e] with dU/dtheta_j[n, e] over the tile's energies
+//   4. reduce_kernel      fixed-order sum of the per-tile partials -> loglike[n, s], grad[n, s, :]
+// Folded counts, G and the per-channel log-likelihoods never reach HBM.
+//
+// Reference lines restated by each piece are cited where the arithmetic lives
+// (components.cuh, stats.cuh) and in include/elisa_b200.h.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/elisa_b200.h"
+#include "components.cuh"
+#include "dual.cuh"
+#include "gemm_f64.cuh"
+#include "stats.cuh"
+
+namespace elisa {
+
+// ======================================================================================
+// device-side descriptors
+// ======================================================================================
+struct LeafDev {
+    int32_t kind, method, np, pad_;
+    int32_t src[ELISA_MAX_COMP_PARAMS];
+    int32_t pad2_;
+    double cst[ELISA_MAX_COMP_PARAMS];
+    double aux[2];
+};
+
+constexpr int MAX_OPS = 2 * ELISA_MAX_COMPONENTS;
+
+struct ModelDev {
+    int32_t n_leaf, n_ops;
+    int32_t ops[MAX_OPS];
+    uint32_t used_mask;  // theta columns this model depends on
+    int32_t pad_;
+    LeafDev leaf[ELISA_MAX_COMPONENTS];
+};
+
+struct UnfoldArgs {
+    ModelDev model;
+    GridView gv;
+    const double* theta;  // [N, P]
+    int32_t P;
+    int32_t n_valid;   // rows < n_valid are evaluated, rows in [n_valid, n_rows) are zero-filled
+    int32_t n_rows;
+    int32_t n_seg;     // segments the energy axis is split into (one warp per (row, segment))
+    int32_t seg_len;   // bins per segment
+    int32_t ld;        // leading dimension of U / dU rows
+    int32_t e_pad;     // columns [E, e_pad) are zero-filled
+    int32_t clip;      // apply clip(unfold, 1e-300, 1e300) (likelihood.py:204)
+    double* U;         // [n_rows, ld]
+    double* dU;        // [P, n_rows, ld] or nullptr
+    int64_t plane;     // n_rows * ld
+};
+
+// per-channel observed data, padded to C_pad with benign values
+struct ChanArrays {
+    const double* scale;    // area_scale * exposure
+    const double* on;
+    const double* off;
+    const double* sigma;
+    const double* ratio;
+    const double* gof_on;
+    const double* gof_off;
+};
+
+// ======================================================================================
+// 1. unfold: component evaluation + composition
+// ======================================================================================
+template <int PU>
+struct StackT {
+    using type = Dual<PU>;
+};
+template <>
+struct StackT<0> {
+    using type = double;
+};
+
+template <int PU, int NPK>
+__device__ __forceinline__ typename StackT<PU>::type scatter_leaf(const Dual<NPK>& x, const int32_t* src) {
+    Dual<PU> r;
+    r.v = x.v;
+#pragma unroll
+    for (int j = 0; j < PU; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NPK; ++k) s += (src[k] == j) ? x.d[k] : 0.0;
+        r.d[j] = s;
+    }
+    return r;
+}
+
+#define ELISA_FOR_EACH_KIND(X)                                                                                     \
+    X(ELISA_COMP_BAND) X(ELISA_COMP_BANDEP) X(ELISA_COMP_BENTPL) X(ELISA_COMP_BLACKBODY)                           \
+    X(ELISA_COMP_BLACKBODYRAD) X(ELISA_COMP_BROKENPL) X(ELISA_COMP_COMPT) X(ELISA_COMP_CUTOFFPL)                   \
+    X(ELISA_COMP_GAUSS) X(ELISA_COMP_LORENTZ) X(ELISA_COMP_OTTB) X(ELISA_COMP_OTTS) X(ELISA_COMP_PLENFLUX)         \
+    X(ELISA_COMP_PLPHFLUX) X(ELISA_COMP_POWERLAW) X(ELISA_COMP_SMOOTHLYBROKENPL) X(ELISA_COMP_CONSTANT)            \
+    X(ELISA_COMP_EDGE) X(ELISA_COMP_EXPABS) X(ELISA_COMP_EXPFAC) X(ELISA_COMP_GABS) X(ELISA_COMP_HIGHECUT)         \
+    X(ELISA_COMP_PLABS)
+
+constexpr int UNFOLD_WARPS = 4;
+
+template <int PU>
+__global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_constant__ UnfoldArgs a) {
+    using TT = typename StackT<PU>::type;
+    constexpr bool GRAD = PU > 0;
+    __shared__ double s_scratch[UNFOLD_WARPS][ELISA_MAX_COMPONENTS][LEAF_SCRATCH];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wid = (int64_t)blockIdx.x * UNFOLD_WARPS + wib;
+    const int row = (int)(wid / a.n_seg), seg = (int)(wid % a.n_seg);
+    if (row >= a.n_rows) return;
+    const int E = a.gv.E;
+    const int e_lo = seg * a.seg_len;
+    const int e_hi = min(e_lo + a.seg_len, E);
+    const bool last_seg = seg == a.n_seg - 1;
+    double* Urow = a.U + (size_t)row * a.ld;
+
+    if (row >= a.n_valid) {  // padding rows: zeros, so that the fold sees finite operands
+        const int hi = last_seg ? a.e_pad : e_hi;
+        for (int e = e_lo + lane; e < hi; e += 32) {
+            Urow[e] = 0.0;
+            if (GRAD)
+                for (int j = 0; j < a.P; ++j)
+                    if ((a.model.used_mask >> j) & 1u) a.dU[j * a.plane + (size_t)row * a.ld + e] = 0.0;
+        }
+        return;
+    }
+
+    // ---- per-parameter-vector scalars, once per warp -------------------------------
+    double(*scr)[LEAF_SCRATCH] = s_scratch[wib];
+    const double* th = a.theta + (size_t)row * a.P;
+    for (int i = 0; i < a.model.n_leaf; ++i) {
+        const LeafDev& L = a.model.leaf[i];
+        if (lane < ELISA_MAX_COMP_PARAMS)
+            scr[i][lane] = lane < L.np ? (L.src[lane] >= 0 ? th[L.src[lane]] : L.cst[lane]) : 0.0;
+    }
+    __syncwarp();
+    for (int i = 0; i < a.model.n_leaf; ++i) {
+        const LeafDev& L = a.model.leaf[i];
+        double tmp[LEAF_SCRATCH];
+#pragma unroll
+        for (int k = 0; k < ELISA_MAX_COMP_PARAMS; ++k) tmp[k] = scr[i][k];
+        switch (L.kind) {
+#define X(KIND)                                                                               \
+    case KIND:                                                                                \
+        if (GRAD) leaf_pre<KIND, Dual<Comp<KIND>::NP>>(tmp, L.aux);                           \
+        else leaf_pre<KIND, double>(tmp, L.aux);                                              \
+        break;
+            ELISA_FOR_EACH_KIND(X)
+#undef X
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = ELISA_MAX_COMP_PARAMS; k < LEAF_SCRATCH; ++k) scr[i][k] = tmp[k];
+        }
+    }
+    __syncwarp();
+
+    // ---- passes of 31 bins ------------------------------------------------------------
+    for (int e0 = e_lo; e0 < e_hi; e0 += 31) {
+        const int e = e0 + lane;
+        TT stk[ELISA_MAX_COMPONENTS];
+        int sp = 0;
+        for (int o = 0; o < a.model.n_ops; ++o) {
+            const int op = a.model.ops[o];
+            if (op >= 0) {
+                const LeafDev& L = a.model.leaf[op];
+                TT val;
+                switch (L.kind) {
+#define X(KIND)                                                                                            \
+    case KIND:                                                                                             \
+        if constexpr (GRAD)                                                                                \
+            val = scatter_leaf<PU, Comp<KIND>::NP>(                                                        \
+                leaf_bin<KIND, Dual<Comp<KIND>::NP>>(scr[op], L.method, a.gv, e), L.src);                  \
+        else                                                                                               \
+            val = leaf_bin<KIND, double>(scr[op], L.method, a.gv, e);                                      \
+        break;
+                    ELISA_FOR_EACH_KIND(X)
+#undef X
+                    default:
+                        val = Cst<TT>::make(0.0);
+                }
+                stk[sp++] = val;
+            } else {
+                const TT rhs = stk[--sp];
+                const TT lhs = stk[sp - 1];
+                stk[sp - 1] = (op == ELISA_OP_ADD) ? lhs + rhs : lhs * rhs;
+            }
+        }
+        const TT res = stk[0];
+        if (lane < 31 && e < e_hi) {
+            const double v = value(res);
+            bool pass = true;
+            double u = v;
+            if (a.clip) {
+                pass = (v >= 1e-300) && (v <= 1e300);
+                u = fmin(fmax(v, 1e-300), 1e300);  // NaN stays NaN through the statistic
+                if (v != v) u = v;
+            }
+            Urow[e] = u;
+            if constexpr (GRAD) {
+#pragma unroll
+                for (int j = 0; j < PU; ++j)
+                    if (j < a.P && ((a.model.used_mask >> j) & 1u))
+                        a.dU[j * a.plane + (size_t)row * a.ld + e] = pass ? res.d[j] : 0.0;
+            }
+        }
+    }
+    if (last_seg) {
+        for (int e = E + lane; e < a.e_pad; e += 32) {
+            Urow[e] = 0.0;
+            if (GRAD)
+                for (int j = 0; j < a.P; ++j)
+                    if ((a.model.used_mask >> j) & 1u) a.dU[j * a.plane + (size_t)row * a.ld + e] = 0.0;
+        }
+    }
+}
+
+// ======================================================================================
+// 2. statistic epilogue of the forward fold
+// ======================================================================================
+// partial log-likelihoods: part[tile_n * ld_part + row]
+template <int STAT, bool GRAD>
+struct EpilogueStat {
+    ChanArrays ch;
+    const double* counts_on;   // per-replica observed data [n, ld_counts] or nullptr
+    const double* counts_off;  // idem
+    int64_t ld_counts;
+    int32_t n_valid;  // rows with real parameter vectors
+    int32_t C;        // real channels
+    double* W;        // [rows, ldw]  d loglike / d (R u) (GRAD only)
+    int32_t ldw;
+    double* part;
+    int32_t ld_part;
+
+    __device__ __forceinline__ void operator()(AccFrag& acc, double* smem, int, int tile_n, int row0, int col0,
+                                               int warp_m, int warp_n, int lane) const {
+        double rs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rs[i] = 0.0;
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = col0 + 16 * l + cc;
+                const bool cvalid = col < C;
+                ChannelData d;
+                const double sc = ch.scale[col];
+                d.on = ch.on[col];
+                d.gof_on = ch.gof_on[col];
+                d.off = d.sigma = d.ratio = d.gof_off = 0.0;
+                if (STAT == ELISA_STAT_CHI2) d.sigma = ch.sigma[col];
+                if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+                    d.off = ch.off[col];
+                    d.ratio = ch.ratio[col];
+                }
+                if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[col];
+                if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[col];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = row0 + 8 * i;
+                    if (counts_on != nullptr && cvalid && row < n_valid) {
+                        d.on = counts_on[(size_t)row * ld_counts + col];
+                        if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
+                    }
+                    if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && counts_off != nullptr && cvalid &&
+                        row < n_valid) {
+                        d.off = counts_off[(size_t)row * ld_counts + col];
+                        if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
+                    }
+                    const double x = acc.get(i, l, cc) * sc;
+                    double dx = 0.0;
+                    const double ll = stat_channel<STAT, GRAD>(x, d, dx);
+                    rs[i] += cvalid ? ll : 0.0;
+                    if (GRAD) acc.set(i, l, cc, cvalid ? dx * sc : 0.0);
+                }
+            }
+        }
+        if (GRAD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double* wrow = W + (size_t)(row0 + 8 * i) * ldw + col0;
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    double2 lo, hi;
+                    lo.x = acc.get(i, l, 0);
+                    lo.y = acc.get(i, l, 1);
+                    hi.x = acc.get(i, l, 2);
+                    hi.y = acc.get(i, l, 3);
+                    *reinterpret_cast<double2*>(wrow + 16 * l) = lo;
+                    *reinterpret_cast<double2*>(wrow + 16 * l + 2) = hi;
+                }
+            }
+        }
+        // row sums: over the quad (4 lanes share a row), then over the two column warps
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+        }
+        double* red = smem;  // [2][128]
+        if ((lane & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp_n * GEMM_BM + warp_m * 64 + 8 * i + (lane >> 2)] = rs[i];
+        }
+        __syncthreads();
+        const int m0 = row0 - warp_m * 64 - (lane >> 2);
+        part[(size_t)tile_n * ld_part + m0 + threadIdx.x] = red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
+    }
+};
+
+// ======================================================================================
+// 3. gradient epilogue of the transposed fold
+// ======================================================================================
+// gpart[(j * n_tiles + tile_n) * ld_part + row]
+struct EpilogueGrad {
+    const double* dU;  // [P, rows, ldu]
+    int64_t plane;
+    int32_t ldu;
+    int32_t P;
+    uint32_t used_mask;
+    int32_t n_tiles;
+    double* gpart;
+    int32_t ld_part;
+
+    __device__ __forceinline__ void operator()(AccFrag& acc, double* smem, int, int tile_n, int row0, int col0,
+                                               int warp_m, int warp_n, int lane) const {
+        double* red = smem;
+        const int m0 = row0 - warp_m * 64 - (lane >> 2);
+        for (int j = 0; j < P; ++j) {
+            if (!((used_mask >> j) & 1u)) continue;
+            const double* base = dU + j * plane + (size_t)row0 * ldu + col0;
+            double rs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double* p = base + (size_t)(8 * i) * ldu;
+                double s = 0.0;
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const double2 lo = *reinterpret_cast<const double2*>(p + 16 * l);
+                    const double2 hi = *reinterpret_cast<const double2*>(p + 16 * l + 2);
+                    s = fma(acc.get(i, l, 0), lo.x, s);
+                    s = fma(acc.get(i, l, 1), lo.y, s);
+                    s = fma(acc.get(i, l, 2), hi.x, s);
+                    s = fma(acc.get(i, l, 3), hi.y, s);
+                }
+                rs[i] = s;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+                rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+            }
+            __syncthreads();
+            if ((lane & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) red[warp_n * GEMM_BM + warp_m * 64 + 8 * i + (lane >> 2)] = rs[i];
+            }
+            __syncthreads();
+            gpart[((size_t)j * n_tiles + tile_n) * ld_part + m0 + threadIdx.x] =
+                red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
+        }
+    }
+};
+
+// ======================================================================================
+// 4. fixed-order reduction of the tile partials
+// ======================================================================================
+struct ReduceArgs {
+    const double* part;  // [tiles_c, ld]
+    const double* gpart;  // [P, tiles_e, ld]
+    int32_t tiles_c, tiles_e, ld;
+    int32_t n;
+    int32_t P, S, s;
+    uint32_t used_mask;
+    double* loglike;  // [n, S]   (already offset to the chunk's first row)
+    double* grad;     // [n, S, P] or nullptr
+};
+
+__global__ void reduce_kernel(const ReduceArgs a) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.n) return;
+    double s = 0.0;
+    for (int t = 0; t < a.tiles_c; ++t) s += a.part[(size_t)t * a.ld + row];
+    a.loglike[(size_t)row * a.S + a.s] = s;
+    if (a.grad != nullptr) {
+        for (int j = 0; j < a.P; ++j) {
+            double g = 0.0;
+            if ((a.used_mask >> j) & 1u)
+                for (int t = 0; t < a.tiles_e; ++t) g += a.gpart[((size_t)j * a.tiles_e + t) * a.ld + row];
+            a.grad[((size_t)row * a.S + a.s) * a.P + j] = g;
+        }
+    }
+}
+
+// ======================================================================================
+// per-channel sites (likelihood.py:206-225 etc.): elementwise on the folded counts
+// ======================================================================================
+struct SitesArgs {
+    const double* X;  // [rows, ldx] folded R u
+    int32_t ldx;
+    ChanArrays ch;
+    const double* inv_width;  // 1 / channel_width (or nullptr: rate = source_rate)
+    const double* area;       // area_scale
+    const double* counts_on;
+    const double* counts_off;
+    int64_t ld_counts;
+    int32_t n, C, stat;
+    double *rate, *model_on, *ll_on, *model_off, *ll_off;  // [n, C] each, nullable
+};
+
+template <int STAT>
+__device__ __forceinline__ void sites_one(const SitesArgs& a, int row, int col) {
+    ChannelData d;
+    d.on = a.ch.on[col];
+    d.off = a.ch.off[col];
+    d.sigma = a.ch.sigma[col];
+    d.ratio = a.ch.ratio[col];
+    if (a.counts_on != nullptr) d.on = a.counts_on[(size_t)row * a.ld_counts + col];
+    if (a.counts_off != nullptr) d.off = a.counts_off[(size_t)row * a.ld_counts + col];
+    d.gof_on = poisson_gof(d.on);
+    d.gof_off = poisson_gof(d.off);
+    const double fold = a.X[(size_t)row * a.ldx + col];
+    double dx, site[4] = {0.0, 0.0, 0.0, 0.0};
+    stat_channel<STAT, false, true>(fold * a.ch.scale[col], d, dx, site);
+    const size_t o = (size_t)row * a.C + col;
+    if (a.rate) a.rate[o] = fold * a.area[col] * (a.inv_width ? a.inv_width[col] : 1.0);
+    if (a.model_on) a.model_on[o] = site[0];
+    if (a.ll_on) a.ll_on[o] = site[1];
+    if (a.model_off) a.model_off[o] = site[2];
+    if (a.ll_off) a.ll_off[o] = site[3];
+}
+
+__global__ void sites_kernel(const SitesArgs a) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (col >= a.C || row >= a.n) return;
+    switch (a.stat) {
+        case ELISA_STAT_CHI2: sites_one<ELISA_STAT_CHI2>(a, row, col); break;
+        case ELISA_STAT_CSTAT: sites_one<ELISA_STAT_CSTAT>(a, row, col); break;
+        case ELISA_STAT_PSTAT: sites_one<ELISA_STAT_PSTAT>(a, row, col); break;
+        case ELISA_STAT_PGSTAT: sites_one<ELISA_STAT_PGSTAT>(a, row, col); break;
+        default: sites_one<ELISA_STAT_WSTAT>(a, row, col); break;
+    }
+}
+
+// ======================================================================================
+// host side: plan
+// ======================================================================================
+static thread_local std::string g_last_error = "";
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ELISA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct PackedHost {
+    std::vector<double> data;
+    std::vector<int64_t> off;
+    std::vector<int32_t> k_lo, k_hi;
+};
+
+struct PackedDevice {
+    double* data = nullptr;
+    int64_t* off = nullptr;
+    int32_t* k_lo = nullptr;
+    int32_t* k_hi = nullptr;
+    int n_tiles = 0;
+    int64_t n_doubles = 0;
+    PackedB view() const { return PackedB{data, off, k_lo, k_hi}; }
+};
+
+struct SpectrumPlan {
+    int E = 0, C = 0, E_pad = 0, C_pad = 0;
+    int stat = 0;
+    ModelDev model;
+    // device arrays
+    double *egrid = nullptr, *lngrid = nullptr, *emid = nullptr, *lnmid = nullptr;
+    double* chan = nullptr;  // 9 arrays of C_pad: scale on off sigma ratio gof_on gof_off area inv_width
+    PackedDevice fwd, bwd;   // R [E, C] tiled over C ; R^T [C, E] tiled over E
+    int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
+    int64_t nnz = 0;
+    GridView grid_view() const { return GridView{egrid, lngrid, emid, lnmid, E}; }
+    ChanArrays chan_view() const {
+        return ChanArrays{chan, chan + C_pad, chan + 2 * C_pad, chan + 3 * C_pad,
+                          chan + 4 * C_pad, chan + 5 * C_pad, chan + 6 * C_pad};
+    }
+};
+
+}  // namespace elisa
+
+using namespace elisa;
+
+struct ElisaPlan {
+    int device = 0;
+    int P = 0, S = 0;
+    int64_t chunk = 0;
+    int64_t sum_C = 0;
+    int max_E_pad = 0, max_C_pad = 0;
+    std::vector<SpectrumPlan> spec;
+    // workspace
+    double *U = nullptr, *dU = nullptr, *W = nullptr, *part = nullptr, *gpart = nullptr;
+    int64_t workspace_bytes = 0;
+    int64_t launches = 0;
+    // host-path staging (device side), grown on demand
+    double *h_theta = nullptr, *h_ll = nullptr, *h_grad = nullptr, *h_on = nullptr, *h_off = nullptr;
+    int64_t h_n = 0;
+    bool h_counts = false;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> owned;
+};
+
+namespace elisa {
+
+template <typename T>
+static int upload(ElisaPlan* plan, const std::vector<T>& h, T** out) {
+    *out = nullptr;
+    const size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc((void**)out, bytes));
+    plan->owned.push_back(*out);
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ELISA_OK;
+}
+
+static int upload_packed(ElisaPlan* plan, const PackedHost& h, PackedDevice* d) {
+    int rc;
+    if ((rc = upload(plan, h.data, &d->data))) return rc;
+    if ((rc = upload(plan, h.off, &d->off))) return rc;
+    if ((rc = upload(plan, h.k_lo, &d->k_lo))) return rc;
+    if ((rc = upload(plan, h.k_hi, &d->k_hi))) return rc;
+    d->n_tiles = (int)h.off.size();
+    d->n_doubles = (int64_t)h.data.size();
+    return ELISA_OK;
+}
+
+// Pack a K x N matrix given by an element accessor into 64-column tiles holding rows
+// [k_lo, k_hi) between the first and last row with a non-zero (16-aligned).
+// get_col_range(n) -> (first k, one past last k) of the non-zeros of column n; fill(k, n).
+template <class Range, class Get>
+static void pack_tiles(int K, int N, int K_pad, Range col_range, Get get, PackedHost* out) {
+    const int n_tiles = round_up(N, GEMM_BN) / GEMM_BN;
+    out->off.resize(n_tiles);
+    out->k_lo.resize(n_tiles);
+    out->k_hi.resize(n_tiles);
+    int64_t total = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+        int lo = K, hi = 0;
+        for (int n = j * GEMM_BN; n < std::min(N, (j + 1) * GEMM_BN); ++n) {
+            int a, b;
+            col_range(n, &a, &b);
+            if (a < b) {
+                lo = std::min(lo, a);
+                hi = std::max(hi, b);
+            }
+        }
+        if (lo >= hi) lo = hi = 0;
+        lo = lo / GEMM_BK * GEMM_BK;
+        hi = std::min(round_up(hi, GEMM_BK), K_pad);
+        out->k_lo[j] = lo;
+        out->k_hi[j] = hi;
+        out->off[j] = total;
+        total += (int64_t)(hi - lo) * GEMM_BN;
+    }
+    out->data.assign((size_t)total, 0.0);
+    for (int j = 0; j < n_tiles; ++j) {
+        double* dst = out->data.data() + out->off[j];
+        const int lo = out->k_lo[j], hi = std::min(out->k_hi[j], K);
+        for (int n = j * GEMM_BN; n < std::min(N, (j + 1) * GEMM_BN); ++n)
+            get(n, lo, hi, dst + (n - j * GEMM_BN));  // writes dst[(k - lo) * 64] for k in [lo, hi)
+    }
+}
+
+static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
+    memset(out, 0, sizeof(*out));
+    if (md.n_components < 1 || md.n_components > ELISA_MAX_COMPONENTS || md.components == nullptr)
+        return fail(ELISA_ERR_INVALID, "model: n_components out of range");
+    out->n_leaf = md.n_components;
+    for (int i = 0; i < md.n_components; ++i) {
+        const ElisaComponentDesc& c = md.components[i];
+        const int np = comp_num_params(c.kind);
+        if (np < 0) return fail(ELISA_ERR_INVALID, "model: unknown component kind");
+        if (c.method != ELISA_METHOD_TRAPZ && c.method != ELISA_METHOD_SIMPSON)
+            return fail(ELISA_ERR_INVALID, "model: unknown integration method");
+        LeafDev& L = out->leaf[i];
+        L.kind = c.kind;
+        L.method = c.method;
+        L.np = np;
+        for (int k = 0; k < ELISA_MAX_COMP_PARAMS; ++k) {
+            L.src[k] = -1;
+            L.cst[k] = 0.0;
+        }
+        for (int k = 0; k < np; ++k) {
+            if (c.param_src[k] >= P) return fail(ELISA_ERR_INVALID, "model: param_src >= n_params");
+            L.src[k] = c.param_src[k] < 0 ? -1 : c.param_src[k];
+            L.cst[k] = c.param_const[k];
+            if (L.src[k] >= 0) out->used_mask |= 1u << L.src[k];
+        }
+        L.aux[0] = c.aux[0];
+        L.aux[1] = c.aux[1];
+        if ((c.kind == ELISA_COMP_PLENFLUX || c.kind == ELISA_COMP_PLPHFLUX) && !(c.aux[0] > 0.0 && c.aux[1] > c.aux[0]))
+            return fail(ELISA_ERR_INVALID, "model: PLPhFlux/PLEnFlux need 0 < emin < emax in aux");
+    }
+    // postfix program; a single component may omit it
+    if (md.n_ops == 0 && md.n_components == 1) {
+        out->n_ops = 1;
+        out->ops[0] = 0;
+        return ELISA_OK;
+    }
+    if (md.n_ops < 1 || md.n_ops > MAX_OPS || md.ops == nullptr)
+        return fail(ELISA_ERR_INVALID, "model: n_ops out of range");
+    int depth = 0;
+    // type check as models/model.py:1228-1258: '+' needs add, add; '*' forbids add * add
+    std::vector<int> types;  // 1 = additive, 0 = multiplicative
+    for (int o = 0; o < md.n_ops; ++o) {
+        const int op = md.ops[o];
+        if (op >= 0) {
+            if (op >= md.n_components) return fail(ELISA_ERR_INVALID, "model: op references unknown component");
+            types.push_back(comp_is_additive(md.components[op].kind) ? 1 : 0);
+            ++depth;
+        } else if (op == ELISA_OP_ADD || op == ELISA_OP_MUL) {
+            if (depth < 2) return fail(ELISA_ERR_INVALID, "model: malformed postfix program");
+            const int r = types.back();
+            types.pop_back();
+            const int l = types.back();
+            types.pop_back();
+            if (op == ELISA_OP_ADD && !(l == 1 && r == 1))
+                return fail(ELISA_ERR_INVALID, "model: '+' needs two additive operands");
+            if (op == ELISA_OP_MUL && l == 1 && r == 1)
+                return fail(ELISA_ERR_INVALID, "model: '*' of two additive operands");
+            types.push_back(op == ELISA_OP_ADD ? 1 : (l | r));
+            --depth;
+        } else {
+            return fail(ELISA_ERR_INVALID, "model: unknown opcode");
+        }
+        if (depth > ELISA_MAX_COMPONENTS) return fail(ELISA_ERR_INVALID, "model: expression too deep");
+        out->ops[o] = op;
+    }
+    if (depth != 1) return fail(ELISA_ERR_INVALID, "model: malformed postfix program");
+    out->n_ops = md.n_ops;
+    return ELISA_OK;
+}
+
+static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, SpectrumPlan* sp) {
+    const int E = sd.n_energies, C = sd.n_channels;
+    if (E < 1 || C < 1) return fail(ELISA_ERR_INVALID, "spectrum: empty energy grid or channel set");
+    if (sd.photon_egrid == nullptr || sd.area_scale == nullptr || sd.on_counts == nullptr)
+        return fail(ELISA_ERR_INVALID, "spectrum: photon_egrid, area_scale and on_counts are required");
+    const bool dense = sd.response_dense != nullptr;
+    const bool sparse = sd.csr_indptr != nullptr && sd.csr_indices != nullptr && sd.csr_values != nullptr;
+    if (dense == sparse) return fail(ELISA_ERR_INVALID, "spectrum: give exactly one of response_dense / csr_*");
+    if (sd.stat < ELISA_STAT_CHI2 || sd.stat > ELISA_STAT_WSTAT) return fail(ELISA_ERR_INVALID, "spectrum: unknown stat");
+    if (sd.stat == ELISA_STAT_CHI2 && sd.on_error == nullptr)
+        return fail(ELISA_ERR_INVALID, "chi2 needs on_error (net_errors)");
+    if (sd.stat >= ELISA_STAT_PSTAT && (sd.off_counts == nullptr || sd.back_ratio == nullptr))
+        return fail(ELISA_ERR_INVALID, "pstat/pgstat/wstat need off_counts and back_ratio");
+    if (sd.stat == ELISA_STAT_PGSTAT && sd.off_error == nullptr)
+        return fail(ELISA_ERR_INVALID, "pgstat needs off_error (back_errors)");
+    for (int e = 0; e <= E; ++e)
+        if (!(sd.photon_egrid[e] > 0.0) || (e > 0 && !(sd.photon_egrid[e] > sd.photon_egrid[e - 1])))
+            return fail(ELISA_ERR_INVALID, "spectrum: photon_egrid must be positive and increasing");
+
+    sp->E = E;
+    sp->C = C;
+    sp->E_pad = round_up(E, GEMM_BN);
+    sp->C_pad = round_up(C, GEMM_BN);
+    sp->stat = sd.stat;
+    int rc;
+    if ((rc = build_model(sd.model, plan->P, &sp->model))) return rc;
+
+    // grids
+    std::vector<double> eg(sd.photon_egrid, sd.photon_egrid + E + 1), lg(E + 1), em(E), lm(E);
+    for (int e = 0; e <= E; ++e) lg[e] = log(eg[e]);
+    for (int e = 0; e < E; ++e) {
+        em[e] = 0.5 * (eg[e] + eg[e + 1]);
+        lm[e] = log(em[e]);
+    }
+    if ((rc = upload(plan, eg, &sp->egrid))) return rc;
+    if ((rc = upload(plan, lg, &sp->lngrid))) return rc;
+    if ((rc = upload(plan, em, &sp->emid))) return rc;
+    if ((rc = upload(plan, lm, &sp->lnmid))) return rc;
+
+    // per-channel data, padded with benign values
+    const int Cp = sp->C_pad;
+    std::vector<double> ch((size_t)9 * Cp, 0.0);
+    auto xlogy_h = [](double x, double y) { return x == 0.0 ? 0.0 : x * log(y); };
+    for (int c = 0; c < Cp; ++c) {
+        const bool v = c < C;
+        const double on = v ? sd.on_counts[c] : 0.0;
+        const double off = v && sd.off_counts ? sd.off_counts[c] : 0.0;
+        double sigma = 1.0;
+        if (v && sd.stat == ELISA_STAT_CHI2) sigma = sd.on_error[c];
+        if (v && sd.stat == ELISA_STAT_PGSTAT) sigma = sd.off_error[c];
+        ch[0 * Cp + c] = v ? sd.area_scale[c] * sd.exposure : 0.0;
+        ch[1 * Cp + c] = on;
+        ch[2 * Cp + c] = off;
+        ch[3 * Cp + c] = sigma;
+        ch[4 * Cp + c] = v && sd.back_ratio ? sd.back_ratio[c] : 1.0;
+        ch[5 * Cp + c] = xlogy_h(on, on) - on;
+        ch[6 * Cp + c] = xlogy_h(off, off) - off;
+        ch[7 * Cp + c] = v ? sd.area_scale[c] : 0.0;
+        ch[8 * Cp + c] = 1.0;  // 1 / channel_width: set by elisa_b200_plan_set_channel_width
+    }
+    if ((rc = upload(plan, ch, &sp->chan))) return rc;
+
+    // response -> two packed operands
+    PackedHost fwd, bwd;
+    if (dense) {
+        const double* R = sd.response_dense;  // [E, C]
+        int64_t nnz = 0;
+        std::vector<int> clo(C, E), chi(C, 0), elo(E, C), ehi(E, 0);
+        for (int e = 0; e < E; ++e)
+            for (int c = 0; c < C; ++c)
+                if (R[(size_t)e * C + c] != 0.0) {
+                    ++nnz;
+                    clo[c] = std::min(clo[c], e);
+                    chi[c] = std::max(chi[c], e + 1);
+                    elo[e] = std::min(elo[e], c);
+                    ehi[e] = std::max(ehi[e], c + 1);
+                }
+        sp->nnz = nnz;
+        pack_tiles(
+            E, C, sp->E_pad, [&](int n, int* a, int* b) { *a = clo[n]; *b = chi[n]; },
+            [&](int n, int lo, int hi, double* dst) {
+                for (int k = lo; k < hi; ++k) dst[(size_t)(k - lo) * GEMM_BN] = R[(size_t)k * C + n];
+            },
+            &fwd);
+        pack_tiles(
+            C, E, sp->C_pad, [&](int n, int* a, int* b) { *a = elo[n]; *b = ehi[n]; },
+            [&](int n, int lo, int hi, double* dst) {
+                for (int k = lo; k < hi; ++k) dst[(size_t)(k - lo) * GEMM_BN] = R[(size_t)n * C + k];
+            },
+            &bwd);
+    } else {
+        const int32_t* ip = sd.csr_indptr;
+        if (ip[0] != 0) return fail(ELISA_ERR_INVALID, "csr_indptr[0] != 0");
+        for (int c = 0; c < C; ++c)
+            if (ip[c + 1] < ip[c]) return fail(ELISA_ERR_INVALID, "csr_indptr not monotone");
+        const int64_t nnz = ip[C];
+        sp->nnz = nnz;
+        for (int64_t i = 0; i < nnz; ++i)
+            if (sd.csr_indices[i] < 0 || sd.csr_indices[i] >= E) return fail(ELISA_ERR_INVALID, "csr_indices out of range");
+        std::vector<int> clo(C, E), chi(C, 0), elo(E, C), ehi(E, 0);
+        for (int c = 0; c < C; ++c)
+            for (int i = ip[c]; i < ip[c + 1]; ++i) {
+                const int e = sd.csr_indices[i];
+                clo[c] = std::min(clo[c], e);
+                chi[c] = std::max(chi[c], e + 1);
+                elo[e] = std::min(elo[e], c);
+                ehi[e] = std::max(ehi[e], c + 1);
+            }
+        // forward: columns = channels; duplicates accumulate like scipy's tocsr would
+        pack_tiles(
+            E, C, sp->E_pad, [&](int n, int* a, int* b) { *a = clo[n]; *b = chi[n]; },
+            [&](int n, int lo, int, double* dst) {
+                for (int i = ip[n]; i < ip[n + 1]; ++i)
+                    dst[(size_t)(sd.csr_indices[i] - lo) * GEMM_BN] += sd.csr_values[i];
+            },
+            &fwd);
+        // transposed: columns = energies; build a CSC view (by energy) first
+        std::vector<int64_t> cp(E + 1, 0);
+        for (int64_t i = 0; i < nnz; ++i) ++cp[sd.csr_indices[i] + 1];
+        for (int e = 0; e < E; ++e) cp[e + 1] += cp[e];
+        std::vector<int32_t> crow((size_t)nnz);
+        std::vector<double> cval((size_t)nnz);
+        {
+            std::vector<int64_t> pos(cp.begin(), cp.end() - 1);
+            for (int c = 0; c < C; ++c)
+                for (int i = ip[c]; i < ip[c + 1]; ++i) {
+                    const int64_t p = pos[sd.csr_indices[i]]++;
+                    crow[p] = c;
+                    cval[p] = sd.csr_values[i];
+                }
+        }
+        pack_tiles(
+            C, E, sp->C_pad, [&](int n, int* a, int* b) { *a = elo[n]; *b = ehi[n]; },
+            [&](int n, int lo, int, double* dst) {
+                for (int64_t i = cp[n]; i < cp[n + 1]; ++i) dst[(size_t)(crow[i] - lo) * GEMM_BN] += cval[i];
+            },
+            &bwd);
+    }
+    if ((rc = upload_packed(plan, fwd, &sp->fwd))) return rc;
+    if ((rc = upload_packed(plan, bwd, &sp->bwd))) return rc;
+    return ELISA_OK;
+}
+
+// ---- launches ------------------------------------------------------------------------
+static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* theta, int n_valid, int n_rows,
+                         bool grad, double* U, double* dU, int ld, int e_pad, bool clip, cudaStream_t st) {
+    UnfoldArgs a;
+    a.model = sp.model;
+    a.gv = sp.grid_view();
+    a.theta = theta;
+    a.P = plan->P;
+    a.n_valid = n_valid;
+    a.n_rows = n_rows;
+    // enough warps to fill the machine: split the energy axis when there are few rows
+    int n_seg = 1;
+    const int64_t want_warps = 148 * 32;
+    while ((int64_t)n_rows * n_seg < want_warps && (sp.E + n_seg - 1) / n_seg > 62) n_seg *= 2;
+    int seg_len = ((sp.E + n_seg - 1) / n_seg + 30) / 31 * 31;
+    n_seg = (sp.E + seg_len - 1) / seg_len;
+    a.n_seg = n_seg;
+    a.seg_len = seg_len;
+    a.ld = ld;
+    a.e_pad = e_pad;
+    a.clip = clip ? 1 : 0;
+    a.U = U;
+    a.dU = dU;
+    a.plane = (int64_t)n_rows * ld;
+    const int64_t warps = (int64_t)n_rows * n_seg;
+    const int blocks = (int)((warps + UNFOLD_WARPS - 1) / UNFOLD_WARPS);
+    const int threads = UNFOLD_WARPS * 32;
+    if (!grad)
+        unfold_kernel<0><<<blocks, threads, 0, st>>>(a);
+    else if (plan->P <= 4)
+        unfold_kernel<4><<<blocks, threads, 0, st>>>(a);
+    else if (plan->P <= 8)
+        unfold_kernel<8><<<blocks, threads, 0, st>>>(a);
+    else
+        unfold_kernel<16><<<blocks, threads, 0, st>>>(a);
+    ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+template <class Epi>
+static int launch_gemm(ElisaPlan* plan, const double* A, int lda, const PackedDevice& B, int m_tiles, const Epi& epi,
+                       cudaStream_t st) {
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_f64_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GEMM_SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid(B.n_tiles, m_tiles);
+    gemm_f64_kernel<Epi><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(A, lda, B.view(), epi);
+    ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+template <int STAT, bool GRAD>
+static int launch_stat_gemm(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid, int m_tiles, const double* on,
+                            const double* off, cudaStream_t st) {
+    EpilogueStat<STAT, GRAD> epi;
+    epi.ch = sp.chan_view();
+    epi.counts_on = on ? on + sp.counts_off : nullptr;
+    epi.counts_off = off ? off + sp.counts_off : nullptr;
+    epi.ld_counts = plan->sum_C;
+    epi.n_valid = n_valid;
+    epi.C = sp.C;
+    epi.W = plan->W;
+    epi.ldw = sp.C_pad;
+    epi.part = plan->part;
+    epi.ld_part = (int)plan->chunk;
+    return launch_gemm(plan, plan->U, sp.E_pad, sp.fwd, m_tiles, epi, st);
+}
+
+template <bool GRAD>
+static int launch_stat_gemm_any(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid, int m_tiles, const double* on,
+                                const double* off, cudaStream_t st) {
+    switch (sp.stat) {
+        case ELISA_STAT_CHI2: return launch_stat_gemm<ELISA_STAT_CHI2, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_CSTAT: return launch_stat_gemm<ELISA_STAT_CSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_PSTAT: return launch_stat_gemm<ELISA_STAT_PSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_PGSTAT: return launch_stat_gemm<ELISA_STAT_PGSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        default: return launch_stat_gemm<ELISA_STAT_WSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+    }
+}
+
+// One (chunk, spectrum) pass.  theta/on/off/loglike/grad already point at the chunk's first row.
+static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off, int n,
+                     double* loglike, double* grad, cudaStream_t st) {
+    const SpectrumPlan& sp = plan->spec[s];
+    const int n_rows = round_up(n, GEMM_BM);
+    const int m_tiles = n_rows / GEMM_BM;
+    const bool want_grad = grad != nullptr;
+    int rc;
+    if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st)))
+        return rc;
+    if (want_grad) {
+        if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
+        EpilogueGrad eg;
+        eg.dU = plan->dU;
+        eg.plane = (int64_t)n_rows * sp.E_pad;
+        eg.ldu = sp.E_pad;
+        eg.P = plan->P;
+        eg.used_mask = sp.model.used_mask;
+        eg.n_tiles = sp.bwd.n_tiles;
+        eg.gpart = plan->gpart;
+        eg.ld_part = (int)plan->chunk;
+        if ((rc = launch_gemm(plan, plan->W, sp.C_pad, sp.bwd, m_tiles, eg, st))) return rc;
+    } else {
+        if ((rc = launch_stat_gemm_any<false>(plan, sp, n, m_tiles, on, off, st))) return rc;
+    }
+    ReduceArgs ra;
+    ra.part = plan->part;
+    ra.gpart = plan->gpart;
+    ra.tiles_c = sp.fwd.n_tiles;
+    ra.tiles_e = sp.bwd.n_tiles;
+    ra.ld = (int)plan->chunk;
+    ra.n = n;
+    ra.P = plan->P;
+    ra.S = plan->S;
+    ra.s = s;
+    ra.used_mask = sp.model.used_mask;
+    ra.loglike = loglike;
+    ra.grad = grad;
+    reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ra);
+    ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+static int run_all(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
+                   double* loglike, double* grad, cudaStream_t st) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
+    if (n == 0) return ELISA_OK;
+    if (theta == nullptr || loglike == nullptr) return fail(ELISA_ERR_INVALID, "theta / loglike is null");
+    int dev;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
+    int rc = ELISA_OK;
+    for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
+        const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
+        for (int s = 0; s < plan->S && rc == ELISA_OK; ++s)
+            rc = run_chunk(plan, s, theta + i0 * plan->P, on ? on + i0 * plan->sum_C : nullptr,
+                           off ? off + i0 * plan->sum_C : nullptr, nc, loglike + i0 * plan->S,
+                           grad ? grad + i0 * plan->S * plan->P : nullptr, st);
+    }
+    if (dev != plan->device) cudaSetDevice(dev);
+    return rc;
+}
+
+}  // namespace elisa
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+int elisa_b200_abi_version(void) { return ELISA_B200_ABI_VERSION; }
+
+const char* elisa_b200_last_error(void) { return g_last_error.c_str(); }
+
+void elisa_b200_plan_destroy(ElisaPlan* plan) {
+    if (plan == nullptr) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaSetDevice(plan->device);
+    for (void* p : plan->owned) cudaFree(p);
+    for (double* p : {plan->h_theta, plan->h_ll, plan->h_grad, plan->h_on, plan->h_off})
+        if (p) cudaFree(p);
+    if (plan->stream) cudaStreamDestroy(plan->stream);
+    cudaSetDevice(dev);
+    delete plan;
+}
+
+int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
+    if (out == nullptr) return fail(ELISA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (desc == nullptr) return fail(ELISA_ERR_INVALID, "desc is null");
+    if (desc->abi_version != ELISA_B200_ABI_VERSION) return fail(ELISA_ERR_INVALID, "ABI version mismatch");
+    if (desc->n_params < 1 || desc->n_params > ELISA_MAX_PARAMS)
+        return fail(ELISA_ERR_INVALID, "n_params out of range [1, ELISA_MAX_PARAMS]");
+    if (desc->n_spectra < 1 || desc->spectra == nullptr) return fail(ELISA_ERR_INVALID, "no spectra");
+    if (desc->chunk < 0) return fail(ELISA_ERR_INVALID, "chunk < 0");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(ELISA_ERR_CUDA, "no CUDA device: elisa_b200 has no CPU fallback");
+    if (desc->device < 0 || desc->device >= n_dev) return fail(ELISA_ERR_INVALID, "device ordinal out of range");
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(desc->device));
+
+    ElisaPlan* plan = new (std::nothrow) ElisaPlan();
+    if (plan == nullptr) return fail(ELISA_ERR_NOMEM, "out of host memory");
+    plan->device = desc->device;
+    plan->P = desc->n_params;
+    plan->S = desc->n_spectra;
+    plan->spec.resize(plan->S);
+    int rc = ELISA_OK;
+    int64_t coff = 0;
+    for (int s = 0; s < plan->S && rc == ELISA_OK; ++s) {
+        rc = build_spectrum(plan, desc->spectra[s], &plan->spec[s]);
+        if (rc) break;
+        plan->spec[s].counts_off = coff;
+        coff += plan->spec[s].C;
+        plan->max_E_pad = std::max(plan->max_E_pad, plan->spec[s].E_pad);
+        plan->max_C_pad = std::max(plan->max_C_pad, plan->spec[s].C_pad);
+    }
+    plan->sum_C = coff;
+    if (rc == ELISA_OK) {
+        // chunk: one 128-row tile per SM by default, bounded by a 6 GiB workspace
+        int64_t chunk = desc->chunk > 0 ? desc->chunk : 148 * GEMM_BM;
+        chunk = (chunk + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
+        const int64_t tiles_c = plan->max_C_pad / GEMM_BN, tiles_e = plan->max_E_pad / GEMM_BN;
+        const int64_t per_row = 8 * ((int64_t)plan->max_E_pad * (1 + plan->P) + plan->max_C_pad + tiles_c +
+                                     tiles_e * plan->P);
+        if (desc->chunk == 0) {
+            const int64_t budget = (int64_t)6 << 30;
+            while (chunk > GEMM_BM && chunk * per_row > budget) chunk = (chunk / 2 + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
+        }
+        plan->chunk = chunk;
+        auto alloc = [&](double** p, int64_t n_doubles) -> int {
+            CUDA_TRY(cudaMalloc((void**)p, (size_t)n_doubles * 8));
+            plan->owned.push_back(*p);
+            plan->workspace_bytes += n_doubles * 8;
+            return ELISA_OK;
+        };
+        if (rc == ELISA_OK) rc = alloc(&plan->U, chunk * plan->max_E_pad);
+        if (rc == ELISA_OK) rc = alloc(&plan->dU, chunk * plan->max_E_pad * plan->P);
+        if (rc == ELISA_OK) rc = alloc(&plan->W, chunk * plan->max_C_pad);
+        if (rc == ELISA_OK) rc = alloc(&plan->part, chunk * tiles_c);
+        if (rc == ELISA_OK) rc = alloc(&plan->gpart, chunk * tiles_e * plan->P);
+    }
+    if (rc == ELISA_OK && cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(ELISA_ERR_CUDA, "cudaStreamCreate failed");
+    cudaSetDevice(prev);
+    if (rc != ELISA_OK) {
+        const std::string keep = g_last_error;
+        elisa_b200_plan_destroy(plan);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = plan;
+    return ELISA_OK;
+}
+
+int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const double* channel_width) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S || channel_width == nullptr)
+        return fail(ELISA_ERR_INVALID, "set_channel_width: bad argument");
+    SpectrumPlan& sp = plan->spec[spectrum];
+    std::vector<double> inv(sp.C_pad, 1.0);
+    for (int c = 0; c < sp.C; ++c) inv[c] = 1.0 / channel_width[c];
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    CUDA_TRY(cudaMemcpy(sp.chan + (size_t)8 * sp.C_pad, inv.data(), (size_t)sp.C_pad * 8, cudaMemcpyHostToDevice));
+    cudaSetDevice(prev);
+    return ELISA_OK;
+}
+
+int elisa_b200_loglike_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
+                           int64_t n, double* loglike, void* cuda_stream) {
+    return run_all(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const double* counts_on,
+                                const double* counts_off, int64_t n, double* loglike, double* grad,
+                                void* cuda_stream) {
+    if (grad == nullptr) return fail(ELISA_ERR_INVALID, "grad is null");
+    return run_all(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
+}
+
+int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, int64_t n, double* unfold,
+                          void* cuda_stream) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "unfold: bad spectrum");
+    if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
+    if (n == 0) return ELISA_OK;
+    if (theta == nullptr || unfold == nullptr) return fail(ELISA_ERR_INVALID, "unfold: null pointer");
+    const SpectrumPlan& sp = plan->spec[spectrum];
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    int rc = ELISA_OK;
+    const int64_t step = 1 << 20;
+    for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += step) {
+        const int nc = (int)std::min<int64_t>(step, n - i0);
+        rc = launch_unfold(plan, sp, theta + i0 * plan->P, nc, nc, false, unfold + i0 * sp.E, nullptr, sp.E, sp.E,
+                           false, (cudaStream_t)cuda_stream);
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, const double* counts_on,
+                         const double* counts_off, int64_t n, double* rate, double* model_on, double* ll_on,
+                         double* model_off, double* ll_off, void* cuda_stream) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "sites: bad spectrum");
+    if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
+    if (n == 0) return ELISA_OK;
+    if (theta == nullptr) return fail(ELISA_ERR_INVALID, "sites: theta is null");
+    const SpectrumPlan& sp = plan->spec[spectrum];
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    int rc = ELISA_OK;
+    for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
+        const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
+        const int n_rows = round_up(nc, GEMM_BM);
+        rc = launch_unfold(plan, sp, theta + i0 * plan->P, nc, n_rows, false, plan->U, nullptr, sp.E_pad, sp.E_pad,
+                           true, st);
+        if (rc) break;
+        EpilogueStore es{plan->W, sp.C_pad};
+        rc = launch_gemm(plan, plan->U, sp.E_pad, sp.fwd, n_rows / GEMM_BM, es, st);
+        if (rc) break;
+        SitesArgs a;
+        a.X = plan->W;
+        a.ldx = sp.C_pad;
+        a.ch = sp.chan_view();
+        a.area = sp.chan + (size_t)7 * sp.C_pad;
+        a.inv_width = sp.chan + (size_t)8 * sp.C_pad;
+        a.counts_on = counts_on ? counts_on + i0 * plan->sum_C + sp.counts_off : nullptr;
+        a.counts_off = counts_off ? counts_off + i0 * plan->sum_C + sp.counts_off : nullptr;
+        a.ld_counts = plan->sum_C;
+        a.n = nc;
+        a.C = sp.C;
+        a.stat = sp.stat;
+        const size_t o = (size_t)i0 * sp.C;
+        a.rate = rate ? rate + o : nullptr;
+        a.model_on = model_on ? model_on + o : nullptr;
+        a.ll_on = ll_on ? ll_on + o : nullptr;
+        a.model_off = model_off ? model_off + o : nullptr;
+        a.ll_off = ll_off ? ll_off + o : nullptr;
+        dim3 grid((sp.C + 127) / 128, nc);
+        sites_kernel<<<grid, 128, 0, st>>>(a);
+        ++plan->launches;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "sites_kernel launch failed");
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const double* counts_on,
+                                 const double* counts_off, int64_t n, double* loglike, double* grad) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
+    if (n == 0) return ELISA_OK;
+    if (theta == nullptr || loglike == nullptr) return fail(ELISA_ERR_INVALID, "theta / loglike is null");
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    const bool counts = counts_on != nullptr || counts_off != nullptr;
+    if (n > plan->h_n || (counts && !plan->h_counts)) {
+        for (double** p : {&plan->h_theta, &plan->h_ll, &plan->h_grad, &plan->h_on, &plan->h_off}) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
+        plan->h_n = 0;
+        CUDA_TRY(cudaMalloc((void**)&plan->h_theta, (size_t)n * plan->P * 8));
+        CUDA_TRY(cudaMalloc((void**)&plan->h_ll, (size_t)n * plan->S * 8));
+        CUDA_TRY(cudaMalloc((void**)&plan->h_grad, (size_t)n * plan->S * plan->P * 8));
+        if (counts) {
+            CUDA_TRY(cudaMalloc((void**)&plan->h_on, (size_t)n * plan->sum_C * 8));
+            CUDA_TRY(cudaMalloc((void**)&plan->h_off, (size_t)n * plan->sum_C * 8));
+        }
+        plan->h_n = n;
+        plan->h_counts = counts;
+    }
+    cudaStream_t st = plan->stream;
+    CUDA_TRY(cudaMemcpyAsync(plan->h_theta, theta, (size_t)n * plan->P * 8, cudaMemcpyHostToDevice, st));
+    if (counts_on)
+        CUDA_TRY(cudaMemcpyAsync(plan->h_on, counts_on, (size_t)n * plan->sum_C * 8, cudaMemcpyHostToDevice, st));
+    if (counts_off)
+        CUDA_TRY(cudaMemcpyAsync(plan->h_off, counts_off, (size_t)n * plan->sum_C * 8, cudaMemcpyHostToDevice, st));
+    int rc = run_all(plan, plan->h_theta, counts_on ? plan->h_on : nullptr, counts_off ? plan->h_off : nullptr, n,
+                     plan->h_ll, grad ? plan->h_grad : nullptr, st);
+    if (rc == ELISA_OK) {
+        CUDA_TRY(cudaMemcpyAsync(loglike, plan->h_ll, (size_t)n * plan->S * 8, cudaMemcpyDeviceToHost, st));
+        if (grad)
+            CUDA_TRY(cudaMemcpyAsync(grad, plan->h_grad, (size_t)n * plan->S * plan->P * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int64_t elisa_b200_plan_workspace_bytes(const ElisaPlan* plan) { return plan ? plan->workspace_bytes : 0; }
+int64_t elisa_b200_plan_launch_count(const ElisaPlan* plan) { return plan ? plan->launches : 0; }
+int64_t elisa_b200_plan_chunk(const ElisaPlan* plan) { return plan ? plan->chunk : 0; }
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+"""Host-side mirror of the reference's likelihood seam for the hot path.
+
+Reference: ``likelihood_wrapper[stat](data, model.eval)`` closures
+(infer/helper.py:313-323; infer/likelihood.py:184-450) and the reductions
+``get_loglike`` / ``deviance`` / ``deviance_total`` (infer/helper.py:494-512, 571-586),
+differentiated by ``jax.grad`` (infer/fit.py:487) and batched by ``jax.vmap`` over
+parameter vectors.  Here one :class:`Likelihood` owns a CUDA plan (replicated constants
++ workspace) and evaluates a whole batch per call through the C ABI
+(include/elisa_b200.h).  torch supplies device memory and streams only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from .data import FixedData
+from .models import CompiledModel, Model
+
+# statistic -> needs (infer/likelihood.py:184-450; validity rules of infer/fit.py:_parse_input)
+_NEEDS_BACK = ('pstat', 'pgstat', 'wstat')
+
+
+def _ptr(a, ctype=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _dev_ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Likelihood:
+    """Batched log-likelihood (+ gradient) of S datasets for N parameter vectors.
+
+    Parameters
+    ----------
+    data : sequence of FixedData
+    model : CompiledModel / Model, or one per dataset.  Free parameters shared between
+        models (the same UniformParameter instance) are one column of ``theta``.
+    stat : sequence of {'chi2', 'cstat', 'pstat', 'pgstat', 'wstat'}, one per dataset
+    device : CUDA device ordinal (default: torch's current device)
+    chunk : parameter vectors per internal pass (0 = library default)
+
+    ``params_name`` lists the columns of ``theta`` (constrained space; priors and
+    transforms stay with the caller, infer/helper.py:409-426).
+    """
+
+    def __init__(self, data: Sequence[FixedData], model, stat: Sequence[str], device: int | None = None, chunk: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.ElisaB200Error('elisa_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        lib = _lib.load()
+        data = list(data)
+        if isinstance(model, (CompiledModel, Model)):
+            model = [model] * len(data)
+        model = [m if isinstance(m, CompiledModel) else m.compile() for m in model]
+        stat = [stat] * len(data) if isinstance(stat, str) else list(stat)
+        if not (len(data) == len(model) == len(stat)) or not data:
+            raise ValueError('data, model and stat must have the same non-zero length')
+        for d, s in zip(data, stat):
+            if s not in _lib.STAT:
+                raise ValueError(f'unknown statistic {s!r}')
+            if s in _NEEDS_BACK and not d.has_back:
+                raise ValueError(f'{s} requires background data ({d.name})')  # likelihood.py:280,331,397
+            if s == 'chi2' and (d.net_counts is None or d.net_errors is None):
+                raise ValueError(f'chi2 requires net_counts / net_errors ({d.name})')
+            if s == 'pgstat' and d.back_errors is None:
+                raise ValueError(f'pgstat requires back_errors ({d.name})')
+        for m in model:
+            if m.type != 'add':
+                raise TypeError('the model folded through a response must be additive')
+        self.data, self.model, self.stat = data, model, stat
+        self.names = [str(d.name) for d in data]
+        # global free-parameter list (columns of theta), first appearance order
+        self.free, self.params_name = [], []
+        for m in model:
+            for p, n in zip(m.free, m.params_name):
+                if all(p is not q for q in self.free):
+                    self.free.append(p)
+                    self.params_name.append(n)
+        self.nparam = len(self.free)
+        if self.nparam > _lib.MAX_PARAMS:
+            raise NotImplementedError(f'more than {_lib.MAX_PARAMS} free parameters')
+        self.params_default = np.array([p.default for p in self.free], dtype=np.float64)
+        self._P = max(self.nparam, 1)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._torch = torch
+        self._lib = lib
+
+        keep = []
+        specs = (_lib.SpectrumDesc * len(data))()
+        for i, (d, m, s) in enumerate(zip(data, model, stat)):
+            sd = specs[i]
+            sd.n_energies, sd.n_channels = d.n_energies, d.n_channels
+            sd.photon_egrid = _ptr(d.photon_egrid)
+            if d.response_sparse:
+                ip, ix, v = d.sparse_matrix
+                sd.csr_indptr, sd.csr_indices, sd.csr_values = _ptr(ip, C.c_int32), _ptr(ix, C.c_int32), _ptr(v)
+            else:
+                sd.response_dense = _ptr(d.response_matrix)
+            sd.area_scale = _ptr(d.area_scale)
+            sd.exposure = d.spec_exposure
+            sd.stat = _lib.STAT[s]
+            if s == 'chi2':
+                sd.on_counts, sd.on_error = _ptr(d.net_counts), _ptr(d.net_errors)
+            else:
+                sd.on_counts = _ptr(d.spec_counts)
+            if s in _NEEDS_BACK:
+                sd.off_counts, sd.back_ratio = _ptr(d.back_counts), _ptr(d.back_ratio)
+            if s == 'pgstat':
+                sd.off_error = _ptr(d.back_errors)
+            sd.model, k = m.to_desc(self.free)
+            keep.append(k)
+        desc = _lib.PlanDesc(_lib.ABI_VERSION, self.device, self._P, len(data), specs, int(chunk), 0)
+        handle = C.c_void_p()
+        _lib.check(lib.elisa_b200_plan_create(C.byref(desc), C.byref(handle)))
+        self._h = handle
+        for i, d in enumerate(data):
+            _lib.check(lib.elisa_b200_plan_set_channel_width(self._h, i, _ptr(d.channel_width)))
+        self.n_channels = [d.n_channels for d in data]
+        self.sum_channels = int(sum(self.n_channels))
+
+    # -- lifetime ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.elisa_b200_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def chunk(self) -> int:
+        return int(self._lib.elisa_b200_plan_chunk(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.elisa_b200_plan_workspace_bytes(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.elisa_b200_plan_launch_count(self._h))
+
+    # -- argument plumbing -----------------------------------------------------------
+    def _theta(self, theta):
+        torch = self._torch
+        t = torch.as_tensor(theta, dtype=torch.float64)
+        if t.dim() == 1:
+            t = t.unsqueeze(0)
+        if t.dim() != 2 or t.shape[1] != self.nparam:
+            raise ValueError(f'expected theta of shape (N, {self.nparam}), got {tuple(t.shape)}')
+        if self.nparam == 0:
+            t = torch.zeros((t.shape[0], 1), dtype=torch.float64)
+        return t.to(f'cuda:{self.device}').contiguous()
+
+    def _counts(self, c, n):
+        if c is None:
+            return None
+        torch = self._torch
+        t = torch.as_tensor(c, dtype=torch.float64)
+        if tuple(t.shape) != (n, self.sum_channels):
+            raise ValueError(f'expected per-replica counts of shape ({n}, {self.sum_channels}), got {tuple(t.shape)}')
+        return t.to(f'cuda:{self.device}').contiguous()
+
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- device API (torch tensors in, torch tensors out) ----------------------------
+    def loglike(self, theta, counts_on=None, counts_off=None):
+        """(N, S) log-likelihood per dataset: get_loglike()['group'], infer/helper.py:494-512."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            t = self._theta(theta)
+            n = t.shape[0]
+            on, off = self._counts(counts_on, n), self._counts(counts_off, n)
+            out = torch.empty((n, len(self.data)), dtype=torch.float64, device=t.device)
+            _lib.check(self._lib.elisa_b200_loglike_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), self._stream()))
+        return out
+
+    def loglike_and_grad(self, theta, counts_on=None, counts_off=None):
+        """((N, S), (N, S, P)): value and d loglike[n, s] / d theta[n, :] -- what
+        jax.value_and_grad of each dataset's log-likelihood returns upstream."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            t = self._theta(theta)
+            n = t.shape[0]
+            on, off = self._counts(counts_on, n), self._counts(counts_off, n)
+            out = torch.empty((n, len(self.data)), dtype=torch.float64, device=t.device)
+            grad = torch.empty((n, len(self.data), self._P), dtype=torch.float64, device=t.device)
+            _lib.check(self._lib.elisa_b200_loglike_grad_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), _dev_ptr(grad), self._stream()))
+        return out, grad[:, :, : self.nparam]
+
+    def deviance(self, theta, **kw):
+        """-2 * loglike per dataset (infer/helper.py:571-580)."""
+        return -2.0 * self.loglike(theta, **kw)
+
+    def deviance_total(self, theta, **kw):
+        """(N,) joint deviance (infer/helper.py:582-586)."""
+        return -2.0 * self.loglike(theta, **kw).sum(-1)
+
+    def deviance_total_and_grad(self, theta, **kw):
+        """(N,), (N, P): what Minuit's FCN / GRAD pair evaluates (infer/fit.py:474-500)."""
+        ll, g = self.loglike_and_grad(theta, **kw)
+        return -2.0 * ll.sum(-1), -2.0 * g.sum(1)
+
+    def sites(self, k: int, theta, counts_on=None, counts_off=None):
+        """Per-channel sites of dataset k with the reference's names
+        (infer/likelihood.py:206-225, 350-385): '{name}', '{name}_Non_model',
+        '{name}_Non_loglike', ['{name}_Noff_model', '{name}_Noff_loglike'], '{name}_loglike'."""
+        torch = self._torch
+        name, stat = self.names[k], self.stat[k]
+        with torch.cuda.device(self.device):
+            t = self._theta(theta)
+            n = t.shape[0]
+            on, off = self._counts(counts_on, n), self._counts(counts_off, n)
+            mk = lambda: torch.empty((n, self.n_channels[k]), dtype=torch.float64, device=t.device)
+            rate, m_on, l_on = mk(), mk(), mk()
+            with_off = stat in ('pgstat', 'wstat')
+            m_off, l_off = (mk(), mk()) if with_off else (None, None)
+            _lib.check(self._lib.elisa_b200_sites_dev(self._h, k, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(rate), _dev_ptr(m_on), _dev_ptr(l_on), _dev_ptr(m_off), _dev_ptr(l_off), self._stream()))
+        out = {name: rate, f'{name}_Non_model': m_on, f'{name}_Non_loglike': l_on}
+        if with_off:
+            out[f'{name}_Noff_model'] = m_off
+            out[f'{name}_Noff_loglike'] = l_off
+            out[f'{name}_loglike'] = l_on + l_off
+        else:
+            out[f'{name}_loglike'] = l_on
+        return out
+
+    def residual(self, theta, **kw):
+        """sqrt(-2 * point log-likelihood) over all channels (infer/helper.py:588-594)."""
+        torch = self._torch
+        pts = [self.sites(k, theta, **kw)[f'{self.names[k]}_loglike'] for k in range(len(self.data))]
+        return torch.sqrt(-2.0 * torch.cat(pts, dim=-1))
+
+    def unfold(self, k: int, theta):
+        """(N, E_k) unfolded model of dataset k (CompiledModel.eval, before the clip)."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            t = self._theta(theta)
+            out = torch.empty((t.shape[0], self.data[k].n_energies), dtype=torch.float64, device=t.device)
+            _lib.check(self._lib.elisa_b200_unfold_dev(self._h, k, _dev_ptr(t), t.shape[0], _dev_ptr(out), self._stream()))
+        return out
+
+    # -- host API (numpy in, numpy out; copies inside) -------------------------------
+    def loglike_and_grad_host(self, theta: np.ndarray, counts_on=None, counts_off=None, grad: bool = True):
+        """Same through ``elisa_b200_loglike_grad_host``: host buffers, H2D / D2H inside."""
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+        if theta.shape[1] != self.nparam:
+            raise ValueError(f'expected theta of shape (N, {self.nparam}), got {theta.shape}')
+        if self.nparam == 0:
+            theta = np.zeros((theta.shape[0], 1))
+        n = theta.shape[0]
+        on = None if counts_on is None else np.ascontiguousarray(counts_on, dtype=np.float64)
+        off = None if counts_off is None else np.ascontiguousarray(counts_off, dtype=np.float64)
+        for c in (on, off):
+            if c is not None and c.shape != (n, self.sum_channels):
+                raise ValueError(f'expected per-replica counts of shape ({n}, {self.sum_channels})')
+        ll = np.empty((n, len(self.data)))
+        g = np.empty((n, len(self.data), self._P)) if grad else None
+        _lib.check(self._lib.elisa_b200_loglike_grad_host(self._h, _ptr(theta), _ptr(on), _ptr(off), n, _ptr(ll), _ptr(g)))
+        return (ll, g[:, :, : self.nparam]) if grad else ll
+
+
+_unfold_cache: dict = {}
+
+
+def unfold_only(model: CompiledModel, egrid: np.ndarray, theta: np.ndarray, device=None) -> np.ndarray:
+    """CompiledModel.eval backend: a plan with a one-channel dummy response around the
+    given grid, cached per (model, grid)."""
+    if model.type != 'add' and False:
+        pass
+    key = (id(model), egrid.tobytes(), device)
+    lk = _unfold_cache.get(key)
+    if lk is None:
+        E = egrid.size - 1
+        d = FixedData(name='eval', photon_egrid=egrid, spec_counts=np.zeros(1), area_scale=np.ones(1),
+                      spec_exposure=1.0, response_matrix=np.zeros((E, 1)))
+        lk = _EvalOnly([d], [model], ['cstat'], device=device, chunk=128)
+        _unfold_cache.clear()
+        _unfold_cache[key] = lk
+    return lk.unfold(0, theta).cpu().numpy()
+
+
+class _EvalOnly(Likelihood):
+    """Plan used by CompiledModel.eval: multiplicative models are allowed here."""
+
+    def __init__(self, data, model, stat, device=None, chunk=0):
+        types = [m.type for m in model]
+        for m in model:
+            m.type = 'add'
+        try:
+            super().__init__(data, model, stat, device=device, chunk=chunk)
+        finally:
+            for m, t in zip(model, types):
+                m.type = t

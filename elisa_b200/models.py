@@ -1,0 +1,346 @@
+"""Host-side mirror of ``elisa.models`` for the hot path: built-in components, ``+`` / ``*``
+composition and ``Model.compile()`` -> ``CompiledModel`` (reference: models/model.py:91,
+293-303, 415; models/add.py; models/mul.py).
+
+Only what the forward-folding likelihood path needs is mirrored: component names,
+parameter names/order/defaults (the reference's ``_config`` tuples), fixed / free /
+linked parameters, the integration ``method`` of numerical-integral components and the
+composition type rules (models/model.py:1228-1258).  A compiled model is a small postfix
+program handed to the CUDA library; ``CompiledModel.eval`` runs it on the GPU.
+"""
+
+from __future__ import annotations
+
+from typing import NamedTuple, Sequence
+
+import numpy as np
+
+from . import _lib
+
+__all__ = [
+    'Band', 'BandEp', 'BentPL', 'Blackbody', 'BlackbodyRad', 'BrokenPL', 'Compt', 'CutoffPL', 'Gauss',
+    'Lorentz', 'OTTB', 'OTTS', 'PLEnFlux', 'PLPhFlux', 'PowerLaw', 'SmoothlyBrokenPL',
+    'Constant', 'Edge', 'ExpAbs', 'ExpFac', 'GAbs', 'HighECut', 'PLAbs',
+    'UniformParameter', 'Model', 'CompiledModel',
+]
+
+
+class ParamConfig(NamedTuple):
+    """models/model.py:1542-1567 (latex / unit dropped: not used on this path)."""
+
+    name: str
+    default: float
+    min: float
+    max: float
+    log: bool = False
+    fixed: bool = False
+
+
+class UniformParameter:
+    """Minimal stand-in for elisa.models.parameter.UniformParameter (parameter.py:453):
+    a named scalar with default / bounds, free or fixed.  Using ONE instance in two
+    components links them (one column of theta)."""
+
+    def __init__(self, name, default, min, max, log=False, fixed=False):
+        self.name = str(name)
+        self.default = float(default)
+        self.min = float(min)
+        self.max = float(max)
+        self.log = bool(log)
+        self.fixed = bool(fixed)
+        if not (self.min <= self.default <= self.max):
+            raise ValueError(f'default {default} of {name} outside [{min}, {max}]')
+
+    def __repr__(self):
+        return f'UniformParameter({self.name!r}, {self.default}, fixed={self.fixed})'
+
+
+class Model:
+    """Base of the model algebra (models/model.py:1204-1295)."""
+
+    type: str  # 'add' | 'mul'
+
+    def __add__(self, other):
+        return CompositeModel(self, other, '+')
+
+    def __mul__(self, other):
+        return CompositeModel(self, other, '*')
+
+    def _leaves(self):
+        raise NotImplementedError
+
+    def _postfix(self, index):
+        raise NotImplementedError
+
+    def compile(self) -> 'CompiledModel':
+        """Model.compile, models/model.py:91."""
+        return CompiledModel(self)
+
+
+class Component(Model):
+    """One built-in component (models/model.py:1570-1874 + the metaclass ctor :1334-1416):
+    each parameter argument may be None (free, reference defaults), a number (fixed to
+    it) or a UniformParameter instance."""
+
+    _kind: int
+    _config: tuple[ParamConfig, ...]
+    _numerical: bool = False
+    type = 'add'
+
+    def __init__(self, *args, method: str | None = None, **params):
+        names = [c.name for c in self._config]
+        if len(args) > len(names):
+            raise TypeError(f'{type(self).__name__} takes at most {len(names)} positional parameters')
+        for n, a in zip(names, args):
+            if n in params:
+                raise TypeError(f'{n} given twice')
+            params[n] = a
+        unknown = set(params) - set(names)
+        if unknown:
+            raise TypeError(f'{type(self).__name__}: unknown parameter(s) {sorted(unknown)}')
+        if method is None:
+            method = 'trapz'
+        if method not in _lib.METHOD:
+            raise NotImplementedError(f"integration method '{method}'")  # models/model.py:1759
+        self.method = method
+        self.name = type(self).__name__
+        self.params: dict[str, UniformParameter] = {}
+        for cfg in self._config:
+            p = params.get(cfg.name)
+            if p is None:
+                p = UniformParameter(cfg.name, cfg.default, cfg.min, cfg.max, cfg.log, cfg.fixed)
+            elif isinstance(p, (int, float, np.number)) or (isinstance(p, np.ndarray) and p.shape == ()):
+                p = UniformParameter(cfg.name, float(p), min(cfg.min, float(p)), max(cfg.max, float(p)), cfg.log, True)
+            elif isinstance(p, np.ndarray):
+                raise ValueError('scalar value is expected')
+            elif not isinstance(p, UniformParameter):
+                raise TypeError(f'{cfg.name}: expected None, a number or a UniformParameter')
+            self.params[cfg.name] = p
+        self.aux = (0.0, 0.0)
+
+    @property
+    def param_names(self):
+        return tuple(c.name for c in self._config)
+
+    def __getitem__(self, key):
+        return self.params[key]
+
+    def _leaves(self):
+        return [self]
+
+    def _postfix(self, index):
+        return [index[id(self)]]
+
+    def __repr__(self):
+        return self.name
+
+
+class CompositeModel(Model):
+    """models/model.py:1204-1295: '+' needs two additive operands; '*' forbids
+    additive * additive; the result of '*' is additive if either operand is."""
+
+    def __init__(self, lhs, rhs, op):
+        if not (isinstance(lhs, Model) and isinstance(rhs, Model)):
+            raise TypeError(
+                f"unsupported operand types for {op}: '{type(lhs).__name__}' and '{type(rhs).__name__}'"
+            )
+        if op == '+':
+            if lhs.type != 'add':
+                raise TypeError(f'{lhs} is not an additive model')
+            if rhs.type != 'add':
+                raise TypeError(f'{rhs} is not an additive model')
+            self.type = 'add'
+        elif op == '*':
+            if lhs.type == 'add' and rhs.type == 'add':
+                raise TypeError(f'unsupported model type for *: {lhs} (additive) and {rhs} (additive)')
+            self.type = 'add' if 'add' in (lhs.type, rhs.type) else 'mul'
+        else:
+            raise NotImplementedError(f'op {op}')
+        self.lhs, self.rhs, self.op = lhs, rhs, op
+
+    def _leaves(self):
+        out = list(self.lhs._leaves())
+        for c in self.rhs._leaves():
+            if all(c is not o for o in out):
+                out.append(c)
+        return out
+
+    def _postfix(self, index):
+        return self.lhs._postfix(index) + self.rhs._postfix(index) + [_lib.OP_ADD if self.op == '+' else _lib.OP_MUL]
+
+    def __repr__(self):
+        def wrap(m):
+            s = repr(m)
+            return f'({s})' if self.op == '*' and isinstance(m, CompositeModel) and m.op == '+' else s
+
+        return f'{wrap(self.lhs)} {self.op} {wrap(self.rhs)}'
+
+
+# --------------------------------------------------------------------------- built-ins
+def _component(name, kind, mtype, numerical, config, extra_args=()):
+    ns = {'_kind': kind, '_config': tuple(ParamConfig(*c) for c in config), '_numerical': numerical, 'type': mtype}
+    if extra_args:  # PLPhFlux / PLEnFlux: (emin, emax) come first (models/add.py:660-680)
+
+        def __init__(self, emin, emax, *args, **kw):
+            emin, emax = float(emin), float(emax)
+            if emin >= emax:
+                raise ValueError('emin must be less than emax')
+            Component.__init__(self, *args, **kw)
+            self.aux = (emin, emax)
+
+        ns['__init__'] = __init__
+    return type(name, (Component,), ns)
+
+
+# (name, default, min, max[, log[, fixed]]) in the reference's _config order
+Band = _component('Band', 0, 'add', True, [('alpha', -1.0, -10.0, 5.0), ('beta', -2.0, -10.0, 10.0), ('Ec', 300.0, 10.0, 1e4), ('K', 1.0, 1e-10, 1e10)])
+BandEp = _component('BandEp', 1, 'add', True, [('alpha', -1.0, -1.99, 10.0), ('beta', -2.0, -10.0, 10.0), ('Ep', 300.0, 10.0, 1e4), ('K', 1.0, 1e-10, 1e10)])
+BentPL = _component('BentPL', 2, 'add', True, [('alpha', 1.5, -3.0, 10.0), ('Eb', 5.0, 1e-2, 1e6), ('K', 1.0, 1e-10, 1e10)])
+Blackbody = _component('Blackbody', 3, 'add', True, [('kT', 3.0, 1e-4, 200.0), ('K', 1.0, 1e-10, 1e10)])
+BlackbodyRad = _component('BlackbodyRad', 4, 'add', True, [('kT', 3.0, 1e-4, 200.0), ('K', 1.0, 1e-10, 1e10)])
+BrokenPL = _component('BrokenPL', 5, 'add', False, [('alpha1', 1.0, -3.0, 10.0), ('Eb', 5.0, 1e-2, 1e6), ('alpha2', 2.0, -3.0, 10.0), ('K', 1.0, 1e-10, 1e10)])
+Compt = _component('Compt', 6, 'add', True, [('alpha', 1.0, -3.0, 10.0), ('Ep', 15.0, 0.01, 1e4), ('K', 1.0, 1e-10, 1e10)])
+CutoffPL = _component('CutoffPL', 7, 'add', True, [('alpha', 1.0, -3.0, 10.0), ('Ec', 15.0, 0.01, 1e4), ('K', 1.0, 1e-10, 1e10)])
+Gauss = _component('Gauss', 8, 'add', True, [('El', 6.5, 0.0, 1e6), ('sigma', 0.1, 0.0, 20.0), ('K', 1.0, 1e-10, 1e10)])
+Lorentz = _component('Lorentz', 9, 'add', False, [('El', 6.5, 1e-6, 1e6), ('sigma', 0.1, 1e-3, 20.0), ('K', 1.0, 1e-10, 1e10)])
+OTTB = _component('OTTB', 10, 'add', True, [('kT', 30.0, 0.1, 1e3), ('K', 1.0, 1e-10, 1e10)])
+OTTS = _component('OTTS', 11, 'add', True, [('Ec', 100.0, 1e-3, 1e3), ('K', 1.0, 1e-10, 1e10)])
+PLEnFlux = _component('PLEnFlux', 12, 'add', False, [('alpha', 1.01, -3.0, 10.0), ('F', 1e-12, 1e-30, 1e30, True)], ('emin', 'emax'))
+PLPhFlux = _component('PLPhFlux', 13, 'add', False, [('alpha', 1.01, -3.0, 10.0), ('F', 1.0, 0.01, 1e10)], ('emin', 'emax'))
+PowerLaw = _component('PowerLaw', 14, 'add', False, [('alpha', 1.01, -3.0, 10.0), ('K', 1.0, 1e-10, 1e10)])
+SmoothlyBrokenPL = _component('SmoothlyBrokenPL', 15, 'add', True, [('alpha1', 1.0, -3.0, 10.0), ('Eb', 5.0, 1e-2, 1e6), ('alpha2', 2.0, -3.0, 10.0), ('rho', 1.0, 1e-2, 1e2, False, True), ('K', 1.0, 1e-10, 1e10)])
+Constant = _component('Constant', 16, 'mul', False, [('f', 1.0, 1e-5, 1e5)])
+Edge = _component('Edge', 17, 'mul', True, [('Ec', 7.0, 0.0, 100.0), ('D', 1.0, 0.0, 10.0)])
+ExpAbs = _component('ExpAbs', 18, 'mul', True, [('Ec', 2.0, 0.0, 200.0)])
+ExpFac = _component('ExpFac', 19, 'mul', True, [('A', 1.0, 0.0, 1e6), ('f', 1.0, 0.0, 1e6), ('Ec', 0.5, 0.0, 1e6)])
+GAbs = _component('GAbs', 20, 'mul', True, [('El', 1.0, 0.0, 1e6), ('sigma', 0.01, 0.0, 20.0), ('tau', 1.0, 0.0, 1e6)])
+HighECut = _component('HighECut', 21, 'mul', True, [('Ec', 10.0, 1e-4, 1e6), ('Ef', 15.0, 1e-4, 1e6)])
+PLAbs = _component('PLAbs', 22, 'mul', False, [('alpha', 2.0, 0.0, 5.0), ('K', 1.0, 0.0, 100.0)])
+
+ADDITIVE = (Band, BandEp, BentPL, Blackbody, BlackbodyRad, BrokenPL, Compt, CutoffPL, Gauss, Lorentz, OTTB, OTTS,
+            PLEnFlux, PLPhFlux, PowerLaw, SmoothlyBrokenPL)
+MULTIPLICATIVE = (Constant, Edge, ExpAbs, ExpFac, GAbs, HighECut, PLAbs)
+
+
+# --------------------------------------------------------------------------- compiled model
+class CompiledModel:
+    """Model.compile() result (models/model.py:293-303): the free parameters in order of
+    first appearance (component order, then _config order) and the postfix program.
+
+    ``eval(egrid, params)`` mirrors CompiledModel.eval (models/model.py:415-436): ``params``
+    is an array (..., nparam), a mapping name -> array, or None (defaults); the result has
+    shape (..., E) and is computed on the GPU by ``elisa_b200_unfold_dev``."""
+
+    def __init__(self, model: Model):
+        if not isinstance(model, Model):
+            raise TypeError('model must be a Model')
+        self.model = model
+        self.type = model.type
+        self.leaves: list[Component] = model._leaves()
+        if len(self.leaves) > _lib.MAX_COMPONENTS:
+            raise NotImplementedError(f'more than {_lib.MAX_COMPONENTS} components in one model')
+        index = {id(c): i for i, c in enumerate(self.leaves)}
+        self.ops: list[int] = model._postfix(index)
+        # component display names: PowerLaw, PowerLaw_2, ... (models/model.py naming)
+        seen: dict[str, int] = {}
+        self.comp_names = []
+        for c in self.leaves:
+            seen[c.name] = seen.get(c.name, 0) + 1
+            self.comp_names.append(c.name if seen[c.name] == 1 else f'{c.name}_{seen[c.name]}')
+        self.free: list[UniformParameter] = []
+        self.params_name: list[str] = []
+        for cname, c in zip(self.comp_names, self.leaves):
+            for pname in c.param_names:
+                p = c.params[pname]
+                if not p.fixed and all(p is not q for q in self.free):
+                    self.free.append(p)
+                    self.params_name.append(f'{cname}.{pname}')
+        self.nparam = len(self.free)
+        self.params_default = np.array([p.default for p in self.free], dtype=np.float64)
+        self._plan = None
+        self._plan_key = None
+
+    # -- descriptors ---------------------------------------------------------------
+    def column_of(self, param: UniformParameter, free: Sequence[UniformParameter] | None = None) -> int:
+        free = self.free if free is None else free
+        for j, q in enumerate(free):
+            if q is param:
+                return j
+        return -1
+
+    def to_desc(self, free: Sequence[UniformParameter] | None = None):
+        """Build the C descriptor; ``free`` is the global free-parameter list of a joint
+        fit (columns of theta), defaulting to this model's own.  Returns (ModelDesc, keepalive)."""
+        comps = (_lib.ComponentDesc * len(self.leaves))()
+        for i, c in enumerate(self.leaves):
+            d = comps[i]
+            d.kind = c._kind
+            d.method = _lib.METHOD[c.method]
+            for k in range(_lib.MAX_COMP_PARAMS):
+                d.param_src[k] = -1
+                d.param_const[k] = 0.0
+            for k, pname in enumerate(c.param_names):
+                p = c.params[pname]
+                if p.fixed:
+                    d.param_const[k] = p.default
+                else:
+                    j = self.column_of(p, free)
+                    if j < 0:
+                        raise ValueError(f'{c.name}.{pname} is free but not among the fit parameters')
+                    d.param_src[k] = j
+            d.aux[0], d.aux[1] = c.aux
+        ops = (_lib.C.c_int32 * len(self.ops))(*self.ops)
+        md = _lib.ModelDesc()
+        md.n_components = len(self.leaves)
+        md.components = comps
+        md.n_ops = len(self.ops)
+        md.ops = ops
+        return md, (comps, ops)
+
+    def to_spec(self, free: Sequence[UniformParameter] | None = None):
+        """Neutral description (nested tuples) of the same program, the format the test
+        oracle consumes: ('comp', name, {pname: ('theta', j) | ('const', v)}, extras),
+        ('+', lhs, rhs), ('*', lhs, rhs)."""
+
+        def rec(m):
+            if isinstance(m, Component):
+                refs = {}
+                for pname in m.param_names:
+                    p = m.params[pname]
+                    refs[pname] = ('const', p.default) if p.fixed else ('theta', self.column_of(p, free))
+                extra = {'method': m.method}
+                if m._kind in (PLEnFlux._kind, PLPhFlux._kind):
+                    extra.update(emin=m.aux[0], emax=m.aux[1])
+                return ('comp', m.name, refs, extra)
+            return (m.op, rec(m.lhs), rec(m.rhs))
+
+        return rec(self.model)
+
+    # -- evaluation ----------------------------------------------------------------
+    def _theta_from(self, params):
+        if params is None:
+            return self.params_default.copy()
+        if isinstance(params, dict):
+            missing = [n for n in self.params_name if n not in params]
+            if missing:
+                raise ValueError(f'missing parameters: {", ".join(missing)}')
+            arrs = [np.asarray(params[n], dtype=np.float64) for n in self.params_name]
+            if not arrs:
+                raise ValueError('params are empty')
+            if any(a.shape != arrs[0].shape for a in arrs[1:]):
+                raise ValueError('all params must have the same shape')
+            return np.stack(arrs, axis=-1)
+        theta = np.atleast_1d(np.asarray(params, dtype=np.float64))
+        if theta.shape[-1] != self.nparam:
+            raise ValueError(f'expected params shape (..., {self.nparam}), got {theta.shape}')
+        return theta
+
+    def eval(self, egrid, params=None, device=None):
+        """CompiledModel.eval (models/model.py:415-436) on the GPU; returns a numpy array
+        of shape (..., E) (no clip: the clip belongs to the likelihood, likelihood.py:204)."""
+        from .likelihood import unfold_only
+
+        theta = self._theta_from(params)
+        batch = theta.shape[:-1]
+        out = unfold_only(self, np.asarray(egrid, dtype=np.float64), theta.reshape(-1, max(self.nparam, 1)), device)
+        return out.reshape(*batch, out.shape[-1])

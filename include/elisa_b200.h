@@ -1,0 +1,212 @@
+/* elisa_b200 -- C ABI of the B200-native forward-folding likelihood path.
+ *
+ * Drop-in boundary for ONE hot path of wcxve/elisa: for a batch of N parameter
+ * vectors, evaluate the built-in spectral components over each spectrum's photon
+ * energy bins, fold through the instrument response, add the scaled background, and
+ * reduce the per-channel fit statistic to one log-likelihood per (sample, spectrum),
+ * with its gradient with respect to the parameters.
+ *
+ * The reference (pure Python on JAX) has no FFI of its own for this path; the seam
+ * this library sits behind is the likelihood-factory seam
+ *   elisa/infer/helper.py:313-323,332-367   likelihood_wrapper[stat](data, model.eval)
+ *   elisa/infer/likelihood.py:184-450       chi2 / cstat / pstat / pgstat / wstat closures
+ *   elisa/models/model.py:202-219,363-436   CompiledModel.eval (+ vmap batching)
+ *   elisa/infer/helper.py:494-512,571-594   get_loglike / deviance reductions
+ *   elisa/infer/fit.py:487                  jax.grad(deviance)  (value + gradient)
+ * INTEGRATION.md shows the jax.ffi / ctypes binding a maintainer adds on the reference
+ * side.  All pointers are plain C; no torch / XLA types appear in any signature.
+ *
+ * Conventions
+ *  - all floating point data is IEEE double, C-contiguous (the reference runs with
+ *    jax_enable_x64, src/elisa/__init__.py:35);
+ *  - theta is [N, P]: row n is one parameter vector in CONSTRAINED space (transforms,
+ *    priors and log-Jacobians stay in numpyro, infer/helper.py:409-426);
+ *  - loglike is [N, S] (get_loglike()['group'], infer/helper.py:494-512); deviance is
+ *    -2 * loglike and the joint total is the row sum;
+ *  - grad is [N, S, P]: d loglike[n, s] / d theta[n, p];
+ *  - "_dev" entry points take DEVICE pointers and only enqueue work on the given
+ *    stream (no allocation, no host synchronisation); "_host" entry points take HOST
+ *    pointers, stage through the plan's pinned buffers and return when results are
+ *    in the caller's memory;
+ *  - every function returns 0 on success or a negative ELISA_ERR_* code and never
+ *    throws or aborts; NaN/Inf in results are data, not errors
+ *    (callers filter them: infer/helper.py:659-664).
+ *  - plans are immutable after creation except for their private workspace: one
+ *    in-flight call per plan (create one plan per host thread / stream).
+ */
+#ifndef ELISA_B200_H_
+#define ELISA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELISA_B200_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------- */
+#define ELISA_OK 0
+#define ELISA_ERR_INVALID -1     /* bad descriptor / argument                         */
+#define ELISA_ERR_CUDA -2        /* a CUDA runtime call failed (see last_error)       */
+#define ELISA_ERR_UNSUPPORTED -3 /* valid in the reference, not handled by this path  */
+#define ELISA_ERR_NOMEM -4
+
+/* ---- fit statistics: elisa/infer/likelihood.py:35 (Statistic literal) ----------- */
+#define ELISA_STAT_CHI2 0   /* likelihood.py:184-227 */
+#define ELISA_STAT_CSTAT 1  /* likelihood.py:230-272 */
+#define ELISA_STAT_PSTAT 2  /* likelihood.py:275-321 */
+#define ELISA_STAT_PGSTAT 3 /* likelihood.py:324-387 */
+#define ELISA_STAT_WSTAT 4  /* likelihood.py:390-450 */
+
+/* ---- built-in components: elisa/models/add.py:20-37, elisa/models/mul.py:24-35 -- */
+/* parameter order inside a component is the reference's _config order.             */
+#define ELISA_COMP_BAND 0             /* add.py:100-121  (alpha, beta, Ec, K)             */
+#define ELISA_COMP_BANDEP 1           /* add.py:177-200  (alpha, beta, Ep, K)             */
+#define ELISA_COMP_BENTPL 2           /* add.py:231-236  (alpha, Eb, K)                   */
+#define ELISA_COMP_BLACKBODY 3        /* add.py:266-286  (kT, K)                          */
+#define ELISA_COMP_BLACKBODYRAD 4     /* add.py:317-338  (kT, K)                          */
+#define ELISA_COMP_BROKENPL 5         /* add.py:378-393  (alpha1, Eb, alpha2, K)          */
+#define ELISA_COMP_COMPT 6            /* add.py:473-479  (alpha, Ep, K)                   */
+#define ELISA_COMP_CUTOFFPL 7         /* add.py:434-439  (alpha, Ec, K)                   */
+#define ELISA_COMP_GAUSS 8            /* add.py:511-516  (El, sigma, K)                   */
+#define ELISA_COMP_LORENTZ 9          /* add.py:553-561  (El, sigma, K)                   */
+#define ELISA_COMP_OTTB 10            /* add.py:590-594  (kT, K)                          */
+#define ELISA_COMP_OTTS 11            /* add.py:625-629  (Ec, K)                          */
+#define ELISA_COMP_PLENFLUX 12        /* add.py:682-708  (alpha, F)  aux = emin, emax     */
+#define ELISA_COMP_PLPHFLUX 13        /* add.py:682-708  (alpha, F)  aux = emin, emax     */
+#define ELISA_COMP_POWERLAW 14        /* add.py:40-50,655-657  (alpha, K)                 */
+#define ELISA_COMP_SMOOTHLYBROKENPL 15 /* add.py:846-861 (alpha1, Eb, alpha2, rho, K)     */
+#define ELISA_COMP_CONSTANT 16        /* mul.py:54-56    (f)                              */
+#define ELISA_COMP_EDGE 17            /* mul.py:88-94    (Ec, D)                          */
+#define ELISA_COMP_EXPABS 18          /* mul.py:116-118  (Ec)                             */
+#define ELISA_COMP_EXPFAC 19          /* mul.py:154-159  (A, f, Ec)                       */
+#define ELISA_COMP_GABS 20            /* mul.py:195-204  (El, sigma, tau)                 */
+#define ELISA_COMP_HIGHECUT 21        /* mul.py:236-240  (Ec, Ef)                         */
+#define ELISA_COMP_PLABS 22           /* mul.py:266-271  (alpha, K)                       */
+#define ELISA_COMP_COUNT 23
+
+/* numerical bin integration: elisa/models/model.py:1731-1761 */
+#define ELISA_METHOD_TRAPZ 0
+#define ELISA_METHOD_SIMPSON 1
+
+#define ELISA_MAX_COMP_PARAMS 5
+#define ELISA_MAX_COMPONENTS 8 /* leaves of one model expression              */
+#define ELISA_MAX_PARAMS 16    /* columns of theta                            */
+
+/* postfix opcodes of the model expression (models/model.py:1285-1295): an entry >= 0
+ * pushes the bin values of component #entry, ELISA_OP_ADD / ELISA_OP_MUL pop two
+ * operands and push lhs + rhs / lhs * rhs (op applied to BIN values).            */
+#define ELISA_OP_ADD -1
+#define ELISA_OP_MUL -2
+
+typedef struct ElisaComponentDesc {
+    int32_t kind;   /* ELISA_COMP_*                                                  */
+    int32_t method; /* ELISA_METHOD_* (ignored by analytic-integral components)      */
+    /* where each parameter comes from: >= 0 -> column of theta (two slots naming one
+     * column = linked parameters); -1 -> the constant in param_const (fixed values,
+     * models/model.py:2248)                                                         */
+    int32_t param_src[ELISA_MAX_COMP_PARAMS];
+    double param_const[ELISA_MAX_COMP_PARAMS];
+    double aux[2]; /* PLPhFlux / PLEnFlux: emin, emax (add.py:662-680)               */
+} ElisaComponentDesc;
+
+typedef struct ElisaModelDesc {
+    int32_t n_components;
+    const ElisaComponentDesc* components;
+    int32_t n_ops;
+    const int32_t* ops; /* postfix program, see ELISA_OP_*                           */
+} ElisaModelDesc;
+
+/* One dataset: the fields of FixedData the path reads (data/base.py:1893-1975).     */
+typedef struct ElisaSpectrumDesc {
+    int32_t n_energies; /* E = len(photon_egrid) - 1                                 */
+    int32_t n_channels; /* C                                                         */
+    const double* photon_egrid; /* [E + 1]                                           */
+    /* dense response, FixedData.response_matrix layout: [E, C] row-major; or NULL   */
+    const double* response_dense;
+    /* sparse response (FixedData.sparse_matrix, used when response_sparse): CSR by
+     * CHANNEL row of R.T = what BCSR.from_scipy_sparse(sparse.T) holds
+     * (infer/likelihood.py:177-181); or NULL                                        */
+    const int32_t* csr_indptr;  /* [C + 1]                                           */
+    const int32_t* csr_indices; /* [nnz] energy-bin index                            */
+    const double* csr_values;   /* [nnz]                                             */
+    const double* area_scale;   /* [C]                                               */
+    double exposure;            /* spec_exposure                                     */
+    int32_t stat;               /* ELISA_STAT_*                                      */
+    /* observed data; which arrays a statistic reads (likelihood.py):
+     *   chi2  : on = net_counts,  on_error = net_errors
+     *   cstat : on = spec_counts
+     *   pstat : on = spec_counts, off = back_counts, back_ratio
+     *   pgstat: on = spec_counts, off = back_counts, off_error = back_errors, back_ratio
+     *   wstat : on = spec_counts, off = back_counts, back_ratio                     */
+    const double* on_counts;  /* [C]                                                 */
+    const double* on_error;   /* [C] or NULL                                         */
+    const double* off_counts; /* [C] or NULL                                         */
+    const double* off_error;  /* [C] or NULL                                         */
+    const double* back_ratio; /* [C] or NULL                                         */
+    ElisaModelDesc model;
+} ElisaSpectrumDesc;
+
+typedef struct ElisaPlanDesc {
+    int32_t abi_version; /* ELISA_B200_ABI_VERSION                                   */
+    int32_t device;      /* CUDA device ordinal                                      */
+    int32_t n_params;    /* P, columns of theta                                      */
+    int32_t n_spectra;   /* S                                                        */
+    const ElisaSpectrumDesc* spectra;
+    int64_t chunk; /* samples processed per internal pass (0 = default); sets the
+                    * private workspace: chunk * (2 E + C) doubles for the widest
+                    * spectrum                                                       */
+    int32_t flags; /* reserved, 0                                                    */
+} ElisaPlanDesc;
+
+typedef struct ElisaPlan ElisaPlan;
+
+/* Uploads and owns every replicated constant (grids, responses, observed data, the
+ * component program) and the workspace.  Replaces the closure construction of
+ * likelihood.py:184-196 etc. (jnp.array(...) of each FixedData field).              */
+int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out);
+void elisa_b200_plan_destroy(ElisaPlan* plan);
+
+/* counts_on / counts_off: NULL, or per-replica observed data [N, sum_s C_s]
+ * (spectra concatenated along the last axis in plan order) replacing on_counts /
+ * off_counts -- what substituting '{name}_Non_data' / '{name}_Noff_data' does
+ * upstream (infer/helper.py:608-613).                                               */
+int elisa_b200_loglike_dev(ElisaPlan* plan, const double* theta, const double* counts_on,
+                           const double* counts_off, int64_t n, double* loglike, void* cuda_stream);
+int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const double* counts_on,
+                                const double* counts_off, int64_t n, double* loglike, double* grad,
+                                void* cuda_stream);
+/* per-channel sites of spectrum `spectrum` (likelihood.py:206-225): any output may be
+ * NULL.  model_on/ll_on/model_off/ll_off/rate are [N, C_s].                         */
+int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, const double* counts_on,
+                         const double* counts_off, int64_t n, double* rate, double* model_on, double* ll_on,
+                         double* model_off, double* ll_off, void* cuda_stream);
+/* the unfolded model (N, E_s) of spectrum `spectrum`: CompiledModel.eval,
+ * models/model.py:415-436, after the clip of likelihood.py:204                      */
+int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, int64_t n, double* unfold,
+                          void* cuda_stream);
+
+/* Host-buffer variants: H2D copy of theta (and counts), compute, D2H copy of the
+ * results, synchronous.  grad may be NULL (value only).                             */
+int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const double* counts_on,
+                                 const double* counts_off, int64_t n, double* loglike, double* grad);
+
+/* 1 / channel_width for the '{name}' site of sites_dev (likelihood.py:206): optional;
+ * without it `rate` is source_rate itself.                                          */
+int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const double* channel_width);
+
+/* introspection */
+/* parameter vectors processed per internal pass                                    */
+int64_t elisa_b200_plan_chunk(const ElisaPlan* plan);
+int64_t elisa_b200_plan_workspace_bytes(const ElisaPlan* plan);
+/* kernels launched by this plan since creation (all entry points)                  */
+int64_t elisa_b200_plan_launch_count(const ElisaPlan* plan);
+int elisa_b200_abi_version(void);
+/* thread-local, never NULL */
+const char* elisa_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELISA_B200_H_ */
