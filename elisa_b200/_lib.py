@@ -85,6 +85,8 @@ SYMBOLS = {
     'elisa_b200_unfold_dev': (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, _VP, _VP]),
     'elisa_b200_loglike_grad_host': (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP]),
     'elisa_b200_plan_set_channel_width': (C.c_int, [_VP, C.c_int32, _VP]),
+    'elisa_b200_plan_set_profiling': (C.c_int, [_VP, C.c_int]),
+    'elisa_b200_plan_get_profile': (C.c_int, [_VP, c_double_p, C.POINTER(C.c_int64)]),
     'elisa_b200_plan_workspace_bytes': (C.c_int64, [_VP]),
     'elisa_b200_plan_launch_count': (C.c_int64, [_VP]),
     'elisa_b200_plan_chunk': (C.c_int64, [_VP]),

@@ -536,6 +536,14 @@ struct ElisaPlan {
     bool h_counts = false;
     cudaStream_t stream = nullptr;
     std::vector<void*> owned;
+    // optional per-kernel-class device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double prof_ms[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0};
+    int64_t prof_n[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0};
 };
 
 namespace elisa {
@@ -811,6 +819,43 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
     return ELISA_OK;
 }
 
+// ---- optional device timing -----------------------------------------------------------
+struct ScopedSpan {
+    ElisaPlan* plan;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    ScopedSpan(ElisaPlan* p, int cls, cudaStream_t s) : plan(p), st(s) {
+        if (!plan->profiling) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (plan->ev_used == plan->ev_pool.size()) {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) return;
+                plan->ev_pool.push_back(e);
+            }
+            ev[i] = plan->ev_pool[plan->ev_used++];
+        }
+        cudaEventRecord(ev[0], st);
+        b = ev[1];
+        plan->spans.push_back({cls, ev[0], ev[1]});
+    }
+    ~ScopedSpan() {
+        if (b) cudaEventRecord(b, st);
+    }
+};
+
+static void drain_spans(ElisaPlan* plan) {
+    for (auto& sp : plan->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            plan->prof_ms[sp.cls] += ms;
+            plan->prof_n[sp.cls] += 1;
+        }
+    }
+    plan->spans.clear();
+    plan->ev_used = 0;
+}
+
 // ---- launches ------------------------------------------------------------------------
 static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* theta, int n_valid, int n_rows,
                          bool grad, double* U, double* dU, int ld, int e_pad, bool clip, cudaStream_t st) {
@@ -838,6 +883,7 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     const int64_t warps = (int64_t)n_rows * n_seg;
     const int blocks = (int)((warps + UNFOLD_WARPS - 1) / UNFOLD_WARPS);
     const int threads = UNFOLD_WARPS * 32;
+    ScopedSpan span(plan, ELISA_PROFILE_UNFOLD, st);
     if (!grad)
         unfold_kernel<0><<<blocks, threads, 0, st>>>(a);
     else if (plan->P <= 4)
@@ -852,8 +898,8 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
 }
 
 template <class Epi>
-static int launch_gemm(ElisaPlan* plan, const double* A, int lda, const PackedDevice& B, int m_tiles, const Epi& epi,
-                       cudaStream_t st) {
+static int launch_gemm(ElisaPlan* plan, int cls, const double* A, int lda, const PackedDevice& B, int m_tiles,
+                       const Epi& epi, cudaStream_t st) {
     static bool configured = false;  // per instantiation
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(gemm_f64_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -861,6 +907,7 @@ static int launch_gemm(ElisaPlan* plan, const double* A, int lda, const PackedDe
         configured = true;
     }
     dim3 grid(B.n_tiles, m_tiles);
+    ScopedSpan span(plan, cls, st);
     gemm_f64_kernel<Epi><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(A, lda, B.view(), epi);
     ++plan->launches;
     CUDA_TRY(cudaGetLastError());
@@ -881,7 +928,7 @@ static int launch_stat_gemm(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid
     epi.ldw = sp.C_pad;
     epi.part = plan->part;
     epi.ld_part = (int)plan->chunk;
-    return launch_gemm(plan, plan->U, sp.E_pad, sp.fwd, m_tiles, epi, st);
+    return launch_gemm(plan, ELISA_PROFILE_FOLD, plan->U, sp.E_pad, sp.fwd, m_tiles, epi, st);
 }
 
 template <bool GRAD>
@@ -917,7 +964,7 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
         eg.n_tiles = sp.bwd.n_tiles;
         eg.gpart = plan->gpart;
         eg.ld_part = (int)plan->chunk;
-        if ((rc = launch_gemm(plan, plan->W, sp.C_pad, sp.bwd, m_tiles, eg, st))) return rc;
+        if ((rc = launch_gemm(plan, ELISA_PROFILE_TFOLD, plan->W, sp.C_pad, sp.bwd, m_tiles, eg, st))) return rc;
     } else {
         if ((rc = launch_stat_gemm_any<false>(plan, sp, n, m_tiles, on, off, st))) return rc;
     }
@@ -934,6 +981,7 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     ra.used_mask = sp.model.used_mask;
     ra.loglike = loglike;
     ra.grad = grad;
+    ScopedSpan span(plan, ELISA_PROFILE_REDUCE, st);
     reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ra);
     ++plan->launches;
     CUDA_TRY(cudaGetLastError());
@@ -980,6 +1028,7 @@ void elisa_b200_plan_destroy(ElisaPlan* plan) {
     for (void* p : plan->owned) cudaFree(p);
     for (double* p : {plan->h_theta, plan->h_ll, plan->h_grad, plan->h_on, plan->h_off})
         if (p) cudaFree(p);
+    for (cudaEvent_t e : plan->ev_pool) cudaEventDestroy(e);
     if (plan->stream) cudaStreamDestroy(plan->stream);
     cudaSetDevice(dev);
     delete plan;
@@ -1123,7 +1172,7 @@ int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta,
                            true, st);
         if (rc) break;
         EpilogueStore es{plan->W, sp.C_pad};
-        rc = launch_gemm(plan, plan->U, sp.E_pad, sp.fwd, n_rows / GEMM_BM, es, st);
+        rc = launch_gemm(plan, ELISA_PROFILE_FOLD, plan->U, sp.E_pad, sp.fwd, n_rows / GEMM_BM, es, st);
         if (rc) break;
         SitesArgs a;
         a.X = plan->W;
@@ -1144,6 +1193,7 @@ int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta,
         a.model_off = model_off ? model_off + o : nullptr;
         a.ll_off = ll_off ? ll_off + o : nullptr;
         dim3 grid((sp.C + 127) / 128, nc);
+        ScopedSpan span(plan, ELISA_PROFILE_REDUCE, st);
         sites_kernel<<<grid, 128, 0, st>>>(a);
         ++plan->launches;
         if (cudaGetLastError() != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "sites_kernel launch failed");
@@ -1194,6 +1244,27 @@ int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const dou
     }
     cudaSetDevice(prev);
     return rc;
+}
+
+int elisa_b200_plan_set_profiling(ElisaPlan* plan, int enable) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    drain_spans(plan);
+    plan->profiling = enable != 0;
+    for (int i = 0; i < ELISA_PROFILE_CLASSES; ++i) {
+        plan->prof_ms[i] = 0.0;
+        plan->prof_n[i] = 0;
+    }
+    return ELISA_OK;
+}
+
+int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches) {
+    if (plan == nullptr || ms == nullptr || launches == nullptr) return fail(ELISA_ERR_INVALID, "get_profile: null");
+    drain_spans(plan);
+    for (int i = 0; i < ELISA_PROFILE_CLASSES; ++i) {
+        ms[i] = plan->prof_ms[i];
+        launches[i] = plan->prof_n[i];
+    }
+    return ELISA_OK;
 }
 
 int64_t elisa_b200_plan_workspace_bytes(const ElisaPlan* plan) { return plan ? plan->workspace_bytes : 0; }

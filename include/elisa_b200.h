@@ -196,6 +196,17 @@ int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const dou
  * without it `rate` is source_rate itself.                                          */
 int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const double* channel_width);
 
+/* Optional device timing per kernel class: while enabled every launch is bracketed by
+ * CUDA events on its stream; get_profile synchronises those events and returns the
+ * summed milliseconds and launch counts since set_profiling(plan, 1).               */
+#define ELISA_PROFILE_UNFOLD 0 /* component evaluation                              */
+#define ELISA_PROFILE_FOLD 1   /* forward fold + statistic epilogue                 */
+#define ELISA_PROFILE_TFOLD 2  /* transposed fold + gradient epilogue               */
+#define ELISA_PROFILE_REDUCE 3 /* partial reductions / per-channel sites            */
+#define ELISA_PROFILE_CLASSES 4
+int elisa_b200_plan_set_profiling(ElisaPlan* plan, int enable);
+int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches);
+
 /* introspection */
 /* parameter vectors processed per internal pass                                    */
 int64_t elisa_b200_plan_chunk(const ElisaPlan* plan);

@@ -17,6 +17,7 @@ expressed in plain Python so the oracle imports nothing from the product):
 
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .components import F64, eval_component
@@ -28,7 +29,7 @@ _WITH_BACK = ('pgstat', 'wstat')
 def _as(x):
     if isinstance(x, torch.Tensor):
         return x.to(F64)
-    return torch.as_tensor(x, dtype=F64)
+    return torch.tensor(np.asarray(x, dtype=np.float64))  # copies: inputs may be read-only views
 
 
 # --------------------------------------------------------------------------- model tree
