@@ -1,0 +1,190 @@
+"""CPU tests of the host side: model algebra mirror, descriptors, data container, the C-ABI
+library (loads, exports every declared symbol, refuses to run without a GPU), sharding."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from elisa_b200 import _lib
+from elisa_b200 import models as M
+from elisa_b200.data import FixedData
+from elisa_b200.parallel import shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ model algebra
+def test_type_rules_follow_reference():
+    """models/model.py:1228-1258."""
+    pl, bb, ea, hc = M.PowerLaw(), M.Blackbody(), M.ExpAbs(), M.HighECut()
+    assert (pl + bb).type == 'add' and (ea * pl).type == 'add' and (pl * ea).type == 'add' and (ea * hc).type == 'mul'
+    with pytest.raises(TypeError):
+        pl * bb
+    with pytest.raises(TypeError):
+        ea + pl
+    with pytest.raises(TypeError):
+        pl + ea
+    with pytest.raises(TypeError):
+        pl + 3.0
+
+
+def test_compile_orders_free_parameters_and_links():
+    K = M.UniformParameter('K', 2.0, 1e-3, 1e3)
+    m = (M.ExpAbs(Ec=0.7) * M.PowerLaw(K=K) + M.Blackbody(K=K) + M.PowerLaw()).compile()
+    assert m.params_name == ['PowerLaw.alpha', 'PowerLaw.K', 'Blackbody.kT', 'PowerLaw_2.alpha', 'PowerLaw_2.K']
+    assert m.nparam == 5 and np.allclose(m.params_default, [1.01, 2.0, 3.0, 1.01, 1.0])
+    md, keep = m.to_desc()
+    assert md.n_components == 4 and md.n_ops == 7
+    comps = keep[0]
+    assert comps[0].kind == 18 and comps[0].param_src[0] == -1 and comps[0].param_const[0] == 0.7
+    assert list(comps[1].param_src[:2]) == [0, 1] and list(comps[2].param_src[:2]) == [2, 1]  # K linked
+    assert list(keep[1]) == [0, 1, _lib.OP_MUL, 2, _lib.OP_ADD, 3, _lib.OP_ADD]
+    spec = m.to_spec()
+    assert spec[0] == '+' and spec[1][0] == '+' and spec[1][1][0] == '*'
+    assert spec[1][1][2][2]['K'] == ('theta', 1) and spec[1][2][2]['K'] == ('theta', 1)
+
+
+def test_component_constructor_semantics():
+    """models/model.py:1426-1465: None -> free default, number -> fixed, Parameter -> as given."""
+    c = M.CutoffPL(alpha=1.5, Ec=None)
+    assert c.params['alpha'].fixed and c.params['alpha'].default == 1.5
+    assert not c.params['Ec'].fixed and c.params['Ec'].default == 15.0
+    assert M.SmoothlyBrokenPL().params['rho'].fixed  # fixed=True in the reference _config
+    with pytest.raises(TypeError):
+        M.PowerLaw(beta=1.0)
+    with pytest.raises(NotImplementedError):
+        M.CutoffPL(method='romberg')
+    with pytest.raises(ValueError):
+        M.PLPhFlux(10.0, 1.0)
+    assert M.PLEnFlux(1.0, 10.0).aux == (1.0, 10.0)
+    assert {c.__name__ for c in M.ADDITIVE} == set(M.__all__[:16]) and len(M.MULTIPLICATIVE) == 7
+
+
+def test_eval_params_validation():
+    m = (M.PowerLaw() + M.Gauss()).compile()
+    with pytest.raises(ValueError):
+        m._theta_from(np.zeros((3, 4)))
+    with pytest.raises(ValueError):
+        m._theta_from({'PowerLaw.alpha': 1.0})
+    t = m._theta_from({n: np.full((2, 3), i) for i, n in enumerate(m.params_name)})
+    assert t.shape == (2, 3, 5) and t[0, 0].tolist() == [0, 1, 2, 3, 4]
+    assert m._theta_from(None).tolist() == m.params_default.tolist()
+
+
+# ------------------------------------------------------------------ data container
+def test_fixed_data_validation_and_sparse_view():
+    eg = np.linspace(1, 2, 6)
+    with pytest.raises(ValueError):
+        FixedData('x', eg, np.zeros(4), 1.0, 1.0, response_matrix=np.zeros((4, 4)))
+    with pytest.raises(ValueError):
+        FixedData('x', eg, np.zeros(4), 1.0, 1.0)
+    indptr = np.array([0, 2, 2, 3, 5]); idx = np.array([0, 1, 2, 3, 4]); val = np.arange(1.0, 6.0)
+    d = FixedData('x', eg, np.zeros(4), 1.0, 1.0, sparse_matrix=(indptr, idx, val), response_sparse=True)
+    R = d.dense_response()
+    assert R.shape == (5, 4) and R[0, 0] == 1 and R[1, 0] == 2 and R[2, 2] == 3 and R[4, 3] == 5 and R.sum() == 15
+    assert not d.has_back and d.as_mapping()['response_matrix'].shape == (5, 4)
+
+
+# ------------------------------------------------------------------ the C-ABI library
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, 'include', 'elisa_b200.h')).read()
+    declared = set(re.findall(r'\b(elisa_b200_\w+)\s*\(', header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.elisa_b200_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header(lib):
+    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16  # 4 bytes of padding before the doubles
+    assert _lib.PlanDesc.chunk.offset == 24 and _lib.SpectrumDesc.exposure.offset % 8 == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device plan creation fails loudly; nothing is computed on the CPU."""
+    desc = _lib.PlanDesc(_lib.ABI_VERSION, 0, 1, 1, None, 0, 0)
+    h = C.c_void_p()
+    rc = lib.elisa_b200_plan_create(C.byref(desc), C.byref(h))
+    assert rc < 0 and not h.value
+    assert lib.elisa_b200_last_error()
+    from elisa_b200 import ElisaB200Error, Likelihood
+
+    d = FixedData('x', np.linspace(1, 2, 5), np.ones(3), 1.0, 1.0, response_matrix=np.ones((4, 3)))
+    with pytest.raises(ElisaB200Error):
+        Likelihood([d], M.PowerLaw(), ['cstat'])
+
+
+def test_argument_errors_do_not_need_a_gpu(lib):
+    h = C.c_void_p()
+    assert lib.elisa_b200_plan_create(None, C.byref(h)) == -1
+    assert b'desc is null' in lib.elisa_b200_last_error()
+    bad = _lib.PlanDesc(99, 0, 1, 1, None, 0, 0)
+    assert lib.elisa_b200_plan_create(C.byref(bad), C.byref(h)) == -1
+    assert lib.elisa_b200_loglike_dev(None, None, None, None, 4, None, None) == -1
+    assert lib.elisa_b200_plan_launch_count(None) == 0
+
+
+# ------------------------------------------------------------------ sharding of the N axis
+def test_shard_bounds():
+    assert shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert shard_bounds(0, 2) == [(0, 0), (0, 0)]
+    for n in (1, 7, 64, 1_000_003):
+        b = shard_bounds(n, 8)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(7))
+        assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+
+    from elisa_b200.parallel import ShardedLikelihood, sharded_map
+
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    theta = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3)
+    counts = torch.arange(n * 2, dtype=torch.float64).reshape(n, 2)
+
+    class Fake:  # stands in for elisa_b200.Likelihood: same call signature, CPU arithmetic
+        calls = []
+
+        def loglike_and_grad(self, t, on=None, off=None):
+            Fake.calls.append(len(t))
+            return (t.sum(1, keepdim=True) + on.sum(1, keepdim=True)), t.unsqueeze(1) * 2.0
+
+        def loglike(self, t, on=None, off=None):
+            return t.sum(1, keepdim=True)
+
+    sl = ShardedLikelihood(Fake())
+    ll, g = sl.loglike_and_grad(theta, counts)
+    local = sl.loglike(theta, gather=False)
+    same = sharded_map(lambda t: t * 1.0, (theta,), n)
+    ok = (torch.equal(ll, theta.sum(1, keepdim=True) + counts.sum(1, keepdim=True)) and torch.equal(g, theta.unsqueeze(1) * 2.0)
+          and torch.equal(same, theta))
+    q.put((rank, bool(ok), Fake.calls[0], local.shape[0]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n', [7, 64])
+def test_sharded_map_gloo_world2(n):
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    b = shard_bounds(n, 2)
+    for rank, ok, first_call, local_rows in res:
+        assert ok
+        assert first_call == b[rank][1] - b[rank][0] == local_rows

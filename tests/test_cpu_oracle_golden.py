@@ -1,0 +1,190 @@
+"""CPU tests: the oracle against the golden vectors produced by executing the reference's
+own source (tools/make_golden.py), and against the closed forms the reference's test-suite
+pins."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.components import ADDITIVE, MULTIPLICATIVE
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+F64 = torch.float64
+
+
+def _params(name, theta):
+    names = (ADDITIVE.get(name) or MULTIPLICATIVE.get(name))[0]
+    return {k: torch.tensor([[v]], dtype=F64) for k, v in zip(names, theta)}
+
+
+@pytest.fixture(scope='module')
+def comp_gold():
+    return np.load(os.path.join(GOLD, 'components.npz'))
+
+
+@pytest.fixture(scope='module')
+def like_gold():
+    return np.load(os.path.join(GOLD, 'likelihood.npz'))
+
+
+def test_golden_covers_every_builtin(comp_gold):
+    assert set(comp_gold['names']) == set(ADDITIVE) | set(MULTIPLICATIVE)
+
+
+@pytest.mark.parametrize('name', sorted(set(ADDITIVE) | set(MULTIPLICATIVE)))
+def test_component_bins_match_reference_source(comp_gold, name):
+    thetas = comp_gold[f'{name}/theta']
+    for gname in ('wide', 'kev'):
+        grid = torch.tensor(comp_gold[f'grid_{gname}'])
+        for method in ('trapz', 'simpson'):
+            key = f'{name}/{gname}/{method}'
+            if key not in comp_gold:
+                continue
+            gold = comp_gold[key]
+            kw = dict(emin=1.0, emax=10.0) if name in ('PLPhFlux', 'PLEnFlux') else {}
+            for t, g in zip(thetas, gold):
+                with np.errstate(all='ignore'):
+                    got = oracle.eval_component(name, grid.unsqueeze(0), _params(name, t), method=method, **kw)[0].numpy()
+                # differences of E^(1-a)/(1-a) amplify the last-ulp libm difference by
+                # |F| / |dF| (~1e4 on these grids at the default alpha = 1.01)
+                scale = np.nanmax(np.abs(g[np.isfinite(g)])) if np.isfinite(g).any() else 1.0
+                np.testing.assert_allclose(got, g, rtol=2e-11, atol=1e-14 * scale, equal_nan=True, err_msg=key)
+
+
+def _data(g):
+    keys = ('photon_egrid', 'response_matrix', 'spec_counts', 'net_counts', 'net_errors', 'back_counts', 'back_errors',
+            'back_ratio', 'channel_width', 'area_scale')
+    d = {k: g[k] for k in keys}
+    d['spec_exposure'] = float(g['spec_exposure'])
+    return d
+
+
+SPEC = ('+', ('comp', 'CutoffPL', {'alpha': ('theta', 0), 'Ec': ('theta', 1), 'K': ('theta', 2)}, {'method': 'trapz'}),
+        ('comp', 'Blackbody', {'kT': ('theta', 3), 'K': ('theta', 4)}, {'method': 'trapz'}))
+SITES = {'g': 'rate', 'g_Non_model': 'Non_model', 'g_Non_loglike': 'Non_loglike', 'g_loglike': 'loglike',
+         'g_Noff_model': 'Noff_model', 'g_Noff_loglike': 'Noff_loglike'}
+
+
+@pytest.mark.parametrize('stat', oracle.STATISTICS)
+def test_statistic_sites_match_reference_closures(like_gold, stat):
+    theta = torch.tensor(like_gold['theta'])
+    got = oracle.sites(stat, _data(like_gold), SPEC, theta)
+    seen = 0
+    for site, mine in SITES.items():
+        key = f'{stat}/{site}'
+        if key not in like_gold:
+            assert mine not in got or mine == 'loglike'
+            continue
+        ref = like_gold[key]
+        np.testing.assert_allclose(got[mine].numpy(), ref, rtol=1e-12, atol=1e-13 * np.abs(ref).max(), err_msg=key)
+        seen += 1
+    assert seen >= 4
+
+
+@pytest.mark.parametrize('stat', oracle.STATISTICS)
+def test_autograd_matches_differences_of_reference(like_gold, stat):
+    theta = like_gold['theta']
+    _, g = oracle.loglike_and_grad([stat], [_data(like_gold)], SPEC, torch.tensor(theta))
+    fd = like_gold[f'{stat}/fd_grad']
+    g = g.numpy()[1:, 0]  # row 0 sits on the lower clip: its finite differences are noise
+    fd = fd[1:]
+    if stat == 'wstat':
+        # channels with n_off = 0 and b = 0 make autodiff return NaN (xlogy(0, 0)), in
+        # JAX as in torch; the CUDA path returns the finite derivative (tests/test_gpu_*)
+        assert np.isnan(g).all()
+        return
+    np.testing.assert_allclose(g, fd, rtol=5e-6, atol=1e-7 * np.abs(fd).max())
+
+
+def test_profile_backgrounds_match_reference(like_gold):
+    s, n_on, n_off = (torch.tensor(like_gold[f'bg/{k}']) for k in ('s', 'n_on', 'n_off'))
+    w = oracle.wstat_background(s, n_on, n_off, torch.tensor(0.4, dtype=F64)).numpy()
+    np.testing.assert_allclose(w, like_gold['bg/wstat'], rtol=1e-14, atol=0)
+    p = oracle.pgstat_background(s, n_on, torch.tensor(like_gold['bg/b_est']), torch.tensor(2.0), torch.tensor(0.4, dtype=F64)).numpy()
+    np.testing.assert_allclose(p, like_gold['bg/pgstat'], rtol=1e-14, atol=0)
+
+
+# ------------------------------------------------------------------ closed forms the reference tests pin
+def test_powerlaw_integral_closed_form():
+    """tests/conftest.py:23-31 (powerlaw_fn): K (E1^(1-a) - E0^(1-a)) / (1-a), log form at a = 1."""
+    eg = np.linspace(1.0, 100.0, 201)
+    for alpha in (0.0, 0.5, 1.0, 1.7, 2.0, 3.5):
+        got = oracle.eval_component('PowerLaw', torch.tensor(eg).unsqueeze(0),
+                                    {'alpha': torch.tensor([[alpha]], dtype=F64), 'K': torch.tensor([[10.0]], dtype=F64)})[0].numpy()
+        if alpha == 1.0:
+            ref = 10.0 * np.log(eg[1:] / eg[:-1])
+        else:
+            ref = 10.0 * (eg[1:] ** (1 - alpha) - eg[:-1] ** (1 - alpha)) / (1 - alpha)
+        np.testing.assert_allclose(got, ref, rtol=1e-12)
+
+
+def _trivial_fit():
+    """tests/conftest.py:45-71: PowerLaw(alpha = 0 fixed, K = 10), 200 linear bins 1-100 keV,
+    identity response, exposure 50, Poisson counts, seed 42."""
+    eg = np.linspace(1.0, 100.0, 201)
+    de = np.diff(eg)
+    expo = 50.0
+    counts = np.random.default_rng(42).poisson(10.0 * de * expo).astype(float)
+    data = dict(photon_egrid=eg, response_matrix=np.eye(200), area_scale=np.ones(200), spec_exposure=expo,
+                channel_width=de, spec_counts=counts)
+    spec = ('comp', 'PowerLaw', {'alpha': ('const', 0.0), 'K': ('theta', 0)}, {})
+    return data, spec, counts, de, expo
+
+
+def test_trivial_cstat_fit_closed_form():
+    """tests/test_fit.py:24-42: K_hat = mean(counts / dE / exposure); sigma = sqrt(K_hat / nbins / exposure / dE)."""
+    data, spec, counts, de, expo = _trivial_fit()
+    k_hat = np.mean(counts / de / expo)
+    ll, g = oracle.loglike_and_grad(['cstat'], [data], spec, torch.tensor([[k_hat]]))
+    assert abs(g[0, 0, 0].item()) < 1e-9 * counts.sum()  # stationary at the closed-form MLE
+    h = 1e-3 * k_hat
+    gp = oracle.loglike_and_grad(['cstat'], [data], spec, torch.tensor([[k_hat + h]]))[1][0, 0, 0].item()
+    gm = oracle.loglike_and_grad(['cstat'], [data], spec, torch.tensor([[k_hat - h]]))[1][0, 0, 0].item()
+    sigma = 1.0 / np.sqrt(-(gp - gm) / (2 * h))
+    assert np.isclose(sigma, np.sqrt(k_hat / 200 / expo / de[0]), rtol=1e-5)
+
+
+def test_deviance_identities():
+    """-2 loglike of cstat is the C-stat deviance 2 sum[mu - n + n ln(n / mu)]
+    (plot/residuals.py:406-427); of chi2 it is sum ((n - mu) / sigma)^2."""
+    data, spec, counts, de, expo = _trivial_fit()
+    theta = torch.tensor([[8.0], [10.0], [13.0]])
+    mu = theta.numpy() * de * expo
+    ll = oracle.loglike(['cstat'], [data], spec, theta).numpy()[:, 0]
+    with np.errstate(all='ignore'):
+        term = np.where(counts > 0, counts * np.log(counts / mu), 0.0)
+    np.testing.assert_allclose(-2 * ll, 2 * np.sum(mu - counts + term, axis=1), rtol=1e-12)
+    data2 = dict(data, net_counts=counts, net_errors=np.sqrt(counts + 1.0))
+    ll2 = oracle.loglike(['chi2'], [data2], spec, theta).numpy()[:, 0]
+    np.testing.assert_allclose(-2 * ll2, np.sum(((counts - mu) / np.sqrt(counts + 1.0)) ** 2, axis=1), rtol=1e-12)
+
+
+def test_profile_background_is_stationary_in_the_interior():
+    """wstat / pgstat: the profiled b zeroes dL/db where no boundary branch is active."""
+    s = torch.tensor([3.0, 8.0, 40.0], dtype=F64)
+    n_on = torch.tensor([5.0, 12.0, 30.0], dtype=F64)
+    n_off = torch.tensor([7.0, 9.0, 25.0], dtype=F64)
+    a = torch.tensor(0.4, dtype=F64)
+    b = oracle.wstat_background(s, n_on, n_off, a).clone().requires_grad_(True)
+    L = (torch.special.xlogy(n_on, s + a * b) - (s + a * b) + torch.special.xlogy(n_off, b) - b).sum()
+    (db,) = torch.autograd.grad(L, b)
+    assert torch.all(db.abs() < 1e-12)
+    sig = torch.tensor(2.0, dtype=F64)
+    b = oracle.pgstat_background(s, n_on, n_off, sig, a).clone().requires_grad_(True)
+    L = (torch.special.xlogy(n_on, s + a * b) - (s + a * b) - 0.5 * ((n_off - b) / sig) ** 2).sum()
+    (db,) = torch.autograd.grad(L, b)
+    assert torch.all(db.abs() < 1e-12)
+
+
+def test_every_builtin_is_finite_on_the_reference_grid():
+    """tests/test_model.py:178-195: all add / mul built-ins evaluate finite on geomspace(1e-4, 1e9, 1301)."""
+    grid = torch.tensor(np.geomspace(1e-4, 1e9, 1301)).unsqueeze(0)
+    for table in (ADDITIVE, MULTIPLICATIVE):
+        for name, (pnames, defaults, *_rest) in table.items():
+            kw = dict(emin=1.0, emax=10.0) if name in ('PLPhFlux', 'PLEnFlux') else {}
+            p = {k: torch.tensor([[v]], dtype=F64) for k, v in zip(pnames, defaults)}
+            v = oracle.eval_component(name, grid, p, **kw)
+            assert torch.isfinite(v).all(), name
