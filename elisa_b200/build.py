@@ -9,15 +9,38 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'elisa_b200.cu')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('elisa_b200.cu', 'components.cuh', 'dual.cuh', 'gemm_f64.cuh', 'stats.cuh')]
-DEPS.append(os.path.join(os.path.dirname(HERE), 'include', 'elisa_b200.h'))
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('elisa_b200.cu', 'components.cuh', 'dual.cuh', 'gemm_f64.cuh', 'stats.cuh', 'unfold_skel.cuh')]
+INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
+DEPS.append(os.path.join(INCLUDE, 'elisa_b200.h'))
+# headers handed to NVRTC at run time travel inside the library as string literals
+EMBED = {
+    'embedded_elisa_b200_h.inc': os.path.join(INCLUDE, 'elisa_b200.h'),
+    'embedded_dual_cuh.inc': os.path.join(HERE, 'csrc', 'dual.cuh'),
+    'embedded_components_cuh.inc': os.path.join(HERE, 'csrc', 'components.cuh'),
+    'embedded_unfold_skel_cuh.inc': os.path.join(HERE, 'csrc', 'unfold_skel.cuh'),
+}
 LIB = os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-O3', '-lineinfo', '-std=c++17',
-    '-Xcompiler', '-fPIC', '-shared',
+    '-Xcompiler', '-fPIC', '-shared', '-I', INCLUDE,
 ]
+
+
+def embed_sources() -> None:
+    """csrc/*.cuh -> csrc/_gen/embedded_*.inc (C++ raw string literals, split below the
+    compilers' per-literal limit)."""
+    out_dir = os.path.join(HERE, 'csrc', '_gen')
+    os.makedirs(out_dir, exist_ok=True)
+    for name, path in EMBED.items():
+        text = open(path).read()
+        chunks = [text[i:i + 8000] for i in range(0, len(text), 8000)]
+        body = '\n'.join(f'R"ELISASRC({c})ELISASRC"' for c in chunks) + '\n'
+        dst = os.path.join(out_dir, name)
+        if not os.path.exists(dst) or open(dst).read() != body:
+            with open(dst, 'w') as f:
+                f.write(body)
 
 
 def find_nvcc() -> str:
@@ -39,7 +62,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, '-o', LIB, SRC]
+    embed_sources()
+    cmd = [find_nvcc(), *NVCC_FLAGS, '-I', os.path.join(HERE, 'csrc', '_gen'), '-o', LIB, SRC, '-ldl']
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

@@ -11,7 +11,7 @@
 // Powers of an energy are evaluated as exp(expo * ln E) with ln E tabulated per grid at
 // plan creation (relative deviation from jnp.power <= |expo ln E| * 2^-53).
 #pragma once
-#include "../../include/elisa_b200.h"
+#include "elisa_b200.h"
 #include "dual.cuh"
 
 namespace elisa {
@@ -528,15 +528,11 @@ __device__ __forceinline__ void leaf_pre(double* scratch, const double* aux) {
     for (int k = 0; k < C::NC; ++k) Flat<T>::put(scratch + ELISA_MAX_COMP_PARAMS + k * Flat<T>::SIZE, c[k]);
 }
 
-// Bin value of leaf KIND for bin e (valid on lanes 0..30 of the pass, for e < E).
+// Bin value of leaf KIND for bin e (valid on lanes 0..30 of the pass, for e < E), given the
+// parameters p and the hoisted constants c.
 template <int KIND, typename T>
-__device__ __forceinline__ T leaf_bin(const double* scratch, int method, const GridView& gv, int e) {
+__device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, const GridView& gv, int e) {
     using C = Comp<KIND>;
-    T p[C::NP], c[C::NC];
-#pragma unroll
-    for (int k = 0; k < C::NP; ++k) p[k] = Flat<T>::seed(scratch[k], k);
-#pragma unroll
-    for (int k = 0; k < C::NC; ++k) c[k] = Flat<T>::get(scratch + ELISA_MAX_COMP_PARAMS + k * Flat<T>::SIZE);
     const int ec = e <= gv.E ? e : gv.E;  // lanes beyond the grid re-evaluate the last edge
     const double E0 = gv.egrid[ec], l0 = gv.lngrid[ec];
     T g0[C::NG], g1[C::NG];
@@ -558,6 +554,18 @@ __device__ __forceinline__ T leaf_bin(const double* scratch, int method, const G
         const double factor = add ? 0.5 * (E1 - E0) : 0.5;
         return factor * (g0[0] + g1[0]);
     }
+}
+
+// Same, with p and c decoded from the interpreter's shared-memory scratch slot.
+template <int KIND, typename T>
+__device__ __forceinline__ T leaf_bin(const double* scratch, int method, const GridView& gv, int e) {
+    using C = Comp<KIND>;
+    T p[C::NP], c[C::NC];
+#pragma unroll
+    for (int k = 0; k < C::NP; ++k) p[k] = Flat<T>::seed(scratch[k], k);
+#pragma unroll
+    for (int k = 0; k < C::NC; ++k) c[k] = Flat<T>::get(scratch + ELISA_MAX_COMP_PARAMS + k * Flat<T>::SIZE);
+    return leaf_bin_pc<KIND, T>(p, c, method, gv, e);
 }
 
 }  // namespace elisa

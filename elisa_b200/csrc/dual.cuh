@@ -6,8 +6,10 @@
 // `Dual<NP>` the value and its NP partial derivatives in one pass (transcendentals
 // are evaluated once and shared by value and tangent).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <math.h>
+#endif
 
 namespace elisa {
 

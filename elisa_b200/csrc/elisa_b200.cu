@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -24,11 +25,18 @@
 #include <string>
 #include <vector>
 
-#include "../../include/elisa_b200.h"
+#include <dlfcn.h>
+#include <nvrtc.h>  // types only: libnvrtc is opened lazily with dlopen
+
+#include <map>
+#include <mutex>
+
+#include "elisa_b200.h"
 #include "components.cuh"
 #include "dual.cuh"
 #include "gemm_f64.cuh"
 #include "stats.cuh"
+#include "unfold_skel.cuh"
 
 namespace elisa {
 
@@ -55,19 +63,7 @@ struct ModelDev {
 
 struct UnfoldArgs {
     ModelDev model;
-    GridView gv;
-    const double* theta;  // [N, P]
-    int32_t P;
-    int32_t n_valid;   // rows < n_valid are evaluated, rows in [n_valid, n_rows) are zero-filled
-    int32_t n_rows;
-    int32_t n_seg;     // segments the energy axis is split into (one warp per (row, segment))
-    int32_t seg_len;   // bins per segment
-    int32_t ld;        // leading dimension of U / dU rows
-    int32_t e_pad;     // columns [E, e_pad) are zero-filled
-    int32_t clip;      // apply clip(unfold, 1e-300, 1e300) (likelihood.py:204)
-    double* U;         // [n_rows, ld]
-    double* dU;        // [P, n_rows, ld] or nullptr
-    int64_t plane;     // n_rows * ld
+    UnfoldCore core;
 };
 
 // per-channel observed data, padded to C_pad with benign values
@@ -115,13 +111,15 @@ __device__ __forceinline__ typename StackT<PU>::type scatter_leaf(const Dual<NPK
     X(ELISA_COMP_EDGE) X(ELISA_COMP_EXPABS) X(ELISA_COMP_EXPFAC) X(ELISA_COMP_GABS) X(ELISA_COMP_HIGHECUT)         \
     X(ELISA_COMP_PLABS)
 
-constexpr int UNFOLD_WARPS = 4;
-
+// Ahead-of-time interpreter: runs any model program without runtime compilation (the
+// fallback when NVRTC is unavailable, and the cross-check of the specialised kernels).
 template <int PU>
-__global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_constant__ UnfoldArgs a) {
+__global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_constant__ UnfoldArgs args) {
     using TT = typename StackT<PU>::type;
     constexpr bool GRAD = PU > 0;
     __shared__ double s_scratch[UNFOLD_WARPS][ELISA_MAX_COMPONENTS][LEAF_SCRATCH];
+    const UnfoldCore& a = args.core;
+    const ModelDev& model = args.model;
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t wid = (int64_t)blockIdx.x * UNFOLD_WARPS + wib;
@@ -131,30 +129,24 @@ __global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_
     const int e_lo = seg * a.seg_len;
     const int e_hi = min(e_lo + a.seg_len, E);
     const bool last_seg = seg == a.n_seg - 1;
-    double* Urow = a.U + (size_t)row * a.ld;
+    const size_t row_off = (size_t)row * a.ld;
 
     if (row >= a.n_valid) {  // padding rows: zeros, so that the fold sees finite operands
-        const int hi = last_seg ? a.e_pad : e_hi;
-        for (int e = e_lo + lane; e < hi; e += 32) {
-            Urow[e] = 0.0;
-            if (GRAD)
-                for (int j = 0; j < a.P; ++j)
-                    if ((a.model.used_mask >> j) & 1u) a.dU[j * a.plane + (size_t)row * a.ld + e] = 0.0;
-        }
+        unfold_zero(a, row_off, e_lo, last_seg ? a.e_pad : e_hi, lane, GRAD);
         return;
     }
 
     // ---- per-parameter-vector scalars, once per warp -------------------------------
     double(*scr)[LEAF_SCRATCH] = s_scratch[wib];
     const double* th = a.theta + (size_t)row * a.P;
-    for (int i = 0; i < a.model.n_leaf; ++i) {
-        const LeafDev& L = a.model.leaf[i];
+    for (int i = 0; i < model.n_leaf; ++i) {
+        const LeafDev& L = model.leaf[i];
         if (lane < ELISA_MAX_COMP_PARAMS)
             scr[i][lane] = lane < L.np ? (L.src[lane] >= 0 ? th[L.src[lane]] : L.cst[lane]) : 0.0;
     }
     __syncwarp();
-    for (int i = 0; i < a.model.n_leaf; ++i) {
-        const LeafDev& L = a.model.leaf[i];
+    for (int i = 0; i < model.n_leaf; ++i) {
+        const LeafDev& L = model.leaf[i];
         double tmp[LEAF_SCRATCH];
 #pragma unroll
         for (int k = 0; k < ELISA_MAX_COMP_PARAMS; ++k) tmp[k] = scr[i][k];
@@ -180,10 +172,10 @@ __global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_
         const int e = e0 + lane;
         TT stk[ELISA_MAX_COMPONENTS];
         int sp = 0;
-        for (int o = 0; o < a.model.n_ops; ++o) {
-            const int op = a.model.ops[o];
+        for (int o = 0; o < model.n_ops; ++o) {
+            const int op = model.ops[o];
             if (op >= 0) {
-                const LeafDev& L = a.model.leaf[op];
+                const LeafDev& L = model.leaf[op];
                 TT val;
                 switch (L.kind) {
 #define X(KIND)                                                                                            \
@@ -206,39 +198,35 @@ __global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_
                 stk[sp - 1] = (op == ELISA_OP_ADD) ? lhs + rhs : lhs * rhs;
             }
         }
-        const TT res = stk[0];
-        if (lane < 31 && e < e_hi) {
-            const double v = value(res);
-            bool pass = true;
-            double u = v;
-            if (a.clip) {
-                pass = (v >= 1e-300) && (v <= 1e300);
-                u = fmin(fmax(v, 1e-300), 1e300);  // NaN stays NaN through the statistic
-                if (v != v) u = v;
-            }
-            Urow[e] = u;
-            if constexpr (GRAD) {
-#pragma unroll
-                for (int j = 0; j < PU; ++j)
-                    if (j < a.P && ((a.model.used_mask >> j) & 1u))
-                        a.dU[j * a.plane + (size_t)row * a.ld + e] = pass ? res.d[j] : 0.0;
-            }
-        }
+        if (lane < 31 && e < e_hi) unfold_store<TT>(a, row_off + e, stk[0]);
     }
-    if (last_seg) {
-        for (int e = E + lane; e < a.e_pad; e += 32) {
-            Urow[e] = 0.0;
-            if (GRAD)
-                for (int j = 0; j < a.P; ++j)
-                    if ((a.model.used_mask >> j) & 1u) a.dU[j * a.plane + (size_t)row * a.ld + e] = 0.0;
-        }
-    }
+    if (last_seg) unfold_zero(a, row_off, E, a.e_pad, lane, GRAD);
 }
 
 // ======================================================================================
 // 2. statistic epilogue of the forward fold
 // ======================================================================================
+// The accumulator tile is parked in shared memory (the pipeline buffers are free by then)
+// and re-read ROW-WISE: thread t owns row t of the 128 x 64 tile and walks its 64 channels,
+// so the row sum is a private register (no shuffles, fixed order), the code is one compact
+// loop (the fully unrolled register version overflowed the instruction cache) and W
+// leaves through coalesced 512-byte row segments.
 // partial log-likelihoods: part[tile_n * ld_part + row]
+constexpr int EPI_LD = GEMM_BN + 1;  // 65 doubles: odd stride -> conflict-free row-wise access
+static_assert(GEMM_BM * EPI_LD * 8 <= GEMM_SMEM_BYTES, "epilogue tile must fit the pipeline buffers");
+
+__device__ __forceinline__ void park_tile(const AccFrag& acc, double* tile, int warp_m, int warp_n, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double* row = tile + (warp_m * 64 + 8 * i + g) * EPI_LD + warp_n * 32 + 4 * q;
+#pragma unroll
+        for (int l = 0; l < 2; ++l)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) row[16 * l + cc] = acc.get(i, l, cc);
+    }
+}
+
 template <int STAT, bool GRAD>
 struct EpilogueStat {
     ChanArrays ch;
@@ -252,79 +240,62 @@ struct EpilogueStat {
     double* part;
     int32_t ld_part;
 
-    __device__ __forceinline__ void operator()(AccFrag& acc, double* smem, int, int tile_n, int row0, int col0,
+    __device__ __forceinline__ void operator()(AccFrag& acc, double* smem, int tile_m, int tile_n, int, int,
                                                int warp_m, int warp_n, int lane) const {
-        double rs[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rs[i] = 0.0;
-#pragma unroll
-        for (int l = 0; l < 2; ++l) {
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int col = col0 + 16 * l + cc;
-                const bool cvalid = col < C;
-                ChannelData d;
-                const double sc = ch.scale[col];
-                d.on = ch.on[col];
-                d.gof_on = ch.gof_on[col];
-                d.off = d.sigma = d.ratio = d.gof_off = 0.0;
-                if (STAT == ELISA_STAT_CHI2) d.sigma = ch.sigma[col];
-                if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
-                    d.off = ch.off[col];
-                    d.ratio = ch.ratio[col];
-                }
-                if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[col];
-                if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[col];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = row0 + 8 * i;
-                    if (counts_on != nullptr && cvalid && row < n_valid) {
-                        d.on = counts_on[(size_t)row * ld_counts + col];
-                        if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
-                    }
-                    if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && counts_off != nullptr && cvalid &&
-                        row < n_valid) {
-                        d.off = counts_off[(size_t)row * ld_counts + col];
-                        if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
-                    }
-                    const double x = acc.get(i, l, cc) * sc;
-                    double dx = 0.0;
-                    const double ll = stat_channel<STAT, GRAD>(x, d, dx);
-                    rs[i] += cvalid ? ll : 0.0;
-                    if (GRAD) acc.set(i, l, cc, cvalid ? dx * sc : 0.0);
-                }
-            }
-        }
-        if (GRAD) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double* wrow = W + (size_t)(row0 + 8 * i) * ldw + col0;
-#pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                    double2 lo, hi;
-                    lo.x = acc.get(i, l, 0);
-                    lo.y = acc.get(i, l, 1);
-                    hi.x = acc.get(i, l, 2);
-                    hi.y = acc.get(i, l, 3);
-                    *reinterpret_cast<double2*>(wrow + 16 * l) = lo;
-                    *reinterpret_cast<double2*>(wrow + 16 * l + 2) = hi;
-                }
-            }
-        }
-        // row sums: over the quad (4 lanes share a row), then over the two column warps
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
-            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
-        }
-        double* red = smem;  // [2][128]
-        if ((lane & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) red[warp_n * GEMM_BM + warp_m * 64 + 8 * i + (lane >> 2)] = rs[i];
-        }
+        double* tile = smem;
+        park_tile(acc, tile, warp_m, warp_n, lane);
         __syncthreads();
-        const int m0 = row0 - warp_m * 64 - (lane >> 2);
-        part[(size_t)tile_n * ld_part + m0 + threadIdx.x] = red[threadIdx.x] + red[GEMM_BM + threadIdx.x];
+        const int t = threadIdx.x;
+        const int row = tile_m * GEMM_BM + t;
+        const int c0 = tile_n * GEMM_BN;
+        const int n_cols = min(GEMM_BN, C - c0);  // real channels of this tile
+        double* xr = tile + t * EPI_LD;
+        const bool rvalid = row < n_valid;
+        const double* con = (counts_on != nullptr && rvalid) ? counts_on + (size_t)row * ld_counts + c0 : nullptr;
+        const double* coff = (counts_off != nullptr && rvalid) ? counts_off + (size_t)row * ld_counts + c0 : nullptr;
+        double rs = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < GEMM_BN; ++j) {
+            const int col = c0 + j;
+            ChannelData d;
+            const double sc = ch.scale[col];
+            d.on = ch.on[col];
+            d.gof_on = ch.gof_on[col];
+            d.off = d.sigma = d.ratio = d.gof_off = 0.0;
+            if (STAT == ELISA_STAT_CHI2) d.sigma = ch.sigma[col];
+            if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+                d.off = ch.off[col];
+                d.ratio = ch.ratio[col];
+            }
+            if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[col];
+            if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[col];
+            const bool cvalid = j < n_cols;
+            if (con != nullptr && cvalid) {
+                d.on = con[j];
+                if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
+            }
+            if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr && cvalid) {
+                d.off = coff[j];
+                if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
+            }
+            const double x = xr[j] * sc;
+            double dx = 0.0;
+            const double ll = stat_channel<STAT, GRAD>(x, d, dx);
+            rs += cvalid ? ll : 0.0;
+            if (GRAD) xr[j] = cvalid ? dx * sc : 0.0;
+        }
+        part[(size_t)tile_n * ld_part + row] = rs;
+        if (GRAD) {
+            __syncthreads();
+            // coalesced copy of the W tile: each warp streams whole 512-byte row segments
+            const int warp = t >> 5;
+            for (int r = warp; r < GEMM_BM; r += GEMM_THREADS / 32) {
+                const double* src = tile + r * EPI_LD;
+                double* dst = W + (size_t)(tile_m * GEMM_BM + r) * ldw + c0;
+                dst[lane] = src[lane];
+                dst[lane + 32] = src[lane + 32];
+            }
+        }
     }
 };
 
@@ -508,6 +479,7 @@ struct SpectrumPlan {
     PackedDevice fwd, bwd;   // R [E, C] tiled over C ; R^T [C, E] tiled over E
     int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
     int64_t nnz = 0;
+    const struct JitKernels* jit = nullptr;  // runtime-specialised unfold (nullptr: interpreter)
     GridView grid_view() const { return GridView{egrid, lngrid, emid, lnmid, E}; }
     ChanArrays chan_view() const {
         return ChanArrays{chan, chan + C_pad, chan + 2 * C_pad, chan + 3 * C_pad,
@@ -819,6 +791,183 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
     return ELISA_OK;
 }
 
+// ======================================================================================
+// runtime specialisation of the unfold kernel (NVRTC)
+// ======================================================================================
+struct JitKernels {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t val = nullptr, grad = nullptr;
+};
+
+static const char* const k_src_elisa_h =
+#include "embedded_elisa_b200_h.inc"
+    ;
+static const char* const k_src_dual =
+#include "embedded_dual_cuh.inc"
+    ;
+static const char* const k_src_components =
+#include "embedded_components_cuh.inc"
+    ;
+static const char* const k_src_skel =
+#include "embedded_unfold_skel_cuh.inc"
+    ;
+
+struct NvrtcApi {
+    void* handle = nullptr;
+    decltype(&nvrtcCreateProgram) create = nullptr;
+    decltype(&nvrtcCompileProgram) compile = nullptr;
+    decltype(&nvrtcDestroyProgram) destroy = nullptr;
+    decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+    decltype(&nvrtcGetCUBIN) cubin = nullptr;
+    decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+    decltype(&nvrtcGetProgramLog) log = nullptr;
+    bool ok = false;
+};
+
+static NvrtcApi& nvrtc_api() {
+    static NvrtcApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+            api.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) return;
+#define ELISA_SYM(field, sym) api.field = (decltype(api.field))dlsym(api.handle, #sym)
+        ELISA_SYM(create, nvrtcCreateProgram);
+        ELISA_SYM(compile, nvrtcCompileProgram);
+        ELISA_SYM(destroy, nvrtcDestroyProgram);
+        ELISA_SYM(cubin_size, nvrtcGetCUBINSize);
+        ELISA_SYM(cubin, nvrtcGetCUBIN);
+        ELISA_SYM(log_size, nvrtcGetProgramLogSize);
+        ELISA_SYM(log, nvrtcGetProgramLog);
+#undef ELISA_SYM
+        api.ok = api.create && api.compile && api.destroy && api.cubin_size && api.cubin && api.log_size && api.log;
+    });
+    return api;
+}
+
+static std::string hexd(double v) {
+    char buf[64];
+    if (v != v) return "(0.0/0.0)";
+    if (v == HUGE_VAL) return "(1.0/0.0)";
+    if (v == -HUGE_VAL) return "(-1.0/0.0)";
+    snprintf(buf, sizeof buf, "%a", v);
+    return std::string("(") + buf + ")";
+}
+
+// The translation unit for one model: see unfold_skel.cuh.
+static std::string generate_unfold_source(const ModelDev& m, int P) {
+    std::string s;
+    s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\nstruct Model {\n";
+    s += "  template <typename T> struct Pre {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const std::string k = std::to_string(m.leaf[i].kind), id = std::to_string(i);
+        s += "    T p" + id + "[Comp<" + k + ">::NP]; T c" + id + "[Comp<" + k + ">::NC];\n";
+    }
+    s += "  };\n  template <typename T> __device__ __forceinline__ static void pre(const double* th, Pre<T>& s) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        const std::string k = std::to_string(L.kind), id = std::to_string(i);
+        for (int q = 0; q < L.np; ++q) {
+            s += "    s.p" + id + "[" + std::to_string(q) + "] = ";
+            if (L.src[q] >= 0)
+                s += "Flat<T>::seed(th[" + std::to_string(L.src[q]) + "], " + std::to_string(L.src[q]) + ");\n";
+            else
+                s += "Flat<T>::seed(" + hexd(L.cst[q]) + ", -1);\n";
+        }
+        s += "    { const double aux[2] = {" + hexd(L.aux[0]) + ", " + hexd(L.aux[1]) + "};\n";
+        s += "      for (int k = 0; k < Comp<" + k + ">::NC; ++k) s.c" + id + "[k] = Flat<T>::seed(0.0, -1);\n";
+        s += "      Comp<" + k + ">::pre(s.p" + id + ", aux, s.c" + id + "); }\n";
+    }
+    s += "  }\n  template <typename T> __device__ __forceinline__ static T bin(const Pre<T>& s, const GridView& gv, int e) {\n";
+    std::vector<std::string> stack;
+    std::vector<bool> emitted(m.n_leaf, false);
+    int tmp = 0;
+    for (int o = 0; o < m.n_ops; ++o) {
+        const int op = m.ops[o];
+        if (op >= 0) {
+            const std::string id = std::to_string(op);
+            if (!emitted[op]) {
+                s += "    const T v" + id + " = leaf_bin_pc<" + std::to_string(m.leaf[op].kind) + ", T>(s.p" + id + ", s.c" +
+                     id + ", " + std::to_string(m.leaf[op].method) + ", gv, e);\n";
+                emitted[op] = true;
+            }
+            stack.push_back("v" + id);
+        } else {
+            const std::string r = stack.back();
+            stack.pop_back();
+            const std::string l = stack.back();
+            stack.pop_back();
+            const std::string t = "t" + std::to_string(tmp++);
+            s += "    const T " + t + " = " + l + (op == ELISA_OP_ADD ? " + " : " * ") + r + ";\n";
+            stack.push_back(t);
+        }
+    }
+    s += "    return " + stack.back() + ";\n  }\n};\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_val(const UnfoldCore a) { unfold_generic<Model, double>(a); }\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_grad(const UnfoldCore a) { unfold_generic<Model, Dual<" +
+         std::to_string(P) + ">>(a); }\n";
+    return s;
+}
+
+// NVRTC: source -> sm_100a cubin.  Needs no GPU.
+static bool compile_unfold_source(const std::string& src, std::vector<char>* cubin, std::string* why) {
+    NvrtcApi& api = nvrtc_api();
+    if (!api.ok) {
+        *why = "libnvrtc.so.12 not found";
+        return false;
+    }
+    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h};
+    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h"};
+    nvrtcProgram prog = nullptr;
+    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 4, headers, names) != NVRTC_SUCCESS) {
+        *why = "nvrtcCreateProgram failed";
+        return false;
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    const nvrtcResult rc = api.compile(prog, 3, opts);
+    if (rc != NVRTC_SUCCESS) {
+        size_t n = 0;
+        api.log_size(prog, &n);
+        std::string log(n, '\0');
+        if (n) api.log(prog, &log[0]);
+        *why = "nvrtc compile failed: " + log.substr(0, 4000);
+        api.destroy(&prog);
+        return false;
+    }
+    size_t n = 0;
+    api.cubin_size(prog, &n);
+    cubin->resize(n);
+    api.cubin(prog, cubin->data());
+    api.destroy(&prog);
+    return true;
+}
+
+// Compile (or fetch from the in-process cache) the specialised kernels of one model.
+// Returns nullptr with `why` set when runtime compilation is not possible.
+static const JitKernels* jit_unfold(const ModelDev& m, int P, std::string* why) {
+    static std::mutex mu;
+    static std::map<std::string, JitKernels*> cache;
+    const std::string src = generate_unfold_source(m, P);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(src);
+    if (it != cache.end()) return it->second;
+    std::vector<char> cubin;
+    if (!compile_unfold_source(src, &cubin, why)) return nullptr;
+    JitKernels* k = new JitKernels();
+    cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->val, k->lib, "unfold_val");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->grad, k->lib, "unfold_grad");
+    if (e != cudaSuccess) {
+        *why = std::string("loading the compiled unfold kernels failed: ") + cudaGetErrorString(e);
+        delete k;
+        return nullptr;
+    }
+    cache[src] = k;
+    return k;
+}
+
 // ---- optional device timing -----------------------------------------------------------
 struct ScopedSpan {
     ElisaPlan* plan;
@@ -859,8 +1008,8 @@ static void drain_spans(ElisaPlan* plan) {
 // ---- launches ------------------------------------------------------------------------
 static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* theta, int n_valid, int n_rows,
                          bool grad, double* U, double* dU, int ld, int e_pad, bool clip, cudaStream_t st) {
-    UnfoldArgs a;
-    a.model = sp.model;
+    UnfoldArgs args;
+    UnfoldCore& a = args.core;
     a.gv = sp.grid_view();
     a.theta = theta;
     a.P = plan->P;
@@ -880,18 +1029,28 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.U = U;
     a.dU = dU;
     a.plane = (int64_t)n_rows * ld;
+    a.used_mask = sp.model.used_mask;
+    a.pad_ = 0;
     const int64_t warps = (int64_t)n_rows * n_seg;
     const int blocks = (int)((warps + UNFOLD_WARPS - 1) / UNFOLD_WARPS);
     const int threads = UNFOLD_WARPS * 32;
     ScopedSpan span(plan, ELISA_PROFILE_UNFOLD, st);
+    if (sp.jit != nullptr) {  // runtime-specialised kernel
+        void* kargs[] = {(void*)&a};
+        CUDA_TRY(cudaLaunchKernel((const void*)(grad ? sp.jit->grad : sp.jit->val), dim3(blocks), dim3(threads), kargs,
+                                  0, st));
+        ++plan->launches;
+        return ELISA_OK;
+    }
+    args.model = sp.model;
     if (!grad)
-        unfold_kernel<0><<<blocks, threads, 0, st>>>(a);
+        unfold_kernel<0><<<blocks, threads, 0, st>>>(args);
     else if (plan->P <= 4)
-        unfold_kernel<4><<<blocks, threads, 0, st>>>(a);
+        unfold_kernel<4><<<blocks, threads, 0, st>>>(args);
     else if (plan->P <= 8)
-        unfold_kernel<8><<<blocks, threads, 0, st>>>(a);
+        unfold_kernel<8><<<blocks, threads, 0, st>>>(args);
     else
-        unfold_kernel<16><<<blocks, threads, 0, st>>>(a);
+        unfold_kernel<16><<<blocks, threads, 0, st>>>(args);
     ++plan->launches;
     CUDA_TRY(cudaGetLastError());
     return ELISA_OK;
@@ -1062,6 +1221,17 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
     for (int s = 0; s < plan->S && rc == ELISA_OK; ++s) {
         rc = build_spectrum(plan, desc->spectra[s], &plan->spec[s]);
         if (rc) break;
+        // specialise the unfold kernel for this model unless told not to
+        const char* env = getenv("ELISA_B200_JIT");
+        const bool off = (desc->flags & ELISA_FLAG_NO_JIT) || (env && strcmp(env, "0") == 0);
+        if (!off) {
+            std::string why;
+            plan->spec[s].jit = jit_unfold(plan->spec[s].model, plan->P, &why);
+            if (plan->spec[s].jit == nullptr && ((desc->flags & ELISA_FLAG_REQUIRE_JIT) || (env && strcmp(env, "require") == 0))) {
+                rc = fail(ELISA_ERR_UNSUPPORTED, "runtime specialisation required but unavailable: " + why);
+                break;
+            }
+        }
         plan->spec[s].counts_off = coff;
         coff += plan->spec[s].C;
         plan->max_E_pad = std::max(plan->max_E_pad, plan->spec[s].E_pad);
@@ -1270,5 +1440,27 @@ int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches) 
 int64_t elisa_b200_plan_workspace_bytes(const ElisaPlan* plan) { return plan ? plan->workspace_bytes : 0; }
 int64_t elisa_b200_plan_launch_count(const ElisaPlan* plan) { return plan ? plan->launches : 0; }
 int64_t elisa_b200_plan_chunk(const ElisaPlan* plan) { return plan ? plan->chunk : 0; }
+int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_params, char* source_out,
+                                    int64_t source_cap) {
+    if (model == nullptr || n_params < 1 || n_params > ELISA_MAX_PARAMS) return fail(ELISA_ERR_INVALID, "specialise_check: bad argument");
+    ModelDev m;
+    int rc = build_model(*model, n_params, &m);
+    if (rc) return rc;
+    const std::string src = generate_unfold_source(m, n_params);
+    if (source_out != nullptr && source_cap > 0) {
+        const size_t n = std::min<size_t>(src.size(), (size_t)source_cap - 1);
+        memcpy(source_out, src.data(), n);
+        source_out[n] = '\0';
+    }
+    std::vector<char> cubin;
+    std::string why;
+    if (!compile_unfold_source(src, &cubin, &why)) return fail(ELISA_ERR_UNSUPPORTED, why);
+    return (int64_t)cubin.size();
+}
+
+int elisa_b200_plan_is_specialised(const ElisaPlan* plan, int32_t spectrum) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return 0;
+    return plan->spec[spectrum].jit != nullptr ? 1 : 0;
+}
 
 }  // extern "C"

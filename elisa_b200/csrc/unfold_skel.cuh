@@ -1,0 +1,92 @@
+// Skeleton of the runtime-specialised unfold kernel.
+//
+// At plan creation the library writes, for each distinct model expression, a tiny
+// translation unit that defines `struct Model` (parameters wired to theta columns or
+// literals, one leaf_bin_pc<KIND> call per component, the +/* tree as straight-line code)
+// and instantiates unfold_generic<Model, T> for T = double (values) and T = Dual<P>
+// (values + d/dtheta).  It is compiled for sm_100a with NVRTC; every component body is the
+// same hand-written code as in the ahead-of-time interpreter (components.cuh), but with
+// all dispatch, parameter routing and derivative sparsity resolved at compile time
+// (dual seeds are literals, so zero tangents vanish by constant folding).
+//
+// Thread layout: one warp per (parameter vector, energy segment); lane = energy edge;
+// passes of 31 bins (see components.cuh).
+#pragma once
+#include "components.cuh"
+
+namespace elisa {
+
+struct UnfoldCore {
+    GridView gv;
+    const double* theta;  // [N, P]
+    int32_t P;
+    int32_t n_valid;  // rows < n_valid are evaluated, rows in [n_valid, n_rows) are zero-filled
+    int32_t n_rows;
+    int32_t n_seg;    // segments the energy axis is split into (one warp per (row, segment))
+    int32_t seg_len;  // bins per segment (multiple of 31)
+    int32_t ld;       // leading dimension of U / dU rows
+    int32_t e_pad;    // columns [E, e_pad) are zero-filled
+    int32_t clip;     // apply clip(unfold, 1e-300, 1e300) (infer/likelihood.py:204)
+    double* U;        // [n_rows, ld]
+    double* dU;       // [P, n_rows, ld] or nullptr
+    int64_t plane;    // n_rows * ld
+    uint32_t used_mask;
+    int32_t pad_;
+};
+
+constexpr int UNFOLD_WARPS = 4;
+
+__device__ __forceinline__ void unfold_zero(const UnfoldCore& a, size_t row_off, int lo, int hi, int lane, bool grad) {
+    for (int e = lo + lane; e < hi; e += 32) {
+        a.U[row_off + e] = 0.0;
+        if (grad)
+            for (int j = 0; j < a.P; ++j)
+                if ((a.used_mask >> j) & 1u) a.dU[j * a.plane + row_off + e] = 0.0;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void unfold_store(const UnfoldCore& a, size_t off, const T& res) {
+    const double v = value(res);
+    bool pass = true;
+    double u = v;
+    if (a.clip) {
+        pass = (v >= 1e-300) && (v <= 1e300);
+        u = fmin(fmax(v, 1e-300), 1e300);
+        if (v != v) u = v;  // jnp.clip propagates NaN
+    }
+    a.U[off] = u;
+    if constexpr (Scalar<T>::NP > 0) {
+#pragma unroll
+        for (int j = 0; j < Scalar<T>::NP; ++j)
+            if (j < a.P && ((a.used_mask >> j) & 1u)) a.dU[j * a.plane + off] = pass ? res.d[j] : 0.0;
+    }
+}
+
+template <class Model, typename T>
+__device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
+    constexpr bool GRAD = Scalar<T>::NP > 0;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wid = (int64_t)blockIdx.x * UNFOLD_WARPS + wib;
+    const int row = (int)(wid / a.n_seg), seg = (int)(wid % a.n_seg);
+    if (row >= a.n_rows) return;
+    const int E = a.gv.E;
+    const int e_lo = seg * a.seg_len;
+    const int e_hi = min(e_lo + a.seg_len, E);
+    const bool last_seg = seg == a.n_seg - 1;
+    const size_t row_off = (size_t)row * a.ld;
+    if (row >= a.n_valid) {  // padding rows: zeros, so that the fold sees finite operands
+        unfold_zero(a, row_off, e_lo, last_seg ? a.e_pad : e_hi, lane, GRAD);
+        return;
+    }
+    typename Model::template Pre<T> pre;
+    Model::template pre<T>(a.theta + (size_t)row * a.P, pre);
+    for (int e0 = e_lo; e0 < e_hi; e0 += 31) {
+        const int e = e0 + lane;
+        const T res = Model::template bin<T>(pre, a.gv, e);
+        if (lane < 31 && e < e_hi) unfold_store<T>(a, row_off + e, res);
+    }
+    if (last_seg) unfold_zero(a, row_off, E, a.e_pad, lane, GRAD);
+}
+
+}  // namespace elisa

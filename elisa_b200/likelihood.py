@@ -43,12 +43,15 @@ class Likelihood:
     stat : sequence of {'chi2', 'cstat', 'pstat', 'pgstat', 'wstat'}, one per dataset
     device : CUDA device ordinal (default: torch's current device)
     chunk : parameter vectors per internal pass (0 = library default)
+    specialise : True = require the NVRTC-specialised component kernel, False = use the
+        ahead-of-time interpreter kernel, None = specialise when NVRTC is available
 
     ``params_name`` lists the columns of ``theta`` (constrained space; priors and
     transforms stay with the caller, infer/helper.py:409-426).
     """
 
-    def __init__(self, data: Sequence[FixedData], model, stat: Sequence[str], device: int | None = None, chunk: int = 0):
+    def __init__(self, data: Sequence[FixedData], model, stat: Sequence[str], device: int | None = None, chunk: int = 0,
+                 specialise: bool | None = None):
         import torch
 
         if not torch.cuda.is_available():
@@ -115,7 +118,8 @@ class Likelihood:
                 sd.off_error = _ptr(d.back_errors)
             sd.model, k = m.to_desc(self.free)
             keep.append(k)
-        desc = _lib.PlanDesc(_lib.ABI_VERSION, self.device, self._P, len(data), specs, int(chunk), 0)
+        flags = 0 if specialise is None else (_lib.FLAG_REQUIRE_JIT if specialise else _lib.FLAG_NO_JIT)
+        desc = _lib.PlanDesc(_lib.ABI_VERSION, self.device, self._P, len(data), specs, int(chunk), flags)
         handle = C.c_void_p()
         _lib.check(lib.elisa_b200_plan_create(C.byref(desc), C.byref(handle)))
         self._h = handle
@@ -135,6 +139,11 @@ class Likelihood:
             self.close()
         except Exception:
             pass
+
+    @property
+    def specialised(self) -> list[bool]:
+        """Per dataset: is the component kernel the runtime-specialised one?"""
+        return [bool(self._lib.elisa_b200_plan_is_specialised(self._h, k)) for k in range(len(self.data))]
 
     @property
     def chunk(self) -> int:
@@ -304,12 +313,12 @@ def unfold_only(model: CompiledModel, egrid: np.ndarray, theta: np.ndarray, devi
 class _EvalOnly(Likelihood):
     """Plan used by CompiledModel.eval: multiplicative models are allowed here."""
 
-    def __init__(self, data, model, stat, device=None, chunk=0):
+    def __init__(self, data, model, stat, device=None, chunk=0, specialise=None):
         types = [m.type for m in model]
         for m in model:
             m.type = 'add'
         try:
-            super().__init__(data, model, stat, device=device, chunk=chunk)
+            super().__init__(data, model, stat, device=device, chunk=chunk, specialise=specialise)
         finally:
             for m, t in zip(model, types):
                 m.type = t

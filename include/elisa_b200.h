@@ -37,7 +37,13 @@
 #ifndef ELISA_B200_H_
 #define ELISA_B200_H_
 
+#ifdef __CUDACC_RTC__ /* runtime-compiled device code (csrc/unfold_skel.cuh): no host headers */
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -100,6 +106,7 @@ extern "C" {
 #define ELISA_OP_ADD -1
 #define ELISA_OP_MUL -2
 
+#ifndef __CUDACC_RTC__ /* host-side descriptors and entry points */
 typedef struct ElisaComponentDesc {
     int32_t kind;   /* ELISA_COMP_*                                                  */
     int32_t method; /* ELISA_METHOD_* (ignored by analytic-integral components)      */
@@ -157,8 +164,15 @@ typedef struct ElisaPlanDesc {
     int64_t chunk; /* samples processed per internal pass (0 = default); sets the
                     * private workspace: chunk * (2 E + C) doubles for the widest
                     * spectrum                                                       */
-    int32_t flags; /* reserved, 0                                                    */
+    int32_t flags; /* ELISA_FLAG_* bits, 0 = defaults                                */
 } ElisaPlanDesc;
+
+/* The component-evaluation kernel is specialised per model expression at plan creation
+ * with NVRTC (csrc/unfold_skel.cuh); without libnvrtc, or with ELISA_FLAG_NO_JIT /
+ * env ELISA_B200_JIT=0, the ahead-of-time interpreter kernel runs the same program.
+ * ELISA_FLAG_REQUIRE_JIT / env ELISA_B200_JIT=require make a failed specialisation an error. */
+#define ELISA_FLAG_NO_JIT 1
+#define ELISA_FLAG_REQUIRE_JIT 2
 
 typedef struct ElisaPlan ElisaPlan;
 
@@ -213,9 +227,18 @@ int64_t elisa_b200_plan_chunk(const ElisaPlan* plan);
 int64_t elisa_b200_plan_workspace_bytes(const ElisaPlan* plan);
 /* kernels launched by this plan since creation (all entry points)                  */
 int64_t elisa_b200_plan_launch_count(const ElisaPlan* plan);
+/* Generate and compile (NVRTC, sm_100a; needs no GPU) the specialised component kernel
+ * of `model`; returns the cubin size in bytes or a negative error.  source_out, if not
+ * NULL, receives the generated translation unit (NUL-terminated, truncated to the cap). */
+int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_params, char* source_out,
+                                    int64_t source_cap);
+/* 1 if spectrum's component kernel is the runtime-specialised one, 0 if interpreted */
+int elisa_b200_plan_is_specialised(const ElisaPlan* plan, int32_t spectrum);
 int elisa_b200_abi_version(void);
 /* thread-local, never NULL */
 const char* elisa_b200_last_error(void);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

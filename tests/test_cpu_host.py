@@ -129,6 +129,24 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.elisa_b200_plan_launch_count(None) == 0
 
 
+def test_specialised_kernel_compiles_for_every_component(lib):
+    """NVRTC needs no GPU: the generated translation unit of every built-in (and of a
+    composite with fixed + linked parameters) must compile for sm_100a."""
+    K = M.UniformParameter('K', 2.0, 1e-3, 1e3)
+    models = [c(1.0, 10.0) if c in (M.PLEnFlux, M.PLPhFlux) else c() for c in M.ADDITIVE]
+    models += [m() * M.PowerLaw() for m in M.MULTIPLICATIVE]
+    models += [M.CutoffPL(method='simpson') + M.Blackbody(method='simpson'),
+               M.Constant() * (M.ExpAbs(Ec=0.7) * M.PowerLaw(K=K) + M.HighECut() * (M.Blackbody(K=K) + M.Gauss(El=6.4)))]
+    buf = C.create_string_buffer(1 << 16)
+    for m in models:
+        cm = m.compile()
+        md, _keep = cm.to_desc()
+        n = lib.elisa_b200_specialise_check(C.byref(md), max(cm.nparam, 1), buf, len(buf))
+        assert n > 0, (repr(m), lib.elisa_b200_last_error().decode()[:500])
+        src = buf.value.decode()
+        assert 'unfold_generic<Model' in src and src.count('leaf_bin_pc<') == len(cm.leaves)
+
+
 # ------------------------------------------------------------------ sharding of the N axis
 def test_shard_bounds():
     assert shard_bounds(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]

@@ -23,11 +23,15 @@ def small_config(k):
     return synthetic.config5(n=257, S=3, E=128, C=64)
 
 
+KERNELS = pytest.mark.parametrize('specialise', [True, False], ids=['nvrtc', 'interp'])
+
+
+@KERNELS
 @pytest.mark.parametrize('k', [1, 2, 3, 4, 5])
-def test_config_parity(lib, k):
+def test_config_parity(lib, k, specialise):
     from parity import RTOL, compare
 
-    err = compare(small_config(k))
+    err = compare(small_config(k), specialise=specialise)
     assert err['value'] <= RTOL, err
     assert err['grad'] <= RTOL, err
 
@@ -75,9 +79,10 @@ def _theta_for(model, n, seed):
 ADD = [c for c in M.ADDITIVE if c not in (M.PLEnFlux, M.PLPhFlux)]
 
 
+@KERNELS
 @pytest.mark.parametrize('method', ['trapz', 'simpson'])
 @pytest.mark.parametrize('comp', ADD, ids=lambda c: c.__name__)
-def test_every_additive_component(lib, comp, method):
+def test_every_additive_component(lib, comp, method, specialise):
     from parity import RTOL, compare
 
     model = comp(method=method) if comp._numerical else comp()
@@ -86,11 +91,12 @@ def test_every_additive_component(lib, comp, method):
     d = _one_spectrum()
     theta = _theta_for(model, 33, 1)
     cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
-    err = compare(cfg)
+    err = compare(cfg, specialise=specialise)
     assert err['value'] <= RTOL and err['grad'] <= RTOL, err
 
 
-def test_powerlaw_alpha_exactly_one(lib):
+@KERNELS
+def test_powerlaw_alpha_exactly_one(lib, specialise):
     """the `where(alpha != 1, ...)` branch of _powerlaw_integral (models/add.py:40-50)."""
     from parity import RTOL, compare
 
@@ -100,12 +106,13 @@ def test_powerlaw_alpha_exactly_one(lib):
         theta[::2, 0] = 1.0
         if isinstance(model, M.BrokenPL):
             theta[:, 2] = 1.0
-        err = compare(dict(data=[d], model=[model], stat=['cstat'], theta=theta))
+        err = compare(dict(data=[d], model=[model], stat=['cstat'], theta=theta), specialise=specialise)
         assert err['value'] <= RTOL and err['grad'] <= RTOL, (model, err)
 
 
+@KERNELS
 @pytest.mark.parametrize('energy', [False, True])
-def test_plflux_components(lib, energy):
+def test_plflux_components(lib, energy, specialise):
     from parity import RTOL, compare
 
     model = (M.PLEnFlux if energy else M.PLPhFlux)(1.0, 10.0)
@@ -113,20 +120,21 @@ def test_plflux_components(lib, energy):
     cfg = dict(data=[d], model=[model], stat=['cstat'], theta=_theta_for(model, 17, 2))
     if energy:
         cfg['theta'][:, 1] *= 1e4  # bring the counts to a sensible range
-    err = compare(cfg)
+    err = compare(cfg, specialise=specialise)
     assert err['value'] <= RTOL and err['grad'] <= RTOL, err
 
 
+@KERNELS
 @pytest.mark.parametrize('method', ['trapz', 'simpson'])
 @pytest.mark.parametrize('comp', M.MULTIPLICATIVE, ids=lambda c: c.__name__)
-def test_every_multiplicative_component(lib, comp, method):
+def test_every_multiplicative_component(lib, comp, method, specialise):
     from parity import RTOL, compare
 
     mul = comp(method=method) if comp._numerical else comp()
     model = mul * M.PowerLaw()
     d = _one_spectrum()
     cfg = dict(data=[d], model=[model], stat=['cstat'], theta=_theta_for(model, 33, 3))
-    err = compare(cfg)
+    err = compare(cfg, specialise=specialise)
     assert err['value'] <= RTOL and err['grad'] <= RTOL, err
 
 
@@ -172,14 +180,15 @@ def test_every_statistic_with_edge_channels(lib, stat):
         assert np.allclose(g[lo:, 0, j], fd[lo:], rtol=2e-5, atol=1e-6 * np.abs(fd).max()), j
 
 
-def test_composite_tree_linked_and_fixed(lib):
+@KERNELS
+def test_composite_tree_linked_and_fixed(lib, specialise):
     from parity import RTOL, compare
 
     K = M.UniformParameter('K', 2.0, 1e-3, 1e3)
     model = M.Constant() * (M.ExpAbs(Ec=0.7) * M.PowerLaw(K=K) + M.HighECut() * (M.Blackbody(K=K) + M.Gauss(El=6.4)))
     d = _one_spectrum(E=90, C=50, seed=9)
     cfg = dict(data=[d], model=[model], stat=['cstat'], theta=_theta_for(model, 50, 7))
-    err = compare(cfg)
+    err = compare(cfg, specialise=specialise)
     assert err['value'] <= RTOL and err['grad'] <= RTOL, err
 
 
