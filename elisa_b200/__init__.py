@@ -7,7 +7,7 @@ reference's model / data / likelihood interfaces for that path.  No CPU fallback
 
 from . import models
 from .data import FixedData
-from .likelihood import Likelihood
+from .likelihood import Likelihood, sliced_gemm
 from .models import *  # noqa: F401,F403
 from ._lib import ElisaB200Error, load as load_library
 

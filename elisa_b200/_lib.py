@@ -16,6 +16,9 @@ OP_ADD = -1
 OP_MUL = -2
 FLAG_NO_JIT = 1
 FLAG_REQUIRE_JIT = 2
+FLAG_FOLD_DMMA = 4
+FLAG_FOLD_I8 = 8
+FLAG_FOLD_SLICES_SHIFT = 8
 METHOD = {'trapz': 0, 'simpson': 1}
 STAT = {'chi2': 0, 'cstat': 1, 'pstat': 2, 'pgstat': 3, 'wstat': 4}
 ERRORS = {-1: 'ELISA_ERR_INVALID', -2: 'ELISA_ERR_CUDA', -3: 'ELISA_ERR_UNSUPPORTED', -4: 'ELISA_ERR_NOMEM'}
@@ -94,6 +97,9 @@ SYMBOLS = {
     'elisa_b200_plan_chunk': (C.c_int64, [_VP]),
     'elisa_b200_specialise_check': (C.c_int64, [C.POINTER(ModelDesc), C.c_int32, C.c_char_p, C.c_int64]),
     'elisa_b200_plan_is_specialised': (C.c_int, [_VP, C.c_int32]),
+    'elisa_b200_plan_fold_slices': (C.c_int, [_VP, C.c_int32]),
+    'elisa_b200_sliced_gemm_dev': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            _VP, C.c_int64, c_double_p, _VP]),
     'elisa_b200_abi_version': (C.c_int, []),
     'elisa_b200_last_error': (C.c_char_p, []),
 }

@@ -34,6 +34,7 @@
 #include "elisa_b200.h"
 #include "components.cuh"
 #include "dual.cuh"
+#include "fold_i8.cuh"
 #include "gemm_f64.cuh"
 #include "stats.cuh"
 #include "unfold_skel.cuh"
@@ -64,17 +65,6 @@ struct ModelDev {
 struct UnfoldArgs {
     ModelDev model;
     UnfoldCore core;
-};
-
-// per-channel observed data, padded to C_pad with benign values
-struct ChanArrays {
-    const double* scale;    // area_scale * exposure
-    const double* on;
-    const double* off;
-    const double* sigma;
-    const double* ratio;
-    const double* gof_on;
-    const double* gof_off;
 };
 
 // ======================================================================================
@@ -469,6 +459,17 @@ struct PackedDevice {
     PackedB view() const { return PackedB{data, off, k_lo, k_hi}; }
 };
 
+// Static (B) operand of the sliced-integer fold: digit images per (64-row tile, k-block).
+struct I8Operand {
+    int8_t* img = nullptr;
+    double* scale = nullptr;      // [n_tiles * 64]
+    int64_t* tile_img = nullptr;  // [n_tiles] first image of the tile
+    int32_t* kb_lo = nullptr;     // [n_tiles] stored k-block range
+    int32_t* kb_hi = nullptr;
+    int n_tiles = 0;
+    int64_t n_images = 0;
+};
+
 struct SpectrumPlan {
     int E = 0, C = 0, E_pad = 0, C_pad = 0;
     int stat = 0;
@@ -477,6 +478,8 @@ struct SpectrumPlan {
     double *egrid = nullptr, *lngrid = nullptr, *emid = nullptr, *lnmid = nullptr;
     double* chan = nullptr;  // 9 arrays of C_pad: scale on off sigma ratio gof_on gof_off area inv_width
     PackedDevice fwd, bwd;   // R [E, C] tiled over C ; R^T [C, E] tiled over E
+    I8Operand i8_fwd, i8_bwd;  // digit images of R^T rows (channels) / R rows (energies); img == nullptr: DMMA fold
+    bool use_i8() const { return i8_fwd.img != nullptr; }
     int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
     int64_t nnz = 0;
     const struct JitKernels* jit = nullptr;  // runtime-specialised unfold (nullptr: interpreter)
@@ -500,6 +503,11 @@ struct ElisaPlan {
     std::vector<SpectrumPlan> spec;
     // workspace
     double *U = nullptr, *dU = nullptr, *W = nullptr, *part = nullptr, *gpart = nullptr;
+    // sliced-integer fold: digit images of the per-chunk A operand (U, then W) and its row scales
+    int ks = 0;  // slices per operand (0: every spectrum folds with DMMA)
+    int8_t* A_img = nullptr;
+    double* a_scale = nullptr;
+    int sm_count = 148;
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
     // host-path staging (device side), grown on demand
@@ -974,7 +982,7 @@ struct ScopedSpan {
     cudaStream_t st;
     cudaEvent_t b = nullptr;
     ScopedSpan(ElisaPlan* p, int cls, cudaStream_t s) : plan(p), st(s) {
-        if (!plan->profiling) return;
+        if (plan == nullptr || !plan->profiling) return;
         cudaEvent_t ev[2];
         for (int i = 0; i < 2; ++i) {
             if (plan->ev_used == plan->ev_pool.size()) {
@@ -1102,6 +1110,227 @@ static int launch_stat_gemm_any(ElisaPlan* plan, const SpectrumPlan& sp, int n_v
     }
 }
 
+
+// ---- sliced-integer fold (fold_i8.cuh) -----------------------------------------------------
+#define ELISA_FOR_EACH_KS(X) X(4) X(5) X(6) X(7)
+
+static int launch_slice(ElisaPlan* plan, int ks, const SliceArgs& a, int cls, cudaStream_t st) {
+    const int rows = a.row_tiles * a.tile_rows;
+    const int blocks = (rows + 7) / 8;
+    ScopedSpan span(plan, cls, st);
+    switch (ks) {
+#define X(K) case K: slice_rows_kernel<K><<<blocks, 256, 0, st>>>(a); break;
+        ELISA_FOR_EACH_KS(X)
+#undef X
+        default: return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
+    }
+    if (plan) ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+template <int KS, class Epi>
+static int launch_fold_i8_ks(ElisaPlan* plan, int cls, const FoldI8Args& fa, const Epi& epi, int sm_count,
+                             cudaStream_t st) {
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(fold_i8_kernel<KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      i8_smem_bytes(KS)));
+        configured = true;
+    }
+    const int tiles = fa.m_tiles * fa.n_tiles;
+    const int grid = std::min(tiles, sm_count);
+    ScopedSpan span(plan, cls, st);
+    fold_i8_kernel<KS, Epi><<<grid, I8_THREADS, i8_smem_bytes(KS), st>>>(fa, epi);
+    if (plan) ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+template <class Epi>
+static int launch_fold_i8(ElisaPlan* plan, int ks, int cls, const FoldI8Args& fa, const Epi& epi, int sm_count,
+                          cudaStream_t st) {
+    switch (ks) {
+#define X(K) case K: return launch_fold_i8_ks<K>(plan, cls, fa, epi, sm_count, st);
+        ELISA_FOR_EACH_KS(X)
+#undef X
+        default: return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
+    }
+}
+
+static FoldI8Args fold_i8_args(const ElisaPlan* plan, const I8Operand& B, int kb_a, int m_tiles) {
+    FoldI8Args fa;
+    fa.A_img = plan->A_img;
+    fa.a_scale = plan->a_scale;
+    fa.kb_a = kb_a;
+    fa.B_img = B.img;
+    fa.b_scale = B.scale;
+    fa.b_tile_img = B.tile_img;
+    fa.kb_lo = B.kb_lo;
+    fa.kb_hi = B.kb_hi;
+    fa.m_tiles = m_tiles;
+    fa.n_tiles = B.n_tiles;
+    return fa;
+}
+
+// Digit images of a static operand: `dense` is [rows, K] row-major on the HOST (rows = output
+// columns of the fold, K = contraction index).  Each 64-row tile stores only the k-blocks
+// between its first and last non-zero (a band-sparse response keeps 2-3 of them).
+static int build_i8_operand(ElisaPlan* plan, int ks, const std::vector<double>& dense, int rows, int K,
+                            I8Operand* out) {
+    const int n_tiles = round_up(rows, I8_BN) / I8_BN;
+    const int kb_total = round_up(K, I8_BK) / I8_BK;
+    std::vector<int64_t> tile_img(n_tiles);
+    std::vector<int32_t> kb_lo(n_tiles), kb_hi(n_tiles);
+    int64_t n_images = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        int lo = K, hi = 0;
+        for (int r = t * I8_BN; r < std::min(rows, (t + 1) * I8_BN); ++r) {
+            const double* x = dense.data() + (size_t)r * K;
+            int a = 0, b = K;
+            while (a < K && x[a] == 0.0) ++a;
+            while (b > a && x[b - 1] == 0.0) --b;
+            if (a < b) {
+                lo = std::min(lo, a);
+                hi = std::max(hi, b);
+            }
+        }
+        if (lo >= hi) lo = hi = 0;
+        kb_lo[t] = lo / I8_BK;
+        kb_hi[t] = (hi + I8_BK - 1) / I8_BK;
+        tile_img[t] = n_images;
+        n_images += kb_hi[t] - kb_lo[t];
+    }
+    int rc;
+    if ((rc = upload(plan, tile_img, &out->tile_img))) return rc;
+    if ((rc = upload(plan, kb_lo, &out->kb_lo))) return rc;
+    if ((rc = upload(plan, kb_hi, &out->kb_hi))) return rc;
+    const size_t img_bytes = std::max<size_t>((size_t)n_images * ks * I8_B_SLICE, 16);
+    CUDA_TRY(cudaMalloc((void**)&out->img, img_bytes));
+    plan->owned.push_back(out->img);
+    CUDA_TRY(cudaMalloc((void**)&out->scale, (size_t)n_tiles * I8_BN * 8));
+    plan->owned.push_back(out->scale);
+    double* tmp = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&tmp, std::max<size_t>(dense.size() * 8, 16)));
+    cudaError_t e = cudaMemcpy(tmp, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        SliceArgs a;
+        a.X = tmp;
+        a.ld = K;
+        a.rows = rows;
+        a.cols = K;
+        a.row_tiles = n_tiles;
+        a.tile_rows = I8_BN;
+        a.kb_total = kb_total;
+        a.tile_img = out->tile_img;
+        a.kb_lo = out->kb_lo;
+        a.kb_hi = out->kb_hi;
+        a.img = out->img;
+        a.scale = out->scale;
+        const bool prof = plan->profiling;
+        plan->profiling = false;
+        rc = launch_slice(plan, ks, a, ELISA_PROFILE_REDUCE, nullptr);
+        plan->profiling = prof;
+        if (rc == ELISA_OK) e = cudaDeviceSynchronize();
+    }
+    cudaFree(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ELISA_ERR_CUDA, std::string("slicing the response failed: ") + cudaGetErrorString(e));
+    out->n_tiles = n_tiles;
+    out->n_images = n_images;
+    plan->workspace_bytes += (int64_t)img_bytes;
+    return ELISA_OK;
+}
+
+template <int STAT, bool GRAD>
+static int launch_stat_fold_i8(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid, int m_tiles, const double* on,
+                               const double* off, cudaStream_t st) {
+    I8EpilogueStat<STAT, GRAD> epi;
+    epi.ch = sp.chan_view();
+    epi.counts_on = on ? on + sp.counts_off : nullptr;
+    epi.counts_off = off ? off + sp.counts_off : nullptr;
+    epi.ld_counts = plan->sum_C;
+    epi.n_valid = n_valid;
+    epi.C = sp.C;
+    epi.W = plan->W;
+    epi.ldw = sp.C_pad;
+    epi.part = plan->part;
+    epi.ld_part = (int)plan->chunk;
+    const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
+    return launch_fold_i8(plan, plan->ks, ELISA_PROFILE_FOLD, fa, epi, plan->sm_count, st);
+}
+
+template <bool GRAD>
+static int launch_stat_fold_i8_any(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid, int m_tiles,
+                                   const double* on, const double* off, cudaStream_t st) {
+    switch (sp.stat) {
+        case ELISA_STAT_CHI2: return launch_stat_fold_i8<ELISA_STAT_CHI2, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_CSTAT: return launch_stat_fold_i8<ELISA_STAT_CSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_PSTAT: return launch_stat_fold_i8<ELISA_STAT_PSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_PGSTAT: return launch_stat_fold_i8<ELISA_STAT_PGSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        default: return launch_stat_fold_i8<ELISA_STAT_WSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+    }
+}
+
+// digits of the per-chunk A operand X [n_rows, ld] (U or W) into plan->A_img / a_scale
+static int slice_chunk_operand(ElisaPlan* plan, const double* X, int ld, int cols, int n_valid, int m_tiles, int cls,
+                               cudaStream_t st) {
+    SliceArgs a;
+    a.X = X;
+    a.ld = ld;
+    a.rows = n_valid;
+    a.cols = cols;
+    a.row_tiles = m_tiles;
+    a.tile_rows = I8_BM;
+    a.kb_total = round_up(ld, I8_BK) / I8_BK;
+    a.tile_img = nullptr;
+    a.kb_lo = nullptr;
+    a.kb_hi = nullptr;
+    a.img = plan->A_img;
+    a.scale = plan->a_scale;
+    return launch_slice(plan, plan->ks, a, cls, st);
+}
+
+static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int n, int m_tiles, bool want_grad,
+                        const double* on, const double* off, cudaStream_t st) {
+    int rc;
+    if ((rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_FOLD, st))) return rc;
+    if (!want_grad) return launch_stat_fold_i8_any<false>(plan, sp, n, m_tiles, on, off, st);
+    if ((rc = launch_stat_fold_i8_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
+    if ((rc = slice_chunk_operand(plan, plan->W, sp.C_pad, sp.C, n, m_tiles, ELISA_PROFILE_TFOLD, st))) return rc;
+    I8EpilogueGrad eg;
+    eg.dU = plan->dU;
+    eg.plane = (int64_t)m_tiles * I8_BM * sp.E_pad;
+    eg.ldu = sp.E_pad;
+    eg.P = plan->P;
+    eg.used_mask = sp.model.used_mask;
+    eg.n_part = 2 * sp.i8_bwd.n_tiles;
+    eg.gpart = plan->gpart;
+    eg.ld_part = (int)plan->chunk;
+    const FoldI8Args fa = fold_i8_args(plan, sp.i8_bwd, round_up(sp.C_pad, I8_BK) / I8_BK, m_tiles);
+    return launch_fold_i8(plan, plan->ks, ELISA_PROFILE_TFOLD, fa, eg, plan->sm_count, st);
+}
+
+// Both static operands of one spectrum: rows of R^T (channels; contraction over energies) for the
+// forward fold and rows of R (energies; contraction over channels) for the transposed fold.
+static int build_spectrum_i8(ElisaPlan* plan, const ElisaSpectrumDesc& sd, SpectrumPlan* sp, int ks) {
+    const int E = sp->E, C = sp->C;
+    std::vector<double> R((size_t)E * C, 0.0), Rt((size_t)C * E, 0.0);
+    if (sd.response_dense != nullptr) {
+        memcpy(R.data(), sd.response_dense, R.size() * 8);
+    } else {
+        for (int c = 0; c < C; ++c)
+            for (int i = sd.csr_indptr[c]; i < sd.csr_indptr[c + 1]; ++i)
+                R[(size_t)sd.csr_indices[i] * C + c] += sd.csr_values[i];
+    }
+    for (int e = 0; e < E; ++e)
+        for (int c = 0; c < C; ++c) Rt[(size_t)c * E + e] = R[(size_t)e * C + c];
+    int rc;
+    if ((rc = build_i8_operand(plan, ks, Rt, C, E, &sp->i8_fwd))) return rc;
+    if ((rc = build_i8_operand(plan, ks, R, E, C, &sp->i8_bwd))) return rc;
+    return ELISA_OK;
+}
+
 // One (chunk, spectrum) pass.  theta/on/off/loglike/grad already point at the chunk's first row.
 static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off, int n,
                      double* loglike, double* grad, cudaStream_t st) {
@@ -1112,7 +1341,10 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     int rc;
     if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st)))
         return rc;
-    if (want_grad) {
+    const bool i8 = sp.use_i8();
+    if (i8) {
+        if ((rc = run_chunk_i8(plan, sp, n, m_tiles, want_grad, on, off, st))) return rc;
+    } else if (want_grad) {
         if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
         EpilogueGrad eg;
         eg.dU = plan->dU;
@@ -1130,8 +1362,8 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     ReduceArgs ra;
     ra.part = plan->part;
     ra.gpart = plan->gpart;
-    ra.tiles_c = sp.fwd.n_tiles;
-    ra.tiles_e = sp.bwd.n_tiles;
+    ra.tiles_c = i8 ? 2 * sp.i8_fwd.n_tiles : sp.fwd.n_tiles;  // partial sums per row
+    ra.tiles_e = i8 ? 2 * sp.i8_bwd.n_tiles : sp.bwd.n_tiles;
     ra.ld = (int)plan->chunk;
     ra.n = n;
     ra.P = plan->P;
@@ -1218,6 +1450,34 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
     plan->spec.resize(plan->S);
     int rc = ELISA_OK;
     int64_t coff = 0;
+    // fold engine: sliced-integer tcgen05 (default) or FP64 DMMA
+    bool force_i8 = (desc->flags & ELISA_FLAG_FOLD_I8) != 0, any_i8 = false;
+    {
+        bool dmma = (desc->flags & ELISA_FLAG_FOLD_DMMA) != 0;
+        int ks = (desc->flags >> ELISA_FLAG_FOLD_SLICES_SHIFT) & 0xf;
+        if (const char* env = getenv("ELISA_B200_FOLD")) {
+            if (!force_i8 && !dmma) {
+                if (strcmp(env, "dmma") == 0) dmma = true;
+                if (strcmp(env, "i8") == 0) force_i8 = true;
+            }
+        }
+        if (const char* env = getenv("ELISA_B200_FOLD_SLICES"))
+            if (ks == 0) ks = atoi(env);
+        if (ks == 0) ks = ELISA_FOLD_SLICES_DEFAULT;
+        if (dmma && force_i8) {
+            delete plan;
+            cudaSetDevice(prev);
+            return fail(ELISA_ERR_INVALID, "ELISA_FLAG_FOLD_DMMA and ELISA_FLAG_FOLD_I8 are exclusive");
+        }
+        if (ks < 4 || ks > 7) {
+            delete plan;
+            cudaSetDevice(prev);
+            return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
+        }
+        plan->ks = dmma ? 0 : ks;
+        cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
+        if (plan->sm_count < 1) plan->sm_count = 148;
+    }
     for (int s = 0; s < plan->S && rc == ELISA_OK; ++s) {
         rc = build_spectrum(plan, desc->spectra[s], &plan->spec[s]);
         if (rc) break;
@@ -1232,6 +1492,13 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                 break;
             }
         }
+        if (plan->ks > 0 && plan->spec[s].E <= I8_MAX_K && plan->spec[s].C <= I8_MAX_K) {
+            if ((rc = build_spectrum_i8(plan, desc->spectra[s], &plan->spec[s], plan->ks))) break;
+            any_i8 = true;
+        } else if (plan->ks > 0 && force_i8) {
+            rc = fail(ELISA_ERR_UNSUPPORTED, "sliced-integer fold requested but E or C exceeds its int32 headroom");
+            break;
+        }
         plan->spec[s].counts_off = coff;
         coff += plan->spec[s].C;
         plan->max_E_pad = std::max(plan->max_E_pad, plan->spec[s].E_pad);
@@ -1242,7 +1509,9 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         // chunk: one 128-row tile per SM by default, bounded by a 6 GiB workspace
         int64_t chunk = desc->chunk > 0 ? desc->chunk : 148 * GEMM_BM;
         chunk = (chunk + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
-        const int64_t tiles_c = plan->max_C_pad / GEMM_BN, tiles_e = plan->max_E_pad / GEMM_BN;
+        // row partials: one per 64-column tile (DMMA) or per 32-column half tile (sliced-integer fold)
+        const int64_t pmul = any_i8 ? 2 : 1;
+        const int64_t tiles_c = pmul * plan->max_C_pad / GEMM_BN, tiles_e = pmul * plan->max_E_pad / GEMM_BN;
         const int64_t per_row = 8 * ((int64_t)plan->max_E_pad * (1 + plan->P) + plan->max_C_pad + tiles_c +
                                      tiles_e * plan->P);
         if (desc->chunk == 0) {
@@ -1261,6 +1530,17 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         if (rc == ELISA_OK) rc = alloc(&plan->W, chunk * plan->max_C_pad);
         if (rc == ELISA_OK) rc = alloc(&plan->part, chunk * tiles_c);
         if (rc == ELISA_OK) rc = alloc(&plan->gpart, chunk * tiles_e * plan->P);
+        if (rc == ELISA_OK && any_i8) {
+            const int64_t kmax = round_up(std::max(plan->max_E_pad, plan->max_C_pad), I8_BK);
+            const int64_t bytes = chunk * kmax * plan->ks;
+            if (cudaMalloc((void**)&plan->A_img, (size_t)bytes) != cudaSuccess) {
+                rc = fail(ELISA_ERR_NOMEM, "out of device memory (digit images)");
+            } else {
+                plan->owned.push_back(plan->A_img);
+                plan->workspace_bytes += bytes;
+                rc = alloc(&plan->a_scale, chunk);
+            }
+        }
     }
     if (rc == ELISA_OK && cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(ELISA_ERR_CUDA, "cudaStreamCreate failed");
@@ -1456,6 +1736,90 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
     std::string why;
     if (!compile_unfold_source(src, &cubin, &why)) return fail(ELISA_ERR_UNSUPPORTED, why);
     return (int64_t)cubin.size();
+}
+
+int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
+    return plan->spec[spectrum].use_i8() ? plan->ks : 0;
+}
+
+int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, int64_t ldb, int32_t m, int32_t n,
+                               int32_t k, int32_t slices, double* D, int64_t ldd, double* ms, void* cuda_stream) {
+    if (A == nullptr || B == nullptr || D == nullptr || m < 1 || n < 1 || k < 1 || lda < k || ldb < k || ldd < n)
+        return fail(ELISA_ERR_INVALID, "sliced_gemm: bad argument");
+    if (slices < 4 || slices > 7) return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
+    if (k > I8_MAX_K) return fail(ELISA_ERR_UNSUPPORTED, "sliced_gemm: k exceeds the int32 headroom (16384)");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int m_tiles = round_up(m, I8_BM) / I8_BM, n_tiles = round_up(n, I8_BN) / I8_BN;
+    const int kb = round_up(k, I8_BK) / I8_BK;
+    int8_t *a_img = nullptr, *b_img = nullptr;
+    double *a_sc = nullptr, *b_sc = nullptr;
+    int32_t* rng = nullptr;
+    int64_t* timg = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = ELISA_OK;
+    auto cleanup = [&]() {
+        cudaFree(a_img); cudaFree(b_img); cudaFree(a_sc); cudaFree(b_sc); cudaFree(rng); cudaFree(timg);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define SG_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            cleanup();                                                                                 \
+            return fail(ELISA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+        }                                                                                              \
+    } while (0)
+    SG_TRY(cudaMalloc((void**)&a_img, (size_t)m_tiles * kb * slices * I8_A_SLICE));
+    SG_TRY(cudaMalloc((void**)&b_img, (size_t)n_tiles * kb * slices * I8_B_SLICE));
+    SG_TRY(cudaMalloc((void**)&a_sc, (size_t)m_tiles * I8_BM * 8));
+    SG_TRY(cudaMalloc((void**)&b_sc, (size_t)n_tiles * I8_BN * 8));
+    std::vector<int32_t> h_rng(2 * n_tiles);
+    std::vector<int64_t> h_timg(n_tiles);
+    for (int t = 0; t < n_tiles; ++t) {
+        h_rng[t] = 0;
+        h_rng[n_tiles + t] = kb;
+        h_timg[t] = (int64_t)t * kb;
+    }
+    SG_TRY(cudaMalloc((void**)&rng, h_rng.size() * 4));
+    SG_TRY(cudaMalloc((void**)&timg, h_timg.size() * 8));
+    SG_TRY(cudaMemcpyAsync(rng, h_rng.data(), h_rng.size() * 4, cudaMemcpyHostToDevice, st));
+    SG_TRY(cudaMemcpyAsync(timg, h_timg.data(), h_timg.size() * 8, cudaMemcpyHostToDevice, st));
+    SG_TRY(cudaStreamSynchronize(st));
+    SliceArgs sa;
+    sa.X = A; sa.ld = lda; sa.rows = m; sa.cols = k; sa.row_tiles = m_tiles; sa.tile_rows = I8_BM; sa.kb_total = kb;
+    sa.tile_img = nullptr; sa.kb_lo = nullptr; sa.kb_hi = nullptr; sa.img = a_img; sa.scale = a_sc;
+    SliceArgs sb = sa;
+    sb.X = B; sb.ld = ldb; sb.rows = n; sb.row_tiles = n_tiles; sb.tile_rows = I8_BN; sb.img = b_img; sb.scale = b_sc;
+    if ((rc = launch_slice(nullptr, slices, sa, 0, st)) || (rc = launch_slice(nullptr, slices, sb, 0, st))) {
+        cleanup();
+        return rc;
+    }
+    FoldI8Args fa;
+    fa.A_img = a_img; fa.a_scale = a_sc; fa.kb_a = kb; fa.B_img = b_img; fa.b_scale = b_sc; fa.b_tile_img = timg;
+    fa.kb_lo = rng; fa.kb_hi = rng + n_tiles; fa.m_tiles = m_tiles; fa.n_tiles = n_tiles;
+    I8EpilogueStore es{D, ldd, m, n};
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SG_TRY(cudaEventCreate(&e0));
+    SG_TRY(cudaEventCreate(&e1));
+    SG_TRY(cudaEventRecord(e0, st));
+    rc = launch_fold_i8(nullptr, slices, 0, fa, es, sms, st);
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    SG_TRY(cudaEventRecord(e1, st));
+    SG_TRY(cudaStreamSynchronize(st));
+    float t = 0.f;
+    SG_TRY(cudaEventElapsedTime(&t, e0, e1));
+    if (ms) *ms = t;
+#undef SG_TRY
+    cleanup();
+    return ELISA_OK;
 }
 
 int elisa_b200_plan_is_specialised(const ElisaPlan* plan, int32_t spectrum) {

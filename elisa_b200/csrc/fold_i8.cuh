@@ -1,0 +1,559 @@
+// Sliced-integer response fold on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   D[M, N] = A[M, K] . B[N, K]^T      to FP64 accuracy, computed by int8 tcgen05.mma
+//
+// forward fold   : A = unfold U [samples, E],  B = R^T [C, E]   (infer/likelihood.py:205)
+// transposed fold: A = W        [samples, C],  B = R   [E, C]   (its reverse-mode transpose)
+//
+// tcgen05.mma has no FP64 kind and DMMA tops out at the FP64 pipe rate (~37 TFLOP/s,
+// gemm_f64.cuh).  This path gets FP64-class accuracy from the int8 pipe instead: every
+// operand row x[k] is written as   x[k] = s_row * sum_{i<KS} d_i[k] * 256^(KS-1-i),
+// d_i in [-128, 127] (balanced base-256 digits of q = rint(x / s_row), |q| < 2^(8 KS - 1)),
+// so that
+//       sum_k x[k] y[k] = s_x s_y * sum_{i,j} 256^(2KS-2-i-j) * (d_i . e_j)
+// with every digit product d_i . e_j an EXACT int32 dot product of the tensor core.
+// Products of order i + j > KS - 1 lie below the digits already dropped and are skipped:
+// KS (KS + 1) / 2 int8 GEMMs replace one FP64 GEMM (21 for KS = 6).  The error is bounded
+// NORMWISE like any floating-point GEMM's,   |dD[m, n]| <~ 2^(-8 KS + 3) * max_k|A[m, k]| *
+// sum_k|B[n, k]| + (A <-> B),  i.e. ~2^-45 for KS = 6; tests/ hold the path to the
+// north-star tolerance (1e-10 on statistic and gradient) on every BASELINE configuration.
+//
+// Layout.  Both operands live in HBM as ready-made shared-memory images: per (row tile,
+// k-block of 128 bytes) one image of KS slices, each slice [rows, 128 B] in the canonical
+// K-major SWIZZLE_128B layout of tcgen05 (8-row atoms of 1024 B, 16-byte chunk index
+// XOR-ed with the row index mod 8).  A tile load is therefore ONE linear bulk copy
+// (cp.async.bulk, the TMA engine in 1-D mode) -- no tensor map, no per-thread addressing.
+// The digits of B are produced once per plan; those of A by slice_rows_kernel per chunk.
+//
+// Kernel.  One persistent CTA per SM, 10 warps:
+//   warps 0-7  epilogue: tcgen05.ld the KS int32 accumulators of their 32 rows x 32
+//              columns, recombine in FP64 (Horner in base 256) and run the fused epilogue
+//              (fit statistic + dl/dx, or the contraction with dU/dtheta) thread-per-row;
+//   warp  8    producer: bulk copies into a ring of A slices (16 KB) and a ring of B
+//              blocks (KS x 8 KB), each with full/empty mbarriers;
+//   warp  9    MMA issuer: for slice i of A one tcgen05.mma of N = (KS - i) * 64 columns
+//              against the STACKED B slices 0 .. KS-1-i, landing on the TMEM accumulators
+//              of orders i .. KS-1 (column offset 64 i): A is read once per slice and the
+//              instruction shapes stay wide (N up to 256).
+// TMEM: KS accumulators of 128 lanes x 64 columns (384 of 512 columns for KS = 6).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "stats.cuh"
+
+namespace elisa {
+
+constexpr int I8_BM = 128;       // rows of A per tile = TMEM lanes
+constexpr int I8_BN = 64;        // output columns per tile (one accumulator per order)
+constexpr int I8_BK = 128;       // contraction bytes per k-block = one 128-byte swizzle atom
+constexpr int I8_A_SLICE = I8_BM * I8_BK;  // 16 KB
+constexpr int I8_B_SLICE = I8_BN * I8_BK;  // 8 KB
+constexpr int I8_NB = 2;         // B-block ring depth
+constexpr int I8_EPI_WARPS = 8;
+constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;
+constexpr int I8_SMEM_BUDGET = 212 * 1024;  // rings; + 1 KB alignment slack + barriers below 227 KB
+constexpr int I8_TOP_DIGIT = 120;           // |most significant digit| <= 120 (+1 carry)
+constexpr int I8_MAX_K = 16384;             // int32 headroom: KS * K * 2^14 < 2^31 for KS <= 7
+
+__host__ __device__ constexpr int i8_na(int ks) { return (I8_SMEM_BUDGET - I8_NB * ks * I8_B_SLICE) / I8_A_SLICE; }
+__host__ __device__ constexpr int i8_smem_bytes(int ks) {
+    return 1024 + I8_NB * ks * I8_B_SLICE + i8_na(ks) * I8_A_SLICE + 256;
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol error traps (launch failure) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns: thread = lane (row), v[j] = column j
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset (between 8-row atoms)
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: s8 x s8 -> s32, both operands K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(I8_BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------
+// slicing: FP64 rows -> digit images + row scales
+// ---------------------------------------------------------------------------------------
+struct SliceArgs {
+    const double* X;   // [rows, ld] row-major
+    int64_t ld;
+    int32_t rows;      // rows holding data (further rows of the last tile are zero-filled)
+    int32_t cols;      // columns holding data (k >= cols is zero)
+    int32_t row_tiles; // tiles of `tile_rows` rows written
+    int32_t tile_rows; // 128 (A operand) or 64 (B operand)
+    int32_t kb_total;  // k-blocks per row tile when kb_lo == nullptr
+    const int64_t* tile_img;  // [row_tiles] first image of the tile (nullptr: tile * kb_total)
+    const int32_t* kb_lo;     // [row_tiles] stored k-block range (nullptr: [0, kb_total))
+    const int32_t* kb_hi;
+    int8_t* img;       // images of KS * tile_rows * 128 bytes
+    double* scale;     // [row_tiles * tile_rows]  x ~= scale * 256^-(KS-1) * q  (see kernel)
+};
+
+// One warp per row.  Pass 1: amax (and a non-finite flag).  Pass 2: q = rint(x * f) as
+// int64, balanced digits from the low end (d = sign-extended low byte, q = (q - d) >> 8),
+// four consecutive k per lane packed into one 32-bit store per slice.
+template <int KS>
+__global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= a.row_tiles * a.tile_rows) return;
+    const int tile = row / a.tile_rows, rr = row % a.tile_rows;
+    const int kb0 = a.kb_lo ? a.kb_lo[tile] : 0;
+    const int kb1 = a.kb_hi ? a.kb_hi[tile] : a.kb_total;
+    const int64_t img0 = a.tile_img ? a.tile_img[tile] : (int64_t)tile * a.kb_total;
+    const bool live = row < a.rows;
+    const double* x = a.X + (size_t)row * a.ld;
+
+    double amax = 0.0;
+    bool bad = false;
+    if (live) {
+        for (int k = 2 * lane; k < a.cols; k += 64) {
+            const double v0 = x[k], v1 = (k + 1 < a.cols) ? x[k + 1] : 0.0;
+            bad |= !(fabs(v0) <= 1.79e308) | !(fabs(v1) <= 1.79e308);
+            amax = fmax(amax, fmax(fabs(v0), fabs(v1)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    bad = __any_sync(0xffffffffu, bad);
+
+    // x * f1 * f2 with f1 * f2 = TOP * 256^(KS-1) / amax, split so neither factor nor the
+    // intermediate leaves the normal range (amax may sit anywhere in [1e-300, 1e300])
+    double f1 = 0.0, f2 = 0.0, sc = 0.0;
+    if (amax > 0.0 && !bad) {
+        int ex;
+        const double m = frexp(amax, &ex);  // amax = m 2^ex, m in [0.5, 1)
+        const int h = ex / 2;
+        f1 = ldexp(1.0, -h);
+        f2 = ldexp((double)I8_TOP_DIGIT / m, 8 * (KS - 1) - (ex - h));
+        sc = amax / (double)I8_TOP_DIGIT;  // D = sc_a * sc_b * Horner(acc), see combine()
+    }
+    if (bad) sc = __longlong_as_double(0x7ff8000000000000LL);  // NaN row -> NaN results
+    if (lane == 0) a.scale[row] = sc;
+
+    const int sub = (rr >> 3) * 1024 + (rr & 7) * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2);
+    const size_t slice_bytes = (size_t)a.tile_rows * I8_BK;
+    for (int kb = kb0; kb < kb1; ++kb) {
+        const int k = kb * I8_BK + 4 * lane;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live && f2 != 0.0) {
+            if (k + 3 < a.cols && (a.ld & 1) == 0) {
+                const double2 p0 = *reinterpret_cast<const double2*>(x + k);
+                const double2 p1 = *reinterpret_cast<const double2*>(x + k + 2);
+                v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (k + t < a.cols) v[t] = x[k + t];
+            }
+        }
+        long long q[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) q[t] = __double2ll_rn(v[t] * f1 * f2);
+        uint32_t w[KS];
+#pragma unroll
+        for (int i = KS - 1; i >= 0; --i) {
+            uint32_t pack = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const long long d = (long long)(int8_t)(q[t] & 0xff);
+                q[t] = (q[t] - d) >> 8;
+                pack |= ((uint32_t)d & 0xffu) << (8 * t);
+            }
+            w[i] = pack;
+        }
+        int8_t* base = a.img + (size_t)(img0 + (kb - kb0)) * KS * slice_bytes + sub;
+#pragma unroll
+        for (int i = 0; i < KS; ++i) *reinterpret_cast<uint32_t*>(base + i * slice_bytes) = w[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// the fold kernel
+// ---------------------------------------------------------------------------------------
+struct FoldI8Args {
+    const int8_t* A_img;        // image (mt, kb) at ((mt * kb_a + kb) * KS) * 16 KB
+    const double* a_scale;      // [m_tiles * 128]
+    int32_t kb_a;               // k-blocks stored per row tile of A
+    const int8_t* B_img;        // image tile_img[nt] + (kb - kb_lo[nt]), KS * 8 KB each
+    const double* b_scale;      // [n_tiles * 64]
+    const int64_t* b_tile_img;  // [n_tiles]
+    const int32_t* kb_lo;       // [n_tiles] k-block range of column tile nt
+    const int32_t* kb_hi;
+    int32_t m_tiles, n_tiles;
+};
+
+// TMEM -> FP64: out[j] = sum_o acc_o[column j] * 256^-o (Horner from the least significant order), j < 8
+template <int KS>
+__device__ __forceinline__ void i8_combine8(uint32_t taddr, double* out) {
+    int32_t v[KS][8];
+#pragma unroll
+    for (int d = 0; d < KS; ++d) tc_ld8(taddr + d * I8_BN, v[d]);
+    tc_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double s = (double)v[KS - 1][j];
+#pragma unroll
+        for (int d = KS - 2; d >= 0; --d) s = fma(s, 0.00390625, (double)v[d][j]);
+        out[j] = s;
+    }
+}
+
+// Epilogue interface:  epi.template run<KS>(taddr, tile_m, tile_n, row, half, a_scale_row, b_scale)
+//   taddr  TMEM address of (this warp's lanes, accumulator 0, column 32 * half)
+//   row    global row of this thread; columns tile_n * 64 + 32 * half + [0, 32)
+template <int KS, class Epi>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi epi) {
+    constexpr int NA = i8_na(KS);
+    constexpr int B_BLOCK = KS * I8_B_SLICE;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t s_B = s_base;
+    const uint32_t s_A = s_base + I8_NB * B_BLOCK;
+    const uint32_t s_bar = s_A + NA * I8_A_SLICE;
+    // barriers: a_full[NA] a_empty[NA] b_full[NB] b_empty[NB] t_full t_empty ; then the TMEM slot
+    auto a_full = [&](int s) { return s_bar + 8u * s; };
+    auto a_empty = [&](int s) { return s_bar + 8u * (NA + s); };
+    auto b_full = [&](int s) { return s_bar + 8u * (2 * NA + s); };
+    auto b_empty = [&](int s) { return s_bar + 8u * (2 * NA + I8_NB + s); };
+    const uint32_t t_full = s_bar + 8u * (2 * NA + 2 * I8_NB);
+    const uint32_t t_empty = t_full + 8u;
+    const uint32_t s_slot = t_empty + 8u;
+    uint8_t* gen_base = smem_raw + (s_base - smem_u32(smem_raw));
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (s_slot - s_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == I8_EPI_WARPS && lane == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+        for (int s = 0; s < I8_NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        mbar_init(t_full, 1);
+        mbar_init(t_empty, I8_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == I8_EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_slot), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+
+    const int n_tiles_total = a.m_tiles * a.n_tiles;
+
+    if (warp == I8_EPI_WARPS) {
+        // ================= producer =================
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+            const int mt = t / a.n_tiles, nt = t % a.n_tiles;
+            const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
+            const int8_t* bsrc = a.B_img + (size_t)a.b_tile_img[nt] * B_BLOCK;
+            const int8_t* asrc = a.A_img + ((size_t)mt * a.kb_a + lo) * KS * I8_A_SLICE;
+            for (int kb = lo; kb < hi; ++kb) {
+                mbar_wait(b_empty(bs), bph ^ 1u);
+                if (lane == 0) {
+                    mbar_expect_tx(b_full(bs), B_BLOCK);
+                    bulk_g2s(s_B + bs * B_BLOCK, bsrc, B_BLOCK, b_full(bs));
+                }
+                bsrc += B_BLOCK;
+                if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
+                for (int i = 0; i < KS; ++i) {
+                    mbar_wait(a_empty(as), aph ^ 1u);
+                    if (lane == 0) {
+                        mbar_expect_tx(a_full(as), I8_A_SLICE);
+                        bulk_g2s(s_A + as * I8_A_SLICE, asrc, I8_A_SLICE, a_full(as));
+                    }
+                    asrc += I8_A_SLICE;
+                    if (++as == NA) { as = 0; aph ^= 1u; }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == I8_EPI_WARPS + 1) {
+        // ================= MMA issuer =================
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0, tph = 0;
+        for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+            const int nt = t % a.n_tiles;
+            const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
+            mbar_wait(t_empty, tph ^ 1u);  // epilogue has drained the accumulators
+            tph ^= 1u;
+            tc_fence_after();
+            for (int kb = lo; kb < hi; ++kb) {
+                mbar_wait(b_full(bs), bph);
+                const uint32_t sb = s_B + bs * B_BLOCK;
+#pragma unroll
+                for (int i = 0; i < KS; ++i) {
+                    mbar_wait(a_full(as), aph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = s_A + as * I8_A_SLICE;
+#pragma unroll
+                        for (int ks = 0; ks < I8_BK / 32; ++ks) {
+                            const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
+                            const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
+#pragma unroll
+                            for (int c0 = 0; c0 < (KS - i) * I8_BN; c0 += 256) {
+                                const int n = ((KS - i) * I8_BN - c0) < 256 ? ((KS - i) * I8_BN - c0) : 256;
+                                const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
+                                tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
+                            }
+                        }
+                        tc_commit(a_empty(as));
+                    }
+                    __syncwarp();
+                    if (++as == NA) { as = 0; aph ^= 1u; }
+                }
+                if (lane == 0) tc_commit(b_empty(bs));
+                __syncwarp();
+                if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
+            }
+            if (lane == 0) tc_commit(t_full);
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue =================
+        const int quarter = warp & 3, half = warp >> 2;
+        uint32_t tph = 0;
+        for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+            const int mt = t / a.n_tiles, nt = t % a.n_tiles;
+            const int row = mt * I8_BM + quarter * 32 + lane;
+            const bool empty = a.kb_lo[nt] >= a.kb_hi[nt];  // no k-blocks: accumulators are stale
+            mbar_wait(t_full, tph);
+            tph ^= 1u;
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + half * 32;
+            epi.template run<KS>(taddr, mt, nt, row, half, empty ? 0.0 : a.a_scale[row],
+                                 a.b_scale + (size_t)nt * I8_BN + half * 32);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == I8_EPI_WARPS + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogues (thread = one row, 32 consecutive columns in 4 chunks of 8)
+// ---------------------------------------------------------------------------------------
+// plain store: D[row, col] (debug / tests / sites)
+struct I8EpilogueStore {
+    double* D;
+    int64_t ldd;
+    int32_t rows, cols;  // bounds of D
+    template <int KS>
+    __device__ __forceinline__ void run(uint32_t taddr, int, int tile_n, int row, int half, double sa,
+                                        const double* sb) const {
+        const int c0 = tile_n * I8_BN + half * 32;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            double x[8];
+            i8_combine8<KS>(taddr + 8 * cc, x);
+            if (row < rows) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + 8 * cc + j;
+                    if (c < cols) D[(size_t)row * ldd + c] = x[j] * sa * sb[8 * cc + j];
+                }
+            }
+        }
+    }
+};
+
+// per-channel observed data, padded to C_pad with benign values (shared with the DMMA path)
+struct ChanArrays {
+    const double* scale;  // area_scale * exposure
+    const double* on;
+    const double* off;
+    const double* sigma;
+    const double* ratio;
+    const double* gof_on;
+    const double* gof_off;
+};
+
+// forward fold: x = (R u) * area * exposure -> statistic, row partial, W = dl/d(R u)
+// part[(2 * tile_n + half) * ld_part + row]
+template <int STAT, bool GRAD>
+struct I8EpilogueStat {
+    ChanArrays ch;
+    const double* counts_on;   // per-replica observed data [n, ld_counts] or nullptr
+    const double* counts_off;
+    int64_t ld_counts;
+    int32_t n_valid;
+    int32_t C;
+    double* W;  // [rows, ldw]
+    int32_t ldw;
+    double* part;
+    int32_t ld_part;
+
+    template <int KS>
+    __device__ __forceinline__ void run(uint32_t taddr, int, int tile_n, int row, int half, double sa,
+                                        const double* sb) const {
+        const int c0 = tile_n * I8_BN + half * 32;
+        const bool rvalid = row < n_valid;
+        const double* con = (counts_on != nullptr && rvalid) ? counts_on + (size_t)row * ld_counts : nullptr;
+        const double* coff = (counts_off != nullptr && rvalid) ? counts_off + (size_t)row * ld_counts : nullptr;
+        double rs = 0.0;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            double x[8];
+            i8_combine8<KS>(taddr + 8 * cc, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = c0 + 8 * cc + j;
+                ChannelData d;
+                const double sc = ch.scale[col];
+                d.on = ch.on[col];
+                d.gof_on = ch.gof_on[col];
+                d.off = d.sigma = d.ratio = d.gof_off = 0.0;
+                if (STAT == ELISA_STAT_CHI2) d.sigma = ch.sigma[col];
+                if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+                    d.off = ch.off[col];
+                    d.ratio = ch.ratio[col];
+                }
+                if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[col];
+                if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[col];
+                const bool cvalid = col < C;
+                if (con != nullptr && cvalid) {
+                    d.on = con[col];
+                    if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
+                }
+                if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr && cvalid) {
+                    d.off = coff[col];
+                    if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
+                }
+                const double fold = x[j] * sa * sb[8 * cc + j];
+                double dx = 0.0;
+                const double ll = stat_channel<STAT, GRAD>(fold * sc, d, dx);
+                rs += cvalid ? ll : 0.0;
+                x[j] = (cvalid && rvalid) ? dx * sc : 0.0;
+            }
+            if (GRAD) {
+                double2* dst = reinterpret_cast<double2*>(W + (size_t)row * ldw + c0 + 8 * cc);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_double2(x[2 * j], x[2 * j + 1]);
+            }
+        }
+        part[(size_t)(2 * tile_n + half) * ld_part + row] = rs;
+    }
+};
+
+// transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the thread's 32 energies
+// gpart[(j * n_part + 2 * tile_n + half) * ld_part + row],  n_part = 2 * n_tiles
+struct I8EpilogueGrad {
+    const double* dU;  // [P, rows, ldu]
+    int64_t plane;
+    int32_t ldu;
+    int32_t P;
+    uint32_t used_mask;
+    int32_t n_part;
+    double* gpart;
+    int32_t ld_part;
+
+    template <int KS>
+    __device__ __forceinline__ void run(uint32_t taddr, int, int tile_n, int row, int half, double sa,
+                                        const double* sb) const {
+        const int e0 = tile_n * I8_BN + half * 32;
+        double rs[ELISA_MAX_PARAMS];
+#pragma unroll
+        for (int j = 0; j < ELISA_MAX_PARAMS; ++j) rs[j] = 0.0;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            double g[8];
+            i8_combine8<KS>(taddr + 8 * cc, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] *= sb[8 * cc + j];
+            const double* base = dU + (size_t)row * ldu + e0 + 8 * cc;
+#pragma unroll
+            for (int p = 0; p < ELISA_MAX_PARAMS; ++p) {
+                if (p < P && ((used_mask >> p) & 1u)) {
+                    const double2* src = reinterpret_cast<const double2*>(base + (size_t)p * plane);
+                    double s = rs[p];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 v = src[j];
+                        s = fma(g[2 * j], v.x, s);
+                        s = fma(g[2 * j + 1], v.y, s);
+                    }
+                    rs[p] = s;
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
+            if (p < P && ((used_mask >> p) & 1u))
+                gpart[((size_t)p * n_part + 2 * tile_n + half) * ld_part + row] = rs[p] * sa;
+    }
+};
+
+}  // namespace elisa

@@ -45,13 +45,17 @@ class Likelihood:
     chunk : parameter vectors per internal pass (0 = library default)
     specialise : True = require the NVRTC-specialised component kernel, False = use the
         ahead-of-time interpreter kernel, None = specialise when NVRTC is available
+    fold : response-fold engine.  None = library default (the sliced-integer tcgen05 fold,
+        FP64 DMMA for spectra it cannot take), 'i8' = require the sliced-integer fold,
+        'dmma' = native FP64 DMMA
+    slices : digits per operand of the sliced-integer fold (4..7, 0 = default 6)
 
     ``params_name`` lists the columns of ``theta`` (constrained space; priors and
     transforms stay with the caller, infer/helper.py:409-426).
     """
 
     def __init__(self, data: Sequence[FixedData], model, stat: Sequence[str], device: int | None = None, chunk: int = 0,
-                 specialise: bool | None = None):
+                 specialise: bool | None = None, fold: str | None = None, slices: int = 0):
         import torch
 
         if not torch.cuda.is_available():
@@ -119,6 +123,12 @@ class Likelihood:
             sd.model, k = m.to_desc(self.free)
             keep.append(k)
         flags = 0 if specialise is None else (_lib.FLAG_REQUIRE_JIT if specialise else _lib.FLAG_NO_JIT)
+        if fold not in (None, 'i8', 'dmma'):
+            raise ValueError("fold must be None, 'i8' or 'dmma'")
+        if slices and not 4 <= int(slices) <= 7:
+            raise ValueError('slices must be 0 or 4..7')
+        flags |= {None: 0, 'i8': _lib.FLAG_FOLD_I8, 'dmma': _lib.FLAG_FOLD_DMMA}[fold]
+        flags |= int(slices) << _lib.FLAG_FOLD_SLICES_SHIFT
         desc = _lib.PlanDesc(_lib.ABI_VERSION, self.device, self._P, len(data), specs, int(chunk), flags)
         handle = C.c_void_p()
         _lib.check(lib.elisa_b200_plan_create(C.byref(desc), C.byref(handle)))
@@ -144,6 +154,11 @@ class Likelihood:
     def specialised(self) -> list[bool]:
         """Per dataset: is the component kernel the runtime-specialised one?"""
         return [bool(self._lib.elisa_b200_plan_is_specialised(self._h, k)) for k in range(len(self.data))]
+
+    @property
+    def fold_slices(self) -> list[int]:
+        """Per dataset: digits of the sliced-integer fold in use, 0 = FP64 DMMA fold."""
+        return [int(self._lib.elisa_b200_plan_fold_slices(self._h, k)) for k in range(len(self.data))]
 
     @property
     def chunk(self) -> int:
@@ -318,7 +333,28 @@ class _EvalOnly(Likelihood):
         for m in model:
             m.type = 'add'
         try:
-            super().__init__(data, model, stat, device=device, chunk=chunk, specialise=specialise)
+            super().__init__(data, model, stat, device=device, chunk=chunk, specialise=specialise, fold='dmma')
         finally:
             for m, t in zip(model, types):
                 m.type = t
+
+
+def sliced_gemm(a, b, slices: int = 6):
+    """``a @ b.T`` for CUDA float64 tensors a (M, K), b (N, K) on the sliced-integer fold
+    engine (int8 tcgen05 tensor cores, FP64-class accuracy; csrc/fold_i8.cuh).  Returns
+    ``(d, ms)``: the (M, N) product and the device time of the contraction kernel."""
+    import torch
+
+    lib = _lib.load()
+    if not (a.is_cuda and b.is_cuda and a.dtype == torch.float64 and b.dtype == torch.float64):
+        raise TypeError('sliced_gemm needs CUDA float64 tensors')
+    a, b = a.contiguous(), b.contiguous()
+    (m, k), (n, k2) = a.shape, b.shape
+    if k != k2:
+        raise ValueError('inner dimensions differ')
+    d = torch.empty((m, n), dtype=torch.float64, device=a.device)
+    ms = C.c_double(0.0)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.elisa_b200_sliced_gemm_dev(_dev_ptr(a), k, _dev_ptr(b), k, m, n, k, int(slices), _dev_ptr(d), n,
+                                                  C.byref(ms), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return d, ms.value

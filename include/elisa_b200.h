@@ -173,6 +173,19 @@ typedef struct ElisaPlanDesc {
  * ELISA_FLAG_REQUIRE_JIT / env ELISA_B200_JIT=require make a failed specialisation an error. */
 #define ELISA_FLAG_NO_JIT 1
 #define ELISA_FLAG_REQUIRE_JIT 2
+/* Fold engine.  Default: the sliced-integer fold (csrc/fold_i8.cuh) -- operands split into
+ * `slices` balanced base-256 digits, digit products on the int8 tcgen05 tensor cores with
+ * exact int32 accumulation in TMEM, recombined in FP64: FP64-class accuracy (normwise
+ * ~2^(-8 slices + 3); 6 slices hold the 1e-10 tolerance of the statistic and gradient) at
+ * several times the FP64 DMMA rate.  ELISA_FLAG_FOLD_DMMA / env ELISA_B200_FOLD=dmma
+ * selects the native FP64 DMMA fold (csrc/gemm_f64.cuh); ELISA_FLAG_FOLD_I8 / env
+ * ELISA_B200_FOLD=i8 makes a spectrum the integer fold cannot take (E or C > 16384) an
+ * error instead of a silent DMMA fold.  Slices: bits 8-11 of flags (4..7; 0 = default 6;
+ * 4 is an FP32-class variant, ~1e-6) or env ELISA_B200_FOLD_SLICES.                       */
+#define ELISA_FLAG_FOLD_DMMA 4
+#define ELISA_FLAG_FOLD_I8 8
+#define ELISA_FLAG_FOLD_SLICES_SHIFT 8
+#define ELISA_FOLD_SLICES_DEFAULT 6
 
 typedef struct ElisaPlan ElisaPlan;
 
@@ -232,6 +245,16 @@ int64_t elisa_b200_plan_launch_count(const ElisaPlan* plan);
  * NULL, receives the generated translation unit (NUL-terminated, truncated to the cap). */
 int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_params, char* source_out,
                                     int64_t source_cap);
+/* slices of the sliced-integer fold used for `spectrum` (ELISA_FLAG_FOLD_*), 0 if it folds
+ * with FP64 DMMA, -1 on a bad argument                                                   */
+int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
+/* The fold engine on its own: D[m, n] = A[m, k] . B[n, k]^T in FP64-class accuracy on the
+ * int8 tensor cores (device pointers, row-major, k <= 16384, slices 4..7).  Allocates its
+ * digit images, runs on `cuda_stream`, synchronises; `ms` (nullable) receives the device
+ * time of the contraction kernel alone.  A validation / benchmarking utility: the plan
+ * entry points above run the same kernel with the statistic and gradient epilogues.     */
+int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, int64_t ldb, int32_t m, int32_t n,
+                               int32_t k, int32_t slices, double* D, int64_t ldd, double* ms, void* cuda_stream);
 /* 1 if spectrum's component kernel is the runtime-specialised one, 0 if interpreted */
 int elisa_b200_plan_is_specialised(const ElisaPlan* plan, int32_t spectrum);
 int elisa_b200_abi_version(void);
