@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 METRIC = 'likelihood+grad evals/sec (samples x spectra)'
 UNIT = 'evals/s'
 WORKLOAD = 'cfg2: CutoffPL+Blackbody, wstat, 1024ch x 2048E dense RSP, 1e6 draws/GPU'
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the ncu --set full
+# captures under profiles/ (same command, --draws 37888): forward + transposed fold, averaged
+TRAFFIC = {'dmma': None, 'i8': None}
 
 
 def parse():
@@ -42,6 +45,8 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=16384, help='draws of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--fold', default=None, choices=['i8', 'dmma'], help='response-fold engine (default: library default)')
+    ap.add_argument('--slices', type=int, default=0, help='digits of the sliced-integer fold (0 = default 6)')
     return ap.parse_args()
 
 
@@ -186,7 +191,8 @@ def run_b200(args):
         cfg['theta'] = synthetic._theta_batch(cfg['truth'], n, 5 + 1000 * rank)
     d = cfg['data'][0]
     E, C, S = d.n_energies, d.n_channels, len(cfg['data'])
-    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, fold=args.fold, slices=args.slices)
+    ks = lk.fold_slices[0]
     P = lk.nparam
     theta = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=f'cuda:{local}')
     ll = torch.empty((n, S), dtype=torch.float64, device=theta.device)
@@ -268,7 +274,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: the two DMMA folds (gemm_f64_kernel)
+    # ---- roofline of the dominant kernel: the two response folds (forward + transposed)
     fold_ms, fold_n = prof['fold']
     tfold_ms, tfold_n = prof['tfold']
     gemm_ms = fold_ms + tfold_ms
@@ -276,17 +282,40 @@ def run_b200(args):
     flops_total = 4.0 * E * C * n * S * args.steps  # 2 E C per eval and fold, both folds
     achieved = flops_total / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     roofline = {
-        'bound': 'tensor', 'kernel': 'gemm_f64_kernel (forward + transposed fold, DMMA)',
+        'bound': 'tensor',
+        'kernel': ('fold_i8_kernel (forward + transposed fold; int8 tcgen05.mma, %d digits per operand, %d digit '
+                   'products per FP64 product, int32 accumulation in TMEM)' % (ks, ks * (ks + 1) // 2)) if ks else
+                  'gemm_f64_kernel (forward + transposed fold, FP64 DMMA)',
         'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
         'frac': achieved / fp64_peak if achieved and fp64_peak else None,
-        'peak_source': 'cuBLAS DGEMM 8192^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no FP64 entry)',
-        'traffic': None,
+        'peak_source': 'cuBLAS DGEMM 8192^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no FP64 entry); '
+                       'achieved = ALGORITHMIC FP64 flops (4 E C per eval) / device time of the fold kernels',
+        'traffic': TRAFFIC.get('i8' if ks else 'dmma'),
         'avg_launch_ms': gemm_ms / gemm_launches if gemm_launches else None,
         'flop_per_launch': flops_total / gemm_launches if gemm_launches else None,
         'share_of_step': gemm_ms / ms if ms > 0 else None,
         'classes_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
         'whole_path_frac': (4.0 * E * C * n * S * args.steps / (ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
     }
+    if ks:
+        # the integer engine beats the FP64 pipe roofline by construction: also report the int8
+        # work it executes against the int8 tensor peak (nominal dense 4500 TOP/s; bf16 burst in
+        # MEASURED_PEAKS.json x 2 as the measured stand-in)
+        int8_ops = flops_total * (ks * (ks + 1) // 2)
+        int8_tops = int8_ops / (gemm_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        int8_peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
+        roofline['int8'] = {'executed_tops': int8_tops, 'peak_tops': int8_peak,
+                            'peak_source': '2 x measured bf16 burst of MEASURED_PEAKS.json (of measured)' if peaks else
+                                           '2 x 1590 fallback bf16 (of fallback)',
+                            'frac': int8_tops / int8_peak, 'nominal_peak_tops': 4500.0}
+        roofline['note'] = ('frac > 1: the fold is FP64-accurate (parity 1e-10) but runs on the int8 tensor pipe, '
+                            'so the FP64 DMMA roofline does not bound it; int8.frac is the fraction of the pipe it '
+                            'does run on')
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -302,6 +331,7 @@ def run_b200(args):
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'draws_per_gpu': n, 'spectra': S, 'n_energies': E, 'n_channels': C,
                    'n_params': P, 'chunk': lk.chunk, 'parallelism': f'dp{world} over draws',
+                   'fold_engine': f'int8 tcgen05 sliced, {ks} digits' if ks else 'FP64 DMMA',
                    'l2': 'inputs larger than L2 (per-chunk workspace 2 GB, theta 40 MB)'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
     }

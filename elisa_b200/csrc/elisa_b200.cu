@@ -522,8 +522,8 @@ struct ElisaPlan {
     size_t ev_used = 0;
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double prof_ms[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0};
-    int64_t prof_n[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0};
+    double prof_ms[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
+    int64_t prof_n[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
 };
 
 namespace elisa {
@@ -1170,6 +1170,7 @@ static FoldI8Args fold_i8_args(const ElisaPlan* plan, const I8Operand& B, int kb
     fa.kb_hi = B.kb_hi;
     fa.m_tiles = m_tiles;
     fa.n_tiles = B.n_tiles;
+    fa.debug = 0;
     return fa;
 }
 
@@ -1294,17 +1295,17 @@ static int slice_chunk_operand(ElisaPlan* plan, const double* X, int ld, int col
 static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int n, int m_tiles, bool want_grad,
                         const double* on, const double* off, cudaStream_t st) {
     int rc;
-    if ((rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_FOLD, st))) return rc;
+    if ((rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st))) return rc;
     if (!want_grad) return launch_stat_fold_i8_any<false>(plan, sp, n, m_tiles, on, off, st);
     if ((rc = launch_stat_fold_i8_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
-    if ((rc = slice_chunk_operand(plan, plan->W, sp.C_pad, sp.C, n, m_tiles, ELISA_PROFILE_TFOLD, st))) return rc;
+    if ((rc = slice_chunk_operand(plan, plan->W, sp.C_pad, sp.C, n, m_tiles, ELISA_PROFILE_SLICE, st))) return rc;
     I8EpilogueGrad eg;
     eg.dU = plan->dU;
     eg.plane = (int64_t)m_tiles * I8_BM * sp.E_pad;
     eg.ldu = sp.E_pad;
     eg.P = plan->P;
     eg.used_mask = sp.model.used_mask;
-    eg.n_part = 2 * sp.i8_bwd.n_tiles;
+    eg.n_part = I8_CG * sp.i8_bwd.n_tiles;
     eg.gpart = plan->gpart;
     eg.ld_part = (int)plan->chunk;
     const FoldI8Args fa = fold_i8_args(plan, sp.i8_bwd, round_up(sp.C_pad, I8_BK) / I8_BK, m_tiles);
@@ -1362,8 +1363,8 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     ReduceArgs ra;
     ra.part = plan->part;
     ra.gpart = plan->gpart;
-    ra.tiles_c = i8 ? 2 * sp.i8_fwd.n_tiles : sp.fwd.n_tiles;  // partial sums per row
-    ra.tiles_e = i8 ? 2 * sp.i8_bwd.n_tiles : sp.bwd.n_tiles;
+    ra.tiles_c = i8 ? I8_CG * sp.i8_fwd.n_tiles : sp.fwd.n_tiles;  // partial sums per row
+    ra.tiles_e = i8 ? I8_CG * sp.i8_bwd.n_tiles : sp.bwd.n_tiles;
     ra.ld = (int)plan->chunk;
     ra.n = n;
     ra.P = plan->P;
@@ -1509,8 +1510,8 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         // chunk: one 128-row tile per SM by default, bounded by a 6 GiB workspace
         int64_t chunk = desc->chunk > 0 ? desc->chunk : 148 * GEMM_BM;
         chunk = (chunk + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
-        // row partials: one per 64-column tile (DMMA) or per 32-column half tile (sliced-integer fold)
-        const int64_t pmul = any_i8 ? 2 : 1;
+        // row partials: one per 64-column tile (DMMA) or per I8_TC-column group (sliced-integer fold)
+        const int64_t pmul = any_i8 ? I8_CG : 1;
         const int64_t tiles_c = pmul * plan->max_C_pad / GEMM_BN, tiles_e = pmul * plan->max_E_pad / GEMM_BN;
         const int64_t per_row = 8 * ((int64_t)plan->max_E_pad * (1 + plan->P) + plan->max_C_pad + tiles_c +
                                      tiles_e * plan->P);
@@ -1799,6 +1800,7 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
     FoldI8Args fa;
     fa.A_img = a_img; fa.a_scale = a_sc; fa.kb_a = kb; fa.B_img = b_img; fa.b_scale = b_sc; fa.b_tile_img = timg;
     fa.kb_lo = rng; fa.kb_hi = rng + n_tiles; fa.m_tiles = m_tiles; fa.n_tiles = n_tiles;
+    fa.debug = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;
     I8EpilogueStore es{D, ldd, m, n};
     int sms = 148;
     int dev = 0;

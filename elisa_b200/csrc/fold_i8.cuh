@@ -25,13 +25,14 @@
 // (cp.async.bulk, the TMA engine in 1-D mode) -- no tensor map, no per-thread addressing.
 // The digits of B are produced once per plan; those of A by slice_rows_kernel per chunk.
 //
-// Kernel.  One persistent CTA per SM, 10 warps:
-//   warps 0-7  epilogue: tcgen05.ld the KS int32 accumulators of their 32 rows x 32
-//              columns, recombine in FP64 (Horner in base 256) and run the fused epilogue
-//              (fit statistic + dl/dx, or the contraction with dU/dtheta) thread-per-row;
-//   warp  8    producer: bulk copies into a ring of A slices (16 KB) and a ring of B
+// Kernel.  One persistent CTA per SM, 18 warps:
+//   warps 0-15 epilogue: tcgen05.ld the KS int32 accumulators of their 32 rows x 16
+//              columns, recombine in FP64 (Horner in base 256), hand TMEM back, then run
+//              the fused epilogue (fit statistic + dl/dx, or the contraction with
+//              dU/dtheta) thread-per-row while the next tile accumulates;
+//   warp  16   producer: bulk copies into a ring of A slices (16 KB) and a ring of B
 //              blocks (KS x 8 KB), each with full/empty mbarriers;
-//   warp  9    MMA issuer: for slice i of A one tcgen05.mma of N = (KS - i) * 64 columns
+//   warp  17   MMA issuer: for slice i of A one tcgen05.mma of N = (KS - i) * 64 columns
 //              against the STACKED B slices 0 .. KS-1-i, landing on the TMEM accumulators
 //              of orders i .. KS-1 (column offset 64 i): A is read once per slice and the
 //              instruction shapes stay wide (N up to 256).
@@ -50,7 +51,9 @@ constexpr int I8_BK = 128;       // contraction bytes per k-block = one 128-byte
 constexpr int I8_A_SLICE = I8_BM * I8_BK;  // 16 KB
 constexpr int I8_B_SLICE = I8_BN * I8_BK;  // 8 KB
 constexpr int I8_NB = 2;         // B-block ring depth
-constexpr int I8_EPI_WARPS = 8;
+constexpr int I8_EPI_WARPS = 16;               // 4 per TMEM lane quarter
+constexpr int I8_CG = I8_EPI_WARPS / 4;        // column groups per tile
+constexpr int I8_TC = I8_BN / I8_CG;           // columns per epilogue thread
 constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;
 constexpr int I8_SMEM_BUDGET = 212 * 1024;  // rings; + 1 KB alignment slack + barriers below 227 KB
 constexpr int I8_TOP_DIGIT = 120;           // |most significant digit| <= 120 (+1 carry)
@@ -242,7 +245,14 @@ struct FoldI8Args {
     const int32_t* kb_lo;       // [n_tiles] k-block range of column tile nt
     const int32_t* kb_hi;
     int32_t m_tiles, n_tiles;
+    int32_t debug;  // experiments only (elisa_b200_sliced_gemm_dev): 1 = no A copies, 2 = no B copies, 4 = no MMAs, 8 = no epilogue, 16 = no TMEM drain
 };
+
+// Exact int32 -> double without the quarter-rate I2F.F64: the bits of 2^52 + (v + 2^31) are
+// assembled with one XOR, and one full-rate DADD removes the offset.
+__device__ __forceinline__ double i32_to_f64(int32_t v) {
+    return __hiloint2double(0x43300000, v ^ (int32_t)0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
+}
 
 // TMEM -> FP64: out[j] = sum_o acc_o[column j] * 256^-o (Horner from the least significant order), j < 8
 template <int KS>
@@ -253,16 +263,28 @@ __device__ __forceinline__ void i8_combine8(uint32_t taddr, double* out) {
     tc_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        double s = (double)v[KS - 1][j];
+        double s = i32_to_f64(v[KS - 1][j]);
 #pragma unroll
-        for (int d = KS - 2; d >= 0; --d) s = fma(s, 0.00390625, (double)v[d][j]);
+        for (int d = KS - 2; d >= 0; --d) s = fma(s, 0.00390625, i32_to_f64(v[d][j]));
         out[j] = s;
     }
 }
 
-// Epilogue interface:  epi.template run<KS>(taddr, tile_m, tile_n, row, half, a_scale_row, b_scale)
-//   taddr  TMEM address of (this warp's lanes, accumulator 0, column 32 * half)
-//   row    global row of this thread; columns tile_n * 64 + 32 * half + [0, 32)
+// Epilogue interface:  epi.run(x, tile_m, tile_n, row, cg, a_scale_row, b_scale)
+//   x      the thread's I8_TC recombined (unscaled) dot products, columns tile_n * 64 + I8_TC * cg + [0, I8_TC)
+//   row    global row of this thread
+// The epilogues walk x in chunks of 8 with a ROLLED loop (the statistic code is long);
+// chunk cc is picked out of the register array with compare-selects, not dynamic indexing.
+__device__ __forceinline__ void i8_pick8(const double (&x)[I8_TC], int cc, double* out) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double v = x[j];
+#pragma unroll
+        for (int k = 1; k < I8_TC / 8; ++k) v = (cc == k) ? x[8 * k + j] : v;
+        out[j] = v;
+    }
+}
+
 template <int KS, class Epi>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi epi) {
@@ -317,16 +339,24 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
             for (int kb = lo; kb < hi; ++kb) {
                 mbar_wait(b_empty(bs), bph ^ 1u);
                 if (lane == 0) {
-                    mbar_expect_tx(b_full(bs), B_BLOCK);
-                    bulk_g2s(s_B + bs * B_BLOCK, bsrc, B_BLOCK, b_full(bs));
+                    if (a.debug & 2) {
+                        mbar_arrive(b_full(bs));
+                    } else {
+                        mbar_expect_tx(b_full(bs), B_BLOCK);
+                        bulk_g2s(s_B + bs * B_BLOCK, bsrc, B_BLOCK, b_full(bs));
+                    }
                 }
                 bsrc += B_BLOCK;
                 if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
                 for (int i = 0; i < KS; ++i) {
                     mbar_wait(a_empty(as), aph ^ 1u);
                     if (lane == 0) {
-                        mbar_expect_tx(a_full(as), I8_A_SLICE);
-                        bulk_g2s(s_A + as * I8_A_SLICE, asrc, I8_A_SLICE, a_full(as));
+                        if (a.debug & 1) {
+                            mbar_arrive(a_full(as));
+                        } else {
+                            mbar_expect_tx(a_full(as), I8_A_SLICE);
+                            bulk_g2s(s_A + as * I8_A_SLICE, asrc, I8_A_SLICE, a_full(as));
+                        }
                     }
                     asrc += I8_A_SLICE;
                     if (++as == NA) { as = 0; aph ^= 1u; }
@@ -354,12 +384,15 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                     if (lane == 0) {
                         const uint32_t sa = s_A + as * I8_A_SLICE;
 #pragma unroll
-                        for (int ks = 0; ks < I8_BK / 32; ++ks) {
+                        for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
                             const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
                             const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
+                            // (KS - i) * 64 columns in equal parts of <= 256 (multiples of 32)
+                            const int width = (KS - i) * I8_BN;
+                            const int parts = (width + 255) / 256;
+                            const int n = width / parts;  // 192, 160, 224 ...: multiples of 32 for KS <= 8
 #pragma unroll
-                            for (int c0 = 0; c0 < (KS - i) * I8_BN; c0 += 256) {
-                                const int n = ((KS - i) * I8_BN - c0) < 256 ? ((KS - i) * I8_BN - c0) : 256;
+                            for (int c0 = 0; c0 < width; c0 += n) {
                                 const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
                                 tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
                             }
@@ -378,7 +411,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
         }
     } else {
         // ================= epilogue =================
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, cg = warp >> 2;
         uint32_t tph = 0;
         for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
             const int mt = t / a.n_tiles, nt = t % a.n_tiles;
@@ -387,12 +420,22 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
             mbar_wait(t_full, tph);
             tph ^= 1u;
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + half * 32;
-            epi.template run<KS>(taddr, mt, nt, row, half, empty ? 0.0 : a.a_scale[row],
-                                 a.b_scale + (size_t)nt * I8_BN + half * 32);
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + cg * I8_TC;
+            // drain: recombine this thread's columns into registers, hand TMEM back to the
+            // MMA warp at once, then run the (long) epilogue math while the next tile accumulates
+            double x[I8_TC];
+            if (a.debug & 16) {
+#pragma unroll
+                for (int j = 0; j < I8_TC; ++j) x[j] = 0.0;
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < I8_TC / 8; ++cc) i8_combine8<KS>(taddr + 8 * cc, x + 8 * cc);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty);
+            if (a.debug & 8) continue;
+            epi.run(x, mt, nt, row, cg, empty ? 0.0 : a.a_scale[row], a.b_scale + (size_t)nt * I8_BN + cg * I8_TC);
         }
     }
 
@@ -404,21 +447,20 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
 }
 
 // ---------------------------------------------------------------------------------------
-// epilogues (thread = one row, 32 consecutive columns in 4 chunks of 8)
+// epilogues (thread = one row, I8_TC consecutive columns in chunks of 8)
 // ---------------------------------------------------------------------------------------
 // plain store: D[row, col] (debug / tests / sites)
 struct I8EpilogueStore {
     double* D;
     int64_t ldd;
     int32_t rows, cols;  // bounds of D
-    template <int KS>
-    __device__ __forceinline__ void run(uint32_t taddr, int, int tile_n, int row, int half, double sa,
+    __device__ __forceinline__ void run(const double (&xx)[I8_TC], int, int tile_n, int row, int cg, double sa,
                                         const double* sb) const {
-        const int c0 = tile_n * I8_BN + half * 32;
+        const int c0 = tile_n * I8_BN + cg * I8_TC;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < I8_TC / 8; ++cc) {
             double x[8];
-            i8_combine8<KS>(taddr + 8 * cc, x);
+            i8_pick8(xx, cc, x);
             if (row < rows) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -442,7 +484,7 @@ struct ChanArrays {
 };
 
 // forward fold: x = (R u) * area * exposure -> statistic, row partial, W = dl/d(R u)
-// part[(2 * tile_n + half) * ld_part + row]
+// part[(I8_CG * tile_n + cg) * ld_part + row]
 template <int STAT, bool GRAD>
 struct I8EpilogueStat {
     ChanArrays ch;
@@ -456,18 +498,17 @@ struct I8EpilogueStat {
     double* part;
     int32_t ld_part;
 
-    template <int KS>
-    __device__ __forceinline__ void run(uint32_t taddr, int, int tile_n, int row, int half, double sa,
+    __device__ __forceinline__ void run(const double (&xx)[I8_TC], int, int tile_n, int row, int cg, double sa,
                                         const double* sb) const {
-        const int c0 = tile_n * I8_BN + half * 32;
+        const int c0 = tile_n * I8_BN + cg * I8_TC;
         const bool rvalid = row < n_valid;
         const double* con = (counts_on != nullptr && rvalid) ? counts_on + (size_t)row * ld_counts : nullptr;
         const double* coff = (counts_off != nullptr && rvalid) ? counts_off + (size_t)row * ld_counts : nullptr;
         double rs = 0.0;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < I8_TC / 8; ++cc) {
             double x[8];
-            i8_combine8<KS>(taddr + 8 * cc, x);
+            i8_pick8(xx, cc, x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int col = c0 + 8 * cc + j;
@@ -504,12 +545,12 @@ struct I8EpilogueStat {
                 for (int j = 0; j < 4; ++j) dst[j] = make_double2(x[2 * j], x[2 * j + 1]);
             }
         }
-        part[(size_t)(2 * tile_n + half) * ld_part + row] = rs;
+        part[(size_t)(I8_CG * tile_n + cg) * ld_part + row] = rs;
     }
 };
 
 // transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the thread's 32 energies
-// gpart[(j * n_part + 2 * tile_n + half) * ld_part + row],  n_part = 2 * n_tiles
+// gpart[(j * n_part + I8_CG * tile_n + cg) * ld_part + row],  n_part = I8_CG * n_tiles
 struct I8EpilogueGrad {
     const double* dU;  // [P, rows, ldu]
     int64_t plane;
@@ -520,17 +561,16 @@ struct I8EpilogueGrad {
     double* gpart;
     int32_t ld_part;
 
-    template <int KS>
-    __device__ __forceinline__ void run(uint32_t taddr, int, int tile_n, int row, int half, double sa,
+    __device__ __forceinline__ void run(const double (&xx)[I8_TC], int, int tile_n, int row, int cg, double sa,
                                         const double* sb) const {
-        const int e0 = tile_n * I8_BN + half * 32;
+        const int e0 = tile_n * I8_BN + cg * I8_TC;
         double rs[ELISA_MAX_PARAMS];
 #pragma unroll
         for (int j = 0; j < ELISA_MAX_PARAMS; ++j) rs[j] = 0.0;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < I8_TC / 8; ++cc) {
             double g[8];
-            i8_combine8<KS>(taddr + 8 * cc, g);
+            i8_pick8(xx, cc, g);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] *= sb[8 * cc + j];
             const double* base = dU + (size_t)row * ldu + e0 + 8 * cc;
@@ -552,7 +592,7 @@ struct I8EpilogueGrad {
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
             if (p < P && ((used_mask >> p) & 1u))
-                gpart[((size_t)p * n_part + 2 * tile_n + half) * ld_part + row] = rs[p] * sa;
+                gpart[((size_t)p * n_part + I8_CG * tile_n + cg) * ld_part + row] = rs[p] * sa;
     }
 };
 

@@ -28,7 +28,7 @@ template <bool GRAD>
 __device__ __forceinline__ double poisson_ll(double n, double mu, double gof, double& dmu) {
     const double v = xlogy(n, mu) - mu - gof;
     if (GRAD) dmu = (v > 0.0) ? 0.0 : (n == 0.0 ? -1.0 : n / mu - 1.0);
-    return fmin(v, 0.0);
+    return v > 0.0 ? 0.0 : v;  // jnp.minimum(v, 0) semantics: NaN propagates (fmin would drop it)
 }
 
 // clip(x, 1e-30, 1e15) of likelihood.py:208 etc.; pass = d clip / d x

@@ -172,15 +172,15 @@ class Likelihood:
     def launch_count(self) -> int:
         return int(self._lib.elisa_b200_plan_launch_count(self._h))
 
-    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce')
+    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice')
 
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.elisa_b200_plan_set_profiling(self._h, int(bool(enable))))
 
     def get_profile(self) -> dict:
         """{class: (milliseconds, launches)} since set_profiling(True) (CUDA events)."""
-        ms = (C.c_double * 4)()
-        n = (C.c_int64 * 4)()
+        ms = (C.c_double * len(self.PROFILE_CLASSES))()
+        n = (C.c_int64 * len(self.PROFILE_CLASSES))()
         _lib.check(self._lib.elisa_b200_plan_get_profile(self._h, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PROFILE_CLASSES)}
 

@@ -230,7 +230,8 @@ int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const d
 #define ELISA_PROFILE_FOLD 1   /* forward fold + statistic epilogue                 */
 #define ELISA_PROFILE_TFOLD 2  /* transposed fold + gradient epilogue               */
 #define ELISA_PROFILE_REDUCE 3 /* partial reductions / per-channel sites            */
-#define ELISA_PROFILE_CLASSES 4
+#define ELISA_PROFILE_SLICE 4  /* digit slicing of U and W (sliced-integer fold only)    */
+#define ELISA_PROFILE_CLASSES 5
 int elisa_b200_plan_set_profiling(ElisaPlan* plan, int enable);
 int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches);
 

@@ -1,0 +1,125 @@
+"""The two response-fold engines behind the same C ABI: the sliced-integer fold on the int8
+tcgen05 tensor cores (default; csrc/fold_i8.cuh) and the native FP64 DMMA fold
+(csrc/gemm_f64.cuh).  Both must hold the 1e-10 tolerance of BASELINE.json's north_star
+against the CPU oracle; the engine on its own is checked as an FP64-class GEMM."""
+
+import numpy as np
+import pytest
+
+from elisa_b200 import models as M
+from elisa_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import _one_spectrum, _theta_for, small_config  # noqa: E402
+
+
+@pytest.mark.parametrize('fold', ['i8', 'dmma'])
+@pytest.mark.parametrize('k', [1, 2, 3, 4, 5])
+def test_config_parity_both_engines(lib, k, fold):
+    from parity import RTOL, compare
+
+    cfg = small_config(k)
+    err = compare(cfg, fold=fold)
+    assert err['value'] <= RTOL and err['grad'] <= RTOL, err
+    assert compare(cfg, grad=False, fold=fold)['value'] <= RTOL
+
+
+@pytest.mark.parametrize('stat', ['chi2', 'cstat', 'pstat', 'pgstat', 'wstat'])
+def test_engines_agree_per_statistic(lib, stat):
+    """same inputs through both engines: they agree far inside the tolerance"""
+    from parity import gpu_eval, rel_err_grad, rel_err_value
+
+    d = _one_spectrum(E=300, C=130, seed=21)
+    d.spec_counts[::9] = 0.0
+    d.back_counts[::4] = 0.0
+    model = M.CutoffPL() + M.Gauss(El=20.0, sigma=2.0)
+    cfg = dict(data=[d], model=[model], stat=[stat], theta=_theta_for(model, 300, 5))
+    ll_a, g_a = gpu_eval(cfg, fold='i8')
+    ll_b, g_b = gpu_eval(cfg, fold='dmma')
+    assert rel_err_value(ll_a, ll_b) <= 2e-12
+    ok = np.isfinite(g_b)
+    assert np.array_equal(ok, np.isfinite(g_a))
+    assert rel_err_grad(np.where(ok, g_a, 0.0), np.where(ok, g_b, 0.0)) <= 2e-11
+
+
+@pytest.mark.parametrize('slices,tol', [(4, 1e-5), (5, 1e-7), (6, 1e-10), (7, 1e-11)])
+def test_slices_set_the_accuracy(lib, slices, tol):
+    """4 digits = the FP32-class variant of the north star (stated tolerance 1e-5),
+    6 digits = the FP64 tolerance 1e-10, 7 digits = full FP64"""
+    from parity import compare
+
+    err = compare(small_config(2), fold='i8', slices=slices)
+    assert err['value'] <= tol and err['grad'] <= tol, (slices, err)
+
+
+def test_i8_chunking_host_path_and_replica_counts(lib):
+    from parity import RTOL, compare, gpu_eval
+
+    cfg = small_config(4)  # band-sparse response, per-replica counts
+    assert cfg.get('counts_on') is not None
+    err = compare(cfg, fold='i8')
+    assert err['value'] <= RTOL and err['grad'] <= RTOL, err
+    ll_d, g_d = gpu_eval(cfg, fold='i8')
+    ll_h, g_h = gpu_eval(cfg, fold='i8', host=True)
+    assert np.array_equal(ll_d, ll_h) and np.array_equal(g_d, g_h)
+    ll_c, g_c = gpu_eval(cfg, fold='i8', chunk=128)  # chunking must not change a single bit
+    assert np.array_equal(ll_d, ll_c) and np.array_equal(g_d, g_c)
+
+
+def test_i8_nan_rows_stay_nan(lib):
+    """a parameter vector that makes the model NaN yields NaN for that row only"""
+    from parity import gpu_eval
+
+    cfg = small_config(1)
+    cfg['theta'] = cfg['theta'].copy()
+    cfg['theta'][3, 1] = np.nan
+    ll, g = gpu_eval(cfg, fold='i8')
+    assert np.isnan(ll[3]).all() and np.isnan(g[3]).all()
+    keep = np.ones(len(ll), bool)
+    keep[3] = False
+    assert np.isfinite(ll[keep]).all() and np.isfinite(g[keep]).all()
+
+
+@pytest.mark.parametrize('shape', [(128, 64, 128), (300, 200, 1000), (77, 65, 129), (1, 1, 1), (513, 1024, 2048)])
+@pytest.mark.parametrize('slices', [4, 5, 6, 7])
+def test_sliced_gemm_is_an_fp64_class_gemm(lib, shape, slices):
+    """normwise error <= 2^(-8 slices + 6) * (max|a| sum|b| + sum|a| max|b|), rows of wildly
+    different magnitude, mixed signs"""
+    import torch
+
+    from elisa_b200 import sliced_gemm
+
+    m, n, k = shape
+    g = torch.Generator(device='cuda').manual_seed(m * 7 + n)
+    a = torch.randn(m, k, dtype=torch.float64, device='cuda', generator=g)
+    b = torch.randn(n, k, dtype=torch.float64, device='cuda', generator=g)
+    a *= torch.exp(20.0 * torch.randn(m, 1, dtype=torch.float64, device='cuda', generator=g))
+    b *= torch.exp(20.0 * torch.randn(n, 1, dtype=torch.float64, device='cuda', generator=g))
+    d, ms = sliced_gemm(a, b, slices)
+    ref = a @ b.T
+    bound = a.abs().amax(1, keepdim=True) * b.abs().sum(1)[None, :] + a.abs().sum(1, keepdim=True) * b.abs().amax(1)[None, :]
+    err = ((d - ref).abs() / bound).max().item()
+    assert err <= max(2.0 ** (-8 * slices + 6), 4e-16), err
+    assert ms > 0.0
+
+
+def test_sliced_gemm_edge_rows(lib):
+    import torch
+
+    from elisa_b200 import sliced_gemm
+
+    a = torch.rand(130, 300, dtype=torch.float64, device='cuda')
+    b = torch.rand(70, 300, dtype=torch.float64, device='cuda')
+    a[5] = 0.0            # an all-zero row
+    a[6] *= 1e-300        # subnormal-adjacent row
+    a[7] *= 1e300         # huge row
+    a[8, 17] = float('nan')
+    b[9] = 0.0
+    d, _ = sliced_gemm(a, b, 6)
+    ref = a @ b.T
+    assert torch.all(d[5] == 0.0) and torch.all(d[:, 9][torch.arange(130, device='cuda') != 8] == 0.0)
+    assert torch.isnan(d[8]).all()
+    keep = torch.ones(130, dtype=torch.bool, device='cuda')
+    keep[8] = False
+    assert torch.allclose(d[keep], ref[keep], rtol=1e-12, atol=0.0)
