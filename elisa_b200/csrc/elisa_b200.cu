@@ -1138,10 +1138,11 @@ static int launch_fold_i8_ks(ElisaPlan* plan, int cls, const FoldI8Args& fa, con
                                       i8_smem_bytes(KS)));
         configured = true;
     }
-    const int tiles = fa.m_tiles * fa.n_tiles;
-    const int grid = std::min(tiles, sm_count);
+    FoldI8Args f = fa;
+    f.n_groups = (f.n_tiles + I8_GROUP - 1) / I8_GROUP;
+    const int grid = std::min(f.m_tiles * f.n_groups, sm_count);  // items: (row tile, column group)
     ScopedSpan span(plan, cls, st);
-    fold_i8_kernel<KS, Epi><<<grid, I8_THREADS, i8_smem_bytes(KS), st>>>(fa, epi);
+    fold_i8_kernel<KS, Epi><<<grid, I8_THREADS, i8_smem_bytes(KS), st>>>(f, epi);
     if (plan) ++plan->launches;
     CUDA_TRY(cudaGetLastError());
     return ELISA_OK;
@@ -1170,7 +1171,9 @@ static FoldI8Args fold_i8_args(const ElisaPlan* plan, const I8Operand& B, int kb
     fa.kb_hi = B.kb_hi;
     fa.m_tiles = m_tiles;
     fa.n_tiles = B.n_tiles;
-    fa.debug = 0;
+    fa.n_groups = 1;  // set at launch
+    static const int dbg = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;  // timing experiments
+    fa.debug = dbg;
     return fa;
 }
 
@@ -1305,7 +1308,7 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int n, int m_ti
     eg.ldu = sp.E_pad;
     eg.P = plan->P;
     eg.used_mask = sp.model.used_mask;
-    eg.n_part = I8_CG * sp.i8_bwd.n_tiles;
+    eg.n_part = I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP);
     eg.gpart = plan->gpart;
     eg.ld_part = (int)plan->chunk;
     const FoldI8Args fa = fold_i8_args(plan, sp.i8_bwd, round_up(sp.C_pad, I8_BK) / I8_BK, m_tiles);
@@ -1363,8 +1366,8 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     ReduceArgs ra;
     ra.part = plan->part;
     ra.gpart = plan->gpart;
-    ra.tiles_c = i8 ? I8_CG * sp.i8_fwd.n_tiles : sp.fwd.n_tiles;  // partial sums per row
-    ra.tiles_e = i8 ? I8_CG * sp.i8_bwd.n_tiles : sp.bwd.n_tiles;
+    ra.tiles_c = i8 ? I8_CG * ((sp.i8_fwd.n_tiles + I8_GROUP - 1) / I8_GROUP) : sp.fwd.n_tiles;  // partial sums per row
+    ra.tiles_e = i8 ? I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP) : sp.bwd.n_tiles;
     ra.ld = (int)plan->chunk;
     ra.n = n;
     ra.P = plan->P;
@@ -1800,6 +1803,7 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
     FoldI8Args fa;
     fa.A_img = a_img; fa.a_scale = a_sc; fa.kb_a = kb; fa.B_img = b_img; fa.b_scale = b_sc; fa.b_tile_img = timg;
     fa.kb_lo = rng; fa.kb_hi = rng + n_tiles; fa.m_tiles = m_tiles; fa.n_tiles = n_tiles;
+    fa.n_groups = 1;  // set at launch
     fa.debug = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;
     I8EpilogueStore es{D, ldd, m, n};
     int sms = 148;

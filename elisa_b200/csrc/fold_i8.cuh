@@ -245,6 +245,7 @@ struct FoldI8Args {
     const int32_t* kb_lo;       // [n_tiles] k-block range of column tile nt
     const int32_t* kb_hi;
     int32_t m_tiles, n_tiles;
+    int32_t n_groups;  // ceil(n_tiles / I8_GROUP)
     int32_t debug;  // experiments only (elisa_b200_sliced_gemm_dev): 1 = no A copies, 2 = no B copies, 4 = no MMAs, 8 = no epilogue, 16 = no TMEM drain
 };
 
@@ -270,11 +271,23 @@ __device__ __forceinline__ void i8_combine8(uint32_t taddr, double* out) {
     }
 }
 
-// Epilogue interface:  epi.run(x, tile_m, tile_n, row, cg, a_scale_row, b_scale)
-//   x      the thread's I8_TC recombined (unscaled) dot products, columns tile_n * 64 + I8_TC * cg + [0, I8_TC)
-//   row    global row of this thread
+// Work decomposition.  The columns of the output are cut into GROUPS of I8_GROUP tiles (fixed,
+// so that the summation tree of the fused reductions never depends on the batch size); a work
+// ITEM is one row tile x one group, items are numbered row-tile major and dealt round-robin
+// to the persistent CTAs: neighbouring CTAs work on the same row tile at the same time, so
+// its A images are fetched from HBM once and shared through L2 (a whole-row sweep per CTA
+// would put 148 different 1.5 MB A sets in flight and thrash the 126 MB L2).
+//
+// Epilogue interface (one thread = one row of the tile and I8_TC consecutive columns):
+//   State st; epi.begin(st)                      once per group
+//   epi.prefetch(row, tile_n, cg)                before the tile's accumulators are awaited
+//   epi.tile(st, x, tile_n, row, cg, sa, sb)     x = I8_TC recombined (unscaled) dot products,
+//                                                columns tile_n * 64 + I8_TC * cg + [0, I8_TC)
+//   epi.end(st, group, row, cg, sa)              once per group: write the row partials
 // The epilogues walk x in chunks of 8 with a ROLLED loop (the statistic code is long);
 // chunk cc is picked out of the register array with compare-selects, not dynamic indexing.
+constexpr int I8_GROUP = 4;
+
 __device__ __forceinline__ void i8_pick8(const double (&x)[I8_TC], int cc, double* out) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -284,6 +297,20 @@ __device__ __forceinline__ void i8_pick8(const double (&x)[I8_TC], int cc, doubl
         out[j] = v;
     }
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// item -> (row tile, first column tile, one past the last column tile)
+struct I8Item {
+    int mt, g;
+};
+__device__ __forceinline__ I8Item i8_item(const FoldI8Args& a, int item) {
+    I8Item it;
+    it.mt = item / a.n_groups;
+    it.g = item % a.n_groups;
+    return it;
+}
+#define I8_FOR_EACH_TILE(it, a, nt) \
+    for (int nt = (it).g * I8_GROUP, ne_ = min(nt + I8_GROUP, (a).n_tiles); nt < ne_; ++nt)
 
 template <int KS, class Epi>
 __global__ void __launch_bounds__(I8_THREADS, 1)
@@ -325,117 +352,127 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
     tc_fence_after();
     const uint32_t tmem = *slot_ptr;
 
-    const int n_tiles_total = a.m_tiles * a.n_tiles;
+    const int n_items = a.m_tiles * a.n_groups;
 
     if (warp == I8_EPI_WARPS) {
         // ================= producer =================
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
-        for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-            const int mt = t / a.n_tiles, nt = t % a.n_tiles;
-            const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
-            const int8_t* bsrc = a.B_img + (size_t)a.b_tile_img[nt] * B_BLOCK;
-            const int8_t* asrc = a.A_img + ((size_t)mt * a.kb_a + lo) * KS * I8_A_SLICE;
-            for (int kb = lo; kb < hi; ++kb) {
-                mbar_wait(b_empty(bs), bph ^ 1u);
-                if (lane == 0) {
-                    if (a.debug & 2) {
-                        mbar_arrive(b_full(bs));
-                    } else {
-                        mbar_expect_tx(b_full(bs), B_BLOCK);
-                        bulk_g2s(s_B + bs * B_BLOCK, bsrc, B_BLOCK, b_full(bs));
-                    }
-                }
-                bsrc += B_BLOCK;
-                if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
-                for (int i = 0; i < KS; ++i) {
-                    mbar_wait(a_empty(as), aph ^ 1u);
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const I8Item it = i8_item(a, item);
+            I8_FOR_EACH_TILE(it, a, nt) {
+                const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
+                const int8_t* bsrc = a.B_img + (size_t)a.b_tile_img[nt] * B_BLOCK;
+                const int8_t* asrc = a.A_img + ((size_t)it.mt * a.kb_a + lo) * KS * I8_A_SLICE;
+                for (int kb = lo; kb < hi; ++kb) {
+                    mbar_wait(b_empty(bs), bph ^ 1u);
                     if (lane == 0) {
-                        if (a.debug & 1) {
-                            mbar_arrive(a_full(as));
+                        if (a.debug & 2) {
+                            mbar_arrive(b_full(bs));
                         } else {
-                            mbar_expect_tx(a_full(as), I8_A_SLICE);
-                            bulk_g2s(s_A + as * I8_A_SLICE, asrc, I8_A_SLICE, a_full(as));
+                            mbar_expect_tx(b_full(bs), B_BLOCK);
+                            bulk_g2s(s_B + bs * B_BLOCK, bsrc, B_BLOCK, b_full(bs));
                         }
                     }
-                    asrc += I8_A_SLICE;
-                    if (++as == NA) { as = 0; aph ^= 1u; }
+                    bsrc += B_BLOCK;
+                    if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
+                    for (int i = 0; i < KS; ++i) {
+                        mbar_wait(a_empty(as), aph ^ 1u);
+                        if (lane == 0) {
+                            if (a.debug & 1) {
+                                mbar_arrive(a_full(as));
+                            } else {
+                                mbar_expect_tx(a_full(as), I8_A_SLICE);
+                                bulk_g2s(s_A + as * I8_A_SLICE, asrc, I8_A_SLICE, a_full(as));
+                            }
+                        }
+                        asrc += I8_A_SLICE;
+                        if (++as == NA) { as = 0; aph ^= 1u; }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else if (warp == I8_EPI_WARPS + 1) {
         // ================= MMA issuer =================
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0, tph = 0;
-        for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-            const int nt = t % a.n_tiles;
-            const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
-            mbar_wait(t_empty, tph ^ 1u);  // epilogue has drained the accumulators
-            tph ^= 1u;
-            tc_fence_after();
-            for (int kb = lo; kb < hi; ++kb) {
-                mbar_wait(b_full(bs), bph);
-                const uint32_t sb = s_B + bs * B_BLOCK;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const I8Item it = i8_item(a, item);
+            I8_FOR_EACH_TILE(it, a, nt) {
+                const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
+                mbar_wait(t_empty, tph ^ 1u);  // epilogue has drained the accumulators
+                tph ^= 1u;
+                tc_fence_after();
+                for (int kb = lo; kb < hi; ++kb) {
+                    mbar_wait(b_full(bs), bph);
+                    const uint32_t sb = s_B + bs * B_BLOCK;
 #pragma unroll
-                for (int i = 0; i < KS; ++i) {
-                    mbar_wait(a_full(as), aph);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sa = s_A + as * I8_A_SLICE;
+                    for (int i = 0; i < KS; ++i) {
+                        mbar_wait(a_full(as), aph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t sa = s_A + as * I8_A_SLICE;
 #pragma unroll
-                        for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
-                            const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
-                            const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
-                            // (KS - i) * 64 columns in equal parts of <= 256 (multiples of 32)
-                            const int width = (KS - i) * I8_BN;
-                            const int parts = (width + 255) / 256;
-                            const int n = width / parts;  // 192, 160, 224 ...: multiples of 32 for KS <= 8
+                            for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
+                                const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
+                                const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
+                                // (KS - i) * 64 columns in equal parts of <= 256 (multiples of 32)
+                                const int width = (KS - i) * I8_BN;
+                                const int parts = (width + 255) / 256;
+                                const int n = width / parts;  // 192, 160, 224 ...: multiples of 32 for KS <= 8
 #pragma unroll
-                            for (int c0 = 0; c0 < width; c0 += n) {
-                                const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
-                                tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
+                                for (int c0 = 0; c0 < width; c0 += n) {
+                                    const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
+                                    tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
+                                }
                             }
+                            tc_commit(a_empty(as));
                         }
-                        tc_commit(a_empty(as));
+                        __syncwarp();
+                        if (++as == NA) { as = 0; aph ^= 1u; }
                     }
+                    if (lane == 0) tc_commit(b_empty(bs));
                     __syncwarp();
-                    if (++as == NA) { as = 0; aph ^= 1u; }
+                    if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
                 }
-                if (lane == 0) tc_commit(b_empty(bs));
+                if (lane == 0) tc_commit(t_full);
                 __syncwarp();
-                if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
             }
-            if (lane == 0) tc_commit(t_full);
-            __syncwarp();
         }
     } else {
         // ================= epilogue =================
         const int quarter = warp & 3, cg = warp >> 2;
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + cg * I8_TC;
         uint32_t tph = 0;
-        for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-            const int mt = t / a.n_tiles, nt = t % a.n_tiles;
-            const int row = mt * I8_BM + quarter * 32 + lane;
-            const bool empty = a.kb_lo[nt] >= a.kb_hi[nt];  // no k-blocks: accumulators are stale
-            mbar_wait(t_full, tph);
-            tph ^= 1u;
-            tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + cg * I8_TC;
-            // drain: recombine this thread's columns into registers, hand TMEM back to the
-            // MMA warp at once, then run the (long) epilogue math while the next tile accumulates
-            double x[I8_TC];
-            if (a.debug & 16) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const I8Item it = i8_item(a, item);
+            const int row = it.mt * I8_BM + quarter * 32 + lane;
+            const double sa = a.a_scale[row];
+            typename Epi::State st;
+            I8_FOR_EACH_TILE(it, a, nt) {
+                if (nt % I8_GROUP == 0) epi.begin(st);
+                epi.prefetch(row, nt, cg);
+                const bool empty = a.kb_lo[nt] >= a.kb_hi[nt];  // no k-blocks: accumulators are stale
+                mbar_wait(t_full, tph);
+                tph ^= 1u;
+                tc_fence_after();
+                // drain: recombine this thread's columns into registers, hand TMEM back to the
+                // MMA warp at once, then run the (long) epilogue math while the next tile accumulates
+                double x[I8_TC];
+                if ((a.debug & 16) || empty) {
 #pragma unroll
-                for (int j = 0; j < I8_TC; ++j) x[j] = 0.0;
-            } else {
+                    for (int j = 0; j < I8_TC; ++j) x[j] = 0.0;
+                } else {
 #pragma unroll
-                for (int cc = 0; cc < I8_TC / 8; ++cc) i8_combine8<KS>(taddr + 8 * cc, x + 8 * cc);
+                    for (int cc = 0; cc < I8_TC / 8; ++cc) i8_combine8<KS>(taddr + 8 * cc, x + 8 * cc);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty);
+                if (!(a.debug & 8)) epi.tile(st, x, nt, row, cg, sa, a.b_scale + (size_t)nt * I8_BN + cg * I8_TC);
+                if (nt + 1 == ne_) epi.end(st, nt / I8_GROUP, row, cg, sa);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty);
-            if (a.debug & 8) continue;
-            epi.run(x, mt, nt, row, cg, empty ? 0.0 : a.a_scale[row], a.b_scale + (size_t)nt * I8_BN + cg * I8_TC);
         }
     }
 
@@ -447,15 +484,19 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
 }
 
 // ---------------------------------------------------------------------------------------
-// epilogues (thread = one row, I8_TC consecutive columns in chunks of 8)
+// epilogues
 // ---------------------------------------------------------------------------------------
-// plain store: D[row, col] (debug / tests / sites)
+// plain store: D[row, col] (debug / tests)
 struct I8EpilogueStore {
     double* D;
     int64_t ldd;
     int32_t rows, cols;  // bounds of D
-    __device__ __forceinline__ void run(const double (&xx)[I8_TC], int, int tile_n, int row, int cg, double sa,
-                                        const double* sb) const {
+    struct State {};
+    __device__ __forceinline__ void begin(State&) const {}
+    __device__ __forceinline__ void prefetch(int, int, int) const {}
+    __device__ __forceinline__ void end(State&, int, int, int, double) const {}
+    __device__ __forceinline__ void tile(State&, const double (&xx)[I8_TC], int tile_n, int row, int cg, double sa,
+                                         const double* sb) const {
         const int c0 = tile_n * I8_BN + cg * I8_TC;
 #pragma unroll 1
         for (int cc = 0; cc < I8_TC / 8; ++cc) {
@@ -484,7 +525,7 @@ struct ChanArrays {
 };
 
 // forward fold: x = (R u) * area * exposure -> statistic, row partial, W = dl/d(R u)
-// part[(I8_CG * tile_n + cg) * ld_part + row]
+// part[(I8_CG * group + cg) * ld_part + row]
 template <int STAT, bool GRAD>
 struct I8EpilogueStat {
     ChanArrays ch;
@@ -498,13 +539,26 @@ struct I8EpilogueStat {
     double* part;
     int32_t ld_part;
 
-    __device__ __forceinline__ void run(const double (&xx)[I8_TC], int, int tile_n, int row, int cg, double sa,
-                                        const double* sb) const {
+    struct State {
+        double rs;
+    };
+    __device__ __forceinline__ void begin(State& st) const { st.rs = 0.0; }
+    __device__ __forceinline__ void prefetch(int row, int tile_n, int cg) const {
+        if (row >= n_valid) return;
+        const size_t o = (size_t)row * ld_counts + tile_n * I8_BN + cg * I8_TC;
+        if (counts_on != nullptr) prefetch_l2(counts_on + o);
+        if (counts_off != nullptr) prefetch_l2(counts_off + o);
+    }
+    __device__ __forceinline__ void end(State& st, int group, int row, int cg, double) const {
+        part[(size_t)(I8_CG * group + cg) * ld_part + row] = st.rs;
+    }
+    __device__ __forceinline__ void tile(State& st, const double (&xx)[I8_TC], int tile_n, int row, int cg, double sa,
+                                         const double* sb) const {
         const int c0 = tile_n * I8_BN + cg * I8_TC;
         const bool rvalid = row < n_valid;
         const double* con = (counts_on != nullptr && rvalid) ? counts_on + (size_t)row * ld_counts : nullptr;
         const double* coff = (counts_off != nullptr && rvalid) ? counts_off + (size_t)row * ld_counts : nullptr;
-        double rs = 0.0;
+        double rs = st.rs;
 #pragma unroll 1
         for (int cc = 0; cc < I8_TC / 8; ++cc) {
             double x[8];
@@ -545,12 +599,12 @@ struct I8EpilogueStat {
                 for (int j = 0; j < 4; ++j) dst[j] = make_double2(x[2 * j], x[2 * j + 1]);
             }
         }
-        part[(size_t)(I8_CG * tile_n + cg) * ld_part + row] = rs;
+        st.rs = rs;
     }
 };
 
-// transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the thread's 32 energies
-// gpart[(j * n_part + I8_CG * tile_n + cg) * ld_part + row],  n_part = I8_CG * n_tiles
+// transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the thread's energies
+// gpart[(j * n_part + I8_CG * group + cg) * ld_part + row],  n_part = I8_CG * n_groups
 struct I8EpilogueGrad {
     const double* dU;  // [P, rows, ldu]
     int64_t plane;
@@ -561,12 +615,30 @@ struct I8EpilogueGrad {
     double* gpart;
     int32_t ld_part;
 
-    __device__ __forceinline__ void run(const double (&xx)[I8_TC], int, int tile_n, int row, int cg, double sa,
-                                        const double* sb) const {
-        const int e0 = tile_n * I8_BN + cg * I8_TC;
+    struct State {
         double rs[ELISA_MAX_PARAMS];
+    };
+    __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
-        for (int j = 0; j < ELISA_MAX_PARAMS; ++j) rs[j] = 0.0;
+        for (int j = 0; j < ELISA_MAX_PARAMS; ++j) st.rs[j] = 0.0;
+    }
+    // the tile's dU lines (one 128-byte line per parameter and thread) are requested from HBM
+    // while the tile is still accumulating, so that the contraction below finds them in L2
+    __device__ __forceinline__ void prefetch(int row, int tile_n, int cg) const {
+        const double* base = dU + (size_t)row * ldu + tile_n * I8_BN + cg * I8_TC;
+#pragma unroll
+        for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
+            if (p < P && ((used_mask >> p) & 1u)) prefetch_l2(base + (size_t)p * plane);
+    }
+    __device__ __forceinline__ void end(State& st, int group, int row, int cg, double sa) const {
+#pragma unroll
+        for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
+            if (p < P && ((used_mask >> p) & 1u))
+                gpart[((size_t)p * n_part + I8_CG * group + cg) * ld_part + row] = st.rs[p] * sa;
+    }
+    __device__ __forceinline__ void tile(State& st, const double (&xx)[I8_TC], int tile_n, int row, int cg, double,
+                                         const double* sb) const {
+        const int e0 = tile_n * I8_BN + cg * I8_TC;
 #pragma unroll 1
         for (int cc = 0; cc < I8_TC / 8; ++cc) {
             double g[8];
@@ -578,21 +650,17 @@ struct I8EpilogueGrad {
             for (int p = 0; p < ELISA_MAX_PARAMS; ++p) {
                 if (p < P && ((used_mask >> p) & 1u)) {
                     const double2* src = reinterpret_cast<const double2*>(base + (size_t)p * plane);
-                    double s = rs[p];
+                    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const double2 v = src[j];
-                        s = fma(g[2 * j], v.x, s);
-                        s = fma(g[2 * j + 1], v.y, s);
+                        s0 = fma(g[2 * j], v.x, s0);
+                        s1 = fma(g[2 * j + 1], v.y, s1);
                     }
-                    rs[p] = s;
+                    st.rs[p] += s0 + s1;
                 }
             }
         }
-#pragma unroll
-        for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
-            if (p < P && ((used_mask >> p) & 1u))
-                gpart[((size_t)p * n_part + I8_CG * tile_n + cg) * ld_part + row] = rs[p] * sa;
     }
 };
 
