@@ -360,9 +360,11 @@ struct ReduceArgs {
 __global__ void reduce_kernel(const ReduceArgs a) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= a.n) return;
-    double s = 0.0;
-    for (int t = 0; t < a.tiles_c; ++t) s += a.part[(size_t)t * a.ld + row];
-    a.loglike[(size_t)row * a.S + a.s] = s;
+    if (a.part != nullptr) {
+        double s = 0.0;
+        for (int t = 0; t < a.tiles_c; ++t) s += a.part[(size_t)t * a.ld + row];
+        a.loglike[(size_t)row * a.S + a.s] = s;
+    }
     if (a.grad != nullptr) {
         for (int j = 0; j < a.P; ++j) {
             double g = 0.0;
@@ -522,8 +524,8 @@ struct ElisaPlan {
     size_t ev_used = 0;
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double prof_ms[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
-    int64_t prof_n[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
+    double prof_ms[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
+    int64_t prof_n[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace elisa {
@@ -1246,33 +1248,34 @@ static int build_i8_operand(ElisaPlan* plan, int ks, const std::vector<double>& 
     return ELISA_OK;
 }
 
+template <int KS, int STAT, bool GRAD>
+static int launch_stat_slice_ks(ElisaPlan* plan, const StatSliceArgs& a, cudaStream_t st) {
+    const int blocks = (a.rows_pad + 7) / 8;
+    ScopedSpan span(plan, ELISA_PROFILE_STAT, st);
+    stat_slice_kernel<KS, STAT, GRAD><<<blocks, 256, 0, st>>>(a);
+    ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
 template <int STAT, bool GRAD>
-static int launch_stat_fold_i8(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid, int m_tiles, const double* on,
-                               const double* off, cudaStream_t st) {
-    I8EpilogueStat<STAT, GRAD> epi;
-    epi.ch = sp.chan_view();
-    epi.counts_on = on ? on + sp.counts_off : nullptr;
-    epi.counts_off = off ? off + sp.counts_off : nullptr;
-    epi.ld_counts = plan->sum_C;
-    epi.n_valid = n_valid;
-    epi.C = sp.C;
-    epi.W = plan->W;
-    epi.ldw = sp.C_pad;
-    epi.part = plan->part;
-    epi.ld_part = (int)plan->chunk;
-    const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
-    return launch_fold_i8(plan, plan->ks, ELISA_PROFILE_FOLD, fa, epi, plan->sm_count, st);
+static int launch_stat_slice(ElisaPlan* plan, const StatSliceArgs& a, cudaStream_t st) {
+    switch (plan->ks) {
+#define X(K) case K: return launch_stat_slice_ks<K, STAT, GRAD>(plan, a, st);
+        ELISA_FOR_EACH_KS(X)
+#undef X
+        default: return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
+    }
 }
 
 template <bool GRAD>
-static int launch_stat_fold_i8_any(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid, int m_tiles,
-                                   const double* on, const double* off, cudaStream_t st) {
+static int launch_stat_slice_any(ElisaPlan* plan, const SpectrumPlan& sp, const StatSliceArgs& a, cudaStream_t st) {
     switch (sp.stat) {
-        case ELISA_STAT_CHI2: return launch_stat_fold_i8<ELISA_STAT_CHI2, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
-        case ELISA_STAT_CSTAT: return launch_stat_fold_i8<ELISA_STAT_CSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
-        case ELISA_STAT_PSTAT: return launch_stat_fold_i8<ELISA_STAT_PSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
-        case ELISA_STAT_PGSTAT: return launch_stat_fold_i8<ELISA_STAT_PGSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
-        default: return launch_stat_fold_i8<ELISA_STAT_WSTAT, GRAD>(plan, sp, n_valid, m_tiles, on, off, st);
+        case ELISA_STAT_CHI2: return launch_stat_slice<ELISA_STAT_CHI2, GRAD>(plan, a, st);
+        case ELISA_STAT_CSTAT: return launch_stat_slice<ELISA_STAT_CSTAT, GRAD>(plan, a, st);
+        case ELISA_STAT_PSTAT: return launch_stat_slice<ELISA_STAT_PSTAT, GRAD>(plan, a, st);
+        case ELISA_STAT_PGSTAT: return launch_stat_slice<ELISA_STAT_PGSTAT, GRAD>(plan, a, st);
+        default: return launch_stat_slice<ELISA_STAT_WSTAT, GRAD>(plan, a, st);
     }
 }
 
@@ -1295,13 +1298,33 @@ static int slice_chunk_operand(ElisaPlan* plan, const double* X, int ld, int col
     return launch_slice(plan, plan->ks, a, cls, st);
 }
 
-static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int n, int m_tiles, bool want_grad,
-                        const double* on, const double* off, cudaStream_t st) {
+// forward fold (plain store) -> statistic + digits of W -> transposed fold with the gradient epilogue
+static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, int m_tiles, bool want_grad,
+                        const double* on, const double* off, double* loglike, cudaStream_t st) {
     int rc;
     if ((rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st))) return rc;
-    if (!want_grad) return launch_stat_fold_i8_any<false>(plan, sp, n, m_tiles, on, off, st);
-    if ((rc = launch_stat_fold_i8_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
-    if ((rc = slice_chunk_operand(plan, plan->W, sp.C_pad, sp.C, n, m_tiles, ELISA_PROFILE_SLICE, st))) return rc;
+    {
+        I8EpilogueStore es{plan->W, sp.C_pad, m_tiles * I8_BM, sp.C_pad};
+        const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
+        if ((rc = launch_fold_i8(plan, plan->ks, ELISA_PROFILE_FOLD, fa, es, plan->sm_count, st))) return rc;
+    }
+    StatSliceArgs a;
+    a.X = plan->W;
+    a.ldx = sp.C_pad;
+    a.ch = sp.chan_view();
+    a.counts_on = on ? on + sp.counts_off : nullptr;
+    a.counts_off = off ? off + sp.counts_off : nullptr;
+    a.ld_counts = plan->sum_C;
+    a.n_valid = n;
+    a.rows_pad = m_tiles * I8_BM;
+    a.C = sp.C;
+    a.loglike = loglike + s;
+    a.ll_stride = plan->S;
+    a.img = plan->A_img;
+    a.scale = plan->a_scale;
+    a.kb_total = round_up(sp.C_pad, I8_BK) / I8_BK;
+    if (!want_grad) return launch_stat_slice_any<false>(plan, sp, a, st);
+    if ((rc = launch_stat_slice_any<true>(plan, sp, a, st))) return rc;
     I8EpilogueGrad eg;
     eg.dU = plan->dU;
     eg.plane = (int64_t)m_tiles * I8_BM * sp.E_pad;
@@ -1347,7 +1370,8 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
         return rc;
     const bool i8 = sp.use_i8();
     if (i8) {
-        if ((rc = run_chunk_i8(plan, sp, n, m_tiles, want_grad, on, off, st))) return rc;
+        if ((rc = run_chunk_i8(plan, sp, s, n, m_tiles, want_grad, on, off, loglike, st))) return rc;
+        if (!want_grad) return ELISA_OK;  // the statistic kernel wrote loglike itself
     } else if (want_grad) {
         if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
         EpilogueGrad eg;
@@ -1364,7 +1388,7 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
         if ((rc = launch_stat_gemm_any<false>(plan, sp, n, m_tiles, on, off, st))) return rc;
     }
     ReduceArgs ra;
-    ra.part = plan->part;
+    ra.part = i8 ? nullptr : plan->part;  // sliced-integer fold: loglike is already final
     ra.gpart = plan->gpart;
     ra.tiles_c = i8 ? I8_CG * ((sp.i8_fwd.n_tiles + I8_GROUP - 1) / I8_GROUP) : sp.fwd.n_tiles;  // partial sums per row
     ra.tiles_e = i8 ? I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP) : sp.bwd.n_tiles;

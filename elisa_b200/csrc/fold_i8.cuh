@@ -156,6 +156,68 @@ struct SliceArgs {
 // One warp per row.  Pass 1: amax (and a non-finite flag).  Pass 2: q = rint(x * f) as
 // int64, balanced digits from the low end (d = sign-extended low byte, q = (q - d) >> 8),
 // four consecutive k per lane packed into one 32-bit store per slice.
+// Scale factors of a row with largest magnitude amax: q = rint(x * f1 * f2), |q| <= TOP * 256^(KS-1).
+// f1 * f2 = TOP * 256^(KS-1) / amax, split so that neither factor nor the intermediate leaves the
+// normal range (amax may sit anywhere in [1e-300, 1e300]).  Returns the row scale
+// (D = sc_a * sc_b * sum_o acc_o 256^-o); NaN for a row with a non-finite element.
+template <int KS>
+__device__ __forceinline__ double slice_scale(double amax, bool bad, double& f1, double& f2) {
+    f1 = f2 = 0.0;
+    if (bad) return __longlong_as_double(0x7ff8000000000000LL);
+    if (!(amax > 0.0)) return 0.0;
+    int ex;
+    const double m = frexp(amax, &ex);  // amax = m 2^ex, m in [0.5, 1)
+    const int h = ex / 2;
+    f1 = ldexp(1.0, -h);
+    f2 = ldexp((double)I8_TOP_DIGIT / m, 8 * (KS - 1) - (ex - h));
+    return amax / (double)I8_TOP_DIGIT;
+}
+
+// Digits of one row (one warp): balanced base-256 digits from the low end (d = sign-extended
+// low byte, q = (q - d) >> 8), four consecutive k per lane packed into one 32-bit store per
+// slice, k-blocks [kb0, kb1) into the images starting at img0.
+template <int KS>
+__device__ __forceinline__ void slice_row_digits(const double* x, bool live, bool aligned, int cols, double f1,
+                                                 double f2, int rr, int tile_rows, int kb0, int kb1, int8_t* img,
+                                                 int64_t img0, int lane) {
+    const int sub = (rr >> 3) * 1024 + (rr & 7) * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2);
+    const size_t slice_bytes = (size_t)tile_rows * I8_BK;
+    for (int kb = kb0; kb < kb1; ++kb) {
+        const int k = kb * I8_BK + 4 * lane;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live && f2 != 0.0) {
+            if (k + 3 < cols && aligned) {
+                const double2 p0 = *reinterpret_cast<const double2*>(x + k);
+                const double2 p1 = *reinterpret_cast<const double2*>(x + k + 2);
+                v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (k + t < cols) v[t] = x[k + t];
+            }
+        }
+        long long q[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) q[t] = __double2ll_rn(v[t] * f1 * f2);
+        uint32_t w[KS];
+#pragma unroll
+        for (int i = KS - 1; i >= 0; --i) {
+            uint32_t pack = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const long long d = (long long)(int8_t)(q[t] & 0xff);
+                q[t] = (q[t] - d) >> 8;
+                pack |= ((uint32_t)d & 0xffu) << (8 * t);
+            }
+            w[i] = pack;
+        }
+        int8_t* base = img + (size_t)(img0 + (kb - kb0)) * KS * slice_bytes + sub;
+#pragma unroll
+        for (int i = 0; i < KS; ++i) *reinterpret_cast<uint32_t*>(base + i * slice_bytes) = w[i];
+    }
+}
+
+// One warp per row.  Pass 1: amax (and a non-finite flag).  Pass 2: the digits.
 template <int KS>
 __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a) {
     const int lane = threadIdx.x & 31;
@@ -180,56 +242,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     bad = __any_sync(0xffffffffu, bad);
-
-    // x * f1 * f2 with f1 * f2 = TOP * 256^(KS-1) / amax, split so neither factor nor the
-    // intermediate leaves the normal range (amax may sit anywhere in [1e-300, 1e300])
-    double f1 = 0.0, f2 = 0.0, sc = 0.0;
-    if (amax > 0.0 && !bad) {
-        int ex;
-        const double m = frexp(amax, &ex);  // amax = m 2^ex, m in [0.5, 1)
-        const int h = ex / 2;
-        f1 = ldexp(1.0, -h);
-        f2 = ldexp((double)I8_TOP_DIGIT / m, 8 * (KS - 1) - (ex - h));
-        sc = amax / (double)I8_TOP_DIGIT;  // D = sc_a * sc_b * Horner(acc), see combine()
-    }
-    if (bad) sc = __longlong_as_double(0x7ff8000000000000LL);  // NaN row -> NaN results
+    double f1, f2;
+    const double sc = slice_scale<KS>(amax, bad, f1, f2);
     if (lane == 0) a.scale[row] = sc;
-
-    const int sub = (rr >> 3) * 1024 + (rr & 7) * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2);
-    const size_t slice_bytes = (size_t)a.tile_rows * I8_BK;
-    for (int kb = kb0; kb < kb1; ++kb) {
-        const int k = kb * I8_BK + 4 * lane;
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
-        if (live && f2 != 0.0) {
-            if (k + 3 < a.cols && (a.ld & 1) == 0) {
-                const double2 p0 = *reinterpret_cast<const double2*>(x + k);
-                const double2 p1 = *reinterpret_cast<const double2*>(x + k + 2);
-                v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-                    if (k + t < a.cols) v[t] = x[k + t];
-            }
-        }
-        long long q[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) q[t] = __double2ll_rn(v[t] * f1 * f2);
-        uint32_t w[KS];
-#pragma unroll
-        for (int i = KS - 1; i >= 0; --i) {
-            uint32_t pack = 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const long long d = (long long)(int8_t)(q[t] & 0xff);
-                q[t] = (q[t] - d) >> 8;
-                pack |= ((uint32_t)d & 0xffu) << (8 * t);
-            }
-            w[i] = pack;
-        }
-        int8_t* base = a.img + (size_t)(img0 + (kb - kb0)) * KS * slice_bytes + sub;
-#pragma unroll
-        for (int i = 0; i < KS; ++i) *reinterpret_cast<uint32_t*>(base + i * slice_bytes) = w[i];
-    }
+    slice_row_digits<KS>(x, live, (a.ld & 1) == 0, a.cols, f1, f2, rr, a.tile_rows, kb0, kb1, a.img, img0, lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -504,9 +520,15 @@ struct I8EpilogueStore {
             i8_pick8(xx, cc, x);
             if (row < rows) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = c0 + 8 * cc + j;
-                    if (c < cols) D[(size_t)row * ldd + c] = x[j] * sa * sb[8 * cc + j];
+                for (int j = 0; j < 8; ++j) x[j] *= sa * sb[8 * cc + j];
+                double* dst = D + (size_t)row * ldd + c0 + 8 * cc;
+                if (c0 + 8 * cc + 8 <= cols && (ldd & 1) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(x[2 * j], x[2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + 8 * cc + j < cols) dst[j] = x[j];
                 }
             }
         }
@@ -663,5 +685,89 @@ struct I8EpilogueGrad {
         }
     }
 };
+
+// ---------------------------------------------------------------------------------------
+// statistic + digits of W in one pass over the folded rates (one warp per row)
+// ---------------------------------------------------------------------------------------
+// The forward fold stores X = R u with the plain epilogue; this kernel turns each row into
+// its log-likelihood (fixed summation order: lane-serial over channels lane, lane + 32, ...,
+// then an xor tree -- bit-reproducible and independent of the batch size), overwrites the
+// row with W = d loglike / d (R u), and slices W into the A-operand images of the transposed
+// fold while the row is still in L1/L2.  At 64 warps per SM the long FP64 chains of the
+// statistics (log, sqrt, divisions) hide each other; inside the fold kernel's 16 epilogue
+// warps they were the critical path.
+struct StatSliceArgs {
+    double* X;  // [rows_pad, ldx]  in: R u   out: W
+    int32_t ldx;
+    ChanArrays ch;
+    const double* counts_on;
+    const double* counts_off;
+    int64_t ld_counts;
+    int32_t n_valid, rows_pad, C;
+    double* loglike;  // element [row * ll_stride]
+    int64_t ll_stride;
+    // digits of W (GRAD only)
+    int8_t* img;
+    double* scale;
+    int32_t kb_total;
+};
+
+template <int KS, int STAT, bool GRAD>
+__global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= a.rows_pad) return;
+    const bool live = row < a.n_valid;
+    double* x = a.X + (size_t)row * a.ldx;
+    double rs = 0.0, amax = 0.0;
+    bool bad = false;
+    if (live) {
+        const double* con = a.counts_on ? a.counts_on + (size_t)row * a.ld_counts : nullptr;
+        const double* coff = a.counts_off ? a.counts_off + (size_t)row * a.ld_counts : nullptr;
+        for (int col = lane; col < a.C; col += 32) {
+            ChannelData d;
+            const double sc = a.ch.scale[col];
+            d.on = a.ch.on[col];
+            d.gof_on = a.ch.gof_on[col];
+            d.off = d.sigma = d.ratio = d.gof_off = 0.0;
+            if (STAT == ELISA_STAT_CHI2) d.sigma = a.ch.sigma[col];
+            if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+                d.off = a.ch.off[col];
+                d.ratio = a.ch.ratio[col];
+            }
+            if (STAT == ELISA_STAT_PGSTAT) d.sigma = a.ch.sigma[col];
+            if (STAT == ELISA_STAT_WSTAT) d.gof_off = a.ch.gof_off[col];
+            if (con != nullptr) {
+                d.on = con[col];
+                if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
+            }
+            if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr) {
+                d.off = coff[col];
+                if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
+            }
+            double dx = 0.0;
+            rs += stat_channel<STAT, GRAD>(x[col] * sc, d, dx);
+            if (GRAD) {
+                const double w = dx * sc;
+                x[col] = w;
+                bad |= !(fabs(w) <= 1.79e308);
+                amax = fmax(amax, fabs(w));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        if (lane == 0) a.loglike[(size_t)row * a.ll_stride] = rs;
+    }
+    if (!GRAD) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    bad = __any_sync(0xffffffffu, bad);
+    double f1, f2;
+    const double sc = slice_scale<KS>(amax, bad, f1, f2);
+    if (lane == 0) a.scale[row] = sc;
+    __syncwarp();  // the row of W written above is read back by other lanes
+    slice_row_digits<KS>(x, live, (a.ldx & 1) == 0, a.C, f1, f2, row % I8_BM, I8_BM, 0, a.kb_total, a.img,
+                         (int64_t)(row / I8_BM) * a.kb_total, lane);
+}
 
 }  // namespace elisa
