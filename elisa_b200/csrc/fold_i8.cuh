@@ -173,9 +173,9 @@ __device__ __forceinline__ double slice_scale(double amax, bool bad, double& f1,
     return amax / (double)I8_TOP_DIGIT;
 }
 
-// Digits of one row (one warp): balanced base-256 digits from the low end (d = sign-extended
-// low byte, q = (q - d) >> 8), four consecutive k per lane packed into one 32-bit store per
-// slice, k-blocks [kb0, kb1) into the images starting at img0.
+// Digits of one row (one warp): balanced base-256 digits of q = rint(x f1 f2), four consecutive
+// k per lane packed into one 32-bit store per slice, k-blocks [kb0, kb1) into the images
+// starting at img0.
 template <int KS>
 __device__ __forceinline__ void slice_row_digits(const double* x, bool live, bool aligned, int cols, double f1,
                                                  double f2, int rr, int tile_rows, int kb0, int kb1, int8_t* img,
@@ -196,20 +196,26 @@ __device__ __forceinline__ void slice_row_digits(const double* x, bool live, boo
                     if (k + t < cols) v[t] = x[k + t];
             }
         }
-        long long q[4];
+        // q + bias (bias = 0x80 in each of the KS digit bytes) has the plain base-256 digits
+        // u_k = d_k + 128 of the balanced digits d_k; xor with the bias turns each byte back into
+        // d_k as an int8.  Byte k of the four elements is then gathered with PRMT.
+        constexpr unsigned long long bias = 0x8080808080808080ull >> (8 * (8 - KS));
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) q[t] = __double2ll_rn(v[t] * f1 * f2);
-        uint32_t w[KS];
+        for (int t = 0; t < 4; ++t) {
+            const unsigned long long u = ((unsigned long long)__double2ll_rn(v[t] * f1 * f2) + bias) ^ bias;
+            lo[t] = (uint32_t)u;
+            hi[t] = (uint32_t)(u >> 32);
+        }
+        uint32_t w[KS];  // w[i]: digit of significance KS-1-i (slice 0 = most significant)
 #pragma unroll
-        for (int i = KS - 1; i >= 0; --i) {
-            uint32_t pack = 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const long long d = (long long)(int8_t)(q[t] & 0xff);
-                q[t] = (q[t] - d) >> 8;
-                pack |= ((uint32_t)d & 0xffu) << (8 * t);
-            }
-            w[i] = pack;
+        for (int i = 0; i < KS; ++i) {
+            const int k = KS - 1 - i;  // byte index in u
+            const uint32_t* src = k < 4 ? lo : hi;
+            const uint32_t sel = 0x0040u + 0x0011u * (uint32_t)(k & 3);  // bytes k of (a, b) -> low half
+            const uint32_t p01 = __byte_perm(src[0], src[1], sel);
+            const uint32_t p23 = __byte_perm(src[2], src[3], sel);
+            w[i] = __byte_perm(p01, p23, 0x5410);
         }
         int8_t* base = img + (size_t)(img0 + (kb - kb0)) * KS * slice_bytes + sub;
 #pragma unroll
