@@ -475,6 +475,10 @@ struct GridView {
     const double* __restrict__ emid;    // [E]      0.5 (E_i + E_{i+1})
     const double* __restrict__ lnmid;   // [E]      ln(emid)
     int E;
+    // grid values of the calling lane's edge, loaded one pass ahead by the unfold kernel
+    // (has_point != 0): E, ln E of edge min(e, E) and of the midpoint of bin min(e, E - 1)
+    int has_point;
+    double pE, pl, pEm, plm;
 };
 
 constexpr int LEAF_MAX_NC = 3;
@@ -534,7 +538,7 @@ template <int KIND, typename T>
 __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, const GridView& gv, int e) {
     using C = Comp<KIND>;
     const int ec = e <= gv.E ? e : gv.E;  // lanes beyond the grid re-evaluate the last edge
-    const double E0 = gv.egrid[ec], l0 = gv.lngrid[ec];
+    const double E0 = gv.has_point ? gv.pE : gv.egrid[ec], l0 = gv.has_point ? gv.pl : gv.lngrid[ec];
     T g0[C::NG], g1[C::NG];
     C::edge(p, c, E0, l0, g0);
 #pragma unroll
@@ -547,7 +551,7 @@ __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, con
         if (method == ELISA_METHOD_SIMPSON) {
             const int em = e < gv.E ? e : gv.E - 1;
             T gm[C::NG];
-            C::edge(p, c, gv.emid[em], gv.lnmid[em], gm);
+            C::edge(p, c, gv.has_point ? gv.pEm : gv.emid[em], gv.has_point ? gv.plm : gv.lnmid[em], gm);
             const double factor = add ? (E1 - E0) / 6.0 : 1.0 / 6.0;
             return factor * (g0[0] + 4.0 * gm[0] + g1[0]);
         }

@@ -821,6 +821,9 @@ static const char* const k_src_components =
 static const char* const k_src_skel =
 #include "embedded_unfold_skel_cuh.inc"
     ;
+static const char* const k_src_slice =
+#include "embedded_slice_i8_cuh.inc"
+    ;
 
 struct NvrtcApi {
     void* handle = nullptr;
@@ -867,7 +870,8 @@ static std::string hexd(double v) {
 }
 
 // The translation unit for one model: see unfold_skel.cuh.
-static std::string generate_unfold_source(const ModelDev& m, int P) {
+// ks > 0: the kernels also write the digits of U for the sliced-integer fold (fold_i8.cuh).
+static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
     std::string s;
     s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\nstruct Model {\n";
     s += "  template <typename T> struct Pre {\n";
@@ -915,9 +919,11 @@ static std::string generate_unfold_source(const ModelDev& m, int P) {
         }
     }
     s += "    return " + stack.back() + ";\n  }\n};\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_val(const UnfoldCore a) { unfold_generic<Model, double>(a); }\n";
+    const std::string k = std::to_string(ks);
+    s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_val(const UnfoldCore a) { unfold_generic<Model, double, " +
+         k + ">(a); }\n";
     s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_grad(const UnfoldCore a) { unfold_generic<Model, Dual<" +
-         std::to_string(P) + ">>(a); }\n";
+         std::to_string(P) + ">, " + k + ">(a); }\n";
     return s;
 }
 
@@ -928,10 +934,10 @@ static bool compile_unfold_source(const std::string& src, std::vector<char>* cub
         *why = "libnvrtc.so.12 not found";
         return false;
     }
-    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h};
-    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h"};
+    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h, k_src_slice};
+    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h", "slice_i8.cuh"};
     nvrtcProgram prog = nullptr;
-    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 4, headers, names) != NVRTC_SUCCESS) {
+    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 5, headers, names) != NVRTC_SUCCESS) {
         *why = "nvrtcCreateProgram failed";
         return false;
     }
@@ -956,10 +962,10 @@ static bool compile_unfold_source(const std::string& src, std::vector<char>* cub
 
 // Compile (or fetch from the in-process cache) the specialised kernels of one model.
 // Returns nullptr with `why` set when runtime compilation is not possible.
-static const JitKernels* jit_unfold(const ModelDev& m, int P, std::string* why) {
+static const JitKernels* jit_unfold(const ModelDev& m, int P, int ks, std::string* why) {
     static std::mutex mu;
     static std::map<std::string, JitKernels*> cache;
-    const std::string src = generate_unfold_source(m, P);
+    const std::string src = generate_unfold_source(m, P, ks);
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(src);
     if (it != cache.end()) return it->second;
@@ -1016,8 +1022,12 @@ static void drain_spans(ElisaPlan* plan) {
 }
 
 // ---- launches ------------------------------------------------------------------------
+// fused_digits (nullable): set to whether the kernel also wrote the digits of U into plan->A_img /
+// a_scale (runtime-specialised kernel, sliced-integer fold, one warp per row); requesting it
+// (non-null) is what asks for the fusion.
 static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* theta, int n_valid, int n_rows,
-                         bool grad, double* U, double* dU, int ld, int e_pad, bool clip, cudaStream_t st) {
+                         bool grad, double* U, double* dU, int ld, int e_pad, bool clip, cudaStream_t st,
+                         bool* fused_digits = nullptr) {
     UnfoldArgs args;
     UnfoldCore& a = args.core;
     a.gv = sp.grid_view();
@@ -1040,7 +1050,17 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.dU = dU;
     a.plane = (int64_t)n_rows * ld;
     a.used_mask = sp.model.used_mask;
-    a.pad_ = 0;
+    a.kb_total = round_up(ld, I8_BK) / I8_BK;
+    a.img = nullptr;
+    a.scale = nullptr;
+    a.gv.has_point = 0;
+    if (fused_digits != nullptr) {
+        *fused_digits = sp.jit != nullptr && sp.use_i8() && n_seg == 1 && plan->A_img != nullptr;
+        if (*fused_digits) {
+            a.img = plan->A_img;
+            a.scale = plan->a_scale;
+        }
+    }
     const int64_t warps = (int64_t)n_rows * n_seg;
     const int blocks = (int)((warps + UNFOLD_WARPS - 1) / UNFOLD_WARPS);
     const int threads = UNFOLD_WARPS * 32;
@@ -1300,9 +1320,11 @@ static int slice_chunk_operand(ElisaPlan* plan, const double* X, int ld, int col
 
 // forward fold (plain store) -> statistic + digits of W -> transposed fold with the gradient epilogue
 static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, int m_tiles, bool want_grad,
-                        const double* on, const double* off, double* loglike, cudaStream_t st) {
+                        bool have_digits, const double* on, const double* off, double* loglike, cudaStream_t st) {
     int rc;
-    if ((rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st))) return rc;
+    if (!have_digits &&  // the unfold kernel did not slice U itself (interpreter kernel / split rows)
+        (rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st)))
+        return rc;
     {
         I8EpilogueStore es{plan->W, sp.C_pad, m_tiles * I8_BM, sp.C_pad};
         const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
@@ -1366,11 +1388,13 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     const int m_tiles = n_rows / GEMM_BM;
     const bool want_grad = grad != nullptr;
     int rc;
-    if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st)))
+    bool fused_digits = false;
+    if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st,
+                            sp.use_i8() ? &fused_digits : nullptr)))
         return rc;
     const bool i8 = sp.use_i8();
     if (i8) {
-        if ((rc = run_chunk_i8(plan, sp, s, n, m_tiles, want_grad, on, off, loglike, st))) return rc;
+        if ((rc = run_chunk_i8(plan, sp, s, n, m_tiles, want_grad, fused_digits, on, off, loglike, st))) return rc;
         if (!want_grad) return ELISA_OK;  // the statistic kernel wrote loglike itself
     } else if (want_grad) {
         if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
@@ -1514,7 +1538,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         const bool off = (desc->flags & ELISA_FLAG_NO_JIT) || (env && strcmp(env, "0") == 0);
         if (!off) {
             std::string why;
-            plan->spec[s].jit = jit_unfold(plan->spec[s].model, plan->P, &why);
+            plan->spec[s].jit = jit_unfold(plan->spec[s].model, plan->P, plan->ks, &why);
             if (plan->spec[s].jit == nullptr && ((desc->flags & ELISA_FLAG_REQUIRE_JIT) || (env && strcmp(env, "require") == 0))) {
                 rc = fail(ELISA_ERR_UNSUPPORTED, "runtime specialisation required but unavailable: " + why);
                 break;
@@ -1754,7 +1778,7 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
     ModelDev m;
     int rc = build_model(*model, n_params, &m);
     if (rc) return rc;
-    const std::string src = generate_unfold_source(m, n_params);
+    const std::string src = generate_unfold_source(m, n_params, ELISA_FOLD_SLICES_DEFAULT);
     if (source_out != nullptr && source_cap > 0) {
         const size_t n = std::min<size_t>(src.size(), (size_t)source_cap - 1);
         memcpy(source_out, src.data(), n);

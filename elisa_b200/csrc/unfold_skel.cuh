@@ -13,6 +13,7 @@
 // passes of 31 bins (see components.cuh).
 #pragma once
 #include "components.cuh"
+#include "slice_i8.cuh"
 
 namespace elisa {
 
@@ -31,7 +32,11 @@ struct UnfoldCore {
     double* dU;       // [P, n_rows, ld] or nullptr
     int64_t plane;    // n_rows * ld
     uint32_t used_mask;
-    int32_t pad_;
+    int32_t kb_total;  // k-blocks per row tile of the digit images
+    // digits of U for the sliced-integer fold, written by the kernel itself when the whole row
+    // belongs to one warp (n_seg == 1) and the kernel was specialised with KS > 0; else nullptr
+    int8_t* img;
+    double* scale;
 };
 
 constexpr int UNFOLD_WARPS = 4;
@@ -46,7 +51,7 @@ __device__ __forceinline__ void unfold_zero(const UnfoldCore& a, size_t row_off,
 }
 
 template <typename T>
-__device__ __forceinline__ void unfold_store(const UnfoldCore& a, size_t off, const T& res) {
+__device__ __forceinline__ double unfold_store(const UnfoldCore& a, size_t off, const T& res) {
     const double v = value(res);
     bool pass = true;
     double u = v;
@@ -61,9 +66,10 @@ __device__ __forceinline__ void unfold_store(const UnfoldCore& a, size_t off, co
         for (int j = 0; j < Scalar<T>::NP; ++j)
             if (j < a.P && ((a.used_mask >> j) & 1u)) a.dU[j * a.plane + off] = pass ? res.d[j] : 0.0;
     }
+    return u;
 }
 
-template <class Model, typename T>
+template <class Model, typename T, int KS = 0>
 __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
     constexpr bool GRAD = Scalar<T>::NP > 0;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -75,18 +81,64 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
     const int e_hi = min(e_lo + a.seg_len, E);
     const bool last_seg = seg == a.n_seg - 1;
     const size_t row_off = (size_t)row * a.ld;
+    const bool slice = KS > 0 && a.img != nullptr;  // host guarantees n_seg == 1 then
     if (row >= a.n_valid) {  // padding rows: zeros, so that the fold sees finite operands
         unfold_zero(a, row_off, e_lo, last_seg ? a.e_pad : e_hi, lane, GRAD);
+        if constexpr (KS > 0) {
+            if (slice) {
+                if (lane == 0) a.scale[row] = 0.0;
+                slice_row_digits<KS>(a.U + row_off, false, false, E, 0.0, 0.0, row % I8_BM, I8_BM, 0, a.kb_total,
+                                     a.img, (int64_t)(row / I8_BM) * a.kb_total, lane);
+            }
+        }
         return;
     }
     typename Model::template Pre<T> pre;
     Model::template pre<T>(a.theta + (size_t)row * a.P, pre);
+    // the grid values of a pass are loaded during the previous one
+    GridView gv = a.gv;
+    gv.has_point = 1;
+    auto load_point = [&](int e, double& pE, double& pl, double& pEm, double& plm) {
+        const int ec = e <= E ? e : E, em = e < E ? e : E - 1;
+        pE = a.gv.egrid[ec];
+        pl = a.gv.lngrid[ec];
+        pEm = a.gv.emid[em];
+        plm = a.gv.lnmid[em];
+    };
+    double nE, nl, nEm, nlm;
+    load_point(e_lo + lane, nE, nl, nEm, nlm);
+    double amax = 0.0;
+    bool bad = false;
     for (int e0 = e_lo; e0 < e_hi; e0 += 31) {
         const int e = e0 + lane;
-        const T res = Model::template bin<T>(pre, a.gv, e);
-        if (lane < 31 && e < e_hi) unfold_store<T>(a, row_off + e, res);
+        gv.pE = nE;
+        gv.pl = nl;
+        gv.pEm = nEm;
+        gv.plm = nlm;
+        if (e0 + 31 < e_hi) load_point(e + 31, nE, nl, nEm, nlm);
+        const T res = Model::template bin<T>(pre, gv, e);
+        if (lane < 31 && e < e_hi) {
+            const double u = unfold_store<T>(a, row_off + e, res);
+            if constexpr (KS > 0) {
+                bad |= !(fabs(u) <= 1.79e308);
+                amax = fmax(amax, fabs(u));
+            }
+        }
     }
     if (last_seg) unfold_zero(a, row_off, E, a.e_pad, lane, GRAD);
+    if constexpr (KS > 0) {
+        if (slice) {  // digits of the finished row, read back while it is still in L2
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            bad = __any_sync(0xffffffffu, bad);
+            double f1, f2;
+            const double sc = slice_scale<KS>(amax, bad, f1, f2);
+            if (lane == 0) a.scale[row] = sc;
+            __syncwarp();
+            slice_row_digits<KS>(a.U + row_off, true, (a.ld & 1) == 0, E, f1, f2, row % I8_BM, I8_BM, 0, a.kb_total,
+                                 a.img, (int64_t)(row / I8_BM) * a.kb_total, lane);
+        }
+    }
 }
 
 }  // namespace elisa

@@ -38,6 +38,8 @@
 #define ELISA_B200_H_
 
 #ifdef __CUDACC_RTC__ /* runtime-compiled device code (csrc/unfold_skel.cuh): no host headers */
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
 typedef int int32_t;
 typedef unsigned int uint32_t;
 typedef long long int64_t;
