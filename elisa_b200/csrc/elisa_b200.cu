@@ -1356,6 +1356,7 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
     eg.n_part = I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP);
     eg.gpart = plan->gpart;
     eg.ld_part = (int)plan->chunk;
+    eg.dbg = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;
     const FoldI8Args fa = fold_i8_args(plan, sp.i8_bwd, round_up(sp.C_pad, I8_BK) / I8_BK, m_tiles);
     return launch_fold_i8(plan, plan->ks, ELISA_PROFILE_TFOLD, fa, eg, plan->sm_count, st);
 }

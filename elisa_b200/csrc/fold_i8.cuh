@@ -573,6 +573,7 @@ struct I8EpilogueGrad {
     int32_t n_part;
     double* gpart;
     int32_t ld_part;
+    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = no prefetch
 
     struct State {
         double rs[ELISA_MAX_PARAMS];
@@ -584,6 +585,7 @@ struct I8EpilogueGrad {
     // the tile's dU lines (one 128-byte line per parameter and thread) are requested from HBM
     // while the tile is still accumulating, so that the contraction below finds them in L2
     __device__ __forceinline__ void prefetch(int row, int tile_n, int cg) const {
+        if (dbg & 64) return;
         const double* base = dU + (size_t)row * ldu + tile_n * I8_BN + cg * I8_TC;
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
@@ -612,7 +614,7 @@ struct I8EpilogueGrad {
                     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const double2 v = src[j];
+                        const double2 v = (dbg & 32) ? make_double2(g[j], g[j + 4]) : src[j];
                         s0 = fma(g[2 * j], v.x, s0);
                         s1 = fma(g[2 * j + 1], v.y, s1);
                     }
