@@ -342,6 +342,12 @@ def run_b200(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner
+    # under NCCL_DEBUG=VERSION) are sent to stderr, and print() writes to the saved descriptor
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, 'w', buffering=1)
     if args.impl == 'reference':
         run_reference(args)
     else:

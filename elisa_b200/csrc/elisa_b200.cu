@@ -464,6 +464,7 @@ struct PackedDevice {
 // Static (B) operand of the sliced-integer fold: digit images per (64-row tile, k-block).
 struct I8Operand {
     int8_t* img = nullptr;
+    double* abs_sum = nullptr;    // [n_tiles * 64] sum_k |row| (accuracy guard)
     double* scale = nullptr;      // [n_tiles * 64]
     int64_t* tile_img = nullptr;  // [n_tiles] first image of the tile
     int32_t* kb_lo = nullptr;     // [n_tiles] stored k-block range
@@ -509,6 +510,7 @@ struct ElisaPlan {
     int ks = 0;  // slices per operand (0: every spectrum folds with DMMA)
     int8_t* A_img = nullptr;
     double* a_scale = nullptr;
+    unsigned long long* guard = nullptr;  // [2] accuracy guard of the integer fold (stat_slice_kernel)
     int sm_count = 148;
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
@@ -1228,6 +1230,16 @@ static int build_i8_operand(ElisaPlan* plan, int ks, const std::vector<double>& 
         n_images += kb_hi[t] - kb_lo[t];
     }
     int rc;
+    {
+        std::vector<double> asum((size_t)n_tiles * I8_BN, 0.0);
+        for (int r = 0; r < rows; ++r) {
+            const double* x = dense.data() + (size_t)r * K;
+            double t = 0.0;
+            for (int k = 0; k < K; ++k) t += fabs(x[k]);
+            asum[r] = t;
+        }
+        if ((rc = upload(plan, asum, &out->abs_sum))) return rc;
+    }
     if ((rc = upload(plan, tile_img, &out->tile_img))) return rc;
     if ((rc = upload(plan, kb_lo, &out->kb_lo))) return rc;
     if ((rc = upload(plan, kb_hi, &out->kb_hi))) return rc;
@@ -1345,6 +1357,13 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
     a.img = plan->A_img;
     a.scale = plan->a_scale;
     a.kb_total = round_up(sp.C_pad, I8_BK) / I8_BK;
+    a.colsum = sp.i8_fwd.abs_sum;
+    a.guard = plan->guard;
+    a.guard_eta = ldexp(1.0, -8 * plan->ks);
+    // trip level: 3x below the 1e-10 tolerance; the estimate adds the per-channel terms linearly
+    // (errors of random sign add in quadrature), so it is already pessimistic
+    static const double tol = getenv("ELISA_B200_GUARD_TOL") ? atof(getenv("ELISA_B200_GUARD_TOL")) : 3e-11;
+    a.guard_tol = tol;
     if (!want_grad) return launch_stat_slice_any<false>(plan, sp, a, st);
     if ((rc = launch_stat_slice_any<true>(plan, sp, a, st))) return rc;
     I8EpilogueGrad eg;
@@ -1592,6 +1611,12 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                 plan->owned.push_back(plan->A_img);
                 plan->workspace_bytes += bytes;
                 rc = alloc(&plan->a_scale, chunk);
+                if (rc == ELISA_OK) {
+                    double* g = nullptr;
+                    rc = alloc(&g, 2);
+                    plan->guard = reinterpret_cast<unsigned long long*>(g);
+                    if (rc == ELISA_OK && cudaMemset(g, 0, 16) != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "cudaMemset failed");
+                }
             }
         }
     }
@@ -1794,6 +1819,26 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
     return plan->spec[spectrum].use_i8() ? plan->ks : 0;
+}
+
+int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    unsigned long long h[2] = {0, 0};
+    if (plan->guard != nullptr) {
+        int prev = 0;
+        CUDA_TRY(cudaGetDevice(&prev));
+        CUDA_TRY(cudaSetDevice(plan->device));
+        CUDA_TRY(cudaMemcpy(h, plan->guard, 16, cudaMemcpyDeviceToHost));
+        if (reset) CUDA_TRY(cudaMemset(plan->guard, 0, 16));
+        cudaSetDevice(prev);
+    }
+    if (flagged) *flagged = (int64_t)h[0];
+    if (worst) {
+        double w;
+        memcpy(&w, &h[1], 8);
+        *worst = w;
+    }
+    return ELISA_OK;
 }
 
 int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, int64_t ldb, int32_t m, int32_t n,

@@ -645,10 +645,17 @@ struct StatSliceArgs {
     int32_t n_valid, rows_pad, C;
     double* loglike;  // element [row * ll_stride]
     int64_t ll_stride;
-    // digits of W (GRAD only)
+    // digits of W (GRAD only); on entry scale[] holds the row scales of U's digits
     int8_t* img;
     double* scale;
     int32_t kb_total;
+    // accuracy guard of the integer fold: colsum[c] = sum_e |R[e, c]|; guard[0] counts the rows
+    // whose estimated log-likelihood error exceeds guard_tol * max(|loglike|, 1), guard[1] keeps
+    // the largest estimate / max(|loglike|, 1) seen (bits of a non-negative double)
+    const double* colsum;
+    unsigned long long* guard;
+    double guard_eta;  // typical normwise error of the engine, 2^(-8 KS)
+    double guard_tol;
 };
 
 template <int KS, int STAT, bool GRAD>
@@ -658,9 +665,10 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     if (row >= a.rows_pad) return;
     const bool live = row < a.n_valid;
     double* x = a.X + (size_t)row * a.ldx;
-    double rs = 0.0, amax = 0.0;
+    double rs = 0.0, amax = 0.0, eb = 0.0;
     bool bad = false;
     if (live) {
+        const double u_max = a.scale[row] * (double)I8_TOP_DIGIT;  // largest |U| of the row
         const double* con = a.counts_on ? a.counts_on + (size_t)row * a.ld_counts : nullptr;
         const double* coff = a.counts_off ? a.counts_off + (size_t)row * a.ld_counts : nullptr;
         for (int col = lane; col < a.C; col += 32) {
@@ -685,7 +693,8 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
                 if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
             }
             double dx = 0.0;
-            rs += stat_channel<STAT, GRAD>(x[col] * sc, d, dx);
+            rs += stat_channel<STAT, true>(x[col] * sc, d, dx);
+            eb = fma(fabs(dx * sc), a.colsum[col], eb);
             if (GRAD) {
                 const double w = dx * sc;
                 x[col] = w;
@@ -694,8 +703,18 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-        if (lane == 0) a.loglike[(size_t)row * a.ll_stride] = rs;
+        for (int o = 16; o > 0; o >>= 1) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            eb += __shfl_xor_sync(0xffffffffu, eb, o);
+        }
+        if (lane == 0) {
+            a.loglike[(size_t)row * a.ll_stride] = rs;
+            // first-order estimate of the log-likelihood error the sliced fold may have caused:
+            // sum_c |dl/dx_c| * (typical normwise error of x_c)
+            const double est = a.guard_eta * u_max * eb / fmax(fabs(rs), 1.0);
+            if (est > a.guard_tol) atomicAdd(a.guard, 1ull);
+            if (est > 0.0 && est < 1.79e308) atomicMax(a.guard + 1, (unsigned long long)__double_as_longlong(est));
+        }
     }
     if (!GRAD) return;
 #pragma unroll

@@ -137,12 +137,41 @@ class Likelihood:
             _lib.check(lib.elisa_b200_plan_set_channel_width(self._h, i, _ptr(d.channel_width)))
         self.n_channels = [d.n_channels for d in data]
         self.sum_channels = int(sum(self.n_channels))
+        # fold=None: the integer fold runs guarded -- a call in which the statistic kernel flags a
+        # row (estimated log-likelihood error of the sliced fold above 3e-11, see
+        # elisa_b200_plan_fold_guard) is re-evaluated by an FP64 DMMA twin of this plan
+        self._auto_guard = fold is None and any(self.fold_slices)
+        self._twin = None
+        self._twin_args = dict(device=self.device, chunk=int(chunk), specialise=specialise)
+        self.guard_fallbacks = 0
 
     # -- lifetime ------------------------------------------------------------------
     def close(self):
+        if getattr(self, '_twin', None) is not None:
+            self._twin.close()
+            self._twin = None
         if getattr(self, '_h', None) is not None and self._h.value:
             self._lib.elisa_b200_plan_destroy(self._h)
             self._h = None
+
+    def fold_guard(self, reset: bool = True):
+        """(rows flagged, largest relative error estimate) of the integer fold's accuracy guard
+        since the last reset (elisa_b200_plan_fold_guard); synchronises the device."""
+        self._torch.cuda.synchronize(self.device)
+        n, w = C.c_int64(0), C.c_double(0.0)
+        _lib.check(self._lib.elisa_b200_plan_fold_guard(self._h, C.byref(n), C.byref(w), 1 if reset else 0))
+        return int(n.value), float(w.value)
+
+    def _guard_tripped(self) -> bool:
+        if not self._auto_guard:
+            return False
+        flagged, _ = self.fold_guard(reset=True)
+        if flagged == 0:
+            return False
+        self.guard_fallbacks += 1
+        if self._twin is None:
+            self._twin = type(self)(self.data, self.model, self.stat, fold='dmma', **self._twin_args)
+        return True
 
     def __del__(self):
         try:
@@ -218,6 +247,8 @@ class Likelihood:
             on, off = self._counts(counts_on, n), self._counts(counts_off, n)
             out = torch.empty((n, len(self.data)), dtype=torch.float64, device=t.device)
             _lib.check(self._lib.elisa_b200_loglike_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), self._stream()))
+        if self._guard_tripped():
+            return self._twin.loglike(t, on, off)
         return out
 
     def loglike_and_grad(self, theta, counts_on=None, counts_off=None):
@@ -231,6 +262,8 @@ class Likelihood:
             out = torch.empty((n, len(self.data)), dtype=torch.float64, device=t.device)
             grad = torch.empty((n, len(self.data), self._P), dtype=torch.float64, device=t.device)
             _lib.check(self._lib.elisa_b200_loglike_grad_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), _dev_ptr(grad), self._stream()))
+        if self._guard_tripped():
+            return self._twin.loglike_and_grad(t, on, off)
         return out, grad[:, :, : self.nparam]
 
     def deviance(self, theta, **kw):
@@ -302,6 +335,9 @@ class Likelihood:
         ll = np.empty((n, len(self.data)))
         g = np.empty((n, len(self.data), self._P)) if grad else None
         _lib.check(self._lib.elisa_b200_loglike_grad_host(self._h, _ptr(theta), _ptr(on), _ptr(off), n, _ptr(ll), _ptr(g)))
+        if self._guard_tripped():
+            return self._twin.loglike_and_grad_host(theta[:, : max(self.nparam, 1)] if self.nparam else theta[:, :0],
+                                                    counts_on, counts_off, grad)
         return (ll, g[:, :, : self.nparam]) if grad else ll
 
 

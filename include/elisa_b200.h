@@ -252,6 +252,17 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
 /* slices of the sliced-integer fold used for `spectrum` (ELISA_FLAG_FOLD_*), 0 if it folds
  * with FP64 DMMA, -1 on a bad argument                                                   */
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
+/* Accuracy guard of the sliced-integer fold.  Its error is bounded relative to (largest
+ * model bin of the row) x (column sum of the response), not to each folded count, so a
+ * channel predicted ~2^40 below the brightest part of the model loses relative accuracy.
+ * While evaluating, the statistic kernel estimates to first order the log-likelihood error
+ * this may have caused, sum_c |dl/dx_c| * 2^(-8 slices) * max_e|u| * sum_e|R[e,c]|, and counts
+ * the rows where it exceeds 3e-11 * max(|loglike|, 1) (env ELISA_B200_GUARD_TOL).  This call returns that count and the
+ * largest relative estimate since the last reset (synchronise the stream of the evaluation
+ * first).  Rows are never flagged on the BASELINE configurations (estimates 7e-14 .. 1.4e-11); a
+ * caller that sees flagged > 0 re-evaluates with an ELISA_FLAG_FOLD_DMMA plan -- the Python
+ * host side (elisa_b200.Likelihood, fold=None) does so automatically.                      */
+int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset);
 /* The fold engine on its own: D[m, n] = A[m, k] . B[n, k]^T in FP64-class accuracy on the
  * int8 tensor cores (device pointers, row-major, k <= 16384, slices 4..7).  Allocates its
  * digit images, runs on `cuda_stream`, synchronises; `ms` (nullable) receives the device

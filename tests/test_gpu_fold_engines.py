@@ -123,3 +123,51 @@ def test_sliced_gemm_edge_rows(lib):
     keep = torch.ones(130, dtype=torch.bool, device='cuda')
     keep[8] = False
     assert torch.allclose(d[keep], ref[keep], rtol=1e-12, atol=0.0)
+
+
+def test_accuracy_guard_quiet_on_baseline_shapes_and_trips_on_starved_channels(lib):
+    """The statistic kernel estimates the log-likelihood error the sliced fold may have caused.
+    BASELINE-like inputs stay ~1e4 below the trip level; a model whose prediction in populated
+    channels lies ~1e-30 below its brightest bin (line only, diagonal response) trips it, and
+    the guarded Python host side re-evaluates with the FP64 DMMA twin."""
+    from parity import RTOL, oracle_eval, rel_err_grad, rel_err_value
+
+    from elisa_b200 import Likelihood
+    from elisa_b200.data import FixedData
+
+    cfg = small_config(2)
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold='i8')
+    lk.loglike_and_grad(cfg['theta'])
+    flagged, worst = lk.fold_guard()
+    assert flagged == 0 and 0.0 < worst < 3e-12, (flagged, worst)
+    lk.close()
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'])
+    assert lk._auto_guard
+    lk.loglike_and_grad(cfg['theta'])
+    assert lk.guard_fallbacks == 0
+    lk.close()
+
+    # narrow line through a diagonal response, counts in every channel
+    E = C = 256
+    eg = np.linspace(1.0, 10.0, E + 1)
+    rng = np.random.default_rng(3)
+    d = FixedData('starved', eg, rng.poisson(20.0, C).astype(float), np.ones(C), 100.0,
+                  response_matrix=np.eye(E) * 50.0)
+    U = M.UniformParameter
+    model = M.Gauss(El=U('El', 5.0, 1.0, 10.0), sigma=U('sigma', 0.05, 0.01, 1.0), K=U('K', 10.0, 1e-3, 1e3))
+    theta = _theta_for(model, 40, 11)
+    cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
+    ll_ref, g_ref = oracle_eval(cfg)
+    lk = Likelihood([d], model, ['cstat'], fold='i8')        # unguarded integer fold: flags rows
+    ll_i8, _ = lk.loglike_and_grad(theta)
+    flagged, worst = lk.fold_guard()
+    assert flagged == len(theta) and worst > 1e-6, (flagged, worst)
+    lk.close()
+    lk = Likelihood([d], model, ['cstat'])                    # guarded: falls back to DMMA
+    ll, g = lk.loglike_and_grad(theta)
+    assert lk.guard_fallbacks == 1
+    assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL
+    assert rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
+    ll_h, g_h = lk.loglike_and_grad_host(theta)
+    assert lk.guard_fallbacks == 2 and rel_err_value(ll_h, ll_ref) <= RTOL
+    lk.close()
