@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_COMP_PARAMS = 5
 MAX_COMPONENTS = 8
 MAX_PARAMS = 16
@@ -34,6 +34,9 @@ class ComponentDesc(C.Structure):
         ('param_src', C.c_int32 * MAX_COMP_PARAMS),
         ('param_const', C.c_double * MAX_COMP_PARAMS),
         ('aux', C.c_double * 2),
+        ('table_energy', c_double_p),
+        ('table_xsect', c_double_p),
+        ('table_len', C.c_int32),
     ]
 
 

@@ -336,6 +336,19 @@ struct Comp<ELISA_COMP_PLENFLUX> : CompPLFlux<true> {};
 template <>
 struct Comp<ELISA_COMP_PLPHFLUX> : CompPLFlux<false> {};
 
+template <>
+struct Comp<ELISA_COMP_PHOTONABS> {  // PhotonAbsorption.continuum, models/mul.py:360-388
+    // the "ln E" slot of edge() carries sigma(E) of the leaf's table (leaf_bin_pc)
+    static constexpr int NP = 1, NG = 1, NC = 1, RULE = RULE_CONTINUUM_MUL;
+    static constexpr bool TABLE = true;
+    template <typename T>
+    __device__ static void pre(const T*, const double*, T*) {}
+    template <typename T>
+    __device__ static void edge(const T* p, const T*, double, double sigma, T* g) {
+        g[0] = ex(-(p[0] * sigma));
+    }
+};
+
 // ------------------------------------------------------------------ multiplicative
 template <>
 struct Comp<ELISA_COMP_CONSTANT> {  // Constant.integral, models/mul.py:54-56
@@ -456,7 +469,7 @@ __host__ __device__ inline int comp_num_params(int kind) {
         case ELISA_COMP_PLENFLUX: case ELISA_COMP_PLPHFLUX: case ELISA_COMP_POWERLAW: case ELISA_COMP_EDGE:
         case ELISA_COMP_HIGHECUT: case ELISA_COMP_PLABS: return 2;
         case ELISA_COMP_SMOOTHLYBROKENPL: return 5;
-        case ELISA_COMP_CONSTANT: case ELISA_COMP_EXPABS: return 1;
+        case ELISA_COMP_CONSTANT: case ELISA_COMP_EXPABS: case ELISA_COMP_PHOTONABS: return 1;
         default: return -1;
     }
 }
@@ -479,6 +492,18 @@ struct GridView {
     // (has_point != 0): E, ln E of edge min(e, E) and of the midpoint of bin min(e, E - 1)
     int has_point;
     double pE, pl, pEm, plm;
+    // table components (ELISA_COMP_PHOTONABS): sigma at the edges [E + 1] / bin midpoints [E]
+    // of leaf i in tab[2 i] / tab[2 i + 1]
+    const double* tab[2 * ELISA_MAX_COMPONENTS];
+};
+
+template <class C, class = void>
+struct IsTable {
+    static constexpr bool value = false;
+};
+template <class C>
+struct IsTable<C, decltype((void)C::TABLE)> {
+    static constexpr bool value = true;
 };
 
 constexpr int LEAF_MAX_NC = 3;
@@ -535,10 +560,15 @@ __device__ __forceinline__ void leaf_pre(double* scratch, const double* aux) {
 // Bin value of leaf KIND for bin e (valid on lanes 0..30 of the pass, for e < E), given the
 // parameters p and the hoisted constants c.
 template <int KIND, typename T>
-__device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, const GridView& gv, int e) {
+__device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, const GridView& gv, int e, int leaf = 0) {
     using C = Comp<KIND>;
     const int ec = e <= gv.E ? e : gv.E;  // lanes beyond the grid re-evaluate the last edge
-    const double E0 = gv.has_point ? gv.pE : gv.egrid[ec], l0 = gv.has_point ? gv.pl : gv.lngrid[ec];
+    const double E0 = gv.has_point ? gv.pE : gv.egrid[ec];
+    double l0;
+    if constexpr (IsTable<C>::value)
+        l0 = gv.tab[2 * leaf][ec];
+    else
+        l0 = gv.has_point ? gv.pl : gv.lngrid[ec];
     T g0[C::NG], g1[C::NG];
     C::edge(p, c, E0, l0, g0);
 #pragma unroll
@@ -551,7 +581,12 @@ __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, con
         if (method == ELISA_METHOD_SIMPSON) {
             const int em = e < gv.E ? e : gv.E - 1;
             T gm[C::NG];
-            C::edge(p, c, gv.has_point ? gv.pEm : gv.emid[em], gv.has_point ? gv.plm : gv.lnmid[em], gm);
+            double lm;
+            if constexpr (IsTable<C>::value)
+                lm = gv.tab[2 * leaf + 1][em];
+            else
+                lm = gv.has_point ? gv.plm : gv.lnmid[em];
+            C::edge(p, c, gv.has_point ? gv.pEm : gv.emid[em], lm, gm);
             const double factor = add ? (E1 - E0) / 6.0 : 1.0 / 6.0;
             return factor * (g0[0] + 4.0 * gm[0] + g1[0]);
         }
@@ -562,14 +597,14 @@ __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, con
 
 // Same, with p and c decoded from the interpreter's shared-memory scratch slot.
 template <int KIND, typename T>
-__device__ __forceinline__ T leaf_bin(const double* scratch, int method, const GridView& gv, int e) {
+__device__ __forceinline__ T leaf_bin(const double* scratch, int method, const GridView& gv, int e, int leaf = 0) {
     using C = Comp<KIND>;
     T p[C::NP], c[C::NC];
 #pragma unroll
     for (int k = 0; k < C::NP; ++k) p[k] = Flat<T>::seed(scratch[k], k);
 #pragma unroll
     for (int k = 0; k < C::NC; ++k) c[k] = Flat<T>::get(scratch + ELISA_MAX_COMP_PARAMS + k * Flat<T>::SIZE);
-    return leaf_bin_pc<KIND, T>(p, c, method, gv, e);
+    return leaf_bin_pc<KIND, T>(p, c, method, gv, e, leaf);
 }
 
 }  // namespace elisa

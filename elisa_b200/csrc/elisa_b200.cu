@@ -99,7 +99,7 @@ __device__ __forceinline__ typename StackT<PU>::type scatter_leaf(const Dual<NPK
     X(ELISA_COMP_GAUSS) X(ELISA_COMP_LORENTZ) X(ELISA_COMP_OTTB) X(ELISA_COMP_OTTS) X(ELISA_COMP_PLENFLUX)         \
     X(ELISA_COMP_PLPHFLUX) X(ELISA_COMP_POWERLAW) X(ELISA_COMP_SMOOTHLYBROKENPL) X(ELISA_COMP_CONSTANT)            \
     X(ELISA_COMP_EDGE) X(ELISA_COMP_EXPABS) X(ELISA_COMP_EXPFAC) X(ELISA_COMP_GABS) X(ELISA_COMP_HIGHECUT)         \
-    X(ELISA_COMP_PLABS)
+    X(ELISA_COMP_PLABS) X(ELISA_COMP_PHOTONABS)
 
 // Ahead-of-time interpreter: runs any model program without runtime compilation (the
 // fallback when NVRTC is unavailable, and the cross-check of the specialised kernels).
@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_
     case KIND:                                                                                             \
         if constexpr (GRAD)                                                                                \
             val = scatter_leaf<PU, Comp<KIND>::NP>(                                                        \
-                leaf_bin<KIND, Dual<Comp<KIND>::NP>>(scr[op], L.method, a.gv, e), L.src);                  \
+                leaf_bin<KIND, Dual<Comp<KIND>::NP>>(scr[op], L.method, a.gv, e, op), L.src);                  \
         else                                                                                               \
-            val = leaf_bin<KIND, double>(scr[op], L.method, a.gv, e);                                      \
+            val = leaf_bin<KIND, double>(scr[op], L.method, a.gv, e, op);                                      \
         break;
                     ELISA_FOR_EACH_KIND(X)
 #undef X
@@ -479,6 +479,7 @@ struct SpectrumPlan {
     ModelDev model;
     // device arrays
     double *egrid = nullptr, *lngrid = nullptr, *emid = nullptr, *lnmid = nullptr;
+    double* tab[2 * ELISA_MAX_COMPONENTS] = {};  // sigma(E) of table components at edges / midpoints
     double* chan = nullptr;  // 9 arrays of C_pad: scale on off sigma ratio gof_on gof_off area inv_width
     PackedDevice fwd, bwd;   // R [E, C] tiled over C ; R^T [C, E] tiled over E
     I8Operand i8_fwd, i8_bwd;  // digit images of R^T rows (channels) / R rows (energies); img == nullptr: DMMA fold
@@ -486,7 +487,11 @@ struct SpectrumPlan {
     int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
     int64_t nnz = 0;
     const struct JitKernels* jit = nullptr;  // runtime-specialised unfold (nullptr: interpreter)
-    GridView grid_view() const { return GridView{egrid, lngrid, emid, lnmid, E}; }
+    GridView grid_view() const {
+        GridView g{egrid, lngrid, emid, lnmid, E};
+        for (int i = 0; i < 2 * ELISA_MAX_COMPONENTS; ++i) g.tab[i] = tab[i];
+        return g;
+    }
     ChanArrays chan_view() const {
         return ChanArrays{chan, chan + C_pad, chan + 2 * C_pad, chan + 3 * C_pad,
                           chan + 4 * C_pad, chan + 5 * C_pad, chan + 6 * C_pad};
@@ -619,6 +624,14 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
         L.aux[1] = c.aux[1];
         if ((c.kind == ELISA_COMP_PLENFLUX || c.kind == ELISA_COMP_PLPHFLUX) && !(c.aux[0] > 0.0 && c.aux[1] > c.aux[0]))
             return fail(ELISA_ERR_INVALID, "model: PLPhFlux/PLEnFlux need 0 < emin < emax in aux");
+        if (c.kind == ELISA_COMP_PHOTONABS) {
+            if (c.table_energy == nullptr || c.table_xsect == nullptr || c.table_len < 2)
+                return fail(ELISA_ERR_INVALID, "model: PhotonAbsorption needs a cross-section table (>= 2 points)");
+            for (int k = 0; k < c.table_len; ++k)
+                if (!(c.table_energy[k] > 0.0) || !(c.table_xsect[k] > 0.0) ||
+                    (k > 0 && !(c.table_energy[k] > c.table_energy[k - 1])))
+                    return fail(ELISA_ERR_INVALID, "model: cross-section table must be positive with increasing energies");
+        }
     }
     // postfix program; a single component may omit it
     if (md.n_ops == 0 && md.n_components == 1) {
@@ -698,6 +711,29 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
     if ((rc = upload(plan, lg, &sp->lngrid))) return rc;
     if ((rc = upload(plan, em, &sp->emid))) return rc;
     if ((rc = upload(plan, lm, &sp->lnmid))) return rc;
+    // table components: sigma on the photon grid, _make_interp of models/mul.py:274-283 --
+    // exp(interp(log e, log energy, log xsect, left='extrapolate', right='extrapolate'))
+    for (int i = 0; i < sd.model.n_components; ++i) {
+        const ElisaComponentDesc& c = sd.model.components[i];
+        if (c.kind != ELISA_COMP_PHOTONABS) continue;
+        const int n = c.table_len;
+        std::vector<double> xp(n), fp(n);
+        for (int k = 0; k < n; ++k) {
+            xp[k] = log(c.table_energy[k]);
+            fp[k] = log(c.table_xsect[k]);
+        }
+        auto sigma = [&](double lx) {
+            int j = (int)(std::upper_bound(xp.begin(), xp.end(), lx) - xp.begin()) - 1;  // xp[j] <= lx < xp[j+1]
+            j = std::max(0, std::min(j, n - 2));                                          // end segments extrapolate
+            const double t = (lx - xp[j]) / (xp[j + 1] - xp[j]);
+            return exp(fp[j] + t * (fp[j + 1] - fp[j]));
+        };
+        std::vector<double> se(E + 1), sm(E);
+        for (int e = 0; e <= E; ++e) se[e] = sigma(log(eg[e]));
+        for (int e = 0; e < E; ++e) sm[e] = sigma(log(em[e]));
+        if ((rc = upload(plan, se, &sp->tab[2 * i]))) return rc;
+        if ((rc = upload(plan, sm, &sp->tab[2 * i + 1]))) return rc;
+    }
 
     // per-channel data, padded with benign values
     const int Cp = sp->C_pad;
@@ -906,7 +942,7 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
             const std::string id = std::to_string(op);
             if (!emitted[op]) {
                 s += "    const T v" + id + " = leaf_bin_pc<" + std::to_string(m.leaf[op].kind) + ", T>(s.p" + id + ", s.c" +
-                     id + ", " + std::to_string(m.leaf[op].method) + ", gv, e);\n";
+                     id + ", " + std::to_string(m.leaf[op].method) + ", gv, e, " + id + ");\n";
                 emitted[op] = true;
             }
             stack.push_back("v" + id);

@@ -217,9 +217,47 @@ GAbs = _component('GAbs', 20, 'mul', True, [('El', 1.0, 0.0, 1e6), ('sigma', 0.0
 HighECut = _component('HighECut', 21, 'mul', True, [('Ec', 10.0, 1e-4, 1e6), ('Ef', 15.0, 1e-4, 1e6)])
 PLAbs = _component('PLAbs', 22, 'mul', False, [('alpha', 2.0, 0.0, 5.0), ('K', 1.0, 0.0, 100.0)])
 
+
+
+class PhotonAbsorption(Component):
+    """PhotonAbsorption (models/mul.py:302-388): ``exp(-nH * sigma(E))`` with sigma(E)
+    log-log interpolated (and extrapolated) from a cross-section table.  The reference reads
+    its tables from ``models/tables/xsect.hdf5`` (dataset ``energy`` and
+    ``{phabs|tbabs|wabs}/{xsect}/{abund}``) with h5py; here the caller hands the two arrays
+    in -- ``PhAbs(f['energy'][:], f['phabs/vern/angr'][:])`` on the reference side."""
+
+    _kind = 23
+    _config = (ParamConfig('nH', 1.0, 0.0, 1e6),)
+    _numerical = True
+    type = 'mul'
+
+    def __init__(self, table_energy, table_xsect, nH=None, method: str | None = None):
+        super().__init__(nH=nH, method=method)
+        e = np.ascontiguousarray(table_energy, dtype=np.float64)
+        x = np.ascontiguousarray(table_xsect, dtype=np.float64)
+        if e.ndim != 1 or e.shape != x.shape or e.size < 2:
+            raise ValueError('cross-section table: two 1-d arrays of equal length >= 2')
+        if not (np.all(e > 0) and np.all(np.diff(e) > 0) and np.all(x > 0)):
+            raise ValueError('cross-section table: positive values, increasing energies')
+        self.table_energy, self.table_xsect = e, x
+
+
+class PhAbs(PhotonAbsorption):  # models/mul.py:429-511
+    pass
+
+
+class TBAbs(PhotonAbsorption):  # models/mul.py:514-585
+    pass
+
+
+class WAbs(PhotonAbsorption):  # models/mul.py:588-640
+    pass
+
+
 ADDITIVE = (Band, BandEp, BentPL, Blackbody, BlackbodyRad, BrokenPL, Compt, CutoffPL, Gauss, Lorentz, OTTB, OTTS,
             PLEnFlux, PLPhFlux, PowerLaw, SmoothlyBrokenPL)
 MULTIPLICATIVE = (Constant, Edge, ExpAbs, ExpFac, GAbs, HighECut, PLAbs)
+TABLE_MULTIPLICATIVE = (PhAbs, TBAbs, WAbs)  # need a cross-section table argument
 
 
 # --------------------------------------------------------------------------- compiled model
@@ -289,6 +327,10 @@ class CompiledModel:
                         raise ValueError(f'{c.name}.{pname} is free but not among the fit parameters')
                     d.param_src[k] = j
             d.aux[0], d.aux[1] = c.aux
+            if isinstance(c, PhotonAbsorption):
+                d.table_energy = c.table_energy.ctypes.data_as(_lib.c_double_p)
+                d.table_xsect = c.table_xsect.ctypes.data_as(_lib.c_double_p)
+                d.table_len = c.table_energy.size
         ops = (_lib.C.c_int32 * len(self.ops))(*self.ops)
         md = _lib.ModelDesc()
         md.n_components = len(self.leaves)
@@ -311,6 +353,9 @@ class CompiledModel:
                 extra = {'method': m.method}
                 if m._kind in (PLEnFlux._kind, PLPhFlux._kind):
                     extra.update(emin=m.aux[0], emax=m.aux[1])
+                if isinstance(m, PhotonAbsorption):
+                    extra.update(table_energy=m.table_energy, table_xsect=m.table_xsect)
+                    return ('comp', 'PhotonAbsorption', refs, extra)
                 return ('comp', m.name, refs, extra)
             return (m.op, rec(m.lhs), rec(m.rhs))
 

@@ -51,7 +51,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define ELISA_B200_ABI_VERSION 1
+#define ELISA_B200_ABI_VERSION 2
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define ELISA_OK 0
@@ -92,7 +92,10 @@ extern "C" {
 #define ELISA_COMP_GABS 20            /* mul.py:195-204  (El, sigma, tau)                 */
 #define ELISA_COMP_HIGHECUT 21        /* mul.py:236-240  (Ec, Ef)                         */
 #define ELISA_COMP_PLABS 22           /* mul.py:266-271  (alpha, K)                       */
-#define ELISA_COMP_COUNT 23
+#define ELISA_COMP_PHOTONABS 23       /* mul.py:274-299,360-388 (nH); PhAbs / TBAbs / WAbs:
+                                        * exp(-nH sigma(E)), sigma from the cross-section table
+                                        * of the descriptor, log-log interpolated, extrapolated  */
+#define ELISA_COMP_COUNT 24
 
 /* numerical bin integration: elisa/models/model.py:1731-1761 */
 #define ELISA_METHOD_TRAPZ 0
@@ -118,6 +121,14 @@ typedef struct ElisaComponentDesc {
     int32_t param_src[ELISA_MAX_COMP_PARAMS];
     double param_const[ELISA_MAX_COMP_PARAMS];
     double aux[2]; /* PLPhFlux / PLEnFlux: emin, emax (add.py:662-680)               */
+    /* ELISA_COMP_PHOTONABS: one cross-section table of the reference's tables/xsect.hdf5
+     * (its 'energy' dataset and '{phabs|tbabs|wabs}/{xsect}/{abund}'), table_len >= 2
+     * increasing positive energies; NULL / 0 for every other kind.  The plan evaluates
+     * sigma on the photon grid at creation exactly as mul.py:274-283 does
+     * (exp(interp(log e, log energy, log xsect)) with linear extrapolation).          */
+    const double* table_energy;
+    const double* table_xsect;
+    int32_t table_len;
 } ElisaComponentDesc;
 
 typedef struct ElisaModelDesc {

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 
 F64 = torch.float64
@@ -243,6 +244,29 @@ def _plabs(egrid, p, **_):
     return (f[..., 1:] - f[..., :-1]) / (egrid[..., 1:] - egrid[..., :-1])
 
 
+def _make_interp(table_energy, table_xsect):
+    """_make_interp, models/mul.py:274-283: exp(jnp.interp(log e, log energy, log xsect,
+    left='extrapolate', right='extrapolate')).  jnp.interp: i = clip(searchsorted(xp, x,
+    'right'), 1, n - 1); f = fp[i-1] + (x - xp[i-1]) / (xp[i] - xp[i-1]) * (fp[i] - fp[i-1]);
+    'extrapolate' keeps that line outside [xp[0], xp[-1]]."""
+    xp = torch.log(torch.as_tensor(np.asarray(table_energy, dtype=np.float64)))
+    fp = torch.log(torch.as_tensor(np.asarray(table_xsect, dtype=np.float64)))
+
+    def interp(e):
+        x = torch.log(e)
+        i = torch.clamp(torch.searchsorted(xp, x.contiguous(), right=True), 1, xp.numel() - 1)
+        df = fp[i] - fp[i - 1]
+        dx = xp[i] - xp[i - 1]
+        return torch.exp(fp[i - 1] + ((x - xp[i - 1]) / dx) * df)
+
+    return interp
+
+
+def _photonabs(egrid, p, sigma_of=None):
+    """PhotonAbsorption.continuum, models/mul.py:360-388."""
+    return torch.exp(-p['nH'] * sigma_of(egrid))
+
+
 # name -> (parameter names in _config order, defaults, 'continuum'|'integral', function, extra kwargs)
 ADDITIVE = {
     'Band': (('alpha', 'beta', 'Ec', 'K'), (-1.0, -2.0, 300.0, 1.0), 'continuum', _band, {}),
@@ -277,6 +301,9 @@ MULTIPLICATIVE = {
 def eval_component(name, egrid, params, method='trapz', **extra):
     """Bin values (..., E) of one component: Component.eval (models/model.py:1693-1698,
     1722-1761).  ``params`` maps parameter name -> tensor."""
+    if name == 'PhotonAbsorption':  # PhAbs / TBAbs / WAbs: the table comes with the call
+        sigma_of = _make_interp(extra['table_energy'], extra['table_xsect'])
+        return _integrate(lambda e, p: _photonabs(e, p, sigma_of), egrid, params, 'mul', method)
     if name in ADDITIVE:
         mtype, entry = 'add', ADDITIVE[name]
     else:

@@ -100,7 +100,8 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_struct_layout_matches_header(lib):
-    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16  # 4 bytes of padding before the doubles
+    # 4 bytes of padding before the doubles; two table pointers, table_len + tail padding
+    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16 + 8 + 8 + 8
     assert _lib.PlanDesc.chunk.offset == 24 and _lib.SpectrumDesc.exposure.offset % 8 == 0
 
 

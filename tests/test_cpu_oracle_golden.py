@@ -188,3 +188,18 @@ def test_every_builtin_is_finite_on_the_reference_grid():
             p = {k: torch.tensor([[v]], dtype=F64) for k, v in zip(pnames, defaults)}
             v = oracle.eval_component(name, grid, p, **kw)
             assert torch.isfinite(v).all(), name
+
+
+def test_photon_absorption_matches_reference_source():
+    """PhAbs / TBAbs / WAbs: `_make_interp` + `PhotonAbsorption.continuum` of the reference
+    (models/mul.py:274-283, 360-388) executed on a synthetic cross-section table, inside and
+    beyond the table's energy range (log-log extrapolation), trapz and Simpson."""
+    g = np.load(os.path.join(GOLD, 'photonabs.npz'))
+    nH = torch.as_tensor(g['nH']).unsqueeze(-1)
+    for gname in ('inside', 'beyond'):
+        eg = torch.as_tensor(g[f'grid_{gname}'])
+        for method in ('trapz', 'simpson'):
+            out = oracle.components.eval_component('PhotonAbsorption', eg, {'nH': nH}, method=method,
+                                                   table_energy=g['table_energy'], table_xsect=g['table_xsect'])
+            ref = g[f'{gname}_{method}']
+            assert np.allclose(out.numpy(), ref, rtol=1e-13, atol=1e-300), (gname, method)

@@ -65,3 +65,16 @@ def test_statistic_sites_and_gradient_match_reference_closures(lib, stat):
     fd = g[f'{stat}/fd_grad'][1:]
     np.testing.assert_allclose(grad.cpu().numpy()[1:, 0], fd, rtol=5e-6, atol=1e-7 * np.abs(fd).max())
     lk.close()
+
+
+@pytest.mark.parametrize('cls', ['PhAbs', 'TBAbs', 'WAbs'])
+def test_photon_absorption_eval_matches_reference_source(lib, cls):
+    """the table component on the GPU against the reference's own `_make_interp` +
+    `PhotonAbsorption.continuum` output (tests/golden/photonabs.npz)"""
+    g = np.load(os.path.join(GOLD, 'photonabs.npz'))
+    for gname in ('inside', 'beyond'):
+        for method in ('trapz', 'simpson'):
+            comp = getattr(M, cls)(g['table_energy'], g['table_xsect'], method=method)
+            out = comp.compile().eval(g[f'grid_{gname}'], g['nH'][:, None])
+            ref = g[f'{gname}_{method}']
+            assert np.allclose(out, ref, rtol=2e-13, atol=1e-300), (gname, method, np.abs(out - ref).max())

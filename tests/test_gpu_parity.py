@@ -216,3 +216,25 @@ def test_sites_and_unfold(lib):
         u_ref = oracle.eval_model(model.to_spec(), torch.as_tensor(d.photon_egrid), torch.as_tensor(theta)).numpy()
         assert np.allclose(u, u_ref, rtol=1e-12, atol=0)
         lk.close()
+
+
+@KERNELS
+@pytest.mark.parametrize('method', ['trapz', 'simpson'])
+@pytest.mark.parametrize('fold', ['i8', 'dmma'])
+def test_photon_absorption_in_a_fit_model(lib, method, fold, specialise):
+    """PhAbs * PowerLaw (the reference's quick-start model) and TBAbs * (CutoffPL + Gauss)
+    with a second, different table: value and gradient incl. d/d nH against the oracle."""
+    import os
+
+    from parity import RTOL, compare
+
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'photonabs.npz'))
+    te, tx = g['table_energy'], g['table_xsect']
+    d = _one_spectrum(E=120, C=60, seed=13)
+    m1 = M.PhAbs(te, tx, method=method) * M.PowerLaw()
+    m2 = M.TBAbs(te, 0.7 * tx * te**0.1, nH=M.UniformParameter('nH', 0.3, 0.0, 10.0), method=method) * (
+        M.CutoffPL() + M.Gauss(El=20.0, sigma=3.0)) + M.WAbs(te, tx, nH=0.2) * M.Blackbody()
+    for model in (m1, m2):
+        cfg = dict(data=[d], model=[model], stat=['cstat'], theta=_theta_for(model, 33, 5))
+        err = compare(cfg, specialise=specialise, fold=fold)
+        assert err['value'] <= RTOL and err['grad'] <= RTOL, (model, err)

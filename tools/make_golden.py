@@ -20,7 +20,7 @@ of those same reference functions.
 Run in the BUILD container only (needs /root/reference); the fixtures are committed and
 travel to the GPU box, this script's input does not.
 
-    python tools/make_golden.py
+    python tools/make_golden.py [--photonabs]
 """
 
 from __future__ import annotations
@@ -398,9 +398,66 @@ def likelihood_fixture(ref: RefModel):
     return out
 
 
+def synthetic_xsect_table():
+    """A photoelectric-like cross-section table (decreasing power law with K edges), in the
+    units of the reference's tables (1e-22 cm^2): plausible input, not the reference's data."""
+    energy = np.geomspace(0.03, 40.0, 300)
+    xsect = 2.4e-2 * energy**-2.6 * (1.0 + 1.5 * (energy > 0.532) + 0.8 * (energy > 1.84) + 2.5 * (energy > 7.11))
+    return energy, xsect
+
+
+def photonabs_fixture(ref: RefModel):
+    """PhotonAbsorption (PhAbs / TBAbs / WAbs): the reference's `_make_interp`
+    (models/mul.py:274-283) and `PhotonAbsorption.continuum` (:360-388) executed as written,
+    through its own trapz / Simpson closures.  `jnp.interp(..., left='extrapolate',
+    right='extrapolate')` is third-party (jax): the stand-in below follows jax's
+    documented implementation (jax/_src/numpy/lax_numpy.py `_interp`)."""
+    jnp = ref.jnp
+
+    def interp(x, xp, fp, left=None, right=None, period=None):
+        assert left == 'extrapolate' and right == 'extrapolate' and period is None
+        x, xp, fp = (np.asarray(v, dtype=np.float64) for v in (x, xp, fp))
+        i = np.clip(np.searchsorted(xp, x, side='right'), 1, len(xp) - 1)
+        df = fp[i] - fp[i - 1]
+        dx = xp[i] - xp[i - 1]
+        delta = x - xp[i - 1]
+        return fp[i - 1] + (delta / dx) * df
+
+    jnp.interp = interp
+    tree = ast.parse(_src('models/mul.py'))
+    glb = {'jnp': jnp, 'np': np, 'jax': sys.modules['jax']}
+    make_interp = None
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == '_make_interp':
+            make_interp = _exec_function(node, glb)
+    assert make_interp is not None
+    energy, xsect = synthetic_xsect_table()
+    kind, cont = ref.comps['PhotonAbsorption']
+    assert kind == 'continuum'
+    cont.__globals__['_XSECT_INTERP'] = {'phabs': {'vern': {'angr': make_interp(energy, xsect)}}}
+    continuum = lambda egrid, params: cont(egrid, params, 'phabs', 'angr', 'vern')  # noqa: E731
+    out = {'table_energy': energy, 'table_xsect': xsect}
+    grids = {'inside': np.geomspace(0.1, 12.0, 151), 'beyond': np.geomspace(0.01, 300.0, 97)}
+    nH = np.array([0.05, 1.0, 7.5])
+    out['nH'] = nH
+    for gname, g in grids.items():
+        out[f'grid_{gname}'] = g
+        for method in ('trapz', 'simpson'):
+            fn = ref.make_integral(method, 'mul', continuum)
+            out[f'{gname}_{method}'] = np.stack([np.asarray(fn(_a(g), {'nH': np.float64(v)})) for v in nH])
+    return out
+
+
 def main():
     ref = RefModel()
     os.makedirs(OUT, exist_ok=True)
+    if '--photonabs' in sys.argv or '--all' in sys.argv or len(sys.argv) == 1:
+        pa = photonabs_fixture(ref)
+        np.savez_compressed(os.path.join(OUT, 'photonabs.npz'), **pa)
+        print('photonabs.npz:', len(pa), 'arrays,', os.path.getsize(os.path.join(OUT, 'photonabs.npz')), 'bytes')
+        if '--photonabs' in sys.argv:
+            return
+        ref = RefModel()  # fresh stand-ins (photonabs_fixture replaces jnp.interp)
     comp = component_fixture(ref)
     np.savez_compressed(os.path.join(OUT, 'components.npz'), **comp)
     like = likelihood_fixture(ref)
