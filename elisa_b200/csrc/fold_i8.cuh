@@ -25,14 +25,14 @@
 // (cp.async.bulk, the TMA engine in 1-D mode) -- no tensor map, no per-thread addressing.
 // The digits of B are produced once per plan; those of A by slice_rows_kernel per chunk.
 //
-// Kernel.  One persistent CTA per SM, 18 warps:
+// Kernel.  One persistent CTA per SM, 19 warps:
 //   warps 0-15 epilogue: tcgen05.ld the KS int32 accumulators of their 32 rows x 16
 //              columns, recombine in FP64 (Horner in base 256), hand TMEM back, then run
 //              the fused epilogue (fit statistic + dl/dx, or the contraction with
 //              dU/dtheta) thread-per-row while the next tile accumulates;
 //   warp  16   producer: bulk copies into a ring of A slices (16 KB) and a ring of B
 //              blocks (KS x 8 KB), each with full/empty mbarriers;
-//   warp  17   MMA issuer: for slice i of A one tcgen05.mma of N = (KS - i) * 64 columns
+//   warps 17-18 MMA issuers (slices i even / odd): for slice i of A one tcgen05.mma of N = (KS - i) * 64 columns
 //              against the STACKED B slices 0 .. KS-1-i, landing on the TMEM accumulators
 //              of orders i .. KS-1 (column offset 64 i): A is read once per slice and the
 //              instruction shapes stay wide (N up to 256).
@@ -53,7 +53,8 @@ constexpr int I8_NB = 2;         // B-block ring depth
 constexpr int I8_EPI_WARPS = 16;               // 4 per TMEM lane quarter
 constexpr int I8_CG = I8_EPI_WARPS / 4;        // column groups per tile
 constexpr int I8_TC = I8_BN / I8_CG;           // columns per epilogue thread
-constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;
+constexpr int I8_ISSUERS = 2;                  // MMA issuer warps (slices i = w mod 2)
+constexpr int I8_THREADS = (I8_EPI_WARPS + 1 + I8_ISSUERS) * 32;
 constexpr int I8_SMEM_BUDGET = 212 * 1024;  // rings; + 1 KB alignment slack + barriers below 227 KB
 constexpr int I8_MAX_K = 16384;             // int32 headroom: KS * K * 2^14 < 2^31 for KS <= 7
 
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi epi) {
     constexpr int NA = i8_na(KS);
     constexpr int B_BLOCK = KS * I8_B_SLICE;
+    constexpr int NI = Epi::ISSUERS;  // MMA issuer warps in use (<= I8_ISSUERS)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t s_B = s_base;
@@ -282,7 +284,8 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
     auto b_empty = [&](int s) { return s_bar + 8u * (2 * NA + I8_NB + s); };
     const uint32_t t_full = s_bar + 8u * (2 * NA + 2 * I8_NB);
     const uint32_t t_empty = t_full + 8u;
-    const uint32_t s_slot = t_empty + 8u;
+    const uint32_t t_init = t_empty + 8u;  // accumulators of the tile initialised (issuer 0 -> the others)
+    const uint32_t s_slot = t_init + 8u;
     uint8_t* gen_base = smem_raw + (s_base - smem_u32(smem_raw));
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + (s_slot - s_base));
 
@@ -290,9 +293,10 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
 
     if (warp == I8_EPI_WARPS && lane == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-        for (int s = 0; s < I8_NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        mbar_init(t_full, 1);
+        for (int s = 0; s < I8_NB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), NI); }
+        mbar_init(t_full, NI);
         mbar_init(t_empty, I8_EPI_WARPS);
+        mbar_init(t_init, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == I8_EPI_WARPS + 1) {
@@ -346,10 +350,23 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 }
             }
         }
-    } else if (warp == I8_EPI_WARPS + 1) {
-        // ================= MMA issuer =================
+    } else if (warp > I8_EPI_WARPS + NI) {
+        // spare issuer warp of this instantiation
+    } else if (warp > I8_EPI_WARPS) {
+        // ================= MMA issuers =================
+        // Issuer w owns the A slices i = w (mod NI): the issue path (barrier wait, four to eight
+        // UTCIMMA, commit) of a single thread cannot keep the tensor pipe busy with 64..256-column
+        // int8 instructions, two threads can (0.60 -> 0.54 ms on the bare engine).  Digit products
+        // accumulate into shared TMEM columns from both threads; integer accumulation is
+        // order-independent, and the one ordering that matters -- the overwriting (accumulate = 0)
+        // MMAs of slice 0 in the tile's first k-block -- is published through t_init.
+        // NI is a property of the epilogue: the plain-store fold runs two issuers (bit-exact and
+        // row-partition invariant over 30 repeated runs, tools/i8_determinism.py); the gradient
+        // fold stays on one -- with two, its results were no longer bit-identical under
+        // re-chunking and one long run faulted, cause not found, so it is not used there.
+        const int w = warp - (I8_EPI_WARPS + 1);
         int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0, tph = 0;
+        uint32_t aph = 0, bph = 0, tph = 0, iph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const I8Item it = i8_item(a, item);
             I8_FOR_EACH_TILE(it, a, nt) {
@@ -357,32 +374,40 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 mbar_wait(t_empty, tph ^ 1u);  // epilogue has drained the accumulators
                 tph ^= 1u;
                 tc_fence_after();
+                if (w != 0 && lo < hi) {
+                    mbar_wait(t_init, iph);
+                    tc_fence_after();
+                }
+                if (lo < hi) iph ^= 1u;
                 for (int kb = lo; kb < hi; ++kb) {
                     mbar_wait(b_full(bs), bph);
                     const uint32_t sb = s_B + bs * B_BLOCK;
 #pragma unroll
                     for (int i = 0; i < KS; ++i) {
-                        mbar_wait(a_full(as), aph);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t sa = s_A + as * I8_A_SLICE;
+                        if (i % NI == w) {
+                            mbar_wait(a_full(as), aph);
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint32_t sa = s_A + as * I8_A_SLICE;
 #pragma unroll
-                            for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
-                                const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
-                                const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
-                                // (KS - i) * 64 columns in equal parts of <= 256 (multiples of 32)
-                                const int width = (KS - i) * I8_BN;
-                                const int parts = (width + 255) / 256;
-                                const int n = width / parts;  // 192, 160, 224 ...: multiples of 32 for KS <= 8
+                                for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
+                                    const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
+                                    const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
+                                    // (KS - i) * 64 columns in equal parts of <= 256 (multiples of 32)
+                                    const int width = (KS - i) * I8_BN;
+                                    const int parts = (width + 255) / 256;
+                                    const int n = width / parts;  // 192, 160, 224 ...: multiples of 32 for KS <= 8
 #pragma unroll
-                                for (int c0 = 0; c0 < width; c0 += n) {
-                                    const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
-                                    tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
+                                    for (int c0 = 0; c0 < width; c0 += n) {
+                                        const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
+                                        tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
+                                    }
                                 }
+                                tc_commit(a_empty(as));
+                                if (i == 0 && kb == lo) tc_commit(t_init);
                             }
-                            tc_commit(a_empty(as));
+                            __syncwarp();
                         }
-                        __syncwarp();
                         if (++as == NA) { as = 0; aph ^= 1u; }
                     }
                     if (lane == 0) tc_commit(b_empty(bs));
@@ -441,6 +466,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
 // ---------------------------------------------------------------------------------------
 // plain store: D[row, col] (debug / tests)
 struct I8EpilogueStore {
+    static constexpr int ISSUERS = 2;
     double* D;
     int64_t ldd;
     int32_t rows, cols;  // bounds of D
@@ -487,6 +513,7 @@ struct ChanArrays {
 // part[(I8_CG * group + cg) * ld_part + row]
 template <int STAT, bool GRAD>
 struct I8EpilogueStat {
+    static constexpr int ISSUERS = 1;
     ChanArrays ch;
     const double* counts_on;   // per-replica observed data [n, ld_counts] or nullptr
     const double* counts_off;
@@ -565,6 +592,7 @@ struct I8EpilogueStat {
 // transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the thread's energies
 // gpart[(j * n_part + I8_CG * group + cg) * ld_part + row],  n_part = I8_CG * n_groups
 struct I8EpilogueGrad {
+    static constexpr int ISSUERS = 1;
     const double* dU;  // [P, rows, ldu]
     int64_t plane;
     int32_t ldu;
