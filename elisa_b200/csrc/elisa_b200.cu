@@ -1374,7 +1374,7 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
         (rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st)))
         return rc;
     {
-        I8EpilogueStore es{plan->W, sp.C_pad, m_tiles * I8_BM, sp.C_pad};
+        I8EpilogueStore es{plan->W, sp.C_pad, m_tiles * I8_BM, sp.C_pad, plan->a_scale};
         const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
         if ((rc = launch_fold_i8(plan, plan->ks, ELISA_PROFILE_FOLD, fa, es, plan->sm_count, st))) return rc;
     }
@@ -1935,7 +1935,7 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
     fa.kb_lo = rng; fa.kb_hi = rng + n_tiles; fa.m_tiles = m_tiles; fa.n_tiles = n_tiles;
     fa.n_groups = 1;  // set at launch
     fa.debug = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;
-    I8EpilogueStore es{D, ldd, m, n};
+    I8EpilogueStore es{D, ldd, m, n, a_sc};
     int sms = 148;
     int dev = 0;
     cudaGetDevice(&dev);

@@ -209,19 +209,37 @@ __device__ __forceinline__ double i32_to_f64(int32_t v) {
     return __hiloint2double(0x43300000, v ^ (int32_t)0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
 }
 
-// TMEM -> FP64: out[j] = sum_o acc_o[column j] * 256^-o (Horner from the least significant order), j < 8
+// Epilogue register layout ("quad layout").  A warp owns 32 rows (its TMEM lane quarter) x 16
+// columns (its column group) of the tile and reads them with tcgen05.ld.16x256b.x2: thread
+// (r = lane / 4, q = lane % 4) receives rows r + 8 k (k = 0..3) and columns
+// {2q, 2q + 1, 8 + 2q, 9 + 2q}: the four threads of a quad cover 64 contiguous bytes of an
+// FP64 row, so the epilogue's global loads and stores touch 8 rows per warp instruction with
+// every 32-byte sector used in full (a thread-per-row layout touches 32 lines for 16 bytes each).
+// x[k][m]: row r + 8 k, column cm(m) = 2 q + (m & 1) + 8 (m >> 1).
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// TMEM -> FP64: x = sum_o acc_o * 256^-o (Horner from the least significant order)
 template <int KS>
-__device__ __forceinline__ void i8_combine8(uint32_t taddr, double* out) {
-    int32_t v[KS][8];
+__device__ __forceinline__ void i8_combine_quad(uint32_t taddr, double (&x)[4][4]) {
 #pragma unroll
-    for (int d = 0; d < KS; ++d) tc_ld8(taddr + d * I8_BN, v[d]);
-    tc_ld_wait();
+    for (int h = 0; h < 2; ++h) {  // TMEM lanes [16 h, 16 h + 16) of the warp's quarter
+        int32_t v[KS][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        double s = i32_to_f64(v[KS - 1][j]);
+        for (int d = 0; d < KS; ++d) tc_ld_16x256b_x2(taddr + ((uint32_t)(16 * h) << 16) + d * I8_BN, v[d]);
+        tc_ld_wait();
 #pragma unroll
-        for (int d = KS - 2; d >= 0; --d) s = fma(s, 0.00390625, i32_to_f64(v[d][j]));
-        out[j] = s;
+        for (int e = 0; e < 8; ++e) {
+            // registers: {0,1} row r cols 2q,2q+1 | {2,3} row r+8 | {4,5} row r cols 8+2q.. | {6,7} row r+8
+            double t = i32_to_f64(v[KS - 1][e]);
+#pragma unroll
+            for (int d = KS - 2; d >= 0; --d) t = fma(t, 0.00390625, i32_to_f64(v[d][e]));
+            x[2 * h + ((e >> 1) & 1)][(e & 1) + 2 * (e >> 2)] = t;
+        }
     }
 }
 
@@ -232,25 +250,15 @@ __device__ __forceinline__ void i8_combine8(uint32_t taddr, double* out) {
 // its A images are fetched from HBM once and shared through L2 (a whole-row sweep per CTA
 // would put 148 different 1.5 MB A sets in flight and thrash the 126 MB L2).
 //
-// Epilogue interface (one thread = one row of the tile and I8_TC consecutive columns):
+// Epilogue interface (quad layout above; row0 = first row of the thread, c0 = first column of
+// the warp's group in the tile's matrix, q = lane % 4):
 //   State st; epi.begin(st)                      once per group
-//   epi.prefetch(row, tile_n, cg)                before the tile's accumulators are awaited
-//   epi.tile(st, x, tile_n, row, cg, sa, sb)     x = I8_TC recombined (unscaled) dot products,
-//                                                columns tile_n * 64 + I8_TC * cg + [0, I8_TC)
-//   epi.end(st, group, row, cg, sa)              once per group: write the row partials
-// The epilogues walk x in chunks of 8 with a ROLLED loop (the statistic code is long);
-// chunk cc is picked out of the register array with compare-selects, not dynamic indexing.
+//   epi.prefetch(row0 + 8 q, c0)                 before the tile's accumulators are awaited
+//   epi.tile(st, x, row0, c0, q, sb)             x[k][m] recombined (unscaled) dot products,
+//                                                sb = column scales of the warp's 16 columns
+//   epi.end(st, group, cg, row0 + 8 q, sa)       once per group: the thread's row partial
 constexpr int I8_GROUP = 4;
 
-__device__ __forceinline__ void i8_pick8(const double (&x)[I8_TC], int cc, double* out) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        double v = x[j];
-#pragma unroll
-        for (int k = 1; k < I8_TC / 8; ++k) v = (cc == k) ? x[8 * k + j] : v;
-        out[j] = v;
-    }
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // item -> (row tile, first column tile, one past the last column tile)
@@ -421,35 +429,39 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
     } else {
         // ================= epilogue =================
         const int quarter = warp & 3, cg = warp >> 2;
+        const int r = lane >> 2, q = lane & 3;
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + cg * I8_TC;
         uint32_t tph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const I8Item it = i8_item(a, item);
-            const int row = it.mt * I8_BM + quarter * 32 + lane;
-            const double sa = a.a_scale[row];
+            const int row0 = it.mt * I8_BM + quarter * 32 + r;  // the thread's rows: row0 + 8 k
+            const int row_acc = row0 + 8 * q;                    // the row whose partial it keeps
+            const double sa = a.a_scale[row_acc];
             typename Epi::State st;
             I8_FOR_EACH_TILE(it, a, nt) {
+                const int c0 = nt * I8_BN + cg * I8_TC;
                 if (nt % I8_GROUP == 0) epi.begin(st);
-                epi.prefetch(row, nt, cg);
+                epi.prefetch(row_acc, c0);
                 const bool empty = a.kb_lo[nt] >= a.kb_hi[nt];  // no k-blocks: accumulators are stale
                 mbar_wait(t_full, tph);
                 tph ^= 1u;
                 tc_fence_after();
-                // drain: recombine this thread's columns into registers, hand TMEM back to the
-                // MMA warp at once, then run the (long) epilogue math while the next tile accumulates
-                double x[I8_TC];
+                // drain: recombine this thread's elements into registers, hand TMEM back to the
+                // MMA warps at once, then run the epilogue math while the next tile accumulates
+                double x[4][4];
                 if ((a.debug & 16) || empty) {
 #pragma unroll
-                    for (int j = 0; j < I8_TC; ++j) x[j] = 0.0;
-                } else {
+                    for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int cc = 0; cc < I8_TC / 8; ++cc) i8_combine8<KS>(taddr + 8 * cc, x + 8 * cc);
+                        for (int m = 0; m < 4; ++m) x[k][m] = 0.0;
+                } else {
+                    i8_combine_quad<KS>(taddr, x);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty);
-                if (!(a.debug & 8)) epi.tile(st, x, nt, row, cg, sa, a.b_scale + (size_t)nt * I8_BN + cg * I8_TC);
-                if (nt + 1 == ne_) epi.end(st, nt / I8_GROUP, row, cg, sa);
+                if (!(a.debug & 8)) epi.tile(st, x, row0, c0, q, a.b_scale + c0);
+                if (nt + 1 == ne_) epi.end(st, nt / I8_GROUP, cg, row_acc, sa, a.a_scale, row0);
             }
         }
     }
@@ -464,7 +476,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
 // ---------------------------------------------------------------------------------------
 // epilogues
 // ---------------------------------------------------------------------------------------
-// plain store: D[row, col] (debug / tests)
+// plain store: D[row, col] = x * scale_row * scale_col
 struct I8EpilogueStore {
     static constexpr int ISSUERS = 2;
     double* D;
@@ -472,30 +484,35 @@ struct I8EpilogueStore {
     int32_t rows, cols;  // bounds of D
     struct State {};
     __device__ __forceinline__ void begin(State&) const {}
-    __device__ __forceinline__ void prefetch(int, int, int) const {}
-    __device__ __forceinline__ void end(State&, int, int, int, double) const {}
-    __device__ __forceinline__ void tile(State&, const double (&xx)[I8_TC], int tile_n, int row, int cg, double sa,
+    __device__ __forceinline__ void prefetch(int, int) const {}
+    __device__ __forceinline__ void end(State&, int, int, int, double, const double*, int) const {}
+    __device__ __forceinline__ void tile(State&, const double (&x)[4][4], int row0, int c0, int q,
                                          const double* sb) const {
-        const int c0 = tile_n * I8_BN + cg * I8_TC;
-#pragma unroll 1
-        for (int cc = 0; cc < I8_TC / 8; ++cc) {
-            double x[8];
-            i8_pick8(xx, cc, x);
-            if (row < rows) {
+        // the store needs every row's own scale: passed through end()'s a_scale in the fused
+        // epilogues, read here directly
+        const double2 s_lo = *reinterpret_cast<const double2*>(sb + 2 * q);
+        const double2 s_hi = *reinterpret_cast<const double2*>(sb + 8 + 2 * q);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] *= sa * sb[8 * cc + j];
-                double* dst = D + (size_t)row * ldd + c0 + 8 * cc;
-                if (c0 + 8 * cc + 8 <= cols && (ldd & 1) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) reinterpret_cast<double2*>(dst)[j] = make_double2(x[2 * j], x[2 * j + 1]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (c0 + 8 * cc + j < cols) dst[j] = x[j];
-                }
+        for (int k = 0; k < 4; ++k) {
+            const int row = row0 + 8 * k;
+            if (row >= rows) continue;
+            const double sa = row_scale[row];
+            double* dst = D + (size_t)row * ldd + c0 + 2 * q;
+            const double v0 = x[k][0] * sa * s_lo.x, v1 = x[k][1] * sa * s_lo.y;
+            const double v2 = x[k][2] * sa * s_hi.x, v3 = x[k][3] * sa * s_hi.y;
+            if (c0 + I8_TC <= cols && (ldd & 1) == 0) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                *reinterpret_cast<double2*>(dst + 8) = make_double2(v2, v3);
+            } else {
+                const int c = c0 + 2 * q;
+                if (c < cols) dst[0] = v0;
+                if (c + 1 < cols) dst[1] = v1;
+                if (c + 8 < cols) dst[8] = v2;
+                if (c + 9 < cols) dst[9] = v3;
             }
         }
     }
+    const double* row_scale;  // a_scale of the fold (set by the launcher)
 };
 
 // per-channel observed data, padded to C_pad with benign values (shared with the DMMA path)
@@ -509,87 +526,9 @@ struct ChanArrays {
     const double* gof_off;
 };
 
-// forward fold: x = (R u) * area * exposure -> statistic, row partial, W = dl/d(R u)
-// part[(I8_CG * group + cg) * ld_part + row]
-template <int STAT, bool GRAD>
-struct I8EpilogueStat {
-    static constexpr int ISSUERS = 1;
-    ChanArrays ch;
-    const double* counts_on;   // per-replica observed data [n, ld_counts] or nullptr
-    const double* counts_off;
-    int64_t ld_counts;
-    int32_t n_valid;
-    int32_t C;
-    double* W;  // [rows, ldw]
-    int32_t ldw;
-    double* part;
-    int32_t ld_part;
-
-    struct State {
-        double rs;
-    };
-    __device__ __forceinline__ void begin(State& st) const { st.rs = 0.0; }
-    __device__ __forceinline__ void prefetch(int row, int tile_n, int cg) const {
-        if (row >= n_valid) return;
-        const size_t o = (size_t)row * ld_counts + tile_n * I8_BN + cg * I8_TC;
-        if (counts_on != nullptr) prefetch_l2(counts_on + o);
-        if (counts_off != nullptr) prefetch_l2(counts_off + o);
-    }
-    __device__ __forceinline__ void end(State& st, int group, int row, int cg, double) const {
-        part[(size_t)(I8_CG * group + cg) * ld_part + row] = st.rs;
-    }
-    __device__ __forceinline__ void tile(State& st, const double (&xx)[I8_TC], int tile_n, int row, int cg, double sa,
-                                         const double* sb) const {
-        const int c0 = tile_n * I8_BN + cg * I8_TC;
-        const bool rvalid = row < n_valid;
-        const double* con = (counts_on != nullptr && rvalid) ? counts_on + (size_t)row * ld_counts : nullptr;
-        const double* coff = (counts_off != nullptr && rvalid) ? counts_off + (size_t)row * ld_counts : nullptr;
-        double rs = st.rs;
-#pragma unroll 1
-        for (int cc = 0; cc < I8_TC / 8; ++cc) {
-            double x[8];
-            i8_pick8(xx, cc, x);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int col = c0 + 8 * cc + j;
-                ChannelData d;
-                const double sc = ch.scale[col];
-                d.on = ch.on[col];
-                d.gof_on = ch.gof_on[col];
-                d.off = d.sigma = d.ratio = d.gof_off = 0.0;
-                if (STAT == ELISA_STAT_CHI2) d.sigma = ch.sigma[col];
-                if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
-                    d.off = ch.off[col];
-                    d.ratio = ch.ratio[col];
-                }
-                if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[col];
-                if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[col];
-                const bool cvalid = col < C;
-                if (con != nullptr && cvalid) {
-                    d.on = con[col];
-                    if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
-                }
-                if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr && cvalid) {
-                    d.off = coff[col];
-                    if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
-                }
-                const double fold = x[j] * sa * sb[8 * cc + j];
-                double dx = 0.0;
-                const double ll = stat_channel<STAT, GRAD>(fold * sc, d, dx);
-                rs += cvalid ? ll : 0.0;
-                x[j] = (cvalid && rvalid) ? dx * sc : 0.0;
-            }
-            if (GRAD) {
-                double2* dst = reinterpret_cast<double2*>(W + (size_t)row * ldw + c0 + 8 * cc);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_double2(x[2 * j], x[2 * j + 1]);
-            }
-        }
-        st.rs = rs;
-    }
-};
-
-// transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the thread's energies
+// transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the tile's energies.
+// Per tile and parameter a thread multiplies its 4 rows x 4 columns, the quad adds up each row
+// (two xor shuffles), and thread q keeps the sum of row row0 + 8 q.
 // gpart[(j * n_part + I8_CG * group + cg) * ld_part + row],  n_part = I8_CG * n_groups
 struct I8EpilogueGrad {
     static constexpr int ISSUERS = 1;
@@ -610,44 +549,58 @@ struct I8EpilogueGrad {
 #pragma unroll
         for (int j = 0; j < ELISA_MAX_PARAMS; ++j) st.rs[j] = 0.0;
     }
-    // the tile's dU lines (one 128-byte line per parameter and thread) are requested from HBM
-    // while the tile is still accumulating, so that the contraction below finds them in L2
-    __device__ __forceinline__ void prefetch(int row, int tile_n, int cg) const {
+    // the tile's dU lines (one 128-byte line per parameter and row; thread q of a quad takes row
+    // row0 + 8 q) are requested from HBM while the tile is still accumulating, so that the
+    // contraction below finds them in L2
+    __device__ __forceinline__ void prefetch(int row, int c0) const {
         if (dbg & 64) return;
-        const double* base = dU + (size_t)row * ldu + tile_n * I8_BN + cg * I8_TC;
+        const double* base = dU + (size_t)row * ldu + c0;
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
             if (p < P && ((used_mask >> p) & 1u)) prefetch_l2(base + (size_t)p * plane);
     }
-    __device__ __forceinline__ void end(State& st, int group, int row, int cg, double sa) const {
+    __device__ __forceinline__ void end(State& st, int group, int cg, int row, double sa, const double*, int) const {
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
             if (p < P && ((used_mask >> p) & 1u))
                 gpart[((size_t)p * n_part + I8_CG * group + cg) * ld_part + row] = st.rs[p] * sa;
     }
-    __device__ __forceinline__ void tile(State& st, const double (&xx)[I8_TC], int tile_n, int row, int cg, double,
+    __device__ __forceinline__ void tile(State& st, const double (&x)[4][4], int row0, int c0, int q,
                                          const double* sb) const {
-        const int e0 = tile_n * I8_BN + cg * I8_TC;
-#pragma unroll 1
-        for (int cc = 0; cc < I8_TC / 8; ++cc) {
-            double g[8];
-            i8_pick8(xx, cc, g);
+        const double2 s_lo = *reinterpret_cast<const double2*>(sb + 2 * q);
+        const double2 s_hi = *reinterpret_cast<const double2*>(sb + 8 + 2 * q);
+        double g[4][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] *= sb[8 * cc + j];
-            const double* base = dU + (size_t)row * ldu + e0 + 8 * cc;
+        for (int k = 0; k < 4; ++k) {
+            g[k][0] = x[k][0] * s_lo.x;
+            g[k][1] = x[k][1] * s_lo.y;
+            g[k][2] = x[k][2] * s_hi.x;
+            g[k][3] = x[k][3] * s_hi.y;
+        }
+        const double* base = dU + (size_t)row0 * ldu + c0 + 2 * q;
 #pragma unroll
-            for (int p = 0; p < ELISA_MAX_PARAMS; ++p) {
-                if (p < P && ((used_mask >> p) & 1u)) {
-                    const double2* src = reinterpret_cast<const double2*>(base + (size_t)p * plane);
-                    double s0 = 0.0, s1 = 0.0;
+        for (int p = 0; p < ELISA_MAX_PARAMS; ++p) {
+            if (p < P && ((used_mask >> p) & 1u)) {
+                const double* src = base + (size_t)p * plane;
+                double s[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double2 v = (dbg & 32) ? make_double2(g[j], g[j + 4]) : src[j];
-                        s0 = fma(g[2 * j], v.x, s0);
-                        s1 = fma(g[2 * j + 1], v.y, s1);
+                for (int k = 0; k < 4; ++k) {
+                    double2 lo, hi;
+                    if (dbg & 32) {
+                        lo = make_double2(g[k][0], g[k][1]);
+                        hi = make_double2(g[k][2], g[k][3]);
+                    } else {
+                        lo = *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu);
+                        hi = *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu + 8);
                     }
-                    st.rs[p] += s0 + s1;
+                    s[k] = fma(g[k][3], hi.y, fma(g[k][2], hi.x, fma(g[k][1], lo.y, g[k][0] * lo.x)));
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
+                    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
+                }
+                st.rs[p] += (q == 0) ? s[0] : (q == 1) ? s[1] : (q == 2) ? s[2] : s[3];
             }
         }
     }
