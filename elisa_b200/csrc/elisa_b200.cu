@@ -1189,12 +1189,27 @@ static int launch_slice(ElisaPlan* plan, int ks, const SliceArgs& a, int cls, cu
     return ELISA_OK;
 }
 
+template <int KS, class Epi, int NI>
+static int launch_fold_i8_ni(ElisaPlan* plan, int cls, const FoldI8Args& fa, const Epi& epi, int sm_count,
+                             cudaStream_t st);
+
+// env ELISA_B200_I8_ISSUERS=1|2 overrides the epilogue's issuer count (cross-checks)
 template <int KS, class Epi>
 static int launch_fold_i8_ks(ElisaPlan* plan, int cls, const FoldI8Args& fa, const Epi& epi, int sm_count,
                              cudaStream_t st) {
+    const char* env = getenv("ELISA_B200_I8_ISSUERS");
+    const int ni = env ? atoi(env) : Epi::ISSUERS;
+    if (ni == 1) return launch_fold_i8_ni<KS, Epi, 1>(plan, cls, fa, epi, sm_count, st);
+    if (ni == 2) return launch_fold_i8_ni<KS, Epi, 2>(plan, cls, fa, epi, sm_count, st);
+    return launch_fold_i8_ni<KS, Epi, Epi::ISSUERS>(plan, cls, fa, epi, sm_count, st);
+}
+
+template <int KS, class Epi, int NI>
+static int launch_fold_i8_ni(ElisaPlan* plan, int cls, const FoldI8Args& fa, const Epi& epi, int sm_count,
+                             cudaStream_t st) {
     static bool configured = false;  // per instantiation
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(fold_i8_kernel<KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(fold_i8_kernel<KS, Epi, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       i8_smem_bytes(KS)));
         configured = true;
     }
@@ -1202,7 +1217,7 @@ static int launch_fold_i8_ks(ElisaPlan* plan, int cls, const FoldI8Args& fa, con
     f.n_groups = (f.n_tiles + I8_GROUP - 1) / I8_GROUP;
     const int grid = std::min(f.m_tiles * f.n_groups, sm_count);  // items: (row tile, column group)
     ScopedSpan span(plan, cls, st);
-    fold_i8_kernel<KS, Epi><<<grid, I8_THREADS, i8_smem_bytes(KS), st>>>(f, epi);
+    fold_i8_kernel<KS, Epi, NI><<<grid, I8_THREADS, i8_smem_bytes(KS), st>>>(f, epi);
     if (plan) ++plan->launches;
     CUDA_TRY(cudaGetLastError());
     return ELISA_OK;

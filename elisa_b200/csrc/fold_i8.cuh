@@ -26,10 +26,10 @@
 // The digits of B are produced once per plan; those of A by slice_rows_kernel per chunk.
 //
 // Kernel.  One persistent CTA per SM, 19 warps:
-//   warps 0-15 epilogue: tcgen05.ld the KS int32 accumulators of their 32 rows x 16
-//              columns, recombine in FP64 (Horner in base 256), hand TMEM back, then run
-//              the fused epilogue (fit statistic + dl/dx, or the contraction with
-//              dU/dtheta) thread-per-row while the next tile accumulates;
+//   warps 0-15 epilogue: tcgen05.ld (16x256b: four threads share 64 contiguous bytes of a
+//              row) the KS int32 accumulators of their 32 rows x 16 columns, recombine in FP64
+//              (Horner in base 256), hand TMEM back, then run the epilogue (plain store of
+//              R u, or the contraction with dU/dtheta) while the next tile accumulates;
 //   warp  16   producer: bulk copies into a ring of A slices (16 KB) and a ring of B
 //              blocks (KS x 8 KB), each with full/empty mbarriers;
 //   warps 17-18 MMA issuers (slices i even / odd): for slice i of A one tcgen05.mma of N = (KS - i) * 64 columns
@@ -50,7 +50,7 @@ constexpr int I8_BN = 64;        // output columns per tile (one accumulator per
 constexpr int I8_A_SLICE = I8_BM * I8_BK;  // 16 KB
 constexpr int I8_B_SLICE = I8_BN * I8_BK;  // 8 KB
 constexpr int I8_NB = 2;         // B-block ring depth
-constexpr int I8_EPI_WARPS = 16;               // 4 per TMEM lane quarter
+constexpr int I8_EPI_WARPS = 16;               // 4 per TMEM lane quarter (8 also works: 32 columns per thread)
 constexpr int I8_CG = I8_EPI_WARPS / 4;        // column groups per tile
 constexpr int I8_TC = I8_BN / I8_CG;           // columns per epilogue thread
 constexpr int I8_ISSUERS = 2;                  // MMA issuer warps (slices i = w mod 2)
@@ -215,7 +215,7 @@ __device__ __forceinline__ double i32_to_f64(int32_t v) {
 // {2q, 2q + 1, 8 + 2q, 9 + 2q}: the four threads of a quad cover 64 contiguous bytes of an
 // FP64 row, so the epilogue's global loads and stores touch 8 rows per warp instruction with
 // every 32-byte sector used in full (a thread-per-row layout touches 32 lines for 16 bytes each).
-// x[k][m]: row r + 8 k, column cm(m) = 2 q + (m & 1) + 8 (m >> 1).
+// x[k][m]: row r + 8 k, column i8_col(m, q) (a second 16-column block follows for I8_TC = 32).
 __device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, int32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -223,22 +223,30 @@ __device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, int32_t* v) {
                  : "memory");
 }
 
+constexpr int I8_NM = I8_TC / 4;  // elements per row and thread
+// column (within the warp's group) of element m of thread q: 16-column blocks of the layout above
+__host__ __device__ constexpr int i8_col(int m, int q) { return 16 * (m >> 2) + 8 * ((m >> 1) & 1) + 2 * q + (m & 1); }
+
 // TMEM -> FP64: x = sum_o acc_o * 256^-o (Horner from the least significant order)
 template <int KS>
-__device__ __forceinline__ void i8_combine_quad(uint32_t taddr, double (&x)[4][4]) {
+__device__ __forceinline__ void i8_combine_quad(uint32_t taddr, double (&x)[4][I8_NM]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {  // TMEM lanes [16 h, 16 h + 16) of the warp's quarter
-        int32_t v[KS][8];
+    for (int b = 0; b < I8_TC / 16; ++b) {  // 16-column blocks of the warp's group
 #pragma unroll
-        for (int d = 0; d < KS; ++d) tc_ld_16x256b_x2(taddr + ((uint32_t)(16 * h) << 16) + d * I8_BN, v[d]);
-        tc_ld_wait();
+        for (int h = 0; h < 2; ++h) {  // TMEM lanes [16 h, 16 h + 16) of the warp's quarter
+            int32_t v[KS][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            // registers: {0,1} row r cols 2q,2q+1 | {2,3} row r+8 | {4,5} row r cols 8+2q.. | {6,7} row r+8
-            double t = i32_to_f64(v[KS - 1][e]);
+            for (int d = 0; d < KS; ++d)
+                tc_ld_16x256b_x2(taddr + ((uint32_t)(16 * h) << 16) + d * I8_BN + 16 * b, v[d]);
+            tc_ld_wait();
 #pragma unroll
-            for (int d = KS - 2; d >= 0; --d) t = fma(t, 0.00390625, i32_to_f64(v[d][e]));
-            x[2 * h + ((e >> 1) & 1)][(e & 1) + 2 * (e >> 2)] = t;
+            for (int e = 0; e < 8; ++e) {
+                // registers: {0,1} row r cols 2q,2q+1 | {2,3} row r+8 | {4,5} row r cols 8+2q.. | {6,7} row r+8
+                double t = i32_to_f64(v[KS - 1][e]);
+#pragma unroll
+                for (int d = KS - 2; d >= 0; --d) t = fma(t, 0.00390625, i32_to_f64(v[d][e]));
+                x[2 * h + ((e >> 1) & 1)][4 * b + (e & 1) + 2 * (e >> 2)] = t;
+            }
         }
     }
 }
@@ -274,12 +282,12 @@ __device__ __forceinline__ I8Item i8_item(const FoldI8Args& a, int item) {
 #define I8_FOR_EACH_TILE(it, a, nt) \
     for (int nt = (it).g * I8_GROUP, ne_ = min(nt + I8_GROUP, (a).n_tiles); nt < ne_; ++nt)
 
-template <int KS, class Epi>
+template <int KS, class Epi, int NI = Epi::ISSUERS>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi epi) {
     constexpr int NA = i8_na(KS);
     constexpr int B_BLOCK = KS * I8_B_SLICE;
-    constexpr int NI = Epi::ISSUERS;  // MMA issuer warps in use (<= I8_ISSUERS)
+    static_assert(NI >= 1 && NI <= I8_ISSUERS, "issuer warps");  // MMA issuer warps in use
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t s_B = s_base;
@@ -448,12 +456,12 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 tc_fence_after();
                 // drain: recombine this thread's elements into registers, hand TMEM back to the
                 // MMA warps at once, then run the epilogue math while the next tile accumulates
-                double x[4][4];
+                double x[4][I8_NM];
                 if ((a.debug & 16) || empty) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) x[k][m] = 0.0;
+                        for (int m = 0; m < I8_NM; ++m) x[k][m] = 0.0;
                 } else {
                     i8_combine_quad<KS>(taddr, x);
                 }
@@ -461,7 +469,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty);
                 if (!(a.debug & 8)) epi.tile(st, x, row0, c0, q, a.b_scale + c0);
-                if (nt + 1 == ne_) epi.end(st, nt / I8_GROUP, cg, row_acc, sa, a.a_scale, row0);
+                if (nt + 1 == ne_) epi.end(st, nt / I8_GROUP, cg, row_acc, sa);
             }
         }
     }
@@ -485,30 +493,30 @@ struct I8EpilogueStore {
     struct State {};
     __device__ __forceinline__ void begin(State&) const {}
     __device__ __forceinline__ void prefetch(int, int) const {}
-    __device__ __forceinline__ void end(State&, int, int, int, double, const double*, int) const {}
-    __device__ __forceinline__ void tile(State&, const double (&x)[4][4], int row0, int c0, int q,
+    __device__ __forceinline__ void end(State&, int, int, int, double) const {}
+    __device__ __forceinline__ void tile(State&, const double (&x)[4][I8_NM], int row0, int c0, int q,
                                          const double* sb) const {
-        // the store needs every row's own scale: passed through end()'s a_scale in the fused
-        // epilogues, read here directly
-        const double2 s_lo = *reinterpret_cast<const double2*>(sb + 2 * q);
-        const double2 s_hi = *reinterpret_cast<const double2*>(sb + 8 + 2 * q);
+        // every row of the thread needs its own scale here (the fused epilogues only that of the
+        // row whose partial they keep)
+        double2 sc[I8_NM / 2];
+#pragma unroll
+        for (int m = 0; m < I8_NM; m += 2) sc[m / 2] = *reinterpret_cast<const double2*>(sb + i8_col(m, q));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int row = row0 + 8 * k;
             if (row >= rows) continue;
             const double sa = row_scale[row];
-            double* dst = D + (size_t)row * ldd + c0 + 2 * q;
-            const double v0 = x[k][0] * sa * s_lo.x, v1 = x[k][1] * sa * s_lo.y;
-            const double v2 = x[k][2] * sa * s_hi.x, v3 = x[k][3] * sa * s_hi.y;
-            if (c0 + I8_TC <= cols && (ldd & 1) == 0) {
-                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-                *reinterpret_cast<double2*>(dst + 8) = make_double2(v2, v3);
-            } else {
-                const int c = c0 + 2 * q;
-                if (c < cols) dst[0] = v0;
-                if (c + 1 < cols) dst[1] = v1;
-                if (c + 8 < cols) dst[8] = v2;
-                if (c + 9 < cols) dst[9] = v3;
+            double* dst = D + (size_t)row * ldd + c0;
+#pragma unroll
+            for (int m = 0; m < I8_NM; m += 2) {
+                const int c = i8_col(m, q);
+                const double v0 = x[k][m] * sa * sc[m / 2].x, v1 = x[k][m + 1] * sa * sc[m / 2].y;
+                if (c0 + I8_TC <= cols && (ldd & 1) == 0) {
+                    *reinterpret_cast<double2*>(dst + c) = make_double2(v0, v1);
+                } else {
+                    if (c0 + c < cols) dst[c] = v0;
+                    if (c0 + c + 1 < cols) dst[c + 1] = v1;
+                }
             }
         }
     }
@@ -557,27 +565,30 @@ struct I8EpilogueGrad {
         const double* base = dU + (size_t)row * ldu + c0;
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
-            if (p < P && ((used_mask >> p) & 1u)) prefetch_l2(base + (size_t)p * plane);
+            if (p < P && ((used_mask >> p) & 1u)) {
+#pragma unroll
+                for (int b = 0; b < I8_TC / 16; ++b) prefetch_l2(base + (size_t)p * plane + 16 * b);
+            }
     }
-    __device__ __forceinline__ void end(State& st, int group, int cg, int row, double sa, const double*, int) const {
+    __device__ __forceinline__ void end(State& st, int group, int cg, int row, double sa) const {
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
             if (p < P && ((used_mask >> p) & 1u))
                 gpart[((size_t)p * n_part + I8_CG * group + cg) * ld_part + row] = st.rs[p] * sa;
     }
-    __device__ __forceinline__ void tile(State& st, const double (&x)[4][4], int row0, int c0, int q,
+    __device__ __forceinline__ void tile(State& st, const double (&x)[4][I8_NM], int row0, int c0, int q,
                                          const double* sb) const {
-        const double2 s_lo = *reinterpret_cast<const double2*>(sb + 2 * q);
-        const double2 s_hi = *reinterpret_cast<const double2*>(sb + 8 + 2 * q);
-        double g[4][4];
+        double g[4][I8_NM];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            g[k][0] = x[k][0] * s_lo.x;
-            g[k][1] = x[k][1] * s_lo.y;
-            g[k][2] = x[k][2] * s_hi.x;
-            g[k][3] = x[k][3] * s_hi.y;
+        for (int m = 0; m < I8_NM; m += 2) {
+            const double2 sc = *reinterpret_cast<const double2*>(sb + i8_col(m, q));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                g[k][m] = x[k][m] * sc.x;
+                g[k][m + 1] = x[k][m + 1] * sc.y;
+            }
         }
-        const double* base = dU + (size_t)row0 * ldu + c0 + 2 * q;
+        const double* base = dU + (size_t)row0 * ldu + c0;
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p) {
             if (p < P && ((used_mask >> p) & 1u)) {
@@ -585,15 +596,14 @@ struct I8EpilogueGrad {
                 double s[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    double2 lo, hi;
-                    if (dbg & 32) {
-                        lo = make_double2(g[k][0], g[k][1]);
-                        hi = make_double2(g[k][2], g[k][3]);
-                    } else {
-                        lo = *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu);
-                        hi = *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu + 8);
+                    double t = 0.0;
+#pragma unroll
+                    for (int m = 0; m < I8_NM; m += 2) {
+                        const double2 v = (dbg & 32) ? make_double2(g[k][m], g[k][m + 1])
+                                                     : *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu + i8_col(m, q));
+                        t = fma(g[k][m + 1], v.y, fma(g[k][m], v.x, t));
                     }
-                    s[k] = fma(g[k][3], hi.y, fma(g[k][2], hi.x, fma(g[k][1], lo.y, g[k][0] * lo.x)));
+                    s[k] = t;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
