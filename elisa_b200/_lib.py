@@ -89,6 +89,7 @@ SYMBOLS = {
     'elisa_b200_plan_destroy': (None, [_VP]),
     'elisa_b200_loglike_dev': (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP]),
     'elisa_b200_loglike_grad_dev': (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    'elisa_b200_normal_eq_dev': (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     'elisa_b200_sites_dev': (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),
     'elisa_b200_unfold_dev': (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, _VP, _VP]),
     'elisa_b200_loglike_grad_host': (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP]),

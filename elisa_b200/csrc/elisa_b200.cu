@@ -427,6 +427,101 @@ __global__ void sites_kernel(const SitesArgs a) {
 }
 
 // ======================================================================================
+// Gauss-Newton normal equations of the deviance residuals (batched re-fit, infer/helper.py:588-660)
+// ======================================================================================
+// The reference re-fits simulated data sets with Levenberg-Marquardt on the residual vector
+// r_c = sqrt(-2 l_c) (helper.py:588-594, 601-625).  One LM step needs, per replica,
+//   loglike = sum_c l_c,   grad_p = d loglike / d theta_p = -(J^T r)_p,
+//   (J^T J)_pq = sum_c (dr_c/dtheta_p)(dr_c/dtheta_q) = sum_c (dl_c/dx)^2 / (-2 l_c) s_pc s_qc,
+// with s_pc = d x_c / d theta_p = scale_c (R dU/dtheta_p)_c the FORWARD-folded tangent spectra
+// (forward mode: no transposed fold).  One warp per replica, lanes stride the channels.
+struct NormalEqArgs {
+    const double* X;  // [1 + P planes][rows_pad, ldx]: plane 0 = R u, plane 1 + j = R du/dtheta_j
+    int64_t plane;
+    int32_t ldx;
+    ChanArrays ch;
+    const double* counts_on;
+    const double* counts_off;
+    int64_t ld_counts;
+    int32_t n, C, P;
+    uint32_t used_mask;
+    int32_t accumulate;  // 0: overwrite the outputs (first spectrum), 1: add to them
+    double* loglike;     // [n]
+    double* grad;        // [n, P]
+    double* jtj;         // [n, P, P]
+};
+
+template <int STAT, int PT>
+__global__ void __launch_bounds__(256) normal_eq_kernel(const NormalEqArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= a.n) return;
+    const double* x0 = a.X + (size_t)row * a.ldx;
+    const double* con = a.counts_on ? a.counts_on + (size_t)row * a.ld_counts : nullptr;
+    const double* coff = a.counts_off ? a.counts_off + (size_t)row * a.ld_counts : nullptr;
+    double ll = 0.0, g[PT], h[PT * (PT + 1) / 2];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) g[p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < PT * (PT + 1) / 2; ++k) h[k] = 0.0;
+    for (int col = lane; col < a.C; col += 32) {
+        ChannelData d;
+        const double sc = a.ch.scale[col];
+        d.on = con ? con[col] : a.ch.on[col];
+        d.off = coff ? coff[col] : a.ch.off[col];
+        d.sigma = a.ch.sigma[col];
+        d.ratio = a.ch.ratio[col];
+        d.gof_on = con ? poisson_gof(d.on) : a.ch.gof_on[col];
+        d.gof_off = coff ? poisson_gof(d.off) : a.ch.gof_off[col];
+        double dx = 0.0;
+        const double l = stat_channel<STAT, true>(x0[col] * sc, d, dx);
+        ll += l;
+        const double r2 = -2.0 * l;
+        const double w = r2 > 1e-300 ? dx * dx / r2 : 0.0;  // (dr/dx)^2; a channel at r = 0 adds no curvature
+        double sp[PT];
+#pragma unroll
+        for (int p = 0; p < PT; ++p)
+            sp[p] = (p < a.P && ((a.used_mask >> p) & 1u)) ? sc * x0[(size_t)(1 + p) * a.plane + col] : 0.0;
+        int k = 0;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+            g[p] = fma(dx, sp[p], g[p]);
+            const double wp = w * sp[p];
+#pragma unroll
+            for (int q = p; q < PT; ++q, ++k) h[k] = fma(wp, sp[q], h[k]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ll += __shfl_xor_sync(0xffffffffu, ll, o);
+#pragma unroll
+        for (int p = 0; p < PT; ++p) g[p] += __shfl_xor_sync(0xffffffffu, g[p], o);
+#pragma unroll
+        for (int k = 0; k < PT * (PT + 1) / 2; ++k) h[k] += __shfl_xor_sync(0xffffffffu, h[k], o);
+    }
+    if (lane != 0) return;
+    a.loglike[row] = (a.accumulate ? a.loglike[row] : 0.0) + ll;
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+        if (p < a.P) {
+            double* gp = a.grad + (size_t)row * a.P + p;
+            *gp = (a.accumulate ? *gp : 0.0) + g[p];
+        }
+#pragma unroll
+        for (int q = p; q < PT; ++q, ++k) {
+            if (q < a.P) {
+                double* hpq = a.jtj + ((size_t)row * a.P + p) * a.P + q;
+                double* hqp = a.jtj + ((size_t)row * a.P + q) * a.P + p;
+                const double v = (a.accumulate ? *hpq : 0.0) + h[k];
+                *hpq = v;
+                *hqp = v;
+            }
+        }
+    }
+}
+
+// ======================================================================================
 // host side: plan
 // ======================================================================================
 static thread_local std::string g_last_error = "";
@@ -516,6 +611,7 @@ struct ElisaPlan {
     int8_t* A_img = nullptr;
     double* a_scale = nullptr;
     unsigned long long* guard = nullptr;  // [2] accuracy guard of the integer fold (stat_slice_kernel)
+    double* Xp = nullptr;  // [1 + P][chunk, max_C_pad] forward-folded model and tangents (normal equations; lazily allocated)
     int sm_count = 148;
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
@@ -1502,6 +1598,74 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     return ELISA_OK;
 }
 
+// ---- normal equations (batched re-fit) ------------------------------------------------------
+template <int STAT>
+static int launch_normal_eq(ElisaPlan* plan, const NormalEqArgs& a, cudaStream_t st) {
+    const int blocks = (a.n + 7) / 8;
+    ScopedSpan span(plan, ELISA_PROFILE_STAT, st);
+    if (a.P <= 4)
+        normal_eq_kernel<STAT, 4><<<blocks, 256, 0, st>>>(a);
+    else
+        normal_eq_kernel<STAT, 8><<<blocks, 256, 0, st>>>(a);
+    ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+// One (chunk, spectrum) pass: unfold with tangents, forward-fold u and every du/dtheta_j with the
+// plain-store epilogue, then the per-replica sums.
+static int run_normal_eq_chunk(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off,
+                               int n, double* loglike, double* grad, double* jtj, cudaStream_t st) {
+    const SpectrumPlan& sp = plan->spec[s];
+    const int n_rows = round_up(n, GEMM_BM);
+    const int m_tiles = n_rows / GEMM_BM;
+    const int64_t xplane = (int64_t)plan->chunk * plan->max_C_pad;
+    int rc;
+    bool fused_digits = false;
+    if ((rc = launch_unfold(plan, sp, theta, n, n_rows, true, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st,
+                            sp.use_i8() ? &fused_digits : nullptr)))
+        return rc;
+    for (int j = -1; j < plan->P; ++j) {  // j = -1: the model itself
+        if (j >= 0 && !((sp.model.used_mask >> j) & 1u)) continue;
+        const double* A = j < 0 ? plan->U : plan->dU + (int64_t)j * n_rows * sp.E_pad;
+        double* X = plan->Xp + (int64_t)(1 + j) * xplane;
+        if (sp.use_i8()) {
+            if (!(j < 0 && fused_digits) &&
+                (rc = slice_chunk_operand(plan, A, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st)))
+                return rc;
+            I8EpilogueStore es{X, sp.C_pad, m_tiles * I8_BM, sp.C_pad, plan->a_scale};
+            const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
+            if ((rc = launch_fold_i8(plan, plan->ks, ELISA_PROFILE_FOLD, fa, es, plan->sm_count, st))) return rc;
+        } else {
+            EpilogueStore es{X, sp.C_pad};
+            if ((rc = launch_gemm(plan, ELISA_PROFILE_FOLD, A, sp.E_pad, sp.fwd, m_tiles, es, st))) return rc;
+        }
+    }
+    NormalEqArgs a;
+    a.X = plan->Xp;
+    a.plane = xplane;
+    a.ldx = sp.C_pad;
+    a.ch = sp.chan_view();
+    a.counts_on = on ? on + sp.counts_off : nullptr;
+    a.counts_off = off ? off + sp.counts_off : nullptr;
+    a.ld_counts = plan->sum_C;
+    a.n = n;
+    a.C = sp.C;
+    a.P = plan->P;
+    a.used_mask = sp.model.used_mask;
+    a.accumulate = s > 0 ? 1 : 0;
+    a.loglike = loglike;
+    a.grad = grad;
+    a.jtj = jtj;
+    switch (sp.stat) {
+        case ELISA_STAT_CHI2: return launch_normal_eq<ELISA_STAT_CHI2>(plan, a, st);
+        case ELISA_STAT_CSTAT: return launch_normal_eq<ELISA_STAT_CSTAT>(plan, a, st);
+        case ELISA_STAT_PSTAT: return launch_normal_eq<ELISA_STAT_PSTAT>(plan, a, st);
+        case ELISA_STAT_PGSTAT: return launch_normal_eq<ELISA_STAT_PGSTAT>(plan, a, st);
+        default: return launch_normal_eq<ELISA_STAT_WSTAT>(plan, a, st);
+    }
+}
+
 static int run_all(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                    double* loglike, double* grad, cudaStream_t st) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
@@ -1870,6 +2034,39 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
     return plan->spec[spectrum].use_i8() ? plan->ks : 0;
+}
+
+int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
+                             int64_t n, double* loglike, double* grad, double* jtj, void* cuda_stream) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
+    if (n == 0) return ELISA_OK;
+    if (theta == nullptr || loglike == nullptr || grad == nullptr || jtj == nullptr)
+        return fail(ELISA_ERR_INVALID, "normal_eq: null pointer");
+    if (plan->P > 8) return fail(ELISA_ERR_UNSUPPORTED, "normal_eq: more than 8 free parameters");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    if (plan->Xp == nullptr) {  // first use: workspace of the folded model and tangent spectra
+        const size_t bytes = (size_t)(1 + plan->P) * plan->chunk * plan->max_C_pad * 8;
+        if (cudaMalloc((void**)&plan->Xp, bytes) != cudaSuccess) {
+            cudaSetDevice(prev);
+            return fail(ELISA_ERR_NOMEM, "out of device memory (normal equations workspace)");
+        }
+        plan->owned.push_back(plan->Xp);
+        plan->workspace_bytes += (int64_t)bytes;
+    }
+    int rc = ELISA_OK;
+    for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
+        const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
+        for (int s = 0; s < plan->S && rc == ELISA_OK; ++s)
+            rc = run_normal_eq_chunk(plan, s, theta + i0 * plan->P, counts_on ? counts_on + i0 * plan->sum_C : nullptr,
+                                     counts_off ? counts_off + i0 * plan->sum_C : nullptr, nc, loglike + i0,
+                                     grad + i0 * plan->P, jtj + i0 * plan->P * plan->P, st);
+    }
+    cudaSetDevice(prev);
+    return rc;
 }
 
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset) {

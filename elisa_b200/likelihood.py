@@ -266,6 +266,95 @@ class Likelihood:
             return self._twin.loglike_and_grad(t, on, off)
         return out, grad[:, :, : self.nparam]
 
+    def normal_equations(self, theta, counts_on=None, counts_off=None):
+        """(loglike (N,), grad (N, P), jtj (N, P, P)) of the deviance residuals
+        r = sqrt(-2 * point log-likelihood) over all datasets (infer/helper.py:588-594):
+        loglike = -|r|^2 / 2, grad = -J^T r, jtj = J^T J -- what one Levenberg-Marquardt step of
+        the reference's re-fit (helper.py:601-625) needs (``elisa_b200_normal_eq_dev``)."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            t = self._theta(theta)
+            n = t.shape[0]
+            on, off = self._counts(counts_on, n), self._counts(counts_off, n)
+            ll = torch.empty((n,), dtype=torch.float64, device=t.device)
+            g = torch.empty((n, self._P), dtype=torch.float64, device=t.device)
+            h = torch.empty((n, self._P, self._P), dtype=torch.float64, device=t.device)
+            _lib.check(self._lib.elisa_b200_normal_eq_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n,
+                                                          _dev_ptr(ll), _dev_ptr(g), _dev_ptr(h), self._stream()))
+        return ll, g[:, : self.nparam], h[:, : self.nparam, : self.nparam]
+
+    def fit(self, theta0, counts_on=None, counts_off=None, lower=None, upper=None, max_iter: int = 200,
+            xtol: float = 1e-9, gtol: float = 1e-7):
+        """Batched re-fit: one Levenberg-Marquardt minimisation of the deviance residuals per
+        row of ``theta0`` / per replica of ``counts_on`` (``counts_off``), all rows advancing
+        together on the GPU -- the reference's ``fit_once`` / ``batch_fit`` (infer/helper.py:
+        601-806: optimistix LM on ``residual`` in unconstrained space, sequential per device).
+
+        Parameters live in the unconstrained space of the reference's interval bijection
+        (theta = lower + (upper - lower) * sigmoid(u), numpyro ``biject_to(interval)``);
+        ``lower`` / ``upper`` default to the parameters' prior bounds.  Returns a dict with
+        'theta' (N, P), 'loglike' / 'deviance' (N,) totals, 'grad_norm' (N,) = |J^T r| in
+        unconstrained space, 'n_iter' and 'valid' (finite deviance and grad_norm <= 1e-3, the
+        reference's validity rule, helper.py:652-657)."""
+        torch = self._torch
+        dev = f'cuda:{self.device}'
+        P = self.nparam
+        t0 = self._theta(theta0)[:, :P]
+        if counts_on is not None and t0.shape[0] == 1:
+            t0 = t0.expand(self._counts(counts_on, len(counts_on)).shape[0], P).contiguous()
+        n = t0.shape[0]
+        on, off = self._counts(counts_on, n), self._counts(counts_off, n)
+        lo = torch.as_tensor(np.array([p.min for p in self.free]) if lower is None else lower, dtype=torch.float64, device=dev)
+        hi = torch.as_tensor(np.array([p.max for p in self.free]) if upper is None else upper, dtype=torch.float64, device=dev)
+        boxed = torch.isfinite(lo) & torch.isfinite(hi)
+        span = torch.where(boxed, hi - lo, torch.ones_like(lo))
+        base = torch.where(boxed, lo, torch.zeros_like(lo))
+
+        def to_theta(u):
+            sg = torch.sigmoid(u)
+            theta = torch.where(boxed, base + span * sg, u)
+            d = torch.where(boxed, span * sg * (1.0 - sg), torch.ones_like(u))
+            return theta, d
+
+        z = ((t0 - base) / span).clamp(1e-12, 1.0 - 1e-12)
+        u = torch.where(boxed, torch.log(z) - torch.log1p(-z), t0)
+
+        def evaluate(u):
+            theta, d = to_theta(u)
+            ll, g, h = self.normal_equations(theta, on, off)
+            return ll, g * d, h * d[:, :, None] * d[:, None, :]
+
+        ll, g, h = evaluate(u)
+        lam = torch.full((n,), 1e-3, dtype=torch.float64, device=dev)
+        done = ~torch.isfinite(ll)
+        n_iter = torch.zeros((n,), dtype=torch.int64, device=dev)
+        eye = torch.eye(P, dtype=torch.float64, device=dev)
+        for _ in range(max_iter):
+            diag = torch.diagonal(h, dim1=1, dim2=2)
+            a = h + (lam[:, None] * (diag + 1e-12 * diag.amax(1, keepdim=True) + 1e-300))[:, :, None] * eye
+            a = torch.where(torch.isfinite(a), a, eye.expand_as(a))
+            delta = torch.linalg.solve(a, torch.nan_to_num(g).unsqueeze(-1)).squeeze(-1)
+            delta = torch.where(done[:, None], torch.zeros_like(delta), delta)
+            u_t = u + delta
+            ll_t, g_t, h_t = evaluate(u_t)
+            better = torch.isfinite(ll_t) & (ll_t >= ll) & ~done
+            step = delta.abs().amax(1)
+            small = (step <= xtol * (1.0 + u.abs().amax(1))) | (g_t.abs().amax(1) <= gtol)
+            u = torch.where(better[:, None], u_t, u)
+            g = torch.where(better[:, None], g_t, g)
+            h = torch.where(better[:, None, None], h_t, h)
+            ll = torch.where(better, ll_t, ll)
+            n_iter += (~done).to(torch.int64)
+            lam = torch.where(better, (lam * 0.2).clamp_min(1e-15), (lam * 4.0).clamp_max(1e15))
+            done = done | (better & small) | (~better & (lam >= 1e15))
+            if bool(done.all()):
+                break
+        theta, _ = to_theta(u)
+        grad_norm = torch.linalg.norm(g, dim=1)
+        valid = torch.isfinite(ll) & torch.isfinite(grad_norm) & (grad_norm <= 1e-3)
+        return {'theta': theta, 'loglike': ll, 'deviance': -2.0 * ll, 'grad_norm': grad_norm, 'n_iter': n_iter,
+                'valid': valid, 'converged': done}
+
     def deviance(self, theta, **kw):
         """-2 * loglike per dataset (infer/helper.py:571-580)."""
         return -2.0 * self.loglike(theta, **kw)

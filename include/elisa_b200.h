@@ -227,6 +227,19 @@ int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta,
 int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, int64_t n, double* unfold,
                           void* cuda_stream);
 
+/* Gauss-Newton normal equations of the deviance residuals r_c = sqrt(-2 l_c), the least-squares
+ * problem the reference's batched re-fit hands to Levenberg-Marquardt (infer/helper.py:588-594,
+ * 601-625: fit_once / batch_fit, used by boot() and ppc()).  Per parameter vector, summed over
+ * all spectra of the plan:
+ *   loglike[n]    = sum_c l_c                                   (= -0.5 * |r|^2)
+ *   grad[n, p]    = d loglike / d theta_p                       (= -(J^T r)_p)
+ *   jtj[n, p, q]  = sum_c (dr_c/dtheta_p)(dr_c/dtheta_q)        (P x P, symmetric, both halves)
+ * from forward-folded tangent spectra (one forward fold per free parameter, no transposed
+ * fold).  counts_on / counts_off as in loglike_dev (per-replica simulated data).  P <= 8.
+ * The first call allocates the plan's tangent workspace ((1 + P) * chunk * C doubles).     */
+int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
+                             int64_t n, double* loglike, double* grad, double* jtj, void* cuda_stream);
+
 /* Host-buffer variants: H2D copy of theta (and counts), compute, D2H copy of the
  * results, synchronous.  grad may be NULL (value only).                             */
 int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const double* counts_on,

@@ -1,0 +1,148 @@
+"""Batched Levenberg-Marquardt re-fit (reference: fit_once / batch_fit,
+infer/helper.py:601-806): the normal equations against the oracle, and the fitted optimum
+against an independent CPU optimiser driving the oracle on the same simulated data."""
+
+import numpy as np
+import pytest
+import torch
+
+from elisa_b200 import models as M
+
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import _one_spectrum, _theta_for  # noqa: E402
+
+
+def _oracle_residuals(cfg, theta, on, off=None):
+    import oracle
+
+    model = cfg['model'][0].compile() if not hasattr(cfg['model'][0], 'to_spec') else cfg['model'][0]
+    d = cfg['data'][0].as_mapping()
+    s = oracle.sites(cfg['stat'][0], d, model.to_spec(), theta, on, off)
+    return torch.sqrt(-2.0 * s['loglike'])
+
+
+@pytest.mark.parametrize('fold', ['i8', 'dmma'])
+@pytest.mark.parametrize('stat', ['chi2', 'cstat', 'pgstat', 'wstat'])
+def test_normal_equations_match_autograd_of_the_oracle_residuals(lib, stat, fold):
+    from elisa_b200 import Likelihood
+
+    d = _one_spectrum(E=90, C=48, seed=31)
+    model = M.CutoffPL() + M.Gauss(El=20.0, sigma=3.0)
+    cm = model.compile()
+    theta = _theta_for(model, 12, 9)
+    rng = np.random.default_rng(4)
+    on = rng.poisson(40.0, (12, 48)).astype(float)
+    off = rng.poisson(15.0, (12, 48)).astype(float)
+    cfg = dict(data=[d], model=[cm], stat=[stat])
+    lk = Likelihood([d], cm, [stat], fold=fold)
+    kw = dict(counts_on=on) if stat in ('chi2', 'cstat') else dict(counts_on=on, counts_off=off)
+    ll, g, h = lk.normal_equations(theta, **kw)
+    lk.close()
+    t = torch.as_tensor(theta, dtype=torch.float64)
+    for i in range(len(theta)):
+        ti = t[i : i + 1].clone().requires_grad_(True)
+        fn = lambda x: _oracle_residuals(cfg, x, on[i : i + 1], off[i : i + 1] if 'counts_off' in kw else None)[0]  # noqa: E731
+        r = fn(ti)
+        J = torch.autograd.functional.jacobian(fn, ti)[:, 0, :]  # (C, P)
+        ok = (r > 0).numpy()  # a channel at r = 0 has no defined dr/dtheta (and adds nothing here)
+        J = torch.nan_to_num(J)[ok]
+        r = r.detach()[ok]
+        assert np.isclose(ll[i].item(), -0.5 * float((r**2).sum()), rtol=1e-10)
+        gref = -(J.T @ r).numpy()
+        href = (J.T @ J).numpy()
+        assert np.allclose(g[i].cpu().numpy(), gref, rtol=1e-8, atol=1e-8 * np.abs(gref).max()), (stat, i)
+        assert np.allclose(h[i].cpu().numpy(), href, rtol=1e-8, atol=1e-8 * np.abs(href).max()), (stat, i)
+
+
+def _resolved_spectrum(E, C, exposure):
+    """a spectrum with an energy-resolving response (synthetic.dense_response), so that spectral
+    shape parameters are actually constrained by the data"""
+    from elisa_b200 import synthetic
+    from elisa_b200.data import FixedData
+
+    eg = np.geomspace(0.3, 80.0, E + 1)
+    cg = np.geomspace(0.3, 12.0, C + 1)
+    R = synthetic.dense_response(eg, cg, seed=1)
+    z = np.zeros(C)
+    return FixedData('d', eg, z.copy(), np.ones(C), exposure, channel_width=np.diff(cg), response_matrix=R,
+                     net_counts=z.copy(), net_errors=np.ones(C), back_counts=np.full(C, 30.0),
+                     back_errors=np.full(C, 5.5), back_ratio=0.5)
+
+
+@pytest.mark.parametrize('case', ['powerlaw_cstat', 'cutoffpl_gauss_chi2', 'absorbed_pl_wstat'])
+def test_batched_fit_reaches_the_optimum_of_an_independent_optimiser(lib, case):
+    import scipy.optimize
+
+    import oracle
+    from elisa_b200 import Likelihood
+
+    rng = np.random.default_rng(17)
+    E, C, n = 160, 96, 24
+    d = _resolved_spectrum(E, C, 20.0)
+    U = M.UniformParameter
+    if case == 'powerlaw_cstat':
+        model, stat, truth = M.PowerLaw(alpha=U('alpha', 1.6, 0.0, 4.0), K=U('K', 3.0, 1e-3, 1e3)), 'cstat', [1.6, 3.0]
+    elif case == 'cutoffpl_gauss_chi2':
+        model = M.CutoffPL(alpha=U('alpha', 1.3, -1.0, 4.0), Ec=U('Ec', 6.0, 0.5, 500.0), K=U('K', 5.0, 1e-3, 1e3)) + \
+            M.Gauss(El=6.4, sigma=0.3, K=U('Kg', 1.0, 1e-3, 1e3))
+        stat, truth = 'chi2', [1.3, 6.0, 5.0, 1.0]
+    else:
+        te = np.geomspace(0.1, 500.0, 200)
+        model = M.PhAbs(te, 0.25 * te**-2.5, nH=U('nH', 1.0, 0.0, 10.0)) * M.PowerLaw(alpha=U('alpha', 1.8, 0.0, 4.0), K=U('K', 6.0, 1e-3, 1e3))
+        stat, truth = 'wstat', [1.0, 1.8, 6.0]
+    cm = model.compile()
+    truth = np.asarray(truth)
+    probe = Likelihood([d], cm, ['cstat'])  # cstat's Non_model site is the folded source counts
+    mu = probe.sites(0, truth[None])['d_Non_model'][0].cpu().numpy()
+    probe.close()
+    off = None
+    if stat == 'chi2':
+        d.net_errors[:] = np.sqrt(np.maximum(mu, 1.0))
+        on = rng.normal(mu, d.net_errors, (n, C))
+    elif stat == 'cstat':
+        on = rng.poisson(mu, (n, C)).astype(float)
+    else:
+        on = rng.poisson(mu + 0.5 * 30.0, (n, C)).astype(float)
+        off = rng.poisson(30.0, (n, C)).astype(float)
+    lk = Likelihood([d], cm, [stat])
+    start = truth * (1.0 + 0.2 * rng.standard_normal((n, truth.size)))
+    start = np.clip(start, [p.min + 1e-3 * (p.max - p.min) for p in cm.free], [p.max - 1e-3 * (p.max - p.min) for p in cm.free])
+    out = lk.fit(start, counts_on=on, counts_off=off)
+    lk.close()
+    assert bool(out['valid'].all()), out['grad_norm']
+    theta = out['theta'].cpu().numpy()
+    dev = out['deviance'].cpu().numpy()
+    # independent optimiser on the oracle: BFGS from the truth, in the same unconstrained space
+    lo = np.array([p.min for p in cm.free]); hi = np.array([p.max for p in cm.free])
+    spec, dm = cm.to_spec(), d.as_mapping()
+    for i in range(0, n, 6):
+        oi = None if off is None else [off[i : i + 1]]
+
+        def f(u):
+            sg = 1.0 / (1.0 + np.exp(-u))
+            th = lo + (hi - lo) * sg
+            ll, g = oracle.loglike_and_grad([stat], [dm], [spec], torch.as_tensor(th[None]), [on[i : i + 1]], oi)
+            return -2.0 * float(ll[0, 0]), -2.0 * g[0, 0].numpy() * (hi - lo) * sg * (1 - sg)
+
+        z = (theta[i] - lo) / (hi - lo)
+        res = scipy.optimize.minimize(f, np.log(z) - np.log1p(-z), jac=True, method='BFGS', options=dict(gtol=1e-9, maxiter=500))
+        th_ref = lo + (hi - lo) / (1.0 + np.exp(-res.x))
+        assert res.fun <= dev[i] * (1 + 1e-12) + 1e-9  # BFGS started at our optimum: it cannot be better than noise
+        assert np.isclose(dev[i], res.fun, rtol=1e-9, atol=1e-7), (case, i, dev[i], res.fun)
+        # the optimum itself: to 1e-3 (along a flat valley -- a cutoff energy far outside the data's range --
+        # parameter values 1e-4 apart share the deviance to 1e-9)
+        assert np.allclose(theta[i], th_ref, rtol=1e-3), (case, i, theta[i], th_ref)
+    # ... and from a fresh start the independent optimiser lands on the same deviance
+    for i in (1, 7):
+        oi = None if off is None else [off[i : i + 1]]
+
+        def f(u):
+            sg = 1.0 / (1.0 + np.exp(-u))
+            th = lo + (hi - lo) * sg
+            ll, g = oracle.loglike_and_grad([stat], [dm], [spec], torch.as_tensor(th[None]), [on[i : i + 1]], oi)
+            return -2.0 * float(ll[0, 0]), -2.0 * g[0, 0].numpy() * (hi - lo) * sg * (1 - sg)
+
+        z = (truth - lo) / (hi - lo)
+        res = scipy.optimize.minimize(f, np.log(z) - np.log1p(-z), jac=True, method='BFGS', options=dict(gtol=1e-8, maxiter=1000))
+        assert np.isclose(dev[i], res.fun, rtol=1e-8, atol=1e-6), (case, i, dev[i], res.fun)
