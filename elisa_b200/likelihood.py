@@ -355,6 +355,58 @@ class Likelihood:
         return {'theta': theta, 'loglike': ll, 'deviance': -2.0 * ll, 'grad_norm': grad_norm, 'n_iter': n_iter,
                 'valid': valid, 'converged': done}
 
+    def simulate(self, theta, n: int = 1, seed: int = 0):
+        """Simulated data sets drawn on the device from the model at ``theta`` (infer/helper.py:
+        221-278): ``{name}_Non`` ~ Poisson(``{name}_Non_model``) -- Normal(model, net_errors) for
+        chi2 -- and, for pgstat / wstat, ``{name}_Noff`` ~ Normal(``{name}_Noff_model``,
+        back_errors) / Poisson(``{name}_Noff_model``).  ``theta`` is (P,) with ``n`` replicas or
+        (N, P) with one replica per row (the reference's posterior-predictive case).  Returns
+        ``(counts_on, counts_off)``, (rows, sum of channels) CUDA tensors in the layout the
+        evaluation entry points take (``counts_off`` is None when no dataset has a sampled
+        background).  The stream of random numbers is torch's Philox generator seeded with
+        ``seed``: the reference's NumPy stream cannot be reproduced on a GPU, so parity here is
+        distributional (tests check moments and the fit recovering the truth)."""
+        torch = self._torch
+        t = self._theta(theta)
+        if t.shape[0] != 1 and n != 1:
+            raise ValueError('n > 1 needs a single parameter vector (helper.py:851-857)')
+        rows = t.shape[0] if t.shape[0] != 1 else int(n)
+        gen = torch.Generator(device=t.device).manual_seed(int(seed))
+        on, off, any_off = [], [], False
+        for k, (d, stat) in enumerate(zip(self.data, self.stat)):
+            sites = self.sites(k, t)
+            name = self.names[k]
+            m_on = sites[f'{name}_Non_model'].expand(rows, -1).contiguous()
+            if stat == 'chi2':
+                err = torch.as_tensor(d.net_errors, dtype=torch.float64, device=t.device)
+                on.append(m_on + err * torch.randn(m_on.shape, dtype=torch.float64, device=t.device, generator=gen))
+            else:
+                on.append(torch.poisson(m_on, generator=gen))
+            if stat in ('pgstat', 'wstat'):
+                any_off = True
+                m_off = sites[f'{name}_Noff_model'].expand(rows, -1).contiguous()
+                if stat == 'pgstat':
+                    err = torch.as_tensor(d.back_errors, dtype=torch.float64, device=t.device)
+                    off.append(m_off + err * torch.randn(m_off.shape, dtype=torch.float64, device=t.device, generator=gen))
+                else:
+                    off.append(torch.poisson(m_off, generator=gen))
+            else:  # not sampled: the observed background (if any) stays in place
+                b = d.back_counts if getattr(d, 'back_counts', None) is not None else np.zeros(d.n_channels)
+                off.append(torch.as_tensor(b, dtype=torch.float64, device=t.device).expand(rows, -1))
+        return torch.cat(on, dim=1).contiguous(), (torch.cat(off, dim=1).contiguous() if any_off else None)
+
+    def simulate_and_fit(self, theta, n: int = 1, seed: int = 0, **fit_kw):
+        """``simulate_and_fit`` of the reference (infer/helper.py:808-876), the core of ``boot()``
+        and ``ppc()``: simulate ``n`` data sets at ``theta`` (or one per row of ``theta``), then
+        re-fit every one of them starting from the generating parameters -- entirely on the
+        device.  Returns the ``fit`` dict plus the simulated 'counts_on' / 'counts_off'."""
+        on, off = self.simulate(theta, n, seed)
+        t = self._theta(theta)[:, : self.nparam]
+        start = t.expand(on.shape[0], -1).contiguous() if t.shape[0] == 1 else t
+        out = self.fit(start, counts_on=on, counts_off=off, **fit_kw)
+        out['counts_on'], out['counts_off'] = on, off
+        return out
+
     def deviance(self, theta, **kw):
         """-2 * loglike per dataset (infer/helper.py:571-580)."""
         return -2.0 * self.loglike(theta, **kw)

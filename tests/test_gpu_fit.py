@@ -146,3 +146,50 @@ def test_batched_fit_reaches_the_optimum_of_an_independent_optimiser(lib, case):
         z = (truth - lo) / (hi - lo)
         res = scipy.optimize.minimize(f, np.log(z) - np.log1p(-z), jac=True, method='BFGS', options=dict(gtol=1e-8, maxiter=1000))
         assert np.isclose(dev[i], res.fun, rtol=1e-8, atol=1e-6), (case, i, dev[i], res.fun)
+
+
+def test_device_simulator_and_bootstrap_loop(lib):
+    """simulate (helper.py:221-278) + simulate_and_fit (:808-876) on the device: the sampled
+    counts have the model's mean and the sampling distribution's variance, the bootstrap
+    re-fits scatter around the generating parameters with the spread the curvature predicts."""
+    from elisa_b200 import Likelihood
+
+    U = M.UniformParameter
+    n = 4000
+    truth = np.array([1.6, 3.0])
+    # Poisson on and off (wstat)
+    d = _resolved_spectrum(160, 96, 20.0)
+    model = M.PowerLaw(alpha=U('alpha', 1.6, 0.0, 4.0), K=U('K', 3.0, 1e-3, 1e3)).compile()
+    lk = Likelihood([d], model, ['wstat'])
+    on, off = lk.simulate(truth, n=n, seed=3)
+    sites = lk.sites(0, truth[None])
+    m_on, m_off = sites['d_Non_model'][0], sites['d_Noff_model'][0]
+    assert on.shape == (n, 96) and off.shape == (n, 96)
+    assert torch.all(on >= 0) and torch.all(on == on.round())
+    z = (on.mean(0) - m_on) / torch.sqrt(m_on / n)
+    assert float(z.abs().max()) < 5.0 and abs(float(z.mean())) < 0.5
+    assert torch.allclose(on.var(0), m_on, rtol=0.2) and torch.allclose(off.var(0), m_off, rtol=0.2)
+    on2, _ = lk.simulate(truth, n=n, seed=3)
+    assert torch.equal(on, on2)  # reproducible per seed
+    out = lk.simulate_and_fit(truth, n=n, seed=5)
+    assert float(out['valid'].double().mean()) > 0.99
+    th = out['theta'][out['valid']]
+    _, _, h = lk.normal_equations(np.tile(truth, (256, 1)), counts_on=on[:256], counts_off=off[:256])
+    cov = torch.linalg.inv(h.mean(0))  # Gauss-Newton (Fisher) covariance at the truth
+    sd = torch.sqrt(torch.diagonal(cov))
+    bias = (th.mean(0) - torch.as_tensor(truth, device=th.device)) / (sd / np.sqrt(len(th)))
+    assert float(bias.abs().max()) < 6.0, bias
+    assert torch.allclose(th.std(0), sd, rtol=0.15), (th.std(0), sd)
+    lk.close()
+    # Normal data (chi2) and per-row parameter vectors
+    d.net_errors[:] = np.sqrt(np.maximum(m_on.cpu().numpy(), 1.0))
+    lk = Likelihood([d], model, ['chi2'])
+    thetas = truth * (1.0 + 0.01 * np.random.default_rng(0).standard_normal((500, 2)))
+    on, off = lk.simulate(thetas, seed=1)
+    assert on.shape == (500, 96) and off is None
+    mu = lk.sites(0, thetas)['d_Non_model']
+    pull = (on - mu) / torch.as_tensor(d.net_errors, device=on.device)
+    assert abs(float(pull.mean())) < 0.02 and abs(float(pull.std()) - 1.0) < 0.02
+    with pytest.raises(ValueError):
+        lk.simulate(thetas, n=3)
+    lk.close()
