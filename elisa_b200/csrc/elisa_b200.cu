@@ -612,6 +612,22 @@ struct ElisaPlan {
     double* a_scale = nullptr;
     unsigned long long* guard = nullptr;  // [2] accuracy guard of the integer fold (stat_slice_kernel)
     double* Xp = nullptr;  // [1 + P][chunk, max_C_pad] forward-folded model and tangents (normal equations; lazily allocated)
+    // Small batches (NUTS chains, single fits) are launch-bound: ~5 kernels per spectrum of a few
+    // microseconds each.  The launch sequence of a (n, with gradient) shape is captured into a CUDA
+    // graph on its second use and replayed afterwards; the caller's buffers enter and leave
+    // through memcpy nodes whose addresses are patched per call, so the graph never goes stale.
+    struct GraphEntry {
+        int64_t n = 0;
+        bool grad = false;
+        int uses = 0;
+        int64_t kernels = 0;  // kernel launches one replay stands for
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t in_theta = nullptr, out_ll = nullptr, out_grad = nullptr;
+    };
+    std::vector<GraphEntry> graphs;
+    double *g_theta = nullptr, *g_ll = nullptr, *g_grad = nullptr;  // staging, GRAPH_MAX_N rows
+    bool graphs_enabled = true;
     int sm_count = 148;
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
@@ -1687,6 +1703,89 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
     return rc;
 }
 
+constexpr int64_t GRAPH_MAX_N = 1024;
+
+static void patch_memcpy(cudaGraphExec_t exec, cudaGraphNode_t node, void* dst, const void* src, size_t bytes) {
+    cudaGraphExecMemcpyNodeSetParams1D(exec, node, dst, src, bytes, cudaMemcpyDeviceToDevice);
+}
+
+// last node captured on `st` so far (the memcpy just enqueued)
+static cudaGraphNode_t last_captured_node(cudaStream_t st) {
+    cudaStreamCaptureStatus status;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t n_deps = 0;
+    if (cudaStreamGetCaptureInfo(st, &status, nullptr, nullptr, &deps, &n_deps) != cudaSuccess || n_deps == 0)
+        return nullptr;
+    return deps[n_deps - 1];
+}
+
+// value (+ gradient) of a small batch through a replayed CUDA graph; falls back to run_all.
+static int run_small(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
+                     double* loglike, double* grad, cudaStream_t st) {
+    const bool eligible = plan != nullptr && plan->graphs_enabled && !plan->profiling && n > 0 && n <= GRAPH_MAX_N &&
+                          n <= plan->chunk && on == nullptr && off == nullptr && theta != nullptr && loglike != nullptr &&
+                          plan->g_theta != nullptr;
+    if (!eligible) return run_all(plan, theta, on, off, n, loglike, grad, st);
+    ElisaPlan::GraphEntry* e = nullptr;
+    for (auto& g : plan->graphs)
+        if (g.n == n && g.grad == (grad != nullptr)) e = &g;
+    if (e == nullptr) {
+        if (plan->graphs.size() >= 16) return run_all(plan, theta, on, off, n, loglike, grad, st);
+        plan->graphs.emplace_back();
+        e = &plan->graphs.back();
+        e->n = n;
+        e->grad = grad != nullptr;
+    }
+    const size_t b_theta = (size_t)n * plan->P * 8, b_ll = (size_t)n * plan->S * 8, b_grad = (size_t)n * plan->S * plan->P * 8;
+    if (e->exec == nullptr) {
+        if (++e->uses < 2)  // first use of a shape runs directly (one-time kernel configuration, JIT loads)
+            return run_all(plan, theta, on, off, n, loglike, grad, st);
+        int dev;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
+        cudaStream_t cs = plan->stream;
+        int rc = ELISA_OK;
+        bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            ok = cudaMemcpyAsync(plan->g_theta, theta, b_theta, cudaMemcpyDeviceToDevice, cs) == cudaSuccess;
+            e->in_theta = last_captured_node(cs);
+            const int64_t before = plan->launches;
+            if (ok) rc = run_all(plan, plan->g_theta, nullptr, nullptr, n, plan->g_ll, grad ? plan->g_grad : nullptr, cs);
+            e->kernels = plan->launches - before;
+            plan->launches = before;  // counted per replay below
+            ok = ok && rc == ELISA_OK;
+            if (ok) ok = cudaMemcpyAsync(loglike, plan->g_ll, b_ll, cudaMemcpyDeviceToDevice, cs) == cudaSuccess;
+            e->out_ll = last_captured_node(cs);
+            if (ok && grad) {
+                ok = cudaMemcpyAsync(grad, plan->g_grad, b_grad, cudaMemcpyDeviceToDevice, cs) == cudaSuccess;
+                e->out_grad = last_captured_node(cs);
+            }
+            cudaGraph_t graph = nullptr;
+            const bool ended = cudaStreamEndCapture(cs, &graph) == cudaSuccess && graph != nullptr;
+            ok = ok && ended && e->in_theta && e->out_ll && (!grad || e->out_grad);
+            if (ok) ok = cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess;
+            if (ok) {
+                e->graph = graph;
+            } else {
+                if (graph) cudaGraphDestroy(graph);
+                e->exec = nullptr;
+            }
+        }
+        if (dev != plan->device) cudaSetDevice(dev);
+        if (!ok) {  // capture is an optimisation: never fail the call because of it
+            cudaGetLastError();
+            plan->graphs_enabled = false;
+            return run_all(plan, theta, on, off, n, loglike, grad, st);
+        }
+    }
+    patch_memcpy(e->exec, e->in_theta, plan->g_theta, theta, b_theta);
+    patch_memcpy(e->exec, e->out_ll, loglike, plan->g_ll, b_ll);
+    if (grad) patch_memcpy(e->exec, e->out_grad, grad, plan->g_grad, b_grad);
+    CUDA_TRY(cudaGraphLaunch(e->exec, st));
+    plan->launches += e->kernels;
+    return ELISA_OK;
+}
+
 }  // namespace elisa
 
 // ======================================================================================
@@ -1706,6 +1805,10 @@ void elisa_b200_plan_destroy(ElisaPlan* plan) {
     for (void* p : plan->owned) cudaFree(p);
     for (double* p : {plan->h_theta, plan->h_ll, plan->h_grad, plan->h_on, plan->h_off})
         if (p) cudaFree(p);
+    for (auto& g : plan->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     for (cudaEvent_t e : plan->ev_pool) cudaEventDestroy(e);
     if (plan->stream) cudaStreamDestroy(plan->stream);
     cudaSetDevice(dev);
@@ -1835,6 +1938,20 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
             }
         }
     }
+    if (rc == ELISA_OK) {
+        const char* env = getenv("ELISA_B200_GRAPHS");
+        plan->graphs_enabled = !(env && atoi(env) == 0);
+        auto alloc_small = [&](double** p, int64_t n_doubles) -> int {
+            CUDA_TRY(cudaMalloc((void**)p, (size_t)n_doubles * 8));
+            plan->owned.push_back(*p);
+            return ELISA_OK;
+        };
+        if (plan->graphs_enabled) {
+            rc = alloc_small(&plan->g_theta, GRAPH_MAX_N * plan->P);
+            if (rc == ELISA_OK) rc = alloc_small(&plan->g_ll, GRAPH_MAX_N * plan->S);
+            if (rc == ELISA_OK) rc = alloc_small(&plan->g_grad, GRAPH_MAX_N * plan->S * plan->P);
+        }
+    }
     if (rc == ELISA_OK && cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(ELISA_ERR_CUDA, "cudaStreamCreate failed");
     cudaSetDevice(prev);
@@ -1864,14 +1981,14 @@ int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const d
 
 int elisa_b200_loglike_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
                            int64_t n, double* loglike, void* cuda_stream) {
-    return run_all(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
+    return run_small(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
 }
 
 int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const double* counts_on,
                                 const double* counts_off, int64_t n, double* loglike, double* grad,
                                 void* cuda_stream) {
     if (grad == nullptr) return fail(ELISA_ERR_INVALID, "grad is null");
-    return run_all(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
+    return run_small(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
 }
 
 int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, int64_t n, double* unfold,

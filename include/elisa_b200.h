@@ -25,7 +25,10 @@
  *    -2 * loglike and the joint total is the row sum;
  *  - grad is [N, S, P]: d loglike[n, s] / d theta[n, p];
  *  - "_dev" entry points take DEVICE pointers and only enqueue work on the given
- *    stream (no allocation, no host synchronisation); "_host" entry points take HOST
+ *    stream (no allocation, no host synchronisation); batches of <= 1024 parameter vectors
+ *    without per-replica counts are launch-bound, so their kernel sequence is captured into a
+ *    CUDA graph on the second call of a shape and replayed afterwards (env
+ *    ELISA_B200_GRAPHS=0 disables it; results are bit-identical either way); "_host" entry points take HOST
  *    pointers, stage through the plan's pinned buffers and return when results are
  *    in the caller's memory;
  *  - every function returns 0 on success or a negative ELISA_ERR_* code and never

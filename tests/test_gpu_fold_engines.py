@@ -171,3 +171,34 @@ def test_accuracy_guard_quiet_on_baseline_shapes_and_trips_on_starved_channels(l
     ll_h, g_h = lk.loglike_and_grad_host(theta)
     assert lk.guard_fallbacks == 2 and rel_err_value(ll_h, ll_ref) <= RTOL
     lk.close()
+
+
+@pytest.mark.parametrize('fold', ['i8', 'dmma'])
+def test_small_batches_replay_a_cuda_graph_with_identical_results(lib, fold, monkeypatch):
+    """n <= 1024 without per-replica counts: the launch sequence is captured on the second call
+    of a shape and replayed afterwards (new theta values, new output buffers): bit-identical to
+    the direct launches (ELISA_B200_GRAPHS=0)."""
+    import torch
+
+    from elisa_b200 import Likelihood
+
+    cfg = synthetic.config3(n=64)
+    rng = np.random.default_rng(0)
+    thetas = [cfg['theta'] * (1.0 + 0.01 * rng.standard_normal(cfg['theta'].shape)) for _ in range(5)]
+    monkeypatch.setenv('ELISA_B200_GRAPHS', '0')
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold=fold)
+    ref = [tuple(x.clone() for x in lk.loglike_and_grad(t)) for t in thetas]
+    ref_v = [lk.loglike(t).clone() for t in thetas]
+    lk.close()
+    monkeypatch.delenv('ELISA_B200_GRAPHS')
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold=fold)
+    n0 = lk.launch_count
+    for rep in range(2):
+        for t, (ll_ref, g_ref), v_ref in zip(thetas, ref, ref_v):
+            ll, g = lk.loglike_and_grad(t)
+            assert torch.equal(ll, ll_ref) and torch.equal(g, g_ref)
+            assert torch.equal(lk.loglike(t), v_ref)
+    assert lk.launch_count > n0
+    ll, g = lk.loglike_and_grad(thetas[0][:7])  # another shape: its own graph
+    assert torch.equal(ll, ref[0][0][:7]) and torch.equal(g, ref[0][1][:7])
+    lk.close()
