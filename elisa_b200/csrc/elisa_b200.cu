@@ -477,7 +477,17 @@ __global__ void __launch_bounds__(256) normal_eq_kernel(const NormalEqArgs a) {
         const double l = stat_channel<STAT, true>(x0[col] * sc, d, dx);
         ll += l;
         const double r2 = -2.0 * l;
-        const double w = r2 > 1e-300 ? dx * dx / r2 : 0.0;  // (dr/dx)^2; a channel at r = 0 adds no curvature
+        double w;  // (dr/dx)^2
+        if (r2 > 1e-9) {
+            w = dx * dx / r2;
+        } else {
+            // r -> 0 (model on the data): dx^2 / r^2 is 0/0 and l itself is rounding noise there;
+            // its limit is the curvature -d2l/dx2, taken from a secant of dl/dx
+            const double xs = x0[col] * sc, step = 1e-4 * fabs(xs);
+            double dx2 = 0.0;
+            if (step > 0.0) stat_channel<STAT, true>(xs + step, d, dx2);
+            w = step > 0.0 ? fmax((dx - dx2) / step, 0.0) : 0.0;
+        }
         double sp[PT];
 #pragma unroll
         for (int p = 0; p < PT; ++p)

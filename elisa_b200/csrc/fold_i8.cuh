@@ -78,15 +78,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait: a protocol error traps (launch failure) instead of hanging the device.
+// try_wait carries a suspend-time hint: the warp sleeps in hardware until the phase completes
+// (or the hint expires) instead of spinning -- in the first version more than half of all
+// instructions the kernel executed were these polls, stealing issue slots and power from the
+// epilogue warps sharing the scheduler.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(1000000u)
             : "memory");
         if (done) return;
     }

@@ -193,3 +193,29 @@ def test_device_simulator_and_bootstrap_loop(lib):
     with pytest.raises(ValueError):
         lk.simulate(thetas, n=3)
     lk.close()
+
+
+def test_normal_equations_on_asimov_data_use_the_curvature_limit(lib):
+    """data equal to the model (r = 0 in every channel): J^T J must be the Fisher matrix
+    sum_c s_p s_q / mu_c (Poisson), not 0/0"""
+    from elisa_b200 import Likelihood
+
+    d = _resolved_spectrum(160, 96, 20.0)
+    U = M.UniformParameter
+    model = M.PowerLaw(alpha=U('alpha', 1.6, 0.0, 4.0), K=U('K', 3.0, 1e-3, 1e3)).compile()
+    truth = np.array([[1.6, 3.0]])
+    lk = Likelihood([d], model, ['cstat'])
+    mu = lk.sites(0, truth)['d_Non_model']
+    ll, g, h = lk.normal_equations(truth, counts_on=mu)
+    eps = 1e-6
+    jac = []
+    for j in range(2):
+        tp, tm = truth.copy(), truth.copy()
+        tp[0, j] *= 1 + eps
+        tm[0, j] *= 1 - eps
+        jac.append((lk.sites(0, tp)['d_Non_model'] - lk.sites(0, tm)['d_Non_model'])[0] / (2 * eps * truth[0, j]))
+    J = torch.stack(jac, dim=1)  # d mu_c / d theta_p
+    fisher = (J / mu[0][:, None]).T @ J
+    assert abs(float(ll[0])) < 1e-9 and float(g.abs().max()) < 1e-6
+    assert torch.allclose(h[0], fisher, rtol=2e-3), (h[0], fisher)
+    lk.close()
