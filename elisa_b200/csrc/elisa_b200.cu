@@ -1631,8 +1631,10 @@ static int launch_normal_eq(ElisaPlan* plan, const NormalEqArgs& a, cudaStream_t
     ScopedSpan span(plan, ELISA_PROFILE_STAT, st);
     if (a.P <= 4)
         normal_eq_kernel<STAT, 4><<<blocks, 256, 0, st>>>(a);
-    else
+    else if (a.P <= 8)
         normal_eq_kernel<STAT, 8><<<blocks, 256, 0, st>>>(a);
+    else  // 136 accumulators per lane: spills, but re-fits with > 8 free parameters are rare
+        normal_eq_kernel<STAT, 16><<<blocks, 256, 0, st>>>(a);
     ++plan->launches;
     CUDA_TRY(cudaGetLastError());
     return ELISA_OK;
@@ -2170,7 +2172,6 @@ int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double*
     if (n == 0) return ELISA_OK;
     if (theta == nullptr || loglike == nullptr || grad == nullptr || jtj == nullptr)
         return fail(ELISA_ERR_INVALID, "normal_eq: null pointer");
-    if (plan->P > 8) return fail(ELISA_ERR_UNSUPPORTED, "normal_eq: more than 8 free parameters");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     int prev = 0;
     CUDA_TRY(cudaGetDevice(&prev));

@@ -87,3 +87,20 @@ class ShardedLikelihood:
 
     def loglike_and_grad(self, theta, counts_on=None, counts_off=None, gather=True):
         return sharded_map(self.lk.loglike_and_grad, (theta, counts_on, counts_off), len(theta), self.group, gather)
+
+    def fit(self, theta0, counts_on=None, counts_off=None, gather=True, **fit_kw):
+        """Batched re-fit of this rank's block of replicas (``Likelihood.fit``); with ``gather``
+        every rank receives the full ('theta', 'deviance', 'grad_norm', 'n_iter', 'valid')
+        -- the reference's ``fit_in_parallel`` (infer/helper.py:690-718) concatenates the
+        per-device results the same way."""
+        keys = ('theta', 'deviance', 'grad_norm', 'n_iter', 'valid')
+
+        def local(t, on, off):
+            out = self.lk.fit(t, counts_on=on, counts_off=off, **fit_kw)
+            return tuple(out[k].double() for k in keys)  # one dtype for the gather
+
+        res = sharded_map(local, (theta0, counts_on, counts_off), len(theta0), self.group, gather)
+        out = dict(zip(keys, res))
+        out['n_iter'] = out['n_iter'].long()
+        out['valid'] = out['valid'] > 0.5
+        return out

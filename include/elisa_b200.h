@@ -238,7 +238,7 @@ int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta
  *   grad[n, p]    = d loglike / d theta_p                       (= -(J^T r)_p)
  *   jtj[n, p, q]  = sum_c (dr_c/dtheta_p)(dr_c/dtheta_q)        (P x P, symmetric, both halves)
  * from forward-folded tangent spectra (one forward fold per free parameter, no transposed
- * fold).  counts_on / counts_off as in loglike_dev (per-replica simulated data).  P <= 8.
+ * fold).  counts_on / counts_off as in loglike_dev (per-replica simulated data).
  * The first call allocates the plan's tangent workspace ((1 + P) * chunk * C doubles).     */
 int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
                              int64_t n, double* loglike, double* grad, double* jtj, void* cuda_stream);

@@ -178,12 +178,20 @@ def _worker(rank, world, port, n, q):
         def loglike(self, t, on=None, off=None):
             return t.sum(1, keepdim=True)
 
+        def fit(self, t, counts_on=None, counts_off=None, **kw):
+            return {'theta': t + 1.0, 'deviance': t.sum(1), 'grad_norm': t[:, 0] * 0.0,
+                    'n_iter': torch.full((len(t),), 3), 'valid': t[:, 0] >= 0, 'loglike': -0.5 * t.sum(1)}
+
     sl = ShardedLikelihood(Fake())
+    fit = sl.fit(theta, counts)
+    fit_ok = (torch.equal(fit['theta'], theta + 1.0) and torch.equal(fit['deviance'], theta.sum(1))
+              and fit['n_iter'].dtype == torch.int64 and bool((fit['n_iter'] == 3).all()) and fit['valid'].dtype == torch.bool
+              and bool(fit['valid'].all()) and fit['theta'].shape[0] == n)
     ll, g = sl.loglike_and_grad(theta, counts)
     local = sl.loglike(theta, gather=False)
     same = sharded_map(lambda t: t * 1.0, (theta,), n)
     ok = (torch.equal(ll, theta.sum(1, keepdim=True) + counts.sum(1, keepdim=True)) and torch.equal(g, theta.unsqueeze(1) * 2.0)
-          and torch.equal(same, theta))
+          and torch.equal(same, theta) and fit_ok)
     q.put((rank, bool(ok), Fake.calls[0], local.shape[0]))
     dist.destroy_process_group()
 

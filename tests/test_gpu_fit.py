@@ -219,3 +219,27 @@ def test_normal_equations_on_asimov_data_use_the_curvature_limit(lib):
     assert abs(float(ll[0])) < 1e-9 and float(g.abs().max()) < 1e-6
     assert torch.allclose(h[0], fisher, rtol=2e-3), (h[0], fisher)
     lk.close()
+
+
+def test_normal_equations_with_more_than_eight_parameters(lib):
+    """P = 11 free parameters (three components): the 16-parameter instantiation against autograd"""
+    from elisa_b200 import Likelihood
+
+    d = _one_spectrum(E=90, C=48, seed=33)
+    U = M.UniformParameter
+    model = (M.Band() + M.CutoffPL() + M.SmoothlyBrokenPL(rho=U('rho', 1.0, 0.1, 10.0))).compile()
+    assert model.nparam == 12
+    theta = _theta_for(model.model, 4, 3)
+    on = np.random.default_rng(8).poisson(60.0, (4, 48)).astype(float)
+    lk = Likelihood([d], model, ['cstat'])
+    ll, g, h = lk.normal_equations(theta, counts_on=on)
+    ll2, g2 = lk.loglike_and_grad(theta, counts_on=on)
+    lk.close()
+    assert torch.allclose(ll, ll2[:, 0], rtol=1e-10) and torch.allclose(g, g2[:, 0], rtol=1e-7, atol=1e-7 * float(g2.abs().max()))
+    cfg = dict(data=[d], model=[model], stat=['cstat'])
+    t = torch.as_tensor(theta, dtype=torch.float64)
+    for i in range(4):
+        fn = lambda x: _oracle_residuals(cfg, x, on[i : i + 1])[0]  # noqa: E731
+        J = torch.nan_to_num(torch.autograd.functional.jacobian(fn, t[i : i + 1].clone())[:, 0, :])
+        href = (J.T @ J).numpy()
+        assert np.allclose(h[i].cpu().numpy(), href, rtol=1e-7, atol=1e-8 * np.abs(href).max()), i
