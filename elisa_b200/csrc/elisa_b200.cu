@@ -638,6 +638,18 @@ struct ElisaPlan {
     std::vector<GraphEntry> graphs;
     double *g_theta = nullptr, *g_ll = nullptr, *g_grad = nullptr;  // staging, GRAPH_MAX_N rows
     bool graphs_enabled = true;
+    int ld_part = 0;  // leading dimension (rows) of the part / gpart arrays in use
+    // Joint fits: inside the captured graph every spectrum runs on its own branch (own stream
+    // during capture, own small workspace), so the S kernel chains of a small batch overlap
+    // instead of queueing behind one another.
+    struct SmallWs {
+        double *U = nullptr, *dU = nullptr, *W = nullptr, *part = nullptr, *gpart = nullptr, *a_scale = nullptr;
+        int8_t* A_img = nullptr;
+    };
+    std::vector<SmallWs> small_ws;
+    std::vector<cudaStream_t> small_stream;
+    std::vector<cudaEvent_t> small_done;
+    cudaEvent_t small_fork = nullptr;
     int sm_count = 148;
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
@@ -1276,7 +1288,7 @@ static int launch_stat_gemm(ElisaPlan* plan, const SpectrumPlan& sp, int n_valid
     epi.W = plan->W;
     epi.ldw = sp.C_pad;
     epi.part = plan->part;
-    epi.ld_part = (int)plan->chunk;
+    epi.ld_part = plan->ld_part;
     return launch_gemm(plan, ELISA_PROFILE_FOLD, plan->U, sp.E_pad, sp.fwd, m_tiles, epi, st);
 }
 
@@ -1547,7 +1559,7 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
     eg.used_mask = sp.model.used_mask;
     eg.n_part = I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP);
     eg.gpart = plan->gpart;
-    eg.ld_part = (int)plan->chunk;
+    eg.ld_part = plan->ld_part;
     eg.dbg = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;
     const FoldI8Args fa = fold_i8_args(plan, sp.i8_bwd, round_up(sp.C_pad, I8_BK) / I8_BK, m_tiles);
     return launch_fold_i8(plan, plan->ks, ELISA_PROFILE_TFOLD, fa, eg, plan->sm_count, st);
@@ -1599,7 +1611,7 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
         eg.used_mask = sp.model.used_mask;
         eg.n_tiles = sp.bwd.n_tiles;
         eg.gpart = plan->gpart;
-        eg.ld_part = (int)plan->chunk;
+        eg.ld_part = plan->ld_part;
         if ((rc = launch_gemm(plan, ELISA_PROFILE_TFOLD, plan->W, sp.C_pad, sp.bwd, m_tiles, eg, st))) return rc;
     } else {
         if ((rc = launch_stat_gemm_any<false>(plan, sp, n, m_tiles, on, off, st))) return rc;
@@ -1609,7 +1621,7 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     ra.gpart = plan->gpart;
     ra.tiles_c = i8 ? I8_CG * ((sp.i8_fwd.n_tiles + I8_GROUP - 1) / I8_GROUP) : sp.fwd.n_tiles;  // partial sums per row
     ra.tiles_e = i8 ? I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP) : sp.bwd.n_tiles;
-    ra.ld = (int)plan->chunk;
+    ra.ld = plan->ld_part;
     ra.n = n;
     ra.P = plan->P;
     ra.S = plan->S;
@@ -1762,7 +1774,26 @@ static int run_small(ElisaPlan* plan, const double* theta, const double* on, con
             ok = cudaMemcpyAsync(plan->g_theta, theta, b_theta, cudaMemcpyDeviceToDevice, cs) == cudaSuccess;
             e->in_theta = last_captured_node(cs);
             const int64_t before = plan->launches;
-            if (ok) rc = run_all(plan, plan->g_theta, nullptr, nullptr, n, plan->g_ll, grad ? plan->g_grad : nullptr, cs);
+            if (ok && !plan->small_ws.empty() && plan->small_fork != nullptr) {
+                // one branch per spectrum: fork from the capture stream, run the spectrum's chain in
+                // its own workspace on its own stream, join
+                struct Saved { double *U, *dU, *W, *part, *gpart, *a_scale; int8_t* A_img; int ld; } keep = {
+                    plan->U, plan->dU, plan->W, plan->part, plan->gpart, plan->a_scale, plan->A_img, plan->ld_part};
+                ok = cudaEventRecord(plan->small_fork, cs) == cudaSuccess;
+                for (int sidx = 0; sidx < plan->S && ok && rc == ELISA_OK; ++sidx) {
+                    const ElisaPlan::SmallWs& w = plan->small_ws[sidx];
+                    cudaStream_t bs = plan->small_stream[sidx];
+                    ok = cudaStreamWaitEvent(bs, plan->small_fork, 0) == cudaSuccess;
+                    plan->U = w.U; plan->dU = w.dU; plan->W = w.W; plan->part = w.part; plan->gpart = w.gpart;
+                    plan->a_scale = w.a_scale; plan->A_img = w.A_img;
+                    plan->ld_part = (int)std::min<int64_t>(GRAPH_MAX_N, plan->chunk);
+                    if (ok) rc = run_chunk(plan, sidx, plan->g_theta, nullptr, nullptr, (int)n, plan->g_ll, grad ? plan->g_grad : nullptr, bs);
+                    if (ok) ok = cudaEventRecord(plan->small_done[sidx], bs) == cudaSuccess &&
+                                 cudaStreamWaitEvent(cs, plan->small_done[sidx], 0) == cudaSuccess;
+                }
+                plan->U = keep.U; plan->dU = keep.dU; plan->W = keep.W; plan->part = keep.part; plan->gpart = keep.gpart;
+                plan->a_scale = keep.a_scale; plan->A_img = keep.A_img; plan->ld_part = keep.ld;
+            } else if (ok) rc = run_all(plan, plan->g_theta, nullptr, nullptr, n, plan->g_ll, grad ? plan->g_grad : nullptr, cs);
             e->kernels = plan->launches - before;
             plan->launches = before;  // counted per replay below
             ok = ok && rc == ELISA_OK;
@@ -1817,6 +1848,11 @@ void elisa_b200_plan_destroy(ElisaPlan* plan) {
     for (void* p : plan->owned) cudaFree(p);
     for (double* p : {plan->h_theta, plan->h_ll, plan->h_grad, plan->h_on, plan->h_off})
         if (p) cudaFree(p);
+    for (cudaStream_t st : plan->small_stream)
+        if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : plan->small_done)
+        if (e) cudaEventDestroy(e);
+    if (plan->small_fork) cudaEventDestroy(plan->small_fork);
     for (auto& g : plan->graphs) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
         if (g.graph) cudaGraphDestroy(g.graph);
@@ -1921,6 +1957,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
             while (chunk > GEMM_BM && chunk * per_row > budget) chunk = (chunk / 2 + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
         }
         plan->chunk = chunk;
+        plan->ld_part = (int)chunk;
         auto alloc = [&](double** p, int64_t n_doubles) -> int {
             CUDA_TRY(cudaMalloc((void**)p, (size_t)n_doubles * 8));
             plan->owned.push_back(*p);
@@ -1962,6 +1999,34 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
             rc = alloc_small(&plan->g_theta, GRAPH_MAX_N * plan->P);
             if (rc == ELISA_OK) rc = alloc_small(&plan->g_ll, GRAPH_MAX_N * plan->S);
             if (rc == ELISA_OK) rc = alloc_small(&plan->g_grad, GRAPH_MAX_N * plan->S * plan->P);
+            const int64_t rows = std::min<int64_t>(GRAPH_MAX_N, plan->chunk);
+            if (rc == ELISA_OK && plan->S > 1 && plan->S <= 32) {
+                plan->small_ws.resize(plan->S);
+                plan->small_stream.assign(plan->S, nullptr);
+                plan->small_done.assign(plan->S, nullptr);
+                for (int s = 0; s < plan->S && rc == ELISA_OK; ++s) {
+                    const SpectrumPlan& sp = plan->spec[s];
+                    ElisaPlan::SmallWs& w = plan->small_ws[s];
+                    const int64_t pc = (sp.use_i8() ? I8_CG : 1) * sp.C_pad / GEMM_BN, pe = (sp.use_i8() ? I8_CG : 1) * sp.E_pad / GEMM_BN;
+                    rc = alloc_small(&w.U, rows * sp.E_pad);
+                    if (rc == ELISA_OK) rc = alloc_small(&w.dU, rows * sp.E_pad * plan->P);
+                    if (rc == ELISA_OK) rc = alloc_small(&w.W, rows * sp.C_pad);
+                    if (rc == ELISA_OK) rc = alloc_small(&w.part, rows * pc);
+                    if (rc == ELISA_OK) rc = alloc_small(&w.gpart, rows * pe * plan->P);
+                    if (rc == ELISA_OK && sp.use_i8()) {
+                        rc = alloc_small(&w.a_scale, rows);
+                        const int64_t kmax = round_up(std::max(sp.E_pad, sp.C_pad), I8_BK);
+                        double* img = nullptr;
+                        if (rc == ELISA_OK) rc = alloc_small(&img, (rows * kmax * plan->ks + 7) / 8);
+                        w.A_img = reinterpret_cast<int8_t*>(img);
+                    }
+                    if (rc == ELISA_OK && (cudaStreamCreateWithFlags(&plan->small_stream[s], cudaStreamNonBlocking) != cudaSuccess ||
+                                           cudaEventCreateWithFlags(&plan->small_done[s], cudaEventDisableTiming) != cudaSuccess))
+                        rc = fail(ELISA_ERR_CUDA, "creating the per-spectrum streams failed");
+                }
+                if (rc == ELISA_OK && cudaEventCreateWithFlags(&plan->small_fork, cudaEventDisableTiming) != cudaSuccess)
+                    rc = fail(ELISA_ERR_CUDA, "creating the per-spectrum streams failed");
+            }
         }
     }
     if (rc == ELISA_OK && cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking) != cudaSuccess)

@@ -27,7 +27,8 @@
  *  - "_dev" entry points take DEVICE pointers and only enqueue work on the given
  *    stream (no allocation, no host synchronisation); batches of <= 1024 parameter vectors
  *    without per-replica counts are launch-bound, so their kernel sequence is captured into a
- *    CUDA graph on the second call of a shape and replayed afterwards (env
+ *    CUDA graph on the second call of a shape and replayed afterwards, the spectra of a joint
+ *    fit as parallel branches (env
  *    ELISA_B200_GRAPHS=0 disables it; results are bit-identical either way); "_host" entry points take HOST
  *    pointers, stage through the plan's pinned buffers and return when results are
  *    in the caller's memory;
