@@ -536,8 +536,39 @@ __global__ void __launch_bounds__(256) normal_eq_kernel(const NormalEqArgs a) {
 // ======================================================================================
 static thread_local std::string g_last_error = "";
 
+// Post-mortem record of the fold kernel's bounded barrier waits: host-mapped, so it survives the
+// launch failure a protocol error ends in (fold_i8.cuh: mbar_wait).
+static int32_t* g_trap_host = nullptr;
+static int32_t* g_trap_dev = nullptr;
+static int32_t* trap_info_dev() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (cudaHostAlloc((void**)&g_trap_host, 512, cudaHostAllocMapped) == cudaSuccess) {
+            memset(g_trap_host, 0, 512);
+            if (cudaHostGetDevicePointer((void**)&g_trap_dev, g_trap_host, 0) != cudaSuccess) g_trap_dev = nullptr;
+        }
+    });
+    return g_trap_dev;
+}
+static std::string trap_report() {
+    if (g_trap_host == nullptr || g_trap_host[0] == 0) return "";
+    char buf[160];
+    snprintf(buf, sizeof buf, " [fold kernel gave up waiting: block %d warp %d barrier code %d parity %d tile %d;",
+             g_trap_host[1], g_trap_host[2], g_trap_host[3], g_trap_host[4], g_trap_host[5]);
+    std::string out = buf;
+    snprintf(buf, sizeof buf, " stalled warps of block %d (warp:code/parity/tile):", g_trap_host[6] - 1);
+    out += buf;
+    for (int w = 0; w < 24; ++w) {
+        const int32_t* st = g_trap_host + 8 + 3 * w;
+        if (st[0] == 0) continue;
+        snprintf(buf, sizeof buf, " %d:%d/%d/%d", w, st[0], st[1], st[2]);
+        out += buf;
+    }
+    return out + "]";
+}
+
 static int fail(int code, const std::string& msg) {
-    g_last_error = msg;
+    g_last_error = code == ELISA_ERR_CUDA ? msg + trap_report() : msg;
     return code;
 }
 
@@ -1381,6 +1412,7 @@ static FoldI8Args fold_i8_args(const ElisaPlan* plan, const I8Operand& B, int kb
     fa.m_tiles = m_tiles;
     fa.n_tiles = B.n_tiles;
     fa.n_groups = 1;  // set at launch
+    fa.trap_info = trap_info_dev();
     static const int dbg = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;  // timing experiments
     fa.debug = dbg;
     return fa;
@@ -2339,6 +2371,7 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
     fa.A_img = a_img; fa.a_scale = a_sc; fa.kb_a = kb; fa.B_img = b_img; fa.b_scale = b_sc; fa.b_tile_img = timg;
     fa.kb_lo = rng; fa.kb_hi = rng + n_tiles; fa.m_tiles = m_tiles; fa.n_tiles = n_tiles;
     fa.n_groups = 1;  // set at launch
+    fa.trap_info = trap_info_dev();
     fa.debug = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;
     I8EpilogueStore es{D, ldd, m, n, a_sc};
     int sms = 148;

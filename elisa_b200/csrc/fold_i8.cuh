@@ -82,10 +82,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // (or the hint expires) instead of spinning -- in the first version more than half of all
 // instructions the kernel executed were these polls, stealing issue slots and power from the
 // epilogue warps sharing the scheduler.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// `what` names the barrier for the post-mortem record (host-mapped memory, FoldI8Args::trap_info):
+// 1 a_full 2 a_empty 3 b_full 4 b_empty 5 t_full 6 t_empty 7 t_init, + 16 * ring slot
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* trap_info = nullptr, int what = 0,
+                                          int tile = 0) {
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 12); ++spin) {  // ~4 s of 1 ms sleeps
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -94,6 +97,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity), "r"(1000000u)
             : "memory");
         if (done) return;
+        if (spin == 1024 && trap_info != nullptr && (threadIdx.x & 31) == 0) {
+            // a wait this long is a stall: every stuck warp of one block leaves what it waits for
+            const int me = (int)blockIdx.x + 1;
+            const int owner = atomicCAS(trap_info + 6, 0, me);
+            if (owner == 0 || owner == me) {
+                int32_t* st = trap_info + 8 + 3 * (threadIdx.x >> 5);
+                st[0] = what;
+                st[1] = (int32_t)parity;
+                st[2] = tile;
+                __threadfence_system();
+            }
+        }
+    }
+    if (trap_info != nullptr && (threadIdx.x & 31) == 0 && atomicCAS(trap_info, 0, 1) == 0) {
+        trap_info[1] = (int32_t)blockIdx.x;
+        trap_info[2] = (int32_t)(threadIdx.x >> 5);
+        trap_info[3] = what;
+        trap_info[4] = (int32_t)parity;
+        trap_info[5] = tile;
+        __threadfence_system();
     }
     __trap();
 }
@@ -205,6 +228,7 @@ struct FoldI8Args {
     const int32_t* kb_hi;
     int32_t m_tiles, n_tiles;
     int32_t n_groups;  // ceil(n_tiles / I8_GROUP)
+    int32_t* trap_info;  // host-mapped int32[128] or nullptr: which waits stalled (see mbar_wait)
     int32_t debug;  // experiments only (elisa_b200_sliced_gemm_dev): 1 = no A copies, 2 = no B copies, 4 = no MMAs, 8 = no epilogue, 16 = no TMEM drain
 };
 
@@ -303,6 +327,9 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
     auto a_empty = [&](int s) { return s_bar + 8u * (NA + s); };
     auto b_full = [&](int s) { return s_bar + 8u * (2 * NA + s); };
     auto b_empty = [&](int s) { return s_bar + 8u * (2 * NA + I8_NB + s); };
+    // ring r (of NI) owns slots [ring_base(r), ring_base(r) + ring_size(r)) of the NA
+    auto ring_size = [](int r) { return NA / NI + (r < NA % NI ? 1 : 0); };
+    auto ring_base = [](int r) { return r * (NA / NI) + (r < NA % NI ? r : NA % NI); };
     const uint32_t t_full = s_bar + 8u * (2 * NA + 2 * I8_NB);
     const uint32_t t_empty = t_full + 8u;
     const uint32_t t_init = t_empty + 8u;  // accumulators of the tile initialised (issuer 0 -> the others)
@@ -334,8 +361,14 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
 
     if (warp == I8_EPI_WARPS) {
         // ================= producer =================
-        int as = 0, bs = 0;
-        uint32_t aph = 0, bph = 0;
+        // One ring of A slots PER ISSUER (slices i = r mod NI go to ring r): a single shared ring
+        // would let an issuer test a slot's full barrier a whole phase early -- bulk copies
+        // complete out of order, so the other issuer's slice of the previous round can still be in
+        // flight when the phase parity is read -- and multiply stale data.
+        int as[NI], bs = 0;
+        uint32_t aph[NI], bph = 0;
+#pragma unroll
+        for (int r = 0; r < NI; ++r) { as[r] = 0; aph[r] = 0; }
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const I8Item it = i8_item(a, item);
             I8_FOR_EACH_TILE(it, a, nt) {
@@ -343,7 +376,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 const int8_t* bsrc = a.B_img + (size_t)a.b_tile_img[nt] * B_BLOCK;
                 const int8_t* asrc = a.A_img + ((size_t)it.mt * a.kb_a + lo) * KS * I8_A_SLICE;
                 for (int kb = lo; kb < hi; ++kb) {
-                    mbar_wait(b_empty(bs), bph ^ 1u);
+                    mbar_wait(b_empty(bs), bph ^ 1u, a.trap_info, 4 + 16 * bs, nt);
                     if (lane == 0) {
                         if (a.debug & 2) {
                             mbar_arrive(b_full(bs));
@@ -354,18 +387,21 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                     }
                     bsrc += B_BLOCK;
                     if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
+#pragma unroll
                     for (int i = 0; i < KS; ++i) {
-                        mbar_wait(a_empty(as), aph ^ 1u);
+                        const int r = i % NI;
+                        const int slot = ring_base(r) + as[r];
+                        mbar_wait(a_empty(slot), aph[r] ^ 1u, a.trap_info, 2 + 16 * slot, nt);
                         if (lane == 0) {
                             if (a.debug & 1) {
-                                mbar_arrive(a_full(as));
+                                mbar_arrive(a_full(slot));
                             } else {
-                                mbar_expect_tx(a_full(as), I8_A_SLICE);
-                                bulk_g2s(s_A + as * I8_A_SLICE, asrc, I8_A_SLICE, a_full(as));
+                                mbar_expect_tx(a_full(slot), I8_A_SLICE);
+                                bulk_g2s(s_A + slot * I8_A_SLICE, asrc, I8_A_SLICE, a_full(slot));
                             }
                         }
                         asrc += I8_A_SLICE;
-                        if (++as == NA) { as = 0; aph ^= 1u; }
+                        if (++as[r] == ring_size(r)) { as[r] = 0; aph[r] ^= 1u; }
                     }
                     __syncwarp();
                 }
@@ -381,35 +417,36 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
         // accumulate into shared TMEM columns from both threads; integer accumulation is
         // order-independent, and the one ordering that matters -- the overwriting (accumulate = 0)
         // MMAs of slice 0 in the tile's first k-block -- is published through t_init.
-        // NI is a property of the epilogue: the plain-store fold runs two issuers (bit-exact and
-        // row-partition invariant over 30 repeated runs, tools/i8_determinism.py); the gradient
-        // fold stays on one -- with two, its results were no longer bit-identical under
-        // re-chunking and one long run faulted, cause not found, so it is not used there.
+        // Each issuer consumes its own ring of A slots (see the producer).  Bit-exact against the
+        // single-issuer kernel and row-partition invariant (tools/i8_issuer_crosscheck.py,
+        // tools/i8_determinism.py).
         const int w = warp - (I8_EPI_WARPS + 1);
-        int as = 0, bs = 0;
+        const int base = ring_base(w), size = ring_size(w);
+        int as = 0, bs = 0;  // as: position in this issuer's own ring
         uint32_t aph = 0, bph = 0, tph = 0, iph = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const I8Item it = i8_item(a, item);
             I8_FOR_EACH_TILE(it, a, nt) {
                 const int lo = a.kb_lo[nt], hi = a.kb_hi[nt];
-                mbar_wait(t_empty, tph ^ 1u);  // epilogue has drained the accumulators
+                mbar_wait(t_empty, tph ^ 1u, a.trap_info, 6, nt);  // epilogue has drained the accumulators
                 tph ^= 1u;
                 tc_fence_after();
                 if (w != 0 && lo < hi) {
-                    mbar_wait(t_init, iph);
+                    mbar_wait(t_init, iph, a.trap_info, 7, nt);
                     tc_fence_after();
                 }
                 if (lo < hi) iph ^= 1u;
                 for (int kb = lo; kb < hi; ++kb) {
-                    mbar_wait(b_full(bs), bph);
+                    mbar_wait(b_full(bs), bph, a.trap_info, 3 + 16 * bs, nt);
                     const uint32_t sb = s_B + bs * B_BLOCK;
 #pragma unroll
                     for (int i = 0; i < KS; ++i) {
                         if (i % NI == w) {
-                            mbar_wait(a_full(as), aph);
+                            const int slot = base + as;
+                            mbar_wait(a_full(slot), aph, a.trap_info, 1 + 16 * slot, nt);
                             tc_fence_after();
                             if (lane == 0) {
-                                const uint32_t sa = s_A + as * I8_A_SLICE;
+                                const uint32_t sa = s_A + slot * I8_A_SLICE;
 #pragma unroll
                                 for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
                                     const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
@@ -424,12 +461,12 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                                         tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
                                     }
                                 }
-                                tc_commit(a_empty(as));
+                                tc_commit(a_empty(slot));
                                 if (i == 0 && kb == lo) tc_commit(t_init);
                             }
                             __syncwarp();
+                            if (++as == size) { as = 0; aph ^= 1u; }
                         }
-                        if (++as == NA) { as = 0; aph ^= 1u; }
                     }
                     if (lane == 0) tc_commit(b_empty(bs));
                     __syncwarp();
@@ -456,7 +493,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 if (nt % I8_GROUP == 0) epi.begin(st);
                 epi.prefetch(row_acc, c0);
                 const bool empty = a.kb_lo[nt] >= a.kb_hi[nt];  // no k-blocks: accumulators are stale
-                mbar_wait(t_full, tph);
+                mbar_wait(t_full, tph, a.trap_info, 5, nt);
                 tph ^= 1u;
                 tc_fence_after();
                 // drain: recombine this thread's elements into registers, hand TMEM back to the
@@ -544,7 +581,7 @@ struct ChanArrays {
 // (two xor shuffles), and thread q keeps the sum of row row0 + 8 q.
 // gpart[(j * n_part + I8_CG * group + cg) * ld_part + row],  n_part = I8_CG * n_groups
 struct I8EpilogueGrad {
-    static constexpr int ISSUERS = 1;
+    static constexpr int ISSUERS = 2;
     const double* dU;  // [P, rows, ldu]
     int64_t plane;
     int32_t ldu;
