@@ -1577,6 +1577,7 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
     a.colsum = sp.i8_fwd.abs_sum;
     a.guard = plan->guard;
     a.guard_eta = ldexp(1.0, -8 * plan->ks);
+    a.guard_grad = 1.0;
     // trip level: 3x below the 1e-10 tolerance; the estimate adds the per-channel terms linearly
     // (errors of random sign add in quadrature), so it is already pessimistic
     static const double tol = getenv("ELISA_B200_GUARD_TOL") ? atof(getenv("ELISA_B200_GUARD_TOL")) : 3e-11;
@@ -2012,9 +2013,9 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                 rc = alloc(&plan->a_scale, chunk);
                 if (rc == ELISA_OK) {
                     double* g = nullptr;
-                    rc = alloc(&g, 2);
+                    rc = alloc(&g, 4);
                     plan->guard = reinterpret_cast<unsigned long long*>(g);
-                    if (rc == ELISA_OK && cudaMemset(g, 0, 16) != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "cudaMemset failed");
+                    if (rc == ELISA_OK && cudaMemset(g, 0, 32) != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "cudaMemset failed");
                 }
             }
         }
@@ -2296,20 +2297,21 @@ int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double*
 
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[4] = {0, 0, 0, 0};
     if (plan->guard != nullptr) {
         int prev = 0;
         CUDA_TRY(cudaGetDevice(&prev));
         CUDA_TRY(cudaSetDevice(plan->device));
-        CUDA_TRY(cudaMemcpy(h, plan->guard, 16, cudaMemcpyDeviceToHost));
-        if (reset) CUDA_TRY(cudaMemset(plan->guard, 0, 16));
+        CUDA_TRY(cudaMemcpy(h, plan->guard, 32, cudaMemcpyDeviceToHost));
+        if (reset) CUDA_TRY(cudaMemset(plan->guard, 0, 32));
         cudaSetDevice(prev);
     }
     if (flagged) *flagged = (int64_t)h[0];
-    if (worst) {
-        double w;
+    if (worst) {  // the larger of the value-side and the gradient-side estimate
+        double w, wg;
         memcpy(&w, &h[1], 8);
-        *worst = w;
+        memcpy(&wg, &h[2], 8);
+        *worst = std::max(w, wg);
     }
     return ELISA_OK;
 }

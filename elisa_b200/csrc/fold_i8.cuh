@@ -684,10 +684,12 @@ struct StatSliceArgs {
     int32_t kb_total;
     // accuracy guard of the integer fold: colsum[c] = sum_e |R[e, c]|; guard[0] counts the rows
     // whose estimated log-likelihood error exceeds guard_tol * max(|loglike|, 1), guard[1] keeps
-    // the largest estimate / max(|loglike|, 1) seen (bits of a non-negative double)
+    // the largest estimate / max(|loglike|, 1) seen (bits of a non-negative double), guard[2] the
+    // largest gradient-side estimate
     const double* colsum;
     unsigned long long* guard;
     double guard_eta;  // typical normwise error of the engine, 2^(-8 KS)
+    double guard_grad; // calibration of the gradient-side estimate (see the kernel)
     double guard_tol;
 };
 
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     if (row >= a.rows_pad) return;
     const bool live = row < a.n_valid;
     double* x = a.X + (size_t)row * a.ldx;
-    double rs = 0.0, amax = 0.0, eb = 0.0;
+    double rs = 0.0, amax = 0.0, eb = 0.0, wsum = 0.0;
     bool bad = false;
     if (live) {
         const double u_max = a.scale[row] * (double)I8_TOP_DIGIT;  // largest |U| of the row
@@ -733,6 +735,7 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
                 x[col] = w;
                 bad |= !(fabs(w) <= 1.79e308);
                 amax = fmax(amax, fabs(w));
+                wsum += fabs(w);
             }
         }
 #pragma unroll
@@ -751,8 +754,20 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     }
     if (!GRAD) return;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
     bad = __any_sync(0xffffffffu, bad);
+    if (live && lane == 0 && wsum > 0.0 && !bad) {
+        // gradient side of the guard.  The transposed fold's error is relative to the LARGEST
+        // |W| of the row; when a few starved channels (n >> mu) tower over the rest, the bulk of
+        // the row -- and with it G and the gradient -- keeps fewer digits.  peak / mean of |W|
+        // times the engine's normwise error estimates the relative error of G.
+        const double est_g = a.guard_eta * a.guard_grad * amax * (double)a.C / wsum;
+        if (est_g > a.guard_tol) atomicAdd(a.guard, 1ull);
+        atomicMax(a.guard + 2, (unsigned long long)__double_as_longlong(est_g));
+    }
     double f1, f2;
     const double sc = slice_scale<KS>(amax, bad, f1, f2);
     if (lane == 0) a.scale[row] = sc;

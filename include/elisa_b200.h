@@ -285,7 +285,10 @@ int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
  * channel predicted ~2^40 below the brightest part of the model loses relative accuracy.
  * While evaluating, the statistic kernel estimates to first order the log-likelihood error
  * this may have caused, sum_c |dl/dx_c| * 2^(-8 slices) * max_e|u| * sum_e|R[e,c]|, and counts
- * the rows where it exceeds 3e-11 * max(|loglike|, 1) (env ELISA_B200_GUARD_TOL).  This call returns that count and the
+ * the rows where it exceeds 3e-11 * max(|loglike|, 1) (env ELISA_B200_GUARD_TOL); on the
+ * gradient side it flags rows in which a few channels tower over the rest of W = dl/d(Ru)
+ * (2^(-8 slices) * C * max|W| / sum|W| above the same level: the transposed fold keeps digits
+ * relative to the largest |W| of the row).  This call returns that count and the
  * largest relative estimate since the last reset (synchronise the stream of the evaluation
  * first).  Rows are never flagged on the BASELINE configurations (estimates 7e-14 .. 1.4e-11); a
  * caller that sees flagged > 0 re-evaluates with an ELISA_FLAG_FOLD_DMMA plan -- the Python
