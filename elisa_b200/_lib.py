@@ -102,6 +102,8 @@ SYMBOLS = {
     'elisa_b200_specialise_check': (C.c_int64, [C.POINTER(ModelDesc), C.c_int32, C.c_char_p, C.c_int64]),
     'elisa_b200_plan_is_specialised': (C.c_int, [_VP, C.c_int32]),
     'elisa_b200_plan_fold_slices': (C.c_int, [_VP, C.c_int32]),
+    'elisa_b200_plan_set_fold': (C.c_int, [_VP, C.c_int]),
+    'elisa_b200_plan_guard_fallbacks': (C.c_int64, [_VP]),
     'elisa_b200_plan_fold_guard': (C.c_int, [_VP, C.POINTER(C.c_int64), c_double_p, C.c_int]),
     'elisa_b200_sliced_gemm_dev': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             _VP, C.c_int64, c_double_p, _VP]),

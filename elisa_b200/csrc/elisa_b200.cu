@@ -669,6 +669,9 @@ struct ElisaPlan {
     std::vector<GraphEntry> graphs;
     double *g_theta = nullptr, *g_ll = nullptr, *g_grad = nullptr;  // staging, GRAPH_MAX_N rows
     bool graphs_enabled = true;
+    bool guard_off = false;   // ELISA_FLAG_FOLD_I8: the caller asked for the integer fold, unguarded
+    int64_t guard_fallbacks = 0;
+    bool force_dmma = false;  // evaluate with the FP64 DMMA fold although the integer operands exist (guard fallback)
     int ld_part = 0;  // leading dimension (rows) of the part / gpart arrays in use
     // Joint fits: inside the captured graph every spectrum runs on its own branch (own stream
     // during capture, own small workspace), so the S kernel chains of a small batch overlap
@@ -1258,7 +1261,7 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.scale = nullptr;
     a.gv.has_point = 0;
     if (fused_digits != nullptr) {
-        *fused_digits = sp.jit != nullptr && sp.use_i8() && n_seg == 1 && plan->A_img != nullptr;
+        *fused_digits = sp.jit != nullptr && (sp.use_i8() && !plan->force_dmma) && n_seg == 1 && plan->A_img != nullptr;
         if (*fused_digits) {
             a.img = plan->A_img;
             a.scale = plan->a_scale;
@@ -1628,9 +1631,9 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     int rc;
     bool fused_digits = false;
     if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st,
-                            sp.use_i8() ? &fused_digits : nullptr)))
+                            (sp.use_i8() && !plan->force_dmma) ? &fused_digits : nullptr)))
         return rc;
-    const bool i8 = sp.use_i8();
+    const bool i8 = (sp.use_i8() && !plan->force_dmma);
     if (i8) {
         if ((rc = run_chunk_i8(plan, sp, s, n, m_tiles, want_grad, fused_digits, on, off, loglike, st))) return rc;
         if (!want_grad) return ELISA_OK;  // the statistic kernel wrote loglike itself
@@ -1696,13 +1699,13 @@ static int run_normal_eq_chunk(ElisaPlan* plan, int s, const double* theta, cons
     int rc;
     bool fused_digits = false;
     if ((rc = launch_unfold(plan, sp, theta, n, n_rows, true, plan->U, plan->dU, sp.E_pad, sp.E_pad, true, st,
-                            sp.use_i8() ? &fused_digits : nullptr)))
+                            (sp.use_i8() && !plan->force_dmma) ? &fused_digits : nullptr)))
         return rc;
     for (int j = -1; j < plan->P; ++j) {  // j = -1: the model itself
         if (j >= 0 && !((sp.model.used_mask >> j) & 1u)) continue;
         const double* A = j < 0 ? plan->U : plan->dU + (int64_t)j * n_rows * sp.E_pad;
         double* X = plan->Xp + (int64_t)(1 + j) * xplane;
-        if (sp.use_i8()) {
+        if ((sp.use_i8() && !plan->force_dmma)) {
             if (!(j < 0 && fused_digits) &&
                 (rc = slice_chunk_operand(plan, A, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st)))
                 return rc;
@@ -1779,7 +1782,7 @@ static cudaGraphNode_t last_captured_node(cudaStream_t st) {
 // value (+ gradient) of a small batch through a replayed CUDA graph; falls back to run_all.
 static int run_small(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                      double* loglike, double* grad, cudaStream_t st) {
-    const bool eligible = plan != nullptr && plan->graphs_enabled && !plan->profiling && n > 0 && n <= GRAPH_MAX_N &&
+    const bool eligible = plan != nullptr && plan->graphs_enabled && !plan->profiling && !plan->force_dmma && n > 0 && n <= GRAPH_MAX_N &&
                           n <= plan->chunk && on == nullptr && off == nullptr && theta != nullptr && loglike != nullptr &&
                           plan->g_theta != nullptr;
     if (!eligible) return run_all(plan, theta, on, off, n, loglike, grad, st);
@@ -1946,6 +1949,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
             return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
         }
         plan->ks = dmma ? 0 : ks;
+        plan->guard_off = force_i8;
         cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
         if (plan->sm_count < 1) plan->sm_count = 148;
     }
@@ -2206,6 +2210,21 @@ int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const dou
         CUDA_TRY(cudaMemcpyAsync(plan->h_off, counts_off, (size_t)n * plan->sum_C * 8, cudaMemcpyHostToDevice, st));
     int rc = run_all(plan, plan->h_theta, counts_on ? plan->h_on : nullptr, counts_off ? plan->h_off : nullptr, n,
                      plan->h_ll, grad ? plan->h_grad : nullptr, st);
+    if (rc == ELISA_OK && plan->guard != nullptr && !plan->force_dmma && !plan->guard_off) {
+        // this entry point synchronises anyway: consult the accuracy guard of the integer fold and
+        // re-evaluate a flagged call with the FP64 DMMA fold of the same plan
+        unsigned long long h[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaMemcpyAsync(h, plan->guard, 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h[0] != 0) {
+            CUDA_TRY(cudaMemsetAsync(plan->guard, 0, 32, st));
+            plan->force_dmma = true;
+            ++plan->guard_fallbacks;
+            rc = run_all(plan, plan->h_theta, counts_on ? plan->h_on : nullptr, counts_off ? plan->h_off : nullptr, n,
+                         plan->h_ll, grad ? plan->h_grad : nullptr, st);
+            plan->force_dmma = false;
+        }
+    }
     if (rc == ELISA_OK) {
         CUDA_TRY(cudaMemcpyAsync(loglike, plan->h_ll, (size_t)n * plan->S * 8, cudaMemcpyDeviceToHost, st));
         if (grad)
@@ -2294,6 +2313,14 @@ int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double*
     cudaSetDevice(prev);
     return rc;
 }
+
+int elisa_b200_plan_set_fold(ElisaPlan* plan, int dmma) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    plan->force_dmma = dmma != 0;
+    return ELISA_OK;
+}
+
+int64_t elisa_b200_plan_guard_fallbacks(const ElisaPlan* plan) { return plan ? plan->guard_fallbacks : 0; }
 
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");

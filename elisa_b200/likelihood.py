@@ -141,15 +141,12 @@ class Likelihood:
         # row (estimated log-likelihood error of the sliced fold above 3e-11, see
         # elisa_b200_plan_fold_guard) is re-evaluated by an FP64 DMMA twin of this plan
         self._auto_guard = fold is None and any(self.fold_slices)
-        self._twin = None
-        self._twin_args = dict(device=self.device, chunk=int(chunk), specialise=specialise)
+        self._in_fallback = False
         self.guard_fallbacks = 0
+        self._py_fallbacks = 0
 
     # -- lifetime ------------------------------------------------------------------
     def close(self):
-        if getattr(self, '_twin', None) is not None:
-            self._twin.close()
-            self._twin = None
         if getattr(self, '_h', None) is not None and self._h.value:
             self._lib.elisa_b200_plan_destroy(self._h)
             self._h = None
@@ -163,21 +160,23 @@ class Likelihood:
         return int(n.value), float(w.value)
 
     def _guard_tripped(self) -> bool:
-        if not self._auto_guard:
+        """After a device call of the guarded default engine: did the accuracy guard flag a row?
+        If so the plan is switched to its FP64 DMMA fold (``elisa_b200_plan_set_fold``) for the
+        caller to repeat the evaluation, and switched back by ``_guard_done``."""
+        if not self._auto_guard or self._in_fallback:
             return False
         flagged, _ = self.fold_guard(reset=True)
         if flagged == 0:
             return False
-        self.guard_fallbacks += 1
-        if self._twin is None:
-            self._twin = type(self)(self.data, self.model, self.stat, fold='dmma', **self._twin_args)
+        self._py_fallbacks += 1
+        self.guard_fallbacks = int(self._lib.elisa_b200_plan_guard_fallbacks(self._h)) + self._py_fallbacks
+        self._in_fallback = True
+        _lib.check(self._lib.elisa_b200_plan_set_fold(self._h, 1))
         return True
 
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+    def _guard_done(self):
+        _lib.check(self._lib.elisa_b200_plan_set_fold(self._h, 0))
+        self._in_fallback = False
 
     @property
     def specialised(self) -> list[bool]:
@@ -248,7 +247,10 @@ class Likelihood:
             out = torch.empty((n, len(self.data)), dtype=torch.float64, device=t.device)
             _lib.check(self._lib.elisa_b200_loglike_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), self._stream()))
         if self._guard_tripped():
-            return self._twin.loglike(t, on, off)
+            try:
+                return self.loglike(theta, counts_on, counts_off)
+            finally:
+                self._guard_done()
         return out
 
     def loglike_and_grad(self, theta, counts_on=None, counts_off=None):
@@ -263,7 +265,10 @@ class Likelihood:
             grad = torch.empty((n, len(self.data), self._P), dtype=torch.float64, device=t.device)
             _lib.check(self._lib.elisa_b200_loglike_grad_dev(self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), _dev_ptr(grad), self._stream()))
         if self._guard_tripped():
-            return self._twin.loglike_and_grad(t, on, off)
+            try:
+                return self.loglike_and_grad(theta, counts_on, counts_off)
+            finally:
+                self._guard_done()
         return out, grad[:, :, : self.nparam]
 
     def normal_equations(self, theta, counts_on=None, counts_off=None):
@@ -476,9 +481,7 @@ class Likelihood:
         ll = np.empty((n, len(self.data)))
         g = np.empty((n, len(self.data), self._P)) if grad else None
         _lib.check(self._lib.elisa_b200_loglike_grad_host(self._h, _ptr(theta), _ptr(on), _ptr(off), n, _ptr(ll), _ptr(g)))
-        if self._guard_tripped():
-            return self._twin.loglike_and_grad_host(theta[:, : max(self.nparam, 1)] if self.nparam else theta[:, :0],
-                                                    counts_on, counts_off, grad)
+        self.guard_fallbacks = int(self._lib.elisa_b200_plan_guard_fallbacks(self._h)) + self._py_fallbacks
         return (ll, g[:, :, : self.nparam]) if grad else ll
 
 

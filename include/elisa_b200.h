@@ -291,9 +291,15 @@ int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
  * relative to the largest |W| of the row).  This call returns that count and the
  * largest relative estimate since the last reset (synchronise the stream of the evaluation
  * first).  Rows are never flagged on the BASELINE configurations (estimates 7e-14 .. 1.4e-11); a
- * caller that sees flagged > 0 re-evaluates with an ELISA_FLAG_FOLD_DMMA plan -- the Python
- * host side (elisa_b200.Likelihood, fold=None) does so automatically.                      */
+ * caller that sees flagged > 0 re-evaluates after elisa_b200_plan_set_fold(plan, 1) -- the
+ * Python host side (elisa_b200.Likelihood, fold=None) and loglike_grad_host do so themselves. */
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset);
+/* dmma != 0: evaluate with the FP64 DMMA fold of the same plan (both sets of operands live in a
+ * plan) until switched back -- what a caller does with a flagged "_dev" call.  The "_host" entry
+ * point, which synchronises anyway, consults the guard and does this itself (unless the plan was
+ * created with ELISA_FLAG_FOLD_I8); plan_guard_fallbacks counts how often it did.          */
+int elisa_b200_plan_set_fold(ElisaPlan* plan, int dmma);
+int64_t elisa_b200_plan_guard_fallbacks(const ElisaPlan* plan);
 /* The fold engine on its own: D[m, n] = A[m, k] . B[n, k]^T in FP64-class accuracy on the
  * int8 tensor cores (device pointers, row-major, k <= 16384, slices 4..7).  Allocates its
  * digit images, runs on `cuda_stream`, synchronises; `ms` (nullable) receives the device

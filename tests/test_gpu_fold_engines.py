@@ -163,13 +163,16 @@ def test_accuracy_guard_quiet_on_baseline_shapes_and_trips_on_starved_channels(l
     flagged, worst = lk.fold_guard()
     assert flagged == len(theta) and worst > 1e-6, (flagged, worst)
     lk.close()
-    lk = Likelihood([d], model, ['cstat'])                    # guarded: falls back to DMMA
+    lk = Likelihood([d], model, ['cstat'])                    # guarded: falls back to the plan's DMMA fold
     ll, g = lk.loglike_and_grad(theta)
     assert lk.guard_fallbacks == 1
     assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL
     assert rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
-    ll_h, g_h = lk.loglike_and_grad_host(theta)
-    assert lk.guard_fallbacks == 2 and rel_err_value(ll_h, ll_ref) <= RTOL
+    ll_h, g_h = lk.loglike_and_grad_host(theta)               # the C host entry point does it itself
+    assert lk.guard_fallbacks == 2 and rel_err_value(ll_h, ll_ref) <= RTOL and rel_err_grad(g_h, g_ref) <= RTOL
+    assert all(s > 0 for s in lk.fold_slices)                 # ... and the plan is back on the integer fold
+    ll2, _ = lk.loglike_and_grad(theta[:3])
+    assert lk.guard_fallbacks == 3 and rel_err_value(ll2.cpu().numpy(), ll_ref[:3]) <= RTOL
     lk.close()
 
 
