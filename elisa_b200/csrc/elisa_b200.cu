@@ -1079,6 +1079,10 @@ static std::string hexd(double v) {
 // ks > 0: the kernels also write the digits of U for the sliced-integer fold (fold_i8.cuh).
 static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
     std::string s;
+    {
+        const char* env = getenv("ELISA_B200_UNFOLD_MIN_BLOCKS");  // occupancy experiments
+        s += "#define UNFOLD_MIN_BLOCKS " + std::to_string(env ? std::max(1, atoi(env)) : 1) + "\n";
+    }
     s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\nstruct Model {\n";
     s += "  template <typename T> struct Pre {\n";
     for (int i = 0; i < m.n_leaf; ++i) {
@@ -1126,9 +1130,9 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
     }
     s += "    return " + stack.back() + ";\n  }\n};\n";
     const std::string k = std::to_string(ks);
-    s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_val(const UnfoldCore a) { unfold_generic<Model, double, " +
+    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_val(const UnfoldCore a) { unfold_generic<Model, double, " +
          k + ">(a); }\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(128) unfold_grad(const UnfoldCore a) { unfold_generic<Model, Dual<" +
+    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_grad(const UnfoldCore a) { unfold_generic<Model, Dual<" +
          std::to_string(P) + ">, " + k + ">(a); }\n";
     return s;
 }

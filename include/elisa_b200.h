@@ -197,7 +197,8 @@ typedef struct ElisaPlanDesc {
  * several times the FP64 DMMA rate.  ELISA_FLAG_FOLD_DMMA / env ELISA_B200_FOLD=dmma
  * selects the native FP64 DMMA fold (csrc/gemm_f64.cuh); ELISA_FLAG_FOLD_I8 / env
  * ELISA_B200_FOLD=i8 makes a spectrum the integer fold cannot take (E or C > 16384) an
- * error instead of a silent DMMA fold.  Slices: bits 8-11 of flags (4..7; 0 = default 6;
+ * error instead of a silent DMMA fold, and switches off the guard fallback of the "_host"
+ * entry point (see elisa_b200_plan_fold_guard).  Slices: bits 8-11 of flags (4..7; 0 = default 6;
  * 4 is an FP32-class variant, ~1e-6) or env ELISA_B200_FOLD_SLICES.                       */
 #define ELISA_FLAG_FOLD_DMMA 4
 #define ELISA_FLAG_FOLD_I8 8
