@@ -8,12 +8,15 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_COMP_PARAMS = 5
 MAX_COMPONENTS = 8
 MAX_PARAMS = 16
 OP_ADD = -1
 OP_MUL = -2
+OP_NORM0 = -16
+MAX_NORMS = 2
+NORM = {'PhFlux': 0, 'EnFlux': 1}
 FLAG_NO_JIT = 1
 FLAG_REQUIRE_JIT = 2
 FLAG_FOLD_DMMA = 4
@@ -37,6 +40,20 @@ class ComponentDesc(C.Structure):
         ('table_energy', c_double_p),
         ('table_xsect', c_double_p),
         ('table_len', C.c_int32),
+        ('grid_scale', C.c_double),
+        ('out_scale', C.c_double),
+        ('norm_grid_scale', C.c_double),
+        ('norm_out_scale', C.c_double),
+    ]
+
+
+class NormDesc(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int32),
+        ('f_src', C.c_int32),
+        ('f_const', C.c_double),
+        ('grid', c_double_p),
+        ('n_grid', C.c_int32),
     ]
 
 
@@ -46,6 +63,8 @@ class ModelDesc(C.Structure):
         ('components', C.POINTER(ComponentDesc)),
         ('n_ops', C.c_int32),
         ('ops', c_int32_p),
+        ('n_norms', C.c_int32),
+        ('norms', C.POINTER(NormDesc)),
     ]
 
 
@@ -108,6 +127,7 @@ SYMBOLS = {
     'elisa_b200_sliced_gemm_dev': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             _VP, C.c_int64, c_double_p, _VP]),
     'elisa_b200_abi_version': (C.c_int, []),
+    'elisa_b200_sizeof': (C.c_int64, [C.c_int32]),
     'elisa_b200_last_error': (C.c_char_p, []),
 }
 

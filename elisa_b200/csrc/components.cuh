@@ -559,16 +559,21 @@ __device__ __forceinline__ void leaf_pre(double* scratch, const double* aux) {
 
 // Bin value of leaf KIND for bin e (valid on lanes 0..30 of the pass, for e < E), given the
 // parameters p and the hoisted constants c.
+// gs / lgs: the leaf sees the grid scaled by gs (lgs = ln gs) -- energy shifts with a fixed
+// factor (models/conv.py:294-432); the tables of table components are built on the scaled grid.
 template <int KIND, typename T>
-__device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, const GridView& gv, int e, int leaf = 0) {
+__device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, const GridView& gv, int e, int leaf = 0,
+                                         double gs = 1.0, double lgs = 0.0) {
     using C = Comp<KIND>;
     const int ec = e <= gv.E ? e : gv.E;  // lanes beyond the grid re-evaluate the last edge
-    const double E0 = gv.has_point ? gv.pE : gv.egrid[ec];
+    const double E0 = gs * (gv.has_point ? gv.pE : gv.egrid[ec]);
     double l0;
-    if constexpr (IsTable<C>::value)
+    if constexpr (IsTable<C>::value) {
         l0 = gv.tab[2 * leaf][ec];
-    else
+    } else {
         l0 = gv.has_point ? gv.pl : gv.lngrid[ec];
+        if (lgs != 0.0) l0 += lgs;
+    }
     T g0[C::NG], g1[C::NG];
     C::edge(p, c, E0, l0, g0);
 #pragma unroll
@@ -582,11 +587,13 @@ __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, con
             const int em = e < gv.E ? e : gv.E - 1;
             T gm[C::NG];
             double lm;
-            if constexpr (IsTable<C>::value)
+            if constexpr (IsTable<C>::value) {
                 lm = gv.tab[2 * leaf + 1][em];
-            else
+            } else {
                 lm = gv.has_point ? gv.plm : gv.lnmid[em];
-            C::edge(p, c, gv.has_point ? gv.pEm : gv.emid[em], lm, gm);
+                if (lgs != 0.0) lm += lgs;
+            }
+            C::edge(p, c, gs * (gv.has_point ? gv.pEm : gv.emid[em]), lm, gm);
             const double factor = add ? (E1 - E0) / 6.0 : 1.0 / 6.0;
             return factor * (g0[0] + 4.0 * gm[0] + g1[0]);
         }
@@ -597,14 +604,15 @@ __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, con
 
 // Same, with p and c decoded from the interpreter's shared-memory scratch slot.
 template <int KIND, typename T>
-__device__ __forceinline__ T leaf_bin(const double* scratch, int method, const GridView& gv, int e, int leaf = 0) {
+__device__ __forceinline__ T leaf_bin(const double* scratch, int method, const GridView& gv, int e, int leaf = 0,
+                                      double gs = 1.0, double lgs = 0.0) {
     using C = Comp<KIND>;
     T p[C::NP], c[C::NC];
 #pragma unroll
     for (int k = 0; k < C::NP; ++k) p[k] = Flat<T>::seed(scratch[k], k);
 #pragma unroll
     for (int k = 0; k < C::NC; ++k) c[k] = Flat<T>::get(scratch + ELISA_MAX_COMP_PARAMS + k * Flat<T>::SIZE);
-    return leaf_bin_pc<KIND, T>(p, c, method, gv, e, leaf);
+    return leaf_bin_pc<KIND, T>(p, c, method, gv, e, leaf, gs, lgs);
 }
 
 }  // namespace elisa

@@ -50,16 +50,27 @@ struct LeafDev {
     int32_t pad2_;
     double cst[ELISA_MAX_COMP_PARAMS];
     double aux[2];
+    // energy shifts around the leaf: grid scale, its log, output scale -- on the photon grid
+    // and on the grid of the enclosing flux normalisation
+    double gs, lgs, os;
+    double ngs, lngs, nos;
 };
 
-constexpr int MAX_OPS = 2 * ELISA_MAX_COMPONENTS;
+constexpr int MAX_OPS = 2 * ELISA_MAX_COMPONENTS + ELISA_MAX_NORMS;
+
+struct NormDev {
+    int32_t kind, f_src;
+    int32_t op_lo, op_hi;  // the normalised sub-expression is ops[op_lo, op_hi); the opcode sits at op_hi
+    double f_cst;
+};
 
 struct ModelDev {
     int32_t n_leaf, n_ops;
     int32_t ops[MAX_OPS];
     uint32_t used_mask;  // theta columns this model depends on
-    int32_t pad_;
+    int32_t n_norms;
     LeafDev leaf[ELISA_MAX_COMPONENTS];
+    NormDev norm[ELISA_MAX_NORMS];
 };
 
 struct UnfoldArgs {
@@ -100,6 +111,51 @@ __device__ __forceinline__ typename StackT<PU>::type scatter_leaf(const Dual<NPK
     X(ELISA_COMP_PLPHFLUX) X(ELISA_COMP_POWERLAW) X(ELISA_COMP_SMOOTHLYBROKENPL) X(ELISA_COMP_CONSTANT)            \
     X(ELISA_COMP_EDGE) X(ELISA_COMP_EXPABS) X(ELISA_COMP_EXPFAC) X(ELISA_COMP_GABS) X(ELISA_COMP_HIGHECUT)         \
     X(ELISA_COMP_PLABS) X(ELISA_COMP_PHOTONABS)
+
+// Stack machine over ops[lo, hi) for one bin per lane.  on_norm_grid: `gv` is the grid of a flux
+// normalisation, leaves take their scales on that grid; nrm: finished normalisation factors.
+template <int PU>
+__device__ __noinline__ typename StackT<PU>::type interp_range(const ModelDev& model,
+                                                               const double (*scr)[LEAF_SCRATCH], int lo, int hi,
+                                                               const GridView& gv, int e, bool on_norm_grid,
+                                                               const typename StackT<PU>::type* nrm) {
+    using TT = typename StackT<PU>::type;
+    constexpr bool GRAD = PU > 0;
+    TT stk[ELISA_MAX_COMPONENTS];
+    int sp = 0;
+    for (int o = lo; o < hi; ++o) {
+        const int op = model.ops[o];
+        if (op >= 0) {
+            const LeafDev& L = model.leaf[op];
+            const double gs = on_norm_grid ? L.ngs : L.gs, lgs = on_norm_grid ? L.lngs : L.lgs;
+            const double os = on_norm_grid ? L.nos : L.os;
+            TT val;
+            switch (L.kind) {
+#define X(KIND)                                                                                            \
+    case KIND:                                                                                             \
+        if constexpr (GRAD)                                                                                \
+            val = scatter_leaf<PU, Comp<KIND>::NP>(                                                        \
+                leaf_bin<KIND, Dual<Comp<KIND>::NP>>(scr[op], L.method, gv, e, op, gs, lgs), L.src);       \
+        else                                                                                               \
+            val = leaf_bin<KIND, double>(scr[op], L.method, gv, e, op, gs, lgs);                           \
+        break;
+                ELISA_FOR_EACH_KIND(X)
+#undef X
+                default:
+                    val = Cst<TT>::make(0.0);
+            }
+            if (os != 1.0) val = os * val;
+            stk[sp++] = val;
+        } else if (op <= ELISA_OP_NORM0) {
+            stk[sp - 1] = nrm[ELISA_OP_NORM0 - op] * stk[sp - 1];
+        } else {
+            const TT rhs = stk[--sp];
+            const TT lhs = stk[sp - 1];
+            stk[sp - 1] = (op == ELISA_OP_ADD) ? lhs + rhs : lhs * rhs;
+        }
+    }
+    return stk[0];
+}
 
 // Ahead-of-time interpreter: runs any model program without runtime compilation (the
 // fallback when NVRTC is unavailable, and the cross-check of the specialised kernels).
@@ -157,38 +213,30 @@ __global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_
     }
     __syncwarp();
 
+    // ---- flux normalisations: F / sum over the normalisation's own grid ----------------
+    TT nrm[ELISA_MAX_NORMS];
+    for (int k = 0; k < model.n_norms; ++k) {
+        const NormDev& nd = model.norm[k];
+        const GridView& gv = a.ngv[k];
+        TT acc = Cst<TT>::make(0.0);
+        for (int e0 = 0; e0 < gv.E; e0 += 31) {
+            const int e = e0 + lane;
+            const TT v = interp_range<PU>(model, scr, nd.op_lo, nd.op_hi, gv, e, true, nrm);
+            if (lane < 31 && e < gv.E) acc = acc + (a.nw[k] != nullptr ? a.nw[k][e] : 1.0) * v;
+        }
+        acc = warp_sum(acc);
+        TT F = Cst<TT>::make(nd.f_src >= 0 ? th[nd.f_src] : nd.f_cst);
+        if constexpr (GRAD) {
+            if (nd.f_src >= 0) F.d[nd.f_src] = 1.0;
+        }
+        nrm[k] = F / acc;
+    }
+
     // ---- passes of 31 bins ------------------------------------------------------------
     for (int e0 = e_lo; e0 < e_hi; e0 += 31) {
         const int e = e0 + lane;
-        TT stk[ELISA_MAX_COMPONENTS];
-        int sp = 0;
-        for (int o = 0; o < model.n_ops; ++o) {
-            const int op = model.ops[o];
-            if (op >= 0) {
-                const LeafDev& L = model.leaf[op];
-                TT val;
-                switch (L.kind) {
-#define X(KIND)                                                                                            \
-    case KIND:                                                                                             \
-        if constexpr (GRAD)                                                                                \
-            val = scatter_leaf<PU, Comp<KIND>::NP>(                                                        \
-                leaf_bin<KIND, Dual<Comp<KIND>::NP>>(scr[op], L.method, a.gv, e, op), L.src);                  \
-        else                                                                                               \
-            val = leaf_bin<KIND, double>(scr[op], L.method, a.gv, e, op);                                      \
-        break;
-                    ELISA_FOR_EACH_KIND(X)
-#undef X
-                    default:
-                        val = Cst<TT>::make(0.0);
-                }
-                stk[sp++] = val;
-            } else {
-                const TT rhs = stk[--sp];
-                const TT lhs = stk[sp - 1];
-                stk[sp - 1] = (op == ELISA_OP_ADD) ? lhs + rhs : lhs * rhs;
-            }
-        }
-        if (lane < 31 && e < e_hi) unfold_store<TT>(a, row_off + e, stk[0]);
+        const TT res = interp_range<PU>(model, scr, 0, model.n_ops, a.gv, e, false, nrm);
+        if (lane < 31 && e < e_hi) unfold_store<TT>(a, row_off + e, res);
     }
     if (last_seg) unfold_zero(a, row_off, E, a.e_pad, lane, GRAD);
 }
@@ -616,6 +664,12 @@ struct SpectrumPlan {
     // device arrays
     double *egrid = nullptr, *lngrid = nullptr, *emid = nullptr, *lnmid = nullptr;
     double* tab[2 * ELISA_MAX_COMPONENTS] = {};  // sigma(E) of table components at edges / midpoints
+    // flux normalisations: their grids (egrid, lngrid, emid, lnmid), EnFlux weights, tables
+    struct NormGrid {
+        double *egrid = nullptr, *lngrid = nullptr, *emid = nullptr, *lnmid = nullptr, *w = nullptr;
+        double* tab[2 * ELISA_MAX_COMPONENTS] = {};
+        int E = 0;
+    } norm_grid[ELISA_MAX_NORMS];
     double* chan = nullptr;  // 9 arrays of C_pad: scale on off sigma ratio gof_on gof_off area inv_width
     PackedDevice fwd, bwd;   // R [E, C] tiled over C ; R^T [C, E] tiled over E
     I8Operand i8_fwd, i8_bwd;  // digit images of R^T rows (channels) / R rows (energies); img == nullptr: DMMA fold
@@ -626,6 +680,12 @@ struct SpectrumPlan {
     GridView grid_view() const {
         GridView g{egrid, lngrid, emid, lnmid, E};
         for (int i = 0; i < 2 * ELISA_MAX_COMPONENTS; ++i) g.tab[i] = tab[i];
+        return g;
+    }
+    GridView norm_view(int k) const {
+        const NormGrid& n = norm_grid[k];
+        GridView g{n.egrid, n.lngrid, n.emid, n.lnmid, n.E};
+        for (int i = 0; i < 2 * ELISA_MAX_COMPONENTS; ++i) g.tab[i] = n.tab[i];
         return g;
     }
     ChanArrays chan_view() const {
@@ -792,6 +852,16 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
         L.aux[1] = c.aux[1];
         if ((c.kind == ELISA_COMP_PLENFLUX || c.kind == ELISA_COMP_PLPHFLUX) && !(c.aux[0] > 0.0 && c.aux[1] > c.aux[0]))
             return fail(ELISA_ERR_INVALID, "model: PLPhFlux/PLEnFlux need 0 < emin < emax in aux");
+        auto one = [](double v) { return v == 0.0 ? 1.0 : v; };
+        L.gs = one(c.grid_scale);
+        L.os = one(c.out_scale);
+        L.ngs = one(c.norm_grid_scale);
+        L.nos = one(c.norm_out_scale);
+        if (!(L.gs > 0.0 && L.gs < HUGE_VAL) || !(L.ngs > 0.0 && L.ngs < HUGE_VAL) || !(fabs(L.os) < HUGE_VAL) ||
+            !(fabs(L.nos) < HUGE_VAL))
+            return fail(ELISA_ERR_INVALID, "model: grid_scale must be positive and finite, out_scale finite");
+        L.lgs = L.gs == 1.0 ? 0.0 : log(L.gs);
+        L.lngs = L.ngs == 1.0 ? 0.0 : log(L.ngs);
         if (c.kind == ELISA_COMP_PHOTONABS) {
             if (c.table_energy == nullptr || c.table_xsect == nullptr || c.table_len < 2)
                 return fail(ELISA_ERR_INVALID, "model: PhotonAbsorption needs a cross-section table (>= 2 points)");
@@ -802,22 +872,52 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
         }
     }
     // postfix program; a single component may omit it
-    if (md.n_ops == 0 && md.n_components == 1) {
+    if (md.n_ops == 0 && md.n_components == 1 && md.n_norms == 0) {
         out->n_ops = 1;
         out->ops[0] = 0;
         return ELISA_OK;
     }
     if (md.n_ops < 1 || md.n_ops > MAX_OPS || md.ops == nullptr)
         return fail(ELISA_ERR_INVALID, "model: n_ops out of range");
+    if (md.n_norms < 0 || md.n_norms > ELISA_MAX_NORMS || (md.n_norms > 0 && md.norms == nullptr))
+        return fail(ELISA_ERR_INVALID, "model: n_norms out of range");
+    out->n_norms = md.n_norms;
+    for (int k = 0; k < md.n_norms; ++k) {
+        const ElisaNormDesc& nd = md.norms[k];
+        if (nd.kind != ELISA_NORM_PHFLUX && nd.kind != ELISA_NORM_ENFLUX)
+            return fail(ELISA_ERR_INVALID, "model: unknown flux normalisation");
+        if (nd.f_src >= P) return fail(ELISA_ERR_INVALID, "model: norm f_src >= n_params");
+        if (nd.grid == nullptr || nd.n_grid < 2) return fail(ELISA_ERR_INVALID, "model: flux grid needs >= 2 points");
+        for (int j = 0; j < nd.n_grid; ++j)
+            if (!(nd.grid[j] > 0.0) || (j > 0 && !(nd.grid[j] > nd.grid[j - 1])))
+                return fail(ELISA_ERR_INVALID, "model: flux grid must be positive and increasing");
+        out->norm[k] = NormDev{nd.kind, nd.f_src < 0 ? -1 : nd.f_src, -1, -1, nd.f_const};
+        if (nd.f_src >= 0) out->used_mask |= 1u << nd.f_src;
+    }
     int depth = 0;
     // type check as models/model.py:1228-1258: '+' needs add, add; '*' forbids add * add
-    std::vector<int> types;  // 1 = additive, 0 = multiplicative
+    std::vector<int> types;   // 1 = additive, 0 = multiplicative
+    std::vector<int> starts;  // first op of the sub-expression on each stack level
+    std::vector<int> normed;  // that sub-expression contains a flux normalisation
     for (int o = 0; o < md.n_ops; ++o) {
         const int op = md.ops[o];
         if (op >= 0) {
             if (op >= md.n_components) return fail(ELISA_ERR_INVALID, "model: op references unknown component");
             types.push_back(comp_is_additive(md.components[op].kind) ? 1 : 0);
+            starts.push_back(o);
+            normed.push_back(0);
             ++depth;
+        } else if (op <= ELISA_OP_NORM0 && op > ELISA_OP_NORM0 - ELISA_MAX_NORMS) {
+            const int k = ELISA_OP_NORM0 - op;
+            if (k >= md.n_norms) return fail(ELISA_ERR_INVALID, "model: op references unknown flux normalisation");
+            if (depth < 1) return fail(ELISA_ERR_INVALID, "model: malformed postfix program");
+            if (types.back() != 1)  // conv.py:24 _supported = {'add'}
+                return fail(ELISA_ERR_INVALID, "model: PhFlux / EnFlux need an additive operand");
+            if (normed.back()) return fail(ELISA_ERR_UNSUPPORTED, "model: nested flux normalisations");
+            if (out->norm[k].op_hi >= 0) return fail(ELISA_ERR_INVALID, "model: flux normalisation used twice");
+            out->norm[k].op_lo = starts.back();
+            out->norm[k].op_hi = o;
+            normed.back() = 1;
         } else if (op == ELISA_OP_ADD || op == ELISA_OP_MUL) {
             if (depth < 2) return fail(ELISA_ERR_INVALID, "model: malformed postfix program");
             const int r = types.back();
@@ -829,6 +929,10 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
             if (op == ELISA_OP_MUL && l == 1 && r == 1)
                 return fail(ELISA_ERR_INVALID, "model: '*' of two additive operands");
             types.push_back(op == ELISA_OP_ADD ? 1 : (l | r));
+            const int nr = normed.back();
+            normed.pop_back();
+            starts.pop_back();
+            normed.back() |= nr;
             --depth;
         } else {
             return fail(ELISA_ERR_INVALID, "model: unknown opcode");
@@ -837,6 +941,8 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
         out->ops[o] = op;
     }
     if (depth != 1) return fail(ELISA_ERR_INVALID, "model: malformed postfix program");
+    for (int k = 0; k < md.n_norms; ++k)
+        if (out->norm[k].op_hi < 0) return fail(ELISA_ERR_INVALID, "model: flux normalisation without its opcode");
     out->n_ops = md.n_ops;
     return ELISA_OK;
 }
@@ -896,11 +1002,45 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
             const double t = (lx - xp[j]) / (xp[j + 1] - xp[j]);
             return exp(fp[j] + t * (fp[j + 1] - fp[j]));
         };
-        std::vector<double> se(E + 1), sm(E);
-        for (int e = 0; e <= E; ++e) se[e] = sigma(log(eg[e]));
-        for (int e = 0; e < E; ++e) sm[e] = sigma(log(em[e]));
-        if ((rc = upload(plan, se, &sp->tab[2 * i]))) return rc;
-        if ((rc = upload(plan, sm, &sp->tab[2 * i + 1]))) return rc;
+        // the component sees the grid scaled by the energy shifts around it
+        auto tables = [&](const std::vector<double>& g, double gs, double** edges, double** mids) -> int {
+            const int n_e = (int)g.size() - 1;
+            std::vector<double> se(n_e + 1), sm(n_e);
+            for (int e = 0; e <= n_e; ++e) se[e] = sigma(log(gs * g[e]));
+            for (int e = 0; e < n_e; ++e) sm[e] = sigma(log(gs * (0.5 * (g[e] + g[e + 1]))));
+            int r;
+            if ((r = upload(plan, se, edges))) return r;
+            return upload(plan, sm, mids);
+        };
+        if ((rc = tables(eg, sp->model.leaf[i].gs, &sp->tab[2 * i], &sp->tab[2 * i + 1]))) return rc;
+        for (int k = 0; k < sd.model.n_norms; ++k) {
+            const NormDev& nd = sp->model.norm[k];
+            bool inside = false;
+            for (int o = nd.op_lo; o < nd.op_hi; ++o) inside |= sp->model.ops[o] == i;
+            if (!inside) continue;
+            const std::vector<double> ng(sd.model.norms[k].grid, sd.model.norms[k].grid + sd.model.norms[k].n_grid);
+            if ((rc = tables(ng, sp->model.leaf[i].ngs, &sp->norm_grid[k].tab[2 * i], &sp->norm_grid[k].tab[2 * i + 1])))
+                return rc;
+        }
+    }
+    // flux normalisations: their own grids; EnFlux weights keV_to_erg * sqrt(e_j e_j+1) (conv.py:251-254)
+    for (int k = 0; k < sd.model.n_norms; ++k) {
+        const ElisaNormDesc& nd = sd.model.norms[k];
+        const int n_e = nd.n_grid - 1;
+        std::vector<double> g(nd.grid, nd.grid + nd.n_grid), l(n_e + 1), m(n_e), ml(n_e), w(n_e);
+        for (int e = 0; e <= n_e; ++e) l[e] = log(g[e]);
+        for (int e = 0; e < n_e; ++e) {
+            m[e] = 0.5 * (g[e] + g[e + 1]);
+            ml[e] = log(m[e]);
+            w[e] = 1.602176634e-9 * sqrt(g[e] * g[e + 1]);
+        }
+        SpectrumPlan::NormGrid& ngd = sp->norm_grid[k];
+        ngd.E = n_e;
+        if ((rc = upload(plan, g, &ngd.egrid))) return rc;
+        if ((rc = upload(plan, l, &ngd.lngrid))) return rc;
+        if ((rc = upload(plan, m, &ngd.emid))) return rc;
+        if ((rc = upload(plan, ml, &ngd.lnmid))) return rc;
+        if (nd.kind == ELISA_NORM_ENFLUX && (rc = upload(plan, w, &ngd.w))) return rc;
     }
 
     // per-channel data, padded with benign values
@@ -1089,6 +1229,7 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
         const std::string k = std::to_string(m.leaf[i].kind), id = std::to_string(i);
         s += "    T p" + id + "[Comp<" + k + ">::NP]; T c" + id + "[Comp<" + k + ">::NC];\n";
     }
+    for (int k = 0; k < m.n_norms; ++k) s += "    T n" + std::to_string(k) + ";\n";
     s += "  };\n  template <typename T> __device__ __forceinline__ static void pre(const double* th, Pre<T>& s) {\n";
     for (int i = 0; i < m.n_leaf; ++i) {
         const LeafDev& L = m.leaf[i];
@@ -1104,31 +1245,74 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
         s += "      for (int k = 0; k < Comp<" + k + ">::NC; ++k) s.c" + id + "[k] = Flat<T>::seed(0.0, -1);\n";
         s += "      Comp<" + k + ">::pre(s.p" + id + ", aux, s.c" + id + "); }\n";
     }
-    s += "  }\n  template <typename T> __device__ __forceinline__ static T bin(const Pre<T>& s, const GridView& gv, int e) {\n";
-    std::vector<std::string> stack;
-    std::vector<bool> emitted(m.n_leaf, false);
-    int tmp = 0;
-    for (int o = 0; o < m.n_ops; ++o) {
-        const int op = m.ops[o];
-        if (op >= 0) {
-            const std::string id = std::to_string(op);
-            if (!emitted[op]) {
-                s += "    const T v" + id + " = leaf_bin_pc<" + std::to_string(m.leaf[op].kind) + ", T>(s.p" + id + ", s.c" +
-                     id + ", " + std::to_string(m.leaf[op].method) + ", gv, e, " + id + ");\n";
-                emitted[op] = true;
+    s += "  }\n";
+    // straight-line code of ops[lo, hi) on grid view `gv`; on_norm_grid selects the leaf's scales
+    // on a flux-normalisation grid (shifts inside the normalised sub-expression only)
+    auto emit_range = [&](int lo, int hi, bool on_norm_grid, const std::string& pfx) {
+        std::vector<std::string> stack;
+        std::vector<bool> emitted(m.n_leaf, false);
+        int tmp = 0;
+        for (int o = lo; o < hi; ++o) {
+            const int op = m.ops[o];
+            if (op >= 0) {
+                const LeafDev& L = m.leaf[op];
+                const std::string id = std::to_string(op);
+                if (!emitted[op]) {
+                    const double gs = on_norm_grid ? L.ngs : L.gs, lgs = on_norm_grid ? L.lngs : L.lgs;
+                    const double os = on_norm_grid ? L.nos : L.os;
+                    s += "    const T " + pfx + "v" + id + " = " + (os != 1.0 ? hexd(os) + " * " : std::string()) +
+                         "leaf_bin_pc<" + std::to_string(L.kind) + ", T>(s.p" + id + ", s.c" + id + ", " +
+                         std::to_string(L.method) + ", gv, e, " + id + ", " + hexd(gs) + ", " + hexd(lgs) + ");\n";
+                    emitted[op] = true;
+                }
+                stack.push_back(pfx + "v" + id);
+            } else if (op <= ELISA_OP_NORM0) {
+                const std::string t = pfx + "t" + std::to_string(tmp++);
+                s += "    const T " + t + " = s.n" + std::to_string(ELISA_OP_NORM0 - op) + " * " + stack.back() + ";\n";
+                stack.back() = t;
+            } else {
+                const std::string r = stack.back();
+                stack.pop_back();
+                const std::string l = stack.back();
+                stack.pop_back();
+                const std::string t = pfx + "t" + std::to_string(tmp++);
+                s += "    const T " + t + " = " + l + (op == ELISA_OP_ADD ? " + " : " * ") + r + ";\n";
+                stack.push_back(t);
             }
-            stack.push_back("v" + id);
-        } else {
-            const std::string r = stack.back();
-            stack.pop_back();
-            const std::string l = stack.back();
-            stack.pop_back();
-            const std::string t = "t" + std::to_string(tmp++);
-            s += "    const T " + t + " = " + l + (op == ELISA_OP_ADD ? " + " : " * ") + r + ";\n";
-            stack.push_back(t);
         }
+        return stack.back();
+    };
+    for (int k = 0; k < m.n_norms; ++k) {
+        s += "  template <typename T> __device__ __forceinline__ static T sub" + std::to_string(k) +
+             "(const Pre<T>& s, const GridView& gv, int e) {\n";
+        const std::string r = emit_range(m.norm[k].op_lo, m.norm[k].op_hi, true, "n");
+        s += "    return " + r + ";\n  }\n";
     }
-    s += "    return " + stack.back() + ";\n  }\n};\n";
+    s += "  template <typename T> __device__ __forceinline__ static void norms(Pre<T>& s, const UnfoldCore& a, "
+         "const double* th, int lane) {\n";
+    for (int k = 0; k < m.n_norms; ++k) {
+        const NormDev& nd = m.norm[k];
+        const std::string id = std::to_string(k);
+        s += "    {\n      const GridView gv = a.ngv[" + id + "];\n      T acc = Cst<T>::make(0.0);\n";
+        s += "      for (int e0 = 0; e0 < gv.E; e0 += 31) {\n        const int e = e0 + lane;\n";
+        s += "        const T v = sub" + id + "<T>(s, gv, e);\n";
+        if (nd.kind == ELISA_NORM_ENFLUX)
+            s += "        if (lane < 31 && e < gv.E) acc = acc + a.nw[" + id + "][e] * v;\n";
+        else
+            s += "        if (lane < 31 && e < gv.E) acc = acc + v;\n";
+        s += "      }\n      acc = warp_sum(acc);\n";
+        if (nd.f_src >= 0)
+            s += "      const T F = Flat<T>::seed(th[" + std::to_string(nd.f_src) + "], " + std::to_string(nd.f_src) + ");\n";
+        else
+            s += "      const T F = Flat<T>::seed(" + hexd(nd.f_cst) + ", -1);\n";
+        s += "      s.n" + id + " = F / acc;\n    }\n";
+    }
+    s += "  }\n";
+    s += "  template <typename T> __device__ __forceinline__ static T bin(const Pre<T>& s, const GridView& gv, int e) {\n";
+    {
+        const std::string r = emit_range(0, m.n_ops, false, "");
+        s += "    return " + r + ";\n  }\n};\n";
+    }
     const std::string k = std::to_string(ks);
     s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_val(const UnfoldCore a) { unfold_generic<Model, double, " +
          k + ">(a); }\n";
@@ -1264,6 +1448,11 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.img = nullptr;
     a.scale = nullptr;
     a.gv.has_point = 0;
+    for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
+        a.ngv[k] = sp.norm_view(k);
+        a.ngv[k].has_point = 0;
+        a.nw[k] = sp.norm_grid[k].w;
+    }
     if (fused_digits != nullptr) {
         *fused_digits = sp.jit != nullptr && (sp.use_i8() && !plan->force_dmma) && n_seg == 1 && plan->A_img != nullptr;
         if (*fused_digits) {
@@ -1877,6 +2066,17 @@ static int run_small(ElisaPlan* plan, const double* theta, const double* on, con
 extern "C" {
 
 int elisa_b200_abi_version(void) { return ELISA_B200_ABI_VERSION; }
+
+int64_t elisa_b200_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return sizeof(ElisaComponentDesc);
+        case 1: return sizeof(ElisaNormDesc);
+        case 2: return sizeof(ElisaModelDesc);
+        case 3: return sizeof(ElisaSpectrumDesc);
+        case 4: return sizeof(ElisaPlanDesc);
+        default: return -1;
+    }
+}
 
 const char* elisa_b200_last_error(void) { return g_last_error.c_str(); }
 

@@ -37,6 +37,10 @@ struct UnfoldCore {
     // belongs to one warp (n_seg == 1) and the kernel was specialised with KS > 0; else nullptr
     int8_t* img;
     double* scale;
+    // flux normalisations (PhFlux / EnFlux, models/conv.py:145-256): their own grids and, for
+    // EnFlux, the bin weights keV_to_erg * sqrt(e_j e_j+1) (nullptr: 1)
+    GridView ngv[ELISA_MAX_NORMS];
+    const double* nw[ELISA_MAX_NORMS];
 };
 
 constexpr int UNFOLD_WARPS = 4;
@@ -69,6 +73,19 @@ __device__ __forceinline__ double unfold_store(const UnfoldCore& a, size_t off, 
     return u;
 }
 
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> warp_sum(Dual<N> x) {
+    x.v = warp_sum(x.v);
+#pragma unroll
+    for (int j = 0; j < N; ++j) x.d[j] = warp_sum(x.d[j]);
+    return x;
+}
+
 template <class Model, typename T, int KS = 0>
 __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
     constexpr bool GRAD = Scalar<T>::NP > 0;
@@ -95,6 +112,9 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
     }
     typename Model::template Pre<T> pre;
     Model::template pre<T>(a.theta + (size_t)row * a.P, pre);
+    // flux normalisations: every warp of the row sums the normalised sub-expression over the
+    // normalisation's own grid (nothing to do for models without PhFlux / EnFlux)
+    Model::template norms<T>(pre, a, a.theta + (size_t)row * a.P, lane);
     // the grid values of a pass are loaded during the previous one
     GridView gv = a.gv;
     gv.has_point = 1;

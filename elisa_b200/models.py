@@ -21,6 +21,8 @@ __all__ = [
     'Band', 'BandEp', 'BentPL', 'Blackbody', 'BlackbodyRad', 'BrokenPL', 'Compt', 'CutoffPL', 'Gauss',
     'Lorentz', 'OTTB', 'OTTS', 'PLEnFlux', 'PLPhFlux', 'PowerLaw', 'SmoothlyBrokenPL',
     'Constant', 'Edge', 'ExpAbs', 'ExpFac', 'GAbs', 'HighECut', 'PLAbs',
+    'PhAbs', 'TBAbs', 'WAbs', 'PhotonAbsorption',
+    'EnFlux', 'PhFlux', 'ZAShift', 'ZMShift', 'VAShift', 'VMShift',
     'UniformParameter', 'Model', 'CompiledModel',
 ]
 
@@ -144,6 +146,8 @@ class CompositeModel(Model):
             raise TypeError(
                 f"unsupported operand types for {op}: '{type(lhs).__name__}' and '{type(rhs).__name__}'"
             )
+        if 'conv' in (lhs.type, rhs.type):
+            raise TypeError(f'unsupported model type for {op}: a convolution model must be applied to a model first')
         if op == '+':
             if lhs.type != 'add':
                 raise TypeError(f'{lhs} is not an additive model')
@@ -254,6 +258,106 @@ class WAbs(PhotonAbsorption):  # models/mul.py:588-640
     pass
 
 
+# --------------------------------------------------------------------------- convolution components
+class ConvolutionComponent(Component):
+    """models/model.py:1877-2000: a component that wraps a model, ``op(model)``.  As in the
+    reference (ConvolvedModel.__init__, :1917-1919) its parameters come AFTER those of the
+    model it wraps."""
+
+    type = 'conv'
+    _kind = -1
+    _supported = frozenset({'add', 'mul'})
+
+    def __call__(self, model: Model) -> 'ConvolvedModel':
+        if not isinstance(model, Model) or model.type not in self._supported:
+            accepted = ', '.join(f"'{i}'" for i in sorted(self._supported))
+            raise TypeError(
+                f'{self.name} convolution model supports models with type: {accepted}; got '
+                f"'{getattr(model, 'type', type(model).__name__)}' type model {model}"
+            )
+        return ConvolvedModel(self, model)
+
+    def __add__(self, other):
+        raise TypeError(f'{self.name} is a convolution model: apply it to a model first')
+
+    __mul__ = __add__
+
+
+class ConvolvedModel(Model):
+    """models/model.py:1905-1959."""
+
+    def __init__(self, op: ConvolutionComponent, model: Model):
+        self.op, self.inner = op, model
+        self.type = model.type
+
+    def _leaves(self):
+        out = list(self.inner._leaves())
+        if all(self.op is not o for o in out):
+            out.append(self.op)
+        return out
+
+    def __repr__(self):
+        return f'{self.op.name}({self.inner!r})'
+
+
+class _Shift(ConvolutionComponent):
+    """Energy shifts (models/conv.py:259-432).  The shift parameter is fixed by default in the
+    reference; a FREE z / v needs the derivative of the wrapped model with respect to its energy
+    grid, which this path does not carry -- it is refused."""
+
+    _divide = False  # ZAShift divides the shifted model by the factor (conv.py:299-300)
+
+    def factor(self) -> float:
+        p = self.params[self._config[0].name]
+        if not p.fixed:
+            raise NotImplementedError(f'{self.name}: a free {p.name} is not supported on this path (fix it)')
+        return self._factor(p.default)
+
+
+def _shift(name, supported, pcfg, factor, divide=False):
+    return type(name, (_Shift,), {'_config': (ParamConfig(*pcfg),), '_supported': frozenset({supported}),
+                                  '_factor': staticmethod(factor), '_divide': divide})
+
+
+_C_KMS = 299792.458  # conv.py:383
+ZAShift = _shift('ZAShift', 'add', ('z', 0.0, -0.999, 15.0, False, True), lambda z: 1.0 + z, divide=True)
+ZMShift = _shift('ZMShift', 'mul', ('z', 0.0, -0.999, 15.0, False, True), lambda z: 1.0 + z)
+VAShift = _shift('VAShift', 'add', ('v', 0.0, -1e4, 1e4, False, True), lambda v: 1.0 - v / _C_KMS)
+VMShift = _shift('VMShift', 'mul', ('v', 0.0, -1e4, 1e4, False, True), lambda v: 1.0 - v / _C_KMS)
+
+
+class _FluxNorm(ConvolutionComponent):
+    """NormConvolution (models/conv.py:21-143): ``PhFlux(emin, emax, F=None, ngrid=1000, elog=True)``."""
+
+    _supported = frozenset({'add'})
+
+    def __init__(self, emin, emax, *args, ngrid=None, elog=None, **params):
+        emin, emax = float(emin), float(emax)
+        if emin >= emax:
+            raise ValueError('emin must be less than emax')
+        super().__init__(*args, **params)
+        self.emin, self.emax = emin, emax
+        self.ngrid = 1000 if ngrid is None else int(ngrid)
+        self.elog = True if elog is None else bool(elog)
+        if self.ngrid < 2:
+            raise ValueError('ngrid must be at least 2')
+
+    def flux_egrid(self) -> np.ndarray:
+        """conv.py:81-84."""
+        fn = np.geomspace if self.elog else np.linspace
+        return np.ascontiguousarray(fn(self.emin, self.emax, self.ngrid), dtype=np.float64)
+
+
+class PhFlux(_FluxNorm):  # conv.py:145-195
+    _config = (ParamConfig('F', 1.0, 0.01, 1e10),)
+
+
+class EnFlux(_FluxNorm):  # conv.py:198-256
+    _config = (ParamConfig('F', 1e-12, 1e-30, 1e30, True),)
+
+
+CONVOLUTION = (EnFlux, PhFlux, ZAShift, ZMShift, VAShift, VMShift)
+
 ADDITIVE = (Band, BandEp, BentPL, Blackbody, BlackbodyRad, BrokenPL, Compt, CutoffPL, Gauss, Lorentz, OTTB, OTTS,
             PLEnFlux, PLPhFlux, PowerLaw, SmoothlyBrokenPL)
 MULTIPLICATIVE = (Constant, Edge, ExpAbs, ExpFac, GAbs, HighECut, PLAbs)
@@ -274,11 +378,16 @@ class CompiledModel:
             raise TypeError('model must be a Model')
         self.model = model
         self.type = model.type
+        if model.type == 'conv':
+            raise TypeError(f'{model} is a convolution model: apply it to a model first')
+        # distinct components in the reference's order (naming, free parameters)
         self.leaves: list[Component] = model._leaves()
-        if len(self.leaves) > _lib.MAX_COMPONENTS:
+        # the program: one entry per (component, energy-shift context), flux normalisations, postfix ops
+        self.entries: list[tuple] = []  # (component, grid_scale, out_scale, norm_grid_scale, norm_out_scale)
+        self.norms: list[_FluxNorm] = []
+        self.ops: list[int] = self._emit(model, (1.0, 1.0, 1.0, 1.0, False))
+        if len(self.entries) > _lib.MAX_COMPONENTS:
             raise NotImplementedError(f'more than {_lib.MAX_COMPONENTS} components in one model')
-        index = {id(c): i for i, c in enumerate(self.leaves)}
-        self.ops: list[int] = model._postfix(index)
         # component display names: PowerLaw, PowerLaw_2, ... (models/model.py naming)
         seen: dict[str, int] = {}
         self.comp_names = []
@@ -298,6 +407,36 @@ class CompiledModel:
         self._plan = None
         self._plan_key = None
 
+    def _emit(self, m: Model, ctx) -> list[int]:
+        gs, os_, ngs, nos, in_norm = ctx
+        if isinstance(m, ConvolvedModel):
+            op = m.op
+            if isinstance(op, _Shift):
+                f = op.factor()
+                g = 1.0 / f if op._divide else 1.0
+                return self._emit(m.inner, (gs * f, os_ * g, ngs * f if in_norm else ngs,
+                                            nos * g if in_norm else nos, in_norm))
+            if isinstance(op, _FluxNorm):
+                if in_norm:
+                    raise NotImplementedError('nested flux normalisations (PhFlux / EnFlux) are not supported')
+                if len(self.norms) >= _lib.MAX_NORMS:
+                    raise NotImplementedError(f'more than {_lib.MAX_NORMS} flux normalisations in one model')
+                k = len(self.norms)
+                self.norms.append(op)
+                return self._emit(m.inner, (gs, os_, 1.0, 1.0, True)) + [_lib.OP_NORM0 - k]
+            raise NotImplementedError(f'convolution component {op.name}')
+        if isinstance(m, CompositeModel):
+            return self._emit(m.lhs, ctx) + self._emit(m.rhs, ctx) + [_lib.OP_ADD if m.op == '+' else _lib.OP_MUL]
+        if not isinstance(m, Component) or m.type == 'conv':
+            raise TypeError(f'cannot compile {m!r}')
+        # ZAShift's 1 / (1 + z) acts on the additive factor of each term of the shifted sum
+        key = (m, gs, os_ if m.type == 'add' else 1.0, ngs, (nos if m.type == 'add' else 1.0), in_norm)
+        for i, e in enumerate(self.entries):
+            if e[0] is m and e[1:] == key[1:]:
+                return [i]
+        self.entries.append(key)
+        return [len(self.entries) - 1]
+
     # -- descriptors ---------------------------------------------------------------
     def column_of(self, param: UniformParameter, free: Sequence[UniformParameter] | None = None) -> int:
         free = self.free if free is None else free
@@ -309,9 +448,10 @@ class CompiledModel:
     def to_desc(self, free: Sequence[UniformParameter] | None = None):
         """Build the C descriptor; ``free`` is the global free-parameter list of a joint
         fit (columns of theta), defaulting to this model's own.  Returns (ModelDesc, keepalive)."""
-        comps = (_lib.ComponentDesc * len(self.leaves))()
-        for i, c in enumerate(self.leaves):
+        comps = (_lib.ComponentDesc * len(self.entries))()
+        for i, (c, gs, os_, ngs, nos, _) in enumerate(self.entries):
             d = comps[i]
+            d.grid_scale, d.out_scale, d.norm_grid_scale, d.norm_out_scale = gs, os_, ngs, nos
             d.kind = c._kind
             d.method = _lib.METHOD[c.method]
             for k in range(_lib.MAX_COMP_PARAMS):
@@ -332,19 +472,44 @@ class CompiledModel:
                 d.table_xsect = c.table_xsect.ctypes.data_as(_lib.c_double_p)
                 d.table_len = c.table_energy.size
         ops = (_lib.C.c_int32 * len(self.ops))(*self.ops)
+        norms = (_lib.NormDesc * max(len(self.norms), 1))()
+        grids = []
+        for k, nm in enumerate(self.norms):
+            p = nm.params['F']
+            norms[k].kind = _lib.NORM[type(nm).__name__]
+            norms[k].f_src = -1 if p.fixed else self.column_of(p, free)
+            if not p.fixed and norms[k].f_src < 0:
+                raise ValueError(f'{nm.name}.F is free but not among the fit parameters')
+            norms[k].f_const = p.default
+            g = nm.flux_egrid()
+            grids.append(g)
+            norms[k].grid = g.ctypes.data_as(_lib.c_double_p)
+            norms[k].n_grid = g.size
         md = _lib.ModelDesc()
-        md.n_components = len(self.leaves)
+        md.n_components = len(self.entries)
         md.components = comps
         md.n_ops = len(self.ops)
         md.ops = ops
-        return md, (comps, ops)
+        md.n_norms = len(self.norms)
+        md.norms = norms
+        return md, (comps, ops, norms, grids)
 
     def to_spec(self, free: Sequence[UniformParameter] | None = None):
         """Neutral description (nested tuples) of the same program, the format the test
         oracle consumes: ('comp', name, {pname: ('theta', j) | ('const', v)}, extras),
         ('+', lhs, rhs), ('*', lhs, rhs)."""
 
+        def prefs(m):
+            return {pn: (('const', m.params[pn].default) if m.params[pn].fixed
+                         else ('theta', self.column_of(m.params[pn], free))) for pn in m.param_names}
+
         def rec(m):
+            if isinstance(m, ConvolvedModel):
+                op = m.op
+                extra = {}
+                if isinstance(op, _FluxNorm):
+                    extra = {'emin': op.emin, 'emax': op.emax, 'ngrid': op.ngrid, 'elog': op.elog}
+                return ('conv', type(op).__name__, prefs(op), extra, rec(m.inner))
             if isinstance(m, Component):
                 refs = {}
                 for pname in m.param_names:

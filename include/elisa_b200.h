@@ -55,7 +55,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define ELISA_B200_ABI_VERSION 2
+#define ELISA_B200_ABI_VERSION 3
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define ELISA_OK 0
@@ -114,6 +114,14 @@ extern "C" {
  * operands and push lhs + rhs / lhs * rhs (op applied to BIN values).            */
 #define ELISA_OP_ADD -1
 #define ELISA_OP_MUL -2
+/* Flux normalisation PhFlux / EnFlux (models/conv.py:145-256): the unary opcode
+ * ELISA_OP_NORM0 - k replaces the operand on top of the stack, an additive sub-expression
+ * N(E), by F_k / flux_k * N(E), flux_k = sum over the bins of ElisaNormDesc #k's own grid of
+ * that same sub-expression (times keV_to_erg * sqrt(e_j e_j+1) for EnFlux).              */
+#define ELISA_OP_NORM0 -16
+#define ELISA_MAX_NORMS 2
+#define ELISA_NORM_PHFLUX 0 /* conv.py:185-195 */
+#define ELISA_NORM_ENFLUX 1 /* conv.py:244-256 */
 
 #ifndef __CUDACC_RTC__ /* host-side descriptors and entry points */
 typedef struct ElisaComponentDesc {
@@ -133,13 +141,35 @@ typedef struct ElisaComponentDesc {
     const double* table_energy;
     const double* table_xsect;
     int32_t table_len;
+    /* Energy shifts ZAShift / ZMShift / VAShift / VMShift with a FIXED z or v
+     * (models/conv.py:294-300, 335-341, 378-386, 424-432): the component is evaluated on
+     * photon_egrid * grid_scale (the product of the factors 1 + z, 1 - v/c of the shifts
+     * around it) and its bin values are multiplied by out_scale (the product of ZAShift's
+     * 1 / (1 + z) around an additive component).  0 reads as 1.  A component that occurs
+     * inside and outside a shift is two entries with the same param_src.  norm_* are the
+     * same two factors on the flux grid of the enclosing ELISA_OP_NORM (shifts INSIDE the
+     * normalised sub-expression only).                                               */
+    double grid_scale, out_scale;
+    double norm_grid_scale, norm_out_scale;
 } ElisaComponentDesc;
+
+/* One PhFlux / EnFlux normalisation (models/conv.py:21-143).                        */
+typedef struct ElisaNormDesc {
+    int32_t kind;      /* ELISA_NORM_*                                                */
+    int32_t f_src;     /* the flux parameter F: column of theta, or -1 -> f_const     */
+    double f_const;
+    const double* grid; /* [n_grid] flux_egrid: geomspace / linspace(emin, emax, ngrid),
+                         * conv.py:81-84; positive, increasing                        */
+    int32_t n_grid;     /* >= 2                                                       */
+} ElisaNormDesc;
 
 typedef struct ElisaModelDesc {
     int32_t n_components;
     const ElisaComponentDesc* components;
     int32_t n_ops;
     const int32_t* ops; /* postfix program, see ELISA_OP_*                           */
+    int32_t n_norms;    /* <= ELISA_MAX_NORMS; normalisations may not nest           */
+    const ElisaNormDesc* norms;
 } ElisaModelDesc;
 
 /* One dataset: the fields of FixedData the path reads (data/base.py:1893-1975).     */
@@ -311,6 +341,10 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
 /* 1 if spectrum's component kernel is the runtime-specialised one, 0 if interpreted */
 int elisa_b200_plan_is_specialised(const ElisaPlan* plan, int32_t spectrum);
 int elisa_b200_abi_version(void);
+/* sizeof of the descriptor structs as this library was compiled, for bindings that declare
+ * them by hand: 0 ElisaComponentDesc, 1 ElisaNormDesc, 2 ElisaModelDesc, 3 ElisaSpectrumDesc,
+ * 4 ElisaPlanDesc; -1 otherwise */
+int64_t elisa_b200_sizeof(int32_t which);
 /* thread-local, never NULL */
 const char* elisa_b200_last_error(void);
 

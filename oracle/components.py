@@ -312,3 +312,44 @@ def eval_component(name, egrid, params, method='trapz', **extra):
     if how == 'integral':
         return fn(egrid, params, **{**kwargs, **extra})
     return _integrate(fn, egrid, params, mtype, method)
+
+
+# --------------------------------------------------------------------------- convolution components
+def _shift_factor(x):
+    """The shift parameter is fixed on this path: one value for the whole batch."""
+    v = x.reshape(-1)
+    if not bool(torch.all(v == v[0])):
+        raise NotImplementedError('oracle: the shift parameter must be the same for every row')
+    return float(v[0])
+
+
+def eval_convolution(name, egrid, params, model_fn, **extra):
+    """``convolve`` of the convolution components (models/conv.py); ``model_fn(egrid)`` is the
+    wrapped model's bin values (..., len(egrid) - 1)."""
+    egrid = _t(egrid)
+    if name == 'ZAShift':  # conv.py:294-300
+        factor = 1.0 + _shift_factor(params['z'])
+        return model_fn(egrid * factor) / factor
+    if name == 'ZMShift':  # conv.py:335-341
+        factor = 1.0 + _shift_factor(params['z'])
+        return model_fn(egrid * factor)
+    if name in ('VAShift', 'VMShift'):  # conv.py:378-386, 424-432
+        c = 299792.458
+        f = 1.0 - _shift_factor(params['v']) / c
+        return model_fn(egrid * f)
+    if name in ('PhFlux', 'EnFlux'):
+        # NormConvolution.eval, conv.py:76-98: the flux grid
+        if extra.get('elog', True):
+            flux_egrid = np.geomspace(extra['emin'], extra['emax'], extra.get('ngrid', 1000))
+        else:
+            flux_egrid = np.linspace(extra['emin'], extra['emax'], extra.get('ngrid', 1000))
+        flux_egrid = _t(flux_egrid)
+        F = params['F']
+        if name == 'PhFlux':  # conv.py:185-195
+            mflux = torch.sum(model_fn(flux_egrid), dim=-1, keepdim=True)
+        else:  # conv.py:244-256
+            keV_to_erg = 1.602176634e-9
+            mid = torch.sqrt(flux_egrid[:-1] * flux_egrid[1:])
+            mflux = torch.sum(keV_to_erg * mid * model_fn(flux_egrid), dim=-1, keepdim=True)
+        return F / mflux * model_fn(egrid)
+    raise ValueError(f'unknown convolution component {name}')

@@ -9,6 +9,7 @@ expressed in plain Python so the oracle imports nothing from the product):
 * model spec -- nested tuples
       ('comp', name, {pname: ref, ...}, {'method': 'trapz'|'simpson', 'emin':..., 'emax':...})
       ('+', lhs, rhs) | ('*', lhs, rhs)
+      ('conv', name, {pname: ref}, {'emin':..., 'emax':..., 'ngrid':..., 'elog':...}, inner)
   with ``ref = ('theta', j)`` (column j of the parameter matrix) or ``('const', v)``.
 * data -- a mapping with the ``FixedData`` field names (data/base.py:1893-1975):
   photon_egrid (E+1,), response_matrix (E, C), area_scale, spec_exposure, channel_width,
@@ -20,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .components import F64, eval_component
+from .components import F64, eval_component, eval_convolution
 
 STATISTICS = ('chi2', 'cstat', 'pstat', 'pgstat', 'wstat')
 _WITH_BACK = ('pgstat', 'wstat')
@@ -49,6 +50,15 @@ def eval_model(spec, egrid, theta):
         extra = dict(extra)
         method = extra.pop('method', 'trapz')
         return eval_component(name, egrid, params, method=method, **extra)
+    if kind == 'conv':  # ConvolvedModel.eval, models/model.py:1945-1955
+        _, name, refs, extra, inner = spec
+        params = {}
+        for pname, ref in refs.items():
+            if ref[0] == 'theta':
+                params[pname] = theta[:, ref[1]].unsqueeze(-1)
+            else:
+                params[pname] = torch.full((theta.shape[0], 1), float(ref[1]), dtype=F64)
+        return eval_convolution(name, egrid, params, lambda e: eval_model(inner, e, theta), **extra)
     lhs = eval_model(spec[1], egrid, theta)
     rhs = eval_model(spec[2], egrid, theta)
     if kind == '+':

@@ -100,8 +100,10 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_struct_layout_matches_header(lib):
-    # 4 bytes of padding before the doubles; two table pointers, table_len + tail padding
-    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16 + 8 + 8 + 8
+    # 4 bytes of padding before the doubles; two table pointers, table_len + padding, four scales
+    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16 + 8 + 8 + 8 + 32
+    for which, st in enumerate((_lib.ComponentDesc, _lib.NormDesc, _lib.ModelDesc, _lib.SpectrumDesc, _lib.PlanDesc)):
+        assert lib.elisa_b200_sizeof(which) == C.sizeof(st), st.__name__
     assert _lib.PlanDesc.chunk.offset == 24 and _lib.SpectrumDesc.exposure.offset % 8 == 0
 
 
@@ -146,6 +148,27 @@ def test_specialised_kernel_compiles_for_every_component(lib):
         assert n > 0, (repr(m), lib.elisa_b200_last_error().decode()[:500])
         src = buf.value.decode()
         assert 'unfold_generic<Model' in src and src.count('leaf_bin_pc<') == len(cm.leaves)
+
+
+def test_specialised_kernel_compiles_for_convolution_models(lib):
+    """Energy shifts become literals of the leaf calls; a flux normalisation adds a `sub<k>`
+    function over its own grid, the pre-pass in `norms` and one multiply in `bin`."""
+    import conv_cases
+
+    buf = C.create_string_buffer(1 << 16)
+    for name, (m, _theta) in conv_cases.cases().items():
+        cm = m.compile()
+        md, _keep = cm.to_desc()
+        n = lib.elisa_b200_specialise_check(C.byref(md), max(cm.nparam, 1), buf, len(buf))
+        assert n > 0, (name, lib.elisa_b200_last_error().decode()[:500])
+        src = buf.value.decode()
+        assert src.count('static T sub') == len(cm.norms)
+        assert src.count('warp_sum(acc)') == len(cm.norms)
+    # a malformed program: the normalisation opcode without a descriptor
+    cm = conv_cases.cases()['phflux_pl'][0].compile()
+    md, _keep = cm.to_desc()
+    md.n_norms = 0
+    assert lib.elisa_b200_specialise_check(C.byref(md), 2, buf, len(buf)) < 0
 
 
 # ------------------------------------------------------------------ sharding of the N axis

@@ -203,3 +203,55 @@ def test_photon_absorption_matches_reference_source():
                                                    table_energy=g['table_energy'], table_xsect=g['table_xsect'])
             ref = g[f'{gname}_{method}']
             assert np.allclose(out.numpy(), ref, rtol=1e-13, atol=1e-300), (gname, method)
+
+
+def _conv_cases():
+    import conv_cases
+
+    return conv_cases
+
+
+@pytest.mark.parametrize('name', ['zashift_sum', 'zmshift_mul', 'vashift_gauss_simpson', 'vmshift_edge',
+                                  'same_component_in_and_out', 'phflux_pl', 'phflux_linear_grid_sum',
+                                  'enflux_zashift_plus_gauss', 'zashift_of_phflux', 'two_norms_fixed_flux'])
+def test_convolution_components_match_reference_source(name):
+    """ZAShift / ZMShift / VAShift / VMShift / PhFlux / EnFlux: the oracle against bins produced
+    by the reference's own `convolve` methods (models/conv.py, tools/make_golden.py --conv)."""
+    from oracle.likelihood import eval_model
+
+    cc = _conv_cases()
+    g = np.load(os.path.join(GOLD, 'conv.npz'))
+    model, theta = cc.cases()[name]
+    assert np.array_equal(theta, g[f'{name}/theta']), 'tests/conv_cases.py changed: re-run tools/make_golden.py --conv'
+    out = eval_model(model.compile().to_spec(), torch.as_tensor(g['grid']), torch.as_tensor(theta)).numpy()
+    ref = g[f'{name}/bins']
+    assert out.shape == ref.shape and np.all(np.isfinite(ref))
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-300), float(np.max(np.abs(out / ref - 1.0)))
+
+
+def test_convolution_host_rules():
+    """Type rules and parameter order of the reference (models/model.py:1884-1923)."""
+    from elisa_b200 import models as M
+
+    with pytest.raises(TypeError):
+        M.ZAShift()(M.ExpAbs())  # additive-only
+    with pytest.raises(TypeError):
+        M.ZMShift()(M.PowerLaw())  # multiplicative-only
+    with pytest.raises(TypeError):
+        M.PhFlux(1.0, 10.0)(M.ExpAbs())
+    with pytest.raises(TypeError):
+        M.PowerLaw() + M.ZAShift()  # not applied to a model yet
+    with pytest.raises(ValueError):
+        M.PhFlux(10.0, 1.0)
+    z = M.UniformParameter('z', 0.5, 0.0, 3.0)
+    with pytest.raises(NotImplementedError):
+        M.ZAShift(z=z)(M.PowerLaw()).compile()  # free shift
+    with pytest.raises(NotImplementedError):
+        M.PhFlux(1.0, 10.0)(M.EnFlux(1.0, 10.0)(M.PowerLaw(K=1.0))).compile()  # nested normalisation
+    cm = M.EnFlux(1.0, 10.0)(M.ZAShift(z=0.2)(M.CutoffPL(K=1.0))).compile()
+    # the wrapped model's parameters first, then the convolution's own; fixed z is not a column
+    assert cm.params_name == ['CutoffPL.alpha', 'CutoffPL.Ec', 'EnFlux.F']
+    assert cm.ops == [0, -16] and cm.entries[0][1:5] == (1.2, 1.0 / 1.2, 1.2, 1.0 / 1.2)
+    pl = M.PowerLaw()
+    cm = (pl + M.ZAShift(z=1.0)(pl)).compile()
+    assert cm.nparam == 2 and len(cm.entries) == 2 and cm.ops == [0, 1, -1]

@@ -20,7 +20,7 @@ of those same reference functions.
 Run in the BUILD container only (needs /root/reference); the fixtures are committed and
 travel to the GPU box, this script's input does not.
 
-    python tools/make_golden.py [--photonabs]
+    python tools/make_golden.py [--photonabs | --conv]
 """
 
 from __future__ import annotations
@@ -448,9 +448,76 @@ def photonabs_fixture(ref: RefModel):
     return out
 
 
+def load_convolutions(jnp):
+    """{class name: convolve} executed from models/conv.py as written."""
+    out = {}
+    glb = {'jnp': jnp, 'jax': sys.modules['jax']}
+    tree = ast.parse(_src('models/conv.py'))
+    for node in tree.body:
+        if not isinstance(node, ast.ClassDef):
+            continue
+        for item in node.body:
+            if isinstance(item, ast.FunctionDef) and item.name == 'convolve' and node.name != 'NormConvolution':
+                out[node.name] = _exec_function(item, dict(glb))
+    return out
+
+
+def conv_fixture(ref: RefModel):
+    """tests/conv_cases.py evaluated by the reference: component bins from its continuum /
+    integral code (RefModel.eval), composition on bin values (models/model.py:1285-1295),
+    and every convolution through the `convolve` static methods of models/conv.py executed
+    as written (ConvolvedModel.eval, models/model.py:1945-1955); the flux grid as
+    NormConvolution.eval builds it (conv.py:81-84)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT), ''))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    import conv_cases
+
+    jnp = ref.jnp
+    jnp.geomspace = _wrapped(np.geomspace)
+    jnp.linspace = _wrapped(np.linspace)
+    conv = load_convolutions(jnp)
+    assert set(conv) == {'PhFlux', 'EnFlux', 'ZAShift', 'ZMShift', 'VAShift', 'VMShift'}, sorted(conv)
+
+    def val(ref_, row):
+        return np.float64(row[ref_[1]]) if ref_[0] == 'theta' else np.float64(ref_[1])
+
+    def ev(spec, egrid, row):
+        kind = spec[0]
+        if kind == 'comp':
+            _, name, refs, extra = spec
+            names = ref.cfgs[name][0]
+            kw = {k: extra[k] for k in ('emin', 'emax') if k in extra}
+            return ref.eval(name, egrid, [val(refs[n], row) for n in names], extra.get('method', 'trapz'), **kw)
+        if kind == 'conv':
+            _, name, refs, extra, inner = spec
+            params = {k: val(v, row) for k, v in refs.items()}
+            model_fn = lambda e: _a(ev(inner, e, row))  # noqa: E731
+            if name in ('PhFlux', 'EnFlux'):
+                make = jnp.geomspace if extra['elog'] else jnp.linspace
+                return np.asarray(conv[name](_a(egrid), params, model_fn, make(extra['emin'], extra['emax'], extra['ngrid'])))
+            return np.asarray(conv[name](_a(egrid), params, model_fn))
+        lhs, rhs = ev(spec[1], egrid, row), ev(spec[2], egrid, row)
+        return lhs + rhs if kind == '+' else lhs * rhs
+
+    g = conv_cases.grid()
+    out = {'grid': g}
+    for name, (model, theta) in conv_cases.cases().items():
+        spec = model.compile().to_spec()
+        out[f'{name}/theta'] = theta
+        out[f'{name}/bins'] = np.stack([ev(spec, g, row) for row in theta])
+    return out
+
+
 def main():
     ref = RefModel()
     os.makedirs(OUT, exist_ok=True)
+    if '--conv' in sys.argv or '--all' in sys.argv or len(sys.argv) == 1:
+        cv = conv_fixture(ref)
+        np.savez_compressed(os.path.join(OUT, 'conv.npz'), **cv)
+        print('conv.npz:', len(cv), 'arrays,', os.path.getsize(os.path.join(OUT, 'conv.npz')), 'bytes')
+        if '--conv' in sys.argv:
+            return
+        ref = RefModel()
     if '--photonabs' in sys.argv or '--all' in sys.argv or len(sys.argv) == 1:
         pa = photonabs_fixture(ref)
         np.savez_compressed(os.path.join(OUT, 'photonabs.npz'), **pa)
