@@ -40,6 +40,7 @@ class ComponentDesc(C.Structure):
         ('table_energy', c_double_p),
         ('table_xsect', c_double_p),
         ('table_len', C.c_int32),
+        ('table_log', C.c_int32),
         ('grid_scale', C.c_double),
         ('out_scale', C.c_double),
         ('norm_grid_scale', C.c_double),

@@ -865,10 +865,15 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
         if (c.kind == ELISA_COMP_PHOTONABS) {
             if (c.table_energy == nullptr || c.table_xsect == nullptr || c.table_len < 2)
                 return fail(ELISA_ERR_INVALID, "model: PhotonAbsorption needs a cross-section table (>= 2 points)");
-            for (int k = 0; k < c.table_len; ++k)
-                if (!(c.table_energy[k] > 0.0) || !(c.table_xsect[k] > 0.0) ||
-                    (k > 0 && !(c.table_energy[k] > c.table_energy[k - 1])))
-                    return fail(ELISA_ERR_INVALID, "model: cross-section table must be positive with increasing energies");
+            for (int k = 0; k < c.table_len; ++k) {
+                const bool ok = c.table_log ? (std::isfinite(c.table_energy[k]) && std::isfinite(c.table_xsect[k]))
+                                            : (c.table_energy[k] > 0.0 && c.table_xsect[k] > 0.0);
+                if (!ok || (k > 0 && !(c.table_energy[k] >= c.table_energy[k - 1])))
+                    return fail(ELISA_ERR_INVALID,
+                                "model: cross-section table must be positive with non-decreasing energies");
+            }
+            if (!(c.table_energy[c.table_len - 1] > c.table_energy[0]))
+                return fail(ELISA_ERR_INVALID, "model: cross-section table spans no energy range");
         }
     }
     // postfix program; a single component may omit it
@@ -993,14 +998,17 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
         const int n = c.table_len;
         std::vector<double> xp(n), fp(n);
         for (int k = 0; k < n; ++k) {
-            xp[k] = log(c.table_energy[k]);
-            fp[k] = log(c.table_xsect[k]);
+            xp[k] = c.table_log ? c.table_energy[k] : log(c.table_energy[k]);
+            fp[k] = c.table_log ? c.table_xsect[k] : log(c.table_xsect[k]);
         }
         auto sigma = [&](double lx) {
             int j = (int)(std::upper_bound(xp.begin(), xp.end(), lx) - xp.begin()) - 1;  // xp[j] <= lx < xp[j+1]
             j = std::max(0, std::min(j, n - 2));                                          // end segments extrapolate
-            const double t = (lx - xp[j]) / (xp[j + 1] - xp[j]);
-            return exp(fp[j] + t * (fp[j + 1] - fp[j]));
+            const double dx = xp[j + 1] - xp[j];
+            // repeated table energies: only a clipped end segment can have zero width; jnp.interp
+            // returns the left value there (jax/_src/numpy/lax_numpy.py, the dx0 branch)
+            if (fabs(dx) <= 4.9303806576313238e-32) return exp(fp[j]);
+            return exp(fp[j] + ((lx - xp[j]) / dx) * (fp[j + 1] - fp[j]));
         };
         // the component sees the grid scaled by the energy shifts around it
         auto tables = [&](const std::vector<double>& g, double gs, double** edges, double** mids) -> int {

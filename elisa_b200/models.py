@@ -237,25 +237,52 @@ class PhotonAbsorption(Component):
 
     def __init__(self, table_energy, table_xsect, nH=None, method: str | None = None):
         super().__init__(nH=nH, method=method)
-        e = np.ascontiguousarray(table_energy, dtype=np.float64)
-        x = np.ascontiguousarray(table_xsect, dtype=np.float64)
+        e, x = np.asarray(table_energy), np.asarray(table_xsect)
+        if e.dtype.kind != 'f':
+            e = e.astype(np.float64)
+        if x.dtype.kind != 'f':
+            x = x.astype(np.float64)
         if e.ndim != 1 or e.shape != x.shape or e.size < 2:
             raise ValueError('cross-section table: two 1-d arrays of equal length >= 2')
-        if not (np.all(e > 0) and np.all(np.diff(e) > 0) and np.all(x > 0)):
-            raise ValueError('cross-section table: positive values, increasing energies')
+        if not (np.all(e > 0) and np.all(np.diff(e) >= 0) and e[-1] > e[0] and np.all(x > 0)):
+            raise ValueError('cross-section table: positive values, non-decreasing energies')
         self.table_energy, self.table_xsect = e, x
+        # `_make_interp` (mul.py:275-276) takes np.log of the arrays AS STORED: the float32
+        # datasets of xsect.hdf5 give float32 logarithms, promoted to float64 by jnp.interp
+        self.table_log_energy = np.ascontiguousarray(np.log(e), dtype=np.float64)
+        self.table_log_xsect = np.ascontiguousarray(np.log(x), dtype=np.float64)
+
+    @classmethod
+    def from_tables(cls, path, abund=None, xsect=None, nH=None, method: str | None = None):
+        """The component as the reference builds it, ``PhAbs(nH, abund=..., xsect=...)``
+        (models/mul.py:302-339, 429-640), from the reference's ``models/tables/xsect.hdf5``
+        read by ``elisa_b200.tables`` (no h5py)."""
+        from .tables import load_xsect
+
+        which = cls.__name__.lower()
+        if which not in ('phabs', 'tbabs', 'wabs'):
+            raise TypeError('from_tables: use PhAbs, TBAbs or WAbs')
+        t = load_xsect(path, dtype=None)
+        abund = cls._default_abund if abund is None else abund
+        xsect = cls._default_xsect if xsect is None else xsect
+        try:
+            sigma = t[which][xsect][abund]
+        except KeyError:
+            have = {xs: sorted(t[which][xs]) for xs in t.get(which, {})}
+            raise ValueError(f'{which}: no table for xsect={xsect!r}, abund={abund!r}; available: {have}') from None
+        return cls(t['energy'], sigma, nH=nH, method=method)
 
 
 class PhAbs(PhotonAbsorption):  # models/mul.py:429-511
-    pass
+    _default_abund, _default_xsect = 'angr', 'vern'
 
 
 class TBAbs(PhotonAbsorption):  # models/mul.py:514-585
-    pass
+    _default_abund, _default_xsect = 'wilm', 'vern'
 
 
 class WAbs(PhotonAbsorption):  # models/mul.py:588-640
-    pass
+    _default_abund, _default_xsect = 'aneb', 'wabs'
 
 
 # --------------------------------------------------------------------------- convolution components
@@ -468,9 +495,10 @@ class CompiledModel:
                     d.param_src[k] = j
             d.aux[0], d.aux[1] = c.aux
             if isinstance(c, PhotonAbsorption):
-                d.table_energy = c.table_energy.ctypes.data_as(_lib.c_double_p)
-                d.table_xsect = c.table_xsect.ctypes.data_as(_lib.c_double_p)
-                d.table_len = c.table_energy.size
+                d.table_energy = c.table_log_energy.ctypes.data_as(_lib.c_double_p)
+                d.table_xsect = c.table_log_xsect.ctypes.data_as(_lib.c_double_p)
+                d.table_len = c.table_log_energy.size
+                d.table_log = 1
         ops = (_lib.C.c_int32 * len(self.ops))(*self.ops)
         norms = (_lib.NormDesc * max(len(self.norms), 1))()
         grids = []

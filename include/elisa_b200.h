@@ -135,12 +135,19 @@ typedef struct ElisaComponentDesc {
     double aux[2]; /* PLPhFlux / PLEnFlux: emin, emax (add.py:662-680)               */
     /* ELISA_COMP_PHOTONABS: one cross-section table of the reference's tables/xsect.hdf5
      * (its 'energy' dataset and '{phabs|tbabs|wabs}/{xsect}/{abund}'), table_len >= 2
-     * increasing positive energies; NULL / 0 for every other kind.  The plan evaluates
+     * non-decreasing positive energies; NULL / 0 for every other kind.  The plan evaluates
      * sigma on the photon grid at creation exactly as mul.py:274-283 does
      * (exp(interp(log e, log energy, log xsect)) with linear extrapolation).          */
     const double* table_energy;
     const double* table_xsect;
     int32_t table_len;
+    /* 1: the two arrays already hold ln(energy), ln(xsect) -- what `_make_interp` keeps
+     * (mul.py:275-276).  The reference takes np.log of the float32 datasets of xsect.hdf5, i.e.
+     * FLOAT32 logarithms promoted to float64 afterwards; a binding that wants its numbers
+     * reproduces that rounding on its side and passes the result here.  Energies may repeat
+     * (the float32 table has 87 duplicates): jnp.interp never selects a zero-width segment
+     * except at the clipped ends, where it returns the left value.                       */
+    int32_t table_log;
     /* Energy shifts ZAShift / ZMShift / VAShift / VMShift with a FIXED z or v
      * (models/conv.py:294-300, 335-341, 378-386, 424-432): the component is evaluated on
      * photon_egrid * grid_scale (the product of the factors 1 + z, 1 - v/c of the shifts

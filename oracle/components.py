@@ -249,15 +249,19 @@ def _make_interp(table_energy, table_xsect):
     left='extrapolate', right='extrapolate')).  jnp.interp: i = clip(searchsorted(xp, x,
     'right'), 1, n - 1); f = fp[i-1] + (x - xp[i-1]) / (xp[i] - xp[i-1]) * (fp[i] - fp[i-1]);
     'extrapolate' keeps that line outside [xp[0], xp[-1]]."""
-    xp = torch.log(torch.as_tensor(np.asarray(table_energy, dtype=np.float64)))
-    fp = torch.log(torch.as_tensor(np.asarray(table_xsect, dtype=np.float64)))
+    # np.log of the arrays AS STORED (mul.py:275-276): float32 tables give float32 logarithms,
+    # which jnp.interp then promotes to float64
+    xp = torch.as_tensor(np.log(np.asarray(table_energy)).astype(np.float64))
+    fp = torch.as_tensor(np.log(np.asarray(table_xsect)).astype(np.float64))
+    eps = float(np.spacing(np.finfo(np.float64).eps))
 
     def interp(e):
         x = torch.log(e)
         i = torch.clamp(torch.searchsorted(xp, x.contiguous(), right=True), 1, xp.numel() - 1)
         df = fp[i] - fp[i - 1]
         dx = xp[i] - xp[i - 1]
-        return torch.exp(fp[i - 1] + ((x - xp[i - 1]) / dx) * df)
+        dx0 = dx.abs() <= eps  # repeated table energies (jnp.interp's dx0 branch)
+        return torch.exp(torch.where(dx0, fp[i - 1], fp[i - 1] + ((x - xp[i - 1]) / torch.where(dx0, 1.0, dx)) * df))
 
     return interp
 

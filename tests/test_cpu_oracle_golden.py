@@ -203,6 +203,12 @@ def test_photon_absorption_matches_reference_source():
                                                    table_energy=g['table_energy'], table_xsect=g['table_xsect'])
             ref = g[f'{gname}_{method}']
             assert np.allclose(out.numpy(), ref, rtol=1e-13, atol=1e-300), (gname, method)
+            # float32 table with repeated energies (the storage of the reference's xsect.hdf5)
+            out = oracle.components.eval_component('PhotonAbsorption', eg, {'nH': nH}, method=method,
+                                                   table_energy=g['table32_energy'], table_xsect=g['table32_xsect'])
+            ref = g[f'f32_{gname}_{method}']
+            assert np.allclose(out.numpy(), ref, rtol=1e-13, atol=1e-300), ('f32', gname, method)
+            assert not np.allclose(ref, g[f'{gname}_{method}'], rtol=1e-7, atol=0)  # the float32 log matters
 
 
 def _conv_cases():
@@ -255,3 +261,54 @@ def test_convolution_host_rules():
     pl = M.PowerLaw()
     cm = (pl + M.ZAShift(z=1.0)(pl)).compile()
     assert cm.nparam == 2 and len(cm.entries) == 2 and cm.ops == [0, 1, -1]
+
+
+REF_TABLES = '/root/reference/src/elisa/models/tables/xsect.hdf5'
+
+
+def test_hdf5_reader_rejects_what_it_does_not_read(tmp_path):
+    from elisa_b200.tables import read_hdf5
+
+    p = tmp_path / 'x.hdf5'
+    p.write_bytes(b'not an hdf5 file at all')
+    with pytest.raises(ValueError):
+        read_hdf5(p)
+    p.write_bytes(b'\x89HDF\r\n\x1a\n' + bytes([2]) + bytes(64))  # version-2 superblock
+    with pytest.raises(NotImplementedError):
+        read_hdf5(p)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TABLES), reason='the reference tree is only present in the build container')
+def test_hdf5_reader_on_the_reference_tables():
+    """models/tables/xsect.hdf5 read without h5py: 38 float32 datasets; the energy dataset is
+    checked against an independent reconstruction from the recipe in
+    tables/generate_xsect_table.py (geomspace(0.1, 20, 10000) refined around three edges)."""
+    from elisa_b200 import models as M
+    from elisa_b200.tables import load_xsect, read_hdf5
+
+    flat = read_hdf5(REF_TABLES)
+    assert len(flat) == 38 and all(a.dtype == np.float32 and a.shape == flat['energy'].shape for a in flat.values())
+    e = flat['energy'].astype(np.float64)
+    eg = np.geomspace(0.1, 20.0, 10000)
+    extra = [np.geomspace(eg[i], eg[j], (j - i) * 5 + 1) for i, j in [[3123, 3155], [3182, 3219], [3202, 3215]]]
+    eg = np.unique(np.hstack([eg, *extra]))
+    idx = np.clip(np.searchsorted(eg, e), 1, eg.size - 1)
+    near = np.where(np.abs(eg[idx] - e) < np.abs(eg[idx - 1] - e), eg[idx], eg[idx - 1])
+    assert np.max(np.abs(near / e - 1.0)) < 1e-7  # every stored energy is a float32 rounding of the recipe's
+    idx = np.clip(np.searchsorted(e, eg), 1, e.size - 1)
+    near = np.where(np.abs(e[idx] - eg) < np.abs(e[idx - 1] - eg), e[idx], e[idx - 1])
+    assert np.max(np.abs(near / eg - 1.0)) < 1e-7  # and every recipe energy is stored
+    assert np.all(np.diff(e) >= 0) and np.sum(np.diff(e) == 0) == 87
+    t = load_xsect(REF_TABLES)
+    assert sorted(k for k in t if k != 'energy') == ['phabs', 'tbabs', 'wabs']
+    assert sorted(t['phabs']) == ['bcmc', 'obcm', 'vern'] and len(t['phabs']['vern']) == 9
+    assert all(np.all(a > 0) for m in ('phabs', 'tbabs', 'wabs') for xs in t[m].values() for a in xs.values())
+    # photo-electric absorption: at 0.1 keV of order 1e2 - 1e3 x 1e-22 cm^2 per H, four decades less at 20 keV
+    s = t['phabs']['vern']['angr']
+    assert 1e2 < s[0] < 1e4 and 1e-4 < s[-1] < 1e-1
+    for cls in (M.PhAbs, M.TBAbs, M.WAbs):  # the reference's default abund / xsect of each class
+        c = cls.from_tables(REF_TABLES)
+        assert c.table_energy.dtype == np.float32 and c.table_log_energy.dtype == np.float64
+        assert np.array_equal(c.table_log_energy, np.log(flat['energy']).astype(np.float64))
+    with pytest.raises(ValueError):
+        M.PhAbs.from_tables(REF_TABLES, abund='nope')

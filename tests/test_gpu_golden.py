@@ -78,3 +78,9 @@ def test_photon_absorption_eval_matches_reference_source(lib, cls):
             out = comp.compile().eval(g[f'grid_{gname}'], g['nH'][:, None])
             ref = g[f'{gname}_{method}']
             assert np.allclose(out, ref, rtol=2e-13, atol=1e-300), (gname, method, np.abs(out - ref).max())
+            # the float32 table with repeated energies, as the reference's xsect.hdf5 stores it:
+            # float32 logarithms (1e-5 away from the float64 ones) and jnp.interp's dx0 branch
+            comp = getattr(M, cls)(g['table32_energy'], g['table32_xsect'], method=method)
+            out = comp.compile().eval(g[f'grid_{gname}'], g['nH'][:, None])
+            ref = g[f'f32_{gname}_{method}']
+            assert np.allclose(out, ref, rtol=2e-13, atol=1e-300), ('f32', gname, method, np.abs(out - ref).max())

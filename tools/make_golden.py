@@ -421,7 +421,8 @@ def photonabs_fixture(ref: RefModel):
         df = fp[i] - fp[i - 1]
         dx = xp[i] - xp[i - 1]
         delta = x - xp[i - 1]
-        return fp[i - 1] + (delta / dx) * df
+        dx0 = np.abs(dx) <= np.spacing(np.finfo(np.float64).eps)
+        return np.where(dx0, fp[i - 1], fp[i - 1] + (delta / np.where(dx0, 1, dx)) * df)
 
     jnp.interp = interp
     tree = ast.parse(_src('models/mul.py'))
@@ -445,6 +446,17 @@ def photonabs_fixture(ref: RefModel):
         for method in ('trapz', 'simpson'):
             fn = ref.make_integral(method, 'mul', continuum)
             out[f'{gname}_{method}'] = np.stack([np.asarray(fn(_a(g), {'nH': np.float64(v)})) for v in nH])
+    # as the reference's own table file: FLOAT32 datasets (np.log of them is a float32 log,
+    # mul.py:275-276) with repeated energies (xsect.hdf5 has 87), here also at the upper end
+    idx = np.sort(np.concatenate([np.arange(energy.size), [17, 18, 140, energy.size - 1]]))
+    e32, x32 = energy.astype(np.float32)[idx], xsect.astype(np.float32)[idx]
+    assert e32.dtype == np.float32 and np.log(e32).dtype == np.float32 and np.sum(np.diff(e32) == 0) == 4
+    cont.__globals__['_XSECT_INTERP'] = {'phabs': {'vern': {'angr': make_interp(e32, x32)}}}
+    out['table32_energy'], out['table32_xsect'] = e32, x32
+    for gname, g in grids.items():
+        for method in ('trapz', 'simpson'):
+            fn = ref.make_integral(method, 'mul', continuum)
+            out[f'f32_{gname}_{method}'] = np.stack([np.asarray(fn(_a(g), {'nH': np.float64(v)})) for v in nH])
     return out
 
 
