@@ -676,6 +676,7 @@ struct SpectrumPlan {
     bool use_i8() const { return i8_fwd.img != nullptr; }
     int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
     int64_t nnz = 0;
+    double fill = 1.0;  // stored fraction of the packed response operands
     const struct JitKernels* jit = nullptr;  // runtime-specialised unfold (nullptr: interpreter)
     GridView grid_view() const {
         GridView g{egrid, lngrid, emid, lnmid, E};
@@ -1152,6 +1153,12 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
     }
     if ((rc = upload_packed(plan, fwd, &sp->fwd))) return rc;
     if ((rc = upload_packed(plan, bwd, &sp->bwd))) return rc;
+    {  // fraction of the two operands that is stored (1 for a dense response)
+        double stored = 0.0;
+        for (size_t j = 0; j < fwd.k_lo.size(); ++j) stored += std::max(0, fwd.k_hi[j] - fwd.k_lo[j]);
+        for (size_t j = 0; j < bwd.k_lo.size(); ++j) stored += std::max(0, bwd.k_hi[j] - bwd.k_lo[j]);
+        sp->fill = stored / ((double)fwd.k_lo.size() * E + (double)bwd.k_lo.size() * C);
+    }
     return ELISA_OK;
 }
 
@@ -2179,7 +2186,18 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                 break;
             }
         }
-        if (plan->ks > 0 && plan->spec[s].E <= I8_MAX_K && plan->spec[s].C <= I8_MAX_K) {
+        // A narrow band-sparse response leaves the folds little to do, and the sliced-integer
+        // engine still slices whole rows of U and W: below ~5 % stored the DMMA fold, which reads
+        // them as they are, is the faster one (cfg 4, 2.7 % stored: 5.6e6 vs 5.1e6 evals/s).
+        const bool sparse_prefers_dmma = !force_i8 && plan->spec[s].fill < 0.05;
+        // A contraction shorter than one 64-wide tile (a heavily grouped spectrum, C < 64, or a
+        // coarse photon grid) gives the integer engine nothing to gain -- it pads to 128-deep
+        // k-blocks -- and takes away the averaging over the contraction index its normwise error
+        // model leans on (a 30 x 6 pgstat case far from the optimum: gradient off by 1.3e-10 with
+        // a guard estimate of 6e-12).  Such spectra keep the DMMA fold.
+        const bool tiny_prefers_dmma = !force_i8 && std::min(plan->spec[s].E, plan->spec[s].C) < 64;
+        if (plan->ks > 0 && !sparse_prefers_dmma && !tiny_prefers_dmma && plan->spec[s].E <= I8_MAX_K &&
+            plan->spec[s].C <= I8_MAX_K) {
             if ((rc = build_spectrum_i8(plan, desc->spectra[s], &plan->spec[s], plan->ks))) break;
             any_i8 = true;
         } else if (plan->ks > 0 && force_i8) {

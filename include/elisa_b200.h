@@ -231,10 +231,14 @@ typedef struct ElisaPlanDesc {
  * `slices` balanced base-256 digits, digit products on the int8 tcgen05 tensor cores with
  * exact int32 accumulation in TMEM, recombined in FP64: FP64-class accuracy (normwise
  * ~2^(-8 slices + 3); 6 slices hold the 1e-10 tolerance of the statistic and gradient) at
- * several times the FP64 DMMA rate.  ELISA_FLAG_FOLD_DMMA / env ELISA_B200_FOLD=dmma
+ * several times the FP64 DMMA rate.  By default a spectrum whose packed response is under
+ * 5 % stored (narrow band-sparse RSPs), or with fewer than 64 energies or channels, keeps
+ * the DMMA fold, which is as fast or faster there;
+ * elisa_b200_plan_fold_slices() tells which engine each spectrum got.
+ * ELISA_FLAG_FOLD_DMMA / env ELISA_B200_FOLD=dmma
  * selects the native FP64 DMMA fold (csrc/gemm_f64.cuh); ELISA_FLAG_FOLD_I8 / env
  * ELISA_B200_FOLD=i8 makes a spectrum the integer fold cannot take (E or C > 16384) an
- * error instead of a silent DMMA fold, and switches off the guard fallback of the "_host"
+ * error instead of a silent DMMA fold, overrides the 5 % rule, and switches off the guard fallback of the "_host"
  * entry point (see elisa_b200_plan_fold_guard).  Slices: bits 8-11 of flags (4..7; 0 = default 6;
  * 4 is an FP32-class variant, ~1e-6) or env ELISA_B200_FOLD_SLICES.                       */
 #define ELISA_FLAG_FOLD_DMMA 4

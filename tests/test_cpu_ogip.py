@@ -1,0 +1,94 @@
+"""Response / spectrum ingest against golden FixedData produced by
+the reference's own `elisa.data.ogip.Data(...).get_fixed_data()` on the synthetic OGIP files of
+tests/ogip_cases.py (tools/make_golden.py --ogip)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import ogip_cases
+from elisa_b200.fitsio import read_fits
+from elisa_b200.ogip import load_data, read_response, read_spectrum
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'ogip.npz')
+CASES = ['a_varlen_arf_back_grouped', 'a_keep_dubious', 'a_no_background_sparse', 'b_fixed_rsp_rate_net',
+         'c_type2_row2_gaussian_back']
+
+
+@pytest.fixture(scope='module')
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp('ogip')
+    return str(d), ogip_cases.build(str(d))
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_fixed_data_matches_reference(files, case, monkeypatch):
+    tmp, cases = files
+    monkeypatch.chdir(tmp)
+    g = np.load(GOLD)
+    kw = {k: v for k, v in cases[case].items() if not k.startswith('_')}
+    d = load_data(**kw)
+    checked = 0
+    for f in ogip_cases.FIELDS:
+        key = f'{case}/{f}'
+        if key not in g.files:
+            assert getattr(d, f, None) is None, f
+            continue
+        mine = d.dense_response() if f == 'response_matrix' else getattr(d, f)
+        mine, ref = np.asarray(mine, dtype=np.float64), g[key]
+        assert mine.shape == ref.shape, (f, mine.shape, ref.shape)
+        assert np.allclose(mine, ref, rtol=1e-14, atol=0.0), (f, float(np.max(np.abs(mine - ref))))
+        checked += 1
+    assert checked >= 10
+    assert np.allclose(d.dense_response(), g[f'{case}/sparse_dense'], rtol=1e-14, atol=0.0)
+    assert d.response_sparse == bool(kw.get('sparse_response', False))
+
+
+def test_file_names_from_the_header_and_errors(files, monkeypatch):
+    tmp, cases = files
+    monkeypatch.chdir('/')
+    g = np.load(GOLD)
+    # BACKFILE / RESPFILE / ANCRFILE keywords resolved next to the spectrum
+    d = load_data([(0.5, 3.0), (4.0, 11.0)], os.path.join(tmp, 'a_src.pha'))
+    assert np.array_equal(d.net_counts, g['a_varlen_arf_back_grouped/net_counts'])
+    with pytest.raises(ValueError):  # type II needs a row
+        read_spectrum(os.path.join(tmp, 'c_ii.pha'))
+    with pytest.raises(ValueError):  # no RESPFILE in the header, none given
+        load_data([(1.0, 5.0)], os.path.join(tmp, 'b_net.pha'))
+    with pytest.raises(ValueError):
+        load_data([(5.0, 1.0)], os.path.join(tmp, 'a_src.pha'))
+    with pytest.raises(ValueError):  # channel numbers do not match
+        load_data([(1.0, 5.0)], os.path.join(tmp, 'a_src.pha'), respfile=os.path.join(tmp, 'b.rsp'))
+    with pytest.raises(RuntimeError):
+        load_data([(100.0, 200.0)], os.path.join(tmp, 'a_src.pha'))
+
+
+def test_response_decode_details(files):
+    tmp, _ = files
+    r = read_response(os.path.join(tmp, 'a.rmf'))
+    E, C = r.shape
+    assert (E, C) == (60, 48) and r.channel[0] == '0' and r.channel_type == 'PI'
+    assert not np.any(r.rows == 0) and not np.any(r.rows == 7)      # energies without a group
+    assert np.all(r.values != 0.0)                                   # explicit zeros dropped
+    hdu = [h for h in read_fits(os.path.join(tmp, 'a.rmf')) if h.name == 'MATRIX'][0]
+    assert isinstance(hdu['MATRIX'], list) and hdu['N_GRP'].dtype == np.int16
+    b = read_response(os.path.join(tmp, 'b.rsp'))
+    assert b.channel[0] == '1' and b.photon_egrid[0] == pytest.approx(0.001 * b.photon_egrid[1])  # zero edge lifted
+    assert b.photon_egrid[-1] == pytest.approx(20.0, rel=1e-6) and b.channel_type == 'PHA'         # eV -> keV
+
+
+HXMT = '/root/reference/docs/notebooks/data'
+
+
+@pytest.mark.skipif(not os.path.isdir(HXMT), reason='the reference tree is only present in the build container')
+def test_hxmt_sample_files():
+    """The mission files the reference's notebooks use (Insight-HXMT LE / ME / HE)."""
+    for det, C, E in (('HE', 256, 485), ('ME', 1024, 660)):
+        d = load_data([(1.0, 300.0)], f'{HXMT}/P011160506306_{det}_TOTAL.fits', backfile=f'{HXMT}/P011160506306_{det}_BKG.fits',
+                      respfile=f'{HXMT}/P011160506306_{det}_RSP.fits', name=det)
+        assert d.n_energies == E and 0 < d.n_channels <= C
+        R = d.dense_response()
+        assert np.all(np.isfinite(R)) and R.sum() > 0 and R.min() > -1e-3 * R.max()  # mission RSPs carry small negatives
+        assert np.all(np.isfinite(d.back_ratio)) and np.all(d.back_ratio > 0)
+        assert np.all(d.spec_counts >= 0) and np.all(d.net_errors >= 0)

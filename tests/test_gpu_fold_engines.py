@@ -205,3 +205,32 @@ def test_small_batches_replay_a_cuda_graph_with_identical_results(lib, fold, mon
     ll, g = lk.loglike_and_grad(thetas[0][:7])  # another shape: its own graph
     assert torch.equal(ll, ref[0][0][:7]) and torch.equal(g, ref[0][1][:7])
     lk.close()
+
+
+def test_narrow_band_sparse_response_keeps_the_dmma_fold(lib):
+    """Default engine choice: under 5 % stored (cfg 4's CCD-like RSP: 2.7 %) the plan stays on the
+    DMMA fold; fold='i8' overrides; both agree with the oracle."""
+    from elisa_b200 import Likelihood
+    from parity import RTOL, compare
+
+    cfg = synthetic.config4(n=40, size=4096)
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'])
+    assert lk.fold_slices == [0]
+    lk.close()
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold='i8')
+    assert lk.fold_slices == [6]
+    lk.close()
+    dense = small_config(2)
+    lk = Likelihood(dense['data'], dense['model'], dense['stat'])
+    assert all(s == 6 for s in lk.fold_slices)
+    lk.close()
+    tiny = _one_spectrum(E=70, C=40)  # fewer than 64 channels: nothing for the integer engine to gain
+    lk = Likelihood([tiny], M.PowerLaw(), ['cstat'])
+    assert lk.fold_slices == [0]
+    lk.close()
+    lk = Likelihood([tiny], M.PowerLaw(), ['cstat'], fold='i8')
+    assert lk.fold_slices == [6]
+    lk.close()
+    for fold in (None, 'i8'):
+        err = compare(cfg, fold=fold) if fold else compare(cfg)
+        assert err['value'] <= RTOL and err['grad'] <= RTOL, (fold, err)

@@ -20,7 +20,7 @@ of those same reference functions.
 Run in the BUILD container only (needs /root/reference); the fixtures are committed and
 travel to the GPU box, this script's input does not.
 
-    python tools/make_golden.py [--photonabs | --conv]
+    python tools/make_golden.py [--photonabs | --conv | --ogip]
 """
 
 from __future__ import annotations
@@ -520,7 +520,129 @@ def conv_fixture(ref: RefModel):
     return out
 
 
+def ogip_fixture():
+    """tests/ogip_cases.py read by the reference's own `elisa.data.ogip.Data` (data/ogip.py,
+    data/base.py, data/grouping.py imported UNMODIFIED from /root/reference) and frozen with
+    `get_fixed_data()`.  astropy is not installable here: `astropy.io.fits` is replaced by a
+    facade over elisa_b200.fitsio (header dict + column access -- the decode of the columns into
+    a matrix, the grouping, masks, scales and ratios are all the reference's code), and
+    `astropy.units.Unit(u).to('keV')` by a table of the energy units."""
+    import tempfile
+
+    sys.path.insert(0, os.path.dirname(OUT))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    import ogip_cases
+    from elisa_b200.fitsio import read_fits
+
+    class Rec:  # the slice of the FITS_rec interface data/ogip.py uses
+        def __init__(self, hdu, rows=None):
+            self.hdu, self.rows = hdu, rows
+            self.names = list(hdu.names)
+
+        def __len__(self):
+            return len(self.hdu) if self.rows is None else len(range(len(self.hdu))[self.rows])
+
+        def __getitem__(self, key):
+            if isinstance(key, slice):
+                return Rec(self.hdu, key)
+            col = self.hdu[key]
+            if isinstance(col, list):
+                arr = np.empty(len(col), dtype=object)
+                arr[:] = col
+                col = arr
+            return col if self.rows is None else col[self.rows]
+
+    class FakeHDU:
+        def __init__(self, h):
+            self.name, self.ver, self.header = h.name, h.ver, h.header
+            self.data = Rec(h) if h.names else None
+
+    class HDUList(list):
+        def __contains__(self, name):
+            return any(h.name == name for h in self)
+
+        def __getitem__(self, key):
+            if isinstance(key, tuple):
+                return next(h for h in self if h.name == key[0] and h.ver == key[1])
+            if isinstance(key, str):
+                return next(h for h in self if h.name == key)
+            return list.__getitem__(self, key)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    fits = types.ModuleType('astropy.io.fits')
+    fits.open = lambda f: HDUList(FakeHDU(h) for h in read_fits(f))
+    fits.Header = dict
+    units = types.ModuleType('astropy.units')
+    to_kev = {'ev': 1e-3, 'kev': 1.0, 'mev': 1e3}
+    units.Unit = lambda u: types.SimpleNamespace(to=lambda target: to_kev[u.lower()] / to_kev[target.lower()])
+    astropy, aio = types.ModuleType('astropy'), types.ModuleType('astropy.io')
+    astropy.io, astropy.units, aio.fits = aio, units, fits
+    mpl, plt = types.ModuleType('matplotlib'), types.ModuleType('matplotlib.pyplot')
+    mpl.pyplot = plt
+    plt.Figure = object
+    stubs = {'astropy': astropy, 'astropy.io': aio, 'astropy.io.fits': fits, 'astropy.units': units,
+             'matplotlib': mpl, 'matplotlib.pyplot': plt}
+    # the package skeleton: only data/{grouping,base,ogip}.py run, from the reference tree
+    for name in ('elisa', 'elisa.data', 'elisa.plot', 'elisa.plot.misc', 'elisa.util', 'elisa.util.misc'):
+        stubs[name] = types.ModuleType(name)
+    stubs['elisa.plot.misc'].get_colors = lambda *a, **k: []
+    tree = ast.parse(_src('util/misc.py'))
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'to_native_byteorder'][0]
+    stubs['elisa.util.misc'].to_native_byteorder = _exec_function(fn, {'np': np})
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        mods = {}
+        for name in ('grouping', 'base', 'ogip'):
+            spec = importlib.util.spec_from_file_location(f'elisa.data.{name}', os.path.join(REF, 'data', f'{name}.py'))
+            mods[name] = importlib.util.module_from_spec(spec)
+            sys.modules[f'elisa.data.{name}'] = mods[name]
+            spec.loader.exec_module(mods[name])
+        Data = mods['ogip'].Data
+        out = {}
+        import warnings
+
+        with tempfile.TemporaryDirectory() as tmp:
+            cwd = os.getcwd()
+            os.chdir(tmp)  # BACKFILE / RESPFILE keywords are resolved relative to the working directory
+            try:
+                for case, kw in ogip_cases.build(tmp).items():
+                    kw = {k: v for k, v in kw.items() if not k.startswith('_')}
+                    with warnings.catch_warnings():
+                        warnings.simplefilter('ignore')
+                        fd = Data(**kw).get_fixed_data()
+                    for f in ogip_cases.FIELDS:
+                        v = getattr(fd, f)
+                        if v is not None:
+                            out[f'{case}/{f}'] = np.asarray(v, dtype=np.float64)
+                    coo = fd.sparse_matrix
+                    out[f'{case}/sparse_dense'] = np.asarray(coo.todense(), dtype=np.float64)
+                    out[f'{case}/channel'] = np.asarray(fd.channel, dtype=str)
+            finally:
+                os.chdir(cwd)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for name in ('grouping', 'base', 'ogip'):
+            sys.modules.pop(f'elisa.data.{name}', None)
+    return out
+
+
 def main():
+    if '--ogip' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        og = ogip_fixture()
+        np.savez_compressed(os.path.join(OUT, 'ogip.npz'), **og)
+        print('ogip.npz:', len(og), 'arrays,', os.path.getsize(os.path.join(OUT, 'ogip.npz')), 'bytes')
+        return
     ref = RefModel()
     os.makedirs(OUT, exist_ok=True)
     if '--conv' in sys.argv or '--all' in sys.argv or len(sys.argv) == 1:
