@@ -127,6 +127,7 @@ SYMBOLS = {
     'elisa_b200_plan_fold_guard': (C.c_int, [_VP, C.POINTER(C.c_int64), c_double_p, C.c_int]),
     'elisa_b200_sliced_gemm_dev': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             _VP, C.c_int64, c_double_p, _VP]),
+    'elisa_b200_plan_rebalance': (C.c_int, [_VP]),
     'elisa_b200_abi_version': (C.c_int, []),
     'elisa_b200_sizeof': (C.c_int64, [C.c_int32]),
     'elisa_b200_last_error': (C.c_char_p, []),

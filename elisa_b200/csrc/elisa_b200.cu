@@ -647,6 +647,8 @@ struct PackedDevice {
 
 // Static (B) operand of the sliced-integer fold: digit images per (64-row tile, k-block).
 struct I8Operand {
+    double* dense = nullptr;      // [rows, K] FP64 copy the digits are (re)sliced from (balancing)
+    int rows = 0, K = 0;
     int8_t* img = nullptr;
     double* abs_sum = nullptr;    // [n_tiles * 64] sum_k |row| (accuracy guard)
     double* scale = nullptr;      // [n_tiles * 64]
@@ -677,6 +679,11 @@ struct SpectrumPlan {
     int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
     int64_t nnz = 0;
     double fill = 1.0;  // stored fraction of the packed response operands
+    // balancing of the integer folds' contraction indices (col_envelope_kernel): power-of-two
+    // envelopes of U over the energies / of W over the channels, and their reciprocals
+    double *t_scale = nullptr, *t_inv = nullptr, *r_scale = nullptr, *r_inv = nullptr;
+    uint8_t *t_exp = nullptr, *r_exp = nullptr;  // log2 of t_inv / r_inv
+    bool balanced_fwd = false, balanced_bwd = false;
     const struct JitKernels* jit = nullptr;  // runtime-specialised unfold (nullptr: interpreter)
     GridView grid_view() const {
         GridView g{egrid, lngrid, emid, lnmid, E};
@@ -733,6 +740,8 @@ struct ElisaPlan {
     bool guard_off = false;   // ELISA_FLAG_FOLD_I8: the caller asked for the integer fold, unguarded
     int64_t guard_fallbacks = 0;
     bool force_dmma = false;  // evaluate with the FP64 DMMA fold although the integer operands exist (guard fallback)
+    bool balance = true;      // balance the integer folds around the first batch seen (ELISA_B200_BALANCE=0: off)
+    double* cal_ll = nullptr; // [128 * S] log-likelihoods of the pilot rows (scratch)
     int ld_part = 0;  // leading dimension (rows) of the part / gpart arrays in use
     // Joint fits: inside the captured graph every spectrum runs on its own branch (own stream
     // during capture, own small workspace), so the S kernel chains of a small batch overlap
@@ -1462,6 +1471,7 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.kb_total = round_up(ld, I8_BK) / I8_BK;
     a.img = nullptr;
     a.scale = nullptr;
+    a.kexp = sp.balanced_fwd ? sp.t_exp : nullptr;
     a.gv.has_point = 0;
     for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
         a.ngv[k] = sp.norm_view(k);
@@ -1693,18 +1703,23 @@ static int build_i8_operand(ElisaPlan* plan, int ks, const std::vector<double>& 
         a.kb_hi = out->kb_hi;
         a.img = out->img;
         a.scale = out->scale;
+        a.kscale = nullptr;
+        a.abs_sum = nullptr;
         const bool prof = plan->profiling;
         plan->profiling = false;
         rc = launch_slice(plan, ks, a, ELISA_PROFILE_REDUCE, nullptr);
         plan->profiling = prof;
         if (rc == ELISA_OK) e = cudaDeviceSynchronize();
     }
-    cudaFree(tmp);
+    plan->owned.push_back(tmp);  // kept: the operand is re-sliced with column scales when the fold is balanced
+    out->dense = tmp;
+    out->rows = rows;
+    out->K = K;
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ELISA_ERR_CUDA, std::string("slicing the response failed: ") + cudaGetErrorString(e));
     out->n_tiles = n_tiles;
     out->n_images = n_images;
-    plan->workspace_bytes += (int64_t)img_bytes;
+    plan->workspace_bytes += (int64_t)img_bytes + (int64_t)dense.size() * 8;
     return ELISA_OK;
 }
 
@@ -1741,7 +1756,7 @@ static int launch_stat_slice_any(ElisaPlan* plan, const SpectrumPlan& sp, const 
 
 // digits of the per-chunk A operand X [n_rows, ld] (U or W) into plan->A_img / a_scale
 static int slice_chunk_operand(ElisaPlan* plan, const double* X, int ld, int cols, int n_valid, int m_tiles, int cls,
-                               cudaStream_t st) {
+                               cudaStream_t st, const double* kscale = nullptr) {
     SliceArgs a;
     a.X = X;
     a.ld = ld;
@@ -1755,15 +1770,39 @@ static int slice_chunk_operand(ElisaPlan* plan, const double* X, int ld, int col
     a.kb_hi = nullptr;
     a.img = plan->A_img;
     a.scale = plan->a_scale;
+    a.kscale = kscale;
+    a.abs_sum = nullptr;
     return launch_slice(plan, plan->ks, a, cls, st);
+}
+
+// Re-slice a static operand with column scales (balancing); same images, ranges and buffers.
+static int reslice_operand(ElisaPlan* plan, const I8Operand& op, const double* kscale, cudaStream_t st) {
+    SliceArgs a;
+    a.X = op.dense;
+    a.ld = op.K;
+    a.rows = op.rows;
+    a.cols = op.K;
+    a.row_tiles = op.n_tiles;
+    a.tile_rows = I8_BN;
+    a.kb_total = round_up(op.K, I8_BK) / I8_BK;
+    a.tile_img = op.tile_img;
+    a.kb_lo = op.kb_lo;
+    a.kb_hi = op.kb_hi;
+    a.img = op.img;
+    a.scale = op.scale;
+    a.kscale = kscale;
+    a.abs_sum = op.abs_sum;
+    return launch_slice(plan, plan->ks, a, ELISA_PROFILE_SLICE, st);
 }
 
 // forward fold (plain store) -> statistic + digits of W -> transposed fold with the gradient epilogue
 static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, int m_tiles, bool want_grad,
-                        bool have_digits, const double* on, const double* off, double* loglike, cudaStream_t st) {
+                        bool have_digits, const double* on, const double* off, double* loglike, cudaStream_t st,
+                        bool stop_after_stat = false) {
     int rc;
     if (!have_digits &&  // the unfold kernel did not slice U itself (interpreter kernel / split rows)
-        (rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st)))
+        (rc = slice_chunk_operand(plan, plan->U, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st,
+                                  sp.balanced_fwd ? sp.t_inv : nullptr)))
         return rc;
     {
         I8EpilogueStore es{plan->W, sp.C_pad, m_tiles * I8_BM, sp.C_pad, plan->a_scale};
@@ -1793,8 +1832,10 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
     // (errors of random sign add in quadrature), so it is already pessimistic
     static const double tol = getenv("ELISA_B200_GUARD_TOL") ? atof(getenv("ELISA_B200_GUARD_TOL")) : 3e-11;
     a.guard_tol = tol;
+    a.kinv = sp.balanced_bwd ? sp.r_inv : nullptr;
     if (!want_grad) return launch_stat_slice_any<false>(plan, sp, a, st);
     if ((rc = launch_stat_slice_any<true>(plan, sp, a, st))) return rc;
+    if (stop_after_stat) return ELISA_OK;
     I8EpilogueGrad eg;
     eg.dU = plan->dU;
     eg.plane = (int64_t)m_tiles * I8_BM * sp.E_pad;
@@ -1915,7 +1956,8 @@ static int run_normal_eq_chunk(ElisaPlan* plan, int s, const double* theta, cons
         double* X = plan->Xp + (int64_t)(1 + j) * xplane;
         if ((sp.use_i8() && !plan->force_dmma)) {
             if (!(j < 0 && fused_digits) &&
-                (rc = slice_chunk_operand(plan, A, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st)))
+                (rc = slice_chunk_operand(plan, A, sp.E_pad, sp.E, n, m_tiles, ELISA_PROFILE_SLICE, st,
+                                          sp.balanced_fwd ? sp.t_inv : nullptr)))
                 return rc;
             I8EpilogueStore es{X, sp.C_pad, m_tiles * I8_BM, sp.C_pad, plan->a_scale};
             const FoldI8Args fa = fold_i8_args(plan, sp.i8_fwd, round_up(sp.E_pad, I8_BK) / I8_BK, m_tiles);
@@ -1950,6 +1992,59 @@ static int run_normal_eq_chunk(ElisaPlan* plan, int s, const double* theta, cons
     }
 }
 
+// Balance the integer folds of one spectrum around a pilot batch (the first rows of the call that
+// finds the plan unbalanced): power-of-two envelopes of U over the energies and of W over the
+// channels, folded into re-sliced response operands.  Everything is enqueued on `st`; nothing is
+// read back.  See col_envelope_kernel for why, DESIGN.md section 2 for the accuracy model.
+static int calibrate_spectrum(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off,
+                              int np, cudaStream_t st) {
+    SpectrumPlan& sp = plan->spec[s];
+    const bool prof = plan->profiling;
+    plan->profiling = false;
+    int rc = ELISA_OK;
+    do {
+        sp.balanced_fwd = sp.balanced_bwd = false;
+        if ((rc = launch_unfold(plan, sp, theta, np, I8_BM, false, plan->U, nullptr, sp.E_pad, sp.E_pad, true, st))) break;
+        unsigned long long* peak = plan->guard + 3;  // fourth word of the guard block: scratch
+        cudaMemsetAsync(peak, 0, 8, st);
+        col_peak_kernel<<<(sp.E_pad + 127) / 128, 128, 0, st>>>(plan->U, sp.E_pad, np, sp.E, peak);
+        const int ek = round_up(sp.E_pad, I8_BK), ck = round_up(sp.C_pad, I8_BK);
+        col_envelope_kernel<<<ek / 128, 128, 0, st>>>(plan->U, sp.E_pad, np, sp.E, ek, 1, peak, sp.t_scale, sp.t_inv,
+                                                      sp.t_exp);
+        plan->launches += 2;
+        if ((rc = reslice_operand(plan, sp.i8_fwd, sp.t_scale, st))) break;
+        sp.balanced_fwd = true;
+        // forward half of the chunk pass on the pilot rows: W of the pilot lands in plan->W
+        if ((rc = run_chunk_i8(plan, sp, 0, np, 1, true, false, on, off, plan->cal_ll, st, true))) break;
+        cudaMemsetAsync(peak, 0, 8, st);
+        col_peak_kernel<<<(sp.C_pad + 127) / 128, 128, 0, st>>>(plan->W, sp.C_pad, np, sp.C, peak);
+        col_envelope_kernel<<<ck / 128, 128, 0, st>>>(plan->W, sp.C_pad, np, sp.C, ck, 4, peak, sp.r_scale, sp.r_inv,
+                                                      sp.r_exp);
+        plan->launches += 2;
+        if ((rc = reslice_operand(plan, sp.i8_bwd, sp.r_scale, st))) break;
+        sp.balanced_bwd = true;
+        if (cudaMemsetAsync(plan->guard, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) {
+            rc = fail(ELISA_ERR_CUDA, "resetting the guard after calibration failed");
+            break;
+        }
+    } while (false);
+    plan->profiling = prof;
+    if (rc == ELISA_OK && cudaGetLastError() != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "calibration launch failed");
+    return rc;
+}
+
+static int ensure_balanced(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
+                           cudaStream_t st) {
+    if (!plan->balance || plan->force_dmma || plan->cal_ll == nullptr) return ELISA_OK;
+    for (int s = 0; s < plan->S; ++s) {
+        SpectrumPlan& sp = plan->spec[s];
+        if (!sp.use_i8() || (sp.balanced_fwd && sp.balanced_bwd) || sp.t_scale == nullptr) continue;
+        const int rc = calibrate_spectrum(plan, s, theta, on, off, (int)std::min<int64_t>(n, I8_BM), st);
+        if (rc) return rc;
+    }
+    return ELISA_OK;
+}
+
 static int run_all(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                    double* loglike, double* grad, cudaStream_t st) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
@@ -1959,7 +2054,7 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
     int dev;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
-    int rc = ELISA_OK;
+    int rc = ensure_balanced(plan, theta, on, off, n, st);
     for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
         const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
         for (int s = 0; s < plan->S && rc == ELISA_OK; ++s)
@@ -2251,6 +2346,26 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                     plan->guard = reinterpret_cast<unsigned long long*>(g);
                     if (rc == ELISA_OK && cudaMemset(g, 0, 32) != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "cudaMemset failed");
                 }
+                // balancing of the integer folds: column envelopes per spectrum + pilot scratch
+                {
+                    const char* env = getenv("ELISA_B200_BALANCE");
+                    plan->balance = !(env && atoi(env) == 0);
+                }
+                if (rc == ELISA_OK && plan->balance) rc = alloc(&plan->cal_ll, (int64_t)I8_BM * plan->S);
+                for (int s = 0; s < plan->S && rc == ELISA_OK && plan->balance; ++s) {
+                    SpectrumPlan& sp = plan->spec[s];
+                    if (!sp.use_i8()) continue;
+                    // padded to whole k-blocks (filled with ones by col_envelope_kernel): the slicers
+                    // read them with unguarded vector loads
+                    const int64_t ek = round_up(sp.E_pad, I8_BK), ck = round_up(sp.C_pad, I8_BK);
+                    if ((rc = alloc(&sp.t_scale, ek)) || (rc = alloc(&sp.t_inv, ek)) || (rc = alloc(&sp.r_scale, ck)) ||
+                        (rc = alloc(&sp.r_inv, ck)))
+                        break;
+                    double* e8 = nullptr;  // byte arrays carved from one FP64 allocation
+                    if ((rc = alloc(&e8, (ek + ck + 7) / 8))) break;
+                    sp.t_exp = reinterpret_cast<uint8_t*>(e8);
+                    sp.r_exp = sp.t_exp + ek;
+                }
             }
         }
     }
@@ -2532,7 +2647,7 @@ int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double*
         plan->owned.push_back(plan->Xp);
         plan->workspace_bytes += (int64_t)bytes;
     }
-    int rc = ELISA_OK;
+    int rc = ensure_balanced(plan, theta, counts_on, counts_off, n, st);
     for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
         const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
         for (int s = 0; s < plan->S && rc == ELISA_OK; ++s)
@@ -2542,6 +2657,12 @@ int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double*
     }
     cudaSetDevice(prev);
     return rc;
+}
+
+int elisa_b200_plan_rebalance(ElisaPlan* plan) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    for (int s = 0; s < plan->S; ++s) plan->spec[s].balanced_fwd = plan->spec[s].balanced_bwd = false;
+    return ELISA_OK;
 }
 
 int elisa_b200_plan_set_fold(ElisaPlan* plan, int dmma) {
@@ -2620,6 +2741,7 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
     SliceArgs sa;
     sa.X = A; sa.ld = lda; sa.rows = m; sa.cols = k; sa.row_tiles = m_tiles; sa.tile_rows = I8_BM; sa.kb_total = kb;
     sa.tile_img = nullptr; sa.kb_lo = nullptr; sa.kb_hi = nullptr; sa.img = a_img; sa.scale = a_sc;
+    sa.kscale = nullptr; sa.abs_sum = nullptr;
     SliceArgs sb = sa;
     sb.X = B; sb.ld = ldb; sb.rows = n; sb.row_tiles = n_tiles; sb.tile_rows = I8_BN; sb.img = b_img; sb.scale = b_sc;
     if ((rc = launch_slice(nullptr, slices, sa, 0, st)) || (rc = launch_slice(nullptr, slices, sb, 0, st))) {

@@ -178,6 +178,10 @@ struct SliceArgs {
     const int32_t* kb_hi;
     int8_t* img;       // images of KS * tile_rows * 128 bytes
     double* scale;     // [row_tiles * tile_rows]  x ~= scale * 256^-(KS-1) * q  (see kernel)
+    // balancing of the contraction index (powers of two, see col_envelope_kernel): the digits are
+    // those of x[k] * kscale[k]; nullptr = 1.  abs_sum (optional): sum_k |x[k] kscale[k]| per row.
+    const double* kscale;
+    double* abs_sum;
 };
 
 // One warp per row.  Pass 1: amax (and a non-finite flag).  Pass 2: q = rint(x * f) as
@@ -196,22 +200,99 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a) {
     const bool live = row < a.rows;
     const double* x = a.X + (size_t)row * a.ld;
 
-    double amax = 0.0;
+    double amax = 0.0, asum = 0.0;
     bool bad = false;
     if (live) {
         for (int k = 2 * lane; k < a.cols; k += 64) {
-            const double v0 = x[k], v1 = (k + 1 < a.cols) ? x[k + 1] : 0.0;
+            double v0 = x[k], v1 = (k + 1 < a.cols) ? x[k + 1] : 0.0;
+            if (a.kscale != nullptr) {
+                v0 *= a.kscale[k];
+                if (k + 1 < a.cols) v1 *= a.kscale[k + 1];
+            }
             bad |= !(fabs(v0) <= 1.79e308) | !(fabs(v1) <= 1.79e308);
             amax = fmax(amax, fmax(fabs(v0), fabs(v1)));
+            asum += fabs(v0) + fabs(v1);
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    }
     bad = __any_sync(0xffffffffu, bad);
     double f1, f2;
     const double sc = slice_scale<KS>(amax, bad, f1, f2);
-    if (lane == 0) a.scale[row] = sc;
-    slice_row_digits<KS>(x, live, (a.ld & 1) == 0, a.cols, f1, f2, rr, a.tile_rows, kb0, kb1, a.img, img0, lane);
+    if (lane == 0) {
+        a.scale[row] = sc;
+        if (a.abs_sum != nullptr) a.abs_sum[row] = live ? asum : 0.0;
+    }
+    slice_row_digits<KS>(x, live, (a.ld & 1) == 0, a.cols, f1, f2, rr, a.tile_rows, kb0, kb1, a.img, img0, lane,
+                         a.kscale);
+}
+
+// Column envelopes for balancing the contraction index of a fold.  The engine's error is
+// relative to (largest element of the A row) x (sum over the B row); when the operand's columns
+// differ by orders of magnitude (a steep photon spectrum; a few starved channels in W) the small
+// columns lose digits.  Dividing column k of A by t_k and multiplying column k of B by t_k leaves
+// the product unchanged -- exactly, t_k being a power of two -- and makes every column of A of
+// order one.  t_k = 2^round(log2(max over the pilot rows and over columns k - w .. k + w of
+// |X|)): an UPPER envelope (a too-small t_k would let one column tower over its row; the window
+// bridges accidental zeros such as sign changes of a residual), 1 where the envelope is zero or
+// not finite.  One thread per column.
+// The envelope is floored at 2^-I8_BALANCE_BITS of its largest column: columns the pilot saw as
+// negligible (an exponential cut-off far above its folding energy: 1e-300 against 1) stay
+// negligible for every row instead of being blown up to order one, where a row with a slightly
+// larger cut-off energy would tower over its own significant columns.  28 bits: columns within
+// 4e-9 of the peak keep full relative precision, a count fed only by columns at 1e-11 of the peak
+// still keeps 1e-12; a deeper floor buys nothing physical and makes tails that vary by many
+// orders between rows (exp(-E/Ec) at E = 20 Ec) dangerous.  Two passes: `peak` (one double,
+// zeroed by the caller) receives the largest column maximum first.
+constexpr int I8_BALANCE_BITS = 28;
+
+__global__ void __launch_bounds__(128) col_peak_kernel(const double* X, int64_t ld, int rows, int cols,
+                                                       unsigned long long* peak) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (k < cols)
+        for (int r = 0; r < rows; ++r) {
+            const double v = fabs(X[(size_t)r * ld + k]);
+            if (v <= 1.79e308) m = fmax(m, v);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(peak, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(128) col_envelope_kernel(const double* X, int64_t ld, int rows, int cols, int cols_pad,
+                                                           int window, const unsigned long long* peak, double* scale,
+                                                           double* inv, uint8_t* inv_exp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cols_pad) return;
+    double m = 0.0;
+    if (k < cols) {
+        const int lo = max(k - window, 0), hi = min(k + window, cols - 1);
+        for (int r = 0; r < rows; ++r)
+            for (int j = lo; j <= hi; ++j) {
+                const double v = fabs(X[(size_t)r * ld + j]);
+                if (v <= 1.79e308) m = fmax(m, v);
+            }
+    }
+    // Only the ratios between columns matter (the row scales absorb any common factor), so the
+    // envelope is expressed relative to its peak: t in [2^-I8_BALANCE_BITS, 1], 1 / t = 2^inv_exp.
+    const double top = __longlong_as_double((long long)*peak);  // bits of a non-negative double order like integers
+    int down = 0;
+    if (top > 0.0 && k < cols) {
+        m = fmax(m, ldexp(top, -I8_BALANCE_BITS));
+        int ex, ex_top;
+        const double f = frexp(m, &ex);  // m = f 2^ex, f in [0.5, 1)
+        const double f_top = frexp(top, &ex_top);
+        ex = (f > 0.70710678118654752 ? ex : ex - 1);
+        ex_top = (f_top > 0.70710678118654752 ? ex_top : ex_top - 1);
+        down = max(0, min(I8_BALANCE_BITS, ex_top - ex));
+    }
+    scale[k] = ldexp(1.0, -down);
+    inv[k] = ldexp(1.0, down);
+    inv_exp[k] = (uint8_t)down;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -691,6 +772,7 @@ struct StatSliceArgs {
     double guard_eta;  // typical normwise error of the engine, 2^(-8 KS)
     double guard_grad; // calibration of the gradient-side estimate (see the kernel)
     double guard_tol;
+    const double* kinv;  // balancing of the transposed fold: the digits are those of W[c] * kinv[c] (nullptr: 1)
 };
 
 template <int KS, int STAT, bool GRAD>
@@ -734,8 +816,9 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
                 const double w = dx * sc;
                 x[col] = w;
                 bad |= !(fabs(w) <= 1.79e308);
-                amax = fmax(amax, fabs(w));
-                wsum += fabs(w);
+                const double wb = a.kinv != nullptr ? fabs(w) * a.kinv[col] : fabs(w);  // as the digits see it
+                amax = fmax(amax, wb);
+                wsum += wb;
             }
         }
 #pragma unroll
@@ -773,7 +856,7 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     if (lane == 0) a.scale[row] = sc;
     __syncwarp();  // the row of W written above is read back by other lanes
     slice_row_digits<KS>(x, live, (a.ldx & 1) == 0, a.C, f1, f2, row % I8_BM, I8_BM, 0, a.kb_total, a.img,
-                         (int64_t)(row / I8_BM) * a.kb_total, lane);
+                         (int64_t)(row / I8_BM) * a.kb_total, lane, a.kinv);
 }
 
 }  // namespace elisa

@@ -28,11 +28,11 @@ __device__ __forceinline__ double slice_scale(double amax, bool bad, double& f1,
 
 // Digits of one row (one warp): balanced base-256 digits of q = rint(x f1 f2), four consecutive
 // k per lane packed into one 32-bit store per slice, k-blocks [kb0, kb1) into the images
-// starting at img0.
+// starting at img0.  kscale (optional): x[k] is multiplied by kscale[k] first.
 template <int KS>
 __device__ __forceinline__ void slice_row_digits(const double* x, bool live, bool aligned, int cols, double f1,
                                                  double f2, int rr, int tile_rows, int kb0, int kb1, int8_t* img,
-                                                 int64_t img0, int lane) {
+                                                 int64_t img0, int lane, const double* kscale = nullptr) {
     const int sub = (rr >> 3) * 1024 + (rr & 7) * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2);
     const size_t slice_bytes = (size_t)tile_rows * I8_BK;
     for (int kb = kb0; kb < kb1; ++kb) {
@@ -47,6 +47,12 @@ __device__ __forceinline__ void slice_row_digits(const double* x, bool live, boo
 #pragma unroll
                 for (int t = 0; t < 4; ++t)
                     if (k + t < cols) v[t] = x[k + t];
+            }
+            if (kscale != nullptr) {  // balancing of the contraction index: exact powers of two;
+                                      // the array is padded with ones to a multiple of 128 entries
+                const double2 s0 = *reinterpret_cast<const double2*>(kscale + k);
+                const double2 s1 = *reinterpret_cast<const double2*>(kscale + k + 2);
+                v[0] *= s0.x; v[1] *= s0.y; v[2] *= s1.x; v[3] *= s1.y;
             }
         }
         // q + bias (bias = 0x80 in each of the KS digit bytes) has the plain base-256 digits

@@ -37,6 +37,9 @@ struct UnfoldCore {
     // belongs to one warp (n_seg == 1) and the kernel was specialised with KS > 0; else nullptr
     int8_t* img;
     double* scale;
+    // balancing of the forward fold: when the kernel slices U itself it stores and slices
+    // U[e] * 2^kexp[e] (the FP64 copy is only read back for its digits then); nullptr: no scaling
+    const uint8_t* kexp;
     // flux normalisations (PhFlux / EnFlux, models/conv.py:145-256): their own grids and, for
     // EnFlux, the bin weights keV_to_erg * sqrt(e_j e_j+1) (nullptr: 1)
     GridView ngv[ELISA_MAX_NORMS];
@@ -55,7 +58,7 @@ __device__ __forceinline__ void unfold_zero(const UnfoldCore& a, size_t row_off,
 }
 
 template <typename T>
-__device__ __forceinline__ double unfold_store(const UnfoldCore& a, size_t off, const T& res) {
+__device__ __forceinline__ double unfold_store(const UnfoldCore& a, size_t off, const T& res, double k = 1.0) {
     const double v = value(res);
     bool pass = true;
     double u = v;
@@ -64,6 +67,7 @@ __device__ __forceinline__ double unfold_store(const UnfoldCore& a, size_t off, 
         u = fmin(fmax(v, 1e-300), 1e300);
         if (v != v) u = v;  // jnp.clip propagates NaN
     }
+    u *= k;  // a power of two: exact
     a.U[off] = u;
     if constexpr (Scalar<T>::NP > 0) {
 #pragma unroll
@@ -127,6 +131,9 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
     };
     double nE, nl, nEm, nlm;
     load_point(e_lo + lane, nE, nl, nEm, nlm);
+    // balancing factor of the lane's bin, loaded one pass ahead like the grid values
+    const bool scaled = slice && a.kexp != nullptr;
+    int nk = scaled ? a.kexp[min(e_lo + lane, E - 1)] : 0;
     double amax = 0.0;
     bool bad = false;
     for (int e0 = e_lo; e0 < e_hi; e0 += 31) {
@@ -135,10 +142,14 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
         gv.pl = nl;
         gv.pEm = nEm;
         gv.plm = nlm;
-        if (e0 + 31 < e_hi) load_point(e + 31, nE, nl, nEm, nlm);
+        const double ck = __hiloint2double((1023 + nk) << 20, 0);  // 2^nk
+        if (e0 + 31 < e_hi) {
+            load_point(e + 31, nE, nl, nEm, nlm);
+            if (scaled) nk = a.kexp[min(e + 31, E - 1)];
+        }
         const T res = Model::template bin<T>(pre, gv, e);
         if (lane < 31 && e < e_hi) {
-            const double u = unfold_store<T>(a, row_off + e, res);
+            const double u = unfold_store<T>(a, row_off + e, res, ck);
             if constexpr (KS > 0) {
                 bad |= !(fabs(u) <= 1.79e308);
                 amax = fmax(amax, fabs(u));

@@ -336,6 +336,18 @@ int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
  * caller that sees flagged > 0 re-evaluates after elisa_b200_plan_set_fold(plan, 1) -- the
  * Python host side (elisa_b200.Likelihood, fold=None) and loglike_grad_host do so themselves. */
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset);
+/* Balancing of the integer fold.  The engine's error is relative to (largest element of a row
+ * of U or W) x (sum over a row of the response operand); a steep spectrum or a few starved
+ * channels would cost the small columns digits.  The first evaluation call of a plan therefore
+ * takes its first <= 128 parameter vectors as a pilot, forms power-of-two envelopes t_e of U over
+ * the energies and r_c of W over the channels, and re-slices the two response operands as
+ * t_e R[e, c] and r_c R[e, c] -- on the call's stream, nothing read back; from then on U / t and
+ * W / r are what gets sliced (products unchanged, exactly).  The envelopes stay until
+ * elisa_b200_plan_rebalance() marks them stale (the next call re-derives them from its own first
+ * rows): call it when the region of parameter space changes by orders of magnitude in flux.
+ * Env ELISA_B200_BALANCE=0 switches balancing off.                                         */
+int elisa_b200_plan_rebalance(ElisaPlan* plan);
+
 /* dmma != 0: evaluate with the FP64 DMMA fold of the same plan (both sets of operands live in a
  * plan) until switched back -- what a caller does with a flagged "_dev" call.  The "_host" entry
  * point, which synchronises anyway, consults the guard and does this itself (unless the plan was
