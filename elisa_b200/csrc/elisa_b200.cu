@@ -684,6 +684,7 @@ struct SpectrumPlan {
     double *t_scale = nullptr, *t_inv = nullptr, *r_scale = nullptr, *r_inv = nullptr;
     uint8_t *t_exp = nullptr, *r_exp = nullptr;  // log2 of t_inv / r_inv
     bool balanced_fwd = false, balanced_bwd = false;
+    bool stale = false;  // elisa_b200_plan_rebalance(): derive the envelopes afresh at the next call
     const struct JitKernels* jit = nullptr;  // runtime-specialised unfold (nullptr: interpreter)
     GridView grid_view() const {
         GridView g{egrid, lngrid, emid, lnmid, E};
@@ -2038,9 +2039,12 @@ static int ensure_balanced(ElisaPlan* plan, const double* theta, const double* o
     if (!plan->balance || plan->force_dmma || plan->cal_ll == nullptr) return ELISA_OK;
     for (int s = 0; s < plan->S; ++s) {
         SpectrumPlan& sp = plan->spec[s];
-        if (!sp.use_i8() || (sp.balanced_fwd && sp.balanced_bwd) || sp.t_scale == nullptr) continue;
+        if (!sp.use_i8() || (sp.balanced_fwd && sp.balanced_bwd && !sp.stale) || sp.t_scale == nullptr) continue;
+        // (the flags only ever change inside calibrate_spectrum, together with the operands they
+        // describe: kernels captured in a CUDA graph keep pointing at the same, rewritten arrays)
         const int rc = calibrate_spectrum(plan, s, theta, on, off, (int)std::min<int64_t>(n, I8_BM), st);
         if (rc) return rc;
+        sp.stale = false;
     }
     return ELISA_OK;
 }
@@ -2089,6 +2093,14 @@ static int run_small(ElisaPlan* plan, const double* theta, const double* on, con
                           n <= plan->chunk && on == nullptr && off == nullptr && theta != nullptr && loglike != nullptr &&
                           plan->g_theta != nullptr;
     if (!eligible) return run_all(plan, theta, on, off, n, loglike, grad, st);
+    {  // envelopes of the balanced integer fold: (re)derived outside any capture, on the caller's stream
+        int dev;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
+        const int rc = ensure_balanced(plan, theta, on, off, n, st);
+        if (dev != plan->device) cudaSetDevice(dev);
+        if (rc) return rc;
+    }
     ElisaPlan::GraphEntry* e = nullptr;
     for (auto& g : plan->graphs)
         if (g.n == n && g.grad == (grad != nullptr)) e = &g;
@@ -2661,7 +2673,7 @@ int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double*
 
 int elisa_b200_plan_rebalance(ElisaPlan* plan) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
-    for (int s = 0; s < plan->S; ++s) plan->spec[s].balanced_fwd = plan->spec[s].balanced_bwd = false;
+    for (int s = 0; s < plan->S; ++s) plan->spec[s].stale = true;
     return ELISA_OK;
 }
 

@@ -141,8 +141,12 @@ class Likelihood:
         # row (estimated log-likelihood error of the sliced fold above 3e-11, see
         # elisa_b200_plan_fold_guard) is re-evaluated by an FP64 DMMA twin of this plan
         self._auto_guard = fold is None and any(self.fold_slices)
-        self._in_fallback = False
+        # 0: integer fold; 1: repeating the call on the integer fold with fresh envelopes;
+        # 2: repeating it on the FP64 DMMA fold
+        self._stage = 0
+        self._try_rebalance = True
         self.guard_fallbacks = 0
+        self.rebalances = 0
         self._py_fallbacks = 0
 
     # -- lifetime ------------------------------------------------------------------
@@ -163,20 +167,35 @@ class Likelihood:
         """After a device call of the guarded default engine: did the accuracy guard flag a row?
         If so the plan is switched to its FP64 DMMA fold (``elisa_b200_plan_set_fold``) for the
         caller to repeat the evaluation, and switched back by ``_guard_done``."""
-        if not self._auto_guard or self._in_fallback:
+        if not self._auto_guard or self._stage == 2:
             return False
         flagged, _ = self.fold_guard(reset=True)
         if flagged == 0:
             return False
+        if self._stage == 0 and self._try_rebalance:
+            # the balancing envelopes (elisa_b200_plan_rebalance) were taken around another region
+            # of parameter space: take them afresh from this call's rows and repeat it once
+            _lib.check(self._lib.elisa_b200_plan_rebalance(self._h))
+            self.rebalances += 1
+            self._stage = 1
+            return True
+        if self._stage == 1:
+            self._try_rebalance = False  # fresh envelopes and it still trips: the data are starved
         self._py_fallbacks += 1
         self.guard_fallbacks = int(self._lib.elisa_b200_plan_guard_fallbacks(self._h)) + self._py_fallbacks
-        self._in_fallback = True
+        self._stage = 2
         _lib.check(self._lib.elisa_b200_plan_set_fold(self._h, 1))
         return True
 
     def _guard_done(self):
-        _lib.check(self._lib.elisa_b200_plan_set_fold(self._h, 0))
-        self._in_fallback = False
+        if self._stage == 2:
+            _lib.check(self._lib.elisa_b200_plan_set_fold(self._h, 0))
+        self._stage = 0
+
+    def rebalance(self):
+        """Mark the balancing envelopes of the integer fold stale: the next evaluation derives
+        them from its own first rows (``elisa_b200_plan_rebalance``)."""
+        _lib.check(self._lib.elisa_b200_plan_rebalance(self._h))
 
     @property
     def specialised(self) -> list[bool]:

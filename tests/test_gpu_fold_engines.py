@@ -234,3 +234,67 @@ def test_narrow_band_sparse_response_keeps_the_dmma_fold(lib):
     for fold in (None, 'i8'):
         err = compare(cfg, fold=fold) if fold else compare(cfg)
         assert err['value'] <= RTOL and err['grad'] <= RTOL, (fold, err)
+
+
+def _random_case(seed):
+    from test_gpu_random import _random_data, _random_model
+
+    rng = np.random.default_rng(1000 + seed)
+    stat = ['chi2', 'cstat', 'pstat', 'pgstat', 'wstat'][seed % 5]
+    E = int(rng.choice([33, 64, 127, 128, 129, 200, 257, 500]))
+    C = int(rng.choice([17, 63, 64, 65, 128, 190, 300]))
+    n = int(rng.choice([1, 5, 127, 128, 129, 300, 700]))
+    model = _random_model(rng)
+    d = _random_data(rng, E, C, stat)
+    return dict(data=[d], model=[model.compile()], stat=[stat], theta=_theta_for(model, n, seed))
+
+
+@pytest.mark.parametrize('seed', [6, 17])
+def test_balancing_removes_the_starved_channel_weakness(lib, seed, monkeypatch):
+    """Bad-fit rows whose starved channels (n >> mu) tower over W: the unbalanced integer fold
+    loses gradient digits (and says so), the balanced one is accurate without a flag."""
+    from elisa_b200 import Likelihood
+    from parity import RTOL, oracle_eval, rel_err_grad, rel_err_value
+
+    cfg = _random_case(seed)
+    ll_ref, g_ref = oracle_eval(cfg)
+    out = {}
+    for bal in ('0', '1'):
+        monkeypatch.setenv('ELISA_B200_BALANCE', bal)
+        lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold='i8')
+        ll, g = lk.loglike_and_grad(cfg['theta'])
+        flagged, _ = lk.fold_guard()
+        lk.close()
+        out[bal] = (rel_err_value(ll.cpu().numpy(), ll_ref), rel_err_grad(g.cpu().numpy(), g_ref), flagged)
+    assert out['0'][1] > RTOL and out['0'][2] > 0, out     # the weakness, detected
+    assert out['1'][0] <= 1e-11 and out['1'][1] <= 1e-11 and out['1'][2] == 0, out
+
+
+def test_stale_envelopes_are_renewed(lib):
+    """Envelopes taken on a steep spectrum (index 4 over three decades: columns 1e12 apart, floored
+    28 bits below the peak) do not fit a flat one: the guard flags the call, the host side renews
+    the envelopes from the call's own rows and repeats it on the integer fold -- no DMMA fallback."""
+    from elisa_b200 import FixedData, Likelihood
+    from parity import RTOL, oracle_eval, rel_err_grad, rel_err_value
+
+    rng = np.random.default_rng(5)
+    E, C = 256, 128
+    eg = np.geomspace(0.1, 100.0, E + 1)
+    R = np.abs(rng.standard_normal((E, C))) + 0.1
+    d = FixedData('d', eg, rng.poisson(50.0, C).astype(float), np.ones(C), 10.0, response_matrix=R)
+    a = M.UniformParameter('alpha', 2.0, -3.0, 10.0)
+    K = M.UniformParameter('K', 1.0, 1e-10, 1e10)
+    model = M.PowerLaw(alpha=a, K=K)
+    lk = Likelihood([d], model, ['cstat'])
+    assert lk.fold_slices == [6]
+    steep = np.column_stack([4.0 + 0.01 * rng.random(200), np.full(200, 5.0)])
+    flat = np.column_stack([0.3 + 0.01 * rng.random(200), np.full(200, 0.05)])
+    # (back on the steep spectrum the flat envelopes merely give the unbalanced accuracy, which
+    # this dense response tolerates: no renewal needed)
+    for theta, renew in ((steep, 0), (flat, 1), (flat, 1), (steep, 1)):
+        cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
+        ll_ref, g_ref = oracle_eval(cfg)
+        ll, g = lk.loglike_and_grad(theta)
+        assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL and rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
+        assert lk.rebalances == renew and lk.guard_fallbacks == 0, (lk.rebalances, lk.guard_fallbacks)
+    lk.close()
