@@ -742,6 +742,7 @@ struct ElisaPlan {
     int64_t guard_fallbacks = 0;
     bool force_dmma = false;  // evaluate with the FP64 DMMA fold although the integer operands exist (guard fallback)
     bool balance = true;      // balance the integer folds around the first batch seen (ELISA_B200_BALANCE=0: off)
+    bool renew_envelopes = true;  // host entry point: answer a flagged call by renewing the envelopes first
     double* cal_ll = nullptr; // [128 * S] log-likelihoods of the pilot rows (scratch)
     int ld_part = 0;  // leading dimension (rows) of the part / gpart arrays in use
     // Joint fits: inside the captured graph every spectrum runs on its own branch (own stream
@@ -2573,7 +2574,20 @@ int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const dou
         unsigned long long h[4] = {0, 0, 0, 0};
         CUDA_TRY(cudaMemcpyAsync(h, plan->guard, 32, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (h[0] != 0) {
+        if (h[0] != 0 && plan->balance && plan->renew_envelopes) {
+            // first the cheap answer: the envelopes of the balanced fold may have been taken in
+            // another region of parameter space -- derive them from this call's rows and repeat it
+            CUDA_TRY(cudaMemsetAsync(plan->guard, 0, 32, st));
+            elisa_b200_plan_rebalance(plan);
+            rc = run_all(plan, plan->h_theta, counts_on ? plan->h_on : nullptr, counts_off ? plan->h_off : nullptr, n,
+                         plan->h_ll, grad ? plan->h_grad : nullptr, st);
+            if (rc == ELISA_OK) {
+                CUDA_TRY(cudaMemcpyAsync(h, plan->guard, 32, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (h[0] != 0) plan->renew_envelopes = false;  // fresh envelopes and still flagged: starved data
+            }
+        }
+        if (rc == ELISA_OK && h[0] != 0) {
             CUDA_TRY(cudaMemsetAsync(plan->guard, 0, 32, st));
             plan->force_dmma = true;
             ++plan->guard_fallbacks;

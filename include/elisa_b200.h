@@ -323,18 +323,20 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
  * with FP64 DMMA, -1 on a bad argument                                                   */
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
 /* Accuracy guard of the sliced-integer fold.  Its error is bounded relative to (largest
- * model bin of the row) x (column sum of the response), not to each folded count, so a
- * channel predicted ~2^40 below the brightest part of the model loses relative accuracy.
- * While evaluating, the statistic kernel estimates to first order the log-likelihood error
- * this may have caused, sum_c |dl/dx_c| * 2^(-8 slices) * max_e|u| * sum_e|R[e,c]|, and counts
- * the rows where it exceeds 3e-11 * max(|loglike|, 1) (env ELISA_B200_GUARD_TOL); on the
- * gradient side it flags rows in which a few channels tower over the rest of W = dl/d(Ru)
- * (2^(-8 slices) * C * max|W| / sum|W| above the same level: the transposed fold keeps digits
- * relative to the largest |W| of the row).  This call returns that count and the
- * largest relative estimate since the last reset (synchronise the stream of the evaluation
- * first).  Rows are never flagged on the BASELINE configurations (estimates 7e-14 .. 1.4e-11); a
- * caller that sees flagged > 0 re-evaluates after elisa_b200_plan_set_fold(plan, 1) -- the
- * Python host side (elisa_b200.Likelihood, fold=None) and loglike_grad_host do so themselves. */
+ * element of the balanced row of U) x (sum over the balanced column of the response), see
+ * elisa_b200_plan_rebalance below; rows far from the spectrum the envelopes were taken on, or
+ * data with genuinely starved channels (counts where the model predicts ~nothing), lose
+ * accuracy.  While evaluating, the statistic kernel estimates to first order the log-likelihood
+ * error this may have caused, sum_c |dl/dx_c| * 2^(-8 slices) * max_e|u'| * sum_e|t_e R[e,c]|,
+ * and counts the rows where it exceeds 3e-11 * max(|loglike|, 1) (env ELISA_B200_GUARD_TOL); on
+ * the gradient side it flags rows in which a few channels tower over the rest of the balanced
+ * W = dl/d(Ru) (2^(-8 slices) * C * max|W'| / sum|W'| above the same level).  This call
+ * returns that count and the largest relative estimate since the last reset (synchronise the
+ * stream of the evaluation first).  Rows are never flagged on the BASELINE configurations
+ * (estimates <= 2e-12).  A caller that sees flagged > 0 first renews the envelopes
+ * (elisa_b200_plan_rebalance) and repeats the call; if it is flagged again, it re-evaluates
+ * after elisa_b200_plan_set_fold(plan, 1) -- the Python host side (elisa_b200.Likelihood,
+ * fold=None) and loglike_grad_host do both themselves.                                     */
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset);
 /* Balancing of the integer fold.  The engine's error is relative to (largest element of a row
  * of U or W) x (sum over a row of the response operand); a steep spectrum or a few starved

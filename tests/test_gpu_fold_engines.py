@@ -298,3 +298,12 @@ def test_stale_envelopes_are_renewed(lib):
         assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL and rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
         assert lk.rebalances == renew and lk.guard_fallbacks == 0, (lk.rebalances, lk.guard_fallbacks)
     lk.close()
+    # the synchronous C entry point answers the same way
+    lk = Likelihood([d], model, ['cstat'])
+    for theta in (steep, flat):
+        cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
+        ll_ref, g_ref = oracle_eval(cfg)
+        ll, g = lk.loglike_and_grad_host(theta)
+        assert rel_err_value(ll, ll_ref) <= RTOL and rel_err_grad(g, g_ref) <= RTOL
+    assert lk.guard_fallbacks == 0
+    lk.close()
