@@ -15,6 +15,6 @@ SHORT="python bench.py --draws 37888 --steps 1 --warmup 1 --no-cpu-baseline --no
 timeout 300 $SHORT > $OUT/plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_$TAG.csv $SHORT > $OUT/ncu1_$TAG.log 2>&1
 echo "ncu1 rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'unfold|gemm|fold_i8|slice|reduce' -s 5 -c 5 -f -o $OUT/prof_$TAG $SHORT > $OUT/ncu2_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'unfold|gemm|fold_i8|stat_slice|reduce' -s 12 -c 5 -f -o $OUT/prof_$TAG $SHORT > $OUT/ncu2_$TAG.log 2>&1
 echo "ncu2 rc=$?"
 cat $OUT/bench_$TAG.json | cut -c1-600
