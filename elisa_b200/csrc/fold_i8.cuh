@@ -671,7 +671,7 @@ struct I8EpilogueGrad {
     int32_t n_part;
     double* gpart;
     int32_t ld_part;
-    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = no prefetch
+    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = L2 prefetch of the tile's dU lines
 
     struct State {
         double rs[ELISA_MAX_PARAMS];
@@ -680,11 +680,13 @@ struct I8EpilogueGrad {
 #pragma unroll
         for (int j = 0; j < ELISA_MAX_PARAMS; ++j) st.rs[j] = 0.0;
     }
-    // the tile's dU lines (one 128-byte line per parameter and row; thread q of a quad takes row
-    // row0 + 8 q) are requested from HBM while the tile is still accumulating, so that the
-    // contraction below finds them in L2
+    // Optional (dbg & 64): request the tile's dU lines (one 128-byte line per parameter and row;
+    // thread q of a quad takes row row0 + 8 q) from HBM while the tile is still accumulating.
+    // It paid while the epilogue was a thread-per-row loop; with the quad layout the loads of a
+    // plane overlap the arithmetic of the previous one and the extra L2 traffic only costs
+    // (ablation on the bench shape: transposed fold 16.0 ms with, 15.6 ms without), so it is off.
     __device__ __forceinline__ void prefetch(int row, int c0) const {
-        if (dbg & 64) return;
+        if (!(dbg & 64)) return;
         const double* base = dU + (size_t)row * ldu + c0;
 #pragma unroll
         for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
