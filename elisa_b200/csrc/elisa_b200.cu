@@ -744,6 +744,7 @@ struct ElisaPlan {
     bool balance = true;      // balance the integer folds around the first batch seen (ELISA_B200_BALANCE=0: off)
     bool renew_envelopes = true;  // host entry point: answer a flagged call by renewing the envelopes first
     double* cal_ll = nullptr; // [128 * S] log-likelihoods of the pilot rows (scratch)
+    double *cal_theta = nullptr, *cal_on = nullptr, *cal_off = nullptr;  // the gathered pilot rows
     int ld_part = 0;  // leading dimension (rows) of the part / gpart arrays in use
     // Joint fits: inside the captured graph every spectrum runs on its own branch (own stream
     // during capture, own small workspace), so the S kernel chains of a small batch overlap
@@ -2038,9 +2039,32 @@ static int calibrate_spectrum(ElisaPlan* plan, int s, const double* theta, const
 static int ensure_balanced(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                            cudaStream_t st) {
     if (!plan->balance || plan->force_dmma || plan->cal_ll == nullptr) return ELISA_OK;
+    bool staged = false;
     for (int s = 0; s < plan->S; ++s) {
         SpectrumPlan& sp = plan->spec[s];
         if (!sp.use_i8() || (sp.balanced_fwd && sp.balanced_bwd && !sp.stale) || sp.t_scale == nullptr) continue;
+        if (!staged && n > I8_BM) {
+            // the pilot: 128 rows spread evenly over the batch (a scan over a parameter grid changes
+            // systematically from its first to its last row), gathered into scratch
+            const int64_t stride = n / I8_BM;
+            auto gather = [&](double** dst, const double* src, int64_t width) -> int {
+                if (*dst == nullptr) {
+                    CUDA_TRY(cudaMalloc((void**)dst, (size_t)I8_BM * width * 8));
+                    plan->owned.push_back(*dst);
+                }
+                CUDA_TRY(cudaMemcpy2DAsync(*dst, (size_t)width * 8, src, (size_t)stride * width * 8, (size_t)width * 8,
+                                           I8_BM, cudaMemcpyDeviceToDevice, st));
+                return ELISA_OK;
+            };
+            int rc = gather(&plan->cal_theta, theta, plan->P);
+            if (rc == ELISA_OK && on != nullptr) rc = gather(&plan->cal_on, on, plan->sum_C);
+            if (rc == ELISA_OK && off != nullptr) rc = gather(&plan->cal_off, off, plan->sum_C);
+            if (rc) return rc;
+            theta = plan->cal_theta;
+            if (on != nullptr) on = plan->cal_on;
+            if (off != nullptr) off = plan->cal_off;
+            staged = true;
+        }
         // (the flags only ever change inside calibrate_spectrum, together with the operands they
         // describe: kernels captured in a CUDA graph keep pointing at the same, rewritten arrays)
         const int rc = calibrate_spectrum(plan, s, theta, on, off, (int)std::min<int64_t>(n, I8_BM), st);

@@ -341,11 +341,12 @@ int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst,
 /* Balancing of the integer fold.  The engine's error is relative to (largest element of a row
  * of U or W) x (sum over a row of the response operand); a steep spectrum or a few starved
  * channels would cost the small columns digits.  The first evaluation call of a plan therefore
- * takes its first <= 128 parameter vectors as a pilot, forms power-of-two envelopes t_e of U over
- * the energies and r_c of W over the channels, and re-slices the two response operands as
+ * takes 128 of its parameter vectors, spread evenly over the batch, as a pilot, forms
+ * power-of-two envelopes t_e of U over the energies and r_c of W over the channels (each
+ * relative to its peak, floored 28 bits below it), and re-slices the two response operands as
  * t_e R[e, c] and r_c R[e, c] -- on the call's stream, nothing read back; from then on U / t and
  * W / r are what gets sliced (products unchanged, exactly).  The envelopes stay until
- * elisa_b200_plan_rebalance() marks them stale (the next call re-derives them from its own first
+ * elisa_b200_plan_rebalance() marks them stale (the next call re-derives them from its own
  * rows): call it when the region of parameter space changes by orders of magnitude in flux.
  * Env ELISA_B200_BALANCE=0 switches balancing off.                                         */
 int elisa_b200_plan_rebalance(ElisaPlan* plan);

@@ -307,3 +307,36 @@ def test_stale_envelopes_are_renewed(lib):
         assert rel_err_value(ll, ll_ref) <= RTOL and rel_err_grad(g, g_ref) <= RTOL
     assert lk.guard_fallbacks == 0
     lk.close()
+
+
+def test_pilot_rows_are_spread_over_the_batch(lib):
+    """A scan of a line energy over a parameter grid: the pilot is 128 rows gathered from the
+    whole batch (theta and per-replica counts), but the rows differ in SHAPE -- every row has its
+    line somewhere else on a continuum 1e5 below it -- which no column scaling can balance.  The
+    guard sees it (renewal does not help, the call is repeated on the DMMA fold) and the result
+    holds the tolerance."""
+    from elisa_b200 import FixedData, Likelihood
+    from parity import RTOL, oracle_eval, rel_err_grad, rel_err_value
+
+    rng = np.random.default_rng(12)
+    E, C, n = 256, 128, 1500
+    eg = np.linspace(1.0, 10.0, E + 1)
+    R = np.zeros((E, C))
+    for e in range(E):
+        c = e // 2
+        R[e, max(0, c - 3): c + 4] = 30.0 * (0.5 + rng.random(min(C, c + 4) - max(0, c - 3)))
+    d = FixedData('d', eg, rng.poisson(40.0, C).astype(float), np.ones(C), 20.0, response_matrix=R)
+    U = M.UniformParameter
+    model = M.Gauss(El=U('El', 5.0, 1.0, 10.0), sigma=U('sigma', 0.15, 0.01, 1.0), K=U('K', 5.0, 1e-3, 1e3))
+    model = model + M.PowerLaw(alpha=U('alpha', 1.5, -3.0, 10.0), K=U('Kp', 0.02, 1e-6, 1e3))
+    theta = np.column_stack([np.linspace(2.0, 9.0, n), np.full(n, 0.15), np.full(n, 5.0), np.full(n, 1.5), np.full(n, 0.02)])
+    counts = rng.poisson(40.0, (n, C)).astype(float)
+    for kw in ({}, {'counts_on': counts}):
+        cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta, **kw)
+        ll_ref, g_ref = oracle_eval(cfg)
+        lk = Likelihood([d], model, ['cstat'])
+        assert lk.fold_slices == [6]
+        ll, g = lk.loglike_and_grad(theta, **kw)
+        assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL and rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
+        assert lk.rebalances <= 1 and lk.guard_fallbacks <= 1, (lk.rebalances, lk.guard_fallbacks)
+        lk.close()
