@@ -92,3 +92,29 @@ def test_hxmt_sample_files():
         assert np.all(np.isfinite(R)) and R.sum() > 0 and R.min() > -1e-3 * R.max()  # mission RSPs carry small negatives
         assert np.all(np.isfinite(d.back_ratio)) and np.all(d.back_ratio > 0)
         assert np.all(d.spec_counts >= 0) and np.all(d.net_errors >= 0)
+
+
+def test_grouped_scales_known_answers():
+    """The reference's own known-answer tests of the XSPEC scale rules
+    (tests/test_data.py:956-1041: count-weighted harmonic mean, arithmetic mean for NET spectra,
+    plain harmonic mean when the weighted denominator vanishes, constant scales stay constant)."""
+    from elisa_b200.ogip import _group_scale
+
+    gidx, ones = np.array([0]), np.ones(2)
+
+    def g(counts, scale, net):
+        return _group_scale(np.asarray(counts, float), np.asarray(scale, float), gidx, ones, net)
+
+    assert np.allclose(g([10.0, 20.0], [2.0, 6.0], False), [3.6])
+    assert np.allclose(g([10.0, 20.0], [4.0, 12.0], False), [7.2])
+    assert np.allclose(g([10.0, 20.0], [2.0, 6.0], True), [4.0])
+    assert np.allclose(g([10.0, 20.0], [3.0, 9.0], True), [6.0])
+    assert np.allclose(g([1.0, -3.0], [1.0, 3.0], False), [1.5])   # weighted denominator is zero
+    assert np.allclose(g([1.0, -3.0], [2.0, 6.0], False), [3.0])
+    # background ratio of a grouped pair (test_background_grouped_ratio_uses_non_net_formula)
+    sa, sb = g([10.0, 20.0], [2.0, 6.0], False), g([10.0, 20.0], [3.0, 9.0], False)
+    ba, bb = g([4.0, 8.0], [2.0, 6.0], False), g([4.0, 8.0], [2.0, 8.0], False)
+    expected = (30.0 / (10.0 / 2.0 + 20.0 / 6.0)) * (30.0 / (10.0 / 3.0 + 20.0 / 9.0)) / (
+        (12.0 / (4.0 / 2.0 + 8.0 / 6.0)) * (12.0 / (4.0 / 2.0 + 8.0 / 8.0)))
+    assert np.allclose(sa * sb / (ba * bb), [expected])
+    assert np.allclose(g([10.0, 20.0], [2.0, 2.0], False), [2.0]) and np.allclose(g([4.0, 8.0], [5.0, 5.0], True), [5.0])

@@ -312,3 +312,17 @@ def test_hdf5_reader_on_the_reference_tables():
         assert np.array_equal(c.table_log_energy, np.log(flat['energy']).astype(np.float64))
     with pytest.raises(ValueError):
         M.PhAbs.from_tables(REF_TABLES, abund='nope')
+
+
+def test_phflux_of_a_powerlaw_is_plphflux():
+    """Closed form: the bins of a power law are exact integrals, so their sum over the flux grid
+    is the exact band flux and PhFlux(emin, emax)(PowerLaw) must equal PLPhFlux(emin, emax)
+    (the identity behind the reference's tests/test_model.py::test_simulation)."""
+    from elisa_b200 import models as M
+    from oracle.likelihood import eval_model
+
+    eg = torch.as_tensor(np.geomspace(0.3, 80.0, 101))
+    theta = torch.tensor([[1.7, 3.0], [0.4, 12.0], [2.6, 0.5]], dtype=torch.float64)
+    a = eval_model(M.PhFlux(1.0, 10.0)(M.PowerLaw(K=1.0)).compile().to_spec(), eg, theta).numpy()
+    b = eval_model(M.PLPhFlux(1.0, 10.0).compile().to_spec(), eg, theta).numpy()
+    assert np.allclose(a, b, rtol=1e-12, atol=0.0)

@@ -104,3 +104,14 @@ def test_fit_recovers_flux(lib):
     lk.close()
     assert th.shape[0] >= 380
     assert np.all(np.abs(th.mean(axis=0) / truth - 1.0) < 0.01), th.mean(axis=0)
+
+
+def test_phflux_of_a_powerlaw_is_plphflux(lib):
+    """Closed form (see the CPU twin): PhFlux(emin, emax)(PowerLaw) == PLPhFlux(emin, emax)."""
+    from elisa_b200 import models as M
+
+    eg = np.geomspace(0.3, 80.0, 101)
+    theta = np.array([[1.7, 3.0], [0.4, 12.0], [2.6, 0.5]])
+    a = M.PhFlux(1.0, 10.0)(M.PowerLaw(K=1.0)).compile().eval(eg, theta)
+    b = M.PLPhFlux(1.0, 10.0).compile().eval(eg, theta)
+    assert np.allclose(a, b, rtol=1e-12, atol=0.0)
