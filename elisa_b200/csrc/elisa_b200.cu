@@ -1995,8 +1995,8 @@ static int run_normal_eq_chunk(ElisaPlan* plan, int s, const double* theta, cons
     }
 }
 
-// Balance the integer folds of one spectrum around a pilot batch (the first rows of the call that
-// finds the plan unbalanced): power-of-two envelopes of U over the energies and of W over the
+// Balance the integer folds of one spectrum around a pilot batch (<= 128 rows of the call that
+// finds the plan unbalanced, gathered by ensure_balanced): power-of-two envelopes of U over the energies and of W over the
 // channels, folded into re-sliced response operands.  Everything is enqueued on `st`; nothing is
 // read back.  See col_envelope_kernel for why, DESIGN.md section 2 for the accuracy model.
 static int calibrate_spectrum(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off,

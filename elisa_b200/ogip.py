@@ -373,7 +373,6 @@ def load_data(erange, specfile: str, backfile: str | None = None, respfile: str 
     else:
         g_emin, g_emax = resp.channel_emin, resp.channel_emax
         rows, cols, vals = resp.rows, resp.cols, resp.values
-    G = gidx.size
     mask = np.any((er[:, :1] <= g_emin) & (g_emax <= er[:, 1:]), axis=0)  # _get_channel_mask
     mask &= _seg_sum(good.astype(np.int64), gidx) > 0
     new_index = np.cumsum(mask) - 1
@@ -382,7 +381,6 @@ def load_data(erange, specfile: str, backfile: str | None = None, respfile: str 
     Cg = int(mask.sum())
     if Cg == 0:
         raise RuntimeError(f'no channel of {name} data lies inside erange')
-    del G
 
     kw = dict(name=name, photon_egrid=resp.photon_egrid, spec_counts=spec_counts[mask], area_scale=spec_area[mask],
               spec_exposure=spec.exposure, channel_width=(g_emax - g_emin)[mask])
