@@ -21,6 +21,7 @@ FLAG_NO_JIT = 1
 FLAG_REQUIRE_JIT = 2
 FLAG_FOLD_DMMA = 4
 FLAG_FOLD_I8 = 8
+FLAG_NO_BALANCE = 16
 FLAG_FOLD_SLICES_SHIFT = 8
 METHOD = {'trapz': 0, 'simpson': 1}
 STAT = {'chi2': 0, 'cstat': 1, 'pstat': 2, 'pgstat': 3, 'wstat': 4}

@@ -2386,7 +2386,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                 // balancing of the integer folds: column envelopes per spectrum + pilot scratch
                 {
                     const char* env = getenv("ELISA_B200_BALANCE");
-                    plan->balance = !(env && atoi(env) == 0);
+                    plan->balance = !(env && atoi(env) == 0) && !(desc->flags & ELISA_FLAG_NO_BALANCE);
                 }
                 if (rc == ELISA_OK && plan->balance) rc = alloc(&plan->cal_ll, (int64_t)I8_BM * plan->S);
                 for (int s = 0; s < plan->S && rc == ELISA_OK && plan->balance; ++s) {

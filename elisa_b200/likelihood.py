@@ -49,13 +49,15 @@ class Likelihood:
         FP64 DMMA for spectra it cannot take), 'i8' = require the sliced-integer fold,
         'dmma' = native FP64 DMMA
     slices : digits per operand of the sliced-integer fold (4..7, 0 = default 6)
+    balance : balance the integer fold's contraction indices around the first batch evaluated
+        (power-of-two column envelopes); False = plain normwise accuracy
 
     ``params_name`` lists the columns of ``theta`` (constrained space; priors and
     transforms stay with the caller, infer/helper.py:409-426).
     """
 
     def __init__(self, data: Sequence[FixedData], model, stat: Sequence[str], device: int | None = None, chunk: int = 0,
-                 specialise: bool | None = None, fold: str | None = None, slices: int = 0):
+                 specialise: bool | None = None, fold: str | None = None, slices: int = 0, balance: bool = True):
         import torch
 
         if not torch.cuda.is_available():
@@ -129,6 +131,8 @@ class Likelihood:
             raise ValueError('slices must be 0 or 4..7')
         flags |= {None: 0, 'i8': _lib.FLAG_FOLD_I8, 'dmma': _lib.FLAG_FOLD_DMMA}[fold]
         flags |= int(slices) << _lib.FLAG_FOLD_SLICES_SHIFT
+        if not balance:
+            flags |= _lib.FLAG_NO_BALANCE
         desc = _lib.PlanDesc(_lib.ABI_VERSION, self.device, self._P, len(data), specs, int(chunk), flags)
         handle = C.c_void_p()
         _lib.check(lib.elisa_b200_plan_create(C.byref(desc), C.byref(handle)))

@@ -243,6 +243,7 @@ typedef struct ElisaPlanDesc {
  * 4 is an FP32-class variant, ~1e-6) or env ELISA_B200_FOLD_SLICES.                       */
 #define ELISA_FLAG_FOLD_DMMA 4
 #define ELISA_FLAG_FOLD_I8 8
+#define ELISA_FLAG_NO_BALANCE 16 /* integer fold without column balancing (see elisa_b200_plan_rebalance) */
 #define ELISA_FLAG_FOLD_SLICES_SHIFT 8
 #define ELISA_FOLD_SLICES_DEFAULT 6
 
@@ -348,7 +349,7 @@ int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst,
  * W / r are what gets sliced (products unchanged, exactly).  The envelopes stay until
  * elisa_b200_plan_rebalance() marks them stale (the next call re-derives them from its own
  * rows): call it when the region of parameter space changes by orders of magnitude in flux.
- * Env ELISA_B200_BALANCE=0 switches balancing off.                                         */
+ * ELISA_FLAG_NO_BALANCE / env ELISA_B200_BALANCE=0 switch balancing off.                                       */
 int elisa_b200_plan_rebalance(ElisaPlan* plan);
 
 /* dmma != 0: evaluate with the FP64 DMMA fold of the same plan (both sets of operands live in a

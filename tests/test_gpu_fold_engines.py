@@ -259,14 +259,15 @@ def test_balancing_removes_the_starved_channel_weakness(lib, seed, monkeypatch):
     cfg = _random_case(seed)
     ll_ref, g_ref = oracle_eval(cfg)
     out = {}
-    for bal in ('0', '1'):
-        monkeypatch.setenv('ELISA_B200_BALANCE', bal)
-        lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold='i8')
+    for bal in ('0', '1', 'flag'):
+        monkeypatch.setenv('ELISA_B200_BALANCE', '1' if bal == 'flag' else bal)
+        lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold='i8', balance=bal != 'flag')
         ll, g = lk.loglike_and_grad(cfg['theta'])
         flagged, _ = lk.fold_guard()
         lk.close()
         out[bal] = (rel_err_value(ll.cpu().numpy(), ll_ref), rel_err_grad(g.cpu().numpy(), g_ref), flagged)
     assert out['0'][1] > RTOL and out['0'][2] > 0, out     # the weakness, detected
+    assert out['flag'] == out['0']                          # ELISA_FLAG_NO_BALANCE == the env switch
     assert out['1'][0] <= 1e-11 and out['1'][1] <= 1e-11 and out['1'][2] == 0, out
 
 
