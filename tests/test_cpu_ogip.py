@@ -118,3 +118,52 @@ def test_grouped_scales_known_answers():
         (12.0 / (4.0 / 2.0 + 8.0 / 6.0)) * (12.0 / (4.0 / 2.0 + 8.0 / 8.0)))
     assert np.allclose(sa * sb / (ba * bb), [expected])
     assert np.allclose(g([10.0, 20.0], [2.0, 2.0], False), [2.0]) and np.allclose(g([4.0, 8.0], [5.0, 5.0], True), [5.0])
+
+
+def test_fits_reader_conventions(tmp_path):
+    """Column conventions found in mission files beyond the synthetic OGIP cases: unsigned 16-bit
+    integers (TZERO = 32768 on a signed column), scaled columns (TSCAL), 64-bit variable-length
+    descriptors ('Q'), logical and string columns, and a header with CONTINUE / HISTORY cards."""
+    import struct
+
+    from ogip_cases import _header, _BLOCK
+
+    n = 3
+    chan = np.array([0, 40000, 65535])                     # stored as int16 with TZERO
+    stored = (chan - 32768).astype('>i2')
+    scaled = np.array([10, 20, 30], dtype='>i2')            # value = 0.5 * stored + 1
+    flags = np.array([b'T', b'F', b'T'])
+    names = [b'ab  ', b'c   ', b'    ']
+    var = [np.array([1.5, 2.5], dtype='>f8'), np.zeros(0, dtype='>f8'), np.array([7.0], dtype='>f8')]
+    heap = b''.join(v.tobytes() for v in var)
+    rows, off = [], 0
+    for i in range(n):
+        desc = struct.pack('>qq', len(var[i]), off)
+        off += var[i].nbytes
+        rows.append(stored[i:i + 1].tobytes() + scaled[i:i + 1].tobytes() + flags[i] + names[i] + desc)
+    row_bytes = len(rows[0])
+    cards = [('XTENSION', 'BINTABLE'), ('BITPIX', 8), ('NAXIS', 2), ('NAXIS1', row_bytes), ('NAXIS2', n),
+             ('PCOUNT', len(heap)), ('GCOUNT', 1), ('TFIELDS', 5),
+             ('TTYPE1', 'CHANNEL'), ('TFORM1', '1I'), ('TZERO1', 32768), ('TSCAL1', 1),
+             ('TTYPE2', 'SCALED'), ('TFORM2', 'I'), ('TSCAL2', 0.5), ('TZERO2', 1.0),
+             ('TTYPE3', 'FLAG'), ('TFORM3', '1L'), ('TTYPE4', 'NAME'), ('TFORM4', '4A'),
+             ('TTYPE5', 'VAR'), ('TFORM5', '1QD(2)'), ('EXTNAME', 'THINGS'), ('EXTVER', 2),
+             ('LONGSTR', "it's"), ('EXPOSURE', 1.5e3)]
+    hdr = _header(cards)
+    # splice a HISTORY and a CONTINUE card in front of END (they carry no '= ' value indicator)
+    body = hdr[:80 * len(cards)]
+    body += b'HISTORY made by a test'.ljust(80) + b"CONTINUE  'ignored'".ljust(80) + b'END'.ljust(80)
+    hdr = body + b' ' * (-len(body) % _BLOCK)
+    data = b''.join(rows) + heap
+    primary = _header([('SIMPLE', True), ('BITPIX', 16), ('NAXIS', 2), ('NAXIS1', 3), ('NAXIS2', 2), ('EXTEND', True)])
+    image = np.arange(6, dtype='>i2').tobytes()              # a primary image to be skipped over
+    p = tmp_path / 't.fits'
+    p.write_bytes(primary + image + bytes(-len(image) % _BLOCK) + hdr + data + bytes(-len(data) % _BLOCK))
+    hdus = read_fits(str(p))
+    assert [h.name for h in hdus] == ['PRIMARY', 'THINGS'] and hdus[1].ver == 2
+    h = hdus[1]
+    assert h.header['LONGSTR'] == "it's" and h.header['EXPOSURE'] == 1500.0 and 'HISTORY' not in h.header
+    assert np.array_equal(h['CHANNEL'], chan) and h['CHANNEL'].dtype.kind == 'i'
+    assert np.allclose(h['SCALED'], [6.0, 11.0, 16.0])
+    assert h['FLAG'].tolist() == [True, False, True] and h['NAME'].tolist() == ['ab', 'c', '']
+    assert [v.tolist() for v in h['VAR']] == [[1.5, 2.5], [], [7.0]]
