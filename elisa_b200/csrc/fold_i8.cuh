@@ -320,6 +320,36 @@ __device__ __forceinline__ double i32_to_f64(int32_t v) {
     return __hiloint2double(0x43300000, v ^ (int32_t)0x80000000) - 4503601774854144.0;  // 2^52 + 2^31
 }
 
+// Two neighbouring orders are first merged in integer arithmetic, p = 256 acc_2j + acc_2j+1
+// (one IMAD.WIDE; |p| < 2^40 under the int32 headroom rule), and the int64 is converted by the
+// same trick: bits(1.5 * 2^52) + p is the double 1.5 * 2^52 + p.  The _m8 variant uses the
+// exponent of 2^44, whose unit in the last place is 2^-8, and returns p / 256.  Halves the FP64
+// instructions of the recombination (the gradient epilogue stalls on the FP64 pipe).
+__device__ __forceinline__ double i64_to_f64(long long p) {
+    return __longlong_as_double(0x4338000000000000LL + p) - 6755399441055744.0;  // 1.5 * 2^52
+}
+__device__ __forceinline__ double i64_to_f64_m8(long long p) {
+    return __longlong_as_double(0x42B8000000000000LL + p) - 26388279066624.0;  // 1.5 * 2^44
+}
+
+// x = sum_o acc_o 256^-o for one element, acc(o) = accumulator of order o
+template <int KS, class Acc>
+__device__ __forceinline__ double i8_recombine(const Acc& acc) {
+    static_assert(KS >= 4, "at least two pairs of orders");
+    constexpr int NP = KS / 2;  // pairs (2j, 2j + 1); an odd KS leaves order KS - 1 on its own
+    auto pair = [&](int j) { return (long long)acc(2 * j) * 256 + (long long)acc(2 * j + 1); };
+    // T = sum_{j >= 1} 65536^-(j-1) p_j (+ the odd order), Horner from the least significant end
+    double T;
+    if (KS & 1) {
+        T = fma(i32_to_f64(acc(KS - 1)), 0.00390625, i64_to_f64(pair(NP - 1)));
+    } else {
+        T = i64_to_f64(pair(NP - 1));
+    }
+#pragma unroll
+    for (int j = NP - 2; j >= 1; --j) T = fma(T, 1.52587890625e-05, i64_to_f64(pair(j)));  // 2^-16
+    return fma(T, 5.9604644775390625e-08, i64_to_f64_m8(pair(0)));  // 2^-24 T + p_0 / 256
+}
+
 // Epilogue register layout ("quad layout").  A warp owns 32 rows (its TMEM lane quarter) x 16
 // columns (its column group) of the tile and reads them with tcgen05.ld.16x256b.x2: thread
 // (r = lane / 4, q = lane % 4) receives rows r + 8 k (k = 0..3) and columns
@@ -353,10 +383,8 @@ __device__ __forceinline__ void i8_combine_quad(uint32_t taddr, double (&x)[4][I
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 // registers: {0,1} row r cols 2q,2q+1 | {2,3} row r+8 | {4,5} row r cols 8+2q.. | {6,7} row r+8
-                double t = i32_to_f64(v[KS - 1][e]);
-#pragma unroll
-                for (int d = KS - 2; d >= 0; --d) t = fma(t, 0.00390625, i32_to_f64(v[d][e]));
-                x[2 * h + ((e >> 1) & 1)][4 * b + (e & 1) + 2 * (e >> 2)] = t;
+                x[2 * h + ((e >> 1) & 1)][4 * b + (e & 1) + 2 * (e >> 2)] =
+                    i8_recombine<KS>([&](int d) { return v[d][e]; });
             }
         }
     }
