@@ -400,11 +400,15 @@ __device__ __forceinline__ void i8_combine_quad(uint32_t taddr, double (&x)[4][I
 // Epilogue interface (quad layout above; row0 = first row of the thread, c0 = first column of
 // the warp's group in the tile's matrix, q = lane % 4):
 //   State st; epi.begin(st)                      once per group
-//   epi.prefetch(row0 + 8 q, c0)                 before the tile's accumulators are awaited
+//   epi.prefetch(row_acc, c0)                    before the tile's accumulators are awaited
 //   epi.tile(st, x, row0, c0, q, sb)             x[k][m] recombined (unscaled) dot products,
 //                                                sb = column scales of the warp's 16 columns
-//   epi.end(st, group, cg, row0 + 8 q, sa)       once per group: the thread's row partial
+//   epi.end(st, group, cg, row_acc, sa)          once per group: the thread's row partial
 constexpr int I8_GROUP = 4;
+
+// the row (k of row0 + 8 k) whose partial thread q of a quad keeps after the transposing butterfly
+// of the fused reductions: q = 0, 1, 2, 3 -> k = 0, 2, 1, 3
+__device__ __forceinline__ int i8_quad_row(int q) { return 2 * (q & 1) + (q >> 1); }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -595,7 +599,7 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const I8Item it = i8_item(a, item);
             const int row0 = it.mt * I8_BM + quarter * 32 + r;  // the thread's rows: row0 + 8 k
-            const int row_acc = row0 + 8 * q;                    // the row whose partial it keeps
+            const int row_acc = row0 + 8 * i8_quad_row(q);       // the row whose partial it keeps
             const double sa = a.a_scale[row_acc];
             typename Epi::State st;
             I8_FOR_EACH_TILE(it, a, nt) {
@@ -688,7 +692,7 @@ struct ChanArrays {
 
 // transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the tile's energies.
 // Per tile and parameter a thread multiplies its 4 rows x 4 columns, the quad adds up each row
-// (two xor shuffles), and thread q keeps the sum of row row0 + 8 q.
+// (a transposing butterfly), and thread q keeps the sum of row row0 + 8 i8_quad_row(q).
 // gpart[(j * n_part + I8_CG * group + cg) * ld_part + row],  n_part = I8_CG * n_groups
 struct I8EpilogueGrad {
     static constexpr int ISSUERS = 2;
@@ -759,12 +763,15 @@ struct I8EpilogueGrad {
                     }
                     s[k] = t;
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
-                    s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
-                }
-                st.rs[p] += (q == 0) ? s[0] : (q == 1) ? s[1] : (q == 2) ? s[2] : s[3];
+                // transposing butterfly over the quad: 3 shuffles + 3 adds instead of 8 + 8 (the four
+                // threads hold partials of the same four rows; each ends up with ONE row's total,
+                // thread q with row i8_quad_row(q))
+                const bool b0 = q & 1, b1 = q & 2;
+                const double r0 = __shfl_xor_sync(0xffffffffu, b0 ? s[0] : s[2], 1);
+                const double r1 = __shfl_xor_sync(0xffffffffu, b0 ? s[1] : s[3], 1);
+                const double k0 = (b0 ? s[2] : s[0]) + r0, k1 = (b0 ? s[3] : s[1]) + r1;
+                const double r2 = __shfl_xor_sync(0xffffffffu, b1 ? k0 : k1, 2);
+                st.rs[p] += (b1 ? k1 : k0) + r2;
             }
         }
     }
