@@ -35,9 +35,9 @@ WORKLOAD = 'cfg2: CutoffPL+Blackbody, wstat, 1024ch x 2048E dense RSP, 1e6 draws
 TRAFFIC = {
     # profiles/r01d_kernels.md: gemm_f64_kernel<Stat> 0.406 + 0.139 GB, <Grad> 1.944 + 0.027 GB
     'dmma': 0.5 * (0.406204 + 0.139177 + 1.943642 + 0.026987) * 1e9,
-    # profiles/r01i_kernels.md: fold_i8_kernel<Store> 0.284 + 0.128 GB, <Grad> 1.907 + 0.068 GB
+    # profiles/r01i_kernels.md: fold_i8_kernel<Store> 0.286 + 0.129 GB, <Grad> 1.793 + 0.064 GB
     # (the gradient epilogue streams dU/dtheta: 18944 x 2048 x 5 x 8 B = 1.55 GB per launch)
-    'i8': 0.5 * (0.283930 + 0.128277 + 1.906850 + 0.068478) * 1e9,
+    'i8': 0.5 * (0.285639 + 0.128670 + 1.792700 + 0.064248) * 1e9,
 }
 
 
