@@ -68,6 +68,14 @@ def cpu_oracle_rate(cfg, n_sample, repeats=1, warmup=0):
     specs = [m.to_spec() for m in models]
     datas = [d.as_mapping() for d in cfg['data']]
     theta = torch.as_tensor(cfg['theta'][:n_sample], dtype=torch.float64)
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would
+    # leave the CPU arm single-threaded at N > 1, where rank 0 alone runs it)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    if torch.get_num_threads() < cores:
+        torch.set_num_threads(cores)
     threads = torch.get_num_threads()
     for _ in range(warmup):
         oracle.loglike_and_grad(cfg['stat'], datas, specs, theta)
