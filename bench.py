@@ -10,6 +10,16 @@ CutoffPL + Blackbody with background, wstat, 1024-channel x 2048-energy dense re
 One "step" = one pass of the hot path over the whole batch of draws: value AND gradient
 of the per-spectrum log-likelihood for every draw.  One eval = one (draw x spectrum).
 Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for the fields).
+
+Order of business on the B200 arm (parity gate BEFORE any throughput is recorded):
+  1. the CPU oracle evaluates the first `--cpu-sample` draws (timed: this is the cpu_baseline);
+  2. the GPU path evaluates the whole batch through the guarded entry point; the rows the oracle
+     did are compared (value, gradient column-normwise and row-normwise); above 1e-10 the bench
+     REFUSES to print a value (exit 3);
+  3. timed region: `value` (device-resident theta, guarded entry point, results all-gathered over
+     the ranks inside the region when N > 1), then `e2e` (host buffers through the C ABI);
+  4. the other BASELINE configurations (cfg 1, 3, 4, 5), each with its own parity check and, for
+     N > 1, cfg 5 strong-scaled over the ranks and cfg 3 with 64 / N chains per rank.
 """
 
 from __future__ import annotations
@@ -30,6 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'likelihood+grad evals/sec (samples x spectra)'
 UNIT = 'evals/s'
 WORKLOAD = 'cfg2: CutoffPL+Blackbody, wstat, 1024ch x 2048E dense RSP, 1e6 draws/GPU'
+RTOL = 1e-10  # north star: 1e-10 relative in FP64 on the statistic and its gradient
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the ncu --set full
 # captures under profiles/ (same command, --draws 37888): forward + transposed fold, averaged
 TRAFFIC = {
@@ -39,6 +50,10 @@ TRAFFIC = {
     # (the gradient epilogue streams dU/dtheta: 18944 x 2048 x 5 x 8 B = 1.55 GB per launch)
     'i8': 0.5 * (0.285639 + 0.128670 + 1.792700 + 0.064248) * 1e9,
 }
+try:  # a newer capture overrides the table above (tools/gpu_round.sh writes it next to the ncu summary)
+    TRAFFIC.update(json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))))
+except Exception:
+    pass
 
 
 def parse():
@@ -48,42 +63,78 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--draws', type=int, default=1_000_000, help='parameter draws per GPU and step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--cpu-sample', type=int, default=16384, help='draws of the bounded CPU-baseline sample')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample', type=int, default=16384, help='draws of the bounded CPU-baseline / parity sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU oracle: no cpu_baseline AND no parity gate')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the cfg 1/3/4/5 side measurements')
     ap.add_argument('--fold', default=None, choices=['i8', 'dmma'], help='response-fold engine (default: library default)')
-    ap.add_argument('--slices', type=int, default=0, help='digits of the sliced-integer fold (0 = default 6)')
+    ap.add_argument('--slices', type=int, default=0, help='digits of the sliced-integer fold (0 = default)')
+    ap.add_argument('--slices-bwd', type=int, default=0, help='digits of its transposed fold (0 = default)')
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------- CPU baseline
-def cpu_oracle_rate(cfg, n_sample, repeats=1, warmup=0):
-    """Time the CPU oracle (torch CPU float64, all host threads; batched-GEMM formulation of
-    the reference arithmetic) on the first n_sample draws.  Returns (evals/s, seconds, threads)."""
-    import torch
-
-    import oracle
-
-    models = [m.compile() for m in cfg['model']]
-    specs = [m.to_spec() for m in models]
-    datas = [d.as_mapping() for d in cfg['data']]
-    theta = torch.as_tensor(cfg['theta'][:n_sample], dtype=torch.float64)
-    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would
-    # leave the CPU arm single-threaded at N > 1, where rank 0 alone runs it)
+def host_threads(torch):
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would
+    leave the CPU arm single-threaded at N > 1, where rank 0 alone runs it)."""
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
     if torch.get_num_threads() < cores:
         torch.set_num_threads(cores)
-    threads = torch.get_num_threads()
+    return torch.get_num_threads()
+
+
+def cpu_oracle(cfg, rows, repeats=1, warmup=0):
+    """The CPU oracle (torch CPU float64, all host threads; batched-GEMM formulation of the
+    reference arithmetic) on the given rows of the batch.  Returns
+    (evals/s, seconds per repeat, threads, loglike (n, S), grad (n, S, P)) -- timed as the CPU
+    baseline, and its outputs are what the GPU path is held to."""
+    import torch
+
+    import oracle
+
+    models = [m.compile() if not hasattr(m, 'to_spec') else m for m in cfg['model']]
+    free = []
+    for m in models:
+        for p in m.free:
+            if all(p is not q for q in free):
+                free.append(p)
+    specs = [m.to_spec(free) for m in models]
+    datas = [d.as_mapping() for d in cfg['data']]
+    theta = torch.as_tensor(np.asarray(cfg['theta'])[rows], dtype=torch.float64)
+    on = off = None
+    split = np.cumsum([d.n_channels for d in cfg['data']])[:-1]
+    if cfg.get('counts_on') is not None:
+        on = np.split(np.asarray(cfg['counts_on'])[rows], split, axis=1)
+    if cfg.get('counts_off') is not None:
+        off = np.split(np.asarray(cfg['counts_off'])[rows], split, axis=1)
+    threads = host_threads(torch)
     for _ in range(warmup):
-        oracle.loglike_and_grad(cfg['stat'], datas, specs, theta)
+        oracle.loglike_and_grad(cfg['stat'], datas, specs, theta, on, off)
     t0 = time.perf_counter()
-    for _ in range(repeats):
-        oracle.loglike_and_grad(cfg['stat'], datas, specs, theta)
-    dt = (time.perf_counter() - t0) / repeats
-    return theta.shape[0] * len(datas) / dt, dt, threads
+    for _ in range(max(repeats, 1)):
+        ll, g = oracle.loglike_and_grad(cfg['stat'], datas, specs, theta, on, off)
+    dt = (time.perf_counter() - t0) / max(repeats, 1)
+    return theta.shape[0] * len(datas) / dt, dt, threads, ll.numpy(), g.numpy()
+
+
+def parity_errors(ll, g, ll_ref, g_ref):
+    """Deviation of the GPU path from the oracle on the same rows.  value: |dll| / max(|ll|, 1);
+    gradient column-normwise: relative to the largest |gradient| of that (spectrum, parameter)
+    over the batch; row-normwise: relative to the row's OWN gradient (its largest component in
+    column units), floored at 1e-2 of the column scale (below that the conditioning of the sum
+    over energies costs 1 / s digits in any arithmetic) -- `rownorm_raw` is the unfloored figure."""
+    val = float(np.max(np.abs(ll - ll_ref) / np.maximum(np.abs(ll_ref), 1.0)))
+    col = np.max(np.abs(g_ref), axis=0, keepdims=True)
+    col = np.where(col == 0.0, 1.0, col)
+    d = np.abs(g - g_ref)
+    row = np.max(np.abs(g_ref) / col, axis=-1, keepdims=True)
+    row = np.where(row == 0.0, 1.0, row)
+    return {'rows': int(ll.shape[0]), 'max_rel_value': val, 'max_rel_grad_batchnorm': float(np.max(d / col)),
+            'max_rel_grad_rownorm': float(np.max(d / (col * np.maximum(row, 1e-2)))),
+            'max_rel_grad_rownorm_raw': float(np.max(d / (col * row))), 'min_row_scale': float(np.min(row))}
 
 
 def run_reference(args):
@@ -97,7 +148,7 @@ def run_reference(args):
 
     n = args.cpu_sample
     cfg = synthetic.config2(n=n)
-    rate, dt, threads = cpu_oracle_rate(cfg, n, repeats=max(args.steps, 1), warmup=max(args.warmup, 1))
+    rate, dt, threads, _, _ = cpu_oracle(cfg, slice(0, n), repeats=max(args.steps, 1), warmup=max(args.warmup, 1))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
@@ -159,14 +210,15 @@ class ClockSampler:
             pass
         if sm:
             out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                   'power_w_max': float(max(power)), 'samples': len(sm)}
+                   'power_w_max': float(max(power)), 'power_w_median': float(np.median(power)), 'samples': len(sm)}
         return out
 
 
-# --------------------------------------------------------------------------- B200 arm
+# --------------------------------------------------------------------------- measured peaks
 def measure_dgemm_peak(torch):
-    """cuBLAS DGEMM 8192^3, best of 6 (burst): the FP64 tensor-pipe denominator.
-    MEASURED_PEAKS.json carries no FP64 entry; same recipe as its bf16 figure."""
+    """cuBLAS DGEMM 8192^3, best of 6 (burst): the FP64 tensor-pipe figure the integer fold is
+    compared with (`fp64_equiv_speedup`).  MEASURED_PEAKS.json carries no FP64 entry; same recipe
+    as its bf16 figure."""
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device='cuda')
     b = torch.randn(n, n, dtype=torch.float64, device='cuda')
@@ -184,6 +236,171 @@ def measure_dgemm_peak(torch):
     return 2.0 * n**3 / best / 1e9
 
 
+def measure_int8_peak(torch):
+    """cuBLASLt int8 x int8 -> int32 GEMM 8192^3 (torch._int_mm), best of 10 (burst): the MEASURED
+    peak of the pipe the integer fold runs on -- the roofline denominator (TOP/s).  Returns
+    (tops, how) or (None, why)."""
+    n = 8192
+    try:
+        a = torch.randint(-127, 127, (n, n), dtype=torch.int8, device='cuda')
+        b = torch.randint(-127, 127, (n, n), dtype=torch.int8, device='cuda')
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n**3 / best / 1e9, 'cuBLASLt int8 GEMM 8192^3 (torch._int_mm) best-of-10 measured in this run'
+    except Exception as e:  # pragma: no cover - depends on the torch build
+        return None, f'torch._int_mm unavailable ({type(e).__name__})'
+
+
+# --------------------------------------------------------------------------- side configurations
+def _time_calls(torch, fn, reps):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def side_configs(torch, dist, world, rank, local, with_oracle):
+    """cfg 1, 3, 4, 5 of BASELINE.json in the same run: evals/s (device-resident inputs, guarded
+    entry point), fold engine, and a parity check of a row sample against the oracle.  Under
+    torchrun cfg 5 is STRONG-scaled (1e6 draws x 16 spectra split over the ranks, results
+    all-gathered inside the timed region) and cfg 3 runs 64 / N chains per rank."""
+    from elisa_b200 import Likelihood, synthetic
+    from elisa_b200.parallel import ShardedLikelihood, shard_bounds
+
+    dev = f'cuda:{local}'
+    out = {}
+
+    def parity_of(cfg, lk, n_rows, **kw):
+        if not with_oracle:
+            return None
+        n = len(cfg['theta'])
+        rows = np.sort(np.random.default_rng(0).choice(n, size=min(n_rows, n), replace=False))
+        _, _, _, ll_ref, g_ref = cpu_oracle(cfg, rows)
+        sub_kw = {k: (None if v is None else torch.as_tensor(np.asarray(v)[rows], dtype=torch.float64, device=dev)) for k, v in kw.items()}
+        ll, g = lk.loglike_and_grad(torch.as_tensor(np.asarray(cfg['theta'])[rows], dtype=torch.float64, device=dev), **sub_kw)
+        return parity_errors(ll.cpu().numpy(), g.cpu().numpy(), ll_ref, g_ref)
+
+    def engine(lk):
+        fs, fb = lk.fold_slices, lk.fold_slices_bwd
+        return 'int8 tcgen05 sliced %d/%d digits' % (fs[0], fb[0]) if fs[0] else 'FP64 DMMA'
+
+    # ---- cfg 1: PowerLaw, cstat, dense 1024 x 2048 (the reference's own CPU-runnable case, batched)
+    if rank == 0:
+        cfg = synthetic.config1(n=200_000)
+        lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
+        th = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+        ms = _time_calls(torch, lambda: lk.loglike_and_grad(th), 3)
+        out['cfg1'] = {'what': 'PowerLaw cstat 1024ch x 2048E dense, 2e5 draws, 1 GPU', 'evals_s': len(th) / ms * 1e3, 'ms': ms,
+                       'engine': engine(lk), 'parity': parity_of(cfg, lk, 256), 'fallback_rows': lk.fallback_rows}
+        lk.close()
+        del th
+    # ---- cfg 3: Band, 4 GBM-like detectors, pgstat, 64 chains (8 per GPU at N = 8): latency per leapfrog
+    cfg = synthetic.config3(n=64)
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, guard='lazy')
+    lo, hi = shard_bounds(64, world)[rank]
+    th = torch.as_tensor(cfg['theta'][lo:hi], dtype=torch.float64, device=dev)
+    sh = ShardedLikelihood(lk)
+    full = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+    for _ in range(5):
+        lk.loglike_and_grad(th)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(300):
+        lk.loglike_and_grad(th)
+    torch.cuda.synchronize()
+    us_local = (time.perf_counter() - t0) / 300 * 1e6
+    us_gather = None
+    if world > 1:
+        for _ in range(5):
+            sh.loglike_and_grad(full)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            sh.loglike_and_grad(full)
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) / 300 * 1e6], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us_gather = float(t.item())
+    t = torch.tensor([us_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        lk_sync = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
+        out['cfg3'] = {'what': 'Band pgstat, 4 detectors 128ch x 140E, 64 chains over %d GPU(s): one leapfrog = one value+gradient '
+                               'call through the Python API (guard=lazy: no host synchronisation, CUDA graph replayed)' % world,
+                       'chains_per_gpu': hi - lo, 'us_per_leapfrog': float(t.item()), 'us_per_leapfrog_with_gather': us_gather,
+                       'evals_s': 64 * 4 / ((us_gather or float(t.item())) * 1e-6), 'engine': engine(lk),
+                       'parity': parity_of(cfg, lk_sync, 64)}
+        lk_sync.close()
+    lk.close()
+    # ---- cfg 4: Gauss + PowerLaw, chi2, 4096 x 4096 band-sparse, per-replica counts
+    if rank == 0:
+        n4 = 20_000
+        cfg = synthetic.config4(n=n4)
+        lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
+        th = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+        on = torch.as_tensor(cfg['counts_on'], dtype=torch.float64, device=dev)
+        ms = _time_calls(torch, lambda: lk.loglike_and_grad(th, counts_on=on), 3)
+        d = cfg['data'][0]
+        nnz = int(len(d.sparse_matrix[2]))
+        out['cfg4'] = {'what': 'Gauss+PowerLaw chi2 4096 x 4096 band-sparse (nnz %d), 2e4 replicas with their own counts, 1 GPU' % nnz,
+                       'evals_s': n4 / ms * 1e3, 'ms': ms, 'engine': engine(lk),
+                       'parity': parity_of(cfg, lk, 48, counts_on=cfg['counts_on']),
+                       'useful_tflops_4nnz': 4.0 * nnz * n4 / ms / 1e9,
+                       'io_gbs_per_replica_arrays': 8.0 * (d.n_channels + 5 + 6) * n4 / ms / 1e6}
+        lk.close()
+        del th, on, cfg
+    # ---- cfg 5: 16 spectra, distinct dense responses, cstat / chi2, 1e6 draws STRONG-scaled over the ranks
+    n5 = 1_000_000
+    cfg = synthetic.config5(n=n5, S=16)
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
+    sh = ShardedLikelihood(lk)
+    th = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+    sh.loglike_and_grad(th)  # warm-up (also balances the plan)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ll5, g5 = sh.loglike_and_grad(th)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item())
+        par = None
+        if with_oracle:
+            rows = np.sort(np.random.default_rng(0).choice(n5, size=64, replace=False))
+            _, _, _, ll_ref, g_ref = cpu_oracle(cfg, rows)
+            par = parity_errors(ll5[rows].cpu().numpy(), g5[rows].cpu().numpy(), ll_ref, g_ref)
+        out['cfg5'] = {'what': 'PowerLaw jointly on 16 spectra (distinct dense 1024 x 2048 RSPs, cstat / chi2), 1e6 draws split over '
+                               '%d GPU(s), all-gather of [N,16] + [N,16,2] inside the timed region (strong scaling)' % world,
+                       'evals_s': n5 * 16 / ms * 1e3, 'ms': ms, 'n_gpus': world, 'engine': engine(lk), 'parity': par,
+                       'fallback_rows': lk.fallback_rows}
+    lk.close()
+    return out
+
+
+# --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -205,30 +422,79 @@ def run_b200(args):
         cfg['theta'] = synthetic._theta_batch(cfg['truth'], n, 5 + 1000 * rank)
     d = cfg['data'][0]
     E, C, S = d.n_energies, d.n_channels, len(cfg['data'])
-    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, fold=args.fold, slices=args.slices)
-    ks = lk.fold_slices[0]
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, fold=args.fold, slices=args.slices,
+                    slices_bwd=args.slices_bwd)
+    ks, ks_bwd = lk.fold_slices[0], lk.fold_slices_bwd[0]
     P = lk.nparam
-    theta = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=f'cuda:{local}')
-    ll = torch.empty((n, S), dtype=torch.float64, device=theta.device)
-    grad = torch.empty((n, S, P), dtype=torch.float64, device=theta.device)
+    dev = f'cuda:{local}'
+    theta = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+    ll = torch.empty((n, S), dtype=torch.float64, device=dev)
+    grad = torch.empty((n, S, P), dtype=torch.float64, device=dev)
+    # results of all ranks, gathered inside the timed region (the one collective)
+    ll_all = torch.empty((world * n, S), dtype=torch.float64, device=dev) if world > 1 else None
+    grad_all = torch.empty((world * n, S, P), dtype=torch.float64, device=dev) if world > 1 else None
 
     import ctypes as Ct
 
     from elisa_b200 import _lib
 
     stream = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fb = Ct.c_int64(0)
+    fb_rows = [0]
+    ev_g0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
-    def step():
-        _lib.check(lk._lib.elisa_b200_loglike_grad_dev(lk._h, Ct.c_void_p(theta.data_ptr()), None, None, n,
-                                                       Ct.c_void_p(ll.data_ptr()), Ct.c_void_p(grad.data_ptr()), stream))
+    def step(i=None):
+        # the GUARDED device entry point: flagged rows are re-evaluated with the FP64 DMMA fold
+        _lib.check(lk._lib.elisa_b200_loglike_grad_guarded_dev(
+            lk._h, Ct.c_void_p(theta.data_ptr()), None, None, n, Ct.c_void_p(ll.data_ptr()), Ct.c_void_p(grad.data_ptr()),
+            stream, Ct.byref(fb)))
+        fb_rows[0] += int(fb.value)
+        if world > 1:
+            if i is not None:
+                ev_g0[i].record()
+            dist.all_gather_into_tensor(ll_all, ll)
+            dist.all_gather_into_tensor(grad_all, grad)
+            if i is not None:
+                ev_g1[i].record()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    fp64_peak = measure_dgemm_peak(torch) if rank == 0 else None
+    # ---- 1. CPU oracle on the parity sample (timed: the cpu_baseline), then the parity gate
+    cpu = parity = None
+    ns = min(args.cpu_sample, n)
+    with_oracle = not args.no_cpu_baseline
+    if with_oracle and rank == 0:
+        rate, dt, threads, ll_ref, g_ref = cpu_oracle(cfg, slice(0, ns), repeats=2, warmup=1)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'first {ns} of the {n} draws, 2 timed repeats ({dt:.2f} s each), torch CPU float64 oracle; '
+                         'the reference JAX path cannot be installed offline'}
+    step()
+    torch.cuda.synchronize()
+    flagged, worst = lk.fold_guard(reset=False)
+    if with_oracle and rank == 0:
+        parity = parity_errors(ll[:ns].cpu().numpy(), grad[:ns].cpu().numpy(), ll_ref, g_ref)
+        parity.update({'tolerance': RTOL, 'guard_flagged': flagged, 'guard_worst_estimate': worst,
+                       'guard_fallback_rows': fb_rows[0], 'guard_fallbacks': int(lk._lib.elisa_b200_plan_guard_fallbacks(lk._h)),
+                       'arm': 'value and e2e both run the guarded entry points (elisa_b200_loglike_grad_guarded_dev / _host)'})
+        ok = (parity['max_rel_value'] <= RTOL and parity['max_rel_grad_batchnorm'] <= RTOL and
+              parity['max_rel_grad_rownorm'] <= RTOL)
+        parity['pass'] = bool(ok)
+        if not ok:
+            sys.stderr.write('PARITY GATE FAILED, no throughput recorded: ' + json.dumps(parity) + '\n')
+            print(json.dumps({'metric': METRIC, 'value': None, 'unit': UNIT, 'n_gpus': world, 'parity': parity,
+                              'error': 'parity gate failed'}), flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            raise SystemExit(3)
 
+    fp64_peak = measure_dgemm_peak(torch) if rank == 0 else None
+    int8_peak, int8_how = measure_int8_peak(torch) if rank == 0 else (None, None)
+
+    # ---- 2. timed region
     for _ in range(args.warmup):
         step()
     barrier()
@@ -237,11 +503,12 @@ def run_b200(args):
         sampler.start()
     lk.set_profiling(True)
     launches0 = lk.launch_count
+    fb_rows[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        step(i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -249,13 +516,14 @@ def run_b200(args):
     prof = lk.get_profile()
     lk.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=theta.device)
+    gather_ms = sum(a.elapsed_time(b) for a, b in zip(ev_g0, ev_g1)) / args.steps if world > 1 else 0.0
+    t = torch.tensor([ms, gather_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max, gather_ms = float(t[0].item()), float(t[1].item())
     value = world * n * S * args.steps / (ms_max * 1e-3)
 
-    # ---- end to end: host buffers through the C ABI, H2D + D2H inside the timed region
+    # ---- 3. end to end: host buffers through the C ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
         th_host = torch.empty((n, P), dtype=torch.float64).pin_memory()
@@ -276,12 +544,22 @@ def run_b200(args):
             step_host()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=theta.device)
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {'value': world * n * S * args.steps / float(tt.item()), 'unit': UNIT,
                'h2d_bytes_per_step': int(th_host.numel() * 8), 'd2h_bytes_per_step': int((ll_host.numel() + g_host.numel()) * 8)}
-        assert torch.equal(ll_host, ll.cpu()), 'host and device paths disagree'
+        assert torch.equal(ll_host, ll.cpu()) and torch.equal(g_host, grad.cpu()), 'host and device paths disagree'
+        del th_host, ll_host, g_host
+
+    # ---- 4. the other BASELINE configurations (all ranks take part in the sharded ones)
+    del ll_all, grad_all
+    lk_chunk, lk_ws = lk.chunk, lk.workspace_bytes
+    configs = None
+    if not args.no_configs:
+        lk.close()
+        torch.cuda.empty_cache()
+        configs = side_configs(torch, dist, world, rank, local, with_oracle)
 
     if rank != 0:
         if world > 1:
@@ -294,60 +572,65 @@ def run_b200(args):
     gemm_ms = fold_ms + tfold_ms
     gemm_launches = fold_n + tfold_n
     flops_total = 4.0 * E * C * n * S * args.steps  # 2 E C per eval and fold, both folds
-    achieved = flops_total / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    roofline = {
-        'bound': 'tensor',
-        'kernel': ('fold_i8_kernel (forward + transposed fold; int8 tcgen05.mma, %d digits per operand, %d digit '
-                   'products per FP64 product, int32 accumulation in TMEM)' % (ks, ks * (ks + 1) // 2)) if ks else
-                  'gemm_f64_kernel (forward + transposed fold, FP64 DMMA)',
-        'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-        'frac': achieved / fp64_peak if achieved and fp64_peak else None,
-        'peak_source': 'cuBLAS DGEMM 8192^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no FP64 entry); '
-                       'achieved = ALGORITHMIC FP64 flops (4 E C per eval) / device time of the fold kernels',
-        'traffic': TRAFFIC.get('i8' if ks else 'dmma'),
-        'avg_launch_ms': gemm_ms / gemm_launches if gemm_launches else None,
-        'flop_per_launch': flops_total / gemm_launches if gemm_launches else None,
-        'share_of_step': gemm_ms / ms if ms > 0 else None,
-        'classes_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
-        'whole_path_frac': (4.0 * E * C * n * S * args.steps / (ms * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
-    }
+    fp64_equiv = flops_total / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    classes = {k: v[0] / args.steps for k, v in prof.items()}
     if ks:
-        # the integer engine beats the FP64 pipe roofline by construction: also report the int8
-        # work it executes against the int8 tensor peak (nominal dense 4500 TOP/s; bf16 burst in
-        # MEASURED_PEAKS.json x 2 as the measured stand-in)
-        int8_ops = flops_total * (ks * (ks + 1) // 2)
-        int8_tops = int8_ops / (gemm_ms * 1e-3) / 1e12
+        # the ALGORITHMIC unit of the integer engine: one FP64-accurate multiply-add = ks (ks + 1) / 2 exact
+        # int8 digit products; executed int8 ops = 2 E C x products per eval and fold
+        prod_f, prod_b = ks * (ks + 1) // 2, ks_bwd * (ks_bwd + 1) // 2
+        ops_f = 2.0 * E * C * n * S * args.steps * prod_f
+        ops_b = 2.0 * E * C * n * S * args.steps * prod_b
+        tops = (ops_f + ops_b) / (gemm_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        int8_peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
-        roofline['int8'] = {'executed_tops': int8_tops, 'peak_tops': int8_peak,
-                            'peak_source': '2 x measured bf16 burst of MEASURED_PEAKS.json (of measured)' if peaks else
-                                           '2 x 1590 fallback bf16 (of fallback)',
-                            'frac': int8_tops / int8_peak, 'nominal_peak_tops': 4500.0}
-        roofline['note'] = ('frac > 1: the fold is FP64-accurate (parity 1e-10) but runs on the int8 tensor pipe, '
-                            'so the FP64 DMMA roofline does not bound it; int8.frac is the fraction of the pipe it '
-                            'does run on')
-
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        ns = min(args.cpu_sample, n)
-        rate, dt, threads = cpu_oracle_rate(cfg, ns, repeats=2, warmup=1)
-        cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': f'first {ns} of the {n} draws, 2 timed repeats ({dt:.2f} s each), torch CPU float64 oracle; '
-                         'the reference JAX path cannot be installed offline'}
+        if int8_peak:
+            peak, how = int8_peak, int8_how
+        else:
+            peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
+            how = ('2 x measured bf16 burst of MEASURED_PEAKS.json' if peaks else '2 x 1590 fallback bf16') + f' ({int8_how})'
+        roofline = {
+            'bound': 'tensor',
+            'kernel': 'fold_i8_kernel (forward + transposed fold; int8 tcgen05.mma, %d / %d digits per operand = %d + %d exact '
+                      'digit products per FP64 product, int32 accumulation in TMEM)' % (ks, ks_bwd, prod_f, prod_b),
+            'achieved': tops, 'peak': peak, 'unit': 'TOP/s', 'frac': tops / peak,
+            'peak_source': how + '; nominal dense int8 4500 TOP/s; achieved = int8 ops the digit products execute '
+                                 '(2 E C x products per eval and fold) / device time of the fold kernels',
+            'per_kernel': {'forward': {'ms_per_step': fold_ms / args.steps, 'tops': ops_f / (fold_ms * 1e-3) / 1e12 if fold_ms else None},
+                           'transposed': {'ms_per_step': tfold_ms / args.steps, 'tops': ops_b / (tfold_ms * 1e-3) / 1e12 if tfold_ms else None}},
+            'fp64_equiv_tflops': fp64_equiv, 'fp64_dgemm_tflops': fp64_peak,
+            'fp64_equiv_speedup': fp64_equiv / fp64_peak if fp64_equiv and fp64_peak else None,
+            'fp64_note': 'fp64_equiv = ALGORITHMIC FP64 flops (4 E C per eval) / fold time; speedup over the cuBLAS DGEMM '
+                         '8192^3 rate measured in this run (the FP64 pipe the DMMA engine is bound by) -- not a roofline fraction',
+        }
+    else:
+        roofline = {'bound': 'tensor', 'kernel': 'gemm_f64_kernel (forward + transposed fold, FP64 DMMA)', 'achieved': fp64_equiv,
+                    'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fp64_equiv / fp64_peak if fp64_equiv and fp64_peak else None,
+                    'peak_source': 'cuBLAS DGEMM 8192^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no FP64 entry)'}
+    roofline.update({
+        'traffic': TRAFFIC.get('i8' if ks else 'dmma'),
+        'avg_launch_ms': gemm_ms / gemm_launches if gemm_launches else None,
+        'flop_per_launch': flops_total / gemm_launches if gemm_launches else None,
+        'share_of_step': gemm_ms / ms if ms > 0 else None,
+        'classes_ms_per_step': classes,
+        'tensor_pipe_share_of_step': gemm_ms / ms if ms > 0 else None,
+    })
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'draws_per_gpu': n, 'spectra': S, 'n_energies': E, 'n_channels': C,
-                   'n_params': P, 'chunk': lk.chunk, 'parallelism': f'dp{world} over draws',
-                   'fold_engine': f'int8 tcgen05 sliced, {ks} digits' if ks else 'FP64 DMMA',
-                   'l2': 'inputs larger than L2 (per-chunk workspace 2 GB, theta 40 MB)'},
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+                   'n_params': P, 'chunk': lk_chunk, 'parallelism': f'dp{world} over draws',
+                   'fold_engine': f'int8 tcgen05 sliced, {ks} digits forward / {ks_bwd} transposed' if ks else 'FP64 DMMA',
+                   'entry_point': 'elisa_b200_loglike_grad_guarded_dev (value), elisa_b200_loglike_grad_host (e2e)',
+                   'collective': ('NCCL all_gather_into_tensor of loglike [N,S] and grad [N,S,P] of all ranks inside the timed '
+                                  'region, %.3f ms per step' % gather_ms) if world > 1 else 'none (1 GPU)',
+                   'l2': 'inputs larger than L2 (per-chunk workspace %.1f GB, theta 40 MB)' % (lk_ws / 1e9)},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'parity': parity, 'gather_ms': gather_ms,
+        'guard_fallback_rows_timed': fb_rows[0], 'roofline': roofline, 'cpu_baseline': cpu, 'configs': configs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

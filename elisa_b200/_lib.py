@@ -8,10 +8,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_COMP_PARAMS = 5
-MAX_COMPONENTS = 8
-MAX_PARAMS = 16
+MAX_COMPONENTS = 16
+MAX_PARAMS = 32
 OP_ADD = -1
 OP_MUL = -2
 OP_NORM0 = -16
@@ -23,6 +23,7 @@ FLAG_FOLD_DMMA = 4
 FLAG_FOLD_I8 = 8
 FLAG_NO_BALANCE = 16
 FLAG_FOLD_SLICES_SHIFT = 8
+FLAG_FOLD_SLICES_BWD_SHIFT = 12
 METHOD = {'trapz': 0, 'simpson': 1}
 STAT = {'chi2': 0, 'cstat': 1, 'pstat': 2, 'pgstat': 3, 'wstat': 4}
 ERRORS = {-1: 'ELISA_ERR_INVALID', -2: 'ELISA_ERR_CUDA', -3: 'ELISA_ERR_UNSUPPORTED', -4: 'ELISA_ERR_NOMEM'}
@@ -125,10 +126,17 @@ SYMBOLS = {
     'elisa_b200_plan_fold_slices': (C.c_int, [_VP, C.c_int32]),
     'elisa_b200_plan_set_fold': (C.c_int, [_VP, C.c_int]),
     'elisa_b200_plan_guard_fallbacks': (C.c_int64, [_VP]),
+    'elisa_b200_plan_guard_stats': (C.c_int, [_VP, C.POINTER(C.c_int64)]),
     'elisa_b200_plan_fold_guard': (C.c_int, [_VP, C.POINTER(C.c_int64), c_double_p, C.c_int]),
     'elisa_b200_sliced_gemm_dev': (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             _VP, C.c_int64, c_double_p, _VP]),
     'elisa_b200_plan_rebalance': (C.c_int, [_VP]),
+    'elisa_b200_loglike_grad_guarded_dev': (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
+    'elisa_b200_plan_guard_snapshot': (C.c_int, [_VP, _VP]),
+    'elisa_b200_plan_guard_poll': (C.c_int, [_VP, C.c_int, C.POINTER(C.c_int64), c_double_p]),
+    'elisa_b200_jacobian_dev': (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    'elisa_b200_plan_set_debug': (C.c_int, [_VP, C.c_int32]),
+    'elisa_b200_plan_fold_slices_bwd': (C.c_int, [_VP, C.c_int32]),
     'elisa_b200_abi_version': (C.c_int, []),
     'elisa_b200_sizeof': (C.c_int64, [C.c_int32]),
     'elisa_b200_last_error': (C.c_char_p, []),

@@ -78,5 +78,42 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+XLA_SRC = os.path.join(HERE, 'csrc', 'elisa_b200_xla.cc')
+XLA_LIB = os.path.join(HERE, 'lib', 'libelisa_b200_xla.so')
+
+
+def xla_ffi_include_dir() -> str | None:
+    """Where xla/ffi/api/ffi.h lives (jax.ffi.include_dir()), or None when JAX is not installed --
+    the case in the image this library is developed in."""
+    try:
+        import jax  # noqa: F401
+        from jax import ffi as jffi
+
+        d = jffi.include_dir()
+    except Exception:
+        return None
+    return d if os.path.exists(os.path.join(d, 'xla', 'ffi', 'api', 'ffi.h')) else None
+
+
+def build_xla_shim(force: bool = False) -> str | None:
+    """Compile csrc/elisa_b200_xla.cc -> lib/libelisa_b200_xla.so (the jax.ffi handlers of
+    INTEGRATION.md section 4) when the XLA FFI headers are present; returns None (and builds
+    nothing) when they are not."""
+    inc = xla_ffi_include_dir()
+    if inc is None:
+        return None
+    if not force and os.path.exists(XLA_LIB) and os.path.getmtime(XLA_LIB) >= max(os.path.getmtime(XLA_SRC), os.path.getmtime(LIB)):
+        return XLA_LIB
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-I', inc, '-I', INCLUDE, '-o', XLA_LIB, XLA_SRC,
+           '-L', os.path.dirname(LIB), '-lelisa_b200', '-Wl,-rpath,$ORIGIN']
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('building the XLA FFI shim failed')
+    return XLA_LIB
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    shim = build_xla_shim(force='--force' in sys.argv)
+    print(shim if shim else 'XLA FFI headers not found (jax absent): csrc/elisa_b200_xla.cc not built')

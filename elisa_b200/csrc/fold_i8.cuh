@@ -412,6 +412,23 @@ __device__ __forceinline__ int i8_quad_row(int q) { return 2 * (q & 1) + (q >> 1
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Streaming access for data that crosses HBM exactly once (the dU/dtheta planes: written by the
+// unfold kernel, read once by the gradient epilogue, 1.5 GB per chunk against a 126 MB L2): no L1
+// allocation and an evict-first L2 policy, so that the stream does not push the folds' operand
+// images -- which ARE re-read, by every CTA working on the same row tile -- out of L2.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double* p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
 // item -> (row tile, first column tile, one past the last column tile)
 struct I8Item {
     int mt, g;
@@ -694,24 +711,25 @@ struct ChanArrays {
 // Per tile and parameter a thread multiplies its 4 rows x 4 columns, the quad adds up each row
 // (a transposing butterfly), and thread q keeps the sum of row row0 + 8 i8_quad_row(q).
 // gpart[(j * n_part + I8_CG * group + cg) * ld_part + row],  n_part = I8_CG * n_groups
+constexpr int I8_GRAD_PMAX = 16;  // parameters per launch of the gradient epilogue (register budget)
 struct I8EpilogueGrad {
     static constexpr int ISSUERS = 2;
-    const double* dU;  // [P, rows, ldu]
+    const double* dU;  // [P, rows, ldu], already offset to plane p0
     int64_t plane;
     int32_t ldu;
-    int32_t P;
-    uint32_t used_mask;
+    int32_t P;           // parameters of this launch: theta columns p0 .. p0 + P - 1, P <= I8_GRAD_PMAX
+    uint32_t used_mask;  // bit j: column p0 + j is used by the model
     int32_t n_part;
-    double* gpart;
+    double* gpart;       // already offset to plane p0
     int32_t ld_part;
-    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = L2 prefetch of the tile's dU lines
+    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = L2 prefetch of the tile's dU lines, 128 = streaming (L1 no-allocate, L2 evict-first) dU loads
 
     struct State {
-        double rs[ELISA_MAX_PARAMS];
+        double rs[I8_GRAD_PMAX];
     };
     __device__ __forceinline__ void begin(State& st) const {
 #pragma unroll
-        for (int j = 0; j < ELISA_MAX_PARAMS; ++j) st.rs[j] = 0.0;
+        for (int j = 0; j < I8_GRAD_PMAX; ++j) st.rs[j] = 0.0;
     }
     // Optional (dbg & 64): request the tile's dU lines (one 128-byte line per parameter and row;
     // thread q of a quad takes row row0 + 8 q) from HBM while the tile is still accumulating.
@@ -722,7 +740,7 @@ struct I8EpilogueGrad {
         if (!(dbg & 64)) return;
         const double* base = dU + (size_t)row * ldu + c0;
 #pragma unroll
-        for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
+        for (int p = 0; p < I8_GRAD_PMAX; ++p)
             if (p < P && ((used_mask >> p) & 1u)) {
 #pragma unroll
                 for (int b = 0; b < I8_TC / 16; ++b) prefetch_l2(base + (size_t)p * plane + 16 * b);
@@ -730,7 +748,7 @@ struct I8EpilogueGrad {
     }
     __device__ __forceinline__ void end(State& st, int group, int cg, int row, double sa) const {
 #pragma unroll
-        for (int p = 0; p < ELISA_MAX_PARAMS; ++p)
+        for (int p = 0; p < I8_GRAD_PMAX; ++p)
             if (p < P && ((used_mask >> p) & 1u))
                 gpart[((size_t)p * n_part + I8_CG * group + cg) * ld_part + row] = st.rs[p] * sa;
     }
@@ -747,8 +765,9 @@ struct I8EpilogueGrad {
             }
         }
         const double* base = dU + (size_t)row0 * ldu + c0;
+        const unsigned long long pol = l2_policy_evict_first();
 #pragma unroll
-        for (int p = 0; p < ELISA_MAX_PARAMS; ++p) {
+        for (int p = 0; p < I8_GRAD_PMAX; ++p) {
             if (p < P && ((used_mask >> p) & 1u)) {
                 const double* src = base + (size_t)p * plane;
                 double s[4];
@@ -757,8 +776,10 @@ struct I8EpilogueGrad {
                     double t = 0.0;
 #pragma unroll
                     for (int m = 0; m < I8_NM; m += 2) {
-                        const double2 v = (dbg & 32) ? make_double2(g[k][m], g[k][m + 1])
-                                                     : *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu + i8_col(m, q));
+                        const double* ptr = src + (size_t)(8 * k) * ldu + i8_col(m, q);
+                        const double2 v = (dbg & 32)    ? make_double2(g[k][m], g[k][m + 1])
+                                          : (dbg & 128) ? ld_stream_f64x2(ptr, pol)
+                                                        : *reinterpret_cast<const double2*>(ptr);
                         t = fma(g[k][m + 1], v.y, fma(g[k][m], v.x, t));
                     }
                     s[k] = t;
@@ -802,17 +823,29 @@ struct StatSliceArgs {
     double* scale;
     int32_t kb_total;
     // accuracy guard of the integer fold: colsum[c] = sum_e |R[e, c]|; guard[0] counts the rows
-    // whose estimated log-likelihood error exceeds guard_tol * max(|loglike|, 1), guard[1] keeps
-    // the largest estimate / max(|loglike|, 1) seen (bits of a non-negative double), guard[2] the
-    // largest gradient-side estimate
+    // whose estimated log-likelihood error exceeds guard_tol * max(|loglike|, 1) or whose
+    // gradient-side estimate does (each row once), guard[1] keeps the largest value-side
+    // estimate / max(|loglike|, 1) seen (bits of a non-negative double), guard[2] the largest
+    // gradient-side estimate.  The first flag_cap flagged rows are also listed (global row
+    // index row_base + row, in arrival order) for the per-row DMMA fallback.
     const double* colsum;
     unsigned long long* guard;
-    double guard_eta;  // typical normwise error of the engine, 2^(-8 KS)
-    double guard_grad; // calibration of the gradient-side estimate (see the kernel)
+    int32_t* flag_list;
+    int32_t flag_cap;
+    int64_t row_base;
+    double guard_eta;    // typical normwise error of the forward fold, 2^(-8 KS_forward)
+    double guard_eta_g;  // of the transposed fold, 2^(-8 KS) -- KS is this kernel's template parameter
+    double guard_grad;   // calibration of the gradient-side estimate (see the kernel)
     double guard_tol;
     const double* kinv;  // balancing of the transposed fold: the digits are those of W[c] * kinv[c] (nullptr: 1)
 };
 
+__device__ __forceinline__ void guard_flag_row(const StatSliceArgs& a, int row) {
+    const unsigned long long idx = atomicAdd(a.guard, 1ull);
+    if (a.flag_list != nullptr && idx < (unsigned long long)a.flag_cap) a.flag_list[idx] = (int32_t)(a.row_base + row);
+}
+
+// KS: slices of W (the transposed fold's A operand).
 template <int KS, int STAT, bool GRAD>
 __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) {
     const int lane = threadIdx.x & 31;
@@ -821,7 +854,7 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     const bool live = row < a.n_valid;
     double* x = a.X + (size_t)row * a.ldx;
     double rs = 0.0, amax = 0.0, eb = 0.0, wsum = 0.0;
-    bool bad = false;
+    bool bad = false, flagged = false;
     if (live) {
         const double u_max = a.scale[row] * (double)I8_TOP_DIGIT;  // largest |U| of the row
         const double* con = a.counts_on ? a.counts_on + (size_t)row * a.ld_counts : nullptr;
@@ -867,10 +900,12 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
         if (lane == 0) {
             a.loglike[(size_t)row * a.ll_stride] = rs;
             // first-order estimate of the log-likelihood error the sliced fold may have caused:
-            // sum_c |dl/dx_c| * (typical normwise error of x_c)
+            // sum_c |dl/dx_c| * (typical normwise error of x_c).  A NaN row (NaN parameters) is
+            // NaN under either fold engine and is not flagged.
             const double est = a.guard_eta * u_max * eb / fmax(fabs(rs), 1.0);
-            if (est > a.guard_tol) atomicAdd(a.guard, 1ull);
+            flagged = est > a.guard_tol;
             if (est > 0.0 && est < 1.79e308) atomicMax(a.guard + 1, (unsigned long long)__double_as_longlong(est));
+            if (!GRAD && flagged) guard_flag_row(a, row);
         }
     }
     if (!GRAD) return;
@@ -880,14 +915,17 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
         wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (live && lane == 0 && wsum > 0.0 && !bad) {
-        // gradient side of the guard.  The transposed fold's error is relative to the LARGEST
-        // |W| of the row; when a few starved channels (n >> mu) tower over the rest, the bulk of
-        // the row -- and with it G and the gradient -- keeps fewer digits.  peak / mean of |W|
-        // times the engine's normwise error estimates the relative error of G.
-        const double est_g = a.guard_eta * a.guard_grad * amax * (double)a.C / wsum;
-        if (est_g > a.guard_tol) atomicAdd(a.guard, 1ull);
-        atomicMax(a.guard + 2, (unsigned long long)__double_as_longlong(est_g));
+    if (live && lane == 0) {
+        if (wsum > 0.0 && !bad) {
+            // gradient side of the guard.  The transposed fold's error is relative to the LARGEST
+            // |W| of the row; when a few starved channels (n >> mu) tower over the rest, the bulk of
+            // the row -- and with it G and the gradient -- keeps fewer digits.  peak / mean of |W|
+            // times the engine's normwise error estimates the relative error of G.
+            const double est_g = a.guard_eta_g * a.guard_grad * amax * (double)a.C / wsum;
+            flagged |= est_g > a.guard_tol;
+            atomicMax(a.guard + 2, (unsigned long long)__double_as_longlong(est_g));
+        }
+        if (flagged) guard_flag_row(a, row);
     }
     double f1, f2;
     const double sc = slice_scale<KS>(amax, bad, f1, f2);

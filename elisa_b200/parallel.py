@@ -42,21 +42,38 @@ def world_info(group=None) -> tuple[int, int]:
 
 def all_gather_rows(local, n_total: int, group=None):
     """Concatenate the ranks' row blocks (shard_bounds order) into the full (n_total, ...)
-    tensor on every rank.  Blocks may differ by one row: pad to the largest, gather, trim."""
+    tensor on every rank with ONE ``all_gather_into_tensor``.  Equal blocks (n_total divisible
+    by the world size -- the bench shapes, 64 chains over 8 GPUs) are gathered straight into the
+    result, no staging copy; blocks that differ by one row are gathered into a padded buffer
+    whose layout matches the result except for one spare row per rank, and compacted in place."""
     import torch
 
     dist = _dist()
     rank, world = world_info(group)
     if world == 1:
         return local
+    local = local.contiguous()
     bounds = shard_bounds(n_total, world)
-    width = max(hi - lo for lo, hi in bounds)
-    pad = torch.zeros((width, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    out = torch.empty((world * width, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
-    parts = [out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(bounds)]
-    return torch.cat(parts, dim=0)
+    width = bounds[0][1] - bounds[0][0]  # the largest block (the first ranks carry the extra row)
+    tail = tuple(local.shape[1:])
+    if n_total % world == 0:
+        out = torch.empty((n_total, *tail), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    send = local
+    if local.shape[0] != width:
+        send = torch.empty((width, *tail), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+        send[local.shape[0]:] = 0
+    buf = torch.empty((world * width, *tail), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, send, group=group)
+    # ranks [0, extra) are full; from rank `extra` on each block is one row short: close the gaps
+    extra = n_total % world
+    out = buf[:n_total]
+    for r in range(extra + 1, world):  # block r moves up by (r - extra) rows; regions may overlap -> clone
+        lo, hi = bounds[r]
+        out[lo:hi] = buf[r * width: r * width + (hi - lo)].clone()
+    return out
 
 
 def sharded_map(fn: Callable, args: Sequence, n_total: int, group=None, gather: bool = True):
@@ -82,24 +99,60 @@ class ShardedLikelihood:
         self.lk = likelihood
         self.group = group
 
+    @staticmethod
+    def _rows(theta, counts_on=None, counts_off=None):
+        """Number of rows of the batch and theta as a 2-D array: a 1-D theta is ONE parameter
+        vector, and a single row next to per-replica counts is broadcast over the replicas."""
+        import numpy as np
+        import torch
+
+        if not isinstance(theta, torch.Tensor):
+            theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        elif theta.dim() == 1:
+            theta = theta.unsqueeze(0)
+        n = theta.shape[0]
+        for c in (counts_on, counts_off):
+            if c is not None and n == 1:
+                n = len(c)
+        return theta, n
+
     def loglike(self, theta, counts_on=None, counts_off=None, gather=True):
-        return sharded_map(self.lk.loglike, (theta, counts_on, counts_off), len(theta), self.group, gather)
+        theta, n = self._rows(theta)
+        return sharded_map(self.lk.loglike, (theta, counts_on, counts_off), n, self.group, gather)
 
     def loglike_and_grad(self, theta, counts_on=None, counts_off=None, gather=True):
-        return sharded_map(self.lk.loglike_and_grad, (theta, counts_on, counts_off), len(theta), self.group, gather)
+        theta, n = self._rows(theta)
+        return sharded_map(self.lk.loglike_and_grad, (theta, counts_on, counts_off), n, self.group, gather)
 
     def fit(self, theta0, counts_on=None, counts_off=None, gather=True, **fit_kw):
         """Batched re-fit of this rank's block of replicas (``Likelihood.fit``); with ``gather``
         every rank receives the full ('theta', 'deviance', 'grad_norm', 'n_iter', 'valid')
         -- the reference's ``fit_in_parallel`` (infer/helper.py:690-718) concatenates the
-        per-device results the same way."""
+        per-device results the same way.  ``theta0`` may be one row (or 1-D) broadcast over the
+        replicas of ``counts_on``, as in ``Likelihood.fit``."""
         keys = ('theta', 'deviance', 'grad_norm', 'n_iter', 'valid')
+        theta0, n = self._rows(theta0, counts_on, counts_off)
+        broadcast = theta0.shape[0] == 1 and n > 1
+        rank, world = world_info(self.group)
+        lo, hi = shard_bounds(n, world)[rank]
 
         def local(t, on, off):
+            if hi == lo:  # more ranks than replicas: this rank has nothing to fit
+                import torch
+
+                P = self.lk.nparam
+                dev = f'cuda:{self.lk.device}'
+                z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+                return z(0, P), z(0), z(0), z(0), z(0)
             out = self.lk.fit(t, counts_on=on, counts_off=off, **fit_kw)
             return tuple(out[k].double() for k in keys)  # one dtype for the gather
 
-        res = sharded_map(local, (theta0, counts_on, counts_off), len(theta0), self.group, gather)
+        if broadcast:  # slice the replicas, not the single start vector
+            res = local(theta0, None if counts_on is None else counts_on[lo:hi], None if counts_off is None else counts_off[lo:hi])
+            if gather and world > 1:
+                res = tuple(all_gather_rows(t, n, self.group) for t in res)
+        else:
+            res = sharded_map(local, (theta0, counts_on, counts_off), n, self.group, gather)
         out = dict(zip(keys, res))
         out['n_iter'] = out['n_iter'].long()
         out['valid'] = out['valid'] > 0.5

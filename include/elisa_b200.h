@@ -55,7 +55,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define ELISA_B200_ABI_VERSION 3
+#define ELISA_B200_ABI_VERSION 4
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define ELISA_OK 0
@@ -106,8 +106,8 @@ extern "C" {
 #define ELISA_METHOD_SIMPSON 1
 
 #define ELISA_MAX_COMP_PARAMS 5
-#define ELISA_MAX_COMPONENTS 8 /* leaves of one model expression              */
-#define ELISA_MAX_PARAMS 16    /* columns of theta                            */
+#define ELISA_MAX_COMPONENTS 16 /* leaves of one model expression             */
+#define ELISA_MAX_PARAMS 32     /* columns of theta (normal_eq_dev: <= 16)    */
 
 /* postfix opcodes of the model expression (models/model.py:1285-1295): an entry >= 0
  * pushes the bin values of component #entry, ELISA_OP_ADD / ELISA_OP_MUL pop two
@@ -245,7 +245,13 @@ typedef struct ElisaPlanDesc {
 #define ELISA_FLAG_FOLD_I8 8
 #define ELISA_FLAG_NO_BALANCE 16 /* integer fold without column balancing (see elisa_b200_plan_rebalance) */
 #define ELISA_FLAG_FOLD_SLICES_SHIFT 8
+/* Slices of the TRANSPOSED fold (W . R^T, the gradient side): bits 12-15 of flags (4..7; 0 =
+ * default) or env ELISA_B200_FOLD_SLICES_BWD.  The gradient contraction tolerates one digit
+ * less than the statistic (profiles/r02_slices.md), so the default is 5 there: 15 digit
+ * products instead of 21.                                                               */
+#define ELISA_FLAG_FOLD_SLICES_BWD_SHIFT 12
 #define ELISA_FOLD_SLICES_DEFAULT 6
+#define ELISA_FOLD_SLICES_BWD_DEFAULT 6
 
 typedef struct ElisaPlan ElisaPlan;
 
@@ -321,8 +327,9 @@ int64_t elisa_b200_plan_launch_count(const ElisaPlan* plan);
 int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_params, char* source_out,
                                     int64_t source_cap);
 /* slices of the sliced-integer fold used for `spectrum` (ELISA_FLAG_FOLD_*), 0 if it folds
- * with FP64 DMMA, -1 on a bad argument                                                   */
+ * with FP64 DMMA, -1 on a bad argument; _bwd: of its transposed fold                     */
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
+int elisa_b200_plan_fold_slices_bwd(const ElisaPlan* plan, int32_t spectrum);
 /* Accuracy guard of the sliced-integer fold.  Its error is bounded relative to (largest
  * element of the balanced row of U) x (sum over the balanced column of the response), see
  * elisa_b200_plan_rebalance below; rows far from the spectrum the envelopes were taken on, or
@@ -358,6 +365,9 @@ int elisa_b200_plan_rebalance(ElisaPlan* plan);
  * created with ELISA_FLAG_FOLD_I8); plan_guard_fallbacks counts how often it did.          */
 int elisa_b200_plan_set_fold(ElisaPlan* plan, int dmma);
 int64_t elisa_b200_plan_guard_fallbacks(const ElisaPlan* plan);
+/* counters of the guarded entry points since plan creation: out[0] calls in which the DMMA fold
+ * answered for some rows, out[1] rows it answered in total, out[2] envelope renewals        */
+int elisa_b200_plan_guard_stats(const ElisaPlan* plan, int64_t out[3]);
 /* The fold engine on its own: D[m, n] = A[m, k] . B[n, k]^T in FP64-class accuracy on the
  * int8 tensor cores (device pointers, row-major, k <= 16384, slices 4..7).  Allocates its
  * digit images, runs on `cuda_stream`, synchronises; `ms` (nullable) receives the device
@@ -365,6 +375,39 @@ int64_t elisa_b200_plan_guard_fallbacks(const ElisaPlan* plan);
  * entry points above run the same kernel with the statistic and gradient epilogues.     */
 int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, int64_t ldb, int32_t m, int32_t n,
                                int32_t k, int32_t slices, double* D, int64_t ldd, double* ms, void* cuda_stream);
+/* Guarded evaluation with DEVICE pointers: like loglike_grad_dev (grad may be NULL), then
+ * consults the accuracy guard -- this entry point SYNCHRONISES `cuda_stream`.  The statistic
+ * kernel keeps a list of the flagged rows; only those rows are re-evaluated with the FP64 DMMA
+ * fold (gathered into a compact batch, scattered back), so that a batch with a few starved rows
+ * keeps the integer fold's rate.  When more than a quarter of the rows are flagged the balancing
+ * envelopes are renewed from the call's own rows first (elisa_b200_plan_rebalance) and the
+ * call repeated; a list overflow (> 65536 rows) falls back to the DMMA fold for the whole call.
+ * fallback_rows (nullable) receives the number of rows answered by the DMMA fold.
+ * loglike_grad_host does the same.                                                       */
+int elisa_b200_loglike_grad_guarded_dev(ElisaPlan* plan, const double* theta, const double* counts_on,
+                                        const double* counts_off, int64_t n, double* loglike, double* grad,
+                                        void* cuda_stream, int64_t* fallback_rows);
+/* Asynchronous view of the guard for callers that must not synchronise (a leapfrog loop
+ * replaying the small-batch graph): snapshot enqueues a copy of the guard words into pinned
+ * host memory on `cuda_stream` followed by an event; poll returns 1 and fills flagged / worst
+ * once that copy has landed (wait != 0: block until it has), 0 if it is still in flight, and
+ * resets nothing -- the counters are cumulative since the last elisa_b200_plan_fold_guard
+ * reset.                                                                                  */
+int elisa_b200_plan_guard_snapshot(ElisaPlan* plan, void* cuda_stream);
+int elisa_b200_plan_guard_poll(ElisaPlan* plan, int wait, int64_t* flagged, double* worst);
+/* Per-channel forward-mode Jacobian of spectrum `spectrum`: the folded model counts
+ * x[n, c] = clip(source_counts) (likelihood.py:207-208) and ds[n, p, c] = d x[n, c] / d theta_p
+ * from forward-folded tangent spectra -- what jax.jacfwd of the '{name}_Non_model' site, and
+ * through dl/dx the LM residual Jacobian (infer/helper.py:588-594, 616-622), are made of.
+ * dl_dx (nullable) [n, c] = d loglike_c / d x_c of the spectrum's statistic (on + off terms),
+ * so that d residual_c / d theta_p = -dl_dx * ds / residual_c.  n_params <= 16.            */
+int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, const double* counts_on,
+                            const double* counts_off, int64_t n, double* x, double* ds, double* dl_dx,
+                            void* cuda_stream);
+/* Timing experiments only: bit mask of kernel classes to SKIP in the evaluation entry points
+ * (1 unfold, 2 forward fold, 4 statistic, 8 transposed fold, 16 reduce); results are garbage
+ * while a bit is set.  tools/power_probe.py uses it to time one class in isolation.        */
+int elisa_b200_plan_set_debug(ElisaPlan* plan, int32_t skip_mask);
 /* 1 if spectrum's component kernel is the runtime-specialised one, 0 if interpreted */
 int elisa_b200_plan_is_specialised(const ElisaPlan* plan, int32_t spectrum);
 int elisa_b200_abi_version(void);
