@@ -201,7 +201,11 @@ def _worker(rank, world, port, n, q):
         def loglike(self, t, on=None, off=None):
             return t.sum(1, keepdim=True)
 
+        nparam, device = 3, 0
+
         def fit(self, t, counts_on=None, counts_off=None, **kw):
+            if len(t) == 1 and counts_on is not None:  # one start vector for every replica (Likelihood.fit)
+                t = t.expand(len(counts_on), -1)
             return {'theta': t + 1.0, 'deviance': t.sum(1), 'grad_norm': t[:, 0] * 0.0,
                     'n_iter': torch.full((len(t),), 3), 'valid': t[:, 0] >= 0, 'loglike': -0.5 * t.sum(1)}
 
@@ -210,6 +214,11 @@ def _worker(rank, world, port, n, q):
     fit_ok = (torch.equal(fit['theta'], theta + 1.0) and torch.equal(fit['deviance'], theta.sum(1))
               and fit['n_iter'].dtype == torch.int64 and bool((fit['n_iter'] == 3).all()) and fit['valid'].dtype == torch.bool
               and bool(fit['valid'].all()) and fit['theta'].shape[0] == n)
+    # one start vector broadcast over the replicas: the REPLICAS are sharded, not the vector
+    bfit = sl.fit(theta[:1], counts)
+    fit_ok = fit_ok and bfit['theta'].shape == (n, 3) and torch.equal(bfit['theta'], (theta[:1] + 1.0).expand(n, 3))
+    bfit1 = sl.fit(theta[0], counts)  # 1-D theta = ONE parameter vector, not P rows
+    fit_ok = fit_ok and torch.equal(bfit1['theta'], bfit['theta'])
     ll, g = sl.loglike_and_grad(theta, counts)
     local = sl.loglike(theta, gather=False)
     same = sharded_map(lambda t: t * 1.0, (theta,), n)
@@ -219,8 +228,10 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n', [7, 64])
-def test_sharded_map_gloo_world2(n):
+@pytest.mark.parametrize('n,world', [(7, 2), (64, 2), (7, 3)])
+def test_sharded_map_gloo(n, world):
+    """world 2: even and uneven blocks; world 3 with 7 rows: blocks of 3, 2, 2 -- the in-place
+    compaction of the padded gather moves the last block."""
     import socket
 
     import torch.multiprocessing as mp
@@ -228,13 +239,13 @@ def test_sharded_map_gloo_world2(n):
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(timeout=60)
-    b = shard_bounds(n, 2)
+    b = shard_bounds(n, world)
     for rank, ok, first_call, local_rows in res:
         assert ok
         assert first_call == b[rank][1] - b[rank][0] == local_rows
