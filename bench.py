@@ -120,21 +120,85 @@ def cpu_oracle(cfg, rows, repeats=1, warmup=0):
     return theta.shape[0] * len(datas) / dt, dt, threads, ll.numpy(), g.numpy()
 
 
-def parity_errors(ll, g, ll_ref, g_ref):
+def clamp_ambiguous_rows(cfg, rows):
+    """Rows in which the REFERENCE's own gradient is decided by rounding.  BetterPoisson.log_prob
+    ends in `minimum(v, 0)` with v = xlogy(n, mu) - mu - (xlogy(n, n) - n) (infer/likelihood.py:
+    171-174); its derivative is n / mu - 1 where v < 0 and exactly 0 where v >= 0.  v has a double
+    zero at mu = n, so within |mu - n| / n <~ 1e-7 the computed v is rounding noise of either sign
+    and the channel's gradient term (|n / mu - 1| <= 1e-7 times d mu / d theta) is switched on or
+    off by the last bit of a logarithm -- XLA, torch and CUDA's libm each decide it their own way
+    (about one row in 10^4 at 1024 channels).  A row is listed when the oracle's sites show such a
+    channel: |v| within 64 ulp of its largest term."""
+    import torch
+
+    import oracle
+
+    models = [m.compile() if not hasattr(m, 'to_spec') else m for m in cfg['model']]
+    free = []
+    for m in models:
+        for p in m.free:
+            if all(p is not q for q in free):
+                free.append(p)
+    out = []
+    theta = torch.as_tensor(np.asarray(cfg['theta'])[rows], dtype=torch.float64)
+    flag = np.zeros(len(rows), dtype=bool)
+    for s_i, (m, d, stat) in enumerate(zip(models, cfg['data'], cfg['stat'])):
+        if stat == 'chi2':
+            continue
+        st = oracle.sites(stat, d.as_mapping(), m.to_spec(free), theta)
+        eps = 64 * 2.220446049250313e-16
+        for term, model, n in (('Non_loglike', 'Non_model', d.spec_counts), ('Noff_loglike', 'Noff_model', getattr(d, 'back_counts', None))):
+            if term not in st or n is None or stat == 'pgstat' and term == 'Noff_loglike':
+                continue
+            v = np.abs(st[term].numpy())
+            mu = st[model].numpy()
+            n = np.asarray(n, dtype=np.float64)[None, :]
+            big = np.abs(n * np.log(np.maximum(mu, 1e-300))) + mu + np.abs(n * np.log(np.maximum(n, 1.0)) - n)
+            flag |= ((v <= eps * big) & (n > 0)).any(axis=1)
+    return np.asarray(rows)[flag]
+
+
+def parity_errors(ll, g, ll_ref, g_ref, cfg=None, row_index=None):
     """Deviation of the GPU path from the oracle on the same rows.  value: |dll| / max(|ll|, 1);
     gradient column-normwise: relative to the largest |gradient| of that (spectrum, parameter)
     over the batch; row-normwise: relative to the row's OWN gradient (its largest component in
     column units), floored at 1e-2 of the column scale (below that the conditioning of the sum
-    over energies costs 1 / s digits in any arithmetic) -- `rownorm_raw` is the unfloored figure."""
-    val = float(np.max(np.abs(ll - ll_ref) / np.maximum(np.abs(ll_ref), 1.0)))
+    over energies costs 1 / s digits in any arithmetic) -- `rownorm_raw` is the unfloored figure.
+    Rows whose gradient the reference formula itself leaves to rounding (clamp_ambiguous_rows) are
+    reported on their own and held to 1e-7, the size of the gradient term that flips."""
+    val = np.abs(ll - ll_ref) / np.maximum(np.abs(ll_ref), 1.0)
     col = np.max(np.abs(g_ref), axis=0, keepdims=True)
     col = np.where(col == 0.0, 1.0, col)
     d = np.abs(g - g_ref)
     row = np.max(np.abs(g_ref) / col, axis=-1, keepdims=True)
     row = np.where(row == 0.0, 1.0, row)
-    return {'rows': int(ll.shape[0]), 'max_rel_value': val, 'max_rel_grad_batchnorm': float(np.max(d / col)),
-            'max_rel_grad_rownorm': float(np.max(d / (col * np.maximum(row, 1e-2)))),
-            'max_rel_grad_rownorm_raw': float(np.max(d / (col * row))), 'min_row_scale': float(np.min(row))}
+    e_col = (d / col).max(axis=(1, 2))
+    e_row = (d / (col * np.maximum(row, 1e-2))).max(axis=(1, 2))
+    keep = np.ones(ll.shape[0], dtype=bool)
+    amb = {'rows': 0}
+    suspects = np.nonzero((e_col > RTOL) | (e_row > RTOL))[0]
+    if cfg is not None and len(suspects):
+        idx = np.arange(ll.shape[0]) if row_index is None else np.asarray(row_index)
+        hit = clamp_ambiguous_rows(cfg, idx[suspects])
+        mask = np.isin(idx, hit)
+        if mask.any():
+            amb = {'rows': int(mask.sum()), 'max_rel_grad_batchnorm': float(e_col[mask].max()),
+                   'max_rel_value': float(val[mask].max()), 'tolerance': 1e-7,
+                   'why': 'a channel with |mu - n| / n < 1e-7: the minimum(v, 0) of BetterPoisson.log_prob '
+                          '(infer/likelihood.py:171-174) switches that channel\'s gradient term on rounding noise'}
+            keep = ~mask
+    return {'rows': int(ll.shape[0]), 'max_rel_value': float(val[keep].max()), 'max_rel_grad_batchnorm': float(e_col[keep].max()),
+            'max_rel_grad_rownorm': float(e_row[keep].max()),
+            'max_rel_grad_rownorm_raw': float((d / (col * row)).max(axis=(1, 2))[keep].max()), 'min_row_scale': float(np.min(row)),
+            'clamp_ambiguous': amb}
+
+
+def parity_ok(p):
+    amb = p.get('clamp_ambiguous', {'rows': 0})
+    ok = p['max_rel_value'] <= RTOL and p['max_rel_grad_batchnorm'] <= RTOL and p['max_rel_grad_rownorm'] <= RTOL
+    if amb['rows']:
+        ok = ok and amb['max_rel_grad_batchnorm'] <= 1e-7 and amb['max_rel_value'] <= RTOL and amb['rows'] <= max(2, p['rows'] // 1000)
+    return bool(ok)
 
 
 def run_reference(args):
@@ -292,7 +356,9 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
         _, _, _, ll_ref, g_ref = cpu_oracle(cfg, rows)
         sub_kw = {k: (None if v is None else torch.as_tensor(np.asarray(v)[rows], dtype=torch.float64, device=dev)) for k, v in kw.items()}
         ll, g = lk.loglike_and_grad(torch.as_tensor(np.asarray(cfg['theta'])[rows], dtype=torch.float64, device=dev), **sub_kw)
-        return parity_errors(ll.cpu().numpy(), g.cpu().numpy(), ll_ref, g_ref)
+        out = parity_errors(ll.cpu().numpy(), g.cpu().numpy(), ll_ref, g_ref, cfg, rows)
+        out['pass'] = parity_ok(out)
+        return out
 
     def engine(lk):
         fs, fb = lk.fold_slices, lk.fold_slices_bwd
@@ -391,7 +457,8 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
         if with_oracle:
             rows = np.sort(np.random.default_rng(0).choice(n5, size=64, replace=False))
             _, _, _, ll_ref, g_ref = cpu_oracle(cfg, rows)
-            par = parity_errors(ll5[rows].cpu().numpy(), g5[rows].cpu().numpy(), ll_ref, g_ref)
+            par = parity_errors(ll5[rows].cpu().numpy(), g5[rows].cpu().numpy(), ll_ref, g_ref, cfg, rows)
+            par['pass'] = parity_ok(par)
         out['cfg5'] = {'what': 'PowerLaw jointly on 16 spectra (distinct dense 1024 x 2048 RSPs, cstat / chi2), 1e6 draws split over '
                                '%d GPU(s), all-gather of [N,16] + [N,16,2] inside the timed region (strong scaling)' % world,
                        'evals_s': n5 * 16 / ms * 1e3, 'ms': ms, 'n_gpus': world, 'engine': engine(lk), 'parity': par,
@@ -476,13 +543,12 @@ def run_b200(args):
     torch.cuda.synchronize()
     flagged, worst = lk.fold_guard(reset=False)
     if with_oracle and rank == 0:
-        parity = parity_errors(ll[:ns].cpu().numpy(), grad[:ns].cpu().numpy(), ll_ref, g_ref)
+        parity = parity_errors(ll[:ns].cpu().numpy(), grad[:ns].cpu().numpy(), ll_ref, g_ref, cfg)
         parity.update({'tolerance': RTOL, 'guard_flagged': flagged, 'guard_worst_estimate': worst,
                        'guard_fallback_rows': fb_rows[0], 'guard_fallbacks': int(lk._lib.elisa_b200_plan_guard_fallbacks(lk._h)),
                        'arm': 'value and e2e both run the guarded entry points (elisa_b200_loglike_grad_guarded_dev / _host)'})
-        ok = (parity['max_rel_value'] <= RTOL and parity['max_rel_grad_batchnorm'] <= RTOL and
-              parity['max_rel_grad_rownorm'] <= RTOL)
-        parity['pass'] = bool(ok)
+        ok = parity_ok(parity)
+        parity['pass'] = ok
         if not ok:
             sys.stderr.write('PARITY GATE FAILED, no throughput recorded: ' + json.dumps(parity) + '\n')
             print(json.dumps({'metric': METRIC, 'value': None, 'unit': UNIT, 'n_gpus': world, 'parity': parity,

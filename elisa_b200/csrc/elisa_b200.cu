@@ -1272,106 +1272,215 @@ static std::string hexd(double v) {
 
 // The translation unit for one model: see unfold_skel.cuh.
 // ks > 0: the kernels also write the digits of U for the sliced-integer fold (fold_i8.cuh).
+//
+// Two policy structs are generated, ModelV (values: every scalar a double) and ModelG (values +
+// d/dtheta).  In ModelG every leaf is evaluated in its OWN dual type, Dual<n_i> with n_i the number
+// of distinct free theta columns among the leaf's parameters -- not Dual<P>: a tangent that is
+// structurally zero costs an IEEE multiply-add all the same (0 * x is not foldable), and for
+// CutoffPL + Blackbody that is 12 scalars per edge carried instead of 7.  The +/* tree above the
+// leaves is emitted as straight-line scalar code over (value, {column: tangent}) pairs, so sums
+// of leaves with disjoint parameters cost nothing beyond the value.
+namespace {
+struct SV {  // a scalar expression and its non-zero tangents by theta column
+    std::string v;
+    std::map<int, std::string> d;
+};
+}  // namespace
+
+static std::string generate_model_struct(const ModelDev& m, int P, bool grad, const std::string& name) {
+    std::string s;
+    auto str = [](int v) { return std::to_string(v); };
+    // distinct free columns per leaf (local tangent index = position in this list)
+    std::vector<std::vector<int>> cols(m.n_leaf);
+    std::vector<std::string> ltype(m.n_leaf);
+    for (int i = 0; i < m.n_leaf; ++i) {
+        if (grad)
+            for (int q = 0; q < m.leaf[i].np; ++q) {
+                const int c = m.leaf[i].src[q];
+                if (c >= 0 && std::find(cols[i].begin(), cols[i].end(), c) == cols[i].end()) cols[i].push_back(c);
+            }
+        std::sort(cols[i].begin(), cols[i].end());
+        ltype[i] = cols[i].empty() ? "double" : "Dual<" + str((int)cols[i].size()) + ">";
+    }
+    // columns each flux normalisation factor F / flux depends on
+    std::vector<std::vector<int>> ncols(m.n_norms);
+    for (int k = 0; k < m.n_norms; ++k) {
+        if (!grad) continue;
+        std::vector<int>& nc = ncols[k];
+        for (int o = m.norm[k].op_lo; o < m.norm[k].op_hi; ++o)
+            if (m.ops[o] >= 0)
+                for (int c : cols[m.ops[o]])
+                    if (std::find(nc.begin(), nc.end(), c) == nc.end()) nc.push_back(c);
+        if (m.norm[k].f_src >= 0 && std::find(nc.begin(), nc.end(), m.norm[k].f_src) == nc.end()) nc.push_back(m.norm[k].f_src);
+        std::sort(nc.begin(), nc.end());
+    }
+    s += "struct " + name + " {\n  struct Pre {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const std::string k = str(m.leaf[i].kind), id = str(i);
+        s += "    " + ltype[i] + " p" + id + "[Comp<" + k + ">::NP]; " + ltype[i] + " c" + id + "[Comp<" + k + ">::NC];\n";
+    }
+    for (int k = 0; k < m.n_norms; ++k) {
+        s += "    double n" + str(k) + "_v;\n";
+        for (int c : ncols[k]) s += "    double n" + str(k) + "_d" + str(c) + ";\n";
+    }
+    s += "  };\n  __device__ __forceinline__ static void pre(const double* th, Pre& s) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        const std::string k = str(L.kind), id = str(i), T = ltype[i];
+        for (int q = 0; q < L.np; ++q) {
+            s += "    s.p" + id + "[" + str(q) + "] = ";
+            if (L.src[q] >= 0) {
+                const int local = grad ? (int)(std::find(cols[i].begin(), cols[i].end(), L.src[q]) - cols[i].begin()) : -1;
+                s += "Flat<" + T + ">::seed(th[" + str(L.src[q]) + "], " + str(local) + ");\n";
+            } else {
+                s += "Flat<" + T + ">::seed(" + hexd(L.cst[q]) + ", -1);\n";
+            }
+        }
+        s += "    { const double aux[2] = {" + hexd(L.aux[0]) + ", " + hexd(L.aux[1]) + "};\n";
+        s += "      for (int k = 0; k < Comp<" + k + ">::NC; ++k) s.c" + id + "[k] = Flat<" + T + ">::seed(0.0, -1);\n";
+        s += "      Comp<" + k + ">::pre(s.p" + id + ", aux, s.c" + id + "); }\n";
+    }
+    s += "  }\n";
+    // straight-line code of ops[lo, hi) on grid view `gv`; on_norm_grid selects the leaf's scales
+    // on a flux-normalisation grid (shifts inside the normalised sub-expression only)
+    auto emit_range = [&](int lo, int hi, bool on_norm_grid, const std::string& pfx, const std::string& ind) -> SV {
+        std::vector<SV> stack;
+        std::vector<bool> emitted(m.n_leaf, false);
+        int tmp = 0;
+        auto fresh = [&](const SV& val) {  // name the pieces of a computed value
+            SV out;
+            const std::string t = pfx + "t" + str(tmp++);
+            s += ind + "const double " + t + "_v = " + val.v + ";\n";
+            out.v = t + "_v";
+            for (const auto& kv : val.d) {
+                s += ind + "const double " + t + "_d" + str(kv.first) + " = " + kv.second + ";\n";
+                out.d[kv.first] = t + "_d" + str(kv.first);
+            }
+            return out;
+        };
+        auto mul = [&](const SV& a, const SV& b) {
+            SV r;
+            r.v = a.v + " * " + b.v;
+            for (const auto& kv : a.d) r.d[kv.first] = kv.second + " * " + b.v;
+            for (const auto& kv : b.d) {
+                auto it = r.d.find(kv.first);
+                if (it == r.d.end())
+                    r.d[kv.first] = a.v + " * " + kv.second;
+                else
+                    it->second = "fma(" + a.v + ", " + kv.second + ", " + it->second + ")";
+            }
+            return fresh(r);
+        };
+        for (int o = lo; o < hi; ++o) {
+            const int op = m.ops[o];
+            if (op >= 0) {
+                const LeafDev& L = m.leaf[op];
+                const std::string id = str(op), T = ltype[op];
+                if (!emitted[op]) {
+                    const double gs = on_norm_grid ? L.ngs : L.gs, lgs = on_norm_grid ? L.lngs : L.lgs;
+                    const double os = on_norm_grid ? L.nos : L.os;
+                    s += ind + "const " + T + " " + pfx + "v" + id + " = " + (os != 1.0 ? hexd(os) + " * " : std::string()) +
+                         "leaf_bin_pc<" + str(L.kind) + ", " + T + ">(s.p" + id + ", s.c" + id + ", " + str(L.method) +
+                         ", gv, e, " + id + ", " + hexd(gs) + ", " + hexd(lgs) + ");\n";
+                    emitted[op] = true;
+                }
+                SV leaf;
+                if (cols[op].empty()) {
+                    leaf.v = pfx + "v" + id;
+                } else {
+                    leaf.v = pfx + "v" + id + ".v";
+                    for (size_t k = 0; k < cols[op].size(); ++k) leaf.d[cols[op][k]] = pfx + "v" + id + ".d[" + str((int)k) + "]";
+                }
+                stack.push_back(leaf);
+            } else if (op <= ELISA_OP_NORM0) {
+                const int k = ELISA_OP_NORM0 - op;
+                SV nrm;
+                nrm.v = "s.n" + str(k) + "_v";
+                for (int c : ncols[k]) nrm.d[c] = "s.n" + str(k) + "_d" + str(c);
+                stack.back() = mul(nrm, stack.back());
+            } else {
+                const SV r = stack.back();
+                stack.pop_back();
+                const SV l = stack.back();
+                stack.pop_back();
+                if (op == ELISA_OP_ADD) {
+                    SV t;
+                    t.v = l.v + " + " + r.v;
+                    t.d = l.d;
+                    for (const auto& kv : r.d) {
+                        auto it = t.d.find(kv.first);
+                        if (it == t.d.end())
+                            t.d[kv.first] = kv.second;
+                        else
+                            it->second = it->second + " + " + kv.second;
+                    }
+                    stack.push_back(fresh(t));
+                } else {
+                    stack.push_back(mul(l, r));
+                }
+            }
+        }
+        return stack.back();
+    };
+    s += "  __device__ __forceinline__ static void norms(Pre& s, const UnfoldCore& a, const double* th, int lane) {\n";
+    for (int k = 0; k < m.n_norms; ++k) {
+        const NormDev& nd = m.norm[k];
+        const std::string id = str(k);
+        s += "    {\n      const GridView gv = a.ngv[" + id + "];\n      double acc_v = 0.0;\n";
+        for (int c : ncols[k]) s += "      double acc_d" + str(c) + " = 0.0;\n";
+        s += "      for (int e0 = 0; e0 < gv.E; e0 += 31) {\n        const int e = e0 + lane;\n";
+        const SV sub = emit_range(nd.op_lo, nd.op_hi, true, "n", "        ");
+        const std::string w = nd.kind == ELISA_NORM_ENFLUX ? "a.nw[" + id + "][e]" : "";
+        s += "        if (lane < 31 && e < gv.E) {\n";
+        if (!w.empty()) s += "          const double w = " + w + ";\n";
+        s += "          acc_v += " + (w.empty() ? sub.v : "w * (" + sub.v + ")") + ";\n";
+        for (int c : ncols[k]) {
+            auto it = sub.d.find(c);
+            if (it != sub.d.end())
+                s += "          acc_d" + str(c) + " += " + (w.empty() ? it->second : "w * (" + it->second + ")") + ";\n";
+        }
+        s += "        }\n      }\n      acc_v = warp_sum(acc_v);\n";
+        for (int c : ncols[k]) s += "      acc_d" + str(c) + " = warp_sum(acc_d" + str(c) + ");\n";
+        s += "      const double F = " + (nd.f_src >= 0 ? "th[" + str(nd.f_src) + "]" : hexd(nd.f_cst)) + ";\n";
+        s += "      const double inv = 1.0 / acc_v;\n      s.n" + id + "_v = F * inv;\n";
+        for (int c : ncols[k])  // d(F / acc) = (dF - (F / acc) d acc) / acc
+            s += "      s.n" + id + "_d" + str(c) + " = (" + (c == nd.f_src ? "1.0" : "0.0") + " - s.n" + id + "_v * acc_d" + str(c) +
+                 ") * inv;\n";
+        s += "    }\n";
+    }
+    s += "  }\n";
+    const std::string RT = grad ? "Dual<" + str(P) + ">" : "double";
+    s += "  __device__ __forceinline__ static " + RT + " bin(const Pre& s, const GridView& gv, int e) {\n";
+    {
+        const SV r = emit_range(0, m.n_ops, false, "", "    ");
+        if (!grad) {
+            s += "    return " + r.v + ";\n";
+        } else {
+            s += "    " + RT + " r;\n    r.v = " + r.v + ";\n";
+            for (int j = 0; j < P; ++j) {
+                auto it = r.d.find(j);
+                s += "    r.d[" + str(j) + "] = " + (it != r.d.end() ? it->second : std::string("0.0")) + ";\n";
+            }
+            s += "    return r;\n";
+        }
+    }
+    s += "  }\n};\n";
+    return s;
+}
+
 static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
     std::string s;
     {
         const char* env = getenv("ELISA_B200_UNFOLD_MIN_BLOCKS");  // occupancy experiments
         s += "#define UNFOLD_MIN_BLOCKS " + std::to_string(env ? std::max(1, atoi(env)) : 1) + "\n";
     }
-    s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\nstruct Model {\n";
-    s += "  template <typename T> struct Pre {\n";
-    for (int i = 0; i < m.n_leaf; ++i) {
-        const std::string k = std::to_string(m.leaf[i].kind), id = std::to_string(i);
-        s += "    T p" + id + "[Comp<" + k + ">::NP]; T c" + id + "[Comp<" + k + ">::NC];\n";
-    }
-    for (int k = 0; k < m.n_norms; ++k) s += "    T n" + std::to_string(k) + ";\n";
-    s += "  };\n  template <typename T> __device__ __forceinline__ static void pre(const double* th, Pre<T>& s) {\n";
-    for (int i = 0; i < m.n_leaf; ++i) {
-        const LeafDev& L = m.leaf[i];
-        const std::string k = std::to_string(L.kind), id = std::to_string(i);
-        for (int q = 0; q < L.np; ++q) {
-            s += "    s.p" + id + "[" + std::to_string(q) + "] = ";
-            if (L.src[q] >= 0)
-                s += "Flat<T>::seed(th[" + std::to_string(L.src[q]) + "], " + std::to_string(L.src[q]) + ");\n";
-            else
-                s += "Flat<T>::seed(" + hexd(L.cst[q]) + ", -1);\n";
-        }
-        s += "    { const double aux[2] = {" + hexd(L.aux[0]) + ", " + hexd(L.aux[1]) + "};\n";
-        s += "      for (int k = 0; k < Comp<" + k + ">::NC; ++k) s.c" + id + "[k] = Flat<T>::seed(0.0, -1);\n";
-        s += "      Comp<" + k + ">::pre(s.p" + id + ", aux, s.c" + id + "); }\n";
-    }
-    s += "  }\n";
-    // straight-line code of ops[lo, hi) on grid view `gv`; on_norm_grid selects the leaf's scales
-    // on a flux-normalisation grid (shifts inside the normalised sub-expression only)
-    auto emit_range = [&](int lo, int hi, bool on_norm_grid, const std::string& pfx) {
-        std::vector<std::string> stack;
-        std::vector<bool> emitted(m.n_leaf, false);
-        int tmp = 0;
-        for (int o = lo; o < hi; ++o) {
-            const int op = m.ops[o];
-            if (op >= 0) {
-                const LeafDev& L = m.leaf[op];
-                const std::string id = std::to_string(op);
-                if (!emitted[op]) {
-                    const double gs = on_norm_grid ? L.ngs : L.gs, lgs = on_norm_grid ? L.lngs : L.lgs;
-                    const double os = on_norm_grid ? L.nos : L.os;
-                    s += "    const T " + pfx + "v" + id + " = " + (os != 1.0 ? hexd(os) + " * " : std::string()) +
-                         "leaf_bin_pc<" + std::to_string(L.kind) + ", T>(s.p" + id + ", s.c" + id + ", " +
-                         std::to_string(L.method) + ", gv, e, " + id + ", " + hexd(gs) + ", " + hexd(lgs) + ");\n";
-                    emitted[op] = true;
-                }
-                stack.push_back(pfx + "v" + id);
-            } else if (op <= ELISA_OP_NORM0) {
-                const std::string t = pfx + "t" + std::to_string(tmp++);
-                s += "    const T " + t + " = s.n" + std::to_string(ELISA_OP_NORM0 - op) + " * " + stack.back() + ";\n";
-                stack.back() = t;
-            } else {
-                const std::string r = stack.back();
-                stack.pop_back();
-                const std::string l = stack.back();
-                stack.pop_back();
-                const std::string t = pfx + "t" + std::to_string(tmp++);
-                s += "    const T " + t + " = " + l + (op == ELISA_OP_ADD ? " + " : " * ") + r + ";\n";
-                stack.push_back(t);
-            }
-        }
-        return stack.back();
-    };
-    for (int k = 0; k < m.n_norms; ++k) {
-        s += "  template <typename T> __device__ __forceinline__ static T sub" + std::to_string(k) +
-             "(const Pre<T>& s, const GridView& gv, int e) {\n";
-        const std::string r = emit_range(m.norm[k].op_lo, m.norm[k].op_hi, true, "n");
-        s += "    return " + r + ";\n  }\n";
-    }
-    s += "  template <typename T> __device__ __forceinline__ static void norms(Pre<T>& s, const UnfoldCore& a, "
-         "const double* th, int lane) {\n";
-    for (int k = 0; k < m.n_norms; ++k) {
-        const NormDev& nd = m.norm[k];
-        const std::string id = std::to_string(k);
-        s += "    {\n      const GridView gv = a.ngv[" + id + "];\n      T acc = Cst<T>::make(0.0);\n";
-        s += "      for (int e0 = 0; e0 < gv.E; e0 += 31) {\n        const int e = e0 + lane;\n";
-        s += "        const T v = sub" + id + "<T>(s, gv, e);\n";
-        if (nd.kind == ELISA_NORM_ENFLUX)
-            s += "        if (lane < 31 && e < gv.E) acc = acc + a.nw[" + id + "][e] * v;\n";
-        else
-            s += "        if (lane < 31 && e < gv.E) acc = acc + v;\n";
-        s += "      }\n      acc = warp_sum(acc);\n";
-        if (nd.f_src >= 0)
-            s += "      const T F = Flat<T>::seed(th[" + std::to_string(nd.f_src) + "], " + std::to_string(nd.f_src) + ");\n";
-        else
-            s += "      const T F = Flat<T>::seed(" + hexd(nd.f_cst) + ", -1);\n";
-        s += "      s.n" + id + " = F / acc;\n    }\n";
-    }
-    s += "  }\n";
-    s += "  template <typename T> __device__ __forceinline__ static T bin(const Pre<T>& s, const GridView& gv, int e) {\n";
-    {
-        const std::string r = emit_range(0, m.n_ops, false, "");
-        s += "    return " + r + ";\n  }\n};\n";
-    }
+    s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\n";
+    s += generate_model_struct(m, P, false, "ModelV");
+    s += generate_model_struct(m, P, true, "ModelG");
     const std::string k = std::to_string(ks);
-    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_val(const UnfoldCore a) { unfold_generic<Model, double, " +
+    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_val(const UnfoldCore a) { unfold_generic<ModelV, double, " +
          k + ">(a); }\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_grad(const UnfoldCore a) { unfold_generic<Model, Dual<" +
+    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_grad(const UnfoldCore a) { unfold_generic<ModelG, Dual<" +
          std::to_string(P) + ">, " + k + ">(a); }\n";
     return s;
 }

@@ -412,23 +412,6 @@ __device__ __forceinline__ int i8_quad_row(int q) { return 2 * (q & 1) + (q >> 1
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Streaming access for data that crosses HBM exactly once (the dU/dtheta planes: written by the
-// unfold kernel, read once by the gradient epilogue, 1.5 GB per chunk against a 126 MB L2): no L1
-// allocation and an evict-first L2 policy, so that the stream does not push the folds' operand
-// images -- which ARE re-read, by every CTA working on the same row tile -- out of L2.
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ double2 ld_stream_f64x2(const double* p, unsigned long long pol) {
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
-                 : "=d"(v.x), "=d"(v.y)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-
 // item -> (row tile, first column tile, one past the last column tile)
 struct I8Item {
     int mt, g;
@@ -722,7 +705,7 @@ struct I8EpilogueGrad {
     int32_t n_part;
     double* gpart;       // already offset to plane p0
     int32_t ld_part;
-    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = L2 prefetch of the tile's dU lines, 128 = streaming (L1 no-allocate, L2 evict-first) dU loads
+    int32_t dbg;  // timing experiments: 32 = no dU loads, 64 = L2 prefetch of the tile's dU lines
 
     struct State {
         double rs[I8_GRAD_PMAX];
@@ -765,7 +748,6 @@ struct I8EpilogueGrad {
             }
         }
         const double* base = dU + (size_t)row0 * ldu + c0;
-        const unsigned long long pol = l2_policy_evict_first();
 #pragma unroll
         for (int p = 0; p < I8_GRAD_PMAX; ++p) {
             if (p < P && ((used_mask >> p) & 1u)) {
@@ -776,10 +758,8 @@ struct I8EpilogueGrad {
                     double t = 0.0;
 #pragma unroll
                     for (int m = 0; m < I8_NM; m += 2) {
-                        const double* ptr = src + (size_t)(8 * k) * ldu + i8_col(m, q);
-                        const double2 v = (dbg & 32)    ? make_double2(g[k][m], g[k][m + 1])
-                                          : (dbg & 128) ? ld_stream_f64x2(ptr, pol)
-                                                        : *reinterpret_cast<const double2*>(ptr);
+                        const double2 v = (dbg & 32) ? make_double2(g[k][m], g[k][m + 1])
+                                                     : *reinterpret_cast<const double2*>(src + (size_t)(8 * k) * ldu + i8_col(m, q));
                         t = fma(g[k][m + 1], v.y, fma(g[k][m], v.x, t));
                     }
                     s[k] = t;

@@ -1,10 +1,11 @@
 // Skeleton of the runtime-specialised unfold kernel.
 //
 // At plan creation the library writes, for each distinct model expression, a tiny
-// translation unit that defines `struct Model` (parameters wired to theta columns or
-// literals, one leaf_bin_pc<KIND> call per component, the +/* tree as straight-line code)
-// and instantiates unfold_generic<Model, T> for T = double (values) and T = Dual<P>
-// (values + d/dtheta).  It is compiled for sm_100a with NVRTC; every component body is the
+// translation unit that defines two policy structs, `ModelV` (values) and `ModelG` (values +
+// d/dtheta): parameters wired to theta columns or literals, one leaf_bin_pc<KIND> call per
+// component -- each in the smallest dual type that holds the leaf's own free parameters --
+// and the +/* tree as straight-line scalar code; and instantiates unfold_generic<ModelV, double>
+// and unfold_generic<ModelG, Dual<P>>.  It is compiled for sm_100a with NVRTC; every component body is the
 // same hand-written code as in the ahead-of-time interpreter (components.cuh), but with
 // all dispatch, parameter routing and derivative sparsity resolved at compile time
 // (dual seeds are literals, so zero tangents vanish by constant folding).
@@ -114,11 +115,11 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
         }
         return;
     }
-    typename Model::template Pre<T> pre;
-    Model::template pre<T>(a.theta + (size_t)row * a.P, pre);
+    typename Model::Pre pre;
+    Model::pre(a.theta + (size_t)row * a.P, pre);
     // flux normalisations: every warp of the row sums the normalised sub-expression over the
     // normalisation's own grid (nothing to do for models without PhFlux / EnFlux)
-    Model::template norms<T>(pre, a, a.theta + (size_t)row * a.P, lane);
+    Model::norms(pre, a, a.theta + (size_t)row * a.P, lane);
     // the grid values of a pass are loaded during the previous one
     GridView gv = a.gv;
     gv.has_point = 1;
@@ -147,7 +148,7 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
             load_point(e + 31, nE, nl, nEm, nlm);
             if (scaled) nk = a.kexp[min(e + 31, E - 1)];
         }
-        const T res = Model::template bin<T>(pre, gv, e);
+        const T res = Model::bin(pre, gv, e);
         if (lane < 31 && e < e_hi) {
             const double u = unfold_store<T>(a, row_off + e, res, ck);
             if constexpr (KS > 0) {

@@ -36,7 +36,7 @@ def test_backward_is_the_transposed_jacobian_product(lib):
 
     cfg = small_config(2)
     lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'])
-    theta = torch.as_tensor(cfg['theta'][:64], dtype=torch.float64, device='cuda', requires_grad=True)
+    theta = torch.as_tensor(cfg['theta'][:64], dtype=torch.float64, device='cuda').requires_grad_(True)
     w = torch.randn((64, 1), dtype=torch.float64, device='cuda', generator=torch.Generator('cuda').manual_seed(1))
     ll = AG.loglike(lk, theta)
     (w * ll).sum().backward()

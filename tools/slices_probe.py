@@ -33,10 +33,11 @@ def cases():
         yield f'random{seed:02d} {stat} {E}x{C} n={n}', dict(data=[d], model=[cm], stat=[stat], theta=_theta_for(model, n, seed))
 
 
+TIME_ONLY = '--time-only' in sys.argv
 print('| case | ' + ' | '.join(f'{f}/{b}: value, grad (col), grad (row), flagged' for f, b in VARIANTS) + ' |')
 print('|---|' + '---|' * len(VARIANTS))
 worst = {v: [0.0, 0.0, 0.0] for v in VARIANTS}
-for label, cfg in cases():
+for label, cfg in ([] if TIME_ONLY else cases()):
     ll_ref, g_ref = oracle_eval(cfg)
     row = []
     for f, b in VARIANTS:
