@@ -1515,6 +1515,12 @@ static bool compile_unfold_source(const std::string& src, std::vector<char>* cub
     cubin->resize(n);
     api.cubin(prog, cubin->data());
     api.destroy(&prog);
+    if (const char* path = getenv("ELISA_B200_DUMP_CUBIN")) {  // for `cuobjdump -sass` of the specialised kernels
+        if (FILE* f = fopen(path, "wb")) {
+            fwrite(cubin->data(), 1, n, f);
+            fclose(f);
+        }
+    }
     return true;
 }
 

@@ -69,18 +69,19 @@ def test_hmc_64_chains_cfg3_matches_the_oracle(lib):
         theta, log_jac = bij(u)
         return -(AG.loglike(lk, theta).sum(-1) + log_jac)
 
-    # step size from the curvature scale of the potential at the start: |grad| ~ 1 / sigma
+    # mass matrix from the gradient scale of the potential at the start (|grad_d| ~ 1 / sigma_d): a
+    # step then moves every coordinate by about a tenth of its posterior width
     q = u0.clone().requires_grad_(True)
     (g,) = torch.autograd.grad(_oracle_potential(cfg, bij)(q).sum(), q)
-    step = float(0.05 / g.abs().max())
-    kw = dict(n_iter=4, n_leapfrog=6, step=step, seed=7)
+    mass = g.abs().amax(dim=0) ** 2
+    kw = dict(n_iter=4, n_leapfrog=6, step=0.1, seed=7, mass=mass)
     ref = AG.hmc(_oracle_potential(cfg, bij), u0, **kw)
     out = AG.hmc(gpu_potential, u0.cuda(), **kw)
     lk.guard_poll(wait=True)
     assert lk.fold_guard()[0] == 0
     assert out['n_grad'] == ref['n_grad'] == 1 + 4 * 6
     assert torch.equal(out['accept'].cpu(), ref['accept'])
-    assert bool(ref['accept'].any()) and float((out['q'].cpu() - u0).abs().max()) > 1e-4  # the chains did move
+    assert bool(ref['accept'].any()) and float(((out['q'].cpu() - u0).abs() * mass.sqrt()).max()) > 0.05  # the chains did move
     dev = (out['q'].cpu() - ref['q']).abs() / ref['q'].abs().clamp_min(1.0)
     assert float(dev.max()) < 1e-8, float(dev.max())
     lk.close()
