@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'elisa_b200.cu')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('elisa_b200.cu', 'components.cuh', 'dual.cuh', 'fold_i8.cuh', 'gemm_f64.cuh', 'slice_i8.cuh', 'stats.cuh', 'unfold_skel.cuh')]
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('elisa_b200.cu', 'components.cuh', 'dual.cuh', 'fastmath.cuh', 'fold_i8.cuh', 'gemm_f64.cuh', 'slice_i8.cuh', 'stats.cuh', 'unfold_skel.cuh')]
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 DEPS.append(os.path.join(INCLUDE, 'elisa_b200.h'))
 # headers handed to NVRTC at run time travel inside the library as string literals
@@ -19,6 +19,7 @@ EMBED = {
     'embedded_components_cuh.inc': os.path.join(HERE, 'csrc', 'components.cuh'),
     'embedded_unfold_skel_cuh.inc': os.path.join(HERE, 'csrc', 'unfold_skel.cuh'),
     'embedded_slice_i8_cuh.inc': os.path.join(HERE, 'csrc', 'slice_i8.cuh'),
+    'embedded_fastmath_cuh.inc': os.path.join(HERE, 'csrc', 'fastmath.cuh'),
 }
 LIB = os.path.join(HERE, 'lib', 'libelisa_b200.so')
 

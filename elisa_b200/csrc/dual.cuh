@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #endif
+#include "fastmath.cuh"
 
 namespace elisa {
 
@@ -149,16 +150,17 @@ __device__ __forceinline__ Dual<N> chain(const Dual<N>& a, double f, double df) 
     return r;
 }
 
-__device__ __forceinline__ double ex(double a) { return exp(a); }
+// exp / log / expm1: the table-driven versions of fastmath.cuh (<= 1 ulp; 4 ulp for expm1)
+__device__ __forceinline__ double ex(double a) { return fm::exp(a); }
 template <int N>
 __device__ __forceinline__ Dual<N> ex(const Dual<N>& a) {
-    const double e = exp(a.v);
+    const double e = fm::exp(a.v);
     return chain(a, e, e);
 }
-__device__ __forceinline__ double lg(double a) { return log(a); }
+__device__ __forceinline__ double lg(double a) { return fm::log(a); }
 template <int N>
 __device__ __forceinline__ Dual<N> lg(const Dual<N>& a) {
-    return chain(a, log(a.v), 1.0 / a.v);
+    return chain(a, fm::log(a.v), 1.0 / a.v);
 }
 __device__ __forceinline__ double sq(double a) { return sqrt(a); }
 template <int N>
@@ -172,17 +174,17 @@ __device__ __forceinline__ Dual<N> at(const Dual<N>& a) {
     return chain(a, atan(a.v), 1.0 / (1.0 + a.v * a.v));
 }
 // x / expm1(x) helper pieces
-__device__ __forceinline__ double em1(double a) { return expm1(a); }
+__device__ __forceinline__ double em1(double a) { return fm::expm1(a); }
 template <int N>
 __device__ __forceinline__ Dual<N> em1(const Dual<N>& a) {
-    const double e = expm1(a.v);
+    const double e = fm::expm1(a.v);
     return chain(a, e, e + 1.0);
 }
 // base^expo with a plain-double base whose log is known (energies): exp(expo * ln base)
-__device__ __forceinline__ double pw_e(double lnbase, double expo) { return exp(expo * lnbase); }
+__device__ __forceinline__ double pw_e(double lnbase, double expo) { return fm::exp(expo * lnbase); }
 template <int N>
 __device__ __forceinline__ Dual<N> pw_e(double lnbase, const Dual<N>& expo) {
-    const double r = exp(expo.v * lnbase);
+    const double r = fm::exp(expo.v * lnbase);
     return chain(expo, r, r * lnbase);
 }
 // general pow for positive base

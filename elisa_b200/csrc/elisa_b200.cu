@@ -307,6 +307,7 @@ struct EpilogueStat {
             }
             if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[col];
             if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[col];
+            d.den = ch.den[col];
             const bool cvalid = j < n_cols;
             if (con != nullptr && cvalid) {
                 d.on = con[j];
@@ -450,6 +451,7 @@ __device__ __forceinline__ void sites_one(const SitesArgs& a, int row, int col) 
     if (a.counts_off != nullptr) d.off = a.counts_off[(size_t)row * a.ld_counts + col];
     d.gof_on = poisson_gof(d.on);
     d.gof_off = poisson_gof(d.off);
+    d.den = a.ch.den[col];
     const double fold = a.X[(size_t)row * a.ldx + col];
     double dx, site[4] = {0.0, 0.0, 0.0, 0.0};
     stat_channel<STAT, false, true>(fold * a.ch.scale[col], d, dx, site);
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(256) normal_eq_kernel(const NormalEqArgs a) {
         d.ratio = a.ch.ratio[col];
         d.gof_on = con ? poisson_gof(d.on) : a.ch.gof_on[col];
         d.gof_off = coff ? poisson_gof(d.off) : a.ch.gof_off[col];
+        d.den = a.ch.den[col];
         double dx = 0.0;
         const double l = stat_channel<STAT, true>(x0[col] * sc, d, dx);
         ll += l;
@@ -685,7 +688,7 @@ struct SpectrumPlan {
         double* tab[2 * ELISA_MAX_COMPONENTS] = {};
         int E = 0;
     } norm_grid[ELISA_MAX_NORMS];
-    double* chan = nullptr;  // 9 arrays of C_pad: scale on off sigma ratio gof_on gof_off area inv_width
+    double* chan = nullptr;  // 10 arrays of C_pad: scale on off sigma ratio gof_on gof_off area inv_width den
     PackedDevice fwd, bwd;   // R [E, C] tiled over C ; R^T [C, E] tiled over E
     I8Operand i8_fwd, i8_bwd;  // digit images of R^T rows (channels) / R rows (energies); img == nullptr: DMMA fold
     bool use_i8() const { return i8_fwd.img != nullptr; }
@@ -712,7 +715,7 @@ struct SpectrumPlan {
     }
     ChanArrays chan_view() const {
         return ChanArrays{chan, chan + C_pad, chan + 2 * C_pad, chan + 3 * C_pad,
-                          chan + 4 * C_pad, chan + 5 * C_pad, chan + 6 * C_pad};
+                          chan + 4 * C_pad, chan + 5 * C_pad, chan + 6 * C_pad, chan + 9 * C_pad};
     }
 };
 
@@ -1094,7 +1097,7 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
 
     // per-channel data, padded with benign values
     const int Cp = sp->C_pad;
-    std::vector<double> ch((size_t)9 * Cp, 0.0);
+    std::vector<double> ch((size_t)10 * Cp, 0.0);
     auto xlogy_h = [](double x, double y) { return x == 0.0 ? 0.0 : x * log(y); };
     for (int c = 0; c < Cp; ++c) {
         const bool v = c < C;
@@ -1112,6 +1115,10 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
         ch[6 * Cp + c] = xlogy_h(off, off) - off;
         ch[7 * Cp + c] = v ? sd.area_scale[c] : 0.0;
         ch[8 * Cp + c] = 1.0;  // 1 / channel_width: set by elisa_b200_plan_set_channel_width
+        {  // 1 / (2 a (a + 1)) (wstat) or 1 / (2 a) (pgstat): likelihood.py:79, 127 -- a division per channel, not per row
+            const double a = ch[4 * Cp + c];
+            ch[9 * Cp + c] = sd.stat == ELISA_STAT_WSTAT ? 1.0 / (2.0 * a * (a + 1.0)) : sd.stat == ELISA_STAT_PGSTAT ? 1.0 / (2.0 * a) : 0.0;
+        }
     }
     if ((rc = upload(plan, ch, &sp->chan))) return rc;
 
@@ -1224,6 +1231,9 @@ static const char* const k_src_skel =
     ;
 static const char* const k_src_slice =
 #include "embedded_slice_i8_cuh.inc"
+    ;
+static const char* const k_src_fastmath =
+#include "embedded_fastmath_cuh.inc"
     ;
 
 struct NvrtcApi {
@@ -1492,10 +1502,10 @@ static bool compile_unfold_source(const std::string& src, std::vector<char>* cub
         *why = "libnvrtc.so.12 not found";
         return false;
     }
-    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h, k_src_slice};
-    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h", "slice_i8.cuh"};
+    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h, k_src_slice, k_src_fastmath};
+    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h", "slice_i8.cuh", "fastmath.cuh"};
     nvrtcProgram prog = nullptr;
-    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 5, headers, names) != NVRTC_SUCCESS) {
+    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 6, headers, names) != NVRTC_SUCCESS) {
         *why = "nvrtcCreateProgram failed";
         return false;
     }
@@ -2216,6 +2226,7 @@ __device__ __forceinline__ void jacobian_one(const JacobianArgs& a, int row, int
     d.ratio = a.ch.ratio[col];
     d.gof_on = poisson_gof(d.on);
     d.gof_off = poisson_gof(d.off);
+    d.den = a.ch.den[col];
     const double sc = a.ch.scale[col];
     const double raw = a.X[(size_t)row * a.ldx + col] * sc;
     double pass;

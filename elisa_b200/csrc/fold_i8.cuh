@@ -688,6 +688,7 @@ struct ChanArrays {
     const double* ratio;
     const double* gof_on;
     const double* gof_off;
+    const double* den;  // stat_den(ratio)
 };
 
 // transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the tile's energies.
@@ -852,6 +853,8 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
             }
             if (STAT == ELISA_STAT_PGSTAT) d.sigma = a.ch.sigma[col];
             if (STAT == ELISA_STAT_WSTAT) d.gof_off = a.ch.gof_off[col];
+            d.den = 0.0;
+            if (STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) d.den = a.ch.den[col];
             if (con != nullptr) {
                 d.on = con[col];
                 if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);

@@ -8,6 +8,7 @@
 // of the oracle in tests/.
 #pragma once
 #include "../../include/elisa_b200.h"
+#include "fastmath.cuh"
 
 namespace elisa {
 
@@ -18,9 +19,32 @@ struct ChannelData {
     double ratio;    // back_ratio
     double gof_on;   // xlogy(on, on) - on     (saturated-model offset, likelihood.py:172)
     double gof_off;  // xlogy(off, off) - off
+    double den;      // stat_den(ratio): 1 / (2 a (a + 1)) for wstat, 1 / (2 a) for pgstat -- per channel, not per row
 };
 
-__device__ __forceinline__ double xlogy(double x, double y) { return x == 0.0 ? 0.0 : x * log(y); }
+template <int STAT>
+__device__ __forceinline__ double stat_den(double a) {
+    if (STAT == ELISA_STAT_WSTAT) return 1.0 / (2.0 * a * (a + 1.0));
+    if (STAT == ELISA_STAT_PGSTAT) return 1.0 / (2.0 * a);
+    return 0.0;
+}
+
+// sqrt(q) and 1 / sqrt(q) together for normal positive q: one MUFU.RSQ64H seed and two Newton steps
+// instead of a square root AND a division (the profile-background formulas need both,
+// likelihood.py:76-86, 118-132, and their derivatives).  Both within 1 ulp.
+__device__ __forceinline__ void sqrt_and_rsqrt(double q, double& root, double& inv) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    const double h = 0.5 * q;
+    y = fma(y, fma(-h * y, y, 0.5), y);  // y <- y (1.5 - h y^2)
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    double r = q * y;
+    r = fma(fma(-r, r, q), 0.5 * y, r);  // one correction of the root
+    root = r;
+    inv = y;
+}
+
+__device__ __forceinline__ double xlogy(double x, double y) { return x == 0.0 ? 0.0 : x * fm::log(y); }
 __device__ __forceinline__ double poisson_gof(double n) { return xlogy(n, n) - n; }
 
 // BetterPoisson.log_prob(n; mu) and d/dmu.
@@ -33,9 +57,12 @@ __device__ __forceinline__ double poisson_ll(double n, double mu, double gof, do
 
 // clip(x, 1e-30, 1e15) of likelihood.py:208 etc.; pass = d clip / d x
 __device__ __forceinline__ double clip_counts(double x, double& pass) {
-    pass = (x >= 1e-30 && x <= 1e15) ? 1.0 : 0.0;
-    if (x != x) return x;  // jnp.clip propagates NaN
-    return fmin(fmax(x, 1e-30), 1e15);
+    pass = 1.0;
+    if (!(x >= 1e-30 && x <= 1e15)) {  // rare: one predictable branch instead of min / max / NaN selects per channel
+        pass = 0.0;
+        x = x < 1e-30 ? 1e-30 : (x > 1e15 ? 1e15 : x);  // jnp.clip propagates NaN
+    }
+    return x;
 }
 
 // One channel of one statistic.  `x` = source_rate * exposure BEFORE the clip.
@@ -70,12 +97,19 @@ __device__ __forceinline__ double stat_channel(double x, const ChannelData& d, d
         const double e = d.off - a * var;
         const double f = a * var * n + e * s;
         const double c = a * e - s;
-        const double dd = sqrt(c * c + 4.0 * a * f);
+        const double q = c * c + 4.0 * a * f;
+        double dd, inv_dd;
+        if (q > 1e-280 && q < 1e280) {
+            sqrt_and_rsqrt(q, dd, inv_dd);
+        } else {  // zero, negative (NaN as in the reference), denormal or huge: the plain operations
+            dd = sqrt(q);
+            inv_dd = 1.0 / dd;
+        }
         double b, db = 0.0;
         if (e >= 0.0 || f >= 0.0) {
             if (n > 0.0) {
-                b = (c + dd) / (2.0 * a);
-                if (GRAD) db = (-1.0 + (-c + 2.0 * a * e) / dd) / (2.0 * a);
+                b = (c + dd) * d.den;
+                if (GRAD) db = (-1.0 + (-c + 2.0 * a * e) * inv_dd) * d.den;
             } else {
                 b = e;
             }
@@ -106,10 +140,17 @@ __device__ __forceinline__ double stat_channel(double x, const ChannelData& d, d
             }
         } else {
             const double c = a * (n_on + n_off) - (a + 1.0) * s;
-            const double dd = sqrt(c * c + 4.0 * a * (a + 1.0) * n_off * s);
-            const double den = 1.0 / (2.0 * a * (a + 1.0));
+            const double q = c * c + 4.0 * a * (a + 1.0) * n_off * s;
+            double dd, inv_dd;
+            if (q > 1e-280 && q < 1e280) {
+                sqrt_and_rsqrt(q, dd, inv_dd);
+            } else {
+                dd = sqrt(q);
+                inv_dd = 1.0 / dd;
+            }
+            const double den = d.den;
             b = (c + dd) * den;
-            if (GRAD) db = (-(a + 1.0) + (-(a + 1.0) * c + 2.0 * a * (a + 1.0) * n_off) / dd) * den;
+            if (GRAD) db = (-(a + 1.0) + (-(a + 1.0) * c + 2.0 * a * (a + 1.0) * n_off) * inv_dd) * den;
         }
         const double mu = s + a * b;
         double dmu, dmb;

@@ -147,12 +147,13 @@ def test_specialised_kernel_compiles_for_every_component(lib):
         n = lib.elisa_b200_specialise_check(C.byref(md), max(cm.nparam, 1), buf, len(buf))
         assert n > 0, (repr(m), lib.elisa_b200_last_error().decode()[:500])
         src = buf.value.decode()
-        assert 'unfold_generic<Model' in src and src.count('leaf_bin_pc<') == len(cm.leaves)
+        assert 'unfold_generic<ModelG' in src and src.count('leaf_bin_pc<') == 2 * len(cm.leaves)  # ModelV + ModelG
 
 
 def test_specialised_kernel_compiles_for_convolution_models(lib):
-    """Energy shifts become literals of the leaf calls; a flux normalisation adds a `sub<k>`
-    function over its own grid, the pre-pass in `norms` and one multiply in `bin`."""
+    """Energy shifts become literals of the leaf calls; a flux normalisation adds a pre-pass over
+    its own grid in `norms` (value accumulator in ModelV and ModelG, one more per tangent column
+    in ModelG) and one multiply in `bin`."""
     import conv_cases
 
     buf = C.create_string_buffer(1 << 16)
@@ -162,8 +163,8 @@ def test_specialised_kernel_compiles_for_convolution_models(lib):
         n = lib.elisa_b200_specialise_check(C.byref(md), max(cm.nparam, 1), buf, len(buf))
         assert n > 0, (name, lib.elisa_b200_last_error().decode()[:500])
         src = buf.value.decode()
-        assert src.count('static T sub') == len(cm.norms)
-        assert src.count('warp_sum(acc)') == len(cm.norms)
+        assert src.count('acc_v = warp_sum(acc_v)') == 2 * len(cm.norms)  # ModelV + ModelG
+        assert src.count('const GridView gv = a.ngv[') == 2 * len(cm.norms)
     # a malformed program: the normalisation opcode without a descriptor
     cm = conv_cases.cases()['phflux_pl'][0].compile()
     md, _keep = cm.to_desc()
@@ -249,3 +250,18 @@ def test_sharded_map_gloo(n, world):
     for rank, ok, first_call, local_rows in res:
         assert ok
         assert first_call == b[rank][1] - b[rank][0] == local_rows
+
+
+# ------------------------------------------------------------------ table-driven exp / log
+def test_fastmath_against_libm(tmp_path):
+    """csrc/fastmath.cuh compiles for the host too: its exp / log / expm1 against glibc's long-double
+    versions over 2e6 arguments -- <= 1.5 ulp (4.5 for expm1 = exp - 1), specials handed to libm."""
+    import subprocess
+
+    exe = tmp_path / 'fastmath_check'
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(['g++', '-O2', '-std=c++17', '-I', os.path.join(root, 'elisa_b200', 'csrc'),
+                    os.path.join(root, 'tools', 'fastmath_check.cc'), '-o', str(exe)], check=True)
+    res = subprocess.run([str(exe), '2000000'], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert 'exp(-800)=0 exp(800)=inf exp(nan)=nan log(0)=-inf log(-1)=-nan log(inf)=inf' in res.stdout

@@ -61,33 +61,32 @@ def test_guard_estimate_covers_the_true_error(lib, block):
 
 
 def test_only_flagged_rows_take_the_dmma_fold(lib):
-    """A batch in which a few rows are starved (a narrow line through a diagonal response):
-    the guarded entry point re-evaluates exactly those rows on the DMMA fold."""
+    """A batch of steep power laws (index 4 over three decades) with a few flat ones (index 0.3)
+    mixed in, none of them among the pilot rows: the envelopes fit the steep rows, the guard flags
+    the flat ones, and the guarded entry point re-evaluates exactly those rows on the DMMA fold."""
     from parity import RTOL, oracle_eval, rel_err_grad, rel_err_value
 
-    E = C = 256
-    rng = np.random.default_rng(3)
-    R = np.eye(E) * 50.0 + 0.5
-    d = FixedData('d', np.linspace(1.0, 10.0, E + 1), rng.poisson(20.0, C).astype(float), np.ones(C), 100.0, response_matrix=R)
-    U = M.UniformParameter
-    model = M.Gauss(El=U('El', 5.0, 1.0, 10.0), sigma=U('sigma', 0.5, 0.001, 5.0), K=U('K', 10.0, 1e-3, 1e6)) + \
-        M.PowerLaw(alpha=U('alpha', 1.5, -3.0, 10.0), K=U('Kp', 0.4, 1e-6, 1e3))
-    n = 2000
-    theta = np.column_stack([5.0 + 0.2 * rng.standard_normal(n), 0.5 + 0.02 * rng.standard_normal(n), np.full(n, 10.0),
-                             1.5 + 0.02 * rng.standard_normal(n), np.full(n, 0.4)])
-    odd = rng.choice(n, size=17, replace=False)
-    theta[odd, 1] = 0.004   # a line much narrower than a bin ...
-    theta[odd, 2] = 3e5     # ... towering over the continuum: these rows differ in SHAPE from the pilot's
+    rng = np.random.default_rng(5)
+    E, C, n = 256, 128, 2000
+    eg = np.geomspace(0.1, 100.0, E + 1)
+    R = np.abs(rng.standard_normal((E, C))) + 0.1
+    d = FixedData('d', eg, rng.poisson(50.0, C).astype(float), np.ones(C), 10.0, response_matrix=R)
+    model = M.PowerLaw(alpha=M.UniformParameter('alpha', 2.0, -3.0, 10.0), K=M.UniformParameter('K', 1.0, 1e-10, 1e10))
+    theta = np.column_stack([4.0 + 0.01 * rng.random(n), np.full(n, 5.0)])
+    odd = 7 + 15 * rng.choice(n // 15 - 1, size=17, replace=False)  # the pilot takes rows 0, 15, 30, ...
+    theta[odd] = np.column_stack([0.3 + 0.01 * rng.random(17), np.full(17, 0.05)])
     cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
     ll_ref, g_ref = oracle_eval(cfg)
     lk = Likelihood([d], model, ['cstat'])
     assert lk.fold_slices == [6]
     ll, g = lk.loglike_and_grad(theta)
     assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL and rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
-    assert 0 < lk.fallback_rows <= 4 * len(odd), (lk.fallback_rows, lk.guard_fallbacks)
+    assert lk.fallback_rows == len(odd) and lk.guard_fallbacks == 1 and lk.rebalances == 0, \
+        (lk.fallback_rows, lk.guard_fallbacks, lk.rebalances)
     # the host entry point does the same
     ll_h, g_h = lk.loglike_and_grad_host(theta)
     assert np.array_equal(ll_h, ll.cpu().numpy()) and np.array_equal(g_h, g.cpu().numpy())
+    assert lk.fallback_rows == 2 * len(odd)
     lk.close()
 
 

@@ -1,0 +1,12 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+timeout 2400 python -m pytest tests -m gpu -q -x > $OUT/r02e_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/r02e_pytest.log
+tail -8 $OUT/r02e_pytest.log
+timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/r02e_bench.json 2> $OUT/r02e_bench.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r02e_bench.json'))
+print(d['value'], d['e2e'], d['roofline']['classes_ms_per_step'], d['parity'])
+PY
