@@ -621,6 +621,7 @@ def run_b200(args):
     # ---- 4. the other BASELINE configurations (all ranks take part in the sharded ones)
     del ll_all, grad_all
     lk_chunk, lk_ws = lk.chunk, lk.workspace_bytes
+    products = lk.fold_products(0) if ks else (0.0, 0.0)  # digit products EXECUTED per FP64 multiply-add
     configs = None
     if not args.no_configs:
         lk.close()
@@ -643,7 +644,10 @@ def run_b200(args):
     if ks:
         # the ALGORITHMIC unit of the integer engine: one FP64-accurate multiply-add = ks (ks + 1) / 2 exact
         # int8 digit products; executed int8 ops = 2 E C x products per eval and fold
-        prod_f, prod_b = ks * (ks + 1) // 2, ks_bwd * (ks_bwd + 1) // 2
+        # nominal products for ks digits; executed = averaged over the operand's (tile, k-block) pairs after the
+        # kernel skipped the digit planes that are zero there (elisa_b200_plan_fold_products)
+        nom_f, nom_b = ks * (ks + 1) // 2, ks_bwd * (ks_bwd + 1) // 2
+        prod_f, prod_b = products
         ops_f = 2.0 * E * C * n * S * args.steps * prod_f
         ops_b = 2.0 * E * C * n * S * args.steps * prod_b
         tops = (ops_f + ops_b) / (gemm_ms * 1e-3) / 1e12
@@ -660,7 +664,9 @@ def run_b200(args):
         roofline = {
             'bound': 'tensor',
             'kernel': 'fold_i8_kernel (forward + transposed fold; int8 tcgen05.mma, %d / %d digits per operand = %d + %d exact '
-                      'digit products per FP64 product, int32 accumulation in TMEM)' % (ks, ks_bwd, prod_f, prod_b),
+                      'digit products per FP64 product, of which %.2f + %.2f are executed on this response (zero digit planes '
+                      'outside the redistribution core are skipped); int32 accumulation in TMEM)' % (ks, ks_bwd, nom_f, nom_b, prod_f, prod_b),
+            'digit_products': {'nominal': [nom_f, nom_b], 'executed': [prod_f, prod_b]},
             'achieved': tops, 'peak': peak, 'unit': 'TOP/s', 'frac': tops / peak,
             'peak_source': how + '; nominal dense int8 4500 TOP/s; achieved = int8 ops the digit products execute '
                                  '(2 E C x products per eval and fold) / device time of the fold kernels',

@@ -673,6 +673,8 @@ struct I8Operand {
     int n_tiles = 0;
     int64_t n_images = 0;
     int ks = 0;  // slices per element of this operand
+    uint8_t* lead = nullptr;  // [n_images] leading all-zero slices of each image (lead_zero_kernel)
+    std::vector<int32_t> h_kb_lo, h_kb_hi;  // host copies of the stored k-block ranges (work accounting)
 };
 
 struct SpectrumPlan {
@@ -1484,6 +1486,11 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
         const char* env = getenv("ELISA_B200_UNFOLD_MIN_BLOCKS");  // occupancy experiments
         s += "#define UNFOLD_MIN_BLOCKS " + std::to_string(env ? std::max(1, atoi(env)) : 1) + "\n";
     }
+    {
+        char buf[32];
+        snprintf(buf, sizeof buf, "0x%xu", m.used_mask);
+        s += std::string("#define UNFOLD_USED_MASK ") + buf + "\n";
+    }
     s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\n";
     s += generate_model_struct(m, P, false, "ModelV");
     s += generate_model_struct(m, P, true, "ModelG");
@@ -1621,7 +1628,7 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.e_pad = e_pad;
     a.clip = clip ? 1 : 0;
     a.U = U;
-    a.dU = dU;
+    a.dU = (plan->debug_skip & 32) ? nullptr : dU;
     a.plane = (int64_t)n_rows * ld;
     a.used_mask = sp.model.used_mask;
     a.kb_total = round_up(ld, I8_BK) / I8_BK;
@@ -1733,6 +1740,19 @@ static int launch_slice(ElisaPlan* plan, int ks, const SliceArgs& a, int cls, cu
     return ELISA_OK;
 }
 
+static int launch_lead_zero(ElisaPlan* plan, const I8Operand& op, cudaStream_t st) {
+    if (op.lead == nullptr || op.n_images == 0) return ELISA_OK;
+    switch (op.ks) {
+#define X(K) case K: lead_zero_kernel<K><<<(unsigned)op.n_images, 256, 0, st>>>(op.img, op.n_images, I8_B_SLICE, op.lead); break;
+        ELISA_FOR_EACH_KS(X)
+#undef X
+        default: return fail(ELISA_ERR_INVALID, "fold slices must be 4..7");
+    }
+    if (plan) ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
 template <int KS, class Epi, int NI>
 static int launch_fold_i8_ni(ElisaPlan* plan, int cls, const FoldI8Args& fa, const Epi& epi, int sm_count,
                              cudaStream_t st);
@@ -1788,6 +1808,12 @@ static FoldI8Args fold_i8_args(const ElisaPlan* plan, const I8Operand& B, int kb
     fa.b_tile_img = B.tile_img;
     fa.kb_lo = B.kb_lo;
     fa.kb_hi = B.kb_hi;
+    // Skipping of leading zero digit planes: OFF unless ELISA_B200_I8_SKIP=1.  On the bench response it
+    // removes 44 % (forward) / 24 % (transposed) of the digit products and the kernel is no faster for
+    // it (profiles/r02_digit_skip.md: the folds are bound by the latency of their load / issue
+    // handshakes, not by the MMA count), the transposed fold even 6 % slower.
+    static const bool skip = getenv("ELISA_B200_I8_SKIP") && atoi(getenv("ELISA_B200_I8_SKIP")) != 0;
+    fa.b_lead = skip ? B.lead : nullptr;
     fa.m_tiles = m_tiles;
     fa.n_tiles = B.n_tiles;
     fa.n_groups = 1;  // set at launch
@@ -1844,6 +1870,11 @@ static int build_i8_operand(ElisaPlan* plan, int ks, const std::vector<double>& 
     plan->owned.push_back(out->img);
     CUDA_TRY(cudaMalloc((void**)&out->scale, (size_t)n_tiles * I8_BN * 8));
     plan->owned.push_back(out->scale);
+    CUDA_TRY(cudaMalloc((void**)&out->lead, std::max<size_t>((size_t)n_images, 16)));
+    plan->owned.push_back(out->lead);
+    CUDA_TRY(cudaMemset(out->lead, 0, std::max<size_t>((size_t)n_images, 16)));
+    out->h_kb_lo = kb_lo;
+    out->h_kb_hi = kb_hi;
     double* tmp = nullptr;
     CUDA_TRY(cudaMalloc((void**)&tmp, std::max<size_t>(dense.size() * 8, 16)));
     cudaError_t e = cudaMemcpy(tmp, dense.data(), dense.size() * 8, cudaMemcpyHostToDevice);
@@ -1867,6 +1898,11 @@ static int build_i8_operand(ElisaPlan* plan, int ks, const std::vector<double>& 
         plan->profiling = false;
         rc = launch_slice(plan, ks, a, ELISA_PROFILE_REDUCE, nullptr);
         plan->profiling = prof;
+        if (rc == ELISA_OK) {
+            out->ks = ks;
+            out->n_images = n_images;
+            rc = launch_lead_zero(plan, *out, nullptr);
+        }
         if (rc == ELISA_OK) e = cudaDeviceSynchronize();
     }
     plan->owned.push_back(tmp);  // kept: the operand is re-sliced with column scales when the fold is balanced
@@ -1951,7 +1987,8 @@ static int reslice_operand(ElisaPlan* plan, const I8Operand& op, const double* k
     a.scale = op.scale;
     a.kscale = kscale;
     a.abs_sum = op.abs_sum;
-    return launch_slice(plan, op.ks, a, ELISA_PROFILE_SLICE, st);
+    const int rc = launch_slice(plan, op.ks, a, ELISA_PROFILE_SLICE, st);
+    return rc ? rc : launch_lead_zero(plan, op, st);  // the scaled operand has other leading zeros
 }
 
 // forward fold (plain store) -> statistic + digits of W -> transposed fold with the gradient epilogue
@@ -3188,6 +3225,34 @@ int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
     return plan->spec[spectrum].use_i8() ? plan->ks : 0;
 }
+int elisa_b200_plan_fold_products(ElisaPlan* plan, int32_t spectrum, double out[2]) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S || out == nullptr) return fail(ELISA_ERR_INVALID, "fold_products: bad argument");
+    const SpectrumPlan& sp = plan->spec[spectrum];
+    out[0] = out[1] = 0.0;
+    if (!sp.use_i8()) return ELISA_OK;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    static const bool skip = getenv("ELISA_B200_I8_SKIP") && atoi(getenv("ELISA_B200_I8_SKIP")) != 0;
+    for (int k = 0; k < 2; ++k) {
+        const I8Operand& op = k == 0 ? sp.i8_fwd : sp.i8_bwd;
+        std::vector<uint8_t> lead((size_t)op.n_images);
+        if (op.n_images) CUDA_TRY(cudaMemcpy(lead.data(), op.lead, lead.size(), cudaMemcpyDeviceToHost));
+        const int kb_total = round_up(op.K, I8_BK) / I8_BK;
+        double prod = 0.0;
+        int64_t img = 0;
+        for (int t = 0; t < op.n_tiles; ++t)
+            for (int kb = op.h_kb_lo[t]; kb < op.h_kb_hi[t]; ++kb, ++img) {
+                const int z = (skip && kb != op.h_kb_lo[t]) ? std::min<int>(lead[img], op.ks) : 0;
+                prod += 0.5 * (op.ks - z) * (op.ks - z + 1);
+            }
+        out[k] = op.n_tiles && kb_total ? prod / ((double)op.n_tiles * kb_total) : 0.0;
+    }
+    cudaSetDevice(prev);
+    return ELISA_OK;
+}
+
 int elisa_b200_plan_fold_slices_bwd(const ElisaPlan* plan, int32_t spectrum) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
     return plan->spec[spectrum].use_i8() ? plan->ks_bwd : 0;
@@ -3360,6 +3425,7 @@ int elisa_b200_sliced_gemm_dev(const double* A, int64_t lda, const double* B, in
     FoldI8Args fa;
     fa.A_img = a_img; fa.a_scale = a_sc; fa.kb_a = kb; fa.B_img = b_img; fa.b_scale = b_sc; fa.b_tile_img = timg;
     fa.kb_lo = rng; fa.kb_hi = rng + n_tiles; fa.m_tiles = m_tiles; fa.n_tiles = n_tiles;
+    fa.b_lead = nullptr;
     fa.n_groups = 1;  // set at launch
     fa.trap_info = trap_info_dev();
     fa.debug = getenv("ELISA_B200_I8_DEBUG") ? atoi(getenv("ELISA_B200_I8_DEBUG")) : 0;

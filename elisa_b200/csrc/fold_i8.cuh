@@ -296,6 +296,26 @@ __global__ void __launch_bounds__(128) col_envelope_kernel(const double* X, int6
     inv_exp[k] = (uint8_t)down;
 }
 
+// Leading all-zero slices of every image of a static operand: lead[img] in [0, KS].  One block
+// per image.
+template <int KS>
+__global__ void __launch_bounds__(256) lead_zero_kernel(const int8_t* img, int64_t n_images, int slice_bytes, uint8_t* lead) {
+    const int64_t im = blockIdx.x;
+    if (im >= n_images) return;
+    const uint4* base = reinterpret_cast<const uint4*>(img + (size_t)im * KS * slice_bytes);
+    const int per_slice = slice_bytes / 16;
+    int z = 0;
+    for (; z < KS; ++z) {
+        unsigned any = 0;
+        for (int t = threadIdx.x; t < per_slice; t += blockDim.x) {
+            const uint4 v = base[(size_t)z * per_slice + t];
+            any |= v.x | v.y | v.z | v.w;
+        }
+        if (__syncthreads_or(any != 0)) break;
+    }
+    if (threadIdx.x == 0) lead[im] = (uint8_t)z;
+}
+
 // ---------------------------------------------------------------------------------------
 // the fold kernel
 // ---------------------------------------------------------------------------------------
@@ -308,6 +328,13 @@ struct FoldI8Args {
     const int64_t* b_tile_img;  // [n_tiles]
     const int32_t* kb_lo;       // [n_tiles] k-block range of column tile nt
     const int32_t* kb_hi;
+    // Leading all-zero digit slices of each stored B image (lead_zero_kernel), same indexing as the
+    // images; nullptr: none.  A response's redistribution core towers over its tails by 4-6 decades,
+    // so outside the core the most significant one or two digit planes of a (64-row, 128-byte)
+    // block are zero throughout: the products with those planes -- 6 + 5 of the 21 for two leading
+    // zero slices -- and the A slices only they would meet are neither loaded nor issued.  Exact:
+    // only multiplications by zero digits are skipped, results are bit-identical.
+    const uint8_t* b_lead;
     int32_t m_tiles, n_tiles;
     int32_t n_groups;  // ceil(n_tiles / I8_GROUP)
     int32_t* trap_info;  // host-mapped int32[128] or nullptr: which waits stalled (see mbar_wait)
@@ -425,6 +452,11 @@ __device__ __forceinline__ I8Item i8_item(const FoldI8Args& a, int item) {
 #define I8_FOR_EACH_TILE(it, a, nt) \
     for (int nt = (it).g * I8_GROUP, ne_ = min(nt + I8_GROUP, (a).n_tiles); nt < ne_; ++nt)
 
+template <int V>
+struct I8Int {
+    static constexpr int value = V;
+};
+
 template <int KS, class Epi, int NI = Epi::ISSUERS>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi epi) {
@@ -490,19 +522,27 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 const int8_t* bsrc = a.B_img + (size_t)a.b_tile_img[nt] * B_BLOCK;
                 const int8_t* asrc = a.A_img + ((size_t)it.mt * a.kb_a + lo) * KS * I8_A_SLICE;
                 for (int kb = lo; kb < hi; ++kb) {
+                    // leading zero slices of this B block; the tile's first block is taken whole (its
+                    // slice-0 products initialise every accumulator)
+                    const int z = (a.b_lead != nullptr && kb != lo) ? min((int)a.b_lead[a.b_tile_img[nt] + (kb - lo)], KS) : 0;
                     mbar_wait(b_empty(bs), bph ^ 1u, a.trap_info, 4 + 16 * bs, nt);
                     if (lane == 0) {
-                        if (a.debug & 2) {
+                        if ((a.debug & 2) || z == KS) {
                             mbar_arrive(b_full(bs));
                         } else {
-                            mbar_expect_tx(b_full(bs), B_BLOCK);
-                            bulk_g2s(s_B + bs * B_BLOCK, bsrc, B_BLOCK, b_full(bs));
+                            const uint32_t bytes = (uint32_t)(KS - z) * I8_B_SLICE;
+                            mbar_expect_tx(b_full(bs), bytes);
+                            bulk_g2s(s_B + bs * B_BLOCK + z * I8_B_SLICE, bsrc + z * I8_B_SLICE, bytes, b_full(bs));
                         }
                     }
                     bsrc += B_BLOCK;
                     if (++bs == I8_NB) { bs = 0; bph ^= 1u; }
 #pragma unroll
                     for (int i = 0; i < KS; ++i) {
+                        if (i + z > KS - 1) {  // this A slice would only meet zero digits
+                            asrc += I8_A_SLICE;
+                            continue;
+                        }
                         const int r = i % NI;
                         const int slot = ring_base(r) + as[r];
                         mbar_wait(a_empty(slot), aph[r] ^ 1u, a.trap_info, 2 + 16 * slot, nt);
@@ -550,11 +590,14 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                     tc_fence_after();
                 }
                 if (lo < hi) iph ^= 1u;
-                for (int kb = lo; kb < hi; ++kb) {
-                    mbar_wait(b_full(bs), bph, a.trap_info, 3 + 16 * bs, nt);
-                    const uint32_t sb = s_B + bs * B_BLOCK;
+                // The MMAs of one k-block whose B image has Z leading zero slices, with every instruction
+                // shape a compile-time constant (a run-time column loop costs the single issuing
+                // thread -- the bottleneck of this kernel -- more than the skipped MMAs give back).
+                auto issue_block = [&](auto zc, int kb) {
+                    constexpr int Z = decltype(zc)::value;
+                    const uint32_t sb = s_B + bs * B_BLOCK + Z * I8_B_SLICE;  // first non-zero slice
 #pragma unroll
-                    for (int i = 0; i < KS; ++i) {
+                    for (int i = 0; i + Z <= KS - 1; ++i) {
                         if (i % NI == w) {
                             const int slot = base + as;
                             mbar_wait(a_full(slot), aph, a.trap_info, 1 + 16 * slot, nt);
@@ -565,14 +608,14 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                                 for (int ks = 0; ks < ((a.debug & 4) ? 0 : I8_BK / 32); ++ks) {
                                     const uint64_t ad = umma_desc_sw128(sa + 32 * ks);
                                     const uint32_t acc = (i > 0 || ks > 0 || kb > lo) ? 1u : 0u;
-                                    // (KS - i) * 64 columns in equal parts of <= 256 (multiples of 32)
-                                    const int width = (KS - i) * I8_BN;
+                                    // (KS - i - Z) * 64 columns in equal parts of <= 256 (multiples of 32)
+                                    const int width = (KS - i - Z) * I8_BN;
                                     const int parts = (width + 255) / 256;
                                     const int n = width / parts;  // 192, 160, 224 ...: multiples of 32 for KS <= 8
 #pragma unroll
                                     for (int c0 = 0; c0 < width; c0 += n) {
                                         const uint64_t bd = umma_desc_sw128(sb + c0 * I8_BK + 32 * ks);
-                                        tc_mma_i8(tmem + i * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
+                                        tc_mma_i8(tmem + (i + Z) * I8_BN + c0, ad, bd, umma_idesc_i8(n), acc);
                                     }
                                 }
                                 tc_commit(a_empty(slot));
@@ -581,6 +624,20 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                             __syncwarp();
                             if (++as == size) { as = 0; aph ^= 1u; }
                         }
+                    }
+                };
+                for (int kb = lo; kb < hi; ++kb) {
+                    const int z = (a.b_lead != nullptr && kb != lo) ? min((int)a.b_lead[a.b_tile_img[nt] + (kb - lo)], KS) : 0;
+                    mbar_wait(b_full(bs), bph, a.trap_info, 3 + 16 * bs, nt);
+                    switch (z) {
+                        case 0: issue_block(I8Int<0>{}, kb); break;
+                        case 1: issue_block(I8Int<1>{}, kb); break;
+                        case 2: issue_block(I8Int<2>{}, kb); break;
+                        case 3: issue_block(I8Int<3>{}, kb); break;
+                        case 4: issue_block(I8Int<(KS > 4 ? 4 : KS)>{}, kb); break;
+                        case 5: issue_block(I8Int<(KS > 5 ? 5 : KS)>{}, kb); break;
+                        case 6: issue_block(I8Int<(KS > 6 ? 6 : KS)>{}, kb); break;
+                        default: break;  // every slice zero: nothing to multiply
                     }
                     if (lane == 0) tc_commit(b_empty(bs));
                     __syncwarp();

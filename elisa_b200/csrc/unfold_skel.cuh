@@ -52,28 +52,41 @@ constexpr int UNFOLD_WARPS = 4;
 __device__ __forceinline__ void unfold_zero(const UnfoldCore& a, size_t row_off, int lo, int hi, int lane, bool grad) {
     for (int e = lo + lane; e < hi; e += 32) {
         a.U[row_off + e] = 0.0;
-        if (grad)
+        if (grad && a.dU != nullptr)
             for (int j = 0; j < a.P; ++j)
                 if ((a.used_mask >> j) & 1u) a.dU[j * a.plane + row_off + e] = 0.0;
     }
 }
 
+// UNFOLD_USED_MASK (defined by the generated translation unit): the theta columns the model
+// depends on, known when the kernel is specialised -- the per-plane tests fold away.
 template <typename T>
 __device__ __forceinline__ double unfold_store(const UnfoldCore& a, size_t off, const T& res, double k = 1.0) {
     const double v = value(res);
     bool pass = true;
     double u = v;
-    if (a.clip) {
-        pass = (v >= 1e-300) && (v <= 1e300);
-        u = fmin(fmax(v, 1e-300), 1e300);
-        if (v != v) u = v;  // jnp.clip propagates NaN
+    if (a.clip && !(v >= 1e-300 && v <= 1e300)) {  // clip(unfold, 1e-300, 1e300), likelihood.py:204: rare, one branch
+        pass = false;
+        u = v < 1e-300 ? 1e-300 : (v > 1e300 ? 1e300 : v);  // jnp.clip propagates NaN
     }
     u *= k;  // a power of two: exact
     a.U[off] = u;
     if constexpr (Scalar<T>::NP > 0) {
+#ifdef UNFOLD_USED_MASK
+        constexpr uint32_t used = UNFOLD_USED_MASK;
+        constexpr int np = Scalar<T>::NP;
+#else
+        const uint32_t used = a.used_mask;
+        const int np = a.P;
+#endif
+        if (a.dU != nullptr) {  // nullptr: timing experiment (elisa_b200_plan_set_debug bit 32), the tangents are dropped
+            double* q = a.dU + off;
 #pragma unroll
-        for (int j = 0; j < Scalar<T>::NP; ++j)
-            if (j < a.P && ((a.used_mask >> j) & 1u)) a.dU[j * a.plane + off] = pass ? res.d[j] : 0.0;
+            for (int j = 0; j < Scalar<T>::NP; ++j) {
+                if (j < np && ((used >> j) & 1u)) *q = pass ? res.d[j] : 0.0;
+                q += a.plane;
+            }
+        }
     }
     return u;
 }

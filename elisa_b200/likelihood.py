@@ -252,6 +252,14 @@ class Likelihood:
         """Per dataset: digits of the TRANSPOSED fold (gradient side), 0 = FP64 DMMA fold."""
         return [int(self._lib.elisa_b200_plan_fold_slices_bwd(self._h, k)) for k in range(len(self.data))]
 
+    def fold_products(self, k: int = 0):
+        """(forward, transposed): int8 digit products the integer fold executes per FP64
+        multiply-add of dataset k's dense contraction (``elisa_b200_plan_fold_products``); 21 for 6
+        digits on a response without structure, fewer where digit planes are zero.  Synchronises."""
+        out = (C.c_double * 2)()
+        _lib.check(self._lib.elisa_b200_plan_fold_products(self._h, int(k), out))
+        return float(out[0]), float(out[1])
+
     def set_debug(self, skip_mask: int):
         """Timing experiments only (``elisa_b200_plan_set_debug``)."""
         _lib.check(self._lib.elisa_b200_plan_set_debug(self._h, int(skip_mask)))

@@ -330,6 +330,14 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
  * with FP64 DMMA, -1 on a bad argument; _bwd: of its transposed fold                     */
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
 int elisa_b200_plan_fold_slices_bwd(const ElisaPlan* plan, int32_t spectrum);
+/* int8 digit products the integer fold EXECUTES per FP64 multiply-add of the dense contraction,
+ * averaged over the (column tile, k-block) pairs of the forward (out[0]) and the transposed
+ * (out[1]) operand: slices (slices + 1) / 2 for a response without structure (21 for 6 digits),
+ * less when k-blocks hold no non-zeros at all (band-sparse responses) or their most significant
+ * digit planes are zero (everything outside the redistribution core of an ordinary response),
+ * which the kernel skips.  Depends on the balancing envelopes: call after a first evaluation.
+ * Synchronises the device.  0 for a spectrum that folds with DMMA.                          */
+int elisa_b200_plan_fold_products(ElisaPlan* plan, int32_t spectrum, double out[2]);
 /* Accuracy guard of the sliced-integer fold.  Its error is bounded relative to (largest
  * element of the balanced row of U) x (sum over the balanced column of the response), see
  * elisa_b200_plan_rebalance below; rows far from the spectrum the envelopes were taken on, or
@@ -405,7 +413,8 @@ int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* the
                             const double* counts_off, int64_t n, double* x, double* ds, double* dl_dx,
                             void* cuda_stream);
 /* Timing experiments only: bit mask of kernel classes to SKIP in the evaluation entry points
- * (1 unfold, 2 forward fold, 4 statistic, 8 transposed fold, 16 reduce); results are garbage
+ * (1 unfold, 2 forward fold, 4 statistic, 8 transposed fold, 16 reduce, 32 the dU/dtheta stores of
+ * the specialised unfold kernel); results are garbage
  * while a bit is set.  tools/power_probe.py uses it to time one class in isolation.        */
 int elisa_b200_plan_set_debug(ElisaPlan* plan, int32_t skip_mask);
 /* 1 if spectrum's component kernel is the runtime-specialised one, 0 if interpreted */

@@ -66,7 +66,7 @@ def main():
     ALL = 31
     cases = [('all five classes (the bench step)', 0), ('unfold_grad only', ALL & ~1), ('forward fold only', ALL & ~2),
              ('statistic + W digits only', ALL & ~4), ('transposed fold + gradient epilogue only', ALL & ~8),
-             ('both folds only', ALL & ~(2 | 8)), ('unfold + statistic only (FP64-pipe kernels)', ALL & ~(1 | 4))]
+             ('unfold_grad only, dU/dtheta stores dropped', (ALL & ~1) | 32), ('both folds only', ALL & ~(2 | 8)), ('unfold + statistic only (FP64-pipe kernels)', ALL & ~(1 | 4))]
     for label, skip in cases:
         lk.set_debug(skip)
         with Sampler() as s:
