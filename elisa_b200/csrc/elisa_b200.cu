@@ -241,6 +241,85 @@ __global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_kernel(const __grid_
     if (last_seg) unfold_zero(a, row_off, E, a.e_pad, lane, GRAD);
 }
 
+// Interpreter version of unfold_contract_generic (unfold_skel.cuh): gradient by contraction of
+// G = d loglike / d u with the tangents, which never reach memory.  One warp per row.
+template <int PU>
+__global__ void __launch_bounds__(UNFOLD_WARPS * 32) unfold_contract_kernel(const __grid_constant__ UnfoldArgs args) {
+    using TT = Dual<PU>;
+    __shared__ double s_scratch[UNFOLD_WARPS][ELISA_MAX_COMPONENTS][LEAF_SCRATCH];
+    const UnfoldCore& a = args.core;
+    const ModelDev& model = args.model;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int row = (int)((int64_t)blockIdx.x * UNFOLD_WARPS + wib);
+    if (row >= a.n_valid) return;
+    const int E = a.gv.E;
+    double(*scr)[LEAF_SCRATCH] = s_scratch[wib];
+    const double* th = a.theta + (size_t)row * a.P;
+    for (int i = 0; i < model.n_leaf; ++i) {
+        const LeafDev& L = model.leaf[i];
+        if (lane < ELISA_MAX_COMP_PARAMS)
+            scr[i][lane] = lane < L.np ? (L.src[lane] >= 0 ? th[L.src[lane]] : L.cst[lane]) : 0.0;
+    }
+    __syncwarp();
+    for (int i = 0; i < model.n_leaf; ++i) {
+        const LeafDev& L = model.leaf[i];
+        double tmp[LEAF_SCRATCH];
+#pragma unroll
+        for (int k = 0; k < ELISA_MAX_COMP_PARAMS; ++k) tmp[k] = scr[i][k];
+        switch (L.kind) {
+#define X(KIND)                                                   \
+    case KIND:                                                    \
+        leaf_pre<KIND, Dual<Comp<KIND>::NP>>(tmp, L.aux);         \
+        break;
+            ELISA_FOR_EACH_KIND(X)
+#undef X
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = ELISA_MAX_COMP_PARAMS; k < LEAF_SCRATCH; ++k) scr[i][k] = tmp[k];
+        }
+    }
+    __syncwarp();
+    TT nrm[ELISA_MAX_NORMS];
+    for (int k = 0; k < model.n_norms; ++k) {
+        const NormDev& nd = model.norm[k];
+        const GridView& gv = a.ngv[k];
+        TT acc = Cst<TT>::make(0.0);
+        for (int e0 = 0; e0 < gv.E; e0 += 31) {
+            const int e = e0 + lane;
+            const TT v = interp_range<PU>(model, scr, nd.op_lo, nd.op_hi, gv, e, true, nrm);
+            if (lane < 31 && e < gv.E) acc = acc + (a.nw[k] != nullptr ? a.nw[k][e] : 1.0) * v;
+        }
+        acc = warp_sum(acc);
+        TT F = Cst<TT>::make(nd.f_src >= 0 ? th[nd.f_src] : nd.f_cst);
+        if (nd.f_src >= 0) F.d[nd.f_src] = 1.0;
+        nrm[k] = F / acc;
+    }
+    const double* g_row = a.G + (size_t)row * a.ldg;
+    double acc[PU];
+#pragma unroll
+    for (int j = 0; j < PU; ++j) acc[j] = 0.0;
+    for (int e0 = 0; e0 < E; e0 += 31) {
+        const int e = e0 + lane;
+        const TT res = interp_range<PU>(model, scr, 0, model.n_ops, a.gv, e, false, nrm);
+        if (lane < 31 && e < E) {
+            const double g = g_row[e];
+            const bool pass = !(a.clip && !(res.v >= 1e-300 && res.v <= 1e300));
+#pragma unroll
+            for (int j = 0; j < PU; ++j) acc[j] = fma(g, pass ? res.d[j] : 0.0, acc[j]);
+        }
+    }
+    double* out = a.grad_out + (size_t)row * a.grad_stride;
+#pragma unroll
+    for (int j = 0; j < PU; ++j) {
+        if (j < a.P) {
+            const double t = ((a.used_mask >> j) & 1u) ? warp_sum(acc[j]) : 0.0;
+            if (lane == 0) out[j] = t;
+        }
+    }
+}
+
 // ======================================================================================
 // 2. statistic epilogue of the forward fold
 // ======================================================================================
@@ -734,6 +813,8 @@ struct ElisaPlan {
     std::vector<SpectrumPlan> spec;
     // workspace
     double *U = nullptr, *dU = nullptr, *W = nullptr, *part = nullptr, *gpart = nullptr;
+    double* G = nullptr;  // [chunk, max_E_pad] d loglike / d u of the transposed fold (gradient by contraction)
+    bool grad_contract = true;  // integer fold: gradient by contraction instead of tangent planes (ELISA_B200_GRAD=planes: off)
     // sliced-integer fold: digit images of the per-chunk A operand (U, then W) and its row scales
     int ks = 0;      // slices per operand of the forward fold (0: every spectrum folds with DMMA)
     int ks_bwd = 0;  // slices per operand of the transposed fold
@@ -779,7 +860,7 @@ struct ElisaPlan {
     // during capture, own small workspace), so the S kernel chains of a small batch overlap
     // instead of queueing behind one another.
     struct SmallWs {
-        double *U = nullptr, *dU = nullptr, *W = nullptr, *part = nullptr, *gpart = nullptr, *a_scale = nullptr;
+        double *U = nullptr, *dU = nullptr, *W = nullptr, *part = nullptr, *gpart = nullptr, *a_scale = nullptr, *G = nullptr;
         int8_t* A_img = nullptr;
     };
     std::vector<SmallWs> small_ws;
@@ -805,8 +886,8 @@ struct ElisaPlan {
     size_t ev_used = 0;
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double prof_ms[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
-    int64_t prof_n[ELISA_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
+    double prof_ms[ELISA_PROFILE_CLASSES] = {};
+    int64_t prof_n[ELISA_PROFILE_CLASSES] = {};
 };
 
 namespace elisa {
@@ -1216,7 +1297,7 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
 // ======================================================================================
 struct JitKernels {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t val = nullptr, grad = nullptr;
+    cudaKernel_t val = nullptr, grad = nullptr, contract = nullptr;
 };
 
 static const char* const k_src_elisa_h =
@@ -1499,6 +1580,8 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
          k + ">(a); }\n";
     s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_grad(const UnfoldCore a) { unfold_generic<ModelG, Dual<" +
          std::to_string(P) + ">, " + k + ">(a); }\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
+         "unfold_contract_generic<ModelG, Dual<" + std::to_string(P) + ">>(a); }\n";
     return s;
 }
 
@@ -1556,6 +1639,7 @@ static const JitKernels* jit_unfold(const ModelDev& m, int P, int ks, std::strin
     cudaError_t e = cudaLibraryLoadData(&k->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->val, k->lib, "unfold_val");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->grad, k->lib, "unfold_grad");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->contract, k->lib, "unfold_contract");
     if (e != cudaSuccess) {
         *why = std::string("loading the compiled unfold kernels failed: ") + cudaGetErrorString(e);
         delete k;
@@ -1634,6 +1718,10 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
     a.kb_total = round_up(ld, I8_BK) / I8_BK;
     a.img = nullptr;
     a.scale = nullptr;
+    a.G = nullptr;
+    a.ldg = 0;
+    a.grad_out = nullptr;
+    a.grad_stride = 0;
     a.kexp = sp.balanced_fwd ? sp.t_exp : nullptr;
     a.gv.has_point = 0;
     for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
@@ -1670,6 +1758,54 @@ static int launch_unfold(ElisaPlan* plan, const SpectrumPlan& sp, const double* 
         unfold_kernel<16><<<blocks, threads, 0, st>>>(args);
     else
         unfold_kernel<32><<<blocks, threads, 0, st>>>(args);
+    ++plan->launches;
+    CUDA_TRY(cudaGetLastError());
+    return ELISA_OK;
+}
+
+// Gradient by contraction (unfold_contract_generic): grad[row, s, :] = sum_e G[row, e] du_e/dtheta.
+static int launch_contract(ElisaPlan* plan, const SpectrumPlan& sp, int s, const double* theta, int n_valid,
+                           const double* G, int ldg, double* grad, cudaStream_t st) {
+    UnfoldArgs args;
+    UnfoldCore& a = args.core;
+    memset(&a, 0, sizeof a);
+    a.gv = sp.grid_view();
+    a.theta = theta;
+    a.P = plan->P;
+    a.n_valid = n_valid;
+    a.n_rows = n_valid;
+    a.n_seg = 1;
+    a.seg_len = (sp.E + 30) / 31 * 31;
+    a.clip = 1;
+    a.used_mask = sp.model.used_mask;
+    a.gv.has_point = 0;
+    for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
+        a.ngv[k] = sp.norm_view(k);
+        a.ngv[k].has_point = 0;
+        a.nw[k] = sp.norm_grid[k].w;
+    }
+    a.G = G;
+    a.ldg = ldg;
+    a.grad_out = grad + (size_t)s * plan->P;
+    a.grad_stride = (int64_t)plan->S * plan->P;
+    const int blocks = (n_valid + UNFOLD_WARPS - 1) / UNFOLD_WARPS;
+    const int threads = UNFOLD_WARPS * 32;
+    ScopedSpan span(plan, ELISA_PROFILE_CONTRACT, st);
+    if (sp.jit != nullptr) {
+        void* kargs[] = {(void*)&a};
+        CUDA_TRY(cudaLaunchKernel((const void*)sp.jit->contract, dim3(blocks), dim3(threads), kargs, 0, st));
+        ++plan->launches;
+        return ELISA_OK;
+    }
+    args.model = sp.model;
+    if (plan->P <= 4)
+        unfold_contract_kernel<4><<<blocks, threads, 0, st>>>(args);
+    else if (plan->P <= 8)
+        unfold_contract_kernel<8><<<blocks, threads, 0, st>>>(args);
+    else if (plan->P <= 16)
+        unfold_contract_kernel<16><<<blocks, threads, 0, st>>>(args);
+    else
+        unfold_contract_kernel<32><<<blocks, threads, 0, st>>>(args);
     ++plan->launches;
     CUDA_TRY(cudaGetLastError());
     return ELISA_OK;
@@ -1994,7 +2130,7 @@ static int reslice_operand(ElisaPlan* plan, const I8Operand& op, const double* k
 // forward fold (plain store) -> statistic + digits of W -> transposed fold with the gradient epilogue
 static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, int m_tiles, bool want_grad,
                         bool have_digits, const double* on, const double* off, double* loglike, cudaStream_t st,
-                        bool stop_after_stat = false) {
+                        bool stop_after_stat = false, const double* theta = nullptr, double* grad = nullptr) {
     int rc;
     const int skip = plan->debug_skip;
     if (!have_digits && !(skip & 1) &&  // the unfold kernel did not slice U itself (interpreter kernel / split rows)
@@ -2041,6 +2177,14 @@ static int run_chunk_i8(ElisaPlan* plan, const SpectrumPlan& sp, int s, int n, i
     }
     if (!want_grad || stop_after_stat || (skip & 8)) return ELISA_OK;
     const FoldI8Args fa = fold_i8_args(plan, sp.i8_bwd, round_up(sp.C_pad, I8_BK) / I8_BK, m_tiles);
+    if (plan->grad_contract && theta != nullptr && grad != nullptr) {
+        // gradient by contraction: the transposed fold stores G = W . R^T like the forward fold stores
+        // R u, and the component kernel contracts it with the tangents it recomputes in registers
+        I8EpilogueStore es{plan->G, sp.E_pad, m_tiles * I8_BM, sp.E_pad, plan->a_scale};
+        if ((rc = launch_fold_i8(plan, plan->ks_bwd, ELISA_PROFILE_TFOLD, fa, es, plan->sm_count, st))) return rc;
+        if (skip & 64) return ELISA_OK;
+        return launch_contract(plan, sp, s, theta, n, plan->G, sp.E_pad, grad, st);
+    }
     const int n_part = I8_CG * ((sp.i8_bwd.n_tiles + I8_GROUP - 1) / I8_GROUP);
     // the gradient epilogue keeps <= 16 row partials in registers: more free parameters take
     // further launches of the transposed fold (the digit products are repeated; models with
@@ -2091,17 +2235,22 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     const int n_rows = round_up(n, GEMM_BM);
     const int m_tiles = n_rows / GEMM_BM;
     const bool want_grad = grad != nullptr;
+    const bool i8 = (sp.use_i8() && !plan->force_dmma);
+    // integer fold, gradient by contraction: the forward pass needs the values only (no tangent
+    // planes are written); the tangents are recomputed against G after the transposed fold
+    const bool contract = i8 && want_grad && plan->grad_contract && plan->G != nullptr;
     int rc;
     bool fused_digits = false;
     if (plan->debug_skip & 1) {
         fused_digits = true;  // timing experiment: the workspace keeps what the last full pass left
-    } else if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad, plan->U, plan->dU, sp.E_pad, sp.E_pad, true,
-                                   st, (sp.use_i8() && !plan->force_dmma) ? &fused_digits : nullptr)))
+    } else if ((rc = launch_unfold(plan, sp, theta, n, n_rows, want_grad && !contract, plan->U, plan->dU, sp.E_pad,
+                                   sp.E_pad, true, st, i8 ? &fused_digits : nullptr)))
         return rc;
-    const bool i8 = (sp.use_i8() && !plan->force_dmma);
     if (i8) {
-        if ((rc = run_chunk_i8(plan, sp, s, n, m_tiles, want_grad, fused_digits, on, off, loglike, st))) return rc;
-        if (!want_grad) return ELISA_OK;  // the statistic kernel wrote loglike itself
+        if ((rc = run_chunk_i8(plan, sp, s, n, m_tiles, want_grad, fused_digits, on, off, loglike, st, false,
+                               contract ? theta : nullptr, contract ? grad : nullptr)))
+            return rc;
+        if (!want_grad || contract) return ELISA_OK;  // the statistic kernel wrote loglike itself, the contraction grad
     } else if (want_grad) {
         if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
         EpilogueGrad eg;
@@ -2457,22 +2606,22 @@ static int run_small(ElisaPlan* plan, const double* theta, const double* on, con
             if (ok && !plan->small_ws.empty() && plan->small_fork != nullptr) {
                 // one branch per spectrum: fork from the capture stream, run the spectrum's chain in
                 // its own workspace on its own stream, join
-                struct Saved { double *U, *dU, *W, *part, *gpart, *a_scale; int8_t* A_img; int ld; } keep = {
-                    plan->U, plan->dU, plan->W, plan->part, plan->gpart, plan->a_scale, plan->A_img, plan->ld_part};
+                struct Saved { double *U, *dU, *W, *part, *gpart, *a_scale, *G; int8_t* A_img; int ld; } keep = {
+                    plan->U, plan->dU, plan->W, plan->part, plan->gpart, plan->a_scale, plan->G, plan->A_img, plan->ld_part};
                 ok = cudaEventRecord(plan->small_fork, cs) == cudaSuccess;
                 for (int sidx = 0; sidx < plan->S && ok && rc == ELISA_OK; ++sidx) {
                     const ElisaPlan::SmallWs& w = plan->small_ws[sidx];
                     cudaStream_t bs = plan->small_stream[sidx];
                     ok = cudaStreamWaitEvent(bs, plan->small_fork, 0) == cudaSuccess;
                     plan->U = w.U; plan->dU = w.dU; plan->W = w.W; plan->part = w.part; plan->gpart = w.gpart;
-                    plan->a_scale = w.a_scale; plan->A_img = w.A_img;
+                    plan->a_scale = w.a_scale; plan->A_img = w.A_img; plan->G = w.G;
                     plan->ld_part = (int)std::min<int64_t>(GRAPH_MAX_N, plan->chunk);
                     if (ok) rc = run_chunk(plan, sidx, plan->g_theta, nullptr, nullptr, (int)n, plan->g_ll, grad ? plan->g_grad : nullptr, bs);
                     if (ok) ok = cudaEventRecord(plan->small_done[sidx], bs) == cudaSuccess &&
                                  cudaStreamWaitEvent(cs, plan->small_done[sidx], 0) == cudaSuccess;
                 }
                 plan->U = keep.U; plan->dU = keep.dU; plan->W = keep.W; plan->part = keep.part; plan->gpart = keep.gpart;
-                plan->a_scale = keep.a_scale; plan->A_img = keep.A_img; plan->ld_part = keep.ld;
+                plan->a_scale = keep.a_scale; plan->A_img = keep.A_img; plan->G = keep.G; plan->ld_part = keep.ld;
             } else if (ok) rc = run_all(plan, plan->g_theta, nullptr, nullptr, n, plan->g_ll, grad ? plan->g_grad : nullptr, cs);
             e->kernels = plan->launches - before;
             plan->launches = before;  // counted per replay below
@@ -2895,6 +3044,11 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         if (rc == ELISA_OK) rc = alloc(&plan->U, chunk * plan->max_E_pad);
         if (rc == ELISA_OK) rc = alloc(&plan->dU, chunk * plan->max_E_pad * plan->P);
         if (rc == ELISA_OK) rc = alloc(&plan->W, chunk * plan->max_C_pad);
+        if (rc == ELISA_OK && any_i8) {
+            const char* env = getenv("ELISA_B200_GRAD");
+            plan->grad_contract = !(env && strcmp(env, "planes") == 0);
+            rc = alloc(&plan->G, chunk * plan->max_E_pad);
+        }
         if (rc == ELISA_OK) rc = alloc(&plan->part, chunk * tiles_c);
         if (rc == ELISA_OK) rc = alloc(&plan->gpart, chunk * tiles_e * plan->P);
         if (rc == ELISA_OK && any_i8) {
@@ -2970,6 +3124,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                     rc = alloc_small(&w.U, rows * sp.E_pad);
                     if (rc == ELISA_OK) rc = alloc_small(&w.dU, rows * sp.E_pad * plan->P);
                     if (rc == ELISA_OK) rc = alloc_small(&w.W, rows * sp.C_pad);
+                    if (rc == ELISA_OK && sp.use_i8()) rc = alloc_small(&w.G, rows * sp.E_pad);
                     if (rc == ELISA_OK) rc = alloc_small(&w.part, rows * pc);
                     if (rc == ELISA_OK) rc = alloc_small(&w.gpart, rows * pe * plan->P);
                     if (rc == ELISA_OK && sp.use_i8()) {

@@ -45,6 +45,14 @@ struct UnfoldCore {
     // EnFlux, the bin weights keV_to_erg * sqrt(e_j e_j+1) (nullptr: 1)
     GridView ngv[ELISA_MAX_NORMS];
     const double* nw[ELISA_MAX_NORMS];
+    // contraction mode (unfold_contract): instead of storing U and dU/dtheta the kernel reads
+    // G[row, e] = d loglike / d u_e (the transposed fold's plain output) and accumulates
+    // grad[row, j] = sum_e G[row, e] * du_e/dtheta_j in registers -- the tangents never exist in
+    // memory.  grad_out points at element (row 0, spectrum s, parameter 0); rows are grad_stride apart.
+    const double* G;
+    int64_t ldg;
+    double* grad_out;
+    int64_t grad_stride;
 };
 
 constexpr int UNFOLD_WARPS = 4;
@@ -182,6 +190,77 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
             __syncwarp();
             slice_row_digits<KS>(a.U + row_off, true, (a.ld & 1) == 0, E, f1, f2, row % I8_BM, I8_BM, 0, a.kb_total,
                                  a.img, (int64_t)(row / I8_BM) * a.kb_total, lane);
+        }
+    }
+}
+
+// Gradient by contraction: grad[row, j] = sum_e G[row, e] * d u_e / d theta_j with the tangents
+// recomputed on the fly (forward duals, as in unfold_generic) and consumed in registers.
+// Replaces the round trip of the P tangent planes through HBM (written by the unfold kernel,
+// read once by the transposed fold's epilogue: 1.5 GB per chunk of the bench, which made the
+// unfold kernel WRITE-bound -- 0.61 ms with the stores, 0.41 ms without, tools/power_probe.py).
+// One warp per row (the host keeps n_seg == 1); lane-serial partial sums, then an xor tree: the
+// summation order is fixed and independent of the batch.
+template <class Model, typename T>
+__device__ __forceinline__ void unfold_contract_generic(const UnfoldCore& a) {
+    constexpr int NP = Scalar<T>::NP;
+    static_assert(NP > 0, "the contraction needs the dual type");
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t wid = (int64_t)blockIdx.x * UNFOLD_WARPS + wib;
+    const int row = (int)wid;
+    if (row >= a.n_valid) return;
+    const int E = a.gv.E;
+    typename Model::Pre pre;
+    Model::pre(a.theta + (size_t)row * a.P, pre);
+    Model::norms(pre, a, a.theta + (size_t)row * a.P, lane);
+    GridView gv = a.gv;
+    gv.has_point = 1;
+    auto load_point = [&](int e, double& pE, double& pl, double& pEm, double& plm) {
+        const int ec = e <= E ? e : E, em = e < E ? e : E - 1;
+        pE = a.gv.egrid[ec];
+        pl = a.gv.lngrid[ec];
+        pEm = a.gv.emid[em];
+        plm = a.gv.lnmid[em];
+    };
+    const double* g_row = a.G + (size_t)row * a.ldg;
+    double nE, nl, nEm, nlm;
+    load_point(lane, nE, nl, nEm, nlm);
+    double ng = (lane < 31 && lane < E) ? g_row[lane] : 0.0;
+    double acc[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) acc[j] = 0.0;
+    for (int e0 = 0; e0 < E; e0 += 31) {
+        const int e = e0 + lane;
+        gv.pE = nE;
+        gv.pl = nl;
+        gv.pEm = nEm;
+        gv.plm = nlm;
+        double g = ng;
+        if (e0 + 31 < E) {
+            load_point(e + 31, nE, nl, nEm, nlm);
+            ng = (lane < 31 && e + 31 < E) ? g_row[e + 31] : 0.0;
+        }
+        const T res = Model::bin(pre, gv, e);
+        // lane 31 and lanes past the grid hold no bin (their duals may be anything); clip(unfold,
+        // 1e-300, 1e300) (likelihood.py:204) passes no derivative where it clips
+        // (as a ZERO tangent, so that a NaN in G -- a NaN parameter vector -- still reaches the sum)
+        if (lane < 31 && e < E) {
+            const bool pass = !(a.clip && !(res.v >= 1e-300 && res.v <= 1e300));
+#pragma unroll
+            for (int j = 0; j < NP; ++j) acc[j] = fma(g, pass ? res.d[j] : 0.0, acc[j]);
+        }
+    }
+#ifdef UNFOLD_USED_MASK
+    constexpr uint32_t used = UNFOLD_USED_MASK;
+#else
+    const uint32_t used = a.used_mask;
+#endif
+    double* out = a.grad_out + (size_t)row * a.grad_stride;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        if (j < a.P) {
+            const double t = ((used >> j) & 1u) ? warp_sum(acc[j]) : 0.0;
+            if (lane == 0) out[j] = t;
         }
     }
 }

@@ -276,7 +276,7 @@ class Likelihood:
     def launch_count(self) -> int:
         return int(self._lib.elisa_b200_plan_launch_count(self._h))
 
-    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice', 'stat')
+    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice', 'stat', 'contract')
 
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.elisa_b200_plan_set_profiling(self._h, int(bool(enable))))

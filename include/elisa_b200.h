@@ -311,7 +311,8 @@ int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const d
 #define ELISA_PROFILE_REDUCE 3 /* partial reductions / per-channel sites            */
 #define ELISA_PROFILE_SLICE 4  /* digit slicing of U and W (sliced-integer fold only)    */
 #define ELISA_PROFILE_STAT 5   /* statistic + digits of W (sliced-integer fold only)       */
-#define ELISA_PROFILE_CLASSES 6
+#define ELISA_PROFILE_CONTRACT 6 /* gradient by contraction: tangents recomputed against G (sliced-integer fold only) */
+#define ELISA_PROFILE_CLASSES 7
 int elisa_b200_plan_set_profiling(ElisaPlan* plan, int enable);
 int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches);
 

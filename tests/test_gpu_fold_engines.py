@@ -341,3 +341,30 @@ def test_pilot_rows_are_spread_over_the_batch(lib):
         assert rel_err_value(ll.cpu().numpy(), ll_ref) <= RTOL and rel_err_grad(g.cpu().numpy(), g_ref) <= RTOL
         assert lk.rebalances <= 1 and lk.guard_fallbacks <= 1, (lk.rebalances, lk.guard_fallbacks)
         lk.close()
+
+
+@pytest.mark.parametrize('k', [1, 2, 3, 5])
+def test_gradient_by_contraction_matches_tangent_planes(lib, k, monkeypatch):
+    """Integer fold: the default gradient (transposed fold stores G, the component kernel contracts it
+    with tangents it recomputes in registers) against the tangent-plane path (ELISA_B200_GRAD=planes:
+    dU/dtheta written by the unfold kernel, contracted in the transposed fold's epilogue) -- with the
+    specialised kernels and with the interpreter."""
+    from elisa_b200 import Likelihood
+    from parity import RTOL, oracle_eval, rel_err_grad, rel_err_value
+
+    cfg = small_config(k)
+    ll_ref, g_ref = oracle_eval(cfg)
+    out = {}
+    for mode in ('planes', 'contract'):
+        monkeypatch.setenv('ELISA_B200_GRAD', mode)
+        for spec in (True, False):
+            lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], fold='i8', specialise=spec)
+            ll, g = lk.loglike_and_grad(cfg['theta'])
+            lk.close()
+            out[mode, spec] = (ll.cpu().numpy(), g.cpu().numpy())
+            assert rel_err_value(out[mode, spec][0], ll_ref) <= RTOL and rel_err_grad(out[mode, spec][1], g_ref) <= RTOL
+    for spec in (True, False):
+        # (values: the planes path takes them from the dual-number kernel, the contraction path from the
+        # value kernel -- the same numbers up to FMA contraction)
+        assert rel_err_value(out['contract', spec][0], out['planes', spec][0]) <= 1e-12
+        assert rel_err_grad(out['contract', spec][1], out['planes', spec][1]) <= 1e-12
