@@ -656,11 +656,16 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        if int8_peak:
+        # denominator: the larger of the cuBLASLt int8 GEMM rate measured in this run and 2 x the measured bf16
+        # burst of MEASURED_PEAKS.json (int8 runs at twice the bf16 rate on the same pipe; this kernel's forward
+        # fold exceeds what cuBLASLt's int8 GEMM reaches, so that figure alone would put frac above 1)
+        bf16x2 = 2.0 * peaks.get('bf16_tflops', 1590.0)
+        bf16_how = '2 x measured bf16 burst of MEASURED_PEAKS.json' if peaks else '2 x 1590 fallback bf16'
+        if int8_peak and int8_peak >= bf16x2:
             peak, how = int8_peak, int8_how
         else:
-            peak = 2.0 * peaks.get('bf16_tflops', 1590.0)
-            how = ('2 x measured bf16 burst of MEASURED_PEAKS.json' if peaks else '2 x 1590 fallback bf16') + f' ({int8_how})'
+            peak = bf16x2
+            how = bf16_how + (' (cuBLASLt int8 GEMM 8192^3 measured in this run: %.0f TOP/s, lower)' % int8_peak if int8_peak else f' ({int8_how})')
         roofline = {
             'bound': 'tensor',
             'kernel': 'fold_i8_kernel (forward + transposed fold; int8 tcgen05.mma, %d / %d digits per operand = %d + %d exact '
@@ -672,6 +677,7 @@ def run_b200(args):
                                  '(2 E C x products per eval and fold) / device time of the fold kernels',
             'per_kernel': {'forward': {'ms_per_step': fold_ms / args.steps, 'tops': ops_f / (fold_ms * 1e-3) / 1e12 if fold_ms else None},
                            'transposed': {'ms_per_step': tfold_ms / args.steps, 'tops': ops_b / (tfold_ms * 1e-3) / 1e12 if tfold_ms else None}},
+            'int8_cublaslt_tops': int8_peak, 'int8_2x_bf16_burst_tops': bf16x2,
             'fp64_equiv_tflops': fp64_equiv, 'fp64_dgemm_tflops': fp64_peak,
             'fp64_equiv_speedup': fp64_equiv / fp64_peak if fp64_equiv and fp64_peak else None,
             'fp64_note': 'fp64_equiv = ALGORITHMIC FP64 flops (4 E C per eval) / fold time; speedup over the cuBLAS DGEMM '

@@ -674,6 +674,45 @@ __global__ void __launch_bounds__(256) normal_eq_kernel(const NormalEqArgs a) {
 }
 
 // ======================================================================================
+// row-wise sparse fold: X[n, c] = sum_k val[c, k] * U[n, idx[c, k]]   (CSR by channel row)
+// ======================================================================================
+// The north star's "warp-per-channel-row" kernel for band-sparse responses, in the mapping that
+// keeps its loads coalesced with U stored [n, E]: a block owns 128 consecutive channel rows and
+// CSR_RT replicas, one THREAD per channel row (a warp = 32 neighbouring rows, whose column indices
+// are neighbours too in a banded response, so the 32 loads of U[n, idx] fall into 2-3 sectors), every
+// value / index loaded once and used for CSR_RT replicas.  4 nnz useful flop per replica, FP64 FMA
+// pipe.  Raced against the block-banded DMMA fold in tools/csr_race.py (profiles/r02_cfg4.md).
+constexpr int CSR_RT = 8;
+__global__ void __launch_bounds__(128) csr_fold_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                       const double* __restrict__ val, const double* __restrict__ U,
+                                                       int64_t ldu, int n, int C, double* __restrict__ X, int64_t ldx) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n0 = blockIdx.y * CSR_RT;
+    if (c >= C) return;
+    const int k0 = ptr[c], k1 = ptr[c + 1];
+    double acc[CSR_RT];
+#pragma unroll
+    for (int r = 0; r < CSR_RT; ++r) acc[r] = 0.0;
+    const double* u = U + (size_t)n0 * ldu;
+    const int rows = min(CSR_RT, n - n0);
+    if (rows == CSR_RT) {
+        for (int k = k0; k < k1; ++k) {
+            const double v = val[k];
+            const double* ue = u + idx[k];
+#pragma unroll
+            for (int r = 0; r < CSR_RT; ++r) acc[r] = fma(v, ue[(size_t)r * ldu], acc[r]);
+        }
+    } else {
+        for (int k = k0; k < k1; ++k) {
+            const double v = val[k];
+            const double* ue = u + idx[k];
+            for (int r = 0; r < rows; ++r) acc[r] = fma(v, ue[(size_t)r * ldu], acc[r]);
+        }
+    }
+    for (int r = 0; r < rows; ++r) X[(size_t)(n0 + r) * ldx + c] = acc[r];
+}
+
+// ======================================================================================
 // host side: plan
 // ======================================================================================
 static thread_local std::string g_last_error = "";
@@ -775,6 +814,10 @@ struct SpectrumPlan {
     bool use_i8() const { return i8_fwd.img != nullptr; }
     int64_t counts_off = 0;  // column offset of this spectrum in the per-replica counts arrays
     int64_t nnz = 0;
+    // CSR by channel row of R^T (what BCSR.from_scipy_sparse(sparse.T) holds, likelihood.py:177-181),
+    // kept for the row-wise sparse fold (csr_fold_kernel); built from the non-zeros of a dense response too
+    int32_t *csr_ptr = nullptr, *csr_idx = nullptr;
+    double* csr_val = nullptr;
     double fill = 1.0;  // stored fraction of the packed response operands
     // balancing of the integer folds' contraction indices (col_envelope_kernel): power-of-two
     // envelopes of U over the energies / of W over the channels, and their reciprocals
@@ -1283,6 +1326,34 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
     }
     if ((rc = upload_packed(plan, fwd, &sp->fwd))) return rc;
     if ((rc = upload_packed(plan, bwd, &sp->bwd))) return rc;
+    {  // CSR by channel row for the row-wise sparse fold
+        std::vector<int32_t> ptr(C + 1, 0), idx;
+        std::vector<double> val;
+        if (dense) {
+            const double* R = sd.response_dense;
+            if (sp->nnz <= (int64_t)E * C / 4) {  // worth keeping only when the response is actually sparse
+                idx.reserve((size_t)sp->nnz);
+                val.reserve((size_t)sp->nnz);
+                for (int c = 0; c < C; ++c) {
+                    for (int e = 0; e < E; ++e)
+                        if (R[(size_t)e * C + c] != 0.0) {
+                            idx.push_back(e);
+                            val.push_back(R[(size_t)e * C + c]);
+                        }
+                    ptr[c + 1] = (int32_t)idx.size();
+                }
+            }
+        } else {
+            ptr.assign(sd.csr_indptr, sd.csr_indptr + C + 1);
+            idx.assign(sd.csr_indices, sd.csr_indices + sp->nnz);
+            val.assign(sd.csr_values, sd.csr_values + sp->nnz);
+        }
+        if (!idx.empty()) {
+            if ((rc = upload(plan, ptr, &sp->csr_ptr))) return rc;
+            if ((rc = upload(plan, idx, &sp->csr_idx))) return rc;
+            if ((rc = upload(plan, val, &sp->csr_val))) return rc;
+        }
+    }
     {  // fraction of the two operands that is stored (1 for a dense response)
         double stored = 0.0;
         for (size_t j = 0; j < fwd.k_lo.size(); ++j) stored += std::max(0, fwd.k_hi[j] - fwd.k_lo[j]);
@@ -2236,9 +2307,9 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     const int m_tiles = n_rows / GEMM_BM;
     const bool want_grad = grad != nullptr;
     const bool i8 = (sp.use_i8() && !plan->force_dmma);
-    // integer fold, gradient by contraction: the forward pass needs the values only (no tangent
+    // gradient by contraction (both fold engines): the forward pass needs the values only (no tangent
     // planes are written); the tangents are recomputed against G after the transposed fold
-    const bool contract = i8 && want_grad && plan->grad_contract && plan->G != nullptr;
+    const bool contract = want_grad && plan->grad_contract && plan->G != nullptr;
     int rc;
     bool fused_digits = false;
     if (plan->debug_skip & 1) {
@@ -2251,6 +2322,10 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
                                contract ? theta : nullptr, contract ? grad : nullptr)))
             return rc;
         if (!want_grad || contract) return ELISA_OK;  // the statistic kernel wrote loglike itself, the contraction grad
+    } else if (contract) {
+        if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
+        EpilogueStore es{plan->G, sp.E_pad};  // G = W . R^T, plain store
+        if ((rc = launch_gemm(plan, ELISA_PROFILE_TFOLD, plan->W, sp.C_pad, sp.bwd, m_tiles, es, st))) return rc;
     } else if (want_grad) {
         if ((rc = launch_stat_gemm_any<true>(plan, sp, n, m_tiles, on, off, st))) return rc;
         EpilogueGrad eg;
@@ -2278,12 +2353,14 @@ static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* 
     ra.s = s;
     ra.used_mask = sp.model.used_mask;
     ra.loglike = loglike;
-    ra.grad = grad;
-    if (plan->debug_skip & 16) return ELISA_OK;
-    ScopedSpan span(plan, ELISA_PROFILE_REDUCE, st);
-    reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ra);
-    ++plan->launches;
-    CUDA_TRY(cudaGetLastError());
+    ra.grad = contract ? nullptr : grad;  // DMMA fold with the gradient by contraction: only the log-likelihood partials
+    if (!(plan->debug_skip & 16)) {
+        ScopedSpan span(plan, ELISA_PROFILE_REDUCE, st);
+        reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ra);
+        ++plan->launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (contract && !(plan->debug_skip & 64)) return launch_contract(plan, sp, s, theta, n, plan->G, sp.E_pad, grad, st);
     return ELISA_OK;
 }
 
@@ -3044,10 +3121,10 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         if (rc == ELISA_OK) rc = alloc(&plan->U, chunk * plan->max_E_pad);
         if (rc == ELISA_OK) rc = alloc(&plan->dU, chunk * plan->max_E_pad * plan->P);
         if (rc == ELISA_OK) rc = alloc(&plan->W, chunk * plan->max_C_pad);
-        if (rc == ELISA_OK && any_i8) {
+        if (rc == ELISA_OK) {
             const char* env = getenv("ELISA_B200_GRAD");
             plan->grad_contract = !(env && strcmp(env, "planes") == 0);
-            rc = alloc(&plan->G, chunk * plan->max_E_pad);
+            if (plan->grad_contract) rc = alloc(&plan->G, chunk * plan->max_E_pad);
         }
         if (rc == ELISA_OK) rc = alloc(&plan->part, chunk * tiles_c);
         if (rc == ELISA_OK) rc = alloc(&plan->gpart, chunk * tiles_e * plan->P);
@@ -3124,7 +3201,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
                     rc = alloc_small(&w.U, rows * sp.E_pad);
                     if (rc == ELISA_OK) rc = alloc_small(&w.dU, rows * sp.E_pad * plan->P);
                     if (rc == ELISA_OK) rc = alloc_small(&w.W, rows * sp.C_pad);
-                    if (rc == ELISA_OK && sp.use_i8()) rc = alloc_small(&w.G, rows * sp.E_pad);
+                    if (rc == ELISA_OK && plan->grad_contract) rc = alloc_small(&w.G, rows * sp.E_pad);
                     if (rc == ELISA_OK) rc = alloc_small(&w.part, rows * pc);
                     if (rc == ELISA_OK) rc = alloc_small(&w.gpart, rows * pe * plan->P);
                     if (rc == ELISA_OK && sp.use_i8()) {
@@ -3476,6 +3553,31 @@ int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* the
         jacobian_kernel<<<grid, 128, 0, st>>>(a);
         ++plan->launches;
         if (cudaGetLastError() != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "jacobian_kernel launch failed");
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int elisa_b200_csr_fold_dev(ElisaPlan* plan, int32_t spectrum, const double* unfold, int64_t ldu, int64_t n, double* folded,
+                            int64_t ldx, void* cuda_stream) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "csr_fold: bad spectrum");
+    const SpectrumPlan& sp = plan->spec[spectrum];
+    if (sp.csr_ptr == nullptr) return fail(ELISA_ERR_UNSUPPORTED, "csr_fold: the response of this spectrum is dense (more than 25 % stored)");
+    if (n < 0 || unfold == nullptr || folded == nullptr || ldu < sp.E || ldx < sp.C) return fail(ELISA_ERR_INVALID, "csr_fold: bad argument");
+    if (n == 0) return ELISA_OK;
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = ELISA_OK;
+    for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += 65535 * CSR_RT) {  // grid.y limit
+        const int nc = (int)std::min<int64_t>(65535 * CSR_RT, n - i0);
+        dim3 grid((sp.C + 127) / 128, (nc + CSR_RT - 1) / CSR_RT);
+        ScopedSpan span(plan, ELISA_PROFILE_FOLD, st);
+        csr_fold_kernel<<<grid, 128, 0, st>>>(sp.csr_ptr, sp.csr_idx, sp.csr_val, unfold + i0 * ldu, ldu, nc, sp.C,
+                                              folded + i0 * ldx, ldx);
+        ++plan->launches;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ELISA_ERR_CUDA, "csr_fold_kernel launch failed");
     }
     cudaSetDevice(prev);
     return rc;

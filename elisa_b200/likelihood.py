@@ -619,6 +619,18 @@ class Likelihood:
             _lib.check(self._lib.elisa_b200_unfold_dev(self._h, k, _dev_ptr(t), t.shape[0], _dev_ptr(out), self._stream()))
         return out
 
+    def csr_fold(self, k: int, unfold):
+        """(N, C_k) = unfold (N, E_k) folded through the CSR-by-channel-row response of dataset k with the
+        row-wise sparse kernel (``elisa_b200_csr_fold_dev``): the plain BCSR product ``resp_matrix @
+        unfold`` of infer/likelihood.py:205, without area / exposure factors."""
+        torch = self._torch
+        with self._device_ctx():
+            u = torch.as_tensor(unfold, dtype=torch.float64).to(self._dev_str).contiguous()
+            out = torch.empty((u.shape[0], self.n_channels[k]), dtype=torch.float64, device=u.device)
+            _lib.check(self._lib.elisa_b200_csr_fold_dev(self._h, int(k), _dev_ptr(u), u.shape[1], u.shape[0], _dev_ptr(out),
+                                                         out.shape[1], self._stream()))
+        return out
+
     # -- host API (numpy in, numpy out; copies inside) -------------------------------
     def loglike_and_grad_host(self, theta: np.ndarray, counts_on=None, counts_off=None, grad: bool = True):
         """Same through ``elisa_b200_loglike_grad_host``: host buffers, H2D / D2H inside."""

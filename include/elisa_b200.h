@@ -413,6 +413,16 @@ int elisa_b200_plan_guard_poll(ElisaPlan* plan, int wait, int64_t* flagged, doub
 int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, const double* counts_on,
                             const double* counts_off, int64_t n, double* x, double* ds, double* dl_dx,
                             void* cuda_stream);
+/* The row-wise sparse fold on its own: folded[n, c] = sum_k values[c, k] * unfold[n, indices[c, k]]
+ * over the CSR-by-channel-row response of `spectrum` (a dense response_dense with at most 25 %
+ * non-zeros is converted at plan creation) -- the BCSR product of infer/likelihood.py:177-181,205
+ * without area / exposure factors.  One thread per channel row, FP64 FMA pipe (the north star's
+ * band-sparse kernel).  The evaluation entry points fold band-sparse responses with the
+ * block-banded DMMA kernel instead, which is faster (profiles/r02_cfg4.md); this entry point is the
+ * reference implementation it was raced against and a building block for callers that hold the
+ * unfolded model already.  ELISA_ERR_UNSUPPORTED for a dense response.                      */
+int elisa_b200_csr_fold_dev(ElisaPlan* plan, int32_t spectrum, const double* unfold, int64_t ldu, int64_t n, double* folded,
+                            int64_t ldx, void* cuda_stream);
 /* Timing experiments only: bit mask of kernel classes to SKIP in the evaluation entry points
  * (1 unfold, 2 forward fold, 4 statistic, 8 transposed fold, 16 reduce, 32 the dU/dtheta stores of
  * the specialised unfold kernel); results are garbage

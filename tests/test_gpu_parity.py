@@ -238,3 +238,33 @@ def test_photon_absorption_in_a_fit_model(lib, method, fold, specialise):
         cfg = dict(data=[d], model=[model], stat=['cstat'], theta=_theta_for(model, 33, 5))
         err = compare(cfg, specialise=specialise, fold=fold)
         assert err['value'] <= RTOL and err['grad'] <= RTOL, (model, err)
+
+
+def test_row_wise_csr_fold_matches_the_dense_product(lib):
+    """elisa_b200_csr_fold_dev (the band-sparse row kernel) against a dense FP64 product, for CSR input
+    and for a dense response that is mostly zeros; refused for a genuinely dense one."""
+    import torch
+
+    from elisa_b200 import Likelihood, _lib
+
+    cfg = small_config(4)
+    d = cfg['data'][0]
+    ip, ix, v = d.sparse_matrix
+    R = np.zeros((d.n_energies, d.n_channels))
+    np.add.at(R, (ix, np.repeat(np.arange(d.n_channels), np.diff(ip))), v)
+    lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'])
+    u = lk.unfold(0, cfg['theta'][:37])
+    x = lk.csr_fold(0, u)
+    ref = u @ torch.as_tensor(R, device='cuda')
+    assert float(((x - ref).abs() / ref.abs().clamp_min(1e-300)).max()) < 1e-13
+    lk.close()
+    dense_like = FixedData('d', d.photon_egrid, d.spec_counts, d.area_scale, d.spec_exposure, response_matrix=R,
+                           net_counts=d.net_counts, net_errors=d.net_errors)
+    lk = Likelihood([dense_like], cfg['model'], cfg['stat'])
+    assert torch.equal(lk.csr_fold(0, u), x)
+    lk.close()
+    full = small_config(1)
+    lk = Likelihood(full['data'], full['model'], full['stat'])
+    with pytest.raises(_lib.ElisaB200Error, match='dense'):
+        lk.csr_fold(0, lk.unfold(0, full['theta'][:4]))
+    lk.close()
