@@ -848,6 +848,10 @@ struct SpectrumPlan {
 using namespace elisa;
 
 struct ElisaPlan {
+    // Calls on one plan share its workspace: they are serialised here, so that a plan may be used
+    // from several host threads (numpyro chain_method='parallel'); for calls that actually overlap
+    // on the device create one plan per thread / stream.
+    std::mutex mu;
     int device = 0;
     int P = 0, S = 0;
     int64_t chunk = 0;
@@ -3235,6 +3239,7 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
 
 int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const double* channel_width) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S || channel_width == nullptr)
+    std::lock_guard<std::mutex> lock(plan->mu);
         return fail(ELISA_ERR_INVALID, "set_channel_width: bad argument");
     SpectrumPlan& sp = plan->spec[spectrum];
     std::vector<double> inv(sp.C_pad, 1.0);
@@ -3249,6 +3254,8 @@ int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const d
 
 int elisa_b200_loglike_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
                            int64_t n, double* loglike, void* cuda_stream) {
+    std::unique_lock<std::mutex> lock;
+    if (plan != nullptr) lock = std::unique_lock<std::mutex>(plan->mu);
     return run_small(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
 }
 
@@ -3256,12 +3263,15 @@ int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const doub
                                 const double* counts_off, int64_t n, double* loglike, double* grad,
                                 void* cuda_stream) {
     if (grad == nullptr) return fail(ELISA_ERR_INVALID, "grad is null");
+    std::unique_lock<std::mutex> lock;
+    if (plan != nullptr) lock = std::unique_lock<std::mutex>(plan->mu);
     return run_small(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
 }
 
 int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, int64_t n, double* unfold,
                           void* cuda_stream) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "unfold: bad spectrum");
+    std::lock_guard<std::mutex> lock(plan->mu);
     if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
     if (n == 0) return ELISA_OK;
     if (theta == nullptr || unfold == nullptr) return fail(ELISA_ERR_INVALID, "unfold: null pointer");
@@ -3284,6 +3294,7 @@ int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta,
                          const double* counts_off, int64_t n, double* rate, double* model_on, double* ll_on,
                          double* model_off, double* ll_off, void* cuda_stream) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "sites: bad spectrum");
+    std::lock_guard<std::mutex> lock(plan->mu);
     if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
     if (n == 0) return ELISA_OK;
     if (theta == nullptr) return fail(ELISA_ERR_INVALID, "sites: theta is null");
@@ -3333,6 +3344,7 @@ int elisa_b200_sites_dev(ElisaPlan* plan, int32_t spectrum, const double* theta,
 int elisa_b200_loglike_grad_host(ElisaPlan* plan, const double* theta, const double* counts_on,
                                  const double* counts_off, int64_t n, double* loglike, double* grad) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    std::lock_guard<std::mutex> lock(plan->mu);
     if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
     if (n == 0) return ELISA_OK;
     if (theta == nullptr || loglike == nullptr) return fail(ELISA_ERR_INVALID, "theta / loglike is null");
@@ -3350,6 +3362,7 @@ int elisa_b200_loglike_grad_guarded_dev(ElisaPlan* plan, const double* theta, co
                                         void* cuda_stream, int64_t* fallback_rows) {
     if (fallback_rows) *fallback_rows = 0;
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    std::lock_guard<std::mutex> lock(plan->mu);
     if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
     if (n == 0) return ELISA_OK;
     if (theta == nullptr || loglike == nullptr) return fail(ELISA_ERR_INVALID, "theta / loglike is null");
@@ -3459,6 +3472,7 @@ int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum) {
 }
 int elisa_b200_plan_fold_products(ElisaPlan* plan, int32_t spectrum, double out[2]) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S || out == nullptr) return fail(ELISA_ERR_INVALID, "fold_products: bad argument");
+    std::lock_guard<std::mutex> lock(plan->mu);
     const SpectrumPlan& sp = plan->spec[spectrum];
     out[0] = out[1] = 0.0;
     if (!sp.use_i8()) return ELISA_OK;
@@ -3493,6 +3507,7 @@ int elisa_b200_plan_fold_slices_bwd(const ElisaPlan* plan, int32_t spectrum) {
 int elisa_b200_normal_eq_dev(ElisaPlan* plan, const double* theta, const double* counts_on, const double* counts_off,
                              int64_t n, double* loglike, double* grad, double* jtj, void* cuda_stream) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    std::lock_guard<std::mutex> lock(plan->mu);
     if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
     if (n == 0) return ELISA_OK;
     if (theta == nullptr || loglike == nullptr || grad == nullptr || jtj == nullptr)
@@ -3519,6 +3534,7 @@ int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* the
                             const double* counts_off, int64_t n, double* x, double* ds, double* dl_dx,
                             void* cuda_stream) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "jacobian: bad spectrum");
+    std::lock_guard<std::mutex> lock(plan->mu);
     if (n < 0) return fail(ELISA_ERR_INVALID, "n < 0");
     if (n == 0) return ELISA_OK;
     if (theta == nullptr) return fail(ELISA_ERR_INVALID, "jacobian: theta is null");
@@ -3561,6 +3577,7 @@ int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* the
 int elisa_b200_csr_fold_dev(ElisaPlan* plan, int32_t spectrum, const double* unfold, int64_t ldu, int64_t n, double* folded,
                             int64_t ldx, void* cuda_stream) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "csr_fold: bad spectrum");
+    std::lock_guard<std::mutex> lock(plan->mu);
     const SpectrumPlan& sp = plan->spec[spectrum];
     if (sp.csr_ptr == nullptr) return fail(ELISA_ERR_UNSUPPORTED, "csr_fold: the response of this spectrum is dense (more than 25 % stored)");
     if (n < 0 || unfold == nullptr || folded == nullptr || ldu < sp.E || ldx < sp.C) return fail(ELISA_ERR_INVALID, "csr_fold: bad argument");
@@ -3606,6 +3623,7 @@ int elisa_b200_plan_guard_stats(const ElisaPlan* plan, int64_t out[3]) {
 
 int elisa_b200_plan_fold_guard(ElisaPlan* plan, int64_t* flagged, double* worst, int reset) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    std::lock_guard<std::mutex> lock(plan->mu);
     unsigned long long h[4] = {0, 0, 0, 0};
     if (plan->guard != nullptr) {
         int prev = 0;

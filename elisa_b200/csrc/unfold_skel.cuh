@@ -222,6 +222,11 @@ __device__ __forceinline__ void unfold_contract_generic(const UnfoldCore& a) {
         pEm = a.gv.emid[em];
         plm = a.gv.lnmid[em];
     };
+#ifdef UNFOLD_USED_MASK
+    constexpr uint32_t used = UNFOLD_USED_MASK;  // compile-time: unused columns cost nothing
+#else
+    const uint32_t used = a.used_mask;
+#endif
     const double* g_row = a.G + (size_t)row * a.ldg;
     double nE, nl, nEm, nlm;
     load_point(lane, nE, nl, nEm, nlm);
@@ -247,14 +252,10 @@ __device__ __forceinline__ void unfold_contract_generic(const UnfoldCore& a) {
         if (lane < 31 && e < E) {
             const bool pass = !(a.clip && !(res.v >= 1e-300 && res.v <= 1e300));
 #pragma unroll
-            for (int j = 0; j < NP; ++j) acc[j] = fma(g, pass ? res.d[j] : 0.0, acc[j]);
+            for (int j = 0; j < NP; ++j)
+                if ((used >> j) & 1u) acc[j] = fma(g, pass ? res.d[j] : 0.0, acc[j]);
         }
     }
-#ifdef UNFOLD_USED_MASK
-    constexpr uint32_t used = UNFOLD_USED_MASK;
-#else
-    const uint32_t used = a.used_mask;
-#endif
     double* out = a.grad_out + (size_t)row * a.grad_stride;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {

@@ -35,8 +35,11 @@
  *  - every function returns 0 on success or a negative ELISA_ERR_* code and never
  *    throws or aborts; NaN/Inf in results are data, not errors
  *    (callers filter them: infer/helper.py:659-664).
- *  - plans are immutable after creation except for their private workspace: one
- *    in-flight call per plan (create one plan per host thread / stream).
+ *  - plans are immutable after creation except for their private workspace.  Entry points may
+ *    be called on one plan from several host threads (numpyro chain_method='parallel'): calls
+ *    that touch the workspace are serialised by a mutex inside the plan, and work enqueued on
+ *    DIFFERENT streams by successive calls is the caller's to order (the workspace is shared).
+ *    For calls that should overlap on the device create one plan per thread / stream.
  */
 #ifndef ELISA_B200_H_
 #define ELISA_B200_H_

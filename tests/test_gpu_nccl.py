@@ -1,7 +1,9 @@
 """The multi-GPU path on real NCCL hardware (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest
 tests/test_gpu_nccl.py -m gpu`): every rank owns a plan on its GPU, evaluates its block of the
 batch, and one all_gather_into_tensor per result puts the full arrays on every rank -- equal to
-the single-GPU evaluation bit for bit (the kernels' summation trees do not depend on the batch)."""
+the single-GPU evaluation to the fold engine's accuracy (each rank's plan balances its integer fold
+around a pilot taken from its OWN block of rows, so the last bits differ between plans; rank 0's own
+block is reproduced bit for bit)."""
 
 import numpy as np
 import pytest
@@ -28,7 +30,9 @@ def _worker(rank, world, port, n, q):
     ok = ll.shape == (n, 1) and g.shape == (n, 1, 5)
     if rank == 0:
         ll1, g1 = lk.loglike_and_grad(theta)  # the whole batch on one GPU
-        ok = ok and torch.equal(ll, ll1) and torch.equal(g, g1)
+        lo = ll_local.shape[0]
+        close = lambda a, b: bool(((a - b).abs() <= 1e-11 * b.abs().amax(dim=0, keepdim=True)).all())
+        ok = ok and close(ll, ll1) and close(g, g1) and torch.equal(ll[:lo], ll1[:lo]) and torch.equal(g[:lo], g1[:lo])
     # cfg 3: 64 chains, sharded, lazily guarded (no host synchronisation per call)
     cfg3 = synthetic.config3(n=64)
     lk3 = Likelihood(cfg3['data'], cfg3['model'], cfg3['stat'], device=rank, guard='lazy')
@@ -39,7 +43,7 @@ def _worker(rank, world, port, n, q):
     if rank == 0:
         ref = Likelihood(cfg3['data'], cfg3['model'], cfg3['stat'], device=rank)
         l3, gg3 = ref.loglike_and_grad(th3)
-        ok = ok and torch.equal(ll3, l3) and torch.equal(g3, gg3)
+        ok = ok and close(ll3, l3) and close(g3, gg3)
         ref.close()
     torch.cuda.synchronize()
     q.put((rank, bool(ok), int(ll_local.shape[0])))
