@@ -3239,8 +3239,8 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
 
 int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const double* channel_width) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S || channel_width == nullptr)
-    std::lock_guard<std::mutex> lock(plan->mu);
         return fail(ELISA_ERR_INVALID, "set_channel_width: bad argument");
+    std::lock_guard<std::mutex> lock(plan->mu);
     SpectrumPlan& sp = plan->spec[spectrum];
     std::vector<double> inv(sp.C_pad, 1.0);
     for (int c = 0; c < sp.C; ++c) inv[c] = 1.0 / channel_width[c];

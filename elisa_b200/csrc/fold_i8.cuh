@@ -338,7 +338,7 @@ struct FoldI8Args {
     int32_t m_tiles, n_tiles;
     int32_t n_groups;  // ceil(n_tiles / I8_GROUP)
     int32_t* trap_info;  // host-mapped int32[128] or nullptr: which waits stalled (see mbar_wait)
-    int32_t debug;  // experiments only (elisa_b200_sliced_gemm_dev): 1 = no A copies, 2 = no B copies, 4 = no MMAs, 8 = no epilogue, 16 = no TMEM drain
+    int32_t debug;  // experiments only: 1 = no A copies, 2 = no B copies, 4 = no MMAs, 8 = no epilogue, 16 = no TMEM drain, 256 = every epilogue warp polls t_full itself (as before round 2)
 };
 
 // Exact int32 -> double without the quarter-rate I2F.F64: the bits of 2^52 + (v + 2^31) are
@@ -664,7 +664,13 @@ fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi
                 if (nt % I8_GROUP == 0) epi.begin(st);
                 epi.prefetch(row_acc, c0);
                 const bool empty = a.kb_lo[nt] >= a.kb_hi[nt];  // no k-blocks: accumulators are stale
-                mbar_wait(t_full, tph, a.trap_info, 5, nt);
+                // One warp waits on the mbarrier, the other fifteen on a named barrier behind it: a warp
+                // sleeping in mbarrier.try_wait is woken by EVERY barrier event of the CTA (~500 per tile:
+                // each bulk-copy completion and each MMA commit) only to go back to sleep, and sixteen of
+                // them polling were a quarter of all instructions this kernel issued (19 M NANOSLEEP /
+                // TRYWAIT pairs per launch, profiles/r02_stalls.md) -- on a chip at its power cap.
+                if ((a.debug & 256) || warp == 0) mbar_wait(t_full, tph, a.trap_info, 5, nt);
+                if (!(a.debug & 256)) asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_WARPS * 32) : "memory");
                 tph ^= 1u;
                 tc_fence_after();
                 // drain: recombine this thread's elements into registers, hand TMEM back to the

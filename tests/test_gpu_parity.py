@@ -268,3 +268,29 @@ def test_row_wise_csr_fold_matches_the_dense_product(lib):
     with pytest.raises(_lib.ElisaB200Error, match='dense'):
         lk.csr_fold(0, lk.unfold(0, full['theta'][:4]))
     lk.close()
+
+
+@pytest.mark.parametrize('fold', [None, 'dmma'])
+def test_joint_fit_of_16_spectra_with_per_spectrum_constants(lib, fold, monkeypatch):
+    """18 free parameters (a shared power law + one cross-calibration constant per spectrum): more than the
+    16 columns round 1 stopped at.  Value and gradient against the oracle with both gradient paths (for the
+    tangent-plane path the integer fold's gradient epilogue runs twice, 16 + 2 columns)."""
+    from parity import RTOL, compare
+
+    base = synthetic.config5(n=97, S=16, E=128, C=64)
+    a = M.UniformParameter('alpha', 1.7, -3.0, 10.0)
+    K = M.UniformParameter('K', 10.0, 1e-10, 1e10)
+    models = [M.Constant(f=M.UniformParameter(f'f{i}', 1.0, 0.1, 10.0)) * M.PowerLaw(alpha=a, K=K) for i in range(16)]
+    rng = np.random.default_rng(3)
+    theta = np.column_stack([1.0 + 0.05 * rng.standard_normal((97, 1)), 1.7 + 0.05 * rng.standard_normal((97, 1)),
+                             10.0 * (1.0 + 0.05 * rng.standard_normal((97, 1))), 1.0 + 0.05 * rng.standard_normal((97, 15))])
+    cfg = dict(base, model=models, theta=theta)
+    from elisa_b200 import Likelihood
+
+    lk = Likelihood(cfg['data'], models, cfg['stat'])
+    assert lk.nparam == 18 and [p.name for p in lk.free][:4] == ['f0', 'alpha', 'K', 'f1']
+    lk.close()
+    for mode in ('contract', 'planes'):
+        monkeypatch.setenv('ELISA_B200_GRAD', mode)
+        err = compare(cfg, fold=fold) if fold else compare(cfg)
+        assert err['value'] <= RTOL and err['grad'] <= RTOL, (mode, err)
