@@ -136,6 +136,7 @@ SYMBOLS = {
     'elisa_b200_plan_guard_poll': (C.c_int, [_VP, C.c_int, C.POINTER(C.c_int64), c_double_p]),
     'elisa_b200_jacobian_dev': (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     'elisa_b200_plan_set_debug': (C.c_int, [_VP, C.c_int32]),
+    'elisa_b200_sample_dev': (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, C.c_int64, C.c_uint64, _VP, C.c_int64, _VP]),
     'elisa_b200_csr_fold_dev': (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, _VP]),
     'elisa_b200_plan_fold_slices_bwd': (C.c_int, [_VP, C.c_int32]),
     'elisa_b200_plan_fold_products': (C.c_int, [_VP, C.c_int32, c_double_p]),

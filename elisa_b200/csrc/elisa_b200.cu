@@ -36,6 +36,7 @@
 #include "dual.cuh"
 #include "fold_i8.cuh"
 #include "gemm_f64.cuh"
+#include "sample.cuh"
 #include "stats.cuh"
 #include "unfold_skel.cuh"
 
@@ -3598,6 +3599,46 @@ int elisa_b200_csr_fold_dev(ElisaPlan* plan, int32_t spectrum, const double* unf
     }
     cudaSetDevice(prev);
     return rc;
+}
+
+int elisa_b200_sample_dev(ElisaPlan* plan, int32_t spectrum, int32_t which, const double* mean, int64_t mean_rows, int64_t n,
+                          uint64_t seed, double* out, int64_t ld, void* cuda_stream) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return fail(ELISA_ERR_INVALID, "sample: bad spectrum");
+    if (which < 0 || which > 1 || mean == nullptr || out == nullptr || n < 0 || (mean_rows != 1 && mean_rows != n))
+        return fail(ELISA_ERR_INVALID, "sample: bad argument");
+    if (n == 0) return ELISA_OK;
+    const SpectrumPlan& sp = plan->spec[spectrum];
+    if (ld < sp.C) return fail(ELISA_ERR_INVALID, "sample: ld < n_channels");
+    // sampling distributions of the reference (infer/likelihood.py:209-225, 350-385; helper.py:221-278):
+    // 'on' data Normal(model, net_errors) for chi2 and Poisson otherwise; 'off' data Normal(model,
+    // back_errors) for pgstat and Poisson for wstat; other statistics have no sampled background
+    const double* sigma = nullptr;
+    if (which == 0 && sp.stat == ELISA_STAT_CHI2) sigma = sp.chan + (size_t)3 * sp.C_pad;
+    if (which == 1) {
+        if (sp.stat == ELISA_STAT_PGSTAT) sigma = sp.chan + (size_t)3 * sp.C_pad;
+        else if (sp.stat != ELISA_STAT_WSTAT) return fail(ELISA_ERR_INVALID, "sample: this statistic has no sampled background");
+    }
+    int prev = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(plan->device));
+    SampleArgs a;
+    a.mean = mean;
+    a.mean_rows = mean_rows;
+    a.sigma = sigma;
+    a.n = n;
+    a.C = sp.C;
+    a.out = out;
+    a.ld = ld;
+    a.seed = seed;
+    // disjoint streams per (spectrum, on / off array): 2^40 elements each
+    a.stream0 = ((uint64_t)(2 * spectrum + which)) << 40;
+    const int64_t total = n * sp.C;
+    sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(a);
+    ++plan->launches;
+    const cudaError_t e = cudaGetLastError();
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(ELISA_ERR_CUDA, std::string("sample_kernel: ") + cudaGetErrorString(e));
+    return ELISA_OK;
 }
 
 int elisa_b200_plan_rebalance(ElisaPlan* plan) {

@@ -523,37 +523,43 @@ class Likelihood:
         (N, P) with one replica per row (the reference's posterior-predictive case).  Returns
         ``(counts_on, counts_off)``, (rows, sum of channels) CUDA tensors in the layout the
         evaluation entry points take (``counts_off`` is None when no dataset has a sampled
-        background).  The stream of random numbers is torch's Philox generator seeded with
-        ``seed``: the reference's NumPy stream cannot be reproduced on a GPU, so parity here is
-        distributional (tests check moments and the fit recovering the truth)."""
+        background).  The draws come from the library's own sampling kernel
+        (``elisa_b200_sample_dev``: Philox4x32-10, one stream per (seed, dataset, array, replica,
+        channel); Poisson by multiplication below a mean of 12 and by transformed rejection above,
+        Normal by Box-Muller): the reference's NumPy stream cannot be reproduced on a GPU, so
+        parity here is distributional (tests check moments, the pmf at small means and the fit
+        recovering the truth)."""
         torch = self._torch
         t = self._theta(theta)
         if t.shape[0] != 1 and n != 1:
             raise ValueError('n > 1 needs a single parameter vector (helper.py:851-857)')
         rows = t.shape[0] if t.shape[0] != 1 else int(n)
-        gen = torch.Generator(device=t.device).manual_seed(int(seed))
-        on, off, any_off = [], [], False
-        for k, (d, stat) in enumerate(zip(self.data, self.stat)):
-            sites = self.sites(k, t)
-            name = self.names[k]
-            m_on = sites[f'{name}_Non_model'].expand(rows, -1).contiguous()
-            if stat == 'chi2':
-                err = torch.as_tensor(d.net_errors, dtype=torch.float64, device=t.device)
-                on.append(m_on + err * torch.randn(m_on.shape, dtype=torch.float64, device=t.device, generator=gen))
-            else:
-                on.append(torch.poisson(m_on, generator=gen))
-            if stat in ('pgstat', 'wstat'):
-                any_off = True
-                m_off = sites[f'{name}_Noff_model'].expand(rows, -1).contiguous()
-                if stat == 'pgstat':
-                    err = torch.as_tensor(d.back_errors, dtype=torch.float64, device=t.device)
-                    off.append(m_off + err * torch.randn(m_off.shape, dtype=torch.float64, device=t.device, generator=gen))
-                else:
-                    off.append(torch.poisson(m_off, generator=gen))
-            else:  # not sampled: the observed background (if any) stays in place
-                b = d.back_counts if getattr(d, 'back_counts', None) is not None else np.zeros(d.n_channels)
-                off.append(torch.as_tensor(b, dtype=torch.float64, device=t.device).expand(rows, -1))
-        return torch.cat(on, dim=1).contiguous(), (torch.cat(off, dim=1).contiguous() if any_off else None)
+        W = self.sum_channels
+        any_off = any(s in ('pgstat', 'wstat') for s in self.stat)
+        with self._device_ctx():
+            on = torch.empty((rows, W), dtype=torch.float64, device=t.device)
+            off = torch.empty((rows, W), dtype=torch.float64, device=t.device) if any_off else None
+            col = 0
+            for k, (d, stat) in enumerate(zip(self.data, self.stat)):
+                sites = self.sites(k, t)
+                name = self.names[k]
+                Ck = self.n_channels[k]
+
+                def draw(which, mean, out):
+                    mean = mean.contiguous()
+                    view = out[:, col: col + Ck]  # element [row, c] at out + col + row * W + c
+                    _lib.check(self._lib.elisa_b200_sample_dev(
+                        self._h, k, which, _dev_ptr(mean), mean.shape[0], rows, int(seed) & (2**64 - 1),
+                        C.c_void_p(view.data_ptr()), W, self._stream()))
+
+                draw(0, sites[f'{name}_Non_model'], on)
+                if stat in ('pgstat', 'wstat'):
+                    draw(1, sites[f'{name}_Noff_model'], off)
+                elif off is not None:  # not sampled: the observed background (if any) stays in place
+                    b = d.back_counts if getattr(d, 'back_counts', None) is not None else np.zeros(Ck)
+                    off[:, col: col + Ck] = torch.as_tensor(b, dtype=torch.float64, device=t.device)
+                col += Ck
+        return on, off
 
     def simulate_and_fit(self, theta, n: int = 1, seed: int = 0, **fit_kw):
         """``simulate_and_fit`` of the reference (infer/helper.py:808-876), the core of ``boot()``

@@ -426,6 +426,16 @@ int elisa_b200_jacobian_dev(ElisaPlan* plan, int32_t spectrum, const double* the
  * unfolded model already.  ELISA_ERR_UNSUPPORTED for a dense response.                      */
 int elisa_b200_csr_fold_dev(ElisaPlan* plan, int32_t spectrum, const double* unfold, int64_t ldu, int64_t n, double* folded,
                             int64_t ldx, void* cuda_stream);
+/* Device-side simulator (infer/helper.py:221-278, simulate; :808-876, simulate_and_fit): draws n data
+ * sets of spectrum `spectrum` from model counts `mean` ([mean_rows, C]; mean_rows = 1: one model for all
+ * replicas, = n: one per replica -- the '{name}_Non_model' / '{name}_Noff_model' sites of
+ * elisa_b200_sites_dev) into out[row * ld + col].  which = 0: the 'on' data, Poisson(mean), or
+ * Normal(mean, net_errors) for chi2; which = 1: the background, Normal(mean, back_errors) for pgstat,
+ * Poisson(mean) for wstat.  Counter-based generator (Philox4x32-10), one stream per (seed, spectrum,
+ * array, replica, channel): reproducible and independent of the launch shape.  NumPy's stream cannot
+ * be reproduced, parity is distributional.                                                  */
+int elisa_b200_sample_dev(ElisaPlan* plan, int32_t spectrum, int32_t which, const double* mean, int64_t mean_rows, int64_t n,
+                          uint64_t seed, double* out, int64_t ld, void* cuda_stream);
 /* Timing experiments only: bit mask of kernel classes to SKIP in the evaluation entry points
  * (1 unfold, 2 forward fold, 4 statistic, 8 transposed fold, 16 reduce, 32 the dU/dtheta stores of
  * the specialised unfold kernel); results are garbage

@@ -243,3 +243,70 @@ def test_normal_equations_with_more_than_eight_parameters(lib):
         J = torch.nan_to_num(torch.autograd.functional.jacobian(fn, t[i : i + 1].clone())[:, 0, :])
         href = (J.T @ J).numpy()
         assert np.allclose(h[i].cpu().numpy(), href, rtol=1e-7, atol=1e-8 * np.abs(href).max()), i
+
+
+def test_sampling_kernel_distributions(lib):
+    """elisa_b200_sample_dev (the repo's own Philox / Poisson / Normal kernel behind Likelihood.simulate):
+    moments over 4e5 draws per mean on both sides of the multiplication / transformed-rejection switch at
+    12, the probability mass function against scipy at small and moderate means, per-seed
+    reproducibility, independence of the launch shape, Normal draws for chi2 data."""
+    import ctypes as C
+
+    from scipy import stats
+
+    from elisa_b200 import FixedData, Likelihood, _lib
+
+    means = np.array([0.0, 0.05, 0.7, 3.0, 11.9, 12.0, 12.1, 50.0, 1e3, 1e5, 3e7])
+    Cn = means.size
+    eg = np.geomspace(1.0, 10.0, 9)
+    d = FixedData('d', eg, np.ones(Cn), np.ones(Cn), 1.0, response_matrix=np.ones((8, Cn)), back_counts=np.ones(Cn),
+                  back_errors=np.full(Cn, 2.5), back_ratio=1.0, net_counts=np.ones(Cn), net_errors=np.linspace(0.5, 3.0, Cn))
+    n = 400_000
+    mean_t = torch.as_tensor(means[None, :], dtype=torch.float64, device='cuda')
+
+    def draw(lk, which, seed, rows=n, mean=mean_t):
+        out = torch.empty((rows, Cn), dtype=torch.float64, device='cuda')
+        _lib.check(lk._lib.elisa_b200_sample_dev(lk._h, 0, which, C.c_void_p(mean.data_ptr()), mean.shape[0], rows, seed,
+                                                 C.c_void_p(out.data_ptr()), Cn, lk._stream()))
+        torch.cuda.synchronize()
+        return out
+
+    lk = Likelihood([d], M.PowerLaw(), ['wstat'])
+    x = draw(lk, 0, 11).cpu().numpy()
+    assert np.all(x >= 0) and np.all(x == np.round(x))
+    m, v = x.mean(0), x.var(0)
+    se_m = np.sqrt(np.maximum(means, 1e-300) / n)
+    assert np.all(np.abs(m - means) <= 5 * se_m + 1e-12), (m, means)
+    se_v = np.sqrt((means + 2 * means**2) / n) + 1e-12   # var of the sample variance of a Poisson, roughly
+    assert np.all(np.abs(v - means) <= 6 * se_v), (v, means)
+    for j, lam in enumerate(means):
+        if 0.0 < lam <= 60.0:  # the whole pmf
+            ks = np.arange(0, int(lam + 10 * np.sqrt(lam) + 10))
+            cnt = np.array([(x[:, j] == k).sum() for k in ks])
+            p = stats.poisson.pmf(ks, lam)
+            keep = n * p > 20
+            chi2 = float((((cnt - n * p) ** 2) / (n * p))[keep].sum())
+            assert chi2 < keep.sum() + 6 * np.sqrt(2 * keep.sum()), (lam, chi2, keep.sum())
+    # reproducible per seed, different across seeds and between the 'on' and 'off' arrays
+    assert torch.equal(draw(lk, 0, 11, rows=1000), torch.as_tensor(x[:1000], device='cuda'))
+    assert not torch.equal(draw(lk, 0, 12, rows=1000), torch.as_tensor(x[:1000], device='cuda'))
+    assert not torch.equal(draw(lk, 1, 11, rows=1000), torch.as_tensor(x[:1000], device='cuda'))
+    # one model row per replica
+    per = torch.as_tensor(np.tile(means, (1000, 1)), device='cuda')
+    assert torch.equal(draw(lk, 0, 11, rows=1000, mean=per), torch.as_tensor(x[:1000], device='cuda'))
+    lk.close()
+    # Normal draws: chi2 'on' data with net_errors, pgstat background with back_errors
+    lk = Likelihood([d], M.PowerLaw(), ['chi2'])
+    g = draw(lk, 0, 5).cpu().numpy()
+    sig = np.linspace(0.5, 3.0, Cn)
+    assert np.all(np.abs(g.mean(0) - means) <= 5 * sig / np.sqrt(n) + 1e-9 * means)
+    assert np.all(np.abs(g.std(0) / sig - 1.0) <= 5 / np.sqrt(2 * n))
+    z = (g[:, 3] - means[3]) / sig[3]
+    assert abs(stats.kstest(z[:50000], 'norm').statistic) < 0.01
+    with pytest.raises(_lib.ElisaB200Error):
+        draw(lk, 1, 5, rows=10)  # chi2 has no sampled background
+    lk.close()
+    lk = Likelihood([d], M.PowerLaw(), ['pgstat'])
+    b = draw(lk, 1, 5).cpu().numpy()
+    assert np.all(np.abs(b.std(0) / 2.5 - 1.0) <= 5 / np.sqrt(2 * n))
+    lk.close()
