@@ -221,6 +221,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const SliceArgs a) {
         asum += __shfl_xor_sync(0xffffffffu, asum, o);
     }
     bad = __any_sync(0xffffffffu, bad);
+    // the same row maximum as the kernels that slice their own output (unfold_generic, stat_slice_kernel):
+    // the upper end of the interval of doubles sharing amax's high word -- a row must get the same digits
+    // whichever kernel slices it (results are bit-identical under re-chunking, which changes that)
+    if (amax > 0.0 && !bad) amax = __hiloint2double(__double2hiint(amax), (int)0xffffffff);
     double f1, f2;
     const double sc = slice_scale<KS>(amax, bad, f1, f2);
     if (lane == 0) {
@@ -897,8 +901,9 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     if (row >= a.rows_pad) return;
     const bool live = row < a.n_valid;
     double* x = a.X + (size_t)row * a.ldx;
-    double rs = 0.0, amax = 0.0, eb = 0.0, wsum = 0.0;
-    bool bad = false, flagged = false;
+    double rs = 0.0, eb = 0.0, wsum = 0.0;
+    int amax_hi = 0;  // largest |W'| of the row, tracked on the high word (see unfold_generic)
+    bool flagged = false;
     if (live) {
         const double u_max = a.scale[row] * (double)I8_TOP_DIGIT;  // largest |U| of the row
         const double* con = a.counts_on ? a.counts_on + (size_t)row * a.ld_counts : nullptr;
@@ -932,9 +937,8 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
             if (GRAD) {
                 const double w = dx * sc;
                 x[col] = w;
-                bad |= !(fabs(w) <= 1.79e308);
                 const double wb = a.kinv != nullptr ? fabs(w) * a.kinv[col] : fabs(w);  // as the digits see it
-                amax = fmax(amax, wb);
+                amax_hi = max(amax_hi, __double2hiint(wb) & 0x7fffffff);  // NaN / Inf: >= 0x7ff00000
                 wsum += wb;
             }
         }
@@ -957,10 +961,11 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
     if (!GRAD) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        amax_hi = max(amax_hi, __shfl_xor_sync(0xffffffffu, amax_hi, o));
         wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
     }
-    bad = __any_sync(0xffffffffu, bad);
+    const bool bad = amax_hi >= 0x7ff00000;
+    const double amax = amax_hi == 0 ? 0.0 : __hiloint2double(amax_hi, (int)0xffffffff);
     if (live && lane == 0) {
         if (wsum > 0.0 && !bad) {
             // gradient side of the guard.  The transposed fold's error is relative to the LARGEST

@@ -156,8 +156,11 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
     // balancing factor of the lane's bin, loaded one pass ahead like the grid values
     const bool scaled = slice && a.kexp != nullptr;
     int nk = scaled ? a.kexp[min(e_lo + lane, E - 1)] : 0;
-    double amax = 0.0;
-    bool bad = false;
+    // largest |u| of the row for the digit scale, tracked on the HIGH WORD of the doubles (an integer
+    // max instead of a NaN-aware FP64 max per bin; a non-finite value shows as a high word >=
+    // 0x7ff00000).  The scale is then taken from the upper end of that high word's interval: at
+    // most 2^-20 above the true maximum, far inside the headroom of the top digit (120 of 127).
+    int amax_hi = 0;
     for (int e0 = e_lo; e0 < e_hi; e0 += 31) {
         const int e = e0 + lane;
         gv.pE = nE;
@@ -172,18 +175,16 @@ __device__ __forceinline__ void unfold_generic(const UnfoldCore& a) {
         const T res = Model::bin(pre, gv, e);
         if (lane < 31 && e < e_hi) {
             const double u = unfold_store<T>(a, row_off + e, res, ck);
-            if constexpr (KS > 0) {
-                bad |= !(fabs(u) <= 1.79e308);
-                amax = fmax(amax, fabs(u));
-            }
+            if constexpr (KS > 0) amax_hi = max(amax_hi, __double2hiint(u) & 0x7fffffff);
         }
     }
     if (last_seg) unfold_zero(a, row_off, E, a.e_pad, lane, GRAD);
     if constexpr (KS > 0) {
         if (slice) {  // digits of the finished row, read back while it is still in L2
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-            bad = __any_sync(0xffffffffu, bad);
+            for (int o = 16; o > 0; o >>= 1) amax_hi = max(amax_hi, __shfl_xor_sync(0xffffffffu, amax_hi, o));
+            const bool bad = amax_hi >= 0x7ff00000;
+            const double amax = amax_hi == 0 ? 0.0 : __hiloint2double(amax_hi, (int)0xffffffff);
             double f1, f2;
             const double sc = slice_scale<KS>(amax, bad, f1, f2);
             if (lane == 0) a.scale[row] = sc;
