@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libelisa_b200.so')
+# ELISA_B200_LIB: another build of the library (A/B runs of kernel variants, tools/ab_lib.sh)
+LIB_PATH = os.environ.get('ELISA_B200_LIB') or os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
 ABI_VERSION = 4
 MAX_COMP_PARAMS = 5

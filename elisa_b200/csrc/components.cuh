@@ -124,8 +124,30 @@ struct Comp<ELISA_COMP_BLACKBODY> {  // Blackbody.continuum, models/add.py:266-2
         } else if (xv >= 50.0) {
             g[0] = Cst<T>::make(0.0);
         } else {
-            g[0] = tmp * x / em1(x);
+            g[0] = tmp * x * rinv(em1(x));  // x in (1e-4, 50): expm1(x) in (1e-4, 5.2e21)
         }
+    }
+    // closed-form edge tangents (see EdgeLeaf): b0 = g / K, b1 = (g / K) (x (1 + 1 / expm1 x) - 4), x = E / kT
+    static constexpr int NB = 2;
+    __device__ static void basis(const double* p, const double* c, double E, double, double& v, double* b) {
+        const double x = E * c[0];
+        const double t = (8.0525 * c[0] * c[0] * c[0]) * E;
+        if (x <= 1e-4) {
+            b[0] = t;
+            b[1] = -3.0 * t;
+        } else if (x >= 50.0) {
+            b[0] = 0.0;
+            b[1] = 0.0;
+        } else {
+            const double r = rinv(em1(x));
+            b[0] = t * x * r;
+            b[1] = b[0] * (fma(x, r, x) - 4.0);
+        }
+        v = p[1] * b[0];
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        d[0] = p[1] * c[0] * S[1];
+        d[1] = S[0];
     }
 };
 
@@ -146,8 +168,30 @@ struct Comp<ELISA_COMP_BLACKBODYRAD> {  // BlackbodyRad.continuum, models/add.py
         } else if (xv >= 50.0) {
             g[0] = Cst<T>::make(0.0);
         } else {
-            g[0] = tmp * E / em1(x);
+            g[0] = tmp * E * rinv(em1(x));
         }
+    }
+    // closed-form edge tangents: b0 = g / K, b1 = kT / K dg/dkT
+    static constexpr int NB = 2;
+    __device__ static void basis(const double* p, const double* c, double E, double, double& v, double* b) {
+        const double x = E * c[0];
+        const double t = 1.0344e-3 * E;
+        if (x <= 1e-4) {
+            b[0] = t * p[0];
+            b[1] = b[0];
+        } else if (x >= 50.0) {
+            b[0] = 0.0;
+            b[1] = 0.0;
+        } else {
+            const double r = rinv(em1(x));
+            b[0] = t * E * r;
+            b[1] = b[0] * fma(x, r, x);
+        }
+        v = p[1] * b[0];
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        d[0] = p[1] * c[0] * S[1];
+        d[1] = S[0];
     }
 };
 
@@ -162,6 +206,21 @@ struct Comp<ELISA_COMP_COMPT> {  // Compt.continuum, models/add.py:473-479
     __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
         g[0] = p[2] * ex(E * c[0] - p[0] * lnE);
     }
+    // closed-form edge tangents: b = e (1, E, ln E), e = exp(E (a - 2) / b - a ln E)
+    static constexpr int NB = 3;
+    __device__ static void basis(const double* p, const double* c, double E, double lnE, double& v, double* b) {
+        const double e = ex(E * c[0] - p[0] * lnE);
+        v = p[2] * e;
+        b[0] = e;
+        b[1] = e * E;
+        b[2] = e * lnE;
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        const double inv = 1.0 / p[1];
+        d[0] = p[2] * (S[1] * inv - S[2]);
+        d[1] = -(p[2] * c[0] * inv * S[1]);
+        d[2] = S[0];
+    }
 };
 
 template <>
@@ -174,6 +233,20 @@ struct Comp<ELISA_COMP_CUTOFFPL> {  // CutoffPL.continuum, models/add.py:434-439
     template <typename T>
     __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
         g[0] = p[2] * ex(-(p[0] * lnE) - E * c[0]);
+    }
+    // closed-form edge tangents: b = e (1, ln E, E), e = exp(-alpha ln E - E / Ec)
+    static constexpr int NB = 3;
+    __device__ static void basis(const double* p, const double* c, double E, double lnE, double& v, double* b) {
+        const double e = ex(-(p[0] * lnE) - E * c[0]);
+        v = p[2] * e;
+        b[0] = e;
+        b[1] = e * lnE;
+        b[2] = e * E;
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        d[0] = -(p[2] * S[1]);
+        d[1] = p[2] * c[0] * c[0] * S[2];
+        d[2] = S[0];
     }
 };
 
@@ -191,6 +264,21 @@ struct Comp<ELISA_COMP_GAUSS> {  // Gauss.continuum, models/add.py:511-516 (jax 
         const T dx = E - p[0];
         g[0] = p[2] * ex((c[0] + dx * dx * c[1]) * -0.5);
     }
+    // closed-form edge tangents: b = e (1, dx, dx^2), e = pdf(E; El, sigma), dx = E - El
+    static constexpr int NB = 3;
+    __device__ static void basis(const double* p, const double* c, double E, double, double& v, double* b) {
+        const double dx = E - p[0];
+        const double e = ex((c[0] + dx * dx * c[1]) * -0.5);
+        v = p[2] * e;
+        b[0] = e;
+        b[1] = e * dx;
+        b[2] = b[1] * dx;
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        d[0] = p[2] * c[1] * S[1];
+        d[1] = p[2] * (c[1] * S[2] - S[0]) / p[1];
+        d[2] = S[0];
+    }
 };
 
 template <>
@@ -203,6 +291,17 @@ struct Comp<ELISA_COMP_OTTB> {  // OTTB.continuum, models/add.py:590-594
     template <typename T>
     __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
         g[0] = p[1] * ex((1.0 - E) * c[0]) * (1.0 / E);
+    }
+    // closed-form edge tangents: b0 = g / K, b1 = (g / K) (E - 1)
+    static constexpr int NB = 2;
+    __device__ static void basis(const double* p, const double* c, double E, double, double& v, double* b) {
+        b[0] = ex((1.0 - E) * c[0]) * (1.0 / E);
+        b[1] = b[0] * (E - 1.0);
+        v = p[1] * b[0];
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        d[0] = p[1] * c[0] * c[0] * S[1];
+        d[1] = S[0];
     }
 };
 
@@ -246,18 +345,36 @@ struct Comp<ELISA_COMP_SMOOTHLYBROKENPL> {  // SmoothlyBrokenPL.continuum, model
 // ------------------------------------------------------------------ additive, analytic
 template <>
 struct Comp<ELISA_COMP_POWERLAW> {  // PowerLaw.integral, models/add.py:40-50,655-657
-    static constexpr int NP = 2, NG = 1, NC = 1, RULE = RULE_CUSTOM;
+    static constexpr int NP = 2, NG = 1, NC = 2, RULE = RULE_CUSTOM;
     template <typename T>
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = sel(value(p[0]) != 1.0, 1.0 - p[0], Cst<T>::make(1.0));
+        c[1] = 1.0 / c[0];  // the division by (1 - alpha) once per parameter vector, not once per edge
     }
     template <typename T>
     __device__ static void edge(const T* p, const T* c, double, double lnE, T* g) {
-        g[0] = powerlaw_antiderivative(value(p[0]) != 1.0, c[0], lnE);
+        if (value(p[0]) != 1.0)
+            g[0] = pw_e(lnE, c[0]) * c[1];
+        else
+            g[0] = Cst<T>::make(lnE);
     }
     template <typename T>
     __device__ static T bin(const T* p, const T*, const T* g0, const T* g1, double, double) {
         return p[1] * (g1[0] - g0[0]);
+    }
+    // closed-form edge tangents of the antiderivative: the bin is K (F(E1) - F(E0)), a DIFFERENCE of
+    // edge values (EDGE_DIFF): b0 = F, b1 = F ln E; dF/dalpha = F (1 / (1 - alpha) - ln E) for alpha != 1
+    static constexpr int NB = 2;
+    static constexpr bool EDGE_DIFF = true;
+    __device__ static void basis(const double* p, const double* c, double, double lnE, double& v, double* b) {
+        const bool cond = p[0] != 1.0;
+        b[0] = cond ? ex(c[0] * lnE) * c[1] : lnE;
+        b[1] = cond ? b[0] * lnE : 0.0;
+        v = p[1] * b[0];
+    }
+    __device__ static void finish(const double* p, const double* c, const double* S, double* d) {
+        d[0] = p[0] != 1.0 ? p[1] * (S[0] * c[1] - S[1]) : 0.0;
+        d[1] = S[0];
     }
 };
 

@@ -180,6 +180,13 @@ __device__ __forceinline__ Dual<N> em1(const Dual<N>& a) {
     const double e = fm::expm1(a.v);
     return chain(a, e, e + 1.0);
 }
+// 1 / a for a normal a well inside the exponent range: fm::rcp (fastmath.cuh)
+__device__ __forceinline__ double rinv(double a) { return fm::rcp(a); }
+template <int N>
+__device__ __forceinline__ Dual<N> rinv(const Dual<N>& a) {
+    const double r = rinv(a.v);
+    return chain(a, r, -(r * r));
+}
 // base^expo with a plain-double base whose log is known (energies): exp(expo * ln base)
 __device__ __forceinline__ double pw_e(double lnbase, double expo) { return fm::exp(expo * lnbase); }
 template <int N>

@@ -1637,6 +1637,79 @@ static std::string generate_model_struct(const ModelDev& m, int P, bool grad, co
     return s;
 }
 
+// Gradient by contraction on edges (unfold_contract_edges, unfold_skel.cuh): possible when the model is a
+// plain sum of trapezoid continuum leaves and power laws -- the bin value is then linear in the edge
+// values of each leaf.  Returns the generated policy struct ModelE, or an empty string when the model
+// does not qualify (products, Simpson's rule, flux normalisations, analytic leaves other than the power
+// law) or ELISA_B200_CONTRACT=generic asks for the dual-number contraction.
+static std::string generate_edge_model(const ModelDev& m, int P) {
+    if (const char* env = getenv("ELISA_B200_CONTRACT"))
+        if (strcmp(env, "generic") == 0) return std::string();
+    if (m.n_norms != 0) return std::string();
+    auto str = [](int v) { return std::to_string(v); };
+    std::vector<int> mult(m.n_leaf, 0);
+    int n_acc = 0;
+    for (int o = 0; o < m.n_ops; ++o) {
+        const int op = m.ops[o];
+        if (op >= 0)
+            ++mult[op];
+        else if (op != ELISA_OP_ADD)
+            return std::string();
+    }
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        const bool trapz_continuum = comp_is_additive(L.kind) && L.kind != ELISA_COMP_POWERLAW && L.kind != ELISA_COMP_BROKENPL &&
+                                     L.kind != ELISA_COMP_LORENTZ && L.kind != ELISA_COMP_PLENFLUX && L.kind != ELISA_COMP_PLPHFLUX &&
+                                     L.method == ELISA_METHOD_TRAPZ;
+        if (!trapz_continuum && L.kind != ELISA_COMP_POWERLAW) return std::string();
+        n_acc += L.np;
+    }
+    if (n_acc > 12) return std::string();  // accumulators and basis values live in registers
+    std::string s = "struct ModelE {\n  static constexpr int NPAR = " + str(P) + ";\n  static constexpr int O0 = 0;\n";
+    for (int i = 0; i < m.n_leaf; ++i)
+        s += "  using L" + str(i) + " = EdgeLeaf<" + str(m.leaf[i].kind) + ">;\n  static constexpr int O" + str(i + 1) + " = O" + str(i) +
+             " + L" + str(i) + "::NB;\n";
+    s += "  static constexpr int NACC = O" + str(m.n_leaf) + ";\n  static constexpr unsigned DMASK = 0u";
+    for (int i = 0; i < m.n_leaf; ++i) s += " | (L" + str(i) + "::DIFF ? ((1u << L" + str(i) + "::NB) - 1u) << O" + str(i) + " : 0u)";
+    s += ";\n  static constexpr bool HAS_T = false";
+    for (int i = 0; i < m.n_leaf; ++i) s += " || !L" + str(i) + "::DIFF";
+    s += ";\n  static constexpr bool HAS_D = false";
+    for (int i = 0; i < m.n_leaf; ++i) s += " || L" + str(i) + "::DIFF";
+    s += ";\n  struct Pre {\n";
+    for (int i = 0; i < m.n_leaf; ++i) s += "    L" + str(i) + "::Pre l" + str(i) + ";\n";
+    s += "  };\n  __device__ __forceinline__ static void pre(const double* th, Pre& s) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        s += "    { const double val[" + str(L.np) + "] = {";
+        for (int q = 0; q < L.np; ++q) s += (q ? ", " : "") + (L.src[q] >= 0 ? "th[" + str(L.src[q]) + "]" : hexd(L.cst[q]));
+        s += "}; const double aux[2] = {" + hexd(L.aux[0]) + ", " + hexd(L.aux[1]) + "}; L" + str(i) + "::pre(val, aux, s.l" + str(i) + "); }\n";
+    }
+    s += "  }\n  __device__ __forceinline__ static void edge(const Pre& s, const GridView&, double E, double lnE, double& vT, double& vD, double* b) {\n"
+         "    double v;\n";
+    // scale of a leaf's contribution: out_scale (x grid_scale for the trapezoid's bin width) x multiplicity
+    std::vector<double> f(m.n_leaf);
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        const bool diff = L.kind == ELISA_COMP_POWERLAW;
+        f[i] = L.os * (diff ? 1.0 : L.gs) * (double)mult[i];
+        s += "    L" + str(i) + "::edge(s.l" + str(i) + ", " + (L.gs != 1.0 ? hexd(L.gs) + " * E" : std::string("E")) + ", " +
+             (L.lgs != 0.0 ? "lnE + " + hexd(L.lgs) : std::string("lnE")) + ", v, b + O" + str(i) + "); " + (diff ? "vD" : "vT") + " += " +
+             (f[i] != 1.0 ? hexd(f[i]) + " * v" : std::string("v")) + ";\n";
+    }
+    s += "  }\n  __device__ __forceinline__ static void finish(const Pre& s, const double* S, double* grad) {\n"
+         "    for (int j = 0; j < NPAR; ++j) grad[j] = 0.0;\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        s += "    { double d[" + str(L.np) + "]; L" + str(i) + "::finish(s.l" + str(i) + ", S + O" + str(i) + ", d);";
+        for (int q = 0; q < L.np; ++q)
+            if (L.src[q] >= 0)
+                s += " grad[" + str(L.src[q]) + "] += " + (f[i] != 1.0 ? hexd(f[i]) + " * " : std::string()) + "d[" + str(q) + "];";
+        s += " }\n";
+    }
+    s += "  }\n};\n";
+    return s;
+}
+
 static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
     std::string s;
     {
@@ -1656,8 +1729,14 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
          k + ">(a); }\n";
     s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_grad(const UnfoldCore a) { unfold_generic<ModelG, Dual<" +
          std::to_string(P) + ">, " + k + ">(a); }\n";
-    s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
-         "unfold_contract_generic<ModelG, Dual<" + std::to_string(P) + ">>(a); }\n";
+    const std::string edge_model = generate_edge_model(m, P);
+    s += edge_model;
+    if (!edge_model.empty())
+        s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
+             "unfold_contract_edges<ModelE>(a); }\n";
+    else
+        s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
+             "unfold_contract_generic<ModelG, Dual<" + std::to_string(P) + ">>(a); }\n";
     return s;
 }
 

@@ -894,8 +894,13 @@ __device__ __forceinline__ void guard_flag_row(const StatSliceArgs& a, int row) 
 }
 
 // KS: slices of W (the transposed fold's A operand).
+// 64 registers = 4 blocks per SM: the kernel lives on occupancy (its FP64 chains -- two logarithms, a
+// square root, two reciprocals per channel -- hide behind other warps); measured on the bench shape
+// (profiles/r02b_ab_stat.txt): 66 registers = 3 blocks 6.47 ms per 400k rows, 64 registers 5.6, forced
+// below that (48 / 40 registers, spills) 6.5; channel constants as 64-byte records (4 x LDG.128 instead
+// of 9 x LDG.64, but 4x the L1 wavefronts of the coalesced column arrays) 6.4 - 7.2.
 template <int KS, int STAT, bool GRAD>
-__global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) {
+__global__ void __launch_bounds__(256, 4) stat_slice_kernel(const StatSliceArgs a) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= a.rows_pad) return;
@@ -908,31 +913,46 @@ __global__ void __launch_bounds__(256) stat_slice_kernel(const StatSliceArgs a) 
         const double u_max = a.scale[row] * (double)I8_TOP_DIGIT;  // largest |U| of the row
         const double* con = a.counts_on ? a.counts_on + (size_t)row * a.ld_counts : nullptr;
         const double* coff = a.counts_off ? a.counts_off + (size_t)row * a.ld_counts : nullptr;
+        constexpr bool HAS_OFF = STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT;
+        const bool use_off = (STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr;
+        // the folded rate (and the row's own counts) of the next pass are loaded during this one: they
+        // come from L2 / HBM, the per-channel constants below from L1 (every row of the SM reads the same)
+        double xn = 0.0, con_n = 0.0, coff_n = 0.0;
+        if (lane < a.C) {
+            xn = x[lane];
+            if (con != nullptr) con_n = con[lane];
+            if (use_off) coff_n = coff[lane];
+        }
         for (int col = lane; col < a.C; col += 32) {
+            const double xv = xn, con_v = con_n, coff_v = coff_n;
+            if (col + 32 < a.C) {
+                xn = x[col + 32];
+                if (con != nullptr) con_n = con[col + 32];
+                if (use_off) coff_n = coff[col + 32];
+            }
             ChannelData d;
             const double sc = a.ch.scale[col];
             d.on = a.ch.on[col];
             d.gof_on = a.ch.gof_on[col];
-            d.off = d.sigma = d.ratio = d.gof_off = 0.0;
+            d.off = d.sigma = d.ratio = d.gof_off = d.den = 0.0;
             if (STAT == ELISA_STAT_CHI2) d.sigma = a.ch.sigma[col];
-            if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+            if (HAS_OFF) {
                 d.off = a.ch.off[col];
                 d.ratio = a.ch.ratio[col];
             }
             if (STAT == ELISA_STAT_PGSTAT) d.sigma = a.ch.sigma[col];
             if (STAT == ELISA_STAT_WSTAT) d.gof_off = a.ch.gof_off[col];
-            d.den = 0.0;
             if (STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) d.den = a.ch.den[col];
             if (con != nullptr) {
-                d.on = con[col];
+                d.on = con_v;
                 if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
             }
-            if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr) {
-                d.off = coff[col];
+            if (use_off) {
+                d.off = coff_v;
                 if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
             }
             double dx = 0.0;
-            rs += stat_channel<STAT, true>(x[col] * sc, d, dx);
+            rs += stat_channel<STAT, true, false, true>(xv * sc, d, dx);  // FAST: n * (1 / mu) for the two divisions
             eb = fma(fabs(dx * sc), a.colsum[col], eb);
             if (GRAD) {
                 const double w = dx * sc;

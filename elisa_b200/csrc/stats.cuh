@@ -48,10 +48,18 @@ __device__ __forceinline__ double xlogy(double x, double y) { return x == 0.0 ? 
 __device__ __forceinline__ double poisson_gof(double n) { return xlogy(n, n) - n; }
 
 // BetterPoisson.log_prob(n; mu) and d/dmu.
-template <bool GRAD>
+// FAST: n / mu as n * fm::rcp(mu) when mu lies in [1e-290, 1e290] (the clipped model counts always do).
+template <bool GRAD, bool FAST = false>
 __device__ __forceinline__ double poisson_ll(double n, double mu, double gof, double& dmu) {
     const double v = xlogy(n, mu) - mu - gof;
-    if (GRAD) dmu = (v > 0.0) ? 0.0 : (n == 0.0 ? -1.0 : n / mu - 1.0);
+    if (GRAD) {
+        double q;
+        if (FAST && mu > 1e-290 && mu < 1e290)
+            q = fma(n, fm::rcp(mu), -1.0);
+        else
+            q = n / mu - 1.0;
+        dmu = (v > 0.0) ? 0.0 : (n == 0.0 ? -1.0 : q);
+    }
     return v > 0.0 ? 0.0 : v;  // jnp.minimum(v, 0) semantics: NaN propagates (fmin would drop it)
 }
 
@@ -68,7 +76,7 @@ __device__ __forceinline__ double clip_counts(double x, double& pass) {
 // One channel of one statistic.  `x` = source_rate * exposure BEFORE the clip.
 // Returns the channel log-likelihood (on + off terms); `dx` receives d loglike / d x;
 // `m_on`, `m_off`, `l_on`, `l_off` the per-channel sites when SITES.
-template <int STAT, bool GRAD, bool SITES = false>
+template <int STAT, bool GRAD, bool SITES = false, bool FAST = false>
 __device__ __forceinline__ double stat_channel(double x, const ChannelData& d, double& dx, double* site = nullptr) {
     double pass, ll;
     if constexpr (STAT == ELISA_STAT_CHI2) {
@@ -81,13 +89,13 @@ __device__ __forceinline__ double stat_channel(double x, const ChannelData& d, d
     } else if constexpr (STAT == ELISA_STAT_CSTAT) {
         const double s = clip_counts(x, pass);
         double dmu;
-        ll = poisson_ll<GRAD>(d.on, s, d.gof_on, dmu);
+        ll = poisson_ll<GRAD, FAST>(d.on, s, d.gof_on, dmu);
         if (GRAD) dx = dmu * pass;
         if (SITES) { site[0] = s; site[1] = ll; }
     } else if constexpr (STAT == ELISA_STAT_PSTAT) {
         const double mu = clip_counts(x + d.ratio * d.off, pass);  // likelihood.py:301-302
         double dmu;
-        ll = poisson_ll<GRAD>(d.on, mu, d.gof_on, dmu);
+        ll = poisson_ll<GRAD, FAST>(d.on, mu, d.gof_on, dmu);
         if (GRAD) dx = dmu * pass;
         if (SITES) { site[0] = mu; site[1] = ll; }
     } else if constexpr (STAT == ELISA_STAT_PGSTAT) {
@@ -118,7 +126,7 @@ __device__ __forceinline__ double stat_channel(double x, const ChannelData& d, d
         }
         const double mu = s + a * b;
         double dmu;
-        const double l_on = poisson_ll<GRAD>(n, mu, d.gof_on, dmu);
+        const double l_on = poisson_ll<GRAD, FAST>(n, mu, d.gof_on, dmu);
         const double inv = 1.0 / d.sigma;
         const double z = (d.off - b) * inv;
         const double l_off = -0.5 * z * z;
@@ -154,8 +162,8 @@ __device__ __forceinline__ double stat_channel(double x, const ChannelData& d, d
         }
         const double mu = s + a * b;
         double dmu, dmb;
-        const double l_on = poisson_ll<GRAD>(n_on, mu, d.gof_on, dmu);
-        const double l_off = poisson_ll<GRAD>(n_off, b, d.gof_off, dmb);
+        const double l_on = poisson_ll<GRAD, FAST>(n_on, mu, d.gof_on, dmu);
+        const double l_off = poisson_ll<GRAD, FAST>(n_off, b, d.gof_off, dmb);
         ll = l_on + l_off;
         if (GRAD) dx = (dmu * (1.0 + a * db) + dmb * db) * pass;
         if (SITES) { site[0] = mu; site[1] = l_on; site[2] = b; site[3] = l_off; }

@@ -267,4 +267,156 @@ __device__ __forceinline__ void unfold_contract_generic(const UnfoldCore& a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Gradient by contraction on EDGES.  For a model that is a plain sum of leaves whose bin value is
+// LINEAR in two neighbouring edge values --
+//   trapezoid continuum leaves:  u_e = 0.5 (E_{e+1} - E_e) (g(E_e) + g(E_{e+1})),
+//   antiderivative leaves:       u_e = h(E_{e+1}) - h(E_e)           (Comp::EDGE_DIFF, the power law)
+// -- the contraction  grad_j = sum_e G_e du_e/dtheta_j  is re-ordered into a sum over edges,
+//   grad_j = sum_k w_k dg(E_k)/dtheta_j,   w_k = 0.5 (G_{k-1} dE_{k-1} + G_k dE_k)   (trapezoid)
+//                                          w_k = G_{k-1} - G_k                       (difference),
+// so the tangents are never shuffled between lanes (one shuffle of the weight instead of one per
+// tangent), and components with closed-form tangents (Comp::basis / Comp::finish: dg/dp_q =
+// sum_i M_qi b_i(E) with M constant along the energy axis) accumulate S_i = sum_k w_k b_i(E_k) and
+// apply M once per row -- no dual arithmetic, no structurally zero multiply-adds.  Components
+// without a closed form are evaluated in Dual<NP> on the edge and contribute b_q = dg/dp_q.
+// The clip of the unfolded model (likelihood.py:204) passes no derivative: the bin value is formed
+// from the edge values for that test alone.
+template <bool B, class X, class Y>
+struct Cond {
+    using type = X;
+};
+template <class X, class Y>
+struct Cond<false, X, Y> {
+    using type = Y;
+};
+template <class C, class = void>
+struct HasBasis {
+    static constexpr bool value = false;
+    static constexpr int NB = C::NP;
+};
+template <class C>
+struct HasBasis<C, decltype((void)C::NB)> {
+    static constexpr bool value = true;
+    static constexpr int NB = C::NB;
+};
+template <class C, class = void>
+struct IsEdgeDiff {
+    static constexpr bool value = false;
+};
+template <class C>
+struct IsEdgeDiff<C, decltype((void)C::EDGE_DIFF)> {
+    static constexpr bool value = true;
+};
+
+template <int KIND>
+struct EdgeLeaf {
+    using C = Comp<KIND>;
+    static constexpr bool CLOSED = HasBasis<C>::value;
+    static constexpr bool DIFF = IsEdgeDiff<C>::value;
+    static constexpr int NP = C::NP, NC = C::NC, NB = HasBasis<C>::NB;
+    static_assert(CLOSED || (C::RULE == RULE_CONTINUUM_ADD && C::NG == 1), "edge contraction: unsupported component");
+    using T = typename Cond<CLOSED, double, Dual<NP>>::type;
+    struct Pre {
+        T p[NP];
+        T c[NC];
+    };
+    __device__ __forceinline__ static void pre(const double* val, const double* aux, Pre& s) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) s.p[k] = Flat<T>::seed(val[k], k);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) s.c[k] = Flat<T>::seed(0.0, -1);
+        C::pre(s.p, aux, s.c);
+    }
+    __device__ __forceinline__ static void edge(const Pre& s, double E, double lnE, double& v, double* b) {
+        if constexpr (CLOSED) {
+            C::basis(s.p, s.c, E, lnE, v, b);
+        } else {
+            T g[1];
+            C::edge(s.p, s.c, E, lnE, g);
+            v = g[0].v;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) b[q] = g[0].d[q];
+        }
+    }
+    __device__ __forceinline__ static void finish(const Pre& s, const double* S, double* d) {
+        if constexpr (CLOSED) {
+            C::finish(s.p, s.c, S, d);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) d[q] = S[q];
+        }
+    }
+};
+
+// Model (generated, ModelE): Pre, pre(theta, Pre&), NACC accumulators of which bit i of DMASK marks the
+// difference-weighted ones, HAS_T / HAS_D, edge(pre, gv, E, lnE, vT, vD, b), finish(pre, S, grad[NPAR]).
+template <class Model>
+__device__ __forceinline__ void unfold_contract_edges(const UnfoldCore& a) {
+    constexpr int NA = Model::NACC;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int row = (int)((int64_t)blockIdx.x * UNFOLD_WARPS + wib);
+    if (row >= a.n_valid) return;
+    const int E = a.gv.E;
+    typename Model::Pre pre;
+    Model::pre(a.theta + (size_t)row * a.P, pre);
+    const double* g_row = a.G + (size_t)row * a.ldg;
+    double nE = a.gv.egrid[min(lane, E)], nl = a.gv.lngrid[min(lane, E)];
+    double ng = (lane < 31 && lane < E) ? g_row[lane] : 0.0;
+    double acc[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+    for (int e0 = 0; e0 < E; e0 += 31) {
+        const int e = e0 + lane;
+        const double pE = nE, pl = nl, g = ng;
+        if (e0 + 31 < E) {  // the next pass's edge and weight, loaded under this pass's arithmetic
+            const int ec = min(e + 31, E);
+            nE = a.gv.egrid[ec];
+            nl = a.gv.lngrid[ec];
+            ng = (lane < 31 && e + 31 < E) ? g_row[e + 31] : 0.0;
+        }
+        double vT = 0.0, vD = 0.0, b[NA];
+        Model::edge(pre, a.gv, pE, pl, vT, vD, b);
+        const double hd = 0.5 * (__shfl_down_sync(0xffffffffu, pE, 1) - pE);
+        double u = 0.0;
+        if constexpr (Model::HAS_T) u = hd * (vT + __shfl_down_sync(0xffffffffu, vT, 1));
+        if constexpr (Model::HAS_D) u += __shfl_down_sync(0xffffffffu, vD, 1) - vD;
+        // lane 31 and lanes past the grid hold no bin (g = 0); a clipped bin passes no derivative: its
+        // weight is g * 0 -- zero, and a zero weight skips the accumulation, so that 0 * inf of an
+        // overflowing tangent does not reach the sum, while a NaN in G (a NaN parameter vector makes
+        // the bin NaN, which fails the clip test too) stays NaN and does
+        const bool pass = !(a.clip && !(u >= 1e-300 && u <= 1e300));
+        const double gg = g * (pass ? 1.0 : 0.0);
+        double wT = 0.0, wD = 0.0;
+        if constexpr (Model::HAS_T) {
+            const double gt = gg * hd;
+            const double up = __shfl_up_sync(0xffffffffu, gt, 1);
+            wT = lane ? gt + up : gt;
+        }
+        if constexpr (Model::HAS_D) {
+            const double up = __shfl_up_sync(0xffffffffu, gg, 1);
+            wD = lane ? up - gg : -gg;
+        }
+        if (Model::HAS_T && wT != 0.0) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                if (!((Model::DMASK >> i) & 1u)) acc[i] = fma(wT, b[i], acc[i]);
+        }
+        if (Model::HAS_D && wD != 0.0) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i)
+                if ((Model::DMASK >> i) & 1u) acc[i] = fma(wD, b[i], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = warp_sum(acc[i]);
+    double grad[Model::NPAR];
+    Model::finish(pre, acc, grad);
+    double* out = a.grad_out + (size_t)row * a.grad_stride;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < Model::NPAR; ++j) out[j] = grad[j];
+    }
+}
+
 }  // namespace elisa
