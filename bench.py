@@ -412,7 +412,9 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
         out['cfg3'] = {'what': 'Band pgstat, 4 detectors 128ch x 140E, 64 chains over %d GPU(s): one leapfrog = one value+gradient '
                                'call through the Python API (guard=lazy: no host synchronisation, CUDA graph replayed)' % world,
                        'chains_per_gpu': hi - lo, 'us_per_leapfrog': float(t.item()), 'us_per_leapfrog_with_gather': us_gather,
-                       'evals_s': 64 * 4 / ((us_gather or float(t.item())) * 1e-6), 'engine': engine(lk),
+                       'evals_s': 64 * 4 / ((us_gather or float(t.item())) * 1e-6),
+                       'engine': ('one kernel per detector (dual-number model + FP64 forward-mode fold + statistic + gradient, '
+                                  'tiny_eval)' if all(lk.small_batch_kernel) else engine(lk)),
                        'parity': parity_of(cfg, lk_sync, 64)}
         lk_sync.close()
     lk.close()

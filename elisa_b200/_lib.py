@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ELISA_B200_LIB: another build of the library (A/B runs of kernel variants, tools/ab_lib.sh)
 LIB_PATH = os.environ.get('ELISA_B200_LIB') or os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_COMP_PARAMS = 5
 MAX_COMPONENTS = 16
 MAX_PARAMS = 32
@@ -23,6 +23,7 @@ FLAG_REQUIRE_JIT = 2
 FLAG_FOLD_DMMA = 4
 FLAG_FOLD_I8 = 8
 FLAG_NO_BALANCE = 16
+FLAG_NO_SMALL_BATCH_KERNEL = 32
 FLAG_FOLD_SLICES_SHIFT = 8
 FLAG_FOLD_SLICES_BWD_SHIFT = 12
 METHOD = {'trapz': 0, 'simpson': 1}
@@ -140,6 +141,7 @@ SYMBOLS = {
     'elisa_b200_sample_dev': (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, C.c_int64, C.c_uint64, _VP, C.c_int64, _VP]),
     'elisa_b200_csr_fold_dev': (C.c_int, [_VP, C.c_int32, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, _VP]),
     'elisa_b200_plan_fold_slices_bwd': (C.c_int, [_VP, C.c_int32]),
+    'elisa_b200_plan_small_batch_kernel': (C.c_int, [_VP, C.c_int32]),
     'elisa_b200_plan_fold_products': (C.c_int, [_VP, C.c_int32, c_double_p]),
     'elisa_b200_abi_version': (C.c_int, []),
     'elisa_b200_sizeof': (C.c_int64, [C.c_int32]),

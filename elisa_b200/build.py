@@ -20,6 +20,7 @@ EMBED = {
     'embedded_unfold_skel_cuh.inc': os.path.join(HERE, 'csrc', 'unfold_skel.cuh'),
     'embedded_slice_i8_cuh.inc': os.path.join(HERE, 'csrc', 'slice_i8.cuh'),
     'embedded_fastmath_cuh.inc': os.path.join(HERE, 'csrc', 'fastmath.cuh'),
+    'embedded_stats_cuh.inc': os.path.join(HERE, 'csrc', 'stats.cuh'),
 }
 LIB = os.path.join(HERE, 'lib', 'libelisa_b200.so')
 

@@ -820,6 +820,9 @@ struct SpectrumPlan {
     int32_t *csr_ptr = nullptr, *csr_idx = nullptr;
     double* csr_val = nullptr;
     double fill = 1.0;  // stored fraction of the packed response operands
+    // small spectra: the dense response [E, C] for the one-kernel small-batch path (tiny_eval, unfold_skel.cuh);
+    // nullptr: the spectrum does not qualify (see tiny_shape_ok)
+    double* tiny_R = nullptr;
     // balancing of the integer folds' contraction indices (col_envelope_kernel): power-of-two
     // envelopes of U over the energies / of W over the channels, and their reciprocals
     double *t_scale = nullptr, *t_inv = nullptr, *r_scale = nullptr, *r_inv = nullptr;
@@ -916,6 +919,11 @@ struct ElisaPlan {
     std::vector<cudaEvent_t> small_done;
     cudaEvent_t small_fork = nullptr;
     int sm_count = 148;
+    // one-kernel path for small batches of small spectra (tiny_eval): the decision is taken per CALL
+    // (tiny_call_n >= 0: rows of the whole call when it is evaluated in pieces), so that re-chunking a
+    // batch never changes which kernels compute a row
+    bool tiny_enabled = true, tiny_now = false;
+    int64_t tiny_call_n = -1;
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
     // host-path staging (device side), grown on demand: theta / loglike / grad for the whole call,
@@ -1127,6 +1135,20 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
     return ELISA_OK;
 }
 
+// Shapes the one-kernel small-batch path takes: every thread folds whole response columns in FP64 with
+// 1 + (free parameters) accumulators, u and du/dtheta of one parameter vector sit in shared memory.
+constexpr int64_t TINY_MAX_N = 1024;          // rows per call
+constexpr int64_t TINY_MAX_WORK = 1 << 18;    // E * C * (1 + used parameters) per row
+static int popcount32(uint32_t v) {
+    int n = 0;
+    for (; v; v &= v - 1) ++n;
+    return n;
+}
+static size_t tiny_smem_bytes(int E, int P) { return ((size_t)(1 + P) * E + (size_t)(TINY_THREADS / 32) * (1 + P)) * 8; }
+static bool tiny_shape_ok(int E, int C, int P, uint32_t used_mask) {
+    return P <= 8 && (int64_t)E * C * (1 + popcount32(used_mask)) <= TINY_MAX_WORK && tiny_smem_bytes(E, P) <= 48 * 1024;
+}
+
 static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, SpectrumPlan* sp) {
     const int E = sd.n_energies, C = sd.n_channels;
     if (E < 1 || C < 1) return fail(ELISA_ERR_INVALID, "spectrum: empty energy grid or channel set");
@@ -1331,6 +1353,16 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
     }
     if ((rc = upload_packed(plan, fwd, &sp->fwd))) return rc;
     if ((rc = upload_packed(plan, bwd, &sp->bwd))) return rc;
+    if (plan->tiny_enabled && tiny_shape_ok(E, C, plan->P, sp->model.used_mask)) {
+        std::vector<double> Rd((size_t)E * C, 0.0);
+        if (dense) {
+            std::copy(sd.response_dense, sd.response_dense + (size_t)E * C, Rd.begin());
+        } else {
+            for (int c = 0; c < C; ++c)
+                for (int i = sd.csr_indptr[c]; i < sd.csr_indptr[c + 1]; ++i) Rd[(size_t)sd.csr_indices[i] * C + c] += sd.csr_values[i];
+        }
+        if ((rc = upload(plan, Rd, &sp->tiny_R))) return rc;
+    }
     {  // CSR by channel row for the row-wise sparse fold
         std::vector<int32_t> ptr(C + 1, 0), idx;
         std::vector<double> val;
@@ -1374,6 +1406,7 @@ static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spectrum
 struct JitKernels {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t val = nullptr, grad = nullptr, contract = nullptr;
+    cudaKernel_t tiny = nullptr;  // one-kernel small-batch evaluation (only in translation units generated with a statistic)
 };
 
 static const char* const k_src_elisa_h =
@@ -1393,6 +1426,9 @@ static const char* const k_src_slice =
     ;
 static const char* const k_src_fastmath =
 #include "embedded_fastmath_cuh.inc"
+    ;
+static const char* const k_src_stats =
+#include "embedded_stats_cuh.inc"
     ;
 
 struct NvrtcApi {
@@ -1710,7 +1746,8 @@ static std::string generate_edge_model(const ModelDev& m, int P) {
     return s;
 }
 
-static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
+// tiny_stat >= 0: also instantiate the one-kernel small-batch evaluation (tiny_eval) for that statistic
+static std::string generate_unfold_source(const ModelDev& m, int P, int ks, int tiny_stat = -1) {
     std::string s;
     {
         const char* env = getenv("ELISA_B200_UNFOLD_MIN_BLOCKS");  // occupancy experiments
@@ -1737,6 +1774,9 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks) {
     else
         s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
              "unfold_contract_generic<ModelG, Dual<" + std::to_string(P) + ">>(a); }\n";
+    if (tiny_stat >= 0)
+        s += "extern \"C\" __global__ void __launch_bounds__(TINY_THREADS) tiny_eval_kernel(const TinyArgs t) { tiny_eval<ModelG, " +
+             std::to_string(P) + ", " + std::to_string(tiny_stat) + ">(t); }\n";
     return s;
 }
 
@@ -1747,10 +1787,10 @@ static bool compile_unfold_source(const std::string& src, std::vector<char>* cub
         *why = "libnvrtc.so.12 not found";
         return false;
     }
-    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h, k_src_slice, k_src_fastmath};
-    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h", "slice_i8.cuh", "fastmath.cuh"};
+    const char* headers[] = {k_src_skel, k_src_components, k_src_dual, k_src_elisa_h, k_src_slice, k_src_fastmath, k_src_stats};
+    const char* names[] = {"unfold_skel.cuh", "components.cuh", "dual.cuh", "elisa_b200.h", "slice_i8.cuh", "fastmath.cuh", "stats.cuh"};
     nvrtcProgram prog = nullptr;
-    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 6, headers, names) != NVRTC_SUCCESS) {
+    if (api.create(&prog, src.c_str(), "elisa_unfold_jit.cu", 7, headers, names) != NVRTC_SUCCESS) {
         *why = "nvrtcCreateProgram failed";
         return false;
     }
@@ -1781,10 +1821,10 @@ static bool compile_unfold_source(const std::string& src, std::vector<char>* cub
 
 // Compile (or fetch from the in-process cache) the specialised kernels of one model.
 // Returns nullptr with `why` set when runtime compilation is not possible.
-static const JitKernels* jit_unfold(const ModelDev& m, int P, int ks, std::string* why) {
+static const JitKernels* jit_unfold(const ModelDev& m, int P, int ks, std::string* why, int tiny_stat = -1) {
     static std::mutex mu;
     static std::map<std::string, JitKernels*> cache;
-    const std::string src = generate_unfold_source(m, P, ks);
+    const std::string src = generate_unfold_source(m, P, ks, tiny_stat);
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(src);
     if (it != cache.end()) return it->second;
@@ -1795,6 +1835,7 @@ static const JitKernels* jit_unfold(const ModelDev& m, int P, int ks, std::strin
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->val, k->lib, "unfold_val");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->grad, k->lib, "unfold_grad");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->contract, k->lib, "unfold_contract");
+    if (e == cudaSuccess && tiny_stat >= 0) e = cudaLibraryGetKernel(&k->tiny, k->lib, "tiny_eval_kernel");
     if (e != cudaSuccess) {
         *why = std::string("loading the compiled unfold kernels failed: ") + cudaGetErrorString(e);
         delete k;
@@ -2384,9 +2425,50 @@ static int build_spectrum_i8(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spect
 }
 
 // One (chunk, spectrum) pass.  theta/on/off/loglike/grad already point at the chunk's first row.
+// One kernel per spectrum for a small batch of a small spectrum (tiny_eval, unfold_skel.cuh): one CTA per row.
+static int launch_tiny(ElisaPlan* plan, const SpectrumPlan& sp, int s, const double* theta, const double* on,
+                       const double* off, int n, double* loglike, double* grad, cudaStream_t st) {
+    TinyArgs t;
+    memset(&t, 0, sizeof t);
+    UnfoldCore& a = t.core;
+    a.gv = sp.grid_view();
+    a.gv.has_point = 0;
+    a.theta = theta;
+    a.P = plan->P;
+    a.n_valid = n;
+    a.n_rows = n;
+    a.n_seg = 1;
+    a.clip = 1;
+    a.used_mask = sp.model.used_mask;
+    for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
+        a.ngv[k] = sp.norm_view(k);
+        a.ngv[k].has_point = 0;
+        a.nw[k] = sp.norm_grid[k].w;
+    }
+    a.grad_out = grad ? grad + (size_t)s * plan->P : nullptr;
+    a.grad_stride = (int64_t)plan->S * plan->P;
+    t.R = sp.tiny_R;
+    t.ldr = sp.C;
+    t.C = sp.C;
+    t.ch = sp.chan_view();
+    t.counts_on = on ? on + sp.counts_off : nullptr;
+    t.counts_off = off ? off + sp.counts_off : nullptr;
+    t.ld_counts = plan->sum_C;
+    t.loglike = loglike + s;
+    t.ll_stride = plan->S;
+    ScopedSpan span(plan, ELISA_PROFILE_TINY, st);
+    void* kargs[] = {(void*)&t};
+    CUDA_TRY(cudaLaunchKernel((const void*)sp.jit->tiny, dim3(n), dim3(TINY_THREADS), kargs, tiny_smem_bytes(sp.E, plan->P), st));
+    ++plan->launches;
+    return ELISA_OK;
+}
+
 static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off, int n,
                      double* loglike, double* grad, cudaStream_t st) {
     const SpectrumPlan& sp = plan->spec[s];
+    if (plan->tiny_now && sp.tiny_R != nullptr && sp.jit != nullptr && sp.jit->tiny != nullptr && !plan->force_dmma &&
+        !plan->debug_skip)
+        return launch_tiny(plan, sp, s, theta, on, off, n, loglike, grad, st);
     const int n_rows = round_up(n, GEMM_BM);
     const int m_tiles = n_rows / GEMM_BM;
     const bool want_grad = grad != nullptr;
@@ -2685,6 +2767,16 @@ static int ensure_balanced(ElisaPlan* plan, const double* theta, const double* o
     return ELISA_OK;
 }
 
+// Sets plan->tiny_now for a call of n rows (tiny_call_n rows when the call is evaluated in pieces) and tells
+// whether EVERY spectrum then takes the one-kernel path.
+static bool decide_tiny(ElisaPlan* plan, int64_t n) {
+    plan->tiny_now = plan->tiny_enabled && (plan->tiny_call_n >= 0 ? plan->tiny_call_n : n) <= TINY_MAX_N;
+    bool all_tiny = plan->tiny_now && !plan->force_dmma && !plan->debug_skip;
+    for (int s = 0; s < plan->S && all_tiny; ++s)
+        all_tiny = plan->spec[s].tiny_R != nullptr && plan->spec[s].jit != nullptr && plan->spec[s].jit->tiny != nullptr;
+    return all_tiny;
+}
+
 static int run_all(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                    double* loglike, double* grad, cudaStream_t st) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
@@ -2694,7 +2786,8 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
     int dev;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
-    int rc = ensure_balanced(plan, theta, on, off, n, st);
+    // the integer folds need their envelopes only when some spectrum of this call runs through them
+    int rc = decide_tiny(plan, n) ? ELISA_OK : ensure_balanced(plan, theta, on, off, n, st);
     const int64_t base = plan->row_base;  // global index of row 0 of this call (host path: of the piece)
     for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
         const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
@@ -2732,7 +2825,7 @@ static int run_small(ElisaPlan* plan, const double* theta, const double* on, con
                           n <= plan->chunk && on == nullptr && off == nullptr && theta != nullptr && loglike != nullptr &&
                           plan->g_theta != nullptr;
     if (!eligible) return run_all(plan, theta, on, off, n, loglike, grad, st);
-    {  // envelopes of the balanced integer fold: (re)derived outside any capture, on the caller's stream
+    if (!decide_tiny(plan, n)) {  // envelopes of the balanced integer fold: (re)derived outside any capture, on the caller's stream
         int dev;
         CUDA_TRY(cudaGetDevice(&dev));
         if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
@@ -3019,9 +3112,11 @@ static int host_call(ElisaPlan* plan, const double* theta, const double* on, con
         if (rc == ELISA_OK) CUDA_TRY(cudaStreamSynchronize(st));
         return rc;
     };
+    plan->tiny_call_n = n;  // pieces of one call take the same kernels
     int rc = run_guarded(plan, n, st, eval_all, [&](const std::vector<int32_t>& rows) {
         return rerun_rows_dmma(plan, rows, plan->h_theta, on, off, true, plan->h_ll, g_dev, st);
     });
+    plan->tiny_call_n = -1;
     if (rc == ELISA_OK) {
         CUDA_TRY(cudaMemcpyAsync(loglike, plan->h_ll, (size_t)n * S * 8, cudaMemcpyDeviceToHost, st));
         if (grad) CUDA_TRY(cudaMemcpyAsync(grad, plan->h_grad, (size_t)n * S * P * 8, cudaMemcpyDeviceToHost, st));
@@ -3140,6 +3235,9 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         plan->ks = dmma ? 0 : ks;
         plan->ks_bwd = dmma ? 0 : ks_bwd;
         plan->guard_off = force_i8;
+        // one-kernel small-batch path: off when a fold engine was asked for by name, or by flag / environment
+        plan->tiny_enabled = !(desc->flags & (ELISA_FLAG_NO_SMALL_BATCH_KERNEL | ELISA_FLAG_FOLD_I8 | ELISA_FLAG_FOLD_DMMA)) && !dmma && !force_i8;
+        if (const char* env = getenv("ELISA_B200_TINY")) plan->tiny_enabled = plan->tiny_enabled && strcmp(env, "0") != 0;
         cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
         if (plan->sm_count < 1) plan->sm_count = 148;
     }
@@ -3151,7 +3249,8 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         const bool off = (desc->flags & ELISA_FLAG_NO_JIT) || (env && strcmp(env, "0") == 0);
         if (!off) {
             std::string why;
-            plan->spec[s].jit = jit_unfold(plan->spec[s].model, plan->P, plan->ks, &why);
+            plan->spec[s].jit = jit_unfold(plan->spec[s].model, plan->P, plan->ks, &why,
+                                           plan->spec[s].tiny_R != nullptr ? plan->spec[s].stat : -1);
             if (plan->spec[s].jit == nullptr && ((desc->flags & ELISA_FLAG_REQUIRE_JIT) || (env && strcmp(env, "require") == 0))) {
                 rc = fail(ELISA_ERR_UNSUPPORTED, "runtime specialisation required but unavailable: " + why);
                 break;
@@ -3534,7 +3633,9 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
     ModelDev m;
     int rc = build_model(*model, n_params, &m);
     if (rc) return rc;
-    const std::string src = generate_unfold_source(m, n_params, ELISA_FOLD_SLICES_DEFAULT);
+    // ELISA_B200_SPECIALISE_TINY=<statistic>: include the one-kernel small-batch evaluation (offline SASS, tests)
+    const char* tiny = getenv("ELISA_B200_SPECIALISE_TINY");
+    const std::string src = generate_unfold_source(m, n_params, ELISA_FOLD_SLICES_DEFAULT, tiny ? atoi(tiny) : -1);
     if (source_out != nullptr && source_cap > 0) {
         const size_t n = std::min<size_t>(src.size(), (size_t)source_cap - 1);
         memcpy(source_out, src.data(), n);
@@ -3579,6 +3680,11 @@ int elisa_b200_plan_fold_products(ElisaPlan* plan, int32_t spectrum, double out[
     return ELISA_OK;
 }
 
+int elisa_b200_plan_small_batch_kernel(const ElisaPlan* plan, int32_t spectrum) {
+    if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
+    const SpectrumPlan& sp = plan->spec[spectrum];
+    return plan->tiny_enabled && sp.tiny_R != nullptr && sp.jit != nullptr && sp.jit->tiny != nullptr ? 1 : 0;
+}
 int elisa_b200_plan_fold_slices_bwd(const ElisaPlan* plan, int32_t spectrum) {
     if (plan == nullptr || spectrum < 0 || spectrum >= plan->S) return -1;
     return plan->spec[spectrum].use_i8() ? plan->ks_bwd : 0;

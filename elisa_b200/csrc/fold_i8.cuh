@@ -747,17 +747,6 @@ struct I8EpilogueStore {
 };
 
 // per-channel observed data, padded to C_pad with benign values (shared with the DMMA path)
-struct ChanArrays {
-    const double* scale;  // area_scale * exposure
-    const double* on;
-    const double* off;
-    const double* sigma;
-    const double* ratio;
-    const double* gof_on;
-    const double* gof_off;
-    const double* den;  // stat_den(ratio)
-};
-
 // transposed fold: G[n, e] contracted with dU/dtheta_j[n, e] over the tile's energies.
 // Per tile and parameter a thread multiplies its 4 rows x 4 columns, the quad adds up each row
 // (a transposing butterfly), and thread q keeps the sum of row row0 + 8 i8_quad_row(q).

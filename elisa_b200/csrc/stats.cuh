@@ -7,7 +7,7 @@
 // same derivatives written out, verified against torch autograd
 // of the oracle in tests/.
 #pragma once
-#include "../../include/elisa_b200.h"
+#include "elisa_b200.h"
 #include "fastmath.cuh"
 
 namespace elisa {
@@ -20,6 +20,18 @@ struct ChannelData {
     double gof_on;   // xlogy(on, on) - on     (saturated-model offset, likelihood.py:172)
     double gof_off;  // xlogy(off, off) - off
     double den;      // stat_den(ratio): 1 / (2 a (a + 1)) for wstat, 1 / (2 a) for pgstat -- per channel, not per row
+};
+
+// per-channel constants of one spectrum as the kernels see them (arrays of C_pad doubles)
+struct ChanArrays {
+    const double* scale;  // area_scale * exposure
+    const double* on;
+    const double* off;
+    const double* sigma;
+    const double* ratio;
+    const double* gof_on;
+    const double* gof_off;
+    const double* den;  // stat_den(ratio)
 };
 
 template <int STAT>

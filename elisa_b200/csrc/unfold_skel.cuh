@@ -15,6 +15,7 @@
 #pragma once
 #include "components.cuh"
 #include "slice_i8.cuh"
+#include "stats.cuh"
 
 namespace elisa {
 
@@ -416,6 +417,142 @@ __device__ __forceinline__ void unfold_contract_edges(const UnfoldCore& a) {
     if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < Model::NPAR; ++j) out[j] = grad[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Small batches in ONE kernel (NUTS chains, a handful of walkers: BASELINE configs[2]).
+// The chunk pipeline is five dependent launches per spectrum -- unfold, fold, statistic + digits,
+// transposed fold, contraction -- each ~10 us at 64 rows, bound by launch and tail latency, not by
+// work.  For a small spectrum the whole evaluation of one parameter vector fits one CTA:
+//   1. the warps evaluate the model in dual numbers, u_e and du_e/dtheta_j into shared memory;
+//   2. thread c folds its channel in FP64, x_c = sum_e R[e, c] u_e and t_jc = sum_e R[e, c] du_e/dtheta_j
+//      (forward mode: (1 + P) FMAs per response element, read coalesced from L2);
+//   3. the statistic of the channel gives l_c and w_c = dl/dx_c; loglike = sum_c l_c and
+//      grad_j = sum_c w_c t_jc are reduced in a fixed order (lane-serial, xor tree, warps in order).
+// Plain FP64 FMAs: no digit slicing, no accuracy guard needed.  One CTA per (parameter vector);
+// the host launches it per spectrum (own branch of the captured graph).
+struct TinyArgs {
+    UnfoldCore core;   // theta, P, n_valid, gv, norms, clip; grad_out / grad_stride (nullptr: value only)
+    const double* R;   // [E, ldr] dense response, row = energy bin
+    int32_t ldr, C;
+    ChanArrays ch;
+    const double* counts_on;   // per-row counts of this spectrum (nullptr: the plan's)
+    const double* counts_off;
+    int64_t ld_counts;
+    double* loglike;   // element [row * ll_stride]
+    int64_t ll_stride;
+};
+
+constexpr int TINY_THREADS = 128;
+
+template <class Model, int NP, int STAT>
+__device__ __forceinline__ void tiny_eval(const TinyArgs& t) {
+    using T = Dual<NP>;
+    extern __shared__ double tiny_smem[];
+    const UnfoldCore& a = t.core;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int row = blockIdx.x;
+    if (row >= a.n_valid) return;
+    const int E = a.gv.E;
+    const bool want_grad = a.grad_out != nullptr;
+#ifdef UNFOLD_USED_MASK
+    constexpr uint32_t used = UNFOLD_USED_MASK;
+#else
+    const uint32_t used = a.used_mask;
+#endif
+    double* su = tiny_smem;              // [E]
+    double* sd = tiny_smem + E;          // [NP][E]
+    double* red = tiny_smem + (size_t)(1 + NP) * E;  // [TINY_THREADS / 32][1 + NP]
+    // 1. the model in dual numbers; warp w takes the passes w, w + 4, ...
+    {
+        typename Model::Pre pre;
+        Model::pre(a.theta + (size_t)row * a.P, pre);
+        Model::norms(pre, a, a.theta + (size_t)row * a.P, lane);
+        GridView gv = a.gv;
+        gv.has_point = 0;
+        for (int e0 = 31 * wib; e0 < E; e0 += 31 * (TINY_THREADS / 32)) {
+            const int e = e0 + lane;
+            const T res = Model::bin(pre, gv, e);
+            if (lane < 31 && e < E) {
+                const double v = res.v;
+                const bool pass = !(a.clip && !(v >= 1e-300 && v <= 1e300));
+                su[e] = pass ? v : (v < 1e-300 ? 1e-300 : (v > 1e300 ? 1e300 : v));  // jnp.clip propagates NaN
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    if ((used >> j) & 1u) sd[(size_t)j * E + e] = pass ? res.d[j] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    // 2 + 3. fold and statistic of the thread's channels
+    double ll = 0.0, g[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) g[j] = 0.0;
+    const double* con = t.counts_on ? t.counts_on + (size_t)row * t.ld_counts : nullptr;
+    const double* coff = t.counts_off ? t.counts_off + (size_t)row * t.ld_counts : nullptr;
+    for (int c = tid; c < t.C; c += TINY_THREADS) {
+        double x = 0.0, tj[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) tj[j] = 0.0;
+        const double* r = t.R + c;
+        if (want_grad) {
+            for (int e = 0; e < E; ++e) {
+                const double rv = r[(size_t)e * t.ldr];
+                x = fma(rv, su[e], x);
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    if ((used >> j) & 1u) tj[j] = fma(rv, sd[(size_t)j * E + e], tj[j]);
+            }
+        } else {
+            for (int e = 0; e < E; ++e) x = fma(r[(size_t)e * t.ldr], su[e], x);
+        }
+        ChannelData d;
+        const double sc = t.ch.scale[c];
+        d.on = t.ch.on[c];
+        d.gof_on = t.ch.gof_on[c];
+        d.off = d.sigma = d.ratio = d.gof_off = d.den = 0.0;
+        if (STAT == ELISA_STAT_CHI2) d.sigma = t.ch.sigma[c];
+        if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+            d.off = t.ch.off[c];
+            d.ratio = t.ch.ratio[c];
+        }
+        if (STAT == ELISA_STAT_PGSTAT) d.sigma = t.ch.sigma[c];
+        if (STAT == ELISA_STAT_WSTAT) d.gof_off = t.ch.gof_off[c];
+        if (STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) d.den = t.ch.den[c];
+        if (con != nullptr) {
+            d.on = con[c];
+            if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
+        }
+        if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr) {
+            d.off = coff[c];
+            if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
+        }
+        double dx = 0.0;
+        ll += stat_channel<STAT, true>(x * sc, d, dx);
+        const double w = dx * sc;
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+            if ((used >> j) & 1u) g[j] = fma(w, tj[j], g[j]);
+    }
+    ll = warp_sum(ll);
+    if (lane == 0) red[wib * (1 + NP)] = ll;
+    if (want_grad) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const double s = ((used >> j) & 1u) ? warp_sum(g[j]) : 0.0;
+            if (lane == 0) red[wib * (1 + NP) + 1 + j] = s;
+        }
+    }
+    __syncthreads();
+    if (tid <= NP && (tid == 0 || want_grad)) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TINY_THREADS / 32; ++w) s += red[w * (1 + NP) + tid];
+        if (tid == 0)
+            t.loglike[(size_t)row * t.ll_stride] = s;
+        else if (tid - 1 < a.P)
+            a.grad_out[(size_t)row * a.grad_stride + tid - 1] = s;
     }
 }
 

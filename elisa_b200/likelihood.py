@@ -37,6 +37,9 @@ def _dev_ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_SMALL_BATCH_ROWS = 1024  # TINY_MAX_N of the library: calls up to this size take the one-kernel path where a spectrum qualifies
+
+
 class GuardTripped(_lib.ElisaB200Error):
     """guard='lazy': the accuracy guard of the integer fold flagged rows of earlier calls."""
 
@@ -69,6 +72,10 @@ class Likelihood:
         memory every ``guard_every`` calls and looked at on the NEXT call -- a flagged snapshot
         raises :class:`GuardTripped` there (callers of a leapfrog loop catch it and repeat the
         trajectory with guard='sync').  'off': never looked at.
+    small_batch : calls of <= 1024 parameter vectors on a small spectrum (E * C * (1 + free parameters)
+        <= 2^18: NUTS chains on GBM-like detectors) are ONE kernel per spectrum in plain FP64 instead of
+        the chunk pipeline (``small_batch_kernel`` tells which spectra qualify); False, or an explicit
+        ``fold``, keeps every call on the pipeline.
 
     ``params_name`` lists the columns of ``theta`` (constrained space; priors and
     transforms stay with the caller, infer/helper.py:409-426).
@@ -76,7 +83,7 @@ class Likelihood:
 
     def __init__(self, data: Sequence[FixedData], model, stat: Sequence[str], device: int | None = None, chunk: int = 0,
                  specialise: bool | None = None, fold: str | None = None, slices: int = 0, balance: bool = True,
-                 slices_bwd: int = 0, guard: str = 'sync', guard_every: int = 16):
+                 slices_bwd: int = 0, guard: str = 'sync', guard_every: int = 16, small_batch: bool = True):
         import torch
 
         if not torch.cuda.is_available():
@@ -157,6 +164,8 @@ class Likelihood:
             raise ValueError("guard must be 'sync', 'lazy' or 'off'")
         if not balance:
             flags |= _lib.FLAG_NO_BALANCE
+        if not small_batch:  # keep calls of <= 1024 rows on the chunk pipeline (see small_batch_kernel)
+            flags |= _lib.FLAG_NO_SMALL_BATCH_KERNEL
         desc = _lib.PlanDesc(_lib.ABI_VERSION, self.device, self._P, len(data), specs, int(chunk), flags)
         handle = C.c_void_p()
         _lib.check(lib.elisa_b200_plan_create(C.byref(desc), C.byref(handle)))
@@ -178,6 +187,7 @@ class Likelihood:
         self.rebalances = 0        # envelope renewals the guard triggered
         self._dev_str = f'cuda:{self.device}'
         self._fb = C.c_int64(0)
+        self._all_small_batch = all(self.small_batch_kernel)
 
     # -- lifetime ------------------------------------------------------------------
     def close(self):
@@ -252,6 +262,12 @@ class Likelihood:
         """Per dataset: digits of the TRANSPOSED fold (gradient side), 0 = FP64 DMMA fold."""
         return [int(self._lib.elisa_b200_plan_fold_slices_bwd(self._h, k)) for k in range(len(self.data))]
 
+    @property
+    def small_batch_kernel(self) -> list[bool]:
+        """Per dataset: calls of <= 1024 parameter vectors evaluate it in ONE kernel (small spectra, the
+        NUTS shape) instead of the chunk pipeline."""
+        return [self._lib.elisa_b200_plan_small_batch_kernel(self._h, k) == 1 for k in range(len(self.data))]
+
     def fold_products(self, k: int = 0):
         """(forward, transposed): int8 digit products the integer fold executes per FP64
         multiply-add of dataset k's dense contraction (``elisa_b200_plan_fold_products``); 21 for 6
@@ -276,7 +292,7 @@ class Likelihood:
     def launch_count(self) -> int:
         return int(self._lib.elisa_b200_plan_launch_count(self._h))
 
-    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice', 'stat', 'contract')
+    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice', 'stat', 'contract', 'tiny')
 
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.elisa_b200_plan_set_profiling(self._h, int(bool(enable))))
@@ -331,6 +347,8 @@ class Likelihood:
             out = torch.empty((n, S), dtype=torch.float64, device=t.device)
             grad = torch.empty((n, S, self._P), dtype=torch.float64, device=t.device) if want_grad else None
             stream = self._stream()
+            if n <= _SMALL_BATCH_ROWS and self._all_small_batch:
+                mode = 'off'  # the one-kernel path is plain FP64: nothing for the guard to watch, no synchronisation
             if mode == 'sync':
                 _lib.check(self._lib.elisa_b200_loglike_grad_guarded_dev(
                     self._h, _dev_ptr(t), _dev_ptr(on), _dev_ptr(off), n, _dev_ptr(out), _dev_ptr(grad), stream,

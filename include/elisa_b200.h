@@ -58,7 +58,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define ELISA_B200_ABI_VERSION 4
+#define ELISA_B200_ABI_VERSION 5
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define ELISA_OK 0
@@ -247,6 +247,11 @@ typedef struct ElisaPlanDesc {
 #define ELISA_FLAG_FOLD_DMMA 4
 #define ELISA_FLAG_FOLD_I8 8
 #define ELISA_FLAG_NO_BALANCE 16 /* integer fold without column balancing (see elisa_b200_plan_rebalance) */
+/* Calls of <= 1024 parameter vectors on a small spectrum (E * C * (1 + free parameters) <= 2^18, <= 8 parameters,
+ * runtime-specialised model) are evaluated by ONE kernel per spectrum in plain FP64 (csrc/unfold_skel.cuh,
+ * tiny_eval) instead of the chunk pipeline; this flag, a fold engine requested by flag or environment, or env
+ * ELISA_B200_TINY=0 switch that off.  elisa_b200_plan_small_batch_kernel() tells what a spectrum got.        */
+#define ELISA_FLAG_NO_SMALL_BATCH_KERNEL 32
 #define ELISA_FLAG_FOLD_SLICES_SHIFT 8
 /* Slices of the TRANSPOSED fold (W . R^T, the gradient side): bits 12-15 of flags (4..7; 0 =
  * default) or env ELISA_B200_FOLD_SLICES_BWD.  The gradient contraction tolerates one digit
@@ -315,7 +320,8 @@ int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const d
 #define ELISA_PROFILE_SLICE 4  /* digit slicing of U and W (sliced-integer fold only)    */
 #define ELISA_PROFILE_STAT 5   /* statistic + digits of W (sliced-integer fold only)       */
 #define ELISA_PROFILE_CONTRACT 6 /* gradient by contraction: tangents recomputed against G (sliced-integer fold only) */
-#define ELISA_PROFILE_CLASSES 7
+#define ELISA_PROFILE_TINY 7   /* one-kernel evaluation of a small batch of a small spectrum (unfold + FP64 fold + statistic + gradient) */
+#define ELISA_PROFILE_CLASSES 8
 int elisa_b200_plan_set_profiling(ElisaPlan* plan, int enable);
 int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches);
 
@@ -334,6 +340,10 @@ int64_t elisa_b200_specialise_check(const ElisaModelDesc* model, int32_t n_param
  * with FP64 DMMA, -1 on a bad argument; _bwd: of its transposed fold                     */
 int elisa_b200_plan_fold_slices(const ElisaPlan* plan, int32_t spectrum);
 int elisa_b200_plan_fold_slices_bwd(const ElisaPlan* plan, int32_t spectrum);
+/* 1 when calls of up to 1024 parameter vectors evaluate this spectrum in ONE kernel (model in dual numbers,
+ * FP64 fold in forward mode, statistic, gradient; small spectra with a runtime-specialised model: the NUTS
+ * shape), 0 when they run the chunk pipeline.  Environment ELISA_B200_TINY=0 turns the path off.            */
+int elisa_b200_plan_small_batch_kernel(const ElisaPlan* plan, int32_t spectrum);
 /* int8 digit products the integer fold EXECUTES per FP64 multiply-add of the dense contraction,
  * averaged over the (column tile, k-block) pairs of the forward (out[0]) and the transposed
  * (out[1]) operand: slices (slices + 1) / 2 for a response without structure (21 for 6 digits),

@@ -19,3 +19,15 @@ def lib():
 
     build.build()
     return _lib.load()
+
+
+@pytest.fixture(autouse=True)
+def _chunk_pipeline_unless_asked(request, monkeypatch):
+    """Small test problems would all take the one-kernel small-batch path (tiny_eval: <= 1024 rows on a small
+    spectrum) and leave the chunk pipeline -- unfold, tensor-core folds, statistic, contraction: the path the
+    bench measures -- untested at test sizes.  Every module but the one that tests the small-batch kernel
+    itself therefore runs with it switched off (ELISA_B200_TINY is read at plan creation)."""
+    if getattr(request.module, 'SMALL_BATCH_KERNEL', False):
+        monkeypatch.delenv('ELISA_B200_TINY', raising=False)
+    else:
+        monkeypatch.setenv('ELISA_B200_TINY', '0')

@@ -35,11 +35,12 @@ def oracle_eval(cfg, theta=None, grad=True):
     return oracle.loglike(cfg['stat'], datas, specs, t, on, off).numpy(), None
 
 
-def gpu_eval(cfg, theta=None, grad=True, chunk=0, host=False, specialise=None, fold=None, slices=0, slices_bwd=0):
+def gpu_eval(cfg, theta=None, grad=True, chunk=0, host=False, specialise=None, fold=None, slices=0, slices_bwd=0,
+             small_batch=True):
     theta = cfg['theta'] if theta is None else theta
     models = [m.compile() if not hasattr(m, 'to_spec') else m for m in cfg['model']]
     lk = Likelihood(cfg['data'], models, cfg['stat'], chunk=chunk, specialise=specialise, fold=fold, slices=slices,
-                    slices_bwd=slices_bwd)
+                    slices_bwd=slices_bwd, small_batch=small_batch)
     if fold is not None:
         assert all((s > 0) == (fold == 'i8') for s in lk.fold_slices), lk.fold_slices
     if specialise is not None:
