@@ -17,6 +17,8 @@ OP_ADD = -1
 OP_MUL = -2
 OP_NORM0 = -16
 MAX_NORMS = 2
+MAX_SHIFTS = 2
+SHIFT_Z, SHIFT_ZA, SHIFT_V = 1, 2, 3
 NORM = {'PhFlux': 0, 'EnFlux': 1}
 FLAG_NO_JIT = 1
 FLAG_REQUIRE_JIT = 2
@@ -49,6 +51,8 @@ class ComponentDesc(C.Structure):
         ('out_scale', C.c_double),
         ('norm_grid_scale', C.c_double),
         ('norm_out_scale', C.c_double),
+        ('shift_kind', C.c_int32 * MAX_SHIFTS),
+        ('shift_src', C.c_int32 * MAX_SHIFTS),
     ]
 
 

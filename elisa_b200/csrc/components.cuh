@@ -31,6 +31,17 @@ struct Cst<Dual<N>> {
     __device__ __forceinline__ static Dual<N> make(double c) { return make_const<N>(c); }
 };
 
+// a grid value as the leaf's scalar type: plain energies are constants, energies under a FREE shift
+// (models/conv.py:294-432 with z / v a fit parameter) already are of that type
+template <typename T>
+__device__ __forceinline__ T lift(double x) {
+    return Cst<T>::make(x);
+}
+template <typename T, int N>
+__device__ __forceinline__ T lift(const Dual<N>& x) {
+    return x;
+}
+
 #define ELISA_PI 3.141592653589793238462643383279502884
 
 // F(x; alpha) of _powerlaw_integral (models/add.py:40-50) on one edge, given ln x.
@@ -39,6 +50,11 @@ template <typename T>
 __device__ __forceinline__ T powerlaw_antiderivative(bool cond, const T& oma, double lnx) {
     if (cond) return pw_e(lnx, oma) / oma;
     return Cst<T>::make(lnx);
+}
+template <int N>
+__device__ __forceinline__ Dual<N> powerlaw_antiderivative(bool cond, const Dual<N>& oma, const Dual<N>& lnx) {
+    if (cond) return ex(oma * lnx) / oma;  // the energy itself carries a tangent (free energy shift)
+    return lnx;
 }
 template <typename T>
 __device__ __forceinline__ T powerlaw_antiderivative_t(bool cond, const T& oma, const T& lnx) {
@@ -63,10 +79,10 @@ struct Comp<ELISA_COMP_BAND> {  // Band.continuum, models/add.py:100-121
         c[1] = Ec * amb;                                // Ebreak
         c[2] = amb * lg(amb * Ec * (1.0 / 100.0)) - amb;  // amb log(amb Ec / e0) - amb
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
-        const double le = lnE - 4.605170185988091368;  // log(E / e0), e0 = 100
-        const T lg_ = sel(E < value(c[1]), p[0] * le - E * c[0], c[2] + p[1] * le);
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE lnE, T* g) {
+        const TE le = lnE - 4.605170185988091368;  // log(E / e0), e0 = 100
+        const T lg_ = sel(value(E) < value(c[1]), p[0] * le - E * c[0], c[2] + p[1] * le);
         g[0] = p[3] * ex(lg_);
     }
 };
@@ -85,10 +101,10 @@ struct Comp<ELISA_COMP_BANDEP> {  // BandEp.continuum, models/add.py:177-200
         c[1] = amb_ * Ec;  // Ebreak uses (alpha - beta), not the guarded amb (add.py:185)
         c[2] = amb * lg(amb * Ec * (1.0 / 100.0)) - amb;
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
-        const double le = lnE - 4.605170185988091368;
-        const T lg_ = sel(E < value(c[1]), p[0] * le - E * c[0], c[2] + p[1] * le);
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE lnE, T* g) {
+        const TE le = lnE - 4.605170185988091368;
+        const T lg_ = sel(value(E) < value(c[1]), p[0] * le - E * c[0], c[2] + p[1] * le);
         g[0] = p[3] * ex(lg_);
     }
 };
@@ -100,8 +116,8 @@ struct Comp<ELISA_COMP_BENTPL> {  // BentPL.continuum, models/add.py:231-236
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = lg(p[1]);
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE lnE, T* g) {
         g[0] = p[2] * 2.0 / (1.0 + ex(p[0] * (lnE - c[0])));
     }
 };
@@ -114,8 +130,8 @@ struct Comp<ELISA_COMP_BLACKBODY> {  // Blackbody.continuum, models/add.py:266-2
         c[0] = 1.0 / p[0];
         c[1] = 8.0525 * p[1] / (p[0] * p[0] * p[0]);
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
         const T x = E * c[0];
         const T tmp = c[1] * E;
         const double xv = value(x);
@@ -158,8 +174,8 @@ struct Comp<ELISA_COMP_BLACKBODYRAD> {  // BlackbodyRad.continuum, models/add.py
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = 1.0 / p[0];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
         const T x = E * c[0];
         const T tmp = (1.0344e-3 * E) * p[1];
         const double xv = value(x);
@@ -202,8 +218,8 @@ struct Comp<ELISA_COMP_COMPT> {  // Compt.continuum, models/add.py:473-479
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = (p[0] - 2.0) / p[1];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE lnE, T* g) {
         g[0] = p[2] * ex(E * c[0] - p[0] * lnE);
     }
     // closed-form edge tangents: b = e (1, E, ln E), e = exp(E (a - 2) / b - a ln E)
@@ -230,8 +246,8 @@ struct Comp<ELISA_COMP_CUTOFFPL> {  // CutoffPL.continuum, models/add.py:434-439
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = 1.0 / p[1];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE lnE, T* g) {
         g[0] = p[2] * ex(-(p[0] * lnE) - E * c[0]);
     }
     // closed-form edge tangents: b = e (1, ln E, E), e = exp(-alpha ln E - E / Ec)
@@ -259,8 +275,8 @@ struct Comp<ELISA_COMP_GAUSS> {  // Gauss.continuum, models/add.py:511-516 (jax 
         c[0] = lg((2.0 * ELISA_PI) * s2);
         c[1] = 1.0 / s2;
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
         const T dx = E - p[0];
         g[0] = p[2] * ex((c[0] + dx * dx * c[1]) * -0.5);
     }
@@ -288,8 +304,8 @@ struct Comp<ELISA_COMP_OTTB> {  // OTTB.continuum, models/add.py:590-594
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = 1.0 / p[0];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
         g[0] = p[1] * ex((1.0 - E) * c[0]) * (1.0 / E);
     }
     // closed-form edge tangents: b0 = g / K, b1 = (g / K) (E - 1)
@@ -312,8 +328,8 @@ struct Comp<ELISA_COMP_OTTS> {  // OTTS.continuum, models/add.py:625-629
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = lg(p[0]);
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE, TE lnE, T* g) {
         g[0] = p[1] * ex(-ex((lnE - c[0]) * (1.0 / 3.0)));
     }
 };
@@ -326,8 +342,8 @@ struct Comp<ELISA_COMP_SMOOTHLYBROKENPL> {  // SmoothlyBrokenPL.continuum, model
         c[0] = lg(p[1]);
         c[1] = (p[2] - p[0]) / p[3];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE, TE lnE, T* g) {
         const T le = lnE - c[0];  // log(E / Eb)
         const T x = c[1] * le;
         const double xv = value(x);
@@ -351,15 +367,15 @@ struct Comp<ELISA_COMP_POWERLAW> {  // PowerLaw.integral, models/add.py:40-50,65
         c[0] = sel(value(p[0]) != 1.0, 1.0 - p[0], Cst<T>::make(1.0));
         c[1] = 1.0 / c[0];  // the division by (1 - alpha) once per parameter vector, not once per edge
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE, TE lnE, T* g) {
         if (value(p[0]) != 1.0)
             g[0] = pw_e(lnE, c[0]) * c[1];
         else
-            g[0] = Cst<T>::make(lnE);
+            g[0] = lift<T>(lnE);
     }
-    template <typename T>
-    __device__ static T bin(const T* p, const T*, const T* g0, const T* g1, double, double) {
+    template <typename T, typename TE>
+    __device__ static T bin(const T* p, const T*, const T* g0, const T* g1, TE, TE) {
         return p[1] * (g1[0] - g0[0]);
     }
     // closed-form edge tangents of the antiderivative: the bin is K (F(E1) - F(E0)), a DIFFERENCE of
@@ -389,15 +405,15 @@ struct Comp<ELISA_COMP_BROKENPL> {  // BrokenPL.integral, models/add.py:378-393
         c[1] = sel(value(p[0]) != 1.0, 1.0 - p[0], Cst<T>::make(1.0));
         c[2] = sel(value(p[2]) != 1.0, 1.0 - p[2], Cst<T>::make(1.0));
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE, TE lnE, T* g) {
         const T lx = lnE - c[0];  // log(E / Eb)
         g[0] = powerlaw_antiderivative_t(value(p[0]) != 1.0, c[1], lx);
         g[1] = powerlaw_antiderivative_t(value(p[2]) != 1.0, c[2], lx);
     }
-    template <typename T>
-    __device__ static T bin(const T* p, const T*, const T* g0, const T* g1, double E0, double) {
-        const bool mask = E0 <= value(p[1]);
+    template <typename T, typename TE>
+    __device__ static T bin(const T* p, const T*, const T* g0, const T* g1, TE E0, TE) {
+        const bool mask = value(E0) <= value(p[1]);
         return p[3] * sel(mask, g1[0] - g0[0], g1[1] - g0[1]);
     }
 };
@@ -410,12 +426,12 @@ struct Comp<ELISA_COMP_LORENTZ> {  // Lorentz.integral, models/add.py:553-561
         c[0] = 2.0 / p[1];
         c[1] = 2.0 * p[2] / (ELISA_PI + 2.0 * at(2.0 * p[0] / p[1]));
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
         g[0] = at((E - p[0]) * c[0]);
     }
-    template <typename T>
-    __device__ static T bin(const T*, const T* c, const T* g0, const T* g1, double, double) {
+    template <typename T, typename TE>
+    __device__ static T bin(const T*, const T* c, const T* g0, const T* g1, TE, TE) {
         return c[1] * (g1[0] - g0[0]);
     }
 };
@@ -439,12 +455,12 @@ struct CompPLFlux {  // PLFluxNorm.eval, models/add.py:682-708
             c[1] = p[1] / f;
         }
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE, TE lnE, T* g) {
         g[0] = powerlaw_antiderivative(value(p[0]) != 1.0, c[0], lnE);
     }
-    template <typename T>
-    __device__ static T bin(const T*, const T* c, const T* g0, const T* g1, double, double) {
+    template <typename T, typename TE>
+    __device__ static T bin(const T*, const T* c, const T* g0, const T* g1, TE, TE) {
         return c[1] * (g1[0] - g0[0]);
     }
 };
@@ -472,12 +488,12 @@ struct Comp<ELISA_COMP_CONSTANT> {  // Constant.integral, models/mul.py:54-56
     static constexpr int NP = 1, NG = 1, NC = 1, RULE = RULE_CUSTOM;
     template <typename T>
     __device__ static void pre(const T*, const double*, T*) {}
-    template <typename T>
-    __device__ static void edge(const T*, const T*, double, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T*, const T*, TE, TE, T* g) {
         g[0] = Cst<T>::make(0.0);
     }
-    template <typename T>
-    __device__ static T bin(const T* p, const T*, const T*, const T*, double, double) {
+    template <typename T, typename TE>
+    __device__ static T bin(const T* p, const T*, const T*, const T*, TE, TE) {
         return p[0];
     }
 };
@@ -489,9 +505,9 @@ struct Comp<ELISA_COMP_EDGE> {  // Edge.continuum, models/mul.py:88-94
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = 1.0 / p[0];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
-        if (E >= value(p[0])) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
+        if (value(E) >= value(p[0])) {
             const T t = E * c[0];
             g[0] = ex(-(p[1] * (t * t * t)));
         } else {
@@ -505,8 +521,8 @@ struct Comp<ELISA_COMP_EXPABS> {  // ExpAbs.continuum, models/mul.py:116-118
     static constexpr int NP = 1, NG = 1, NC = 1, RULE = RULE_CONTINUUM_MUL;
     template <typename T>
     __device__ static void pre(const T*, const double*, T*) {}
-    template <typename T>
-    __device__ static void edge(const T* p, const T*, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T*, TE E, TE, T* g) {
         g[0] = ex(p[0] * (-1.0 / E));
     }
 };
@@ -516,9 +532,9 @@ struct Comp<ELISA_COMP_EXPFAC> {  // ExpFac.continuum, models/mul.py:154-159
     static constexpr int NP = 3, NG = 1, NC = 1, RULE = RULE_CONTINUUM_MUL;
     template <typename T>
     __device__ static void pre(const T*, const double*, T*) {}
-    template <typename T>
-    __device__ static void edge(const T* p, const T*, double E, double, T* g) {
-        if (E >= value(p[2])) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T*, TE E, TE, T* g) {
+        if (value(E) >= value(p[2])) {
             g[0] = 1.0 + p[0] * ex(p[1] * (-E));
         } else {
             g[0] = Cst<T>::make(1.0);
@@ -534,8 +550,8 @@ struct Comp<ELISA_COMP_GABS> {  // GAbs.continuum, models/mul.py:195-204
         c[0] = 1.0 / p[1];
         c[1] = -(p[2] / (2.50662827463100050242 * p[1]));  // -tau / (sqrt(2 pi) sigma)
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
         const T z = (E - p[0]) * c[0];
         g[0] = ex(c[1] * ex(z * z * -0.5));
     }
@@ -548,9 +564,9 @@ struct Comp<ELISA_COMP_HIGHECUT> {  // HighECut.continuum, models/mul.py:236-240
     __device__ static void pre(const T* p, const double*, T* c) {
         c[0] = 1.0 / p[1];
     }
-    template <typename T>
-    __device__ static void edge(const T* p, const T* c, double E, double, T* g) {
-        if (E >= value(p[0])) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T* p, const T* c, TE E, TE, T* g) {
+        if (value(E) >= value(p[0])) {
             g[0] = ex((p[0] - E) * c[0]);
         } else {
             g[0] = Cst<T>::make(1.0);
@@ -566,12 +582,12 @@ struct Comp<ELISA_COMP_PLABS> {  // PLAbs.integral, models/mul.py:266-271 (alpha
         c[0] = 1.0 - p[0];
         c[1] = p[1] / c[0];
     }
-    template <typename T>
-    __device__ static void edge(const T*, const T* c, double, double lnE, T* g) {
+    template <typename T, typename TE>
+    __device__ static void edge(const T*, const T* c, TE, TE lnE, T* g) {
         g[0] = c[1] * pw_e(lnE, c[0]);
     }
-    template <typename T>
-    __device__ static T bin(const T*, const T*, const T* g0, const T* g1, double E0, double E1) {
+    template <typename T, typename TE>
+    __device__ static T bin(const T*, const T*, const T* g0, const T* g1, TE E0, TE E1) {
         return (g1[0] - g0[0]) * (1.0 / (E1 - E0));
     }
 };
@@ -716,6 +732,46 @@ __device__ __forceinline__ T leaf_bin_pc(const T* p, const T* c, int method, con
         }
         const double factor = add ? 0.5 * (E1 - E0) : 0.5;
         return factor * (g0[0] + g1[0]);
+    }
+}
+
+// The same under FREE energy shifts (ZAShift / ZMShift / VAShift / VMShift with z or v a fit parameter,
+// models/conv.py:294-432): the leaf sees E' = F gs E, where F -- the product of the enclosing factors 1 + z,
+// 1 - v / c -- is of the leaf's dual type and carries the tangent of the shift parameter.  Every component body
+// is generic in the type of its energy argument, so d(bin)/dz comes out of the same dual arithmetic that gives
+// the parameter derivatives (the reference gets it from JAX differentiating model_fn(egrid * factor)).
+// lnF = ln F.  T = double (values only) works as well.
+template <int KIND, typename T>
+__device__ __forceinline__ T leaf_bin_shift(const T* p, const T* c, int method, const GridView& gv, int e, double gs,
+                                            double lgs, const T& F, const T& lnF) {
+    using C = Comp<KIND>;
+    static_assert(!IsTable<C>::value, "free energy shifts around table components are not supported");
+    const int ec = e <= gv.E ? e : gv.E;
+    const double E0d = gs * (gv.has_point ? gv.pE : gv.egrid[ec]);
+    const double l0d = (gv.has_point ? gv.pl : gv.lngrid[ec]) + lgs;
+    const double E1d = __shfl_down_sync(0xffffffffu, E0d, 1);
+    const T E0 = F * E0d, E1 = F * E1d, l0 = lnF + l0d;
+    T g0[C::NG], g1[C::NG];
+    C::edge(p, c, E0, l0, g0);
+#pragma unroll
+    for (int i = 0; i < C::NG; ++i) g1[i] = shfl_down1(g0[i]);
+    if constexpr (C::RULE == RULE_CUSTOM) {
+        return C::bin(p, c, g0, g1, E0, E1);
+    } else {
+        const bool add = C::RULE == RULE_CONTINUUM_ADD;
+        if (method == ELISA_METHOD_SIMPSON) {
+            const int em = e < gv.E ? e : gv.E - 1;
+            T gm[C::NG];
+            const T Em = F * (gs * (gv.has_point ? gv.pEm : gv.emid[em]));
+            const T lm = lnF + ((gv.has_point ? gv.plm : gv.lnmid[em]) + lgs);
+            C::edge(p, c, Em, lm, gm);
+            const T s = g0[0] + 4.0 * gm[0] + g1[0];
+            if (add) return (E1 - E0) * (1.0 / 6.0) * s;
+            return s * (1.0 / 6.0);
+        }
+        const T s = g0[0] + g1[0];
+        if (add) return (E1 - E0) * 0.5 * s;
+        return s * 0.5;
     }
 }
 

@@ -194,6 +194,10 @@ __device__ __forceinline__ Dual<N> pw_e(double lnbase, const Dual<N>& expo) {
     const double r = fm::exp(expo.v * lnbase);
     return chain(expo, r, r * lnbase);
 }
+template <int N>
+__device__ __forceinline__ Dual<N> pw_e(const Dual<N>& lnbase, const Dual<N>& expo) {  // energies under a free shift
+    return ex(expo * lnbase);
+}
 // general pow for positive base
 __device__ __forceinline__ double pw(double base, double expo) { return pow(base, expo); }
 template <int N>

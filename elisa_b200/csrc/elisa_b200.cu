@@ -55,6 +55,10 @@ struct LeafDev {
     // and on the grid of the enclosing flux normalisation
     double gs, lgs, os;
     double ngs, lngs, nos;
+    // FREE energy shifts around the leaf (ELISA_SHIFT_*, theta column); n_shift of them
+    int32_t n_shift, pad3_;
+    int32_t shift_kind[ELISA_MAX_SHIFTS];
+    int32_t shift_src[ELISA_MAX_SHIFTS];
 };
 
 constexpr int MAX_OPS = 2 * ELISA_MAX_COMPONENTS + ELISA_MAX_NORMS;
@@ -924,6 +928,7 @@ struct ElisaPlan {
     // batch never changes which kernels compute a row
     bool tiny_enabled = true, tiny_now = false;
     int64_t tiny_call_n = -1;
+    TinyArgs* tiny_args = nullptr;  // [S] device array (entries of spectra that do not qualify are unused)
     int64_t workspace_bytes = 0;
     int64_t launches = 0;
     // host-path staging (device side), grown on demand: theta / loglike / grad for the whole call,
@@ -1045,6 +1050,21 @@ static int build_model(const ElisaModelDesc& md, int P, ModelDev* out) {
             return fail(ELISA_ERR_INVALID, "model: grid_scale must be positive and finite, out_scale finite");
         L.lgs = L.gs == 1.0 ? 0.0 : log(L.gs);
         L.lngs = L.ngs == 1.0 ? 0.0 : log(L.ngs);
+        L.n_shift = 0;
+        for (int k = 0; k < ELISA_MAX_SHIFTS; ++k) {
+            if (c.shift_kind[k] == 0) continue;
+            if (c.shift_kind[k] != ELISA_SHIFT_Z && c.shift_kind[k] != ELISA_SHIFT_ZA && c.shift_kind[k] != ELISA_SHIFT_V)
+                return fail(ELISA_ERR_INVALID, "model: unknown shift_kind");
+            if (c.shift_src[k] < 0 || c.shift_src[k] >= P) return fail(ELISA_ERR_INVALID, "model: shift_src out of range");
+            if (c.kind == ELISA_COMP_PHOTONABS)
+                return fail(ELISA_ERR_UNSUPPORTED, "model: a free energy shift around a table component");
+            if (md.n_norms > 0)
+                return fail(ELISA_ERR_UNSUPPORTED, "model: free energy shifts together with flux normalisations");
+            L.shift_kind[L.n_shift] = c.shift_kind[k];
+            L.shift_src[L.n_shift] = c.shift_src[k];
+            ++L.n_shift;
+            out->used_mask |= 1u << c.shift_src[k];
+        }
         if (c.kind == ELISA_COMP_PHOTONABS) {
             if (c.table_energy == nullptr || c.table_xsect == nullptr || c.table_len < 2)
                 return fail(ELISA_ERR_INVALID, "model: PhotonAbsorption needs a cross-section table (>= 2 points)");
@@ -1144,7 +1164,7 @@ static int popcount32(uint32_t v) {
     for (; v; v &= v - 1) ++n;
     return n;
 }
-static size_t tiny_smem_bytes(int E, int P) { return ((size_t)(1 + P) * E + (size_t)(TINY_THREADS / 32) * (1 + P)) * 8; }
+static size_t tiny_smem_bytes(int E, int P) { return tiny_smem_doubles(E, P) * 8; }
 static bool tiny_shape_ok(int E, int C, int P, uint32_t used_mask) {
     return P <= 8 && (int64_t)E * C * (1 + popcount32(used_mask)) <= TINY_MAX_WORK && tiny_smem_bytes(E, P) <= 48 * 1024;
 }
@@ -1492,6 +1512,12 @@ struct SV {  // a scalar expression and its non-zero tangents by theta column
 };
 }  // namespace
 
+static bool model_has_free_shift(const ModelDev& m) {
+    for (int i = 0; i < m.n_leaf; ++i)
+        if (m.leaf[i].n_shift > 0) return true;
+    return false;
+}
+
 static std::string generate_model_struct(const ModelDev& m, int P, bool grad, const std::string& name) {
     std::string s;
     auto str = [](int v) { return std::to_string(v); };
@@ -1499,11 +1525,16 @@ static std::string generate_model_struct(const ModelDev& m, int P, bool grad, co
     std::vector<std::vector<int>> cols(m.n_leaf);
     std::vector<std::string> ltype(m.n_leaf);
     for (int i = 0; i < m.n_leaf; ++i) {
-        if (grad)
+        if (grad) {
             for (int q = 0; q < m.leaf[i].np; ++q) {
                 const int c = m.leaf[i].src[q];
                 if (c >= 0 && std::find(cols[i].begin(), cols[i].end(), c) == cols[i].end()) cols[i].push_back(c);
             }
+            for (int k = 0; k < m.leaf[i].n_shift; ++k) {  // a free shift's z / v is one more tangent of the leaf
+                const int c = m.leaf[i].shift_src[k];
+                if (std::find(cols[i].begin(), cols[i].end(), c) == cols[i].end()) cols[i].push_back(c);
+            }
+        }
         std::sort(cols[i].begin(), cols[i].end());
         ltype[i] = cols[i].empty() ? "double" : "Dual<" + str((int)cols[i].size()) + ">";
     }
@@ -1523,6 +1554,8 @@ static std::string generate_model_struct(const ModelDev& m, int P, bool grad, co
     for (int i = 0; i < m.n_leaf; ++i) {
         const std::string k = str(m.leaf[i].kind), id = str(i);
         s += "    " + ltype[i] + " p" + id + "[Comp<" + k + ">::NP]; " + ltype[i] + " c" + id + "[Comp<" + k + ">::NC];\n";
+        if (m.leaf[i].n_shift > 0)  // free energy shifts: grid factor, its logarithm, output factor
+            s += "    " + ltype[i] + " F" + id + ", lnF" + id + ", oF" + id + ";\n";
     }
     for (int k = 0; k < m.n_norms; ++k) {
         s += "    double n" + str(k) + "_v;\n";
@@ -1544,6 +1577,22 @@ static std::string generate_model_struct(const ModelDev& m, int P, bool grad, co
         s += "    { const double aux[2] = {" + hexd(L.aux[0]) + ", " + hexd(L.aux[1]) + "};\n";
         s += "      for (int k = 0; k < Comp<" + k + ">::NC; ++k) s.c" + id + "[k] = Flat<" + T + ">::seed(0.0, -1);\n";
         s += "      Comp<" + k + ">::pre(s.p" + id + ", aux, s.c" + id + "); }\n";
+        if (L.n_shift > 0) {
+            // F = prod of (1 + z) / (1 - v / c) over the free shifts around the leaf, as a dual number seeded in
+            // the shift parameter's tangent; oF = prod of 1 / (1 + z) over the ZAShifts among them (conv.py:299-300)
+            s += "    s.F" + id + " = Flat<" + T + ">::seed(1.0, -1); s.oF" + id + " = Flat<" + T + ">::seed(1.0, -1);\n";
+            for (int q = 0; q < L.n_shift; ++q) {
+                const int local = grad ? (int)(std::find(cols[i].begin(), cols[i].end(), L.shift_src[q]) - cols[i].begin()) : -1;
+                const std::string z = "Flat<" + T + ">::seed(th[" + str(L.shift_src[q]) + "], " + str(local) + ")";
+                if (L.shift_kind[q] == ELISA_SHIFT_V)
+                    s += "    { const " + T + " f = 1.0 - " + z + " * (1.0 / 299792.458); s.F" + id + " = s.F" + id + " * f; }\n";
+                else if (L.shift_kind[q] == ELISA_SHIFT_ZA)
+                    s += "    { const " + T + " f = 1.0 + " + z + "; s.F" + id + " = s.F" + id + " * f; s.oF" + id + " = s.oF" + id + " / f; }\n";
+                else
+                    s += "    { const " + T + " f = 1.0 + " + z + "; s.F" + id + " = s.F" + id + " * f; }\n";
+            }
+            s += "    s.lnF" + id + " = lg(s.F" + id + ");\n";
+        }
     }
     s += "  }\n";
     // straight-line code of ops[lo, hi) on grid view `gv`; on_norm_grid selects the leaf's scales
@@ -1584,6 +1633,11 @@ static std::string generate_model_struct(const ModelDev& m, int P, bool grad, co
                 if (!emitted[op]) {
                     const double gs = on_norm_grid ? L.ngs : L.gs, lgs = on_norm_grid ? L.lngs : L.lgs;
                     const double os = on_norm_grid ? L.nos : L.os;
+                    if (L.n_shift > 0)
+                        s += ind + "const " + T + " " + pfx + "v" + id + " = " + (os != 1.0 ? hexd(os) + " * " : std::string()) +
+                             "(s.oF" + id + " * leaf_bin_shift<" + str(L.kind) + ", " + T + ">(s.p" + id + ", s.c" + id + ", " +
+                             str(L.method) + ", gv, e, " + hexd(gs) + ", " + hexd(lgs) + ", s.F" + id + ", s.lnF" + id + "));\n";
+                    else
                     s += ind + "const " + T + " " + pfx + "v" + id + " = " + (os != 1.0 ? hexd(os) + " * " : std::string()) +
                          "leaf_bin_pc<" + str(L.kind) + ", " + T + ">(s.p" + id + ", s.c" + id + ", " + str(L.method) +
                          ", gv, e, " + id + ", " + hexd(gs) + ", " + hexd(lgs) + ");\n";
@@ -1682,6 +1736,8 @@ static std::string generate_edge_model(const ModelDev& m, int P) {
     if (const char* env = getenv("ELISA_B200_CONTRACT"))
         if (strcmp(env, "generic") == 0) return std::string();
     if (m.n_norms != 0) return std::string();
+    for (int i = 0; i < m.n_leaf; ++i)
+        if (m.leaf[i].n_shift > 0) return std::string();  // a free shift differentiates the edge ENERGIES as well
     auto str = [](int v) { return std::to_string(v); };
     std::vector<int> mult(m.n_leaf, 0);
     int n_acc = 0;
@@ -1775,7 +1831,7 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks, int 
         s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
              "unfold_contract_generic<ModelG, Dual<" + std::to_string(P) + ">>(a); }\n";
     if (tiny_stat >= 0)
-        s += "extern \"C\" __global__ void __launch_bounds__(TINY_THREADS) tiny_eval_kernel(const TinyArgs t) { tiny_eval<ModelG, " +
+        s += "extern \"C\" __global__ void __launch_bounds__(TINY_THREADS) tiny_eval_kernel(const TinyCall t) { tiny_eval<ModelG, " +
              std::to_string(P) + ", " + std::to_string(tiny_stat) + ">(t); }\n";
     return s;
 }
@@ -2425,40 +2481,32 @@ static int build_spectrum_i8(ElisaPlan* plan, const ElisaSpectrumDesc& sd, Spect
 }
 
 // One (chunk, spectrum) pass.  theta/on/off/loglike/grad already point at the chunk's first row.
-// One kernel per spectrum for a small batch of a small spectrum (tiny_eval, unfold_skel.cuh): one CTA per row.
-static int launch_tiny(ElisaPlan* plan, const SpectrumPlan& sp, int s, const double* theta, const double* on,
-                       const double* off, int n, double* loglike, double* grad, cudaStream_t st) {
-    TinyArgs t;
-    memset(&t, 0, sizeof t);
-    UnfoldCore& a = t.core;
-    a.gv = sp.grid_view();
-    a.gv.has_point = 0;
-    a.theta = theta;
-    a.P = plan->P;
-    a.n_valid = n;
-    a.n_rows = n;
-    a.n_seg = 1;
-    a.clip = 1;
-    a.used_mask = sp.model.used_mask;
-    for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
-        a.ngv[k] = sp.norm_view(k);
-        a.ngv[k].has_point = 0;
-        a.nw[k] = sp.norm_grid[k].w;
-    }
-    a.grad_out = grad ? grad + (size_t)s * plan->P : nullptr;
-    a.grad_stride = (int64_t)plan->S * plan->P;
-    t.R = sp.tiny_R;
-    t.ldr = sp.C;
-    t.C = sp.C;
-    t.ch = sp.chan_view();
-    t.counts_on = on ? on + sp.counts_off : nullptr;
-    t.counts_off = off ? off + sp.counts_off : nullptr;
-    t.ld_counts = plan->sum_C;
-    t.loglike = loglike + s;
-    t.ll_stride = plan->S;
+static bool tiny_ready(const ElisaPlan* plan, int s) {
+    const SpectrumPlan& sp = plan->spec[s];
+    return plan->tiny_args != nullptr && sp.tiny_R != nullptr && sp.jit != nullptr && sp.jit->tiny != nullptr;
+}
+
+// Small batch of small spectra in one kernel (tiny_eval, unfold_skel.cuh): one CTA per (row, spectrum) for the
+// spectra [s0, s0 + count), which share one translation unit (same model expression and statistic).
+static int launch_tiny(ElisaPlan* plan, int s0, int count, const double* theta, const double* on, const double* off, int n,
+                       double* loglike, double* grad, cudaStream_t st) {
+    TinyCall k;
+    k.spec = plan->tiny_args;
+    k.s0 = s0;
+    k.S = plan->S;
+    k.P = plan->P;
+    k.n_valid = n;
+    k.theta = theta;
+    k.counts_on = on;
+    k.counts_off = off;
+    k.ld_counts = plan->sum_C;
+    k.loglike = loglike;
+    k.grad = grad;
+    size_t smem = 0;
+    for (int s = s0; s < s0 + count; ++s) smem = std::max(smem, tiny_smem_bytes(plan->spec[s].E, plan->P));
     ScopedSpan span(plan, ELISA_PROFILE_TINY, st);
-    void* kargs[] = {(void*)&t};
-    CUDA_TRY(cudaLaunchKernel((const void*)sp.jit->tiny, dim3(n), dim3(TINY_THREADS), kargs, tiny_smem_bytes(sp.E, plan->P), st));
+    void* kargs[] = {(void*)&k};
+    CUDA_TRY(cudaLaunchKernel((const void*)plan->spec[s0].jit->tiny, dim3(n, count), dim3(TINY_THREADS), kargs, smem, st));
     ++plan->launches;
     return ELISA_OK;
 }
@@ -2466,9 +2514,8 @@ static int launch_tiny(ElisaPlan* plan, const SpectrumPlan& sp, int s, const dou
 static int run_chunk(ElisaPlan* plan, int s, const double* theta, const double* on, const double* off, int n,
                      double* loglike, double* grad, cudaStream_t st) {
     const SpectrumPlan& sp = plan->spec[s];
-    if (plan->tiny_now && sp.tiny_R != nullptr && sp.jit != nullptr && sp.jit->tiny != nullptr && !plan->force_dmma &&
-        !plan->debug_skip)
-        return launch_tiny(plan, sp, s, theta, on, off, n, loglike, grad, st);
+    if (plan->tiny_now && tiny_ready(plan, s) && !plan->force_dmma && !plan->debug_skip)
+        return launch_tiny(plan, s, 1, theta, on, off, n, loglike, grad, st);
     const int n_rows = round_up(n, GEMM_BM);
     const int m_tiles = n_rows / GEMM_BM;
     const bool want_grad = grad != nullptr;
@@ -2772,8 +2819,7 @@ static int ensure_balanced(ElisaPlan* plan, const double* theta, const double* o
 static bool decide_tiny(ElisaPlan* plan, int64_t n) {
     plan->tiny_now = plan->tiny_enabled && (plan->tiny_call_n >= 0 ? plan->tiny_call_n : n) <= TINY_MAX_N;
     bool all_tiny = plan->tiny_now && !plan->force_dmma && !plan->debug_skip;
-    for (int s = 0; s < plan->S && all_tiny; ++s)
-        all_tiny = plan->spec[s].tiny_R != nullptr && plan->spec[s].jit != nullptr && plan->spec[s].jit->tiny != nullptr;
+    for (int s = 0; s < plan->S && all_tiny; ++s) all_tiny = tiny_ready(plan, s);
     return all_tiny;
 }
 
@@ -2786,8 +2832,26 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
     int dev;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
+    if (decide_tiny(plan, n)) {
+        // every spectrum takes the one-kernel path: spectra sharing a translation unit (a joint fit of like
+        // detectors) are ONE launch; nothing else runs (no envelopes, no workspace, no guard)
+        int rc = ELISA_OK;
+        for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
+            const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
+            for (int s0 = 0; s0 < plan->S && rc == ELISA_OK;) {
+                int s1 = s0 + 1;
+                while (s1 < plan->S && plan->spec[s1].jit == plan->spec[s0].jit) ++s1;
+                rc = launch_tiny(plan, s0, s1 - s0, theta + i0 * plan->P, on ? on + i0 * plan->sum_C : nullptr,
+                                 off ? off + i0 * plan->sum_C : nullptr, nc, loglike + i0 * plan->S,
+                                 grad ? grad + i0 * plan->S * plan->P : nullptr, st);
+                s0 = s1;
+            }
+        }
+        if (dev != plan->device) cudaSetDevice(dev);
+        return rc;
+    }
     // the integer folds need their envelopes only when some spectrum of this call runs through them
-    int rc = decide_tiny(plan, n) ? ELISA_OK : ensure_balanced(plan, theta, on, off, n, st);
+    int rc = ensure_balanced(plan, theta, on, off, n, st);
     const int64_t base = plan->row_base;  // global index of row 0 of this call (host path: of the piece)
     for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
         const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
@@ -2825,7 +2889,9 @@ static int run_small(ElisaPlan* plan, const double* theta, const double* on, con
                           n <= plan->chunk && on == nullptr && off == nullptr && theta != nullptr && loglike != nullptr &&
                           plan->g_theta != nullptr;
     if (!eligible) return run_all(plan, theta, on, off, n, loglike, grad, st);
-    if (!decide_tiny(plan, n)) {  // envelopes of the balanced integer fold: (re)derived outside any capture, on the caller's stream
+    // every spectrum on the one-kernel path: a launch or two on the caller's stream, nothing to replay
+    if (decide_tiny(plan, n)) return run_all(plan, theta, on, off, n, loglike, grad, st);
+    {  // envelopes of the balanced integer fold: (re)derived outside any capture, on the caller's stream
         int dev;
         CUDA_TRY(cudaGetDevice(&dev));
         if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
@@ -3247,10 +3313,18 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         // specialise the unfold kernel for this model unless told not to
         const char* env = getenv("ELISA_B200_JIT");
         const bool off = (desc->flags & ELISA_FLAG_NO_JIT) || (env && strcmp(env, "0") == 0);
+        if (off && model_has_free_shift(plan->spec[s].model)) {
+            rc = fail(ELISA_ERR_UNSUPPORTED, "free energy shifts need the runtime-specialised kernel (ELISA_FLAG_NO_JIT / ELISA_B200_JIT=0 given)");
+            break;
+        }
         if (!off) {
             std::string why;
             plan->spec[s].jit = jit_unfold(plan->spec[s].model, plan->P, plan->ks, &why,
                                            plan->spec[s].tiny_R != nullptr ? plan->spec[s].stat : -1);
+            if (plan->spec[s].jit == nullptr && model_has_free_shift(plan->spec[s].model)) {
+                rc = fail(ELISA_ERR_UNSUPPORTED, "free energy shifts need the runtime-specialised kernel, which is unavailable: " + why);
+                break;
+            }
             if (plan->spec[s].jit == nullptr && ((desc->flags & ELISA_FLAG_REQUIRE_JIT) || (env && strcmp(env, "require") == 0))) {
                 rc = fail(ELISA_ERR_UNSUPPORTED, "runtime specialisation required but unavailable: " + why);
                 break;
@@ -3280,6 +3354,35 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         plan->max_C_pad = std::max(plan->max_C_pad, plan->spec[s].C_pad);
     }
     plan->sum_C = coff;
+    if (rc == ELISA_OK && plan->tiny_enabled) {  // per-spectrum arguments of the one-kernel small-batch path
+        std::vector<TinyArgs> ta(plan->S);
+        bool any = false;
+        for (int s = 0; s < plan->S; ++s) {
+            const SpectrumPlan& sp = plan->spec[s];
+            TinyArgs& t = ta[s];
+            memset(&t, 0, sizeof t);
+            if (sp.tiny_R == nullptr || sp.jit == nullptr || sp.jit->tiny == nullptr) continue;
+            any = true;
+            UnfoldCore& a = t.core;
+            a.gv = sp.grid_view();
+            a.gv.has_point = 0;
+            a.P = plan->P;
+            a.n_seg = 1;
+            a.clip = 1;
+            a.used_mask = sp.model.used_mask;
+            for (int k = 0; k < ELISA_MAX_NORMS; ++k) {
+                a.ngv[k] = sp.norm_view(k);
+                a.ngv[k].has_point = 0;
+                a.nw[k] = sp.norm_grid[k].w;
+            }
+            t.R = sp.tiny_R;
+            t.ldr = sp.C;
+            t.C = sp.C;
+            t.ch = sp.chan_view();
+            t.counts_off = sp.counts_off;
+        }
+        if (any) rc = upload(plan, ta, &plan->tiny_args);
+    }
     if (rc == ELISA_OK) {
         // chunk: one 128-row tile per SM by default, bounded by a 6 GiB workspace
         int64_t chunk = desc->chunk > 0 ? desc->chunk : 148 * GEMM_BM;

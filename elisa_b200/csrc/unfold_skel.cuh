@@ -430,45 +430,63 @@ __device__ __forceinline__ void unfold_contract_edges(const UnfoldCore& a) {
 //      (forward mode: (1 + P) FMAs per response element, read coalesced from L2);
 //   3. the statistic of the channel gives l_c and w_c = dl/dx_c; loglike = sum_c l_c and
 //      grad_j = sum_c w_c t_jc are reduced in a fixed order (lane-serial, xor tree, warps in order).
-// Plain FP64 FMAs: no digit slicing, no accuracy guard needed.  One CTA per (parameter vector);
-// the host launches it per spectrum (own branch of the captured graph).
-struct TinyArgs {
-    UnfoldCore core;   // theta, P, n_valid, gv, norms, clip; grad_out / grad_stride (nullptr: value only)
+// Plain FP64 FMAs: no digit slicing, no accuracy guard needed.  One CTA per (parameter vector, spectrum):
+// the spectra of a joint fit that share a model and a statistic (one translation unit) are ONE launch.
+struct TinyArgs {      // per spectrum, fixed at plan creation (an array of these lives in device memory)
+    UnfoldCore core;   // gv, norms, used_mask, clip (the per-call fields of it are not used)
     const double* R;   // [E, ldr] dense response, row = energy bin
     int32_t ldr, C;
     ChanArrays ch;
-    const double* counts_on;   // per-row counts of this spectrum (nullptr: the plan's)
+    int64_t counts_off;  // column of this spectrum in the per-row counts arrays
+};
+struct TinyCall {      // per launch: spectra [s0, s0 + gridDim.y) of the plan, one CTA per (row, spectrum)
+    const TinyArgs* spec;  // the plan's array, indexed by spectrum
+    int32_t s0, S, P, n_valid;
+    const double* theta;       // [n, P]
+    const double* counts_on;   // [n, ld_counts] per-row counts (nullptr: the plan's)
     const double* counts_off;
     int64_t ld_counts;
-    double* loglike;   // element [row * ll_stride]
-    int64_t ll_stride;
+    double* loglike;   // [n, S]
+    double* grad;      // [n, S, P] or nullptr (value only)
 };
 
-constexpr int TINY_THREADS = 128;
+constexpr int TINY_THREADS = 256;
+constexpr int TINY_SPLIT = 2;  // the contraction over the energies is dealt to this many thread groups per channel
+
+// shared memory (doubles): u [E] | du/dtheta [NP][E] | partial folds [TINY_SPLIT][1 + NP][CG] | warp sums [warps][1 + NP]
+// with CG = TINY_THREADS / TINY_SPLIT channels per pass
+__host__ __device__ inline size_t tiny_smem_doubles(int E, int NP) {
+    return (size_t)(1 + NP) * E + (size_t)TINY_SPLIT * (1 + NP) * (TINY_THREADS / TINY_SPLIT) + (size_t)(TINY_THREADS / 32) * (1 + NP);
+}
 
 template <class Model, int NP, int STAT>
-__device__ __forceinline__ void tiny_eval(const TinyArgs& t) {
+__device__ __forceinline__ void tiny_eval(const TinyCall& k) {
     using T = Dual<NP>;
     extern __shared__ double tiny_smem[];
+    const int spec = k.s0 + blockIdx.y;
+    const TinyArgs& t = k.spec[spec];  // global memory: uniform loads
     const UnfoldCore& a = t.core;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int row = blockIdx.x;
-    if (row >= a.n_valid) return;
+    if (row >= k.n_valid) return;
     const int E = a.gv.E;
-    const bool want_grad = a.grad_out != nullptr;
+    const bool want_grad = k.grad != nullptr;
+    const double* theta = k.theta + (size_t)row * k.P;
 #ifdef UNFOLD_USED_MASK
     constexpr uint32_t used = UNFOLD_USED_MASK;
 #else
     const uint32_t used = a.used_mask;
 #endif
-    double* su = tiny_smem;              // [E]
-    double* sd = tiny_smem + E;          // [NP][E]
-    double* red = tiny_smem + (size_t)(1 + NP) * E;  // [TINY_THREADS / 32][1 + NP]
-    // 1. the model in dual numbers; warp w takes the passes w, w + 4, ...
+    constexpr int CG = TINY_THREADS / TINY_SPLIT;
+    double* su = tiny_smem;                       // [E]
+    double* sd = su + E;                          // [NP][E]
+    double* part = sd + (size_t)NP * E;           // [TINY_SPLIT][1 + NP][CG]
+    double* red = part + (size_t)TINY_SPLIT * (1 + NP) * CG;  // [warps][1 + NP]
+    // 1. the model in dual numbers; warp w takes the passes w, w + 8, ...
     {
         typename Model::Pre pre;
-        Model::pre(a.theta + (size_t)row * a.P, pre);
-        Model::norms(pre, a, a.theta + (size_t)row * a.P, lane);
+        Model::pre(theta, pre);
+        Model::norms(pre, a, theta, lane);
         GridView gv = a.gv;
         gv.has_point = 0;
         for (int e0 = 31 * wib; e0 < E; e0 += 31 * (TINY_THREADS / 32)) {
@@ -485,56 +503,95 @@ __device__ __forceinline__ void tiny_eval(const TinyArgs& t) {
         }
     }
     __syncthreads();
-    // 2 + 3. fold and statistic of the thread's channels
+    // 2 + 3. fold and statistic, CG channels per pass; thread (h, cl) folds the energies [h E / SPLIT, (h + 1) E / SPLIT)
+    // of channel c0 + cl -- eight independent loads of the response in flight per thread: the loop is bound by the
+    // latency of L2, not by arithmetic -- and group 0 adds the partial folds in a fixed order and does the statistic
+    const int h = tid / CG, cl = tid % CG;
+    const int e_lo = (int)((int64_t)E * h / TINY_SPLIT), e_hi = (int)((int64_t)E * (h + 1) / TINY_SPLIT);
     double ll = 0.0, g[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) g[j] = 0.0;
-    const double* con = t.counts_on ? t.counts_on + (size_t)row * t.ld_counts : nullptr;
-    const double* coff = t.counts_off ? t.counts_off + (size_t)row * t.ld_counts : nullptr;
-    for (int c = tid; c < t.C; c += TINY_THREADS) {
+    const double* con = k.counts_on ? k.counts_on + (size_t)row * k.ld_counts + t.counts_off : nullptr;
+    const double* coff = k.counts_off ? k.counts_off + (size_t)row * k.ld_counts + t.counts_off : nullptr;
+    const int C = t.C, ldr = t.ldr;
+    const double* R = t.R;
+    const ChanArrays ch = t.ch;
+    for (int c0 = 0; c0 < C; c0 += CG) {
+        const int c = c0 + cl;
         double x = 0.0, tj[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) tj[j] = 0.0;
-        const double* r = t.R + c;
-        if (want_grad) {
-            for (int e = 0; e < E; ++e) {
-                const double rv = r[(size_t)e * t.ldr];
-                x = fma(rv, su[e], x);
+        if (c < C) {
+            const double* r = R + c;
+            int e = e_lo;
+            for (; e + 8 <= e_hi; e += 8) {
+                double rv[8];
 #pragma unroll
-                for (int j = 0; j < NP; ++j)
-                    if ((used >> j) & 1u) tj[j] = fma(rv, sd[(size_t)j * E + e], tj[j]);
+                for (int k = 0; k < 8; ++k) rv[k] = r[(size_t)(e + k) * ldr];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    x = fma(rv[k], su[e + k], x);
+                    if (want_grad) {
+#pragma unroll
+                        for (int j = 0; j < NP; ++j)
+                            if ((used >> j) & 1u) tj[j] = fma(rv[k], sd[(size_t)j * E + e + k], tj[j]);
+                    }
+                }
             }
-        } else {
-            for (int e = 0; e < E; ++e) x = fma(r[(size_t)e * t.ldr], su[e], x);
+            for (; e < e_hi; ++e) {
+                const double rv = r[(size_t)e * ldr];
+                x = fma(rv, su[e], x);
+                if (want_grad) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j)
+                        if ((used >> j) & 1u) tj[j] = fma(rv, sd[(size_t)j * E + e], tj[j]);
+                }
+            }
         }
-        ChannelData d;
-        const double sc = t.ch.scale[c];
-        d.on = t.ch.on[c];
-        d.gof_on = t.ch.gof_on[c];
-        d.off = d.sigma = d.ratio = d.gof_off = d.den = 0.0;
-        if (STAT == ELISA_STAT_CHI2) d.sigma = t.ch.sigma[c];
-        if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
-            d.off = t.ch.off[c];
-            d.ratio = t.ch.ratio[c];
-        }
-        if (STAT == ELISA_STAT_PGSTAT) d.sigma = t.ch.sigma[c];
-        if (STAT == ELISA_STAT_WSTAT) d.gof_off = t.ch.gof_off[c];
-        if (STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) d.den = t.ch.den[c];
-        if (con != nullptr) {
-            d.on = con[c];
-            if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
-        }
-        if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr) {
-            d.off = coff[c];
-            if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
-        }
-        double dx = 0.0;
-        ll += stat_channel<STAT, true>(x * sc, d, dx);
-        const double w = dx * sc;
+        if (c0 > 0) __syncthreads();  // the previous pass's partial folds have been consumed
+        part[((size_t)h * (1 + NP)) * CG + cl] = x;
 #pragma unroll
         for (int j = 0; j < NP; ++j)
-            if ((used >> j) & 1u) g[j] = fma(w, tj[j], g[j]);
+            if ((used >> j) & 1u) part[((size_t)h * (1 + NP) + 1 + j) * CG + cl] = tj[j];
+        __syncthreads();
+        if (h == 0 && c < C) {
+#pragma unroll
+            for (int q = 1; q < TINY_SPLIT; ++q) {
+                x += part[((size_t)q * (1 + NP)) * CG + cl];
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    if ((used >> j) & 1u) tj[j] += part[((size_t)q * (1 + NP) + 1 + j) * CG + cl];
+            }
+            ChannelData d;
+            const double sc = ch.scale[c];
+            d.on = ch.on[c];
+            d.gof_on = ch.gof_on[c];
+            d.off = d.sigma = d.ratio = d.gof_off = d.den = 0.0;
+            if (STAT == ELISA_STAT_CHI2) d.sigma = ch.sigma[c];
+            if (STAT == ELISA_STAT_PSTAT || STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) {
+                d.off = ch.off[c];
+                d.ratio = ch.ratio[c];
+            }
+            if (STAT == ELISA_STAT_PGSTAT) d.sigma = ch.sigma[c];
+            if (STAT == ELISA_STAT_WSTAT) d.gof_off = ch.gof_off[c];
+            if (STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) d.den = ch.den[c];
+            if (con != nullptr) {
+                d.on = con[c];
+                if (STAT != ELISA_STAT_CHI2) d.gof_on = poisson_gof(d.on);
+            }
+            if ((STAT == ELISA_STAT_PGSTAT || STAT == ELISA_STAT_WSTAT) && coff != nullptr) {
+                d.off = coff[c];
+                if (STAT == ELISA_STAT_WSTAT) d.gof_off = poisson_gof(d.off);
+            }
+            double dx = 0.0;
+            ll += stat_channel<STAT, true>(x * sc, d, dx);
+            const double w = dx * sc;
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                if ((used >> j) & 1u) g[j] = fma(w, tj[j], g[j]);
+        }
     }
+    // fixed-order reduction: lane-serial sums above, xor tree, then the warps of group 0 in order
     ll = warp_sum(ll);
     if (lane == 0) red[wib * (1 + NP)] = ll;
     if (want_grad) {
@@ -548,11 +605,11 @@ __device__ __forceinline__ void tiny_eval(const TinyArgs& t) {
     if (tid <= NP && (tid == 0 || want_grad)) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < TINY_THREADS / 32; ++w) s += red[w * (1 + NP) + tid];
+        for (int w = 0; w < CG / 32; ++w) s += red[w * (1 + NP) + tid];
         if (tid == 0)
-            t.loglike[(size_t)row * t.ll_stride] = s;
-        else if (tid - 1 < a.P)
-            a.grad_out[(size_t)row * a.grad_stride + tid - 1] = s;
+            k.loglike[(size_t)row * k.S + spec] = s;
+        else if (tid - 1 < k.P)
+            k.grad[((size_t)row * k.S + spec) * k.P + tid - 1] = s;
     }
 }
 

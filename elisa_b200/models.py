@@ -329,28 +329,33 @@ class ConvolvedModel(Model):
 
 class _Shift(ConvolutionComponent):
     """Energy shifts (models/conv.py:259-432).  The shift parameter is fixed by default in the
-    reference; a FREE z / v needs the derivative of the wrapped model with respect to its energy
-    grid, which this path does not carry -- it is refused."""
+    reference, and then the shift is a compile-time scale of the leaves' grids.  A FREE z / v (pass a
+    ``UniformParameter``) is an ordinary column of theta: the kernels evaluate the wrapped components on
+    dual-number energies, so d/dz comes with the other derivatives (``ElisaComponentDesc.shift_*``)."""
 
     _divide = False  # ZAShift divides the shifted model by the factor (conv.py:299-300)
+    _velocity = False  # V*Shift: factor 1 - v / c
 
-    def factor(self) -> float:
-        p = self.params[self._config[0].name]
-        if not p.fixed:
-            raise NotImplementedError(f'{self.name}: a free {p.name} is not supported on this path (fix it)')
-        return self._factor(p.default)
+    @property
+    def shift_param(self) -> UniformParameter:
+        return self.params[self._config[0].name]
+
+    def factor(self) -> float | None:
+        """The grid factor of a FIXED shift; None when the shift parameter is free."""
+        p = self.shift_param
+        return None if not p.fixed else self._factor(p.default)
 
 
-def _shift(name, supported, pcfg, factor, divide=False):
+def _shift(name, supported, pcfg, factor, divide=False, velocity=False):
     return type(name, (_Shift,), {'_config': (ParamConfig(*pcfg),), '_supported': frozenset({supported}),
-                                  '_factor': staticmethod(factor), '_divide': divide})
+                                  '_factor': staticmethod(factor), '_divide': divide, '_velocity': velocity})
 
 
 _C_KMS = 299792.458  # conv.py:383
 ZAShift = _shift('ZAShift', 'add', ('z', 0.0, -0.999, 15.0, False, True), lambda z: 1.0 + z, divide=True)
 ZMShift = _shift('ZMShift', 'mul', ('z', 0.0, -0.999, 15.0, False, True), lambda z: 1.0 + z)
-VAShift = _shift('VAShift', 'add', ('v', 0.0, -1e4, 1e4, False, True), lambda v: 1.0 - v / _C_KMS)
-VMShift = _shift('VMShift', 'mul', ('v', 0.0, -1e4, 1e4, False, True), lambda v: 1.0 - v / _C_KMS)
+VAShift = _shift('VAShift', 'add', ('v', 0.0, -1e4, 1e4, False, True), lambda v: 1.0 - v / _C_KMS, velocity=True)
+VMShift = _shift('VMShift', 'mul', ('v', 0.0, -1e4, 1e4, False, True), lambda v: 1.0 - v / _C_KMS, velocity=True)
 
 
 class _FluxNorm(ConvolutionComponent):
@@ -410,9 +415,12 @@ class CompiledModel:
         # distinct components in the reference's order (naming, free parameters)
         self.leaves: list[Component] = model._leaves()
         # the program: one entry per (component, energy-shift context), flux normalisations, postfix ops
-        self.entries: list[tuple] = []  # (component, grid_scale, out_scale, norm_grid_scale, norm_out_scale)
+        # (component, grid_scale, out_scale, norm_grid_scale, norm_out_scale, in_norm, free shifts around it)
+        self.entries: list[tuple] = []
         self.norms: list[_FluxNorm] = []
-        self.ops: list[int] = self._emit(model, (1.0, 1.0, 1.0, 1.0, False))
+        self.ops: list[int] = self._emit(model, (1.0, 1.0, 1.0, 1.0, False, ()))
+        if self.norms and any(e[6] for e in self.entries):
+            raise NotImplementedError('a free energy shift together with a flux normalisation (PhFlux / EnFlux)')
         if len(self.entries) > _lib.MAX_COMPONENTS:
             raise NotImplementedError(f'more than {_lib.MAX_COMPONENTS} components in one model')
         # component display names: PowerLaw, PowerLaw_2, ... (models/model.py naming)
@@ -435,14 +443,18 @@ class CompiledModel:
         self._plan_key = None
 
     def _emit(self, m: Model, ctx) -> list[int]:
-        gs, os_, ngs, nos, in_norm = ctx
+        gs, os_, ngs, nos, in_norm, shifts = ctx
         if isinstance(m, ConvolvedModel):
             op = m.op
             if isinstance(op, _Shift):
                 f = op.factor()
+                if f is None:  # free z / v: the leaves below carry it as a dual-number factor
+                    if len(shifts) >= _lib.MAX_SHIFTS:
+                        raise NotImplementedError(f'more than {_lib.MAX_SHIFTS} nested free energy shifts')
+                    return self._emit(m.inner, (gs, os_, ngs, nos, in_norm, shifts + (op,)))
                 g = 1.0 / f if op._divide else 1.0
                 return self._emit(m.inner, (gs * f, os_ * g, ngs * f if in_norm else ngs,
-                                            nos * g if in_norm else nos, in_norm))
+                                            nos * g if in_norm else nos, in_norm, shifts))
             if isinstance(op, _FluxNorm):
                 if in_norm:
                     raise NotImplementedError('nested flux normalisations (PhFlux / EnFlux) are not supported')
@@ -450,16 +462,22 @@ class CompiledModel:
                     raise NotImplementedError(f'more than {_lib.MAX_NORMS} flux normalisations in one model')
                 k = len(self.norms)
                 self.norms.append(op)
-                return self._emit(m.inner, (gs, os_, 1.0, 1.0, True)) + [_lib.OP_NORM0 - k]
+                return self._emit(m.inner, (gs, os_, 1.0, 1.0, True, shifts)) + [_lib.OP_NORM0 - k]
             raise NotImplementedError(f'convolution component {op.name}')
         if isinstance(m, CompositeModel):
             return self._emit(m.lhs, ctx) + self._emit(m.rhs, ctx) + [_lib.OP_ADD if m.op == '+' else _lib.OP_MUL]
         if not isinstance(m, Component) or m.type == 'conv':
             raise TypeError(f'cannot compile {m!r}')
         # ZAShift's 1 / (1 + z) acts on the additive factor of each term of the shifted sum
-        key = (m, gs, os_ if m.type == 'add' else 1.0, ngs, (nos if m.type == 'add' else 1.0), in_norm)
+        if shifts and isinstance(m, PhotonAbsorption):
+            raise NotImplementedError('a free energy shift around a table component (PhAbs / TBAbs / WAbs)')
+        # (shift kind, parameter): ZAShift's division acts on additive leaves only, like its fixed form
+        free_shifts = tuple((_lib.SHIFT_V if op._velocity else (_lib.SHIFT_ZA if op._divide and m.type == 'add' else _lib.SHIFT_Z),
+                             op.shift_param) for op in shifts)
+        key = (m, gs, os_ if m.type == 'add' else 1.0, ngs, (nos if m.type == 'add' else 1.0), in_norm, free_shifts)
         for i, e in enumerate(self.entries):
-            if e[0] is m and e[1:] == key[1:]:
+            if e[0] is m and e[1:6] == key[1:6] and len(e[6]) == len(free_shifts) and all(
+                    a[0] == b[0] and a[1] is b[1] for a, b in zip(e[6], free_shifts)):
                 return [i]
         self.entries.append(key)
         return [len(self.entries) - 1]
@@ -476,9 +494,14 @@ class CompiledModel:
         """Build the C descriptor; ``free`` is the global free-parameter list of a joint
         fit (columns of theta), defaulting to this model's own.  Returns (ModelDesc, keepalive)."""
         comps = (_lib.ComponentDesc * len(self.entries))()
-        for i, (c, gs, os_, ngs, nos, _) in enumerate(self.entries):
+        for i, (c, gs, os_, ngs, nos, _, free_shifts) in enumerate(self.entries):
             d = comps[i]
             d.grid_scale, d.out_scale, d.norm_grid_scale, d.norm_out_scale = gs, os_, ngs, nos
+            for k, (kind, sp) in enumerate(free_shifts):
+                j = self.column_of(sp, free)
+                if j < 0:
+                    raise ValueError(f'the free shift parameter {sp.name} is not among the fit parameters')
+                d.shift_kind[k], d.shift_src[k] = kind, j
             d.kind = c._kind
             d.method = _lib.METHOD[c.method]
             for k in range(_lib.MAX_COMP_PARAMS):

@@ -123,6 +123,10 @@ extern "C" {
  * that same sub-expression (times keV_to_erg * sqrt(e_j e_j+1) for EnFlux).              */
 #define ELISA_OP_NORM0 -16
 #define ELISA_MAX_NORMS 2
+#define ELISA_MAX_SHIFTS 2 /* FREE energy shifts (z / v a fit parameter) around one component */
+#define ELISA_SHIFT_Z 1
+#define ELISA_SHIFT_ZA 2
+#define ELISA_SHIFT_V 3
 #define ELISA_NORM_PHFLUX 0 /* conv.py:185-195 */
 #define ELISA_NORM_ENFLUX 1 /* conv.py:244-256 */
 
@@ -161,6 +165,16 @@ typedef struct ElisaComponentDesc {
      * normalised sub-expression only).                                               */
     double grid_scale, out_scale;
     double norm_grid_scale, norm_out_scale;
+    /* The same shifts with a FREE z or v (an ordinary fit parameter, conv.py:294-300): up to
+     * ELISA_MAX_SHIFTS entries around the component.  shift_kind[k]: 0 = none, ELISA_SHIFT_Z = the grid
+     * is multiplied by 1 + z, ELISA_SHIFT_ZA = the same and the bin values are divided by 1 + z
+     * (ZAShift around an additive component), ELISA_SHIFT_V = the grid is multiplied by 1 - v / c
+     * (c = 299792.458 km/s); shift_src[k] = the theta column of z / v.  The factor then is a dual
+     * number: the component is differentiated with respect to its energy grid as well.  Needs the
+     * runtime-specialised kernel; not available for table components or together with flux
+     * normalisations (ELISA_ERR_UNSUPPORTED).                                                  */
+    int32_t shift_kind[ELISA_MAX_SHIFTS];
+    int32_t shift_src[ELISA_MAX_SHIFTS];
 } ElisaComponentDesc;
 
 /* One PhFlux / EnFlux normalisation (models/conv.py:21-143).                        */

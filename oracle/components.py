@@ -320,11 +320,13 @@ def eval_component(name, egrid, params, method='trapz', **extra):
 
 # --------------------------------------------------------------------------- convolution components
 def _shift_factor(x):
-    """The shift parameter is fixed on this path: one value for the whole batch."""
+    """z or v: one value (fixed shift) or one per row (a free shift parameter; the row axis broadcasts
+    against the energy axis like every other parameter)."""
+    x = x if isinstance(x, torch.Tensor) else _t(x)
     v = x.reshape(-1)
-    if not bool(torch.all(v == v[0])):
-        raise NotImplementedError('oracle: the shift parameter must be the same for every row')
-    return float(v[0])
+    if not x.requires_grad and bool(torch.all(v == v[0])):
+        return float(v[0])  # a fixed shift: the grid stays one-dimensional, as in the reference
+    return x
 
 
 def eval_convolution(name, egrid, params, model_fn, **extra):

@@ -101,7 +101,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_matches_header(lib):
     # 4 bytes of padding before the doubles; two table pointers, table_len + padding, four scales
-    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16 + 8 + 8 + 8 + 32
+    assert C.sizeof(_lib.ComponentDesc) == 4 + 4 + 5 * 4 + 4 + 5 * 8 + 16 + 8 + 8 + 8 + 32 + 2 * 4 + 2 * 4
     for which, st in enumerate((_lib.ComponentDesc, _lib.NormDesc, _lib.ModelDesc, _lib.SpectrumDesc, _lib.PlanDesc)):
         assert lib.elisa_b200_sizeof(which) == C.sizeof(st), st.__name__
     assert _lib.PlanDesc.chunk.offset == 24 and _lib.SpectrumDesc.exposure.offset % 8 == 0

@@ -249,11 +249,29 @@ def test_convolution_host_rules():
         M.PowerLaw() + M.ZAShift()  # not applied to a model yet
     with pytest.raises(ValueError):
         M.PhFlux(10.0, 1.0)
-    z = M.UniformParameter('z', 0.5, 0.0, 3.0)
-    with pytest.raises(NotImplementedError):
-        M.ZAShift(z=z)(M.PowerLaw()).compile()  # free shift
     with pytest.raises(NotImplementedError):
         M.PhFlux(1.0, 10.0)(M.EnFlux(1.0, 10.0)(M.PowerLaw(K=1.0))).compile()  # nested normalisation
+    # a FREE shift parameter is a column of theta after the wrapped model's own (model.py:1917-1919) and a
+    # dual-number factor of the leaves below it; ZAShift's division reaches the additive leaves only
+    from elisa_b200 import _lib
+
+    z = M.UniformParameter('z', 0.5, 0.0, 3.0)
+    v = M.UniformParameter('v', 100.0, -1e4, 1e4)
+    cm = M.ZAShift(z=z)(M.VMShift(v=v)(M.ExpAbs()) * M.PowerLaw() + M.ZAShift(z=0.25)(M.CutoffPL())).compile()
+    assert cm.params_name == ['ExpAbs.Ec', 'VMShift.v', 'PowerLaw.alpha', 'PowerLaw.K', 'CutoffPL.alpha', 'CutoffPL.Ec', 'CutoffPL.K',
+                              'ZAShift_2.z']  # the inner, fixed ZAShift is 'ZAShift'
+    kinds = [[(k, p.name) for k, p in e[6]] for e in cm.entries]
+    assert kinds == [[(_lib.SHIFT_Z, 'z'), (_lib.SHIFT_V, 'v')], [(_lib.SHIFT_ZA, 'z')], [(_lib.SHIFT_ZA, 'z')]]
+    assert cm.entries[2][1:3] == (1.25, 1.0 / 1.25) and cm.entries[0][1:3] == (1.0, 1.0)  # the fixed shift stays a scale
+    md, _keep = cm.to_desc()
+    assert [md.components[0].shift_kind[k] for k in range(2)] == [_lib.SHIFT_Z, _lib.SHIFT_V]
+    assert [md.components[0].shift_src[k] for k in range(2)] == [7, 1]
+    assert md.components[2].shift_kind[0] == _lib.SHIFT_ZA and md.components[2].shift_kind[1] == 0
+    with pytest.raises(NotImplementedError):  # more than two nested free shifts
+        z2, z3 = M.UniformParameter('z', 0.1, 0.0, 3.0), M.UniformParameter('z', 0.2, 0.0, 3.0)
+        M.ZAShift(z=z)(M.ZAShift(z=z2)(M.ZAShift(z=z3)(M.PowerLaw()))).compile()
+    with pytest.raises(NotImplementedError):  # together with a flux normalisation
+        M.PhFlux(1.0, 10.0)(M.ZAShift(z=z)(M.PowerLaw(K=1.0))).compile()
     cm = M.EnFlux(1.0, 10.0)(M.ZAShift(z=0.2)(M.CutoffPL(K=1.0))).compile()
     # the wrapped model's parameters first, then the convolution's own; fixed z is not a column
     assert cm.params_name == ['CutoffPL.alpha', 'CutoffPL.Ec', 'EnFlux.F']
@@ -326,3 +344,41 @@ def test_phflux_of_a_powerlaw_is_plphflux():
     a = eval_model(M.PhFlux(1.0, 10.0)(M.PowerLaw(K=1.0)).compile().to_spec(), eg, theta).numpy()
     b = eval_model(M.PLPhFlux(1.0, 10.0).compile().to_spec(), eg, theta).numpy()
     assert np.allclose(a, b, rtol=1e-12, atol=0.0)
+
+
+def test_oracle_free_shift_rows_equal_fixed_shift():
+    """A FREE z / v in the oracle (one factor per row, models/conv.py:294-300 under the reference's vmap over rows)
+    gives, row by row, what the FIXED shift gives -- the form tests/golden/conv.npz pins to the reference."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from parity import oracle_eval
+    from elisa_b200 import FixedData
+    from elisa_b200 import models as M
+
+    rng = np.random.default_rng(4)
+    g = np.geomspace(0.5, 120.0, 97)
+    C = 24
+    R = np.abs(rng.standard_normal((g.size - 1, C))) + 0.05
+    counts = rng.poisson(60.0, C).astype(float)
+    d = FixedData('d', g, counts, 0.5 + rng.random(C), 2.0, response_matrix=R)
+    base = np.array([1.2, 40.0, 2.0, 6.4, 0.3, 1.5])
+    for zz, vv in ((0.0, 0.0), (0.7, -3000.0), (2.5, 9000.0)):
+        z = M.UniformParameter('z', 0.5, -0.9, 5.0)
+        v = M.UniformParameter('v', 100.0, -1e4, 1e4)
+        free = M.ZAShift(z=z)(M.CutoffPL() + M.VAShift(v=v)(M.Gauss()))
+        fixed = M.ZAShift(z=zz)(M.CutoffPL() + M.VAShift(v=vv)(M.Gauss()))
+        names = free.compile().params_name
+        assert names[-2:] == ['VAShift.v', 'ZAShift.z'], names
+        ll_free, g_free = oracle_eval(dict(data=[d], model=[free], stat=['cstat'], theta=np.concatenate([base, [vv, zz]])[None]))
+        ll_fix, g_fix = oracle_eval(dict(data=[d], model=[fixed], stat=['cstat'], theta=base[None]))
+        assert np.allclose(ll_free, ll_fix, rtol=1e-13, atol=0.0)
+        assert np.allclose(g_free[..., :6], g_fix, rtol=1e-11, atol=1e-9)
+        # d/dz against a central difference of the fixed-shift value
+        h = 1e-5
+        lp, _ = oracle_eval(dict(data=[d], model=[M.ZAShift(z=zz + h)(M.CutoffPL() + M.VAShift(v=vv)(M.Gauss()))], stat=['cstat'],
+                                 theta=base[None]), grad=False)
+        lm, _ = oracle_eval(dict(data=[d], model=[M.ZAShift(z=zz - h)(M.CutoffPL() + M.VAShift(v=vv)(M.Gauss()))], stat=['cstat'],
+                                 theta=base[None]), grad=False)
+        fd = (lp - lm) / (2 * h)
+        assert np.allclose(g_free[..., 7], fd, rtol=2e-6), (g_free[..., 7], fd)
