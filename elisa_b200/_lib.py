@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ELISA_B200_LIB: another build of the library (A/B runs of kernel variants, tools/ab_lib.sh)
 LIB_PATH = os.environ.get('ELISA_B200_LIB') or os.path.join(HERE, 'lib', 'libelisa_b200.so')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_COMP_PARAMS = 5
 MAX_COMPONENTS = 16
 MAX_PARAMS = 32

@@ -58,7 +58,7 @@ typedef long long int64_t;
 extern "C" {
 #endif
 
-#define ELISA_B200_ABI_VERSION 5
+#define ELISA_B200_ABI_VERSION 6
 
 /* ---- error codes ---------------------------------------------------------------- */
 #define ELISA_OK 0
