@@ -456,13 +456,23 @@ __device__ __forceinline__ I8Item i8_item(const FoldI8Args& a, int item) {
 #define I8_FOR_EACH_TILE(it, a, nt) \
     for (int nt = (it).g * I8_GROUP, ne_ = min(nt + I8_GROUP, (a).n_tiles); nt < ne_; ++nt)
 
+// Registers per thread of the fold kernel.  One persistent CTA per SM owns the shared memory whatever it
+// is compiled to; what its REGISTER footprint decides is whether blocks of the FP64-pipe kernels of the
+// neighbouring chunk (component evaluation, statistic, contraction: no shared memory to speak of) can be
+// resident next to it.  -DI8_MAXNREG=n caps it ("Two chunks in flight").
+#ifdef I8_MAXNREG
+#define I8_KERNEL_BOUNDS __maxnreg__(I8_MAXNREG)  // (nvcc refuses __launch_bounds__ next to it)
+#else
+#define I8_KERNEL_BOUNDS __launch_bounds__(I8_THREADS, 1)
+#endif
+
 template <int V>
 struct I8Int {
     static constexpr int value = V;
 };
 
 template <int KS, class Epi, int NI = Epi::ISSUERS>
-__global__ void __launch_bounds__(I8_THREADS, 1)
+__global__ void I8_KERNEL_BOUNDS
 fold_i8_kernel(const __grid_constant__ FoldI8Args a, const __grid_constant__ Epi epi) {
     constexpr int NA = i8_na(KS);
     constexpr int B_BLOCK = KS * I8_B_SLICE;
