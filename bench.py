@@ -374,6 +374,23 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
                        'engine': engine(lk), 'parity': parity_of(cfg, lk, 256), 'fallback_rows': lk.fallback_rows}
         lk.close()
         del th
+    # ---- cfg 2 at the north star's OTHER tolerance ("an FP32 variant with a stated tolerance": 1e-5 relative on
+    # the statistic and its gradient): 4 digits per operand = 10 + 10 digit products instead of 21 + 21; everything
+    # outside the folds stays FP64.  A side line: the headline is the 1e-10 path.
+    if rank == 0:
+        cfg = synthetic.config2(n=200_000)
+        lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, fold='i8', slices=4, slices_bwd=4)
+        th = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+        ms = _time_calls(torch, lambda: lk.loglike_and_grad(th), 3)
+        par = parity_of(cfg, lk, 256)
+        if par is not None:
+            par['tolerance'] = 1e-5
+            par['pass'] = bool(max(par['max_rel_value'], par['max_rel_grad_batchnorm'], par['max_rel_grad_rownorm']) <= 1e-5)
+        out['cfg2_tol1e-5'] = {'what': 'cfg2 (CutoffPL+Blackbody wstat 1024ch x 2048E) with the fold at 4 digits per operand: the '
+                                       '1e-5 tolerance class of the north star, 2e5 draws, 1 GPU, unguarded',
+                               'evals_s': len(th) / ms * 1e3, 'ms': ms, 'engine': engine(lk), 'parity': par}
+        lk.close()
+        del th
     # ---- cfg 3: Band, 4 GBM-like detectors, pgstat, 64 chains (8 per GPU at N = 8): latency per leapfrog
     cfg = synthetic.config3(n=64)
     lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, guard='lazy')
