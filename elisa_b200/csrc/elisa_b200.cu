@@ -1164,7 +1164,30 @@ static int popcount32(uint32_t v) {
     for (; v; v &= v - 1) ++n;
     return n;
 }
-static size_t tiny_smem_bytes(int E, int P) { return tiny_smem_doubles(E, P) * 8; }
+// launch shape of the small-batch kernel: compiled defaults, or ELISA_B200_TINY_TUNE="threads,split,unroll"
+// (threads a multiple of 32 * split, <= 1024; the same numbers are written into the generated translation unit)
+struct TinyTune {
+    int threads = TINY_THREADS, split = TINY_SPLIT, unroll = TINY_UNROLL;
+    bool custom = false;
+};
+static const TinyTune& tiny_tune() {
+    static const TinyTune t = [] {
+        TinyTune v;
+        if (const char* env = getenv("ELISA_B200_TINY_TUNE")) {
+            int a = 0, b = 0, c = 0;
+            if (sscanf(env, "%d,%d,%d", &a, &b, &c) == 3 && b >= 1 && b <= 32 && a >= 32 * b && a <= 1024 && a % (32 * b) == 0 &&
+                c >= 1 && c <= 32) {
+                v.threads = a;
+                v.split = b;
+                v.unroll = c;
+                v.custom = true;
+            }
+        }
+        return v;
+    }();
+    return t;
+}
+static size_t tiny_smem_bytes(int E, int P) { return tiny_smem_doubles(E, P, tiny_tune().threads, tiny_tune().split) * 8; }
 static bool tiny_shape_ok(int E, int C, int P, uint32_t used_mask) {
     return P <= 8 && (int64_t)E * C * (1 + popcount32(used_mask)) <= TINY_MAX_WORK && tiny_smem_bytes(E, P) <= 48 * 1024;
 }
@@ -1814,6 +1837,9 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks, int 
         snprintf(buf, sizeof buf, "0x%xu", m.used_mask);
         s += std::string("#define UNFOLD_USED_MASK ") + buf + "\n";
     }
+    if (tiny_tune().custom)
+        s += "#define TINY_THREADS_CFG " + std::to_string(tiny_tune().threads) + "\n#define TINY_SPLIT_CFG " +
+             std::to_string(tiny_tune().split) + "\n#define TINY_UNROLL_CFG " + std::to_string(tiny_tune().unroll) + "\n";
     s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\n";
     s += generate_model_struct(m, P, false, "ModelV");
     s += generate_model_struct(m, P, true, "ModelG");
@@ -2506,7 +2532,7 @@ static int launch_tiny(ElisaPlan* plan, int s0, int count, const double* theta, 
     for (int s = s0; s < s0 + count; ++s) smem = std::max(smem, tiny_smem_bytes(plan->spec[s].E, plan->P));
     ScopedSpan span(plan, ELISA_PROFILE_TINY, st);
     void* kargs[] = {(void*)&k};
-    CUDA_TRY(cudaLaunchKernel((const void*)plan->spec[s0].jit->tiny, dim3(n, count), dim3(TINY_THREADS), kargs, smem, st));
+    CUDA_TRY(cudaLaunchKernel((const void*)plan->spec[s0].jit->tiny, dim3(n, count), dim3(tiny_tune().threads), kargs, smem, st));
     ++plan->launches;
     return ELISA_OK;
 }

@@ -450,13 +450,25 @@ struct TinyCall {      // per launch: spectra [s0, s0 + gridDim.y) of the plan, 
     double* grad;      // [n, S, P] or nullptr (value only)
 };
 
-constexpr int TINY_THREADS = 256;
-constexpr int TINY_SPLIT = 2;  // the contraction over the energies is dealt to this many thread groups per channel
+// Launch shape: the generated translation unit may override the three numbers (the host reads the same ones from
+// ELISA_B200_TINY_TUNE = "threads,split,unroll" -- a tuning hook, tools/small_batch_latency.py).
+#ifndef TINY_THREADS_CFG
+#define TINY_THREADS_CFG 256
+#endif
+#ifndef TINY_SPLIT_CFG
+#define TINY_SPLIT_CFG 2
+#endif
+#ifndef TINY_UNROLL_CFG
+#define TINY_UNROLL_CFG 8
+#endif
+constexpr int TINY_THREADS = TINY_THREADS_CFG;
+constexpr int TINY_SPLIT = TINY_SPLIT_CFG;  // the contraction over the energies is dealt to this many thread groups per channel
+constexpr int TINY_UNROLL = TINY_UNROLL_CFG;  // independent loads of the response in flight per thread
 
 // shared memory (doubles): u [E] | du/dtheta [NP][E] | partial folds [TINY_SPLIT][1 + NP][CG] | warp sums [warps][1 + NP]
 // with CG = TINY_THREADS / TINY_SPLIT channels per pass
-__host__ __device__ inline size_t tiny_smem_doubles(int E, int NP) {
-    return (size_t)(1 + NP) * E + (size_t)TINY_SPLIT * (1 + NP) * (TINY_THREADS / TINY_SPLIT) + (size_t)(TINY_THREADS / 32) * (1 + NP);
+__host__ __device__ inline size_t tiny_smem_doubles(int E, int NP, int threads = TINY_THREADS, int split = TINY_SPLIT) {
+    return (size_t)(1 + NP) * E + (size_t)split * (1 + NP) * (threads / split) + (size_t)(threads / 32) * (1 + NP);
 }
 
 template <class Model, int NP, int STAT>
@@ -524,12 +536,12 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
         if (c < C) {
             const double* r = R + c;
             int e = e_lo;
-            for (; e + 8 <= e_hi; e += 8) {
-                double rv[8];
+            for (; e + TINY_UNROLL <= e_hi; e += TINY_UNROLL) {
+                double rv[TINY_UNROLL];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) rv[k] = r[(size_t)(e + k) * ldr];
+                for (int k = 0; k < TINY_UNROLL; ++k) rv[k] = r[(size_t)(e + k) * ldr];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < TINY_UNROLL; ++k) {
                     x = fma(rv[k], su[e + k], x);
                     if (want_grad) {
 #pragma unroll

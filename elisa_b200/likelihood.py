@@ -37,6 +37,14 @@ def _dev_ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _raw_stream(torch, device):
+    """cudaStream_t of torch's current stream on `device` as an integer (no Stream object)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(device)
+    except AttributeError:  # an older / newer torch without the private accessor
+        return torch.cuda.current_stream(device).cuda_stream
+
+
 _SMALL_BATCH_ROWS = 1024  # TINY_MAX_N of the library: calls up to this size take the one-kernel path where a spectrum qualifies
 
 
@@ -188,6 +196,8 @@ class Likelihood:
         self._dev_str = f'cuda:{self.device}'
         self._fb = C.c_int64(0)
         self._all_small_batch = all(self.small_batch_kernel)
+        self._S = len(self.data)
+        self._f_grad, self._f_val = self._lib.elisa_b200_loglike_grad_dev, self._lib.elisa_b200_loglike_dev
 
     # -- lifetime ------------------------------------------------------------------
     def close(self):
@@ -336,8 +346,31 @@ class Likelihood:
         return self._torch.cuda.device(self.device)
 
     # -- device API (torch tensors in, torch tensors out) ----------------------------
+    def _evaluate_small(self, t, want_grad: bool):
+        """The leapfrog path: a small batch already on the device, every spectrum on the one-kernel path (plain FP64, no
+        guard to consult).  The kernel takes ~12 us, so what this method spends is the rate of a sampler that calls it
+        back to back: no tensor conversion, no device context, no stream object, plain integers through ctypes."""
+        torch = self._torch
+        n = t.shape[0]
+        out = torch.empty((n, self._S), dtype=torch.float64, device=t.device)
+        stream = _raw_stream(torch, self.device)
+        if want_grad:
+            grad = torch.empty((n, self._S, self._P), dtype=torch.float64, device=t.device)
+            rc = self._f_grad(self._h, t.data_ptr(), None, None, n, out.data_ptr(), grad.data_ptr(), stream)
+        else:
+            grad = None
+            rc = self._f_val(self._h, t.data_ptr(), None, None, n, out.data_ptr(), stream)
+        if rc:
+            _lib.check(rc)
+        return out, grad
+
     def _evaluate(self, theta, counts_on, counts_off, want_grad: bool, guard):
         torch = self._torch
+        if (self._all_small_batch and counts_on is None and counts_off is None and type(theta) is torch.Tensor
+                and theta.is_cuda and theta.dtype is torch.float64 and theta.dim() == 2 and theta.shape[1] == self.nparam
+                and 0 < theta.shape[0] <= _SMALL_BATCH_ROWS and self.nparam > 0 and theta.is_contiguous()
+                and theta.device.index == self.device and torch.cuda.current_device() == self.device):
+            return self._evaluate_small(theta, want_grad)
         mode = self.guard_mode if guard is None else (guard if self._auto_guard else 'off')
         with self._device_ctx():
             t = self._theta(theta)
@@ -374,7 +407,7 @@ class Likelihood:
         """((N, S), (N, S, P)): value and d loglike[n, s] / d theta[n, :] -- what
         jax.value_and_grad of each dataset's log-likelihood returns upstream."""
         out, grad = self._evaluate(theta, counts_on, counts_off, True, guard)
-        return out, grad[:, :, : self.nparam]
+        return out, (grad if self._P == self.nparam else grad[:, :, : self.nparam])
 
     def normal_equations(self, theta, counts_on=None, counts_off=None, guard: bool = True):
         """(loglike (N,), grad (N, P), jtj (N, P, P)) of the deviance residuals
