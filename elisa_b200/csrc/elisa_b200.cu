@@ -1164,10 +1164,11 @@ static int popcount32(uint32_t v) {
     for (; v; v &= v - 1) ++n;
     return n;
 }
-// launch shape of the small-batch kernel: compiled defaults, or ELISA_B200_TINY_TUNE="threads,split,unroll"
-// (threads a multiple of 32 * split, <= 1024; the same numbers are written into the generated translation unit)
+// launch shape of the small-batch kernel: compiled defaults, or ELISA_B200_TINY_TUNE="threads,channels per thread,unroll"
+// (threads a multiple of 32 and >= 32 * channels per thread; 0 channels = by the number of parameters; the same numbers
+// are written into the generated translation unit)
 struct TinyTune {
-    int threads = TINY_THREADS, split = TINY_SPLIT, unroll = TINY_UNROLL;
+    int threads = TINY_THREADS, ch = 0, unroll = TINY_UNROLL;
     bool custom = false;
 };
 static const TinyTune& tiny_tune() {
@@ -1175,10 +1176,10 @@ static const TinyTune& tiny_tune() {
         TinyTune v;
         if (const char* env = getenv("ELISA_B200_TINY_TUNE")) {
             int a = 0, b = 0, c = 0;
-            if (sscanf(env, "%d,%d,%d", &a, &b, &c) == 3 && b >= 1 && b <= 32 && a >= 32 * b && a <= 1024 && a % (32 * b) == 0 &&
-                c >= 1 && c <= 32) {
+            if (sscanf(env, "%d,%d,%d", &a, &b, &c) == 3 && b >= 0 && b <= 8 && a >= 32 * std::max(b, 4) && a <= 1024 && a % 32 == 0 &&
+                c >= 1 && c <= 16) {
                 v.threads = a;
-                v.split = b;
+                v.ch = b;
                 v.unroll = c;
                 v.custom = true;
             }
@@ -1187,9 +1188,10 @@ static const TinyTune& tiny_tune() {
     }();
     return t;
 }
-static size_t tiny_smem_bytes(int E, int P) { return tiny_smem_doubles(E, P, tiny_tune().threads, tiny_tune().split) * 8; }
+constexpr size_t TINY_MAX_SMEM = 96 * 1024;  // opt-in dynamic shared memory of the kernel (two CTAs per SM still fit)
+static size_t tiny_smem_bytes(int E, int P) { return tiny_smem_doubles(E, P, tiny_tune().threads, tiny_tune().ch) * 8; }
 static bool tiny_shape_ok(int E, int C, int P, uint32_t used_mask) {
-    return P <= 8 && (int64_t)E * C * (1 + popcount32(used_mask)) <= TINY_MAX_WORK && tiny_smem_bytes(E, P) <= 48 * 1024;
+    return P <= 8 && (int64_t)E * C * (1 + popcount32(used_mask)) <= TINY_MAX_WORK && tiny_smem_bytes(E, P) <= TINY_MAX_SMEM;
 }
 
 static int build_spectrum(ElisaPlan* plan, const ElisaSpectrumDesc& sd, SpectrumPlan* sp) {
@@ -1838,8 +1840,8 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks, int 
         s += std::string("#define UNFOLD_USED_MASK ") + buf + "\n";
     }
     if (tiny_tune().custom)
-        s += "#define TINY_THREADS_CFG " + std::to_string(tiny_tune().threads) + "\n#define TINY_SPLIT_CFG " +
-             std::to_string(tiny_tune().split) + "\n#define TINY_UNROLL_CFG " + std::to_string(tiny_tune().unroll) + "\n";
+        s += "#define TINY_THREADS_CFG " + std::to_string(tiny_tune().threads) + "\n#define TINY_CH_CFG " +
+             std::to_string(tiny_tune().ch) + "\n#define TINY_UNROLL_CFG " + std::to_string(tiny_tune().unroll) + "\n";
     s += "#include \"unfold_skel.cuh\"\nusing namespace elisa;\n";
     s += generate_model_struct(m, P, false, "ModelV");
     s += generate_model_struct(m, P, true, "ModelG");
@@ -1918,6 +1920,8 @@ static const JitKernels* jit_unfold(const ModelDev& m, int P, int ks, std::strin
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->grad, k->lib, "unfold_grad");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->contract, k->lib, "unfold_contract");
     if (e == cudaSuccess && tiny_stat >= 0) e = cudaLibraryGetKernel(&k->tiny, k->lib, "tiny_eval_kernel");
+    if (e == cudaSuccess && tiny_stat >= 0)
+        e = cudaFuncSetAttribute((const void*)k->tiny, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TINY_MAX_SMEM);
     if (e != cudaSuccess) {
         *why = std::string("loading the compiled unfold kernels failed: ") + cudaGetErrorString(e);
         delete k;
@@ -2528,11 +2532,25 @@ static int launch_tiny(ElisaPlan* plan, int s0, int count, const double* theta, 
     k.ld_counts = plan->sum_C;
     k.loglike = loglike;
     k.grad = grad;
+    k.clk = nullptr;
+    static const bool clocks = getenv("ELISA_B200_TINY_CLOCKS") != nullptr;  // phase clocks of CTA (0, 0): a diagnostic, synchronises
+    static long long* clk_dev = nullptr;
+    if (clocks) {
+        if (clk_dev == nullptr) CUDA_TRY(cudaMalloc(&clk_dev, 8 * sizeof(long long)));
+        k.clk = clk_dev;
+    }
     size_t smem = 0;
     for (int s = s0; s < s0 + count; ++s) smem = std::max(smem, tiny_smem_bytes(plan->spec[s].E, plan->P));
     ScopedSpan span(plan, ELISA_PROFILE_TINY, st);
     void* kargs[] = {(void*)&k};
     CUDA_TRY(cudaLaunchKernel((const void*)plan->spec[s0].jit->tiny, dim3(n, count), dim3(tiny_tune().threads), kargs, smem, st));
+    if (clocks) {
+        long long h[8];
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpy(h, clk_dev, sizeof h, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "tiny_eval clocks (n = %d x %d spectra): pre %lld, model %lld, barrier %lld, fold %lld, statistic %lld, reduce + store %lld\n",
+                n, count, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5]);
+    }
     ++plan->launches;
     return ELISA_OK;
 }

@@ -448,27 +448,31 @@ struct TinyCall {      // per launch: spectra [s0, s0 + gridDim.y) of the plan, 
     int64_t ld_counts;
     double* loglike;   // [n, S]
     double* grad;      // [n, S, P] or nullptr (value only)
+    long long* clk;    // nullptr, or 8 slots: thread 0 of CTA (0, 0) leaves clock64() at the phase boundaries (ELISA_B200_TINY_CLOCKS)
 };
 
 // Launch shape: the generated translation unit may override the three numbers (the host reads the same ones from
-// ELISA_B200_TINY_TUNE = "threads,split,unroll" -- a tuning hook, tools/small_batch_latency.py).
+// ELISA_B200_TINY_TUNE = "threads,channels per thread,unroll" -- a tuning hook, tools/tiny_tune.py).
 #ifndef TINY_THREADS_CFG
 #define TINY_THREADS_CFG 256
 #endif
-#ifndef TINY_SPLIT_CFG
-#define TINY_SPLIT_CFG 2
+#ifndef TINY_CH_CFG
+#define TINY_CH_CFG 0
 #endif
 #ifndef TINY_UNROLL_CFG
-#define TINY_UNROLL_CFG 8
+#define TINY_UNROLL_CFG 4
 #endif
 constexpr int TINY_THREADS = TINY_THREADS_CFG;
-constexpr int TINY_SPLIT = TINY_SPLIT_CFG;  // the contraction over the energies is dealt to this many thread groups per channel
-constexpr int TINY_UNROLL = TINY_UNROLL_CFG;  // independent loads of the response in flight per thread
+constexpr int TINY_UNROLL = TINY_UNROLL_CFG;  // energies per step of the fold loop: UNROLL x CH independent loads in flight per thread
+// channels per thread of the fold (register blocking: one broadcast read of u_e, du_e/dtheta serves CH channels);
+// 1 + NP accumulators per channel live in registers
+__host__ __device__ constexpr int tiny_ch(int NP, int cfg = TINY_CH_CFG) { return cfg > 0 ? cfg : (NP <= 4 ? 4 : 2); }
 
-// shared memory (doubles): u [E] | du/dtheta [NP][E] | partial folds [TINY_SPLIT][1 + NP][CG] | warp sums [warps][1 + NP]
-// with CG = TINY_THREADS / TINY_SPLIT channels per pass
-__host__ __device__ inline size_t tiny_smem_doubles(int E, int NP, int threads = TINY_THREADS, int split = TINY_SPLIT) {
-    return (size_t)(1 + NP) * E + (size_t)split * (1 + NP) * (threads / split) + (size_t)(threads / 32) * (1 + NP);
+// shared memory (doubles): u [E] | du/dtheta [NP][E] | partial folds [warps][1 + NP][CB] | warp sums [warps][1 + NP]
+// with CB = 32 * channels per thread = channels per pass
+__host__ __device__ inline size_t tiny_smem_doubles(int E, int NP, int threads = TINY_THREADS, int ch = 0) {
+    const int cb = 32 * (ch > 0 ? ch : tiny_ch(NP));
+    return (size_t)(1 + NP) * E + (size_t)(threads / 32) * (1 + NP) * cb + (size_t)(threads / 32) * (1 + NP);
 }
 
 template <class Model, int NP, int STAT>
@@ -484,21 +488,28 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
     const int E = a.gv.E;
     const bool want_grad = k.grad != nullptr;
     const double* theta = k.theta + (size_t)row * k.P;
+    const bool clk = k.clk != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+#define TINY_CLK(i) do { if (clk) k.clk[i] = clock64(); } while (0)
+    TINY_CLK(0);
 #ifdef UNFOLD_USED_MASK
     constexpr uint32_t used = UNFOLD_USED_MASK;
 #else
     const uint32_t used = a.used_mask;
 #endif
-    constexpr int CG = TINY_THREADS / TINY_SPLIT;
+    constexpr int NW = TINY_THREADS / 32;         // warps = groups the energies are dealt to
+    constexpr int CH = tiny_ch(NP);               // channels per thread
+    constexpr int CB = 32 * CH;                   // channels per pass
+    static_assert(CB <= TINY_THREADS, "one thread per channel of a pass does the statistic");
     double* su = tiny_smem;                       // [E]
     double* sd = su + E;                          // [NP][E]
-    double* part = sd + (size_t)NP * E;           // [TINY_SPLIT][1 + NP][CG]
-    double* red = part + (size_t)TINY_SPLIT * (1 + NP) * CG;  // [warps][1 + NP]
+    double* part = sd + (size_t)NP * E;           // [NW][1 + NP][CB]
+    double* red = part + (size_t)NW * (1 + NP) * CB;  // [warps][1 + NP]
     // 1. the model in dual numbers; warp w takes the passes w, w + 8, ...
     {
         typename Model::Pre pre;
         Model::pre(theta, pre);
         Model::norms(pre, a, theta, lane);
+        TINY_CLK(1);
         GridView gv = a.gv;
         gv.has_point = 0;
         for (int e0 = 31 * wib; e0 < E; e0 += 31 * (TINY_THREADS / 32)) {
@@ -514,12 +525,16 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
             }
         }
     }
+    TINY_CLK(2);
     __syncthreads();
-    // 2 + 3. fold and statistic, CG channels per pass; thread (h, cl) folds the energies [h E / SPLIT, (h + 1) E / SPLIT)
-    // of channel c0 + cl -- eight independent loads of the response in flight per thread: the loop is bound by the
-    // latency of L2, not by arithmetic -- and group 0 adds the partial folds in a fixed order and does the statistic
-    const int h = tid / CG, cl = tid % CG;
-    const int e_lo = (int)((int64_t)E * h / TINY_SPLIT), e_hi = (int)((int64_t)E * (h + 1) / TINY_SPLIT);
+    TINY_CLK(3);
+    // 2 + 3. fold and statistic, CB channels per pass.  Warp w folds the energies [w E / NW, (w + 1) E / NW) of the
+    // channels c0 + lane + 32 q, q < CH: u_e and du_e/dtheta are broadcast reads of shared memory, and with one
+    // channel per thread those 1 + NP reads per response element were what bound the loop (r02c clocks: 8.2 k of
+    // 14 k cycles); blocked over CH channels a read serves CH (1 + NP) multiply-adds, and UNROLL x CH loads of the
+    // response are in flight per thread.  Then thread c of the pass adds the NW partial folds in a fixed order
+    // and does the statistic.
+    const int e_lo = (int)((int64_t)E * wib / NW), e_hi = (int)((int64_t)E * (wib + 1) / NW);
     double ll = 0.0, g[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) g[j] = 0.0;
@@ -528,51 +543,70 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
     const int C = t.C, ldr = t.ldr;
     const double* R = t.R;
     const ChanArrays ch = t.ch;
-    for (int c0 = 0; c0 < C; c0 += CG) {
-        const int c = c0 + cl;
-        double x = 0.0, tj[NP];
+    for (int c0 = 0; c0 < C; c0 += CB) {
+        double xq[CH], tq[CH][NP];
+        bool ok[CH];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) tj[j] = 0.0;
-        if (c < C) {
-            const double* r = R + c;
-            int e = e_lo;
-            for (; e + TINY_UNROLL <= e_hi; e += TINY_UNROLL) {
-                double rv[TINY_UNROLL];
+        for (int q = 0; q < CH; ++q) {
+            xq[q] = 0.0;
+            ok[q] = c0 + lane + 32 * q < C;
 #pragma unroll
-                for (int k = 0; k < TINY_UNROLL; ++k) rv[k] = r[(size_t)(e + k) * ldr];
+            for (int j = 0; j < NP; ++j) tq[q][j] = 0.0;
+        }
+        {
+            const double* r = R + c0 + lane;
+            auto step = [&](const double (&rv)[CH], int e) {
+                const double u = su[e];
 #pragma unroll
-                for (int k = 0; k < TINY_UNROLL; ++k) {
-                    x = fma(rv[k], su[e + k], x);
-                    if (want_grad) {
-#pragma unroll
-                        for (int j = 0; j < NP; ++j)
-                            if ((used >> j) & 1u) tj[j] = fma(rv[k], sd[(size_t)j * E + e + k], tj[j]);
-                    }
-                }
-            }
-            for (; e < e_hi; ++e) {
-                const double rv = r[(size_t)e * ldr];
-                x = fma(rv, su[e], x);
+                for (int q = 0; q < CH; ++q) xq[q] = fma(rv[q], u, xq[q]);
                 if (want_grad) {
 #pragma unroll
                     for (int j = 0; j < NP; ++j)
-                        if ((used >> j) & 1u) tj[j] = fma(rv, sd[(size_t)j * E + e], tj[j]);
+                        if ((used >> j) & 1u) {
+                            const double dj = sd[(size_t)j * E + e];
+#pragma unroll
+                            for (int q = 0; q < CH; ++q) tq[q][j] = fma(rv[q], dj, tq[q][j]);
+                        }
                 }
+            };
+            int e = e_lo;
+            for (; e + TINY_UNROLL <= e_hi; e += TINY_UNROLL) {
+                double rv[TINY_UNROLL][CH];
+#pragma unroll
+                for (int i = 0; i < TINY_UNROLL; ++i)
+#pragma unroll
+                    for (int q = 0; q < CH; ++q) rv[i][q] = ok[q] ? __ldg(r + (size_t)(e + i) * ldr + 32 * q) : 0.0;
+#pragma unroll
+                for (int i = 0; i < TINY_UNROLL; ++i) step(rv[i], e + i);
+            }
+            for (; e < e_hi; ++e) {
+                double rv[CH];
+#pragma unroll
+                for (int q = 0; q < CH; ++q) rv[q] = ok[q] ? __ldg(r + (size_t)e * ldr + 32 * q) : 0.0;
+                step(rv, e);
             }
         }
+        if (c0 == 0) TINY_CLK(4);
         if (c0 > 0) __syncthreads();  // the previous pass's partial folds have been consumed
-        part[((size_t)h * (1 + NP)) * CG + cl] = x;
 #pragma unroll
-        for (int j = 0; j < NP; ++j)
-            if ((used >> j) & 1u) part[((size_t)h * (1 + NP) + 1 + j) * CG + cl] = tj[j];
+        for (int q = 0; q < CH; ++q) {
+            part[((size_t)wib * (1 + NP)) * CB + lane + 32 * q] = xq[q];
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                if ((used >> j) & 1u) part[((size_t)wib * (1 + NP) + 1 + j) * CB + lane + 32 * q] = tq[q][j];
+        }
         __syncthreads();
-        if (h == 0 && c < C) {
+        const int c = c0 + tid;
+        if (tid < CB && c < C) {
+            double x = 0.0, tj[NP];
 #pragma unroll
-            for (int q = 1; q < TINY_SPLIT; ++q) {
-                x += part[((size_t)q * (1 + NP)) * CG + cl];
+            for (int j = 0; j < NP; ++j) tj[j] = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                x += part[((size_t)w * (1 + NP)) * CB + tid];
 #pragma unroll
                 for (int j = 0; j < NP; ++j)
-                    if ((used >> j) & 1u) tj[j] += part[((size_t)q * (1 + NP) + 1 + j) * CG + cl];
+                    if ((used >> j) & 1u) tj[j] += part[((size_t)w * (1 + NP) + 1 + j) * CB + tid];
             }
             ChannelData d;
             const double sc = ch.scale[c];
@@ -604,6 +638,7 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
         }
     }
     // fixed-order reduction: lane-serial sums above, xor tree, then the warps of group 0 in order
+    TINY_CLK(5);
     ll = warp_sum(ll);
     if (lane == 0) red[wib * (1 + NP)] = ll;
     if (want_grad) {
@@ -617,12 +652,14 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
     if (tid <= NP && (tid == 0 || want_grad)) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < CG / 32; ++w) s += red[w * (1 + NP) + tid];
+        for (int w = 0; w < (CB < TINY_THREADS ? CB : TINY_THREADS) / 32; ++w) s += red[w * (1 + NP) + tid];
         if (tid == 0)
             k.loglike[(size_t)row * k.S + spec] = s;
         else if (tid - 1 < k.P)
             k.grad[((size_t)row * k.S + spec) * k.P + tid - 1] = s;
     }
+    TINY_CLK(6);
+#undef TINY_CLK
 }
 
 }  // namespace elisa

@@ -1,13 +1,12 @@
 #!/bin/bash
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_tiny.py tests/test_gpu_autograd.py -m gpu -q -x 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_gpu_tiny.py tests/test_gpu_autograd.py tests/test_gpu_free_shift.py -m gpu -q -x 2>&1 | tail -5
 for rep in 1 2; do
-for t in default 512,4,12; do
+for t in default 256,4,2 256,4,8 256,2,8 512,4,4 128,4,4 256,8,2; do
   timeout 120 python tools/tiny_tune.py $t 2>&1 | tail -1
-done; done | tee $OUT/r02ad_tiny_tune.txt
-python tools/small_batch_latency.py 2>&1 | tail -4 | tee $OUT/r02ad_small_batch.txt
-ELISA_B200_TINY_CLOCKS=1 python - <<'PY' 2>&1 | tail -6 | tee gpurun_out/r02ad_tiny_clocks.txt
+done; done | tee $OUT/r02ae_tiny_tune.txt
+ELISA_B200_TINY_CLOCKS=1 python - <<'PY' 2>&1 | tail -4 | tee gpurun_out/r02ae_tiny_clocks.txt
 import torch
 from elisa_b200 import Likelihood, synthetic
 for n in (64, 8):

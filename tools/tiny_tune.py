@@ -27,4 +27,4 @@ for n in (64, 8):
     lk.set_profiling(False)
     out.append(f"n={n}: {call_us:.1f} us/call, kernel {prof['tiny'][0] / max(prof['tiny'][1], 1) * 1e3:.2f} us")
     lk.close()
-print(os.environ.get('ELISA_B200_TINY_TUNE', 'default 256,2,8'), '|', ' | '.join(out), flush=True)
+print(os.environ.get('ELISA_B200_TINY_TUNE', 'default (256 threads, 4 channels per thread for <= 4 parameters else 2, unroll 4)'), '|', ' | '.join(out), flush=True)
