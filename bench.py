@@ -424,14 +424,35 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
     t = torch.tensor([us_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    us_graph = None
+    if rank == 0 and all(lk.small_batch_kernel):
+        # the same call captured once into a CUDA graph by the caller (what a sampler with a captured leapfrog pays)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            lk.loglike_and_grad(th)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            lk.loglike_and_grad(th)
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            graph.replay()
+        torch.cuda.synchronize()
+        us_graph = (time.perf_counter() - t0) / 300 * 1e6
+        del graph
     if rank == 0:
         lk_sync = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
         out['cfg3'] = {'what': 'Band pgstat, 4 detectors 128ch x 140E, 64 chains over %d GPU(s): one leapfrog = one value+gradient '
-                               'call through the Python API (guard=lazy: no host synchronisation, CUDA graph replayed)' % world,
+                               'call through the Python API (no host synchronisation)' % world,
                        'chains_per_gpu': hi - lo, 'us_per_leapfrog': float(t.item()), 'us_per_leapfrog_with_gather': us_gather,
+                       'us_per_leapfrog_in_callers_cuda_graph': us_graph,
                        'evals_s': 64 * 4 / ((us_gather or float(t.item())) * 1e-6),
-                       'engine': ('one kernel per detector (dual-number model + FP64 forward-mode fold + statistic + gradient, '
-                                  'tiny_eval)' if all(lk.small_batch_kernel) else engine(lk)),
+                       'engine': ('one launch for the four detectors (dual-number model + FP64 forward-mode fold + statistic + '
+                                  'gradient, tiny_eval)' if all(lk.small_batch_kernel) else engine(lk)),
                        'parity': parity_of(cfg, lk_sync, 64)}
         lk_sync.close()
     lk.close()

@@ -127,3 +127,35 @@ def test_small_versions_of_the_baseline_configs(lib, k):
     # (the values sit at a few 1e-11 on cfg 1 / 2 / 4 / 5 under EITHER path: x log(mu) - mu - gof cancels four
     # to five digits per channel, so two correctly rounded FP64 evaluations differ by that much)
     assert err['value'] <= RTOL and err['grad'] <= 1e-11, err
+
+
+def test_small_batch_call_inside_a_cuda_graph(lib):
+    """A sampler that captures its leapfrog into a CUDA graph (torch.cuda.graph) can keep the likelihood call inside
+    the capture: the one-kernel path is one launch on the capturing stream -- no allocation of its own, no
+    synchronisation, no guard round trip -- and a replay with new parameter values in place gives bit for bit what a
+    direct call gives."""
+    from elisa_b200 import Likelihood
+
+    cfg = synthetic.config3(n=8)
+    rng = np.random.default_rng(5)
+    theta = torch.as_tensor(cfg['theta'], dtype=torch.float64, device='cuda')
+    with Likelihood(cfg['data'], cfg['model'], cfg['stat']) as lk:
+        assert all(lk.small_batch_kernel)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up on a side stream, as torch's capture recipe asks
+            for _ in range(3):
+                lk.loglike_and_grad(theta)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ll_g, g_g = lk.loglike_and_grad(theta)
+            step = theta + 1e-3 * g_g.sum(dim=1)  # something a sampler would do with the gradient, in the same graph
+        for _ in range(3):
+            new = torch.as_tensor(cfg['theta'] * (1.0 + 0.02 * rng.standard_normal(cfg['theta'].shape)), dtype=torch.float64, device='cuda')
+            theta.copy_(new)
+            graph.replay()
+            torch.cuda.synchronize()
+            ll_d, g_d = lk.loglike_and_grad(new)
+            assert torch.equal(ll_g, ll_d) and torch.equal(g_g, g_d)
+            assert torch.equal(step, new + 1e-3 * g_d.sum(dim=1))
