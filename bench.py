@@ -68,6 +68,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-configs', action='store_true', help='skip the cfg 1/3/4/5 side measurements')
     ap.add_argument('--fold', default=None, choices=['i8', 'dmma'], help='response-fold engine (default: library default)')
+    ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: gather fused into the evaluation (peer-to-peer pushes of finished chunks) or NCCL all-gathers after it')
     ap.add_argument('--slices', type=int, default=0, help='digits of the sliced-integer fold (0 = default)')
     ap.add_argument('--slices-bwd', type=int, default=0, help='digits of its transposed fold (0 = default)')
     return ap.parse_args()
@@ -337,7 +339,7 @@ def _time_calls(torch, fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def side_configs(torch, dist, world, rank, local, with_oracle):
+def side_configs(torch, dist, world, rank, local, with_oracle, peer=False):
     """cfg 1, 3, 4, 5 of BASELINE.json in the same run: evals/s (device-resident inputs, guarded
     entry point), fold engine, and a parity check of a row sample against the oracle.  Under
     torchrun cfg 5 is STRONG-scaled (1e6 draws x 16 spectra split over the ranks, results
@@ -396,7 +398,7 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
     lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local, guard='lazy')
     lo, hi = shard_bounds(64, world)[rank]
     th = torch.as_tensor(cfg['theta'][lo:hi], dtype=torch.float64, device=dev)
-    sh = ShardedLikelihood(lk)
+    sh = ShardedLikelihood(lk, peer=peer)
     full = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
     for _ in range(5):
         lk.loglike_and_grad(th)
@@ -427,23 +429,28 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
     us_graph = None
     if rank == 0 and all(lk.small_batch_kernel):
         # the same call captured once into a CUDA graph by the caller (what a sampler with a captured leapfrog pays)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            lk.loglike_and_grad(th)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            lk.loglike_and_grad(th)
-        for _ in range(5):
-            graph.replay()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(300):
-            graph.replay()
-        torch.cuda.synchronize()
-        us_graph = (time.perf_counter() - t0) / 300 * 1e6
-        del graph
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                lk.loglike_and_grad(th)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread of a torchrun job may touch the device during the capture
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                lk.loglike_and_grad(th)
+            for _ in range(5):
+                graph.replay()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(300):
+                graph.replay()
+            torch.cuda.synchronize()
+            us_graph = (time.perf_counter() - t0) / 300 * 1e6
+            del graph
+        except Exception as exc:  # a side line: never let it take the bench down
+            sys.stderr.write(f'cfg3: capture into a CUDA graph failed: {exc}\n')
+            us_graph = None
     if rank == 0:
         lk_sync = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
         out['cfg3'] = {'what': 'Band pgstat, 4 detectors 128ch x 140E, 64 chains over %d GPU(s): one leapfrog = one value+gradient '
@@ -455,6 +462,7 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
                                   'gradient, tiny_eval)' if all(lk.small_batch_kernel) else engine(lk)),
                        'parity': parity_of(cfg, lk_sync, 64)}
         lk_sync.close()
+    sh.close()
     lk.close()
     # ---- cfg 4: Gauss + PowerLaw, chi2, 4096 x 4096 band-sparse, per-replica counts
     if rank == 0:
@@ -477,7 +485,7 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
     n5 = 1_000_000
     cfg = synthetic.config5(n=n5, S=16)
     lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
-    sh = ShardedLikelihood(lk)
+    sh = ShardedLikelihood(lk, peer=peer)
     th = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
     sh.loglike_and_grad(th)  # warm-up (also balances the plan)
     torch.cuda.synchronize()
@@ -502,7 +510,8 @@ def side_configs(torch, dist, world, rank, local, with_oracle):
         out['cfg5'] = {'what': 'PowerLaw jointly on 16 spectra (distinct dense 1024 x 2048 RSPs, cstat / chi2), 1e6 draws split over '
                                '%d GPU(s), all-gather of [N,16] + [N,16,2] inside the timed region (strong scaling)' % world,
                        'evals_s': n5 * 16 / ms * 1e3, 'ms': ms, 'n_gpus': world, 'engine': engine(lk), 'parity': par,
-                       'fallback_rows': lk.fallback_rows}
+                       'fallback_rows': lk.fallback_rows, 'gather': 'peer pushes fused into the evaluation' if peer and world > 1 else ('NCCL' if world > 1 else None)}
+    sh.close()
     lk.close()
     return out
 
@@ -538,8 +547,36 @@ def run_b200(args):
     ll = torch.empty((n, S), dtype=torch.float64, device=dev)
     grad = torch.empty((n, S, P), dtype=torch.float64, device=dev)
     # results of all ranks, gathered inside the timed region (the one collective)
-    ll_all = torch.empty((world * n, S), dtype=torch.float64, device=dev) if world > 1 else None
-    grad_all = torch.empty((world * n, S, P), dtype=torch.float64, device=dev) if world > 1 else None
+    ll_all = grad_all = pg = None
+    gather_kind = 'none'
+    if world > 1:
+        gather_kind = 'nccl'
+        if args.gather == 'peer':
+            # every rank's FULL result arrays live in CUDA-IPC memory mapped by all; the plan pushes finished chunks
+            # into them while it computes (elisa_b200_plan_set_gather); the ranks agree on whether that came up
+            try:
+                from elisa_b200.parallel import PeerGather
+
+                pg = PeerGather(lk, world * n, sets=1)
+                ll_all, grad_all, lo_, hi_ = pg.begin()  # stays set for the whole run
+                ll, grad = ll_all[lo_:hi_], grad_all[lo_:hi_]
+                up = 1
+            except Exception as exc:
+                sys.stderr.write(f'rank {rank}: peer gather unavailable ({exc}); NCCL all-gather instead\n')
+                up = 0
+            t_up = torch.tensor([up], dtype=torch.int32, device=dev)
+            dist.all_reduce(t_up, op=dist.ReduceOp.MIN)
+            if int(t_up.item()) == 1:
+                gather_kind = 'peer'
+            else:
+                if pg is not None and up:
+                    pg.end()
+                pg = None
+                ll = torch.empty((n, S), dtype=torch.float64, device=dev)
+                grad = torch.empty((n, S, P), dtype=torch.float64, device=dev)
+        if gather_kind == 'nccl':
+            ll_all = torch.empty((world * n, S), dtype=torch.float64, device=dev)
+            grad_all = torch.empty((world * n, S, P), dtype=torch.float64, device=dev)
 
     import ctypes as Ct
 
@@ -557,7 +594,7 @@ def run_b200(args):
             lk._h, Ct.c_void_p(theta.data_ptr()), None, None, n, Ct.c_void_p(ll.data_ptr()), Ct.c_void_p(grad.data_ptr()),
             stream, Ct.byref(fb)))
         fb_rows[0] += int(fb.value)
-        if world > 1:
+        if gather_kind == 'nccl':
             if i is not None:
                 ev_g0[i].record()
             dist.all_gather_into_tensor(ll_all, ll)
@@ -622,7 +659,12 @@ def run_b200(args):
     prof = lk.get_profile()
     lk.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
-    gather_ms = sum(a.elapsed_time(b) for a, b in zip(ev_g0, ev_g1)) / args.steps if world > 1 else 0.0
+    if gather_kind == 'nccl':
+        gather_ms = sum(a.elapsed_time(b) for a, b in zip(ev_g0, ev_g1)) / args.steps
+    elif gather_kind == 'peer':  # what is left of it after the last chunk: the tail pushes and the wait for the peers
+        gather_ms = prof['gather'][0] / args.steps
+    else:
+        gather_ms = 0.0
     t = torch.tensor([ms, gather_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -659,14 +701,19 @@ def run_b200(args):
         del th_host, ll_host, g_host
 
     # ---- 4. the other BASELINE configurations (all ranks take part in the sharded ones)
+    if pg is not None:
+        pg.end()
+        del ll, grad
     del ll_all, grad_all
+    if pg is not None:
+        pg.close()
     lk_chunk, lk_ws = lk.chunk, lk.workspace_bytes
     products = lk.fold_products(0) if ks else (0.0, 0.0)  # digit products EXECUTED per FP64 multiply-add
     configs = None
     if not args.no_configs:
         lk.close()
         torch.cuda.empty_cache()
-        configs = side_configs(torch, dist, world, rank, local, with_oracle)
+        configs = side_configs(torch, dist, world, rank, local, with_oracle, peer=(gather_kind == 'peer'))
 
     if rank != 0:
         if world > 1:
@@ -744,8 +791,13 @@ def run_b200(args):
                    'n_params': P, 'chunk': lk_chunk, 'parallelism': f'dp{world} over draws',
                    'fold_engine': f'int8 tcgen05 sliced, {ks} digits forward / {ks_bwd} transposed' if ks else 'FP64 DMMA',
                    'entry_point': 'elisa_b200_loglike_grad_guarded_dev (value), elisa_b200_loglike_grad_host (e2e)',
-                   'collective': ('NCCL all_gather_into_tensor of loglike [N,S] and grad [N,S,P] of all ranks inside the timed '
-                                  'region, %.3f ms per step' % gather_ms) if world > 1 else 'none (1 GPU)',
+                   'collective': {'nccl': 'NCCL all_gather_into_tensor of loglike [N,S] and grad [N,S,P] of all ranks inside the timed '
+                                          'region, %.3f ms per step' % gather_ms,
+                                  'peer': 'gather fused into the evaluation: every few finished chunks are pushed into every rank\'s full '
+                                          '[N,S] + [N,S,P] arrays (CUDA IPC) by the copy engines over NVLink while the next chunks are '
+                                          'computed; flag + wait at the end of the call, inside the timed region: %.3f ms per step '
+                                          'exposed' % gather_ms,
+                                  'none': 'none (1 GPU)'}[gather_kind],
                    'l2': 'inputs larger than L2 (per-chunk workspace %.1f GB, theta 40 MB)' % (lk_ws / 1e9)},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'parity': parity, 'gather_ms': gather_ms,
         'guard_fallback_rows_timed': fb_rows[0], 'roofline': roofline, 'cpu_baseline': cpu, 'configs': configs,

@@ -148,6 +148,12 @@ SYMBOLS = {
     'elisa_b200_plan_small_batch_kernel': (C.c_int, [_VP, C.c_int32]),
     'elisa_b200_plan_fold_products': (C.c_int, [_VP, C.c_int32, c_double_p]),
     'elisa_b200_abi_version': (C.c_int, []),
+    'elisa_b200_peer_alloc': (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    'elisa_b200_peer_open': (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    'elisa_b200_peer_close': (C.c_int, [_VP]),
+    'elisa_b200_peer_free': (C.c_int, [_VP]),
+    'elisa_b200_plan_set_gather': (C.c_int, [_VP, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_void_p), C.c_int64]),
     'elisa_b200_sizeof': (C.c_int64, [C.c_int32]),
     'elisa_b200_last_error': (C.c_char_p, []),
 }

@@ -940,6 +940,20 @@ struct ElisaPlan {
     cudaEvent_t pipe_free[2] = {nullptr, nullptr}, pipe_ready[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // peer gather (elisa_b200_plan_set_gather): full result arrays of every rank as mapped here
+    struct PeerGather {
+        int world = 0, rank = 0;
+        std::vector<double*> ll, grad;
+        std::vector<long long*> flags;
+        int64_t row_offset = 0;
+        long long epoch = 0;
+        cudaStream_t copy = nullptr;
+        cudaEvent_t ready = nullptr, done = nullptr;
+        int64_t pend_lo = 0, pend_hi = 0;  // rows computed and not pushed yet
+        int pend_chunks = 0;
+        int every = 4;                     // chunks per push
+        int32_t* timeout = nullptr;        // host-mapped: a peer's flag did not arrive
+    } gather;
     std::vector<void*> owned;
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profiling = false;
@@ -2867,6 +2881,94 @@ static bool decide_tiny(ElisaPlan* plan, int64_t n) {
     return all_tiny;
 }
 
+// ---- peer gather -------------------------------------------------------------------------
+constexpr int GATHER_MAX_WORLD = 16;
+struct GatherFlags {
+    long long* flags[GATHER_MAX_WORLD];
+};
+// one thread per peer: this rank's slot of the peer's flag array takes the call's sequence number (after the
+// copies of the stream: the peer finds the rows behind the flag)
+__global__ void gather_signal_kernel(GatherFlags f, int world, int rank, long long epoch) {
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile long long*>(f.flags[r] + rank) = epoch;
+    __threadfence_system();
+}
+// one thread per peer: wait until its flag in THIS rank's array has reached the sequence number.  Bounded
+// (~4 s): a missing peer leaves a mark instead of hanging the device.
+__global__ void gather_wait_kernel(const long long* flags, int world, int rank, long long epoch, int32_t* timeout) {
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    const volatile long long* f = flags + r;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000LL) {
+            if (timeout != nullptr) *timeout = r + 1;
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+static bool gather_on(const ElisaPlan* plan) { return plan->gather.world > 1; }
+
+// rows [lo, hi) of the call's outputs -> every rank's full arrays (copy engines, behind the work on `st` so far)
+static int gather_push(ElisaPlan* plan, int64_t lo, int64_t hi, const double* loglike, const double* grad, cudaStream_t st) {
+    ElisaPlan::PeerGather& g = plan->gather;
+    if (hi <= lo) return ELISA_OK;
+    const int64_t S = plan->S, P = plan->P;
+    CUDA_TRY(cudaEventRecord(g.ready, st));
+    CUDA_TRY(cudaStreamWaitEvent(g.copy, g.ready, 0));
+    for (int k = 1; k <= g.world; ++k) {  // the peers first, starting with the next rank: the ranks do not all hit rank 0 at once
+        const int r = (g.rank + k) % g.world;
+        double* dl = g.ll[r] + (g.row_offset + lo) * S;
+        const double* sl = loglike + lo * S;
+        if (dl != sl) CUDA_TRY(cudaMemcpyAsync(dl, sl, (size_t)(hi - lo) * S * 8, cudaMemcpyDeviceToDevice, g.copy));
+        if (grad != nullptr && !g.grad.empty()) {
+            double* dg = g.grad[r] + (g.row_offset + lo) * S * P;
+            const double* sg = grad + lo * S * P;
+            if (dg != sg) CUDA_TRY(cudaMemcpyAsync(dg, sg, (size_t)(hi - lo) * S * P * 8, cudaMemcpyDeviceToDevice, g.copy));
+        }
+    }
+    return ELISA_OK;
+}
+
+// called after every chunk of run_all: pushes every `every` chunks
+static int gather_note(ElisaPlan* plan, int64_t lo, int64_t hi, bool last, const double* loglike, const double* grad,
+                       cudaStream_t st) {
+    ElisaPlan::PeerGather& g = plan->gather;
+    if (g.pend_chunks == 0) g.pend_lo = lo;
+    g.pend_hi = hi;
+    ++g.pend_chunks;
+    if (!last && g.pend_chunks < g.every) return ELISA_OK;
+    g.pend_chunks = 0;
+    return gather_push(plan, g.pend_lo, g.pend_hi, loglike, grad, st);
+}
+
+// end of a gathered call: flags to the peers behind the pushes, `st` waits for the pushes and for the peers' flags
+static int gather_finish(ElisaPlan* plan, cudaStream_t st) {
+    ElisaPlan::PeerGather& g = plan->gather;
+    if (g.timeout != nullptr && *g.timeout != 0) {
+        const int r = *g.timeout - 1;
+        *g.timeout = 0;
+        return fail(ELISA_ERR_CUDA, "peer gather: the flag of rank " + std::to_string(r) + " did not arrive in an earlier call (the ranks must make the same sequence of gathered calls)");
+    }
+    ScopedSpan span(plan, ELISA_PROFILE_GATHER, st);
+    ++g.epoch;
+    GatherFlags f;
+    for (int r = 0; r < GATHER_MAX_WORLD; ++r) f.flags[r] = r < g.world ? g.flags[r] : nullptr;
+    gather_signal_kernel<<<1, 32, 0, g.copy>>>(f, g.world, g.rank, g.epoch);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(g.done, g.copy));
+    CUDA_TRY(cudaStreamWaitEvent(st, g.done, 0));
+    gather_wait_kernel<<<1, 32, 0, st>>>(g.flags[g.rank], g.world, g.rank, g.epoch, g.timeout);
+    CUDA_TRY(cudaGetLastError());
+    plan->launches += 2;
+    return ELISA_OK;
+}
+
 static int run_all(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                    double* loglike, double* grad, cudaStream_t st) {
     if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
@@ -2890,6 +2992,7 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
                                  grad ? grad + i0 * plan->S * plan->P : nullptr, st);
                 s0 = s1;
             }
+            if (rc == ELISA_OK && gather_on(plan)) rc = gather_note(plan, i0, i0 + nc, i0 + nc >= n, loglike, grad, st);
         }
         if (dev != plan->device) cudaSetDevice(dev);
         return rc;
@@ -2904,6 +3007,7 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
             rc = run_chunk(plan, s, theta + i0 * plan->P, on ? on + i0 * plan->sum_C : nullptr,
                            off ? off + i0 * plan->sum_C : nullptr, nc, loglike + i0 * plan->S,
                            grad ? grad + i0 * plan->S * plan->P : nullptr, st);
+        if (rc == ELISA_OK && gather_on(plan)) rc = gather_note(plan, i0, i0 + nc, i0 + nc >= n, loglike, grad, st);
     }
     plan->row_base = base;
     if (dev != plan->device) cudaSetDevice(dev);
@@ -2929,7 +3033,7 @@ static cudaGraphNode_t last_captured_node(cudaStream_t st) {
 // value (+ gradient) of a small batch through a replayed CUDA graph; falls back to run_all.
 static int run_small(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
                      double* loglike, double* grad, cudaStream_t st) {
-    const bool eligible = plan != nullptr && plan->graphs_enabled && !plan->profiling && !plan->force_dmma && n > 0 && n <= GRAPH_MAX_N &&
+    const bool eligible = plan != nullptr && plan->graphs_enabled && !plan->profiling && !plan->force_dmma && !gather_on(plan) && n > 0 && n <= GRAPH_MAX_N &&
                           n <= plan->chunk && on == nullptr && off == nullptr && theta != nullptr && loglike != nullptr &&
                           plan->g_theta != nullptr;
     if (!eligible) return run_all(plan, theta, on, off, n, loglike, grad, st);
@@ -3244,6 +3348,80 @@ extern "C" {
 
 int elisa_b200_abi_version(void) { return ELISA_B200_ABI_VERSION; }
 
+int elisa_b200_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]) {
+    if (dev_ptr == nullptr || ipc_handle == nullptr || bytes <= 0) return fail(ELISA_ERR_INVALID, "peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    *dev_ptr = nullptr;
+    CUDA_TRY(cudaMalloc(dev_ptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaMemset(*dev_ptr, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr);
+        *dev_ptr = nullptr;
+        return fail(ELISA_ERR_CUDA, std::string("peer_alloc: ") + cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle, &h, 64);
+    return ELISA_OK;
+}
+int elisa_b200_peer_open(const unsigned char ipc_handle[64], void** dev_ptr) {
+    if (dev_ptr == nullptr || ipc_handle == nullptr) return fail(ELISA_ERR_INVALID, "peer_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, 64);
+    *dev_ptr = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return ELISA_OK;
+}
+int elisa_b200_peer_close(void* dev_ptr) {
+    if (dev_ptr != nullptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return ELISA_OK;
+}
+int elisa_b200_peer_free(void* dev_ptr) {
+    if (dev_ptr != nullptr) CUDA_TRY(cudaFree(dev_ptr));
+    return ELISA_OK;
+}
+int elisa_b200_plan_set_gather(ElisaPlan* plan, int32_t world, int32_t rank, void* const* ll_all, void* const* grad_all,
+                               void* const* flags, int64_t row_offset) {
+    if (plan == nullptr) return fail(ELISA_ERR_INVALID, "null plan");
+    std::lock_guard<std::mutex> lock(plan->mu);
+    ElisaPlan::PeerGather& g = plan->gather;
+    if (world <= 1) {
+        g.world = 0;
+        return ELISA_OK;
+    }
+    if (world > GATHER_MAX_WORLD || rank < 0 || rank >= world || ll_all == nullptr || flags == nullptr || row_offset < 0)
+        return fail(ELISA_ERR_INVALID, "set_gather: bad argument");
+    for (int r = 0; r < world; ++r)
+        if (ll_all[r] == nullptr || flags[r] == nullptr || (grad_all != nullptr && grad_all[r] == nullptr))
+            return fail(ELISA_ERR_INVALID, "set_gather: null array");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev != plan->device) CUDA_TRY(cudaSetDevice(plan->device));
+    if (g.copy == nullptr) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaHostAlloc((void**)&g.timeout, sizeof(int32_t), cudaHostAllocMapped));
+        *g.timeout = 0;
+        if (const char* env = getenv("ELISA_B200_GATHER_EVERY")) g.every = std::max(1, atoi(env));
+    }
+    g.ll.assign(world, nullptr);
+    g.flags.assign(world, nullptr);
+    g.grad.clear();
+    if (grad_all != nullptr) g.grad.assign(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        g.ll[r] = (double*)ll_all[r];
+        g.flags[r] = (long long*)flags[r];
+        if (grad_all != nullptr) g.grad[r] = (double*)grad_all[r];
+    }
+    g.world = world;
+    g.rank = rank;
+    g.row_offset = row_offset;
+    g.pend_chunks = 0;
+    if (dev != plan->device) cudaSetDevice(dev);
+    return ELISA_OK;
+}
+
 int64_t elisa_b200_sizeof(int32_t which) {
     switch (which) {
         case 0: return sizeof(ElisaComponentDesc);
@@ -3285,6 +3463,10 @@ void elisa_b200_plan_destroy(ElisaPlan* plan) {
     }
     if (plan->copy_stream) cudaStreamDestroy(plan->copy_stream);
     if (plan->stream) cudaStreamDestroy(plan->stream);
+    if (plan->gather.copy) cudaStreamDestroy(plan->gather.copy);
+    if (plan->gather.ready) cudaEventDestroy(plan->gather.ready);
+    if (plan->gather.done) cudaEventDestroy(plan->gather.done);
+    if (plan->gather.timeout) cudaFreeHost(plan->gather.timeout);
     cudaSetDevice(dev);
     delete plan;
 }
@@ -3582,7 +3764,9 @@ int elisa_b200_loglike_dev(ElisaPlan* plan, const double* theta, const double* c
                            int64_t n, double* loglike, void* cuda_stream) {
     std::unique_lock<std::mutex> lock;
     if (plan != nullptr) lock = std::unique_lock<std::mutex>(plan->mu);
-    return run_small(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
+    int rc = run_small(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
+    if (rc == ELISA_OK && plan != nullptr && gather_on(plan)) rc = gather_finish(plan, (cudaStream_t)cuda_stream);
+    return rc;
 }
 
 int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const double* counts_on,
@@ -3591,7 +3775,9 @@ int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const doub
     if (grad == nullptr) return fail(ELISA_ERR_INVALID, "grad is null");
     std::unique_lock<std::mutex> lock;
     if (plan != nullptr) lock = std::unique_lock<std::mutex>(plan->mu);
-    return run_small(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
+    int rc = run_small(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
+    if (rc == ELISA_OK && plan != nullptr && gather_on(plan)) rc = gather_finish(plan, (cudaStream_t)cuda_stream);
+    return rc;
 }
 
 int elisa_b200_unfold_dev(ElisaPlan* plan, int32_t spectrum, const double* theta, int64_t n, double* unfold,
@@ -3698,12 +3884,17 @@ int elisa_b200_loglike_grad_guarded_dev(ElisaPlan* plan, const double* theta, co
     CUDA_TRY(cudaGetDevice(&prev));
     CUDA_TRY(cudaSetDevice(plan->device));
     const int64_t before = plan->fallback_rows;
-    const int rc = run_guarded(
+    int rc = run_guarded(
         plan, n, st, [&]() { return run_small(plan, theta, counts_on, counts_off, n, loglike, grad, st); },
         [&](const std::vector<int32_t>& rows) {
             return rerun_rows_dmma(plan, rows, theta, counts_on, counts_off, false, loglike, grad, st);
         });
     if (fallback_rows) *fallback_rows = plan->fallback_rows - before;
+    if (rc == ELISA_OK && gather_on(plan)) {
+        // rows the DMMA fold re-evaluated were pushed with their first values: push the block again
+        if (plan->fallback_rows != before) rc = gather_push(plan, 0, n, loglike, grad, st);
+        if (rc == ELISA_OK) rc = gather_finish(plan, st);
+    }
     cudaSetDevice(prev);
     return rc;
 }

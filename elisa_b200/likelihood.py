@@ -302,7 +302,7 @@ class Likelihood:
     def launch_count(self) -> int:
         return int(self._lib.elisa_b200_plan_launch_count(self._h))
 
-    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice', 'stat', 'contract', 'tiny')
+    PROFILE_CLASSES = ('unfold', 'fold', 'tfold', 'reduce', 'slice', 'stat', 'contract', 'tiny', 'gather')
 
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.elisa_b200_plan_set_profiling(self._h, int(bool(enable))))
@@ -346,16 +346,17 @@ class Likelihood:
         return self._torch.cuda.device(self.device)
 
     # -- device API (torch tensors in, torch tensors out) ----------------------------
-    def _evaluate_small(self, t, want_grad: bool):
+    def _evaluate_small(self, t, want_grad: bool, out=None):
         """The leapfrog path: a small batch already on the device, every spectrum on the one-kernel path (plain FP64, no
         guard to consult).  The kernel takes ~12 us, so what this method spends is the rate of a sampler that calls it
         back to back: no tensor conversion, no device context, no stream object, plain integers through ctypes."""
         torch = self._torch
         n = t.shape[0]
-        out = torch.empty((n, self._S), dtype=torch.float64, device=t.device)
+        out, grad = out if out is not None else (torch.empty((n, self._S), dtype=torch.float64, device=t.device), None)
         stream = _raw_stream(torch, self.device)
         if want_grad:
-            grad = torch.empty((n, self._S, self._P), dtype=torch.float64, device=t.device)
+            if grad is None:
+                grad = torch.empty((n, self._S, self._P), dtype=torch.float64, device=t.device)
             rc = self._f_grad(self._h, t.data_ptr(), None, None, n, out.data_ptr(), grad.data_ptr(), stream)
         else:
             grad = None
@@ -364,21 +365,34 @@ class Likelihood:
             _lib.check(rc)
         return out, grad
 
-    def _evaluate(self, theta, counts_on, counts_off, want_grad: bool, guard):
+    def _check_out(self, out, n, want_grad):
+        """Caller-provided result arrays (ll (n, S), grad (n, S, P_plan) or None): contiguous float64 on this device."""
+        ll, g = out
+        shapes = [(ll, (n, self._S))] + ([(g, (n, self._S, self._P))] if want_grad else [])
+        for t, shape in shapes:
+            if (t is None or tuple(t.shape) != shape or t.dtype is not self._torch.float64 or not t.is_cuda
+                    or t.device.index != self.device or not t.is_contiguous()):
+                raise ValueError(f'out: expected a contiguous float64 tensor of shape {shape} on cuda:{self.device}')
+        return ll, (g if want_grad else None)
+
+    def _evaluate(self, theta, counts_on, counts_off, want_grad: bool, guard, out=None):
         torch = self._torch
         if (self._all_small_batch and counts_on is None and counts_off is None and type(theta) is torch.Tensor
                 and theta.is_cuda and theta.dtype is torch.float64 and theta.dim() == 2 and theta.shape[1] == self.nparam
                 and 0 < theta.shape[0] <= _SMALL_BATCH_ROWS and self.nparam > 0 and theta.is_contiguous()
                 and theta.device.index == self.device and torch.cuda.current_device() == self.device):
-            return self._evaluate_small(theta, want_grad)
+            return self._evaluate_small(theta, want_grad, None if out is None else self._check_out(out, theta.shape[0], want_grad))
         mode = self.guard_mode if guard is None else (guard if self._auto_guard else 'off')
         with self._device_ctx():
             t = self._theta(theta)
             n = t.shape[0]
             on, off = self._counts(counts_on, n), self._counts(counts_off, n)
             S = len(self.data)
-            out = torch.empty((n, S), dtype=torch.float64, device=t.device)
-            grad = torch.empty((n, S, self._P), dtype=torch.float64, device=t.device) if want_grad else None
+            if out is not None:
+                out, grad = self._check_out(out, n, want_grad)
+            else:
+                out = torch.empty((n, S), dtype=torch.float64, device=t.device)
+                grad = torch.empty((n, S, self._P), dtype=torch.float64, device=t.device) if want_grad else None
             stream = self._stream()
             if n <= _SMALL_BATCH_ROWS and self._all_small_batch:
                 mode = 'off'  # the one-kernel path is plain FP64: nothing for the guard to watch, no synchronisation
@@ -398,15 +412,16 @@ class Likelihood:
                     self._lazy_guard(stream)
         return out, grad
 
-    def loglike(self, theta, counts_on=None, counts_off=None, guard=None):
+    def loglike(self, theta, counts_on=None, counts_off=None, guard=None, out=None):
         """(N, S) log-likelihood per dataset: get_loglike()['group'], infer/helper.py:494-512.
-        ``guard`` overrides the object's guard mode for this call."""
-        return self._evaluate(theta, counts_on, counts_off, False, guard)[0]
+        ``guard`` overrides the object's guard mode for this call; ``out``: a (N, S) tensor to write into."""
+        return self._evaluate(theta, counts_on, counts_off, False, guard, None if out is None else (out, None))[0]
 
-    def loglike_and_grad(self, theta, counts_on=None, counts_off=None, guard=None):
+    def loglike_and_grad(self, theta, counts_on=None, counts_off=None, guard=None, out=None):
         """((N, S), (N, S, P)): value and d loglike[n, s] / d theta[n, :] -- what
-        jax.value_and_grad of each dataset's log-likelihood returns upstream."""
-        out, grad = self._evaluate(theta, counts_on, counts_off, True, guard)
+        jax.value_and_grad of each dataset's log-likelihood returns upstream.  ``out``: (ll (N, S), grad (N, S,
+        plan_params)) tensors to write into (``plan_params`` = max(P, 1))."""
+        out, grad = self._evaluate(theta, counts_on, counts_off, True, guard, out)
         return out, (grad if self._P == self.nparam else grad[:, :, : self.nparam])
 
     def normal_equations(self, theta, counts_on=None, counts_off=None, guard: bool = True):

@@ -90,14 +90,146 @@ def sharded_map(fn: Callable, args: Sequence, n_total: int, group=None, gather: 
     return all_gather_rows(local, n_total, group)
 
 
+class _DeviceArray:
+    """A raw device allocation as something ``torch.as_tensor`` takes without copying."""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str = '<f8'):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
+
+
+class PeerGather:
+    """The gather fused into the evaluation (``elisa_b200_plan_set_gather``, include/elisa_b200.h): every rank owns
+    FULL result arrays ``ll [n_total, S]`` / ``grad [n_total, S, P]`` in CUDA-IPC memory which every peer maps, and a
+    plan with the gather set pushes the rows of its finished chunks into all of them over NVLink with the copy
+    engines while it computes the next chunks; the call ends with a flag to every peer and a wait for theirs.  No
+    NCCL on the data path: ``torch.distributed`` only carries the 64-byte IPC handles, once.  ``sets`` copies of the
+    arrays are used in turn (a rank may be one call ahead of a peer whose consumer still reads the previous
+    results)."""
+
+    def __init__(self, likelihood, n_total: int, group=None, sets: int = 2):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        dist = _dist()
+        self.lk, self.group, self.n_total, self.sets = likelihood, group, int(n_total), int(sets)
+        self.rank, self.world = world_info(group)
+        if self.world < 2:
+            raise ValueError('PeerGather needs an initialised process group of at least 2 ranks')
+        self._lib = lib = likelihood._lib
+        S, P = likelihood._S, likelihood._P
+        self.bounds = shard_bounds(self.n_total, self.world)
+        sizes = [self.world * 8] + [self.n_total * S * 8, self.n_total * S * P * 8] * self.sets  # flags, (ll, grad) per set
+        self._own, handles = [], []
+        with torch.cuda.device(likelihood.device):
+            for b in sizes:
+                ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                _lib.check(lib.elisa_b200_peer_alloc(max(int(b), 8), C.byref(ptr), h))
+                self._own.append(ptr.value)
+                handles.append(h.raw)
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handles, group=group)
+            self._maps = []  # [rank][array] device pointers as mapped here
+            for r in range(self.world):
+                if r == self.rank:
+                    self._maps.append(list(self._own))
+                    continue
+                row = []
+                for h in everyone[r]:
+                    ptr = C.c_void_p()
+                    _lib.check(lib.elisa_b200_peer_open(h, C.byref(ptr)))
+                    row.append(ptr.value)
+                self._maps.append(row)
+        dev = f'cuda:{likelihood.device}'
+        self._views = []
+        for k in range(self.sets):
+            ll = torch.as_tensor(_DeviceArray(self._own[1 + 2 * k], (self.n_total, S)), device=dev)
+            g = torch.as_tensor(_DeviceArray(self._own[2 + 2 * k], (self.n_total, S, P)), device=dev)
+            self._views.append((ll, g))
+        self._next = 0
+        self._C = C
+        dist.barrier(group=group)  # every rank has mapped every array before anyone pushes
+
+    def _ptr_array(self, index):
+        C = self._C
+        return (C.c_void_p * self.world)(*[self._maps[r][index] for r in range(self.world)])
+
+    def begin(self):
+        """Set the plan's gather to the next set of arrays; returns (ll_full, grad_full, lo, hi): the full arrays
+        of this rank and its block of rows -- evaluate with ``out=(ll_full[lo:hi], grad_full[lo:hi])``."""
+        from . import _lib
+
+        k = self._next
+        self._next = (k + 1) % self.sets
+        lo, hi = self.bounds[self.rank]
+        _lib.check(self._lib.elisa_b200_plan_set_gather(self.lk._h, self.world, self.rank, self._ptr_array(1 + 2 * k),
+                                                        self._ptr_array(2 + 2 * k), self._ptr_array(0), lo))
+        ll, g = self._views[k]
+        return ll, g, lo, hi
+
+    def end(self):
+        from . import _lib
+
+        _lib.check(self._lib.elisa_b200_plan_set_gather(self.lk._h, 0, 0, None, None, None, 0))
+
+    def close(self):
+        """Unmap the peers' arrays and free this rank's (collective: the peers must have stopped pushing)."""
+        if self._maps is None:
+            return
+        import torch
+
+        torch.cuda.synchronize(self.lk.device)
+        _dist().barrier(group=self.group)
+        with torch.cuda.device(self.lk.device):
+            for r in range(self.world):
+                if r != self.rank:
+                    for p in self._maps[r]:
+                        self._lib.elisa_b200_peer_close(p)
+            _dist().barrier(group=self.group)
+            self._views = []
+            for p in self._own:
+                self._lib.elisa_b200_peer_free(p)
+        self._maps = None
+
+
 class ShardedLikelihood:
     """A :class:`elisa_b200.Likelihood` per rank (constants replicated on its GPU) evaluating
     this rank's block of the batch.  ``gather=False`` keeps results sharded (e.g. NUTS with
-    the chains resident per GPU: no collective at all)."""
+    the chains resident per GPU: no collective at all).  ``peer=True`` (GPUs of one box, one process each): the
+    gather of ``loglike`` / ``loglike_and_grad`` is fused into the evaluation (:class:`PeerGather`) instead of
+    NCCL all-gathers after it; the arrays returned are then reused two gathered calls later."""
 
-    def __init__(self, likelihood, group=None):
+    def __init__(self, likelihood, group=None, peer: bool = False):
         self.lk = likelihood
         self.group = group
+        self.peer = bool(peer)
+        self._gathers = {}
+
+    def _peer_gather(self, n):
+        if n not in self._gathers:
+            self._gathers[n] = PeerGather(self.lk, n, self.group)
+        return self._gathers[n]
+
+    def close(self):
+        for g in self._gathers.values():
+            g.close()
+        self._gathers = {}
+
+    def _peer_eval(self, theta, counts_on, counts_off, n, want_grad):
+        pg = self._peer_gather(n)
+        ll, g, lo, hi = pg.begin()
+        try:
+            sl = lambda a: None if a is None else a[lo:hi]
+            if want_grad:
+                self.lk.loglike_and_grad(theta[lo:hi], sl(counts_on), sl(counts_off), out=(ll[lo:hi], g[lo:hi]))
+            else:
+                self.lk.loglike(theta[lo:hi], sl(counts_on), sl(counts_off), out=ll[lo:hi])
+        finally:
+            pg.end()
+        return (ll, g[:, :, : self.lk.nparam]) if want_grad else ll
 
     @staticmethod
     def _rows(theta, counts_on=None, counts_off=None):
@@ -116,12 +248,19 @@ class ShardedLikelihood:
                 n = len(c)
         return theta, n
 
+    def _use_peer(self, gather, n):
+        return self.peer and gather and world_info(self.group)[1] > 1 and n >= world_info(self.group)[1]
+
     def loglike(self, theta, counts_on=None, counts_off=None, gather=True):
         theta, n = self._rows(theta)
+        if self._use_peer(gather, n):
+            return self._peer_eval(theta, counts_on, counts_off, n, False)
         return sharded_map(self.lk.loglike, (theta, counts_on, counts_off), n, self.group, gather)
 
     def loglike_and_grad(self, theta, counts_on=None, counts_off=None, gather=True):
         theta, n = self._rows(theta)
+        if self._use_peer(gather, n):
+            return self._peer_eval(theta, counts_on, counts_off, n, True)
         return sharded_map(self.lk.loglike_and_grad, (theta, counts_on, counts_off), n, self.group, gather)
 
     def fit(self, theta0, counts_on=None, counts_off=None, gather=True, **fit_kw):

@@ -335,7 +335,8 @@ int elisa_b200_plan_set_channel_width(ElisaPlan* plan, int32_t spectrum, const d
 #define ELISA_PROFILE_STAT 5   /* statistic + digits of W (sliced-integer fold only)       */
 #define ELISA_PROFILE_CONTRACT 6 /* gradient by contraction: tangents recomputed against G (sliced-integer fold only) */
 #define ELISA_PROFILE_TINY 7   /* one-kernel evaluation of a small batch of a small spectrum (unfold + FP64 fold + statistic + gradient) */
-#define ELISA_PROFILE_CLASSES 8
+#define ELISA_PROFILE_GATHER 8 /* peer gather: what is left of it after the last chunk (tail pushes + waiting for the peers) */
+#define ELISA_PROFILE_CLASSES 9
 int elisa_b200_plan_set_profiling(ElisaPlan* plan, int enable);
 int elisa_b200_plan_get_profile(ElisaPlan* plan, double* ms, int64_t* launches);
 
@@ -460,6 +461,36 @@ int elisa_b200_csr_fold_dev(ElisaPlan* plan, int32_t spectrum, const double* unf
  * be reproduced, parity is distributional.                                                  */
 int elisa_b200_sample_dev(ElisaPlan* plan, int32_t spectrum, int32_t which, const double* mean, int64_t mean_rows, int64_t n,
                           uint64_t seed, double* out, int64_t ld, void* cuda_stream);
+/* ---- peer gather (the N axis is sharded over the GPUs of one box, only the per-sample results are
+ * gathered).  The reference's counterpart is the concatenation jax.pmap / shard_map do after the per-device work
+ * (infer/helper.py:706-716).  Instead of a collective AFTER the evaluation, a plan with a gather set pushes the
+ * rows of every few finished chunks into EVERY rank's copy of the full result arrays while the next chunks are
+ * being computed: peer-to-peer copies on the copy engines over NVLink / NVSwitch -- no SM, no NCCL kernel that
+ * would compete with the persistent fold CTAs for the SMs -- and the call ends with one flag per peer and a wait
+ * for theirs.  One process per GPU; the arrays are CUDA IPC allocations:
+ *   elisa_b200_peer_alloc   cudaMalloc on the current device + its IPC handle (64 bytes, to be sent to the peers
+ *                           by whatever the host side uses: torch.distributed objects, MPI, a file)
+ *   elisa_b200_peer_open    maps a peer's allocation into this process (peer access enabled lazily)
+ *   elisa_b200_peer_close / elisa_b200_peer_free
+ *   elisa_b200_plan_set_gather(plan, world, rank, ll_all, grad_all, flags, row_offset)
+ *       ll_all[r] / grad_all[r]: base of rank r's FULL arrays [n_total, S] / [n_total, S, P] (grad_all may be NULL)
+ *       as mapped in THIS process (entry `rank` is this rank's own allocation); flags[r]: rank r's int64[world],
+ *       zero-initialised; row_offset: global index of row 0 of this rank's block.  world <= 1 switches it off.
+ *   Then elisa_b200_loglike_dev / _loglike_grad_dev / _loglike_grad_guarded_dev additionally (a) copy rows
+ *   [i0, i1) of their loglike / grad OUTPUT arguments to ll_all[r] + (row_offset + i0) S (and grad likewise) of
+ *   every r (skipping a destination that IS the source: hand in views of the own full arrays and nothing is
+ *   copied locally), (b) after the last chunk -- and after the guard's DMMA re-evaluation of flagged rows, which
+ *   re-pushes the block -- write the call's sequence number into flags[r][rank] of every peer and make the
+ *   stream wait until flags[rank][r] of every peer has reached it: when the call's work on the stream is done,
+ *   this rank's full arrays hold every rank's rows.  Every rank must make the same sequence of gathered calls.
+ *   A rank may run ahead by one call: keep two sets of arrays and alternate them if a consumer reads the
+ *   results while the next call is already running (elisa_b200/parallel.py does).                        */
+int elisa_b200_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
+int elisa_b200_peer_open(const unsigned char ipc_handle[64], void** dev_ptr);
+int elisa_b200_peer_close(void* dev_ptr);
+int elisa_b200_peer_free(void* dev_ptr);
+int elisa_b200_plan_set_gather(ElisaPlan* plan, int32_t world, int32_t rank, void* const* ll_all, void* const* grad_all,
+                               void* const* flags, int64_t row_offset);
 /* Timing experiments only: bit mask of kernel classes to SKIP in the evaluation entry points
  * (1 unfold, 2 forward fold, 4 statistic, 8 transposed fold, 16 reduce, 32 the dU/dtheta stores of
  * the specialised unfold kernel); results are garbage

@@ -45,6 +45,32 @@ def _worker(rank, world, port, n, q):
         l3, gg3 = ref.loglike_and_grad(th3)
         ok = ok and close(ll3, l3) and close(g3, gg3)
         ref.close()
+    # the gather fused into the evaluation (peer-to-peer pushes of the finished chunks, copy engines): the same bits as
+    # the NCCL gather of the same plan's results, call after call (two sets of arrays used in turn), for a batch of
+    # several chunks, for unequal blocks, value only, and on the one-kernel small-batch path
+    sp = ShardedLikelihood(lk, peer=True)
+    for rep in range(5):
+        th = theta * (1.0 + 0.01 * rep)
+        ll_n, g_n = sl.loglike_and_grad(th)
+        ll_p, g_p = sp.loglike_and_grad(th)
+        ok = ok and torch.equal(ll_p, ll_n) and torch.equal(g_p, g_n)
+        if rep == 0:
+            ok = ok and torch.equal(sp.loglike(th), sl.loglike(th))
+    lk_c = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=rank, chunk=128)  # four chunks per rank: two pushes
+    sc, scn = ShardedLikelihood(lk_c, peer=True), ShardedLikelihood(lk_c)
+    ll_p, g_p = sc.loglike_and_grad(theta)
+    ll_n, g_n = scn.loglike_and_grad(theta)
+    ok = ok and torch.equal(ll_p, ll_n) and torch.equal(g_p, g_n)
+    s3p = ShardedLikelihood(lk3, peer=True)
+    for rep in range(4):
+        th = th3 * (1.0 + 0.002 * rep)
+        a, b = s3.loglike_and_grad(th)
+        c, d = s3p.loglike_and_grad(th)
+        ok = ok and torch.equal(a, c) and torch.equal(b, d)
+    torch.cuda.synchronize()
+    for x in (sp, sc, s3p):
+        x.close()
+    lk_c.close()
     torch.cuda.synchronize()
     q.put((rank, bool(ok), int(ll_local.shape[0])))
     lk.close()
