@@ -487,6 +487,8 @@ def side_configs(torch, dist, world, rank, local, with_oracle, peer=False):
     lk = Likelihood(cfg['data'], cfg['model'], cfg['stat'], device=local)
     sh = ShardedLikelihood(lk, peer=peer)
     th = torch.as_tensor(cfg['theta'], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()  # rank 0 comes out of cfg 4 and its oracle seconds after the others
     sh.loglike_and_grad(th)  # warm-up (also balances the plan)
     torch.cuda.synchronize()
     if world > 1:
@@ -616,6 +618,7 @@ def run_b200(args):
         cpu = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'first {ns} of the {n} draws, 2 timed repeats ({dt:.2f} s each), torch CPU float64 oracle; '
                          'the reference JAX path cannot be installed offline'}
+    barrier()  # rank 0 comes out of the CPU oracle seconds after the others: a gathered step waits for every rank
     step()
     torch.cuda.synchronize()
     flagged, worst = lk.fold_guard(reset=False)

@@ -953,6 +953,7 @@ struct ElisaPlan {
         int pend_chunks = 0;
         int every = 4;                     // chunks per push
         int32_t* timeout = nullptr;        // host-mapped: a peer's flag did not arrive
+        unsigned long long limit_ns = 60ull * 1000000000ull;  // how long a call waits for a peer (ranks may be skewed by host work)
     } gather;
     std::vector<void*> owned;
     // optional per-kernel-class device timing (CUDA events on the launching stream)
@@ -2896,15 +2897,21 @@ __global__ void gather_signal_kernel(GatherFlags f, int world, int rank, long lo
     __threadfence_system();
 }
 // one thread per peer: wait until its flag in THIS rank's array has reached the sequence number.  Bounded
-// (~4 s): a missing peer leaves a mark instead of hanging the device.
-__global__ void gather_wait_kernel(const long long* flags, int world, int rank, long long epoch, int32_t* timeout) {
+// (60 s, ELISA_B200_GATHER_TIMEOUT_S): a missing peer leaves a mark instead of hanging the device.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void gather_wait_kernel(const long long* flags, int world, int rank, long long epoch, int32_t* timeout,
+                                   unsigned long long limit_ns) {
     const int r = threadIdx.x;
     if (r >= world || r == rank) return;
     const volatile long long* f = flags + r;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
     while (*f < epoch) {
         __nanosleep(200);
-        if (clock64() - t0 > 8000000000LL) {
+        if (global_ns() - t0 > limit_ns) {
             if (timeout != nullptr) *timeout = r + 1;
             break;
         }
@@ -2963,7 +2970,7 @@ static int gather_finish(ElisaPlan* plan, cudaStream_t st) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(g.done, g.copy));
     CUDA_TRY(cudaStreamWaitEvent(st, g.done, 0));
-    gather_wait_kernel<<<1, 32, 0, st>>>(g.flags[g.rank], g.world, g.rank, g.epoch, g.timeout);
+    gather_wait_kernel<<<1, 32, 0, st>>>(g.flags[g.rank], g.world, g.rank, g.epoch, g.timeout, g.limit_ns);
     CUDA_TRY(cudaGetLastError());
     plan->launches += 2;
     return ELISA_OK;
@@ -3404,6 +3411,7 @@ int elisa_b200_plan_set_gather(ElisaPlan* plan, int32_t world, int32_t rank, voi
         CUDA_TRY(cudaHostAlloc((void**)&g.timeout, sizeof(int32_t), cudaHostAllocMapped));
         *g.timeout = 0;
         if (const char* env = getenv("ELISA_B200_GATHER_EVERY")) g.every = std::max(1, atoi(env));
+        if (const char* env = getenv("ELISA_B200_GATHER_TIMEOUT_S")) g.limit_ns = (unsigned long long)std::max(1, atoi(env)) * 1000000000ull;
     }
     g.ll.assign(world, nullptr);
     g.flags.assign(world, nullptr);
