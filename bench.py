@@ -412,17 +412,23 @@ def side_configs(torch, dist, world, rank, local, with_oracle, peer=False):
     us_local = (time.perf_counter() - t0) / 300 * 1e6
     us_gather = None
     if world > 1:
-        for _ in range(5):
-            sh.loglike_and_grad(full)
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(300):
-            sh.loglike_and_grad(full)
-        torch.cuda.synchronize()
-        t = torch.tensor([(time.perf_counter() - t0) / 300 * 1e6], dtype=torch.float64, device=dev)
+        try:
+            for _ in range(5):
+                sh.loglike_and_grad(full)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(300):
+                sh.loglike_and_grad(full)
+            torch.cuda.synchronize()
+            us = (time.perf_counter() - t0) / 300 * 1e6
+        except Exception as exc:  # a side line: never let it take the bench down
+            sys.stderr.write(f'rank {rank}: cfg3 gathered leapfrog failed: {exc}\n')
+            us = float('nan')
+        t = torch.tensor([us], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         us_gather = float(t.item())
+        us_gather = None if us_gather != us_gather else us_gather
     t = torch.tensor([us_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

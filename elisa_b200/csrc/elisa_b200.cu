@@ -948,10 +948,12 @@ struct ElisaPlan {
         int64_t row_offset = 0;
         long long epoch = 0;
         cudaStream_t copy = nullptr;
-        cudaEvent_t ready = nullptr, done = nullptr;
+        cudaEvent_t ready = nullptr, pushed = nullptr;
         int64_t pend_lo = 0, pend_hi = 0;  // rows computed and not pushed yet
         int pend_chunks = 0;
         int every = 4;                     // chunks per push
+        unsigned int* done = nullptr;      // device counter of the small-batch kernel's fused signal
+        bool signalled = false;            // this call's flags were raised by the evaluation kernel itself
         int32_t* timeout = nullptr;        // host-mapped: a peer's flag did not arrive
         unsigned long long limit_ns = 60ull * 1000000000ull;  // how long a call waits for a peer (ranks may be skewed by host work)
     } gather;
@@ -2534,8 +2536,22 @@ static bool tiny_ready(const ElisaPlan* plan, int s) {
 // Small batch of small spectra in one kernel (tiny_eval, unfold_skel.cuh): one CTA per (row, spectrum) for the
 // spectra [s0, s0 + count), which share one translation unit (same model expression and statistic).
 static int launch_tiny(ElisaPlan* plan, int s0, int count, const double* theta, const double* on, const double* off, int n,
-                       double* loglike, double* grad, cudaStream_t st) {
+                       double* loglike, double* grad, cudaStream_t st, int64_t i0 = 0, bool fuse_gather = false,
+                       bool last_launch = false) {
     TinyCall k;
+    memset(&k, 0, sizeof k);
+    if (fuse_gather) {  // results go to the peers' full arrays from inside the kernel; the last launch raises the flags
+        const ElisaPlan::PeerGather& g = plan->gather;
+        k.world = g.world;
+        k.rank = g.rank;
+        for (int r = 0; r < g.world; ++r) {
+            k.peer_ll[r] = g.ll[r] + (g.row_offset + i0) * plan->S;
+            k.peer_grad[r] = (grad != nullptr && !g.grad.empty()) ? g.grad[r] + (g.row_offset + i0) * plan->S * plan->P : nullptr;
+            k.peer_flags[r] = g.flags[r];
+        }
+        k.done = g.done;
+        k.epoch = last_launch ? g.epoch : 0;
+    }
     k.spec = plan->tiny_args;
     k.s0 = s0;
     k.S = plan->S;
@@ -2963,17 +2979,27 @@ static int gather_finish(ElisaPlan* plan, cudaStream_t st) {
         return fail(ELISA_ERR_CUDA, "peer gather: the flag of rank " + std::to_string(r) + " did not arrive in an earlier call (the ranks must make the same sequence of gathered calls)");
     }
     ScopedSpan span(plan, ELISA_PROFILE_GATHER, st);
-    ++g.epoch;
-    GatherFlags f;
-    for (int r = 0; r < GATHER_MAX_WORLD; ++r) f.flags[r] = r < g.world ? g.flags[r] : nullptr;
-    gather_signal_kernel<<<1, 32, 0, g.copy>>>(f, g.world, g.rank, g.epoch);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(g.done, g.copy));
-    CUDA_TRY(cudaStreamWaitEvent(st, g.done, 0));
+    if (!g.signalled) {
+        GatherFlags f;
+        for (int r = 0; r < GATHER_MAX_WORLD; ++r) f.flags[r] = r < g.world ? g.flags[r] : nullptr;
+        gather_signal_kernel<<<1, 32, 0, g.copy>>>(f, g.world, g.rank, g.epoch);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(g.pushed, g.copy));
+        CUDA_TRY(cudaStreamWaitEvent(st, g.pushed, 0));
+        ++plan->launches;
+    }
+    g.signalled = false;
     gather_wait_kernel<<<1, 32, 0, st>>>(g.flags[g.rank], g.world, g.rank, g.epoch, g.timeout, g.limit_ns);
     CUDA_TRY(cudaGetLastError());
-    plan->launches += 2;
+    ++plan->launches;
     return ELISA_OK;
+}
+
+// start of a gathered call: its sequence number
+static void gather_begin(ElisaPlan* plan) {
+    ++plan->gather.epoch;
+    plan->gather.signalled = false;
+    plan->gather.pend_chunks = 0;
 }
 
 static int run_all(ElisaPlan* plan, const double* theta, const double* on, const double* off, int64_t n,
@@ -2989,6 +3015,8 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
         // every spectrum takes the one-kernel path: spectra sharing a translation unit (a joint fit of like
         // detectors) are ONE launch; nothing else runs (no envelopes, no workspace, no guard)
         int rc = ELISA_OK;
+        // peer gather: the kernel stores into the peers' arrays itself and its last CTA raises the flags
+        const bool fuse = gather_on(plan) && plan->gather.world <= TINY_MAX_PEERS && plan->gather.done != nullptr;
         for (int64_t i0 = 0; i0 < n && rc == ELISA_OK; i0 += plan->chunk) {
             const int nc = (int)std::min<int64_t>(plan->chunk, n - i0);
             for (int s0 = 0; s0 < plan->S && rc == ELISA_OK;) {
@@ -2996,11 +3024,13 @@ static int run_all(ElisaPlan* plan, const double* theta, const double* on, const
                 while (s1 < plan->S && plan->spec[s1].jit == plan->spec[s0].jit) ++s1;
                 rc = launch_tiny(plan, s0, s1 - s0, theta + i0 * plan->P, on ? on + i0 * plan->sum_C : nullptr,
                                  off ? off + i0 * plan->sum_C : nullptr, nc, loglike + i0 * plan->S,
-                                 grad ? grad + i0 * plan->S * plan->P : nullptr, st);
+                                 grad ? grad + i0 * plan->S * plan->P : nullptr, st, i0, fuse, i0 + nc >= n && s1 >= plan->S);
                 s0 = s1;
             }
-            if (rc == ELISA_OK && gather_on(plan)) rc = gather_note(plan, i0, i0 + nc, i0 + nc >= n, loglike, grad, st);
+            if (rc == ELISA_OK && gather_on(plan) && !fuse)
+                rc = gather_note(plan, i0, i0 + nc, i0 + nc >= n, loglike, grad, st);
         }
+        if (rc == ELISA_OK && fuse) plan->gather.signalled = true;
         if (dev != plan->device) cudaSetDevice(dev);
         return rc;
     }
@@ -3407,7 +3437,9 @@ int elisa_b200_plan_set_gather(ElisaPlan* plan, int32_t world, int32_t rank, voi
     if (g.copy == nullptr) {
         CUDA_TRY(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&g.pushed, cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc((void**)&g.done, sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(g.done, 0, sizeof(unsigned int)));
         CUDA_TRY(cudaHostAlloc((void**)&g.timeout, sizeof(int32_t), cudaHostAllocMapped));
         *g.timeout = 0;
         if (const char* env = getenv("ELISA_B200_GATHER_EVERY")) g.every = std::max(1, atoi(env));
@@ -3473,7 +3505,8 @@ void elisa_b200_plan_destroy(ElisaPlan* plan) {
     if (plan->stream) cudaStreamDestroy(plan->stream);
     if (plan->gather.copy) cudaStreamDestroy(plan->gather.copy);
     if (plan->gather.ready) cudaEventDestroy(plan->gather.ready);
-    if (plan->gather.done) cudaEventDestroy(plan->gather.done);
+    if (plan->gather.pushed) cudaEventDestroy(plan->gather.pushed);
+    if (plan->gather.done) cudaFree(plan->gather.done);
     if (plan->gather.timeout) cudaFreeHost(plan->gather.timeout);
     cudaSetDevice(dev);
     delete plan;
@@ -3772,6 +3805,7 @@ int elisa_b200_loglike_dev(ElisaPlan* plan, const double* theta, const double* c
                            int64_t n, double* loglike, void* cuda_stream) {
     std::unique_lock<std::mutex> lock;
     if (plan != nullptr) lock = std::unique_lock<std::mutex>(plan->mu);
+    if (plan != nullptr && gather_on(plan)) gather_begin(plan);
     int rc = run_small(plan, theta, counts_on, counts_off, n, loglike, nullptr, (cudaStream_t)cuda_stream);
     if (rc == ELISA_OK && plan != nullptr && gather_on(plan)) rc = gather_finish(plan, (cudaStream_t)cuda_stream);
     return rc;
@@ -3783,6 +3817,7 @@ int elisa_b200_loglike_grad_dev(ElisaPlan* plan, const double* theta, const doub
     if (grad == nullptr) return fail(ELISA_ERR_INVALID, "grad is null");
     std::unique_lock<std::mutex> lock;
     if (plan != nullptr) lock = std::unique_lock<std::mutex>(plan->mu);
+    if (plan != nullptr && gather_on(plan)) gather_begin(plan);
     int rc = run_small(plan, theta, counts_on, counts_off, n, loglike, grad, (cudaStream_t)cuda_stream);
     if (rc == ELISA_OK && plan != nullptr && gather_on(plan)) rc = gather_finish(plan, (cudaStream_t)cuda_stream);
     return rc;
@@ -3892,6 +3927,7 @@ int elisa_b200_loglike_grad_guarded_dev(ElisaPlan* plan, const double* theta, co
     CUDA_TRY(cudaGetDevice(&prev));
     CUDA_TRY(cudaSetDevice(plan->device));
     const int64_t before = plan->fallback_rows;
+    if (gather_on(plan)) gather_begin(plan);
     int rc = run_guarded(
         plan, n, st, [&]() { return run_small(plan, theta, counts_on, counts_off, n, loglike, grad, st); },
         [&](const std::vector<int32_t>& rows) {

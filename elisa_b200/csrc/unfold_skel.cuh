@@ -439,6 +439,7 @@ struct TinyArgs {      // per spectrum, fixed at plan creation (an array of thes
     ChanArrays ch;
     int64_t counts_off;  // column of this spectrum in the per-row counts arrays
 };
+constexpr int TINY_MAX_PEERS = 8;
 struct TinyCall {      // per launch: spectra [s0, s0 + gridDim.y) of the plan, one CTA per (row, spectrum)
     const TinyArgs* spec;  // the plan's array, indexed by spectrum
     int32_t s0, S, P, n_valid;
@@ -449,6 +450,15 @@ struct TinyCall {      // per launch: spectra [s0, s0 + gridDim.y) of the plan, 
     double* loglike;   // [n, S]
     double* grad;      // [n, S, P] or nullptr (value only)
     long long* clk;    // nullptr, or 8 slots: thread 0 of CTA (0, 0) leaves clock64() at the phase boundaries (ELISA_B200_TINY_CLOCKS)
+    // peer gather fused into the kernel (elisa_b200_plan_set_gather): every result is also stored into the other
+    // ranks' full arrays over NVLink (peer-mapped CUDA IPC memory), and the LAST CTA of the call's last launch
+    // raises this rank's flag at every peer -- evaluation and all-gather are one kernel
+    int32_t world, rank;                  // world <= 1: no peers
+    double* peer_ll[TINY_MAX_PEERS];      // rank r's full loglike array at this launch's first row
+    double* peer_grad[TINY_MAX_PEERS];    // ... gradient array (nullptr: not gathered)
+    long long* peer_flags[TINY_MAX_PEERS];
+    unsigned int* done;                   // CTAs of this launch that have stored their results (device counter, self-resetting)
+    long long epoch;                      // sequence number to raise at the peers; 0: not the last launch of the call
 };
 
 // Launch shape: the generated translation unit may override the three numbers (the host reads the same ones from
@@ -653,10 +663,37 @@ __device__ __forceinline__ void tiny_eval(const TinyCall& k) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < (CB < TINY_THREADS ? CB : TINY_THREADS) / 32; ++w) s += red[w * (1 + NP) + tid];
+        const size_t i_ll = (size_t)row * k.S + spec, i_g = ((size_t)row * k.S + spec) * k.P + tid - 1;
         if (tid == 0)
-            k.loglike[(size_t)row * k.S + spec] = s;
+            k.loglike[i_ll] = s;
         else if (tid - 1 < k.P)
-            k.grad[((size_t)row * k.S + spec) * k.P + tid - 1] = s;
+            k.grad[i_g] = s;
+        if (k.world > 1) {
+#pragma unroll 1
+            for (int r = 0; r < k.world; ++r) {
+                if (tid == 0) {
+                    if (k.peer_ll[r] + i_ll != k.loglike + i_ll) k.peer_ll[r][i_ll] = s;
+                } else if (tid - 1 < k.P && k.peer_grad[r] != nullptr) {
+                    if (k.peer_grad[r] + i_g != k.grad + i_g) k.peer_grad[r][i_g] = s;
+                }
+            }
+        }
+    }
+    if (k.world > 1 && k.epoch != 0) {
+        // results of this CTA are on their way to the peers; the last CTA to get here raises the flags behind them
+        __shared__ bool last;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int total = gridDim.x * gridDim.y;
+            last = atomicAdd(k.done, 1u) == total - 1;
+            if (last) *k.done = 0u;
+        }
+        __syncthreads();
+        if (last && tid < k.world && tid != k.rank) {
+            __threadfence_system();
+            *reinterpret_cast<volatile long long*>(k.peer_flags[tid] + k.rank) = k.epoch;
+        }
     }
     TINY_CLK(6);
 #undef TINY_CLK

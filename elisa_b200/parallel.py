@@ -150,30 +150,32 @@ class PeerGather:
             g = torch.as_tensor(_DeviceArray(self._own[2 + 2 * k], (self.n_total, S, P)), device=dev)
             self._views.append((ll, g))
         self._next = 0
-        self._C = C
+        ptrs = lambda index: (C.c_void_p * self.world)(*[self._maps[r][index] for r in range(self.world)])
+        self._flag_ptrs = ptrs(0)
+        self._set_ptrs = [(ptrs(1 + 2 * k), ptrs(2 + 2 * k)) for k in range(self.sets)]
+        self._set_gather = lib.elisa_b200_plan_set_gather
         dist.barrier(group=group)  # every rank has mapped every array before anyone pushes
-
-    def _ptr_array(self, index):
-        C = self._C
-        return (C.c_void_p * self.world)(*[self._maps[r][index] for r in range(self.world)])
 
     def begin(self):
         """Set the plan's gather to the next set of arrays; returns (ll_full, grad_full, lo, hi): the full arrays
         of this rank and its block of rows -- evaluate with ``out=(ll_full[lo:hi], grad_full[lo:hi])``."""
-        from . import _lib
-
         k = self._next
         self._next = (k + 1) % self.sets
         lo, hi = self.bounds[self.rank]
-        _lib.check(self._lib.elisa_b200_plan_set_gather(self.lk._h, self.world, self.rank, self._ptr_array(1 + 2 * k),
-                                                        self._ptr_array(2 + 2 * k), self._ptr_array(0), lo))
+        rc = self._set_gather(self.lk._h, self.world, self.rank, self._set_ptrs[k][0], self._set_ptrs[k][1], self._flag_ptrs, lo)
+        if rc:
+            from . import _lib
+
+            _lib.check(rc)
         ll, g = self._views[k]
         return ll, g, lo, hi
 
     def end(self):
-        from . import _lib
+        rc = self._set_gather(self.lk._h, 0, 0, None, None, None, 0)
+        if rc:
+            from . import _lib
 
-        _lib.check(self._lib.elisa_b200_plan_set_gather(self.lk._h, 0, 0, None, None, None, 0))
+            _lib.check(rc)
 
     def close(self):
         """Unmap the peers' arrays and free this rank's (collective: the peers must have stopped pushing)."""
