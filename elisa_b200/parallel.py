@@ -123,26 +123,56 @@ class PeerGather:
         S, P = likelihood._S, likelihood._P
         self.bounds = shard_bounds(self.n_total, self.world)
         sizes = [self.world * 8] + [self.n_total * S * 8, self.n_total * S * P * 8] * self.sets  # flags, (ll, grad) per set
-        self._own, handles = [], []
-        with torch.cuda.device(likelihood.device):
-            for b in sizes:
-                ptr, h = C.c_void_p(), C.create_string_buffer(64)
-                _lib.check(lib.elisa_b200_peer_alloc(max(int(b), 8), C.byref(ptr), h))
-                self._own.append(ptr.value)
-                handles.append(h.raw)
+        # Setting up is collective and must fail on EVERY rank or on none (a rank that raised while the others wait in
+        # a collective would hang the job): errors are collected, exchanged, and raised together.
+        self._own, handles, self._maps, err = [], [], None, None
+        import contextlib
+
+        stack = contextlib.ExitStack()
+        try:
+            stack.enter_context(torch.cuda.device(likelihood.device))
+        except Exception as exc:
+            err = f'rank {self.rank}: {exc}'
+        with stack:
+            try:
+                if err is not None:
+                    raise RuntimeError(err.split(': ', 1)[1])
+                for b in sizes:
+                    ptr, h = C.c_void_p(), C.create_string_buffer(64)
+                    _lib.check(lib.elisa_b200_peer_alloc(max(int(b), 8), C.byref(ptr), h))
+                    self._own.append(ptr.value)
+                    handles.append(h.raw)
+            except Exception as exc:
+                err = f'rank {self.rank}: {exc}'
             everyone = [None] * self.world
-            dist.all_gather_object(everyone, handles, group=group)
-            self._maps = []  # [rank][array] device pointers as mapped here
-            for r in range(self.world):
-                if r == self.rank:
-                    self._maps.append(list(self._own))
-                    continue
-                row = []
-                for h in everyone[r]:
-                    ptr = C.c_void_p()
-                    _lib.check(lib.elisa_b200_peer_open(h, C.byref(ptr)))
-                    row.append(ptr.value)
-                self._maps.append(row)
+            dist.all_gather_object(everyone, None if err else handles, group=group)
+            maps = []  # [rank][array] device pointers as mapped here
+            if err is None and all(h is not None for h in everyone):
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            maps.append(list(self._own))
+                            continue
+                        row = []
+                        maps.append(row)
+                        for h in everyone[r]:
+                            ptr = C.c_void_p()
+                            _lib.check(lib.elisa_b200_peer_open(h, C.byref(ptr)))
+                            row.append(ptr.value)
+                except Exception as exc:
+                    err = f'rank {self.rank}: {exc}'
+            errors = [None] * self.world
+            dist.all_gather_object(errors, err, group=group)  # also: every rank has mapped every array before anyone pushes
+            if any(e is not None for e in errors) or any(h is None for h in everyone):
+                for r, row in enumerate(maps):
+                    if r != self.rank:
+                        for p in row:
+                            lib.elisa_b200_peer_close(p)
+                for p in self._own:
+                    lib.elisa_b200_peer_free(p)
+                self._own = []
+                raise RuntimeError('peer gather could not be set up: ' + '; '.join(e for e in errors if e))
+            self._maps = maps
         dev = f'cuda:{likelihood.device}'
         self._views = []
         for k in range(self.sets):
@@ -154,7 +184,6 @@ class PeerGather:
         self._flag_ptrs = ptrs(0)
         self._set_ptrs = [(ptrs(1 + 2 * k), ptrs(2 + 2 * k)) for k in range(self.sets)]
         self._set_gather = lib.elisa_b200_plan_set_gather
-        dist.barrier(group=group)  # every rank has mapped every array before anyone pushes
 
     def begin(self):
         """Set the plan's gather to the next set of arrays; returns (ll_full, grad_full, lo, hi): the full arrays

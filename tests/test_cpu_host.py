@@ -229,6 +229,48 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
+def _peer_setup_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from elisa_b200 import _lib
+    from elisa_b200.parallel import PeerGather
+
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+
+    class Fake:  # the attributes PeerGather reads of a Likelihood
+        _lib, _S, _P, device, _h = _lib.load(), 1, 3, 0, None
+
+    try:
+        PeerGather(Fake(), 10)
+        out = 'no error'
+    except RuntimeError as exc:
+        out = str(exc)
+    dist.barrier()  # the ranks are still in step after the failure
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_peer_gather_setup_fails_on_every_rank_together():
+    """Without a GPU the CUDA-IPC allocation fails: every rank must raise the same RuntimeError (naming the ranks
+    that failed) and stay in step -- a rank that raised alone would leave the others in a collective for ever."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    if torch.cuda.is_available():
+        pytest.skip('needs a machine WITHOUT a GPU: the allocation has to fail')
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1] and 'peer gather could not be set up' in res[0][1] and 'rank 0' in res[0][1] and 'rank 1' in res[0][1], res
+
+
 @pytest.mark.parametrize('n,world', [(7, 2), (64, 2), (7, 3)])
 def test_sharded_map_gloo(n, world):
     """world 2: even and uneven blocks; world 3 with 7 rows: blocks of 3, 2, 2 -- the in-place
@@ -265,3 +307,14 @@ def test_fastmath_against_libm(tmp_path):
     res = subprocess.run([str(exe), '2000000'], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     assert 'exp(-800)=0 exp(800)=inf exp(nan)=nan log(0)=-inf log(-1)=-nan log(inf)=inf' in res.stdout
+
+
+def test_peer_gather_entry_points_reject_bad_arguments(lib):
+    """No GPU here: the argument checks of the peer-gather entry points (include/elisa_b200.h) come before any CUDA call."""
+    ptr, h = C.c_void_p(), C.create_string_buffer(64)
+    assert lib.elisa_b200_peer_alloc(0, C.byref(ptr), h) == -1
+    assert lib.elisa_b200_peer_alloc(64, None, h) == -1
+    assert lib.elisa_b200_peer_open(None, C.byref(ptr)) == -1
+    assert lib.elisa_b200_peer_close(None) == 0 and lib.elisa_b200_peer_free(None) == 0
+    assert lib.elisa_b200_plan_set_gather(None, 2, 0, None, None, None, 0) == -1
+    assert b'null plan' in lib.elisa_b200_last_error()
