@@ -1844,6 +1844,157 @@ static std::string generate_edge_model(const ModelDev& m, int P) {
     return s;
 }
 
+// Edge-wise contraction for a TREE of sums and products (unfold_contract_tree, csrc/unfold_skel.cuh): every leaf an
+// additive trapezoid continuum, a power law, a multiplicative trapezoid continuum (incl. the table absorption) or a
+// Constant; no Simpson's rule, no flux normalisation, no free shift.  Empty string: does not apply.
+static std::string generate_tree_model(const ModelDev& m, int P) {
+    if (const char* env = getenv("ELISA_B200_CONTRACT"))
+        if (strcmp(env, "generic") == 0) return std::string();
+    if (m.n_norms != 0 || m.n_leaf > 8) return std::string();
+    auto str = [](int v) { return std::to_string(v); };
+    enum { T_ADD = 0, T_DIFF = 1, T_MUL = 2 };
+    std::vector<int> rule(m.n_leaf);
+    int n_acc = 0;
+    bool any_mul_op = false;
+    for (int o = 0; o < m.n_ops; ++o) {
+        if (m.ops[o] >= 0) continue;
+        if (m.ops[o] == ELISA_OP_MUL)
+            any_mul_op = true;
+        else if (m.ops[o] != ELISA_OP_ADD)
+            return std::string();
+    }
+    if (!any_mul_op) return std::string();  // plain sums have their own, leaner form (generate_edge_model)
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        if (L.n_shift > 0) return std::string();
+        if (L.kind == ELISA_COMP_POWERLAW) {
+            rule[i] = T_DIFF;
+        } else if (comp_is_additive(L.kind)) {
+            if (L.kind == ELISA_COMP_BROKENPL || L.kind == ELISA_COMP_LORENTZ || L.kind == ELISA_COMP_PLENFLUX ||
+                L.kind == ELISA_COMP_PLPHFLUX || L.method != ELISA_METHOD_TRAPZ)
+                return std::string();
+            rule[i] = T_ADD;
+        } else if (L.kind == ELISA_COMP_CONSTANT) {
+            rule[i] = T_MUL;
+        } else {
+            if (L.kind == ELISA_COMP_PLABS || L.method != ELISA_METHOD_TRAPZ) return std::string();
+            rule[i] = T_MUL;
+        }
+        n_acc += L.np;
+    }
+    if (n_acc > 12) return std::string();  // accumulators and basis values live in registers
+    std::string s = "struct ModelT {\n  static constexpr int NPAR = " + str(P) + ", NLEAF = " + str(m.n_leaf) + ";\n  static constexpr int O0 = 0;\n";
+    for (int i = 0; i < m.n_leaf; ++i)
+        s += "  using L" + str(i) + " = EdgeLeaf<" + str(m.leaf[i].kind) + ">;\n  static constexpr int O" + str(i + 1) + " = O" + str(i) +
+             " + L" + str(i) + "::NB;\n";
+    s += "  static constexpr int NACC = O" + str(m.n_leaf) + ";\n  struct Pre {\n";
+    for (int i = 0; i < m.n_leaf; ++i) s += "    L" + str(i) + "::Pre l" + str(i) + ";\n";
+    s += "  };\n  __device__ __forceinline__ static void pre(const double* th, Pre& s) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        s += "    { const double val[" + str(L.np) + "] = {";
+        for (int q = 0; q < L.np; ++q) s += (q ? ", " : "") + (L.src[q] >= 0 ? "th[" + str(L.src[q]) + "]" : hexd(L.cst[q]));
+        s += "}; const double aux[2] = {" + hexd(L.aux[0]) + ", " + hexd(L.aux[1]) + "}; L" + str(i) + "::pre(val, aux, s.l" + str(i) + "); }\n";
+    }
+    // edge values and tangent bases; a table leaf takes sigma(E) of its own table in the ln E slot
+    s += "  }\n  __device__ __forceinline__ static void edge(const Pre& s, const GridView& gv, int ec, double E, double lnE, double* v, double* b) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        const std::string second = L.kind == ELISA_COMP_PHOTONABS ? "gv.tab[" + str(2 * i) + "][ec]"
+                                                                  : (L.lgs != 0.0 ? "lnE + " + hexd(L.lgs) : std::string("lnE"));
+        s += "    L" + str(i) + "::edge(s.l" + str(i) + ", " + (L.gs != 1.0 ? hexd(L.gs) + " * E" : std::string("E")) + ", " + second +
+             ", v[" + str(i) + "], b + O" + str(i) + ");\n";
+    }
+    // scale of a leaf's bin value: out_scale (x grid_scale for the bin width of an additive trapezoid leaf)
+    std::vector<double> f(m.n_leaf);
+    for (int i = 0; i < m.n_leaf; ++i) f[i] = rule[i] == T_ADD ? m.leaf[i].os * m.leaf[i].gs : (rule[i] == T_DIFF ? m.leaf[i].os : 1.0);
+    s += "  }\n  __device__ __forceinline__ static void bins(const double* v, double hd, double* binv) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const std::string id = str(i), nx = "__shfl_down_sync(0xffffffffu, v[" + id + "], 1)";
+        const std::string fs = f[i] != 1.0 ? hexd(f[i]) + " * " : std::string();
+        if (rule[i] == T_ADD)
+            s += "    binv[" + id + "] = " + fs + "(hd * (v[" + id + "] + " + nx + "));\n";
+        else if (rule[i] == T_DIFF)
+            s += "    binv[" + id + "] = " + fs + "(" + nx + " - v[" + id + "]);\n";
+        else
+            s += "    binv[" + id + "] = 0.5 * (v[" + id + "] + " + nx + ");\n";
+    }
+    // the tree forward (values n_k) ...
+    s += "  }\n  __device__ __forceinline__ static void tree(const double* binv, double* adj, double& u) {\n";
+    struct Node { bool leaf; int idx; int a, b, op; };  // internal: children a, b (node ids)
+    std::vector<Node> nodes;
+    std::vector<int> stack;
+    for (int o = 0; o < m.n_ops; ++o) {
+        const int op = m.ops[o];
+        if (op >= 0) {
+            nodes.push_back({true, op, -1, -1, 0});
+            stack.push_back((int)nodes.size() - 1);
+        } else {
+            if (stack.size() < 2) return std::string();
+            const int rb = stack.back(); stack.pop_back();
+            const int ra = stack.back(); stack.pop_back();
+            nodes.push_back({false, -1, ra, rb, op});
+            stack.push_back((int)nodes.size() - 1);
+        }
+    }
+    if (stack.size() != 1) return std::string();
+    auto val = [&](int n) { return nodes[n].leaf ? "binv[" + str(nodes[n].idx) + "]" : "n" + str(n); };
+    for (int n = 0; n < (int)nodes.size(); ++n)
+        if (!nodes[n].leaf)
+            s += "    const double n" + str(n) + " = " + val(nodes[n].a) + (nodes[n].op == ELISA_OP_ADD ? " + " : " * ") + val(nodes[n].b) + ";\n";
+    const int root = stack.back();
+    s += "    u = " + val(root) + ";\n";
+    for (int i = 0; i < m.n_leaf; ++i) s += "    adj[" + str(i) + "] = 0.0;\n";
+    // ... and in reverse: a node's adjoint goes to its children (times the sibling's value under a product)
+    std::vector<std::string> bar(nodes.size());
+    bar[root] = "1.0";
+    for (int n = (int)nodes.size() - 1; n >= 0; --n) {
+        if (bar[n].empty()) return std::string();  // unreachable node: not a tree
+        if (nodes[n].leaf) {
+            s += "    adj[" + str(nodes[n].idx) + "] += " + bar[n] + ";\n";
+            continue;
+        }
+        const int ca = nodes[n].a, cb = nodes[n].b;
+        if (nodes[n].op == ELISA_OP_ADD) {
+            bar[ca] = bar[n];
+            bar[cb] = bar[n];
+        } else {
+            s += "    const double a" + str(ca) + " = " + (bar[n] == "1.0" ? std::string() : bar[n] + " * ") + val(cb) + ";\n";
+            s += "    const double a" + str(cb) + " = " + (bar[n] == "1.0" ? std::string() : bar[n] + " * ") + val(ca) + ";\n";
+            bar[ca] = "a" + str(ca);
+            bar[cb] = "a" + str(cb);
+        }
+    }
+    // per leaf: adjoint of the bin -> weights of its two edges -> accumulators of its tangent basis
+    s += "  }\n  __device__ __forceinline__ static void accumulate(const double* adj, double gg, double hd, int lane, const double* b, double* acc) {\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const std::string id = str(i);
+        const std::string fs = f[i] != 1.0 ? hexd(f[i]) + " * " : std::string();
+        std::string t;  // gg = 0 (no bin, or a clipped one) must give weight zero whatever the adjoint overflowed to
+        if (rule[i] == T_ADD)
+            t = "gg != 0.0 ? " + fs + "(gg * adj[" + id + "] * hd) : 0.0";
+        else if (rule[i] == T_DIFF)
+            t = "gg != 0.0 ? " + fs + "(gg * adj[" + id + "]) : 0.0";
+        else
+            t = "gg != 0.0 ? 0.5 * (gg * adj[" + id + "]) : 0.0";
+        s += "    { const double w = " + std::string(rule[i] == T_DIFF ? "edge_weight_diff" : "edge_weight_sum") + "(" + t + ", lane);\n"
+             "      if (w != 0.0) {\n"
+             "#pragma unroll\n"
+             "        for (int q = O" + id + "; q < O" + str(i + 1) + "; ++q) acc[q] = fma(w, b[q], acc[q]);\n      } }\n";
+    }
+    s += "  }\n  __device__ __forceinline__ static void finish(const Pre& s, const double* S, double* grad) {\n"
+         "    for (int j = 0; j < NPAR; ++j) grad[j] = 0.0;\n";
+    for (int i = 0; i < m.n_leaf; ++i) {
+        const LeafDev& L = m.leaf[i];
+        s += "    { double d[" + str(L.np) + "]; L" + str(i) + "::finish(s.l" + str(i) + ", S + O" + str(i) + ", d);";
+        for (int q = 0; q < L.np; ++q)
+            if (L.src[q] >= 0) s += " grad[" + str(L.src[q]) + "] += d[" + str(q) + "];";
+        s += " }\n";
+    }
+    s += "  }\n};\n";
+    return s;
+}
+
 // tiny_stat >= 0: also instantiate the one-kernel small-batch evaluation (tiny_eval) for that statistic
 static std::string generate_unfold_source(const ModelDev& m, int P, int ks, int tiny_stat = -1) {
     std::string s;
@@ -1868,10 +2019,15 @@ static std::string generate_unfold_source(const ModelDev& m, int P, int ks, int 
     s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_grad(const UnfoldCore a) { unfold_generic<ModelG, Dual<" +
          std::to_string(P) + ">, " + k + ">(a); }\n";
     const std::string edge_model = generate_edge_model(m, P);
+    const std::string tree_model = edge_model.empty() ? generate_tree_model(m, P) : std::string();
     s += edge_model;
+    s += tree_model;
     if (!edge_model.empty())
         s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
              "unfold_contract_edges<ModelE>(a); }\n";
+    else if (!tree_model.empty())
+        s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
+             "unfold_contract_tree<ModelT>(a); }\n";
     else
         s += "extern \"C\" __global__ void __launch_bounds__(128, UNFOLD_MIN_BLOCKS) unfold_contract(const UnfoldCore a) { "
              "unfold_contract_generic<ModelG, Dual<" + std::to_string(P) + ">>(a); }\n";

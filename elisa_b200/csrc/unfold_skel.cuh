@@ -316,7 +316,8 @@ struct EdgeLeaf {
     static constexpr bool CLOSED = HasBasis<C>::value;
     static constexpr bool DIFF = IsEdgeDiff<C>::value;
     static constexpr int NP = C::NP, NC = C::NC, NB = HasBasis<C>::NB;
-    static_assert(CLOSED || (C::RULE == RULE_CONTINUUM_ADD && C::NG == 1), "edge contraction: unsupported component");
+    static_assert(CLOSED || ((C::RULE == RULE_CONTINUUM_ADD || C::RULE == RULE_CONTINUUM_MUL) && C::NG == 1),
+                  "edge contraction: unsupported component");
     using T = typename Cond<CLOSED, double, Dual<NP>>::type;
     struct Pre {
         T p[NP];
@@ -348,6 +349,23 @@ struct EdgeLeaf {
             for (int q = 0; q < NP; ++q) d[q] = S[q];
         }
     }
+};
+
+// Constant (models/mul.py:54-56): its bin value is the parameter itself -- as an edge value with the trapezoid
+// rule of a multiplicative leaf, (f + f) / 2 = f exactly, tangent 1
+template <>
+struct EdgeLeaf<ELISA_COMP_CONSTANT> {
+    static constexpr bool CLOSED = true, DIFF = false;
+    static constexpr int NP = 1, NC = 0, NB = 1;
+    struct Pre {
+        double f;
+    };
+    __device__ __forceinline__ static void pre(const double* val, const double*, Pre& s) { s.f = val[0]; }
+    __device__ __forceinline__ static void edge(const Pre& s, double, double, double& v, double* b) {
+        v = s.f;
+        b[0] = 1.0;
+    }
+    __device__ __forceinline__ static void finish(const Pre&, const double* S, double* d) { d[0] = S[0]; }
 };
 
 // Model (generated, ModelE): Pre, pre(theta, Pre&), NACC accumulators of which bit i of DMASK marks the
@@ -418,6 +436,71 @@ __device__ __forceinline__ void unfold_contract_edges(const UnfoldCore& a) {
 #pragma unroll
         for (int j = 0; j < Model::NPAR; ++j) out[j] = grad[j];
     }
+}
+
+// The same for an expression TREE of sums and products (an absorbed continuum, PhAbs * (PowerLaw + Blackbody): what
+// people fit).  The bin value of every leaf is linear in two neighbouring edge values -- additive trapezoid leaves,
+// the power law's antiderivative, and multiplicative trapezoid leaves, (m(E_e) + m(E_e+1)) / 2 -- and the `+` / `*`
+// tree acts on bin values, so  grad_j = sum_e G_e du_e/dtheta_j  goes through the tree in REVERSE per bin (the adjoint
+// of a leaf's bin value is G_e times the product of the factors it is multiplied with) and then, leaf by leaf, onto
+// the edges exactly as above, with the leaf's own weights.  Model (generated, ModelT): Pre, pre(theta, Pre&),
+// NLEAF, NACC, edge(pre, gv, ec, E, lnE, v[NLEAF], b[NACC]) -- edge value and tangent basis of every leaf;
+// bins(v, hd, binv) -- the leaves' bin values (shuffles: every lane calls it); tree(binv, adj, u) -- the model's bin
+// value u and the adjoints of the leaves' bin values for a unit adjoint of u; accumulate(adj, gg, hd, lane, b, acc);
+// finish(pre, S, grad[NPAR]).
+template <class Model>
+__device__ __forceinline__ void unfold_contract_tree(const UnfoldCore& a) {
+    constexpr int NA = Model::NACC, NL = Model::NLEAF;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int row = (int)((int64_t)blockIdx.x * UNFOLD_WARPS + wib);
+    if (row >= a.n_valid) return;
+    const int E = a.gv.E;
+    typename Model::Pre pre;
+    Model::pre(a.theta + (size_t)row * a.P, pre);
+    const double* g_row = a.G + (size_t)row * a.ldg;
+    double nE = a.gv.egrid[min(lane, E)], nl = a.gv.lngrid[min(lane, E)];
+    double ng = (lane < 31 && lane < E) ? g_row[lane] : 0.0;
+    double acc[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+    for (int e0 = 0; e0 < E; e0 += 31) {
+        const int e = e0 + lane;
+        const double pE = nE, pl = nl, g = ng;
+        if (e0 + 31 < E) {  // the next pass's edge and weight, loaded under this pass's arithmetic
+            const int ec = min(e + 31, E);
+            nE = a.gv.egrid[ec];
+            nl = a.gv.lngrid[ec];
+            ng = (lane < 31 && e + 31 < E) ? g_row[e + 31] : 0.0;
+        }
+        double v[NL], b[NA], binv[NL], adj[NL], u;
+        Model::edge(pre, a.gv, min(e, E), pE, pl, v, b);
+        const double hd = 0.5 * (__shfl_down_sync(0xffffffffu, pE, 1) - pE);
+        Model::bins(v, hd, binv);
+        Model::tree(binv, adj, u);
+        // as in unfold_contract_edges: no bin in lane 31 and past the grid (g = 0), a clipped bin passes no
+        // derivative, zero weights skip the accumulation, a NaN in G stays NaN
+        const bool pass = !(a.clip && !(u >= 1e-300 && u <= 1e300));
+        const double gg = g * (pass ? 1.0 : 0.0);
+        Model::accumulate(adj, gg, hd, lane, b, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = warp_sum(acc[i]);
+    double grad[Model::NPAR];
+    Model::finish(pre, acc, grad);
+    double* out = a.grad_out + (size_t)row * a.grad_stride;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < Model::NPAR; ++j) out[j] = grad[j];
+    }
+}
+// weight of an edge from the per-bin adjoint t of the lane's bin (bin e lies between the edges e and e + 1)
+__device__ __forceinline__ double edge_weight_sum(double t, int lane) {   // trapezoid: both neighbouring bins
+    const double up = __shfl_up_sync(0xffffffffu, t, 1);
+    return lane ? t + up : t;
+}
+__device__ __forceinline__ double edge_weight_diff(double t, int lane) {  // difference of edge values: F(E_e+1) - F(E_e)
+    const double up = __shfl_up_sync(0xffffffffu, t, 1);
+    return lane ? up - t : -t;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -51,10 +51,79 @@ def test_edge_model_is_generated_only_where_it_applies(lib):
 
     for name, m in _cases().items():
         assert 'unfold_contract_edges<ModelE>' in src(m), name
-    for m in (M.ExpAbs() * M.PowerLaw(), M.CutoffPL(method='simpson') + M.Blackbody(), M.BrokenPL() + M.CutoffPL(),
-              M.PhFlux(1.0, 10.0, ngrid=100)(M.CutoffPL(K=1.0)), M.Constant() * (M.CutoffPL() + M.Blackbody())):
+    # trees of sums and products of such leaves and multiplicative trapezoid leaves: the tree form (ModelT)
+    for name, m in _tree_cases().items():
         s = src(m)
-        assert 'ModelE' not in s and 'unfold_contract_generic<ModelG' in s, repr(m)
+        assert 'ModelE' not in s and 'unfold_contract_tree<ModelT>' in s, name
+    for m in (M.CutoffPL(method='simpson') + M.Blackbody(), M.BrokenPL() + M.CutoffPL(),
+              M.PhFlux(1.0, 10.0, ngrid=100)(M.CutoffPL(K=1.0)), M.PLAbs() * M.CutoffPL(), M.ExpAbs(method='simpson') * M.PowerLaw(),
+              M.ZAShift(z=M.UniformParameter('z', 0.5, 0.0, 3.0))(M.ExpAbs() * M.PowerLaw())):
+        s = src(m)
+        assert 'ModelE' not in s and 'ModelT' not in s and 'unfold_contract_generic<ModelG' in s, repr(m)
+
+
+def _tree_cases():
+    ea = M.ExpAbs()
+    K = M.UniformParameter('K', 2.0, 1e-3, 1e3)
+    return {
+        'expabs*pl': M.ExpAbs() * M.PowerLaw(),
+        'const*(cpl+bb)': M.Constant() * (M.CutoffPL() + M.Blackbody()),
+        # one multiplicative leaf in two terms; one K in two additive leaves
+        'leaf_in_two_terms': ea * M.PowerLaw(K=K) + ea * M.Blackbody(K=K) + M.Gauss(El=_free('El', 20.0), sigma=_free('sigma', 4.0)),
+        'two_factors': M.HighECut(Ec=_free('Ec', 8.0), Ef=_free('Ef', 30.0)) * M.Edge(Ec=_free('Ec', 3.0)) * M.CutoffPL(),
+        'dual_leaf_under_product': M.GAbs(El=_free('El', 15.0), sigma=_free('sigma', 3.0)) * M.Band(Ec=_free('Ec', 40.0)),
+        'shifted_product': M.ZAShift(z=0.4)(M.ExpFac() * (M.CutoffPL() + M.PowerLaw())) + M.ZMShift(z=1.0)(M.ExpAbs()) * M.OTTB(),
+    }
+
+
+@pytest.mark.parametrize('name', list(_tree_cases()))
+@pytest.mark.parametrize('stat', ['cstat', 'wstat'])
+def test_tree_form_matches_oracle_and_dual_contraction(lib, name, stat, monkeypatch):
+    from parity import RTOL, gpu_eval, oracle_eval, rel_err_grad, rel_err_grad_rownorm, rel_err_value
+
+    model = _tree_cases()[name]
+    d = _one_spectrum(E=97, C=40, seed=4)
+    theta = _theta_for(model, 65, 9)
+    cfg = dict(data=[d], model=[model], stat=[stat], theta=theta)
+    ll_ref, g_ref = oracle_eval(cfg)
+    out = {}
+    for mode in ('edges', 'generic'):
+        monkeypatch.setenv('ELISA_B200_CONTRACT', mode)
+        out[mode] = gpu_eval(cfg, specialise=True)
+        assert rel_err_value(out[mode][0], ll_ref) <= RTOL, (mode, name)
+        assert rel_err_grad(out[mode][1], g_ref) <= RTOL, (mode, name)
+    assert np.array_equal(out['edges'][0], out['generic'][0])
+    assert rel_err_grad_rownorm(out['edges'][1], out['generic'][1]) <= 1e-11, name
+
+
+def test_tree_form_with_table_absorption_and_clipped_bins(lib, monkeypatch):
+    """PhAbs * (PowerLaw + Blackbody) -- the table leaf reads sigma(E) of its own table on the edge -- and a product whose
+    bins underflow below 1e-300 (the clip passes no derivative; a zero weight skips the accumulation)."""
+    from parity import RTOL, gpu_eval, oracle_eval, rel_err_grad, rel_err_value
+
+    d = _one_spectrum(E=97, C=40, seed=6)
+    rng = np.random.default_rng(2)
+    te = np.geomspace(0.05, 500.0, 300)
+    tx = 1e-2 * te ** -2.5 * (1.0 + 0.3 * rng.random(300))
+    model = M.PhAbs(te, tx) * (M.PowerLaw() + M.Blackbody())
+    theta = _theta_for(model, 33, 3)
+    cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
+    ll_ref, g_ref = oracle_eval(cfg)
+    for mode in ('edges', 'generic'):
+        monkeypatch.setenv('ELISA_B200_CONTRACT', mode)
+        ll, g = gpu_eval(cfg, specialise=True)
+        assert rel_err_value(ll, ll_ref) <= RTOL and rel_err_grad(g, g_ref) <= RTOL, mode
+    model = M.ExpAbs() * M.CutoffPL() + M.Gauss(El=1.0, sigma=0.05)
+    cm = model.compile()
+    theta = np.tile(cm.params_default, (6, 1))
+    theta[:, list(cm.params_name).index('CutoffPL.Ec')] = [0.05, 0.08, 0.12, 0.2, 0.3, 15.0]
+    cfg = dict(data=[d], model=[model], stat=['cstat'], theta=theta)
+    ll_ref, g_ref = oracle_eval(cfg)
+    for mode in ('edges', 'generic'):
+        monkeypatch.setenv('ELISA_B200_CONTRACT', mode)
+        ll, g = gpu_eval(cfg, specialise=True)
+        assert rel_err_value(ll, ll_ref) <= RTOL and rel_err_grad(g, g_ref) <= RTOL, mode
+        assert np.isfinite(g).all()
 
 
 @pytest.mark.parametrize('name', list(_cases()))
