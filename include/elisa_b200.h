@@ -484,7 +484,10 @@ int elisa_b200_sample_dev(ElisaPlan* plan, int32_t spectrum, int32_t which, cons
  *   stream wait until flags[rank][r] of every peer has reached it: when the call's work on the stream is done,
  *   this rank's full arrays hold every rank's rows.  Every rank must make the same sequence of gathered calls.
  *   A rank may run ahead by one call: keep two sets of arrays and alternate them if a consumer reads the
- *   results while the next call is already running (elisa_b200/parallel.py does).                        */
+ *   results while the next call is already running (elisa_b200/parallel.py does).  The gathered calls of one plan
+ *   belong on ONE stream (their pushes share a copy stream, an event pair and, on the small-batch path, a device
+ *   counter).  A peer whose flag has not arrived after 60 s (ELISA_B200_GATHER_TIMEOUT_S) is reported by the NEXT
+ *   gathered call (ELISA_ERR_CUDA, naming the rank) -- the wait is bounded so that a lost rank cannot hang the device. */
 int elisa_b200_peer_alloc(int64_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
 int elisa_b200_peer_open(const unsigned char ipc_handle[64], void** dev_ptr);
 int elisa_b200_peer_close(void* dev_ptr);
