@@ -410,6 +410,17 @@ def side_configs(torch, dist, world, rank, local, with_oracle, peer=False):
         lk.loglike_and_grad(th)
     torch.cuda.synchronize()
     us_local = (time.perf_counter() - t0) / 300 * 1e6
+    # the same with result arrays the caller allocated once (out=): no allocation per call
+    out3 = (torch.empty((hi - lo, len(cfg['data'])), dtype=torch.float64, device=dev),
+            torch.empty((hi - lo, len(cfg['data']), lk._P), dtype=torch.float64, device=dev))
+    for _ in range(5):
+        lk.loglike_and_grad(th, out=out3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(300):
+        lk.loglike_and_grad(th, out=out3)
+    torch.cuda.synchronize()
+    us_local_out = (time.perf_counter() - t0) / 300 * 1e6
     us_gather = None
     if world > 1:
         try:
@@ -462,7 +473,7 @@ def side_configs(torch, dist, world, rank, local, with_oracle, peer=False):
         out['cfg3'] = {'what': 'Band pgstat, 4 detectors 128ch x 140E, 64 chains over %d GPU(s): one leapfrog = one value+gradient '
                                'call through the Python API (no host synchronisation)' % world,
                        'chains_per_gpu': hi - lo, 'us_per_leapfrog': float(t.item()), 'us_per_leapfrog_with_gather': us_gather,
-                       'us_per_leapfrog_in_callers_cuda_graph': us_graph,
+                       'us_per_leapfrog_in_callers_cuda_graph': us_graph, 'us_per_leapfrog_preallocated_results_rank0': us_local_out,
                        'evals_s': 64 * 4 / ((us_gather or float(t.item())) * 1e-6),
                        'engine': ('one launch for the four detectors (dual-number model + FP64 forward-mode fold + statistic + '
                                   'gradient, tiny_eval)' if all(lk.small_batch_kernel) else engine(lk)),
