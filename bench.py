@@ -795,7 +795,7 @@ def run_b200(args):
                     'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': fp64_equiv / fp64_peak if fp64_equiv and fp64_peak else None,
                     'peak_source': 'cuBLAS DGEMM 8192^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no FP64 entry)'}
     roofline.update({
-        'traffic': TRAFFIC.get('i8' if ks else 'dmma'),
+        'traffic': TRAFFIC.get('i8' if ks else 'dmma') * lk_chunk / 18944.0,  # measured per launch of 18 944 rows; linear in the rows
         'avg_launch_ms': gemm_ms / gemm_launches if gemm_launches else None,
         'flop_per_launch': flops_total / gemm_launches if gemm_launches else None,
         'share_of_step': gemm_ms / ms if ms > 0 else None,

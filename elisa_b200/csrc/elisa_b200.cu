@@ -3807,8 +3807,9 @@ int elisa_b200_plan_create(const ElisaPlanDesc* desc, ElisaPlan** out) {
         if (any) rc = upload(plan, ta, &plan->tiny_args);
     }
     if (rc == ELISA_OK) {
-        // chunk: one 128-row tile per SM by default, bounded by a 6 GiB workspace
-        int64_t chunk = desc->chunk > 0 ? desc->chunk : 148 * GEMM_BM;
+        // chunk: two 128-row tiles per SM by default (one: 2.7 % slower on the bench -- five launches and their tails per
+        // chunk; three: + 0.5 % for 8 GB, tools/chunk_probe.py), bounded by a 6 GiB workspace
+        int64_t chunk = desc->chunk > 0 ? desc->chunk : 2 * 148 * GEMM_BM;
         chunk = (chunk + GEMM_BM - 1) / GEMM_BM * GEMM_BM;
         // row partials: one per 64-column tile (DMMA) or per I8_TC-column group (sliced-integer fold)
         const int64_t pmul = any_i8 ? I8_CG : 1;
